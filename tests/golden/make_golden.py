@@ -1,0 +1,191 @@
+"""Generate golden vectors by running the UNMODIFIED reference (imported from /root/reference).
+
+Run in the authoring container only (the GPU box has no /root/reference):
+
+    python tests/golden/make_golden.py
+
+Writes tests/golden/*.npz.  Inputs are synthetic; weights come from
+`oracle.flow_oracle.synth_state_dict` (a pure function of key/shape/seed) loaded into the
+reference model with `load_state_dict(strict=True)`, so nothing but small arrays is stored.
+
+Import recipe = SURVEY.md Appendix C (stub modules for absent plotting deps, one dataclass
+__hash__ shim for Python >= 3.11; no reference code is modified or copied).
+"""
+import os
+import sys
+import types
+import profile, cProfile  # noqa: F401,E401  (import stdlib `profile` before reference/profile.py can shadow it)
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+REF = "/root/reference"
+LINK_DIR = "/tmp/tw_ref_pkg"
+os.makedirs(LINK_DIR, exist_ok=True)
+if not os.path.exists(os.path.join(LINK_DIR, "timewarp")):
+    os.symlink(REF, os.path.join(LINK_DIR, "timewarp"))
+sys.path.insert(0, LINK_DIR)
+sys.path.append(REF)
+for n in ("pymol2", "mdtraj", "matplotlib", "matplotlib.pyplot"):
+    sys.modules.setdefault(n, types.ModuleType(n))
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+import timewarp.modules.model_wrappers.flow as F  # noqa: E402
+
+F.ConditionalFlowDensityConfig.__hash__ = lambda s: id(s)
+from timewarp.model_constructor import custom_transformer_nvp_constructor  # noqa: E402
+from timewarp.model_configs import CustomAttentionTransformerNVPConfig  # noqa: E402
+from timewarp.modules.layers.custom_attention_encoder import CustomAttentionEncoderLayerConfig  # noqa: E402
+from timewarp.modules.layers.kernel_attention import compute_kernel_attention_scores  # noqa: E402
+from timewarp.utils import chirality as ref_chirality  # noqa: E402
+
+from oracle.flow_oracle import OracleConfig, synth_state_dict  # noqa: E402
+from timewarp_b200.peptides import alanine_dipeptide, tetrapeptide_2olx  # noqa: E402
+
+
+def ref_model(cfg: OracleConfig, seed: int):
+    enc = CustomAttentionEncoderLayerConfig(
+        d_model=cfg.d_model,
+        dim_feedforward=cfg.dim_feedforward,
+        dropout=0.0,
+        num_heads=len(cfg.lengthscales),
+        attention_type="kernel",
+        lengthscales=list(cfg.lengthscales),
+        normalise_kernel_values=True,
+    )
+    mc = CustomAttentionTransformerNVPConfig(
+        atom_embedding_dim=cfg.atom_embedding_dim,
+        latent_mlp_hidden_dims=list(cfg.latent_mlp_hidden_dims),
+        num_coupling_layers=cfg.num_coupling_layers,
+        num_transformer_layers=cfg.num_transformer_layers,
+        encoder_layer_config=enc,
+        position_layer_index_mod_2=cfg.position_layer_index_mod_2,
+    )
+    model = custom_transformer_nvp_constructor(mc)
+    sd = synth_state_dict(cfg, seed)
+    model.load_state_dict(sd, strict=True)
+    model.eval()
+    return model, sd
+
+
+def synth_batch(peptide, B, seed, lengths=None):
+    """x = pdb + N(0, 0.01^2), y = x + N(0, 0.02^2) nm, velocities N(0,1); ragged -> zero padded."""
+    g = torch.Generator().manual_seed(seed)
+    V = peptide.num_atoms
+    base = torch.tensor(peptide.coords_nm, dtype=torch.float32)
+    x = base[None] + 0.01 * torch.randn(B, V, 3, generator=g)
+    y = x + 0.02 * torch.randn(B, V, 3, generator=g)
+    xv = torch.randn(B, V, 3, generator=g)
+    yv = torch.randn(B, V, 3, generator=g)
+    at = torch.tensor(peptide.atom_types)[None].repeat(B, 1)
+    mask = torch.zeros(B, V, dtype=torch.bool)
+    if lengths is not None:
+        for b, n in enumerate(lengths):
+            mask[b, n:] = True
+        keep = (~mask)[:, :, None]
+        x, y, xv, yv = x * keep, y * keep, xv * keep, yv * keep
+        at = at * (~mask)
+    return at, x, xv, y, yv, mask
+
+
+EMPTY_ADJ = torch.zeros(0, 2, dtype=torch.long)
+EMPTY_EBI = torch.zeros(0, dtype=torch.long)
+
+
+def run_case(name, cfg, peptide, B, seed, lengths=None, sample_S=3, wseed=0, trace_layer0=True):
+    model, sd = ref_model(cfg, wseed)
+    at, x, xv, y, yv, mask = synth_batch(peptide, B, seed, lengths)
+    out = dict(atom_types=at.numpy(), x_coords=x.numpy(), x_velocs=xv.numpy(), y_coords=y.numpy(), y_velocs=yv.numpy(),
+               masked_elements=mask.numpy(), weight_seed=np.int64(wseed))
+    kw = dict(atom_types=at, x_coords=x, x_velocs=xv, adj_list=EMPTY_ADJ, edge_batch_idx=EMPTY_EBI, masked_elements=mask)
+    with torch.no_grad():
+        out["log_likelihood"] = model.log_likelihood(y_coords=y, y_velocs=yv, **kw).numpy()
+        out["loss"] = model(y_coords=y, y_velocs=yv, **kw).numpy()
+        # fp64 truth from the same reference code
+        m64 = __import__("copy").deepcopy(model).double()
+        kw64 = dict(atom_types=at, x_coords=x.double(), x_velocs=xv.double(), adj_list=EMPTY_ADJ,
+                    edge_batch_idx=EMPTY_EBI, masked_elements=mask)
+        out["log_likelihood_f64"] = m64.log_likelihood(y_coords=y.double(), y_velocs=yv.double(), **kw64).numpy()
+        # attention scores straight from the reference function
+        com = (x * (~mask)[:, :, None]).sum(1, keepdim=True) / (~mask).sum(1)[:, None, None]
+        ls = torch.tensor(cfg.lengthscales, dtype=torch.float32)
+        out["scores"] = compute_kernel_attention_scores(query=x - com, key=x - com, masked_elements=mask, lengthscales=ls).numpy()
+
+        # sampling, S=1 over the whole batch (exploration.py shape) -- same RNG consumption as the reference
+        torch.manual_seed(1234 + seed)
+        yc1, yv1, lp1 = model.conditional_sample_with_logp(num_samples=1, **kw)
+        torch.manual_seed(1234 + seed)
+        xc_c = x - com
+        zc1 = torch.distributions.Normal(torch.zeros_like(xc_c), torch.exp(model.coords_prior_log_scale)).rsample((1,))
+        zv1 = torch.distributions.Normal(torch.zeros_like(xv), torch.exp(model.velocs_prior_log_scale)).rsample((1,))
+        out.update(s1_z_coords=zc1.numpy(), s1_z_velocs=zv1.numpy(), s1_y_coords=yc1.numpy(), s1_y_velocs=yv1.numpy(), s1_logp=lp1.numpy())
+
+        # sampling, S proposals from one state (sample_with_model shape, B == 1)
+        kw1 = dict(atom_types=at[:1], x_coords=x[:1], x_velocs=xv[:1], adj_list=EMPTY_ADJ, edge_batch_idx=EMPTY_EBI,
+                   masked_elements=mask[:1])
+        torch.manual_seed(4321 + seed)
+        ycS, yvS, lpS = model.conditional_sample_with_logp(num_samples=sample_S, **kw1)
+        torch.manual_seed(4321 + seed)
+        zcS = torch.distributions.Normal(torch.zeros_like(x[:1]), torch.exp(model.coords_prior_log_scale)).rsample((sample_S,))
+        zvS = torch.distributions.Normal(torch.zeros_like(xv[:1]), torch.exp(model.velocs_prior_log_scale)).rsample((sample_S,))
+        out.update(sS_z_coords=zcS.numpy(), sS_z_velocs=zvS.numpy(), sS_y_coords=ycS.numpy(), sS_y_velocs=yvS.numpy(), sS_logp=lpS.numpy())
+        # MH reverse move density (evaluation_utils.py:648-657) for those proposals
+        S = sample_S
+        p_yx = model.log_likelihood(
+            atom_types=at[:1].repeat(S, 1), y_coords=x[:1].repeat(S, 1, 1), y_velocs=xv[:1].repeat(S, 1, 1),
+            x_coords=ycS.squeeze(1), x_velocs=yvS.squeeze(1), adj_list=EMPTY_ADJ, edge_batch_idx=EMPTY_EBI,
+            masked_elements=mask[:1].repeat(S, 1))
+        out["sS_p_yx"] = p_yx.numpy()
+
+        if trace_layer0:
+            layer0 = model.flow.chain[0]
+            feats = model.flow.atom_embedder(at)
+            cache = model.cache.empty_like()
+            scale, shift = layer0._get_scale_and_shift(
+                atom_types=at, z_coords=y - x, z_velocs=yv, x_features=feats, x_coords=x - com, x_velocs=xv,
+                adj_list=EMPTY_ADJ, edge_batch_idx=EMPTY_EBI, masked_elements=mask, logger=None, cache=cache)
+            out["layer0_scale"] = scale.numpy()
+            out["layer0_shift"] = shift.numpy()
+    path = os.path.join(HERE, f"{name}.npz")
+    np.savez_compressed(path, **out)
+    print(name, "ll", out["log_likelihood"], "f64", out["log_likelihood_f64"], "loss", out["loss"])
+    return sd
+
+
+TINY = OracleConfig(atom_embedding_dim=8, latent_mlp_hidden_dims=[24], num_coupling_layers=4, num_transformer_layers=2,
+                    d_model=16, dim_feedforward=32, lengthscales=[0.3, 1.0])
+FULL = OracleConfig()
+
+
+def chirality_case():
+    """Known answers for utils/chirality.py on the 2olx topology (hand-derived bonds)."""
+    pep = tetrapeptide_2olx()
+    adj = torch.tensor(pep.bonds)
+    at = torch.tensor(pep.atom_types)[None]
+    centers = ref_chirality.find_chirality_centers(adj, at)
+    g = torch.Generator().manual_seed(5)
+    coords = torch.tensor(pep.coords_nm, dtype=torch.float32)[None] + 0.01 * torch.randn(6, pep.num_atoms, 3, generator=g)
+    coords[1] = coords[1] * torch.tensor([1.0, 1.0, -1.0])  # mirror -> every centre flips
+    # sample 3: swap two substituents of one centre only
+    c0 = centers[0]
+    tmp = coords[3, c0[1]].clone(); coords[3, c0[1]] = coords[3, c0[2]]; coords[3, c0[2]] = tmp
+    ref_signs = ref_chirality.compute_chirality_sign(coords[:1], centers)
+    signs = ref_chirality.compute_chirality_sign(coords, centers)
+    changed = ref_chirality.check_symmetry_change(coords, centers, ref_signs)
+    np.savez_compressed(os.path.join(HERE, "chirality_2olx.npz"), bonds=pep.bonds, atom_types=at.numpy(), centers=centers.numpy(),
+                        coords=coords.numpy(), ref_signs=ref_signs.numpy(), signs=signs.numpy(), changed=changed.numpy())
+    print("chirality centers", centers.tolist(), "changed", changed.tolist())
+
+
+if __name__ == "__main__":
+    torch.set_num_threads(8)
+    ad, olx = alanine_dipeptide(), tetrapeptide_2olx()
+    run_case("tiny_ad_ragged", TINY, ad, B=3, seed=11, lengths=[22, 15, 9], sample_S=4)
+    run_case("tiny_ad", TINY, ad, B=4, seed=12, sample_S=4)
+    run_case("full_ad22", FULL, ad, B=4, seed=0, sample_S=3)
+    run_case("full_ad22_ragged", FULL, ad, B=3, seed=1, lengths=[22, 17, 12], sample_S=2)
+    run_case("full_2olx65", FULL, olx, B=2, seed=2, sample_S=2)
+    chirality_case()

@@ -1,0 +1,96 @@
+"""Pin the CPU oracle (oracle/flow_oracle.py) against golden vectors produced by the
+unmodified reference (tests/golden/make_golden.py)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import flow_oracle as fo
+
+TINY = fo.OracleConfig(atom_embedding_dim=8, latent_mlp_hidden_dims=[24], num_coupling_layers=4,
+                       num_transformer_layers=2, d_model=16, dim_feedforward=32, lengthscales=[0.3, 1.0])
+FULL = fo.OracleConfig()
+CASES = [("tiny_ad_ragged", TINY), ("tiny_ad", TINY), ("full_ad22", FULL), ("full_ad22_ragged", FULL), ("full_2olx65", FULL)]
+
+
+def load(golden_dir, name):
+    d = np.load(os.path.join(golden_dir, name + ".npz"))
+    return {k: torch.from_numpy(d[k]) for k in d.files}
+
+
+@pytest.mark.parametrize("name,cfg", CASES)
+def test_log_likelihood_and_loss(golden_dir, name, cfg):
+    g = load(golden_dir, name)
+    sd = fo.synth_state_dict(cfg, int(g["weight_seed"]))
+    args = (g["atom_types"], g["x_coords"], g["x_velocs"], g["y_coords"], g["y_velocs"], g["masked_elements"])
+    ll = fo.log_likelihood(sd, cfg, *args)
+    # same torch ops in the same order as the reference: agreement is to fp32 round-off
+    torch.testing.assert_close(ll, g["log_likelihood"], rtol=2e-6, atol=2e-5)
+    loss = fo.nll_loss(sd, cfg, *args)
+    torch.testing.assert_close(loss, g["loss"], rtol=2e-6, atol=2e-6)
+    # fp64 oracle with direct distances == reference fp64 run (cdist in fp64)
+    sd64 = fo.to_dtype(sd, torch.float64)
+    ll64 = fo.log_likelihood(sd64, cfg, args[0], *[a.double() for a in args[1:5]], args[5], distance_mode="direct")
+    torch.testing.assert_close(ll64, g["log_likelihood_f64"], rtol=1e-9, atol=1e-7)
+
+
+@pytest.mark.parametrize("name,cfg", CASES)
+def test_scores_and_layer0(golden_dir, name, cfg):
+    g = load(golden_dir, name)
+    sd = fo.synth_state_dict(cfg, int(g["weight_seed"]))
+    mask = g["masked_elements"]
+    xc = g["x_coords"] - fo.centre_of_mass(g["x_coords"], mask)
+    ls = torch.tensor(cfg.lengthscales)
+    sc = fo.kernel_attention_scores(xc, mask, ls)
+    torch.testing.assert_close(sc, g["scores"], rtol=1e-6, atol=1e-7)
+    # rows over un-masked keys sum to ~1 (reference tests/test_kernel_attention.py:19-46)
+    assert torch.allclose(sc.sum(-1), torch.ones_like(sc.sum(-1)), atol=1e-3)
+    # direct-difference distances stay within 2e-3 of the mm-based cdist scores
+    sc_d = fo.kernel_attention_scores(xc, mask, ls, distance_mode="direct")
+    assert (sc_d - sc).abs().max() < 2e-3
+    feats = torch.nn.functional.embedding(g["atom_types"], sd["flow.atom_embedder.weight"])
+    scale, shift = fo.scale_and_shift(sd, cfg, 0, g["y_coords"] - g["x_coords"], g["y_velocs"], feats, xc, g["x_velocs"], sc)
+    torch.testing.assert_close(scale, g["layer0_scale"], rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(shift, g["layer0_shift"], rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("name,cfg", CASES)
+def test_sampling(golden_dir, name, cfg):
+    g = load(golden_dir, name)
+    sd = fo.synth_state_dict(cfg, int(g["weight_seed"]))
+    at, x, xv, mask = g["atom_types"], g["x_coords"], g["x_velocs"], g["masked_elements"]
+    yc, yv, lp = fo.conditional_sample_with_logp(sd, cfg, at, x, xv, mask, 1, g["s1_z_coords"], g["s1_z_velocs"])
+    torch.testing.assert_close(yc, g["s1_y_coords"], rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(yv, g["s1_y_velocs"], rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(lp, g["s1_logp"], rtol=2e-6, atol=5e-5)
+    S = g["sS_z_coords"].shape[0]
+    yc, yv, lp = fo.conditional_sample_with_logp(sd, cfg, at[:1], x[:1], xv[:1], mask[:1], S, g["sS_z_coords"], g["sS_z_velocs"])
+    torch.testing.assert_close(yc, g["sS_y_coords"], rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(lp, g["sS_logp"], rtol=2e-6, atol=5e-5)
+    p_yx = fo.log_likelihood(sd, cfg, at[:1].repeat(S, 1), yc.squeeze(1), yv.squeeze(1), x[:1].repeat(S, 1, 1),
+                             xv[:1].repeat(S, 1, 1), mask[:1].repeat(S, 1))
+    torch.testing.assert_close(p_yx, g["sS_p_yx"], rtol=5e-6, atol=2e-4)
+
+
+def test_rng_contract(golden_dir):
+    """Latent draws == two normal_() draws [S,B,V,3], coords first (flow.py:274-275)."""
+    g = load(golden_dir, "tiny_ad")
+    sd = fo.synth_state_dict(TINY, 0)
+    torch.manual_seed(4321 + 12)
+    zc, zv = fo.draw_latents(sd, g["x_coords"][:1], g["x_velocs"][:1], 4)
+    torch.testing.assert_close(zc, g["sS_z_coords"], rtol=0, atol=0)
+    torch.testing.assert_close(zv, g["sS_z_velocs"], rtol=0, atol=0)
+    torch.manual_seed(4321 + 12)
+    e1 = torch.empty(4, 1, 22, 3).normal_() * torch.exp(sd["coords_prior_log_scale"])
+    torch.testing.assert_close(e1, zc, rtol=0, atol=0)
+
+
+def test_sample_then_density_roundtrip(golden_dir):
+    """Size-independent property: log p from sampling == log_likelihood of the sample."""
+    g = load(golden_dir, "full_ad22")
+    sd = fo.synth_state_dict(FULL, 0)
+    at, x, xv, mask = g["atom_types"], g["x_coords"], g["x_velocs"], g["masked_elements"]
+    yc, yv, lp = fo.conditional_sample_with_logp(sd, FULL, at, x, xv, mask, 1, g["s1_z_coords"], g["s1_z_velocs"])
+    ll = fo.log_likelihood(sd, FULL, at, x, xv, yc[0], yv[0], mask)
+    torch.testing.assert_close(ll, lp[0], rtol=1e-5, atol=2e-3)
