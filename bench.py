@@ -1,0 +1,334 @@
+#!/usr/bin/env python
+"""Benchmark of the Timewarp MH hot path on B200 (BASELINE.json: "MH proposals/sec").
+
+One STEP = one Metropolis-Hastings iteration of `--chains` independent chains of the synthetic
+4-residue peptide (2olx, 65 atoms): reverse flow pass (proposal + log p_xy), potential + kinetic
+energies, forward flow pass (log p_yx), accept/reject  -- utils/evaluation_utils.py:589-689 with
+num_proposal_steps == 1 applied to every chain (BASELINE.json configs[2]).  Proposals/s = chains * steps / time.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+N > 1 is launched by the driver with torch.distributed.run (one rank per GPU, NCCL); chains are
+sharded (weak scaling: --chains per GPU), no data-path collective, one all-gather of acceptance
+statistics after the timed region.  Rank 0 prints ONE JSON line.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "mh_proposals_per_sec"
+UNIT = "proposals/s"
+
+
+def f_atom(V):  # algorithmic FLOPs per atom per flow pass
+    return 71_663_616 + 73_728 * V
+
+
+def ffn_flops_per_token(D=128, F=2048):
+    return 2 * (D * F + F * D)
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sustained=d["bf16_tflops_sustained"], source="measured")
+    return dict(hbm_gbs=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback")
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clocks / throttle reasons with nvidia-smi while the timed region runs."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu, self.rows, self.stop_flag = gpu_index, [], threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.gpu)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except Exception:
+                continue
+            for n, v in zip(names, r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def synthetic_chains(pep, n_chains, seed):
+    """Chain starts: 2olx MD frame jittered with N(0, 0.005^2) nm."""
+    g = torch.Generator().manual_seed(seed)
+    x = torch.tensor(pep.coords_nm, dtype=torch.float32)[None] + 0.005 * torch.randn(n_chains, pep.num_atoms, 3, generator=g)
+    at = torch.tensor(pep.atom_types)[None].repeat(n_chains, 1)
+    mask = torch.zeros(n_chains, pep.num_atoms, dtype=torch.bool)
+    return x, at, mask
+
+
+# --------------------------------------------------------------------------------------------
+def cpu_reference_iteration(sd, o, sysd, kbT, x, at, mask, gen):
+    """One MH iteration on the CPU through the oracle port of the reference path (flow in torch fp32
+    on all host threads + fp64 numpy energy): evaluation_utils.py:589-668."""
+    from oracle import energy_oracle as eo
+    from oracle import flow_oracle as fo
+
+    n = x.shape[0]
+    xv = torch.randn(x.shape, generator=gen)
+    zc = torch.randn((1,) + tuple(x.shape), generator=gen) * torch.exp(sd["coords_prior_log_scale"])
+    zv = torch.randn((1,) + tuple(x.shape), generator=gen) * torch.exp(sd["velocs_prior_log_scale"])
+    with torch.no_grad():
+        yc, yv, p_xy = fo.conditional_sample_with_logp(sd, o, at, x, xv, mask, 1, zc, zv)
+        p_yx = fo.log_likelihood(sd, o, at, yc[0], yv[0], x, xv, mask)
+    e_x = torch.from_numpy(eo.potential_energy(sysd, x.numpy().astype(np.float64))).float() / kbT
+    e_y = torch.from_numpy(eo.potential_energy(sysd, yc[0].numpy().astype(np.float64))).float() / kbT
+    e_kin = 0.5 * (yv[0] ** 2).sum((-1, -2)) - 0.5 * (xv**2).sum((-1, -2))
+    ex = (e_y - e_x) + e_kin + p_xy[0] - p_yx
+    acc = torch.rand(n, generator=gen) < torch.clamp(torch.exp(-ex), max=1.0)
+    return torch.where(acc[:, None, None], yc[0], x), acc
+
+
+def time_cpu_reference(sample_chains, iters, warmup, seed=0):
+    from oracle import flow_oracle as fo
+    from timewarp_b200.forcefield import MOLAR_GAS_CONSTANT_R, amber_like_system
+    from timewarp_b200.peptides import tetrapeptide_2olx
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    pep = tetrapeptide_2olx()
+    o = fo.OracleConfig()
+    sd = fo.synth_state_dict(o, 0)
+    sysd = amber_like_system(pep).as_float32()
+    kbT = 310.0 * MOLAR_GAS_CONSTANT_R
+    x, at, mask = synthetic_chains(pep, sample_chains, seed)
+    gen = torch.Generator().manual_seed(seed)
+    for _ in range(warmup):
+        x, _ = cpu_reference_iteration(sd, o, sysd, kbT, x, at, mask, gen)
+    times = []
+    for _ in range(iters):
+        t0 = time.perf_counter()
+        x, _ = cpu_reference_iteration(sd, o, sysd, kbT, x, at, mask, gen)
+        times.append(time.perf_counter() - t0)
+    return sample_chains * iters / sum(times), torch.get_num_threads(), 1e3 * sum(times) / iters
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    S = args.cpu_sample
+    w = min(args.warmup, 1)
+    value, cores, ms = time_cpu_reference(S, args.steps, w)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": w,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"mh_2olx65_chains{args.chains}_per_gpu", "atoms": 65, "chains_per_gpu": args.chains,
+                   "note": "reference is pure Python (PyTorch + OpenMM); OpenMM is not installable offline, so this arm runs the oracle port "
+                           "of the same path (oracle/flow_oracle.py torch-CPU fp32 + oracle/energy_oracle.py numpy fp64) on a bounded sample"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{S} chains x {args.steps} MH iterations of the same 2olx-65 workload (flow 2 passes + 2 energies each)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------
+def run_ours(args):
+    import ctypes as C
+
+    import timewarp_b200 as tw
+    from oracle import flow_oracle as fo  # weights generator only (synthetic, random-init-scale parameters)
+    from timewarp_b200 import _lib
+    from timewarp_b200.energy import PeptidePotentialEnergy
+    from timewarp_b200.forcefield import amber_like_system
+    from timewarp_b200.peptides import tetrapeptide_2olx
+    from timewarp_b200.sampling import MHChains
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl ours needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    lib = _lib.load()
+    pep = tetrapeptide_2olx()
+    V = pep.num_atoms
+    o = fo.OracleConfig()
+    model = tw.custom_transformer_nvp_constructor(tw.kernel_transformer_nvp_config(args.precision))
+    model.load_state_dict(fo.synth_state_dict(o, 0))
+    model = model.to(dev).eval()
+    energy = PeptidePotentialEnergy(amber_like_system(pep))
+    x0, at, mask = synthetic_chains(pep, args.chains, seed=1000 + rank)
+    torch.manual_seed(args.seed + rank)  # per-rank generator
+    chains = MHChains(model, energy, at.to(dev), mask.to(dev), x0.to(dev))
+
+    for _ in range(args.warmup):
+        chains.step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+
+    # ---- device-resident timed region: exactly K steps -------------------------------------
+    lib.tw_prof_enable(1)  # CUDA events around every fused-FFN launch (dominant kernel)
+    launches0 = lib.tw_debug_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        chains.step()
+    ev1.record()
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    launches = lib.tw_debug_launch_count() - launches0
+    ffn_ms, ffn_scopes = C.c_double(0), C.c_longlong(0)
+    _lib.check(lib.tw_prof_collect(C.byref(ffn_ms), C.byref(ffn_scopes)), "tw_prof_collect")
+    lib.tw_prof_enable(0)
+
+    # ---- end-to-end region: host (pinned) state in, host state + decisions out, every step --
+    hx = x0.clone().pin_memory()
+    hat, hmask = at.clone().pin_memory(), mask.clone().pin_memory()
+    hy = torch.empty_like(hx).pin_memory()
+    hacc = torch.empty(args.chains, dtype=torch.bool).pin_memory()
+    h2d = hx.numel() * 4 + hat.numel() * 8 + hmask.numel()
+    d2h = hy.numel() * 4 + hacc.numel()
+
+    def e2e_step():
+        chains.x.copy_(hx, non_blocking=True)
+        chains.atom_types.copy_(hat, non_blocking=True)
+        chains.mask.copy_(hmask, non_blocking=True)
+        chains.e_pot_x = (energy(chains.x) / chains.kbT).squeeze(-1).contiguous()  # host-fed state: its energy is part of the call
+        acc = chains.step()
+        hy.copy_(chains.x, non_blocking=True)
+        hacc.copy_(acc, non_blocking=True)
+        torch.cuda.current_stream().synchronize()  # the caller reads the result
+        hx.copy_(hy)
+
+    e2e_step()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+    if rank == 0:
+        sampler.stop_flag.set()
+        sampler.join(timeout=3)
+
+    t = torch.tensor([ms_total, ms_e2e], device=dev, dtype=torch.float64)
+    acc_rate = chains.acceptance_rate()
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)  # max over ranks
+        gathered = [torch.empty_like(acc_rate) for _ in range(world)]
+        dist.all_gather(gathered, acc_rate)  # the path's only collective: acceptance statistics
+        acc_rate = torch.cat(gathered)
+    ms_total, ms_e2e = t.tolist()
+    total_chains = args.chains * world
+    value = total_chains * args.steps / (ms_total / 1e3)
+    e2e_value = total_chains * args.steps / (ms_e2e / 1e3)
+
+    if rank == 0:
+        peaks = load_peaks()
+        M = args.chains * V
+        n_ffn = max(int(ffn_scopes.value), 1)
+        ffn_ms_avg = ffn_ms.value / n_ffn
+        ffn_flops = 2 * M * ffn_flops_per_token()  # one timed scope = FFN of BOTH conditioner networks over all tokens
+        achieved = ffn_flops / (ffn_ms_avg / 1e3) / 1e12 if ffn_ms_avg > 0 else 0.0
+        issued_factor = 3 if args.precision == "bf16x3" else 1
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "ffn_traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get(args.precision)
+            except Exception:
+                traffic = None
+        step_flops = args.chains * 2 * V * f_atom(V)
+        cpu_val, cpu_cores, _ = time_cpu_reference(args.cpu_sample, 2, 1) if not args.no_cpu_baseline else (None, None, None)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": {"fp32": "f32", "bf16x3": "bf16x3(f32-accumulate)", "bf16": "bf16"}[args.precision], "data": "synthetic",
+            "config": {"workload": f"mh_2olx65_chains{args.chains}_per_gpu", "atoms": V, "chains_per_gpu": args.chains,
+                       "model": "kernel_transformer_nvp (35.97M params, synthetic weights)", "precision": args.precision,
+                       "energy": "synthetic Amber-like + GB-OBC2, on-GPU fp64",
+                       "l2": "working set per step (activations+workspace) >> 126 MB L2; no explicit flush",
+                       "algorithmic_tflops_per_step": step_flops / 1e12},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches),
+            "clocks": sampler.summary(),
+            "roofline": {"bound": "tensor", "kernel": "fused FFN (linear1+ReLU+linear2+residual), both conditioner nets",
+                         "achieved": achieved, "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["tf_sustained"],
+                         "peak_source": peaks["source"] + " (sustained bf16 cuBLAS)", "issued_mma_factor": issued_factor,
+                         "avg_launch_ms": ffn_ms_avg, "launches_timed": n_ffn, "share_of_step": ffn_ms.value / ms_total, "traffic": traffic},
+            "whole_step_algorithmic_tflops": step_flops * args.steps / (ms_total / 1e3) / 1e12,
+            "acceptance_rate_mean": float(acc_rate.mean().item()),
+        }
+        if cpu_val is not None:
+            line["cpu_baseline"] = {"value": cpu_val, "unit": UNIT, "cores": cpu_cores, "kind": "port",
+                                    "sample": f"{args.cpu_sample} chains x 2 MH iterations of the same workload through oracle/ (torch-CPU fp32 flow + numpy fp64 energy)"}
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--chains", type=int, default=1024, help="chains per GPU (BASELINE configs[2]: 1024)")
+    ap.add_argument("--precision", default=os.environ.get("TW_PRECISION", "fp32"), choices=["fp32", "bf16x3", "bf16"])
+    ap.add_argument("--cpu-sample", type=int, default=32, help="chains in the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--seed", type=int, default=0)
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

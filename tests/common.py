@@ -1,0 +1,44 @@
+"""Helpers shared by the test files."""
+import os
+
+import numpy as np
+import torch
+
+from oracle import flow_oracle as fo
+import timewarp_b200 as tw
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+TINY_O = fo.OracleConfig(atom_embedding_dim=8, latent_mlp_hidden_dims=[24], num_coupling_layers=4,
+                         num_transformer_layers=2, d_model=16, dim_feedforward=32, lengthscales=[0.3, 1.0])
+FULL_O = fo.OracleConfig()
+
+
+def model_config(o: fo.OracleConfig, precision: str):
+    return tw.CustomAttentionTransformerNVPConfig(
+        atom_embedding_dim=o.atom_embedding_dim,
+        latent_mlp_hidden_dims=list(o.latent_mlp_hidden_dims),
+        num_coupling_layers=o.num_coupling_layers,
+        num_transformer_layers=o.num_transformer_layers,
+        encoder_layer_config=tw.CustomAttentionEncoderLayerConfig(
+            d_model=o.d_model, dim_feedforward=o.dim_feedforward, dropout=0.0, num_heads=len(o.lengthscales),
+            attention_type="kernel", lengthscales=list(o.lengthscales), normalise_kernel_values=True),
+        position_layer_index_mod_2=o.position_layer_index_mod_2,
+        precision=precision,
+    )
+
+
+def load_golden(name):
+    d = np.load(os.path.join(GOLDEN, name + ".npz"))
+    return {k: torch.from_numpy(d[k]) for k in d.files}
+
+
+def build_model(o: fo.OracleConfig, precision: str, weight_seed: int = 0, device="cuda"):
+    m = tw.custom_transformer_nvp_constructor(model_config(o, precision))
+    sd = fo.synth_state_dict(o, weight_seed)
+    m.load_state_dict(sd, strict=True)
+    return m.to(device).eval(), sd
+
+
+EMPTY_ADJ = torch.zeros(0, 2, dtype=torch.long)
+EMPTY_EBI = torch.zeros(0, dtype=torch.long)

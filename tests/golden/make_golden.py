@@ -180,8 +180,24 @@ def chirality_case():
     print("chirality centers", centers.tolist(), "changed", changed.tolist())
 
 
+def init_case():
+    """Reference default initialisation under a fixed torch seed (construction-order contract)."""
+    enc = CustomAttentionEncoderLayerConfig(d_model=TINY.d_model, dim_feedforward=TINY.dim_feedforward, dropout=0.0,
+                                            num_heads=len(TINY.lengthscales), attention_type="kernel",
+                                            lengthscales=list(TINY.lengthscales), normalise_kernel_values=True)
+    mc = CustomAttentionTransformerNVPConfig(atom_embedding_dim=TINY.atom_embedding_dim, latent_mlp_hidden_dims=list(TINY.latent_mlp_hidden_dims),
+                                             num_coupling_layers=TINY.num_coupling_layers, num_transformer_layers=TINY.num_transformer_layers,
+                                             encoder_layer_config=enc)
+    torch.manual_seed(0)
+    model = custom_transformer_nvp_constructor(mc)
+    sd = {k: v.numpy() for k, v in model.state_dict().items()}
+    np.savez_compressed(os.path.join(HERE, "tiny_init_seed0.npz"), **sd)
+    print("init case:", len(sd), "tensors")
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
+    init_case()
     ad, olx = alanine_dipeptide(), tetrapeptide_2olx()
     run_case("tiny_ad_ragged", TINY, ad, B=3, seed=11, lengths=[22, 15, 9], sample_S=4)
     run_case("tiny_ad", TINY, ad, B=4, seed=12, sample_S=4)

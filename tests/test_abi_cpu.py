@@ -1,0 +1,138 @@
+"""CPU-only checks: the C-ABI library loads and exports every symbol include/timewarp_b200.h declares,
+host logic (config validation, parameter table, state_dict contract, seeded init) -- no compute calls."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import timewarp_b200 as tw
+from timewarp_b200 import _lib
+from timewarp_b200.build import build_library
+from oracle import flow_oracle as fo
+from tests.common import FULL_O, TINY_O, GOLDEN, model_config
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    build_library()
+    return _lib.load()
+
+
+def test_header_symbols_exported(lib):
+    hdr = open(os.path.join(ROOT, "include", "timewarp_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = sorted(set(re.findall(r"\b(tw_[a-z0-9_]+)\s*\(", hdr)))
+    assert declared, "no declarations parsed"
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+    assert sorted(_lib.exported_symbols()) == declared
+    assert lib.tw_abi_version() == 1
+
+
+def test_struct_layout_matches_c(lib):
+    # sizes computed by the C compiler for the same declarations
+    import subprocess, tempfile, textwrap
+    src = textwrap.dedent("""
+        #include <stdio.h>
+        #include "timewarp_b200.h"
+        int main(){ printf("%zu %zu\\n", sizeof(tw_flow_config), sizeof(tw_energy_system)); return 0; }
+    """)
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "s.c"), "w").write(src)
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), os.path.join(d, "s.c"), "-o", os.path.join(d, "s")])
+        a, b = map(int, subprocess.check_output([os.path.join(d, "s")]).split())
+    assert a == C.sizeof(_lib.FlowConfig) and b == C.sizeof(_lib.EnergySystem)
+
+
+def test_param_table_and_state_dict_keys(lib):
+    for o in (TINY_O, FULL_O):
+        m = tw.custom_transformer_nvp_constructor(model_config(o, "fp32"))
+        sd = m.state_dict()
+        assert list(sd.keys()) == list(fo.state_dict_shapes(o).keys())
+        for k, shape in fo.state_dict_shapes(o).items():
+            assert tuple(sd[k].shape) == shape, k
+        assert lib.tw_flow_num_params(C.byref(m._cfg)) == len(m._ordered_params())
+    assert sum(p.numel() for p in m.parameters()) == 35_971_282
+
+
+def test_seeded_init_matches_reference():
+    ref = np.load(os.path.join(GOLDEN, "tiny_init_seed0.npz"))
+    torch.manual_seed(0)
+    m = tw.custom_transformer_nvp_constructor(model_config(TINY_O, "fp32"))
+    sd = m.state_dict()
+    assert sorted(sd.keys()) == sorted(ref.files)
+    for k in ref.files:
+        assert np.array_equal(sd[k].numpy(), ref[k]), k
+
+
+def test_config_validation(lib):
+    bad = model_config(TINY_O, "fp32")
+    bad.num_coupling_layers = 3
+    with pytest.raises(AssertionError, match="even number of coupling layers"):
+        tw.custom_transformer_nvp_constructor(bad)
+    bad = model_config(TINY_O, "fp32")
+    bad.position_layer_index_mod_2 = 2
+    with pytest.raises(AssertionError):
+        tw.custom_transformer_nvp_constructor(bad)
+    bad = model_config(TINY_O, "fp32")
+    bad.encoder_layer_config.attention_type = "local"
+    with pytest.raises(NotImplementedError):
+        tw.custom_transformer_nvp_constructor(bad)
+    # tensor-core precisions reject layer sizes they do not cover (status TW_ERR_UNSUPPORTED)
+    m = tw.custom_transformer_nvp_constructor(model_config(TINY_O, "bf16x3"))
+    n = C.c_size_t()
+    assert lib.tw_flow_workspace_bytes(C.byref(m._cfg), 4, 4, 22, C.byref(n)) == 4
+    assert b"tensor-core" in lib.tw_last_error()
+    # NULL pointers are reported, not dereferenced
+    m = tw.custom_transformer_nvp_constructor(model_config(TINY_O, "fp32"))
+    assert lib.tw_flow_log_likelihood(C.byref(m._cfg), None, None, None, None, None, None, None, 1, 3, 1, None, None, None, None, 0, None) == 1
+    assert lib.tw_attn_scores(None, None, None, 1, 3, 2, None, None) == 1
+
+
+def test_no_cpu_fallback():
+    m = tw.custom_transformer_nvp_constructor(model_config(TINY_O, "fp32"))
+    B, V = 2, 5
+    kw = dict(atom_types=torch.zeros(B, V, dtype=torch.long), x_coords=torch.zeros(B, V, 3), x_velocs=torch.zeros(B, V, 3),
+              adj_list=torch.zeros(0, 2, dtype=torch.long), edge_batch_idx=torch.zeros(0, dtype=torch.long),
+              masked_elements=torch.zeros(B, V, dtype=torch.bool))
+    with pytest.raises(_lib.TimewarpB200Error, match="no CPU fallback"):
+        m.log_likelihood(y_coords=torch.zeros(B, V, 3), y_velocs=torch.zeros(B, V, 3), **kw)
+    with pytest.raises(_lib.TimewarpB200Error, match="no CPU fallback"):
+        m.conditional_sample(num_samples=1, **kw)
+    with pytest.raises(NotImplementedError):
+        m.flow.chain[0].scale_transformer.in_mlp(torch.zeros(1, 17))
+    from timewarp_b200.energy import PeptidePotentialEnergy
+    from timewarp_b200.forcefield import amber_like_system
+    from timewarp_b200.peptides import alanine_dipeptide
+    e = PeptidePotentialEnergy(amber_like_system(alanine_dipeptide()))
+    assert abs(e.kbT - 2.577483411627504) < 1e-12  # utils/evaluation_utils_o2.py:17
+    with pytest.raises(_lib.TimewarpB200Error, match="no CPU fallback"):
+        e(torch.zeros(1, 22, 3))
+    with pytest.raises(AssertionError):
+        e(torch.zeros(1, 21, 3))
+
+
+def test_chirality_centers_host():
+    from timewarp_b200.chirality import find_chirality_centers
+    g = np.load(os.path.join(GOLDEN, "chirality_2olx.npz"))
+    c = find_chirality_centers(torch.from_numpy(g["bonds"]), torch.from_numpy(g["atom_types"]))
+    assert c.tolist() == g["centers"].tolist()
+
+
+def test_num_proposal_steps_and_chainstats(tmp_path):
+    from timewarp_b200.sampling import ChainStats, compute_num_proposal_steps
+    # utils/evaluation_utils.py:32-64
+    assert compute_num_proposal_steps(1e-3, max_num_proposal_steps=100) == 100
+    assert compute_num_proposal_steps(0.5) == 4  # ceil(log(0.1)/log(0.5))
+    assert compute_num_proposal_steps(1.0) == 1
+    assert compute_num_proposal_steps(0.0, max_num_proposal_steps=7) == 7
+    a = np.arange(10.0)
+    s = ChainStats(*(a.copy() for _ in range(9)))
+    assert len(s) == 10 and len(s.thin(3)) == 4 and len(s[2:5]) == 3
+    s.save(tmp_path / "c.pkl")
+    assert np.array_equal(ChainStats.load(tmp_path / "c.pkl").p_xy, a)

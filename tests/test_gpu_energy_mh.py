@@ -1,0 +1,213 @@
+"""Energy kernel vs the fp64 numpy oracle, MH / exploration / chirality kernels vs torch restatements
+of the reference lines, and the sampling drivers end to end."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import energy_oracle as eo
+from oracle import flow_oracle as fo
+from tests.common import EMPTY_ADJ, EMPTY_EBI, FULL_O, TINY_O, build_model, load_golden
+from timewarp_b200.chirality import check_symmetry_change, compute_chirality_sign, find_chirality_centers
+from timewarp_b200.energy import OpenmmPotentialEnergyTorch, PeptidePotentialEnergy
+from timewarp_b200.forcefield import amber_like_system
+from timewarp_b200.peptides import alanine_dipeptide, tetrapeptide_2olx
+from timewarp_b200 import sampling
+
+pytestmark = pytest.mark.gpu
+
+
+def _confs(pep, B, seed, noise=0.01):
+    g = np.random.default_rng(seed)
+    return (pep.coords_nm[None] + noise * g.standard_normal((B, pep.num_atoms, 3))).astype(np.float32)
+
+
+@pytest.mark.parametrize("pep_fn,gb", [(alanine_dipeptide, "obc2"), (tetrapeptide_2olx, "obc2"), (tetrapeptide_2olx, "obc1")])
+def test_energy_matches_oracle(pep_fn, gb):
+    pep = pep_fn()
+    sysd = amber_like_system(pep, gb=gb)
+    energy = PeptidePotentialEnergy(sysd)
+    x = _confs(pep, 33, 0)
+    e, terms = energy(torch.from_numpy(x).cuda(), return_terms=True)
+    assert e.shape == (33, 1) and e.dtype == torch.float32
+    ref_terms = eo.energy_terms(sysd.as_float32(), x.astype(np.float64))
+    # test_md.py:35-47 checks potential energies at atol 1e-3 kJ/mol; fp32 output rounding of |E|~1e3 is ~6e-5
+    np.testing.assert_allclose(terms.cpu().numpy(), ref_terms, rtol=2e-6, atol=1e-3)
+    np.testing.assert_allclose(e.cpu().numpy()[:, 0], ref_terms.sum(-1), rtol=2e-6, atol=1e-3)
+    assert len(set(np.round(ref_terms[0], 6))) >= 3  # >= 3 distinct force components (test_md.py:50-83)
+
+
+def test_energy_cutoff_and_options():
+    pep = tetrapeptide_2olx()
+    sysd = amber_like_system(pep)
+    sysd.cutoff = 0.9  # make the cutoff bite inside the molecule
+    sysd.reaction_field_eps = 78.3
+    x = _confs(pep, 5, 1)
+    e = PeptidePotentialEnergy(sysd)(torch.from_numpy(x).cuda())
+    np.testing.assert_allclose(e.cpu().numpy()[:, 0], eo.potential_energy(sysd.as_float32(), x), rtol=2e-6, atol=1e-3)
+    sysd.use_gb = False
+    e = PeptidePotentialEnergy(sysd)(torch.from_numpy(x).cuda())
+    np.testing.assert_allclose(e.cpu().numpy()[:, 0], eo.potential_energy(sysd.as_float32(), x), rtol=2e-6, atol=1e-3)
+
+
+def test_energy_properties_and_nonfinite():
+    pep = tetrapeptide_2olx()
+    energy = OpenmmPotentialEnergyTorch(amber_like_system(pep), None, platform_name="CUDA")
+    assert abs(energy.kbT - 2.577483411627504) < 1e-12 and energy.num_particles == 65
+    x = torch.from_numpy(_confs(pep, 4, 2)).cuda()
+    e = energy(x)
+    # rigid motion invariance
+    th = 0.9
+    R = torch.tensor([[math.cos(th), -math.sin(th), 0], [math.sin(th), math.cos(th), 0], [0, 0, 1.0]], device="cuda")
+    e2 = energy(x @ R.T + torch.tensor([0.5, -0.2, 1.0], device="cuda"))
+    torch.testing.assert_close(e, e2, rtol=1e-5, atol=5e-3)
+    # leading dims are flattened like the reference (openmm_bridge.py:292)
+    assert energy(x.reshape(2, 2, 65, 3)).shape == (4, 1)
+    # overlapping atoms / NaN coordinates give non-finite energies, never a crash (a12)
+    bad = x.clone()
+    bad[0, 1] = bad[0, 0]
+    bad[1, 3, 0] = float("nan")
+    eb = energy(bad)
+    assert not torch.isfinite(eb[0]).all() and not torch.isfinite(eb[1]).all() and torch.isfinite(eb[2:]).all()
+    assert energy(x[:0]).shape == (0, 1)
+
+
+def test_chirality_kernels_match_reference_golden():
+    g = load_golden("chirality_2olx")
+    signs = compute_chirality_sign(g["coords"].cuda(), g["centers"].cuda())
+    assert torch.equal(signs.cpu(), g["signs"])
+    changed = check_symmetry_change(g["coords"].cuda(), g["centers"].cuda(), g["ref_signs"].cuda())
+    assert torch.equal(changed.cpu(), g["changed"])
+    # mirror => every centre flips (reference tests/test_chirality.py:91-99)
+    mirrored = g["coords"] * torch.tensor([1.0, 1.0, -1.0])
+    assert torch.equal(compute_chirality_sign(mirrored.cuda(), g["centers"].cuda()).cpu(), -g["signs"])
+
+
+def test_mh_accept_kernel():
+    n = 4096
+    g = torch.Generator().manual_seed(0)
+    epx, epy, ekx, eky, pxy, pyx = (torch.randn(n, generator=g) * s for s in (30, 30, 5, 5, 200, 200))
+    u = torch.rand(n, generator=g)
+    epy[5] = float("nan"); epy[6] = float("inf"); epy[7] = -float("inf")
+    ex_ref = ((epy - epx) + (eky - ekx) + pxy) - pyx  # evaluation_utils.py:644-663
+    p_ref = torch.min(torch.tensor(1.0), torch.exp(-ex_ref))
+    acc_ref = u < p_ref
+    ex, pa, acc, first = sampling.mh_accept(*(t.cuda() for t in (epx, epy, ekx, eky, pxy, pyx, u)), want_first=True)
+    torch.testing.assert_close(ex.cpu(), ex_ref, rtol=0, atol=0, equal_nan=True)
+    torch.testing.assert_close(pa.cpu(), p_ref, rtol=2e-6, atol=0, equal_nan=True)
+    # decisions are identical except where |u - p_acc| is inside exp() round-off
+    diff = acc.view(torch.bool).cpu() != acc_ref
+    assert (diff & ((u - p_ref).abs() > 1e-6)).sum() == 0
+    assert not acc[5] and not acc[6] and acc[7]  # NaN/+inf reject, -inf accepts (a12)
+    assert int(first.item()) == int(acc.view(torch.bool).cpu().nonzero()[0])
+    # state update in place only where accepted
+    V = 7
+    x, xv, y, yv = (torch.randn(n, V, 3, generator=g).cuda() for _ in range(4))
+    x0, xv0 = x.clone(), xv.clone()
+    _, _, acc2, _ = sampling.mh_accept(*(t.cuda() for t in (epx, epy, ekx, eky, pxy, pyx, u)), x_coords=x, x_velocs=xv, y_coords=y, y_velocs=yv)
+    a = acc2.view(torch.bool)[:, None, None]
+    assert torch.equal(x, torch.where(a, y, x0)) and torch.equal(xv, torch.where(a, yv, xv0))
+    # nothing accepted -> -1
+    _, _, _, first = sampling.mh_accept(epx.cuda(), (epx + 1e6).cuda(), ekx.cuda(), ekx.cuda(), pxy.cuda(), pxy.cuda(), u.cuda(), want_first=True)
+    assert int(first.item()) == -1
+
+
+def test_kinetic_energy():
+    v = torch.randn(9, 22, 3)
+    m = torch.rand(22) * 10 + 1
+    kbT = 2.5774834
+    a = sampling.compute_kinetic_energy(v.cuda(), None, random_velocs=True)
+    torch.testing.assert_close(a.cpu(), 0.5 * (v**2.0).sum(-1).sum(-1), rtol=1e-5, atol=1e-5)
+    b = sampling.compute_kinetic_energy(v.cuda(), m.cuda(), random_velocs=False, kbT=kbT)
+    torch.testing.assert_close(b.cpu(), 0.5 * (m * (v**2.0).sum(-1)).sum(-1) / kbT, rtol=1e-5, atol=1e-5)
+
+
+class _Batch:
+    def __init__(self, pep, dev):
+        self.atom_coords = torch.tensor(pep.coords_nm, dtype=torch.float32)[None]
+        self.atom_velocs = torch.zeros_like(self.atom_coords)
+        self.atom_types = torch.tensor(pep.atom_types)[None]
+        self.masked_elements = torch.zeros(1, pep.num_atoms, dtype=torch.bool)
+        self.adj_list = torch.tensor(pep.bonds)
+        self.edge_batch_idx = torch.zeros(len(pep.bonds), dtype=torch.long)
+
+
+@pytest.mark.parametrize("random_velocs", [True, False])
+@pytest.mark.parametrize("accept", [True, False])
+@pytest.mark.parametrize("S", [1, 10])
+def test_sample_with_model_shapes(random_velocs, accept, S):
+    """Reference tests/test_evaluation_utils.py:112-138: len(sampled_coords) == len(chain_stats.acceptance) + 1."""
+    if not accept and S > 1:
+        pytest.skip("reference raises for accept=False with several proposals")
+    pep = alanine_dipeptide()
+    m, _ = build_model(TINY_O, "fp32", 0)
+    energy = PeptidePotentialEnergy(amber_like_system(pep))
+    batch = _Batch(pep, "cuda")
+    centers = find_chirality_centers(batch.adj_list, batch.atom_types)
+    ref_signs = compute_chirality_sign(batch.atom_coords.cuda(), centers.cuda())
+    torch.manual_seed(0)
+    coords, velocs, accepted, stats = sampling.sample_with_model(
+        batch, m, torch.device("cuda"), energy, torch.tensor(pep.masses, dtype=torch.float32), num_samples=12, accept=accept,
+        random_velocs=random_velocs, resample_velocs=random_velocs, num_proposal_steps=S, reference_signs=ref_signs, chirality_centers=centers)
+    assert len(coords) == len(stats.acceptance) + 1 == len(velocs)
+    assert coords.shape[1:] == (22, 3) and len(stats) >= 12
+    assert 0 <= accepted <= len(stats)
+    for f in ("p_xy", "p_yx", "exponent", "energies_pot", "energies_kin", "energies_pot_delta", "energies_kin_delta", "acceptance_indicator"):
+        assert len(getattr(stats, f)) == len(stats)
+
+
+def test_mh_chains_against_oracle_step():
+    """One lock-step MH iteration over B chains == the reference formulae evaluated with the CPU oracles."""
+    pep = alanine_dipeptide()
+    m, sd = build_model(TINY_O, "fp32", 0)
+    sysd = amber_like_system(pep)
+    energy = PeptidePotentialEnergy(sysd)
+    B = 16
+    x0 = torch.from_numpy(_confs(pep, B, 3)).cuda()
+    at = torch.tensor(pep.atom_types)[None].repeat(B, 1).cuda()
+    mask = torch.zeros(B, 22, dtype=torch.bool, device="cuda")
+    torch.manual_seed(11)
+    chains = sampling.MHChains(m, energy, at, mask, x0)
+    x_before, e_before = chains.x.clone(), chains.e_pot_x.clone()
+    torch.manual_seed(12)
+    acc = chains.step()
+    # replay the RNG stream: velocities, latents (coords, velocs), uniforms
+    torch.manual_seed(12)
+    xv = torch.randn_like(x_before)
+    zc = torch.empty(1, B, 22, 3, device="cuda").normal_() * torch.exp(m.coords_prior_log_scale.detach())
+    zv = torch.empty(1, B, 22, 3, device="cuda").normal_() * torch.exp(m.velocs_prior_log_scale.detach())
+    u = torch.rand(B, device="cuda")
+    c = lambda t: t.detach().cpu()  # noqa: E731
+    yc, yv, p_xy = fo.conditional_sample_with_logp(sd, TINY_O, c(at), c(x_before), c(xv), c(mask), 1, c(zc), c(zv), distance_mode="direct")
+    p_yx = fo.log_likelihood(sd, TINY_O, c(at), yc[0], yv[0], c(x_before), c(xv), c(mask), distance_mode="direct")
+    kbT = energy.kbT
+    e_y = torch.from_numpy(eo.potential_energy(sysd.as_float32(), yc[0].numpy().astype(np.float64))).float() / kbT
+    e_kin = 0.5 * (yv[0] ** 2).sum((-1, -2)) - 0.5 * (c(xv) ** 2).sum((-1, -2))
+    ex = (e_y - c(e_before)) + e_kin + p_xy[0] - p_yx
+    torch.testing.assert_close(c(chains.last["exponent"]), ex, rtol=1e-4, atol=2e-2)
+    p_acc = torch.clamp(torch.exp(-ex), max=1.0)
+    safe = (c(u) - p_acc).abs() > 1e-3
+    assert torch.equal(c(acc)[safe], (c(u) < p_acc)[safe])
+    torch.testing.assert_close(c(chains.x), torch.where(c(acc)[:, None, None], yc[0], c(x_before)), rtol=1e-4, atol=1e-5)
+
+
+def test_explore_rule():
+    pep = tetrapeptide_2olx()
+    m, _ = build_model(TINY_O, "fp32", 0)
+    energy = PeptidePotentialEnergy(amber_like_system(pep))
+    x = torch.tensor(pep.coords_nm, dtype=torch.float32)[None].cuda()
+    at = torch.tensor(pep.atom_types)[None].cuda()
+    mask = torch.zeros(1, 65, dtype=torch.bool, device="cuda")
+    centers = find_chirality_centers(torch.tensor(pep.bonds), at.cpu())
+    ref_signs = compute_chirality_sign(x, centers.cuda())
+    torch.manual_seed(0)
+    pos, en, n_acc = sampling.explore(m, energy, at, mask, x, torch.randn_like(x), num_steps=3, num_chains=8, threshold=300.0,
+                                      chirality_centers=centers, reference_signs=ref_signs)
+    assert pos.shape == (24, 65, 3) and en.shape == (24,) and n_acc.shape == (8,)
+    # energies never rise by more than the threshold between consecutive kept states (exploration.py:243-246)
+    e = en.reshape(3, 8)
+    e0 = energy(x).squeeze()
+    assert ((e[0] - e0) <= 300.0 + 1e-3).all() and ((e[1:] - e[:-1]) <= 300.0 + 1e-3).all()
+    # stored energies are the energies of the stored positions
+    torch.testing.assert_close(energy(pos).squeeze(-1), en, rtol=1e-5, atol=2e-2)

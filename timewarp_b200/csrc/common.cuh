@@ -1,0 +1,93 @@
+// Shared helpers for the timewarp_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+
+#include "../../include/timewarp_b200.h"
+
+namespace tw {
+
+// thread-local last-error string behind tw_last_error()
+char* err_buf();
+int fail(int code, const char* fmt, ...);
+void count_launch();
+
+// Optional per-kernel-class device timing (tw_prof_* in the ABI): CUDA events recorded on the
+// launching stream around every launch of one kernel class.
+enum ProfClass { PROF_NONE = 0, PROF_FFN = 1, PROF_ATTN = 2, PROF_MLP = 3, PROF_ENERGY = 4 };
+struct ProfScope {
+  cudaStream_t st;
+  int slot;
+  ProfScope(int cls, cudaStream_t s);
+  ~ProfScope();
+};
+
+#define TW_CHECK_ARG(cond, ...)                               \
+  do {                                                        \
+    if (!(cond)) return ::tw::fail(TW_ERR_INVALID, __VA_ARGS__); \
+  } while (0)
+
+#define TW_CUDA(call)                                                                          \
+  do {                                                                                         \
+    cudaError_t _e = (call);                                                                   \
+    if (_e != cudaSuccess)                                                                     \
+      return ::tw::fail(TW_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+#define TW_LAUNCH_CHECK()                                                                      \
+  do {                                                                                         \
+    ::tw::count_launch();                                                                      \
+    cudaError_t _e = cudaGetLastError();                                                       \
+    if (_e != cudaSuccess)                                                                     \
+      return ::tw::fail(TW_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+#define TW_TRY(call)          \
+  do {                        \
+    int _s = (call);          \
+    if (_s != TW_OK) return _s; \
+  } while (0)
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// Bump allocator over the caller's workspace.
+struct Arena {
+  char* base;
+  size_t cap;
+  size_t off;
+  Arena(void* p, size_t n) : base((char*)p), cap(n), off(0) {}
+  template <typename T>
+  T* take(size_t count) {
+    off = align_up(off, 256);
+    T* p = (T*)(base ? base + off : nullptr);
+    off += count * sizeof(T);
+    return p;
+  }
+  bool ok() const { return off <= cap; }
+};
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Sum over a block; result valid in every thread.  `red` must hold >= 33 floats.
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  if (w == 0) {
+    float t = lane < nw ? red[lane] : 0.f;
+    t = warp_sum(t);
+    if (lane == 0) red[32] = t;
+  }
+  __syncthreads();
+  return red[32];
+}
+
+}  // namespace tw

@@ -1,0 +1,222 @@
+// Standalone potential-energy kernel: Amber bonded terms + NonbondedForce(CutoffNonPeriodic,
+// reaction field) + 1-4 exceptions + GBSA-OBC, one thread block per conformation, fp64 math.
+//
+// Replaces the OpenMM call behind OpenmmPotentialEnergyTorch.forward
+// (utils/openmm/openmm_bridge.py:281-294 -> :170-249 -> bgflow -> OpenMM 7.7) for the systems
+// of simulation/md.py:149-173.  OpenMM is a third-party dependency that is absent here
+// (openmm==7.7, timewarp-environment.yml:22): the functional forms below restate OpenMM's
+// documented/Reference-platform algorithms (HarmonicBondForce, HarmonicAngleForce,
+// PeriodicTorsionForce, NonbondedForce with CutoffNonPeriodic, GBSAOBCForce / ReferenceObc).
+// PARITY UNPINNED against the reference's golden energies (no force-field parameter files on
+// this machine); pinned against oracle/energy_oracle.py (independent fp64 numpy restatement).
+#include "common.cuh"
+
+namespace tw {
+
+struct Vec3 {
+  double x, y, z;
+};
+__device__ __forceinline__ Vec3 sub(const Vec3& a, const Vec3& b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+__device__ __forceinline__ double dot(const Vec3& a, const Vec3& b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ Vec3 cross(const Vec3& a, const Vec3& b) {
+  return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
+}
+
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+constexpr int ENERGY_THREADS = 128;
+
+__global__ void __launch_bounds__(ENERGY_THREADS) k_energy(tw_energy_system s, const float* __restrict__ coords,
+                                                           float* __restrict__ out_energy, float* __restrict__ out_terms) {
+  extern __shared__ double sm[];
+  const int N = s.n_atoms;
+  Vec3* pos = reinterpret_cast<Vec3*>(sm);            // [N]
+  double* born = sm + 3 * (size_t)N;                  // [N]
+  __shared__ double red[ENERGY_THREADS / 32][5];
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int64_t b = blockIdx.x;
+  const float* cb = coords + b * (int64_t)N * 3;
+  for (int i = tid; i < N; i += nt) pos[i] = {(double)cb[i * 3], (double)cb[i * 3 + 1], (double)cb[i * 3 + 2]};
+  __syncthreads();
+
+  double e_bond = 0, e_angle = 0, e_tors = 0, e_nb = 0, e_gb = 0;
+
+  // HarmonicBondForce: 1/2 k (r - r0)^2
+  for (int i = tid; i < s.n_bonds; i += nt) {
+    Vec3 d = sub(pos[s.bond_idx[2 * i]], pos[s.bond_idx[2 * i + 1]]);
+    double r = sqrt(dot(d, d)), dr = r - (double)s.bond_param[2 * i];
+    e_bond += 0.5 * (double)s.bond_param[2 * i + 1] * dr * dr;
+  }
+  // HarmonicAngleForce: 1/2 k (theta - theta0)^2
+  for (int i = tid; i < s.n_angles; i += nt) {
+    Vec3 pj = pos[s.angle_idx[3 * i + 1]];
+    Vec3 a = sub(pos[s.angle_idx[3 * i]], pj), c = sub(pos[s.angle_idx[3 * i + 2]], pj);
+    double cs = dot(a, c) / sqrt(dot(a, a) * dot(c, c));
+    cs = fmin(1.0, fmax(-1.0, cs));
+    double dth = acos(cs) - (double)s.angle_param[2 * i];
+    e_angle += 0.5 * (double)s.angle_param[2 * i + 1] * dth * dth;
+  }
+  // PeriodicTorsionForce: k (1 + cos(n phi - phase)); phi with the IUPAC sign (OpenMM Reference:
+  // cross products of (p0-p1),(p2-p1),(p2-p3); sign from (p0-p1).cross2)
+  for (int i = tid; i < s.n_torsions; i += nt) {
+    Vec3 p0 = pos[s.torsion_idx[4 * i]], p1 = pos[s.torsion_idx[4 * i + 1]], p2 = pos[s.torsion_idx[4 * i + 2]],
+         p3 = pos[s.torsion_idx[4 * i + 3]];
+    Vec3 d0 = sub(p0, p1), d1 = sub(p2, p1), d2 = sub(p2, p3);
+    Vec3 c1 = cross(d0, d1), c2 = cross(d1, d2);
+    double cs = dot(c1, c2) / sqrt(dot(c1, c1) * dot(c2, c2));
+    cs = fmin(1.0, fmax(-1.0, cs));
+    double phi = acos(cs);
+    if (dot(d0, c2) < 0) phi = -phi;
+    e_tors += (double)s.torsion_param[3 * i + 2] *
+              (1.0 + cos((double)s.torsion_param[3 * i] * phi - (double)s.torsion_param[3 * i + 1]));
+  }
+  // 1-4 exceptions: plain Coulomb + LJ with the exception parameters, no cutoff
+  for (int i = tid; i < s.n_exceptions; i += nt) {
+    Vec3 d = sub(pos[s.exception_idx[2 * i]], pos[s.exception_idx[2 * i + 1]]);
+    double r2 = dot(d, d), inv_r = 1.0 / sqrt(r2);
+    double sig = (double)s.exception_param[3 * i + 1], eps = (double)s.exception_param[3 * i + 2];
+    double sr2 = sig * sig / r2, sr6 = sr2 * sr2 * sr2;
+    e_nb += 4.0 * eps * (sr6 * sr6 - sr6) + s.one_4pi_eps0 * (double)s.exception_param[3 * i] * inv_r;
+  }
+  // NonbondedForce, CutoffNonPeriodic: LJ (Lorentz-Berthelot) truncated at the cutoff + Coulomb
+  // with reaction field  qq (1/r + k_rf r^2 - c_rf).
+  const bool use_cut = s.cutoff > 0;
+  const double rc = s.cutoff;
+  const double krf = use_cut ? (1.0 / (rc * rc * rc)) * (s.reaction_field_eps - 1.0) / (2.0 * s.reaction_field_eps + 1.0) : 0.0;
+  const double crf = use_cut ? (1.0 / rc) * (3.0 * s.reaction_field_eps) / (2.0 * s.reaction_field_eps + 1.0) : 0.0;
+  const int warp = tid >> 5, lane = tid & 31, nwarps = nt >> 5;
+  for (int i = warp; i < N; i += nwarps) {
+    const Vec3 pi = pos[i];
+    const double qi = (double)s.charge[i], si = (double)s.sigma[i], ei = (double)s.epsilon[i];
+    for (int j = i + 1 + lane; j < N; j += 32) {
+      if (s.excluded[(size_t)i * N + j]) continue;
+      Vec3 d = sub(pi, pos[j]);
+      double r2 = dot(d, d), r = sqrt(r2);
+      if (use_cut && r > rc) continue;
+      double sig = 0.5 * (si + (double)s.sigma[j]), eps = sqrt(ei * (double)s.epsilon[j]);
+      double sr2 = sig * sig / r2, sr6 = sr2 * sr2 * sr2;
+      e_nb += 4.0 * eps * (sr6 * sr6 - sr6) + s.one_4pi_eps0 * qi * (double)s.charge[j] * (1.0 / r + krf * r2 - crf);
+    }
+  }
+
+  if (s.use_gb) {
+    // ---- Born radii (ReferenceObc::computeBornRadii) ----
+    for (int i = warp; i < N; i += nwarps) {
+      const Vec3 pi = pos[i];
+      const double ri = (double)s.gb_radius[i], ori = ri - s.gb_offset;
+      double sum = 0;
+      for (int j = lane; j < N; j += 32) {
+        if (j == i) continue;
+        Vec3 d = sub(pi, pos[j]);
+        double r = sqrt(dot(d, d));
+        if (use_cut && r > rc) continue;
+        double srj = ((double)s.gb_radius[j] - s.gb_offset) * (double)s.gb_scale[j];
+        double rsr = r + srj;
+        if (ori < rsr) {
+          double rinv = 1.0 / r;
+          double adiff = fabs(r - srj);
+          double l_ij = 1.0 / (ori > adiff ? ori : adiff);
+          double u_ij = 1.0 / rsr;
+          double l2 = l_ij * l_ij, u2 = u_ij * u_ij;
+          double ratio = log(u_ij / l_ij);
+          double term = l_ij - u_ij + 0.25 * r * (u2 - l2) + 0.5 * rinv * ratio + 0.25 * srj * srj * rinv * (l2 - u2);
+          if (ori < (srj - r)) term += 2.0 * (1.0 / ori - l_ij);
+          sum += term;
+        }
+      }
+      sum = warp_sum_d(sum);
+      if (lane == 0) {
+        sum *= 0.5 * ori;
+        double s2 = sum * sum, s3 = sum * s2;
+        double th = tanh(s.gb_alpha * sum - s.gb_beta * s2 + s.gb_gamma * s3);
+        born[i] = 1.0 / (1.0 / ori - th / ri);
+      }
+    }
+    __syncthreads();
+    // ---- ACE surface-area term ----
+    if (s.surface_area_energy != 0.0) {
+      for (int i = tid; i < N; i += nt) {
+        if (born[i] > 0) {
+          double ri = (double)s.gb_radius[i], rr = ri + 0.14, q = ri / born[i];
+          double q2 = q * q;
+          e_gb += s.surface_area_energy * rr * rr * q2 * q2 * q2;
+        }
+      }
+    }
+    // ---- polarisation energy (ReferenceObc::computeBornEnergyForces), pairs j >= i ----
+    const double pre = (s.solute_dielectric != 0 && s.solvent_dielectric != 0)
+                           ? -s.one_4pi_eps0 * (1.0 / s.solute_dielectric - 1.0 / s.solvent_dielectric)
+                           : 0.0;
+    for (int i = warp; i < N; i += nwarps) {
+      const Vec3 pi = pos[i];
+      const double qi = pre * (double)s.charge[i], bi = born[i];
+      for (int j = i + lane; j < N; j += 32) {
+        Vec3 d = sub(pi, pos[j]);
+        double r2 = dot(d, d);
+        if (use_cut && r2 > rc * rc) continue;
+        double a2 = bi * born[j];
+        double den = sqrt(r2 + a2 * exp(-r2 / (4.0 * a2)));
+        double g = qi * (double)s.charge[j] / den;
+        if (j != i) {
+          if (use_cut) g -= qi * (double)s.charge[j] / rc;
+        } else {
+          g *= 0.5;
+        }
+        e_gb += g;
+      }
+    }
+  }
+
+  double v[5] = {e_bond, e_angle, e_tors, e_nb, e_gb};
+#pragma unroll
+  for (int k = 0; k < 5; k++) {
+    double t = warp_sum_d(v[k]);
+    if (lane == 0) red[warp][k] = t;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    double tot = 0, terms[5];
+    for (int k = 0; k < 5; k++) {
+      terms[k] = 0;
+      for (int w = 0; w < nwarps; w++) terms[k] += red[w][k];
+      tot += terms[k];
+      if (out_terms) out_terms[b * 5 + k] = (float)terms[k];
+    }
+    out_energy[b] = (float)tot;
+  }
+}
+
+}  // namespace tw
+
+using namespace tw;
+
+extern "C" int tw_peptide_energy(const tw_energy_system* sys, const float* coords, int64_t B, float* out_energy,
+                                 float* out_forces, float* out_terms, void* stream) {
+  TW_CHECK_ARG(sys && coords && out_energy, "NULL pointer");
+  TW_CHECK_ARG(sys->n_atoms >= 1 && sys->n_atoms <= 4096, "n_atoms out of range (1..4096)");
+  TW_CHECK_ARG(B >= 0 && B <= 2147483647LL, "bad batch size");
+  TW_CHECK_ARG(sys->n_bonds == 0 || (sys->bond_idx && sys->bond_param), "bond arrays missing");
+  TW_CHECK_ARG(sys->n_angles == 0 || (sys->angle_idx && sys->angle_param), "angle arrays missing");
+  TW_CHECK_ARG(sys->n_torsions == 0 || (sys->torsion_idx && sys->torsion_param), "torsion arrays missing");
+  TW_CHECK_ARG(sys->n_exceptions == 0 || (sys->exception_idx && sys->exception_param), "exception arrays missing");
+  TW_CHECK_ARG(sys->charge && sys->sigma && sys->epsilon && sys->excluded, "nonbonded arrays missing");
+  TW_CHECK_ARG(!sys->use_gb || (sys->gb_radius && sys->gb_scale), "GB arrays missing");
+  if (out_forces) return fail(TW_ERR_UNSUPPORTED, "forces are not implemented yet (SURVEY.md section 8f-1)");
+  if (B == 0) return TW_OK;
+  size_t smem = (size_t)sys->n_atoms * 4 * sizeof(double);
+  static bool attr_set = false;
+  if (smem > 48 * 1024 && !attr_set) {
+    TW_CUDA(cudaFuncSetAttribute(k_energy, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * 4 * (int)sizeof(double)));
+    attr_set = true;
+  }
+  {
+    ProfScope prof(PROF_ENERGY, (cudaStream_t)stream);
+    k_energy<<<(unsigned)B, ENERGY_THREADS, smem, (cudaStream_t)stream>>>(*sys, coords, out_energy, out_terms);
+  }
+  TW_LAUNCH_CHECK();
+  return TW_OK;
+}

@@ -1,0 +1,118 @@
+"""Potential-energy module with the call surface of the reference's OpenmmPotentialEnergyTorch
+(utils/openmm/openmm_bridge.py:252-307): `energy(coords[..., N, 3]) -> [B, 1]` in kJ/mol on the
+input's device/dtype, `.kbT`, `.num_particles`, `.get_integrator()`.  The arithmetic runs in the
+`tw_peptide_energy` CUDA kernel -- no OpenMM, no host round trip, no per-sample Python loop."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+import torch
+import torch.nn as nn
+from torch import Tensor
+
+from . import _lib
+from .forcefield import MOLAR_GAS_CONSTANT_R, SystemDescription
+
+
+class _Integrator:
+    """Stand-in for the openmm integrator object the reference passes around (only the temperature is used)."""
+
+    def __init__(self, temperature_kelvin: float):
+        self._t = float(temperature_kelvin)
+
+    def getTemperature(self) -> float:
+        return self._t
+
+
+class PeptidePotentialEnergy(nn.Module):
+    def __init__(self, system: SystemDescription, temperature: Optional[float] = None):
+        super().__init__()
+        self.system = system
+        self.num_particles = system.n_atoms
+        self._integrator = _Integrator(system.temperature if temperature is None else temperature)
+        self._dev_arrays = {}
+        self._struct: Optional[_lib.EnergySystem] = None
+        self._struct_device = None
+
+    def get_integrator(self):
+        return self._integrator
+
+    @property
+    def kbT(self) -> float:
+        """T * R in kJ/mol (openmm_bridge.py:299-307); 2.577483411627504 at 310 K."""
+        return self._integrator.getTemperature() * MOLAR_GAS_CONSTANT_R
+
+    def _build(self, device):
+        s = self.system
+        d = {}
+
+        def put(name, arr, dtype):
+            t = torch.as_tensor(np.ascontiguousarray(arr), dtype=dtype).to(device).contiguous()
+            d[name] = t
+            return t.data_ptr() if t.numel() else None
+
+        es = _lib.EnergySystem()
+        es.n_atoms = s.n_atoms
+        es.n_bonds = len(s.bond_idx)
+        es.bond_idx = put("bond_idx", s.bond_idx, torch.int32)
+        es.bond_param = put("bond_param", s.bond_param, torch.float32)
+        es.n_angles = len(s.angle_idx)
+        es.angle_idx = put("angle_idx", s.angle_idx, torch.int32)
+        es.angle_param = put("angle_param", s.angle_param, torch.float32)
+        es.n_torsions = len(s.torsion_idx)
+        es.torsion_idx = put("torsion_idx", s.torsion_idx, torch.int32)
+        es.torsion_param = put("torsion_param", s.torsion_param, torch.float32)
+        es.charge = put("charge", s.charge, torch.float32)
+        es.sigma = put("sigma", s.sigma, torch.float32)
+        es.epsilon = put("epsilon", s.epsilon, torch.float32)
+        es.excluded = put("excluded", s.excluded, torch.uint8)
+        es.n_exceptions = len(s.exception_idx)
+        es.exception_idx = put("exception_idx", s.exception_idx, torch.int32)
+        es.exception_param = put("exception_param", s.exception_param, torch.float32)
+        es.cutoff, es.reaction_field_eps, es.one_4pi_eps0 = s.cutoff, s.reaction_field_eps, s.one_4pi_eps0
+        es.use_gb = 1 if s.use_gb else 0
+        es.gb_radius = put("gb_radius", s.gb_radius, torch.float32)
+        es.gb_scale = put("gb_scale", s.gb_scale, torch.float32)
+        es.gb_alpha, es.gb_beta, es.gb_gamma, es.gb_offset = s.gb_alpha, s.gb_beta, s.gb_gamma, s.gb_offset
+        es.solute_dielectric, es.solvent_dielectric = s.solute_dielectric, s.solvent_dielectric
+        es.surface_area_energy = s.surface_area_energy
+        self._dev_arrays, self._struct, self._struct_device = d, es, device
+
+    def forward(self, coords: Tensor, return_terms: bool = False) -> Tensor:
+        assert coords.size(-1) == 3, f"last dimension is expected to be of size 3 but it is {coords.size(-1)}"
+        assert (
+            coords.size(-2) == self.num_particles
+        ), f"size {coords.size()} does not align with expected number of particles {self.num_particles}"
+        if coords.device.type != "cuda":
+            raise _lib.TimewarpB200Error(f"coords are on {coords.device}: the energy kernel runs on CUDA only (no CPU fallback)")
+        if coords.requires_grad:
+            raise NotImplementedError("forces / backward through the energy are not implemented yet (SURVEY.md section 8f-1)")
+        dev = coords.device
+        if self._struct is None or self._struct_device != dev:
+            self._build(dev)
+        x = coords.reshape(-1, self.num_particles, 3).to(torch.float32).contiguous()
+        B = x.shape[0]
+        out = torch.empty(B, dtype=torch.float32, device=dev)
+        terms = torch.empty(B, 5, dtype=torch.float32, device=dev) if return_terms else None
+        _lib.check(
+            _lib.load().tw_peptide_energy(C.byref(self._struct), _lib.ptr(x), B, _lib.ptr(out), None, _lib.ptr(terms),
+                                          torch.cuda.current_stream(dev).cuda_stream),
+            "tw_peptide_energy",
+        )
+        energy = out.to(coords.dtype).reshape(-1, 1)  # [B,1], input dtype/device (openmm_bridge.py:228)
+        return (energy, terms) if return_terms else energy
+
+
+class OpenmmPotentialEnergyTorch(PeptidePotentialEnergy):
+    """Constructor-compatible alias: OpenmmPotentialEnergyTorch(system, integrator, platform_name, ...)
+    (openmm_bridge.py:259-279) where `system` is a SystemDescription and `integrator` anything with
+    getTemperature() in kelvin.  platform_* arguments are accepted and ignored (the platform is the GPU)."""
+
+    def __init__(self, system, integrator=None, platform_name: str = "CUDA", platform_properties=None, bridge_kwargs=None):
+        t = None
+        if integrator is not None:
+            t = integrator.getTemperature()
+            t = float(getattr(t, "_value", t))
+        super().__init__(system, temperature=t)

@@ -1,0 +1,287 @@
+"""ConditionalFlowDensityModel -- the drop-in for the reference's density-model wrapper
+(modules/model_wrappers/flow.py:106-336, density_model_base.py:10-88) on top of the CUDA library.
+
+Same method names, keyword names, shapes, RNG consumption and state_dict keys as the reference;
+every flow pass is ONE call into libtimewarp_b200.so on the current CUDA stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import torch
+import torch.nn as nn
+from torch import BoolTensor, Tensor
+
+from . import _lib
+from .modules import ConditionalSequentialFlow
+
+
+def _require_cuda(name: str, t: Tensor, dtype=None) -> Tensor:
+    if not isinstance(t, Tensor):
+        raise TypeError(f"{name} must be a torch.Tensor")
+    if t.device.type != "cuda":
+        raise _lib.TimewarpB200Error(
+            f"{name} is on {t.device}: timewarp_b200 computes on CUDA (sm_100a) only -- there is no CPU fallback"
+        )
+    if dtype is not None and t.dtype != dtype:
+        raise TypeError(f"{name} must have dtype {dtype}, got {t.dtype}")
+    return t.contiguous()
+
+
+class ConditionalFlowDensityModel(nn.Module):
+    def __init__(
+        self,
+        flow: ConditionalSequentialFlow,
+        flow_config: _lib.FlowConfig,
+        use_displacement_as_target: bool = True,
+        scale_requires_grad: bool = True,
+        ignore_conditional_velocity: bool = False,
+    ):
+        super().__init__()
+        self.flow = flow
+        self.coords_prior_log_scale = nn.Parameter(torch.tensor(0.0), requires_grad=scale_requires_grad)
+        self.velocs_prior_log_scale = nn.Parameter(torch.tensor(0.0), requires_grad=scale_requires_grad)
+        self.ignore_conditional_velocity = ignore_conditional_velocity
+        self.use_displacement_as_target = use_displacement_as_target
+        self._cfg = flow_config
+        self._table = None  # (ctypes array, keep-alive list)
+        self._workspace: Optional[Tensor] = None
+
+    # ---------------------------------------------------------------- plumbing
+    @property
+    def precision(self) -> str:
+        return {v: k for k, v in _lib.PRECISION.items()}[self._cfg.precision]
+
+    def set_precision(self, precision: str) -> "ConditionalFlowDensityModel":
+        self._cfg.precision = _lib.PRECISION[precision]
+        return self
+
+    def _apply(self, fn, *a, **kw):  # .to()/.cuda()/.float() move the parameters: rebuild the pointer table
+        self._table = None
+        self._workspace = None
+        return super()._apply(fn, *a, **kw)
+
+    def load_state_dict(self, *a, **kw):
+        self._table = None
+        return super().load_state_dict(*a, **kw)
+
+    def _ordered_params(self):
+        """Tensors in the order of the C-ABI parameter table (include/timewarp_b200.h)."""
+        out = [self.flow.atom_embedder.weight, self.coords_prior_log_scale, self.velocs_prior_log_scale]
+        for layer in self.flow.chain:
+            for block in (layer.scale_transformer, layer.shift_transformer):
+                for lin in block.in_mlp.linears():
+                    out += [lin.weight, lin.bias]
+                for enc in block.encoder_layers:
+                    out += [
+                        enc.self_attn.values_proj.weight, enc.self_attn.attention.lengthscales,
+                        enc.self_attn.attention._out_projection.weight, enc.linear1.weight, enc.linear1.bias,
+                        enc.linear2.weight, enc.linear2.bias, enc.norm1.weight, enc.norm1.bias, enc.norm2.weight,
+                        enc.norm2.bias,
+                    ]  # fmt: skip
+                for lin in block.out_mlp.linears():
+                    out += [lin.weight, lin.bias]
+        return out
+
+    def _param_table(self, device):
+        if self._table is None or self._table[2] != device:
+            tensors = self._ordered_params()
+            lib = _lib.load()
+            n = lib.tw_flow_num_params(C.byref(self._cfg))
+            if n != len(tensors):
+                raise _lib.TimewarpB200Error(f"parameter table mismatch: library expects {n}, module has {len(tensors)}")
+            for t in tensors:
+                if t.device != device:
+                    raise _lib.TimewarpB200Error(
+                        f"model parameters are on {t.device} but inputs are on {device}; call model.to(device) first"
+                    )
+                if t.dtype != torch.float32 or not t.is_contiguous():
+                    raise TypeError("model parameters must be contiguous float32")
+            arr = (C.c_void_p * n)(*[t.data_ptr() for t in tensors])
+            self._table = (arr, tensors, device)
+        return self._table[0]
+
+    def _get_workspace(self, n: int, n_cond: int, V: int, device) -> Tuple[Tensor, int]:
+        lib = _lib.load()
+        need = C.c_size_t(0)
+        _lib.check(lib.tw_flow_workspace_bytes(C.byref(self._cfg), n, n_cond, V, C.byref(need)), "tw_flow_workspace_bytes")
+        if self._workspace is None or self._workspace.numel() < need.value or self._workspace.device != device:
+            self._workspace = torch.empty(need.value, dtype=torch.uint8, device=device)
+        return self._workspace, self._workspace.numel()
+
+    @staticmethod
+    def _stream(device) -> int:
+        return torch.cuda.current_stream(device).cuda_stream
+
+    def _flags(self) -> int:
+        return _lib.TW_FLOW_DISPLACEMENT_TARGET if self.use_displacement_as_target else 0
+
+    # ---------------------------------------------------------------- reference API
+    def forward(
+        self,
+        atom_types: Tensor,  # [B, V] int64
+        x_coords: Tensor,  # [B, V, 3]
+        x_velocs: Tensor,  # [B, V, 3]
+        y_coords: Tensor,  # [B, V, 3]
+        y_velocs: Tensor,  # [B, V, 3]
+        adj_list: Tensor,  # [E, 2] int64 (unused by this model, kept for the interface)
+        edge_batch_idx: Tensor,  # [E] int64 (unused)
+        masked_elements: BoolTensor,  # [B, V] True = padding
+        logger=None,
+    ) -> Tensor:
+        """Average negative log-likelihood per atom (density_model_base.py:14-47)."""
+        num_atoms = (~masked_elements).sum(dim=1)
+        log_likelihood = self.log_likelihood(
+            atom_types=atom_types, adj_list=adj_list, x_coords=x_coords, x_velocs=x_velocs, y_coords=y_coords,
+            y_velocs=y_velocs, edge_batch_idx=edge_batch_idx, masked_elements=masked_elements, logger=logger,
+        )  # fmt: skip
+        loss = -(log_likelihood / num_atoms).mean()
+        if logger is not None:
+            logger.log_scalar_async("nll_loss", loss)
+        return loss
+
+    def log_likelihood(
+        self, atom_types: Tensor, x_coords: Tensor, x_velocs: Tensor, y_coords: Tensor, y_velocs: Tensor,
+        adj_list: Tensor, edge_batch_idx: Tensor, masked_elements: BoolTensor, logger=None,
+    ) -> Tensor:  # fmt: skip
+        """log p(y | x) for each batch element (flow.py:131-215)."""
+        ll, _, _ = self._log_likelihood_impl(atom_types, x_coords, x_velocs, y_coords, y_velocs, masked_elements, False)
+        if logger is not None:  # flow.py:206-214 logs means of the pieces; only the total is materialised here
+            logger.log_scalar_async("log_prob_y", ll.mean())
+            logger.log_scalar_async("coord_std", torch.exp(self.coords_prior_log_scale.detach()))
+            logger.log_scalar_async("veloc_std", torch.exp(self.velocs_prior_log_scale.detach()))
+        return ll
+
+    def _log_likelihood_impl(self, atom_types, x_coords, x_velocs, y_coords, y_velocs, masked_elements, want_latent):
+        x_coords = _require_cuda("x_coords", x_coords, torch.float32)
+        dev = x_coords.device
+        B, V = x_coords.shape[0], x_coords.shape[1]
+        if x_coords.dim() != 3 or x_coords.shape[2] != 3:
+            raise ValueError(f"x_coords must be [B, V, 3], got {tuple(x_coords.shape)}")
+        x_velocs = _require_cuda("x_velocs", x_velocs, torch.float32)
+        y_coords = _require_cuda("y_coords", y_coords, torch.float32)
+        y_velocs = _require_cuda("y_velocs", y_velocs, torch.float32)
+        atom_types = _require_cuda("atom_types", atom_types, torch.int64)
+        mask = _require_cuda("masked_elements", masked_elements, torch.bool)
+        for name, t in (("x_velocs", x_velocs), ("y_coords", y_coords), ("y_velocs", y_velocs)):
+            if t.shape != x_coords.shape:
+                raise ValueError(f"{name} has shape {tuple(t.shape)}, expected {tuple(x_coords.shape)}")
+        if atom_types.shape != (B, V) or mask.shape != (B, V):
+            raise ValueError("atom_types / masked_elements must be [B, V]")
+        if self.ignore_conditional_velocity:  # flow.py:144-145
+            x_velocs = torch.zeros_like(x_velocs)
+        lib = _lib.load()
+        table = self._param_table(dev)
+        ws, ws_bytes = self._get_workspace(B, B, V, dev)
+        out = torch.empty(B, dtype=torch.float32, device=dev)
+        zc = torch.empty_like(x_coords) if want_latent else None
+        zv = torch.empty_like(x_coords) if want_latent else None
+        mask_u8 = mask.view(torch.uint8)
+        _lib.check(
+            lib.tw_flow_log_likelihood(
+                C.byref(self._cfg), table, _lib.ptr(atom_types), _lib.ptr(x_coords), _lib.ptr(x_velocs), _lib.ptr(y_coords),
+                _lib.ptr(y_velocs), _lib.ptr(mask_u8), B, V, self._flags(), _lib.ptr(out), _lib.ptr(zc), _lib.ptr(zv),
+                _lib.ptr(ws), ws_bytes, self._stream(dev),
+            ),
+            "tw_flow_log_likelihood",
+        )  # fmt: skip
+        return out, zc, zv
+
+    def conditional_sample(
+        self, atom_types: Tensor, x_coords: Tensor, x_velocs: Tensor, adj_list: Tensor, edge_batch_idx: Tensor,
+        masked_elements: BoolTensor, num_samples: int, logger=None,
+    ) -> Tuple[Tensor, Tensor]:  # fmt: skip
+        """Conditional samples y ~ p(.|x): ([S,B,V,3], [S,B,V,3])  (flow.py:217-240)."""
+        y_coords, y_velocs, _ = self._sample_impl(atom_types, x_coords, x_velocs, masked_elements, num_samples, None, None, False)
+        return y_coords, y_velocs
+
+    def conditional_sample_with_logp(
+        self, atom_types: Tensor, x_coords: Tensor, x_velocs: Tensor, adj_list: Tensor, edge_batch_idx: Tensor,
+        masked_elements: BoolTensor, num_samples: int, logger=None,
+    ) -> Tuple[Tensor, Tensor, Tensor]:  # fmt: skip
+        """Conditional samples and their log-density: (..., ..., [S,B])  (flow.py:242-336)."""
+        return self._sample_impl(atom_types, x_coords, x_velocs, masked_elements, num_samples, None, None, True)
+
+    def sample_from_latents(self, atom_types, x_coords, x_velocs, masked_elements, z_coords: Tensor, z_velocs: Tensor):
+        """Same as conditional_sample_with_logp but with the prior draws given ([S,B,V,3], already
+        scaled by exp(log_scale)) -- used by parity tests and by drivers that own the RNG."""
+        return self._sample_impl(atom_types, x_coords, x_velocs, masked_elements, z_coords.shape[0], z_coords, z_velocs, True)
+
+    def _sample_impl(self, atom_types, x_coords, x_velocs, masked_elements, num_samples, z_coords, z_velocs, want_logp):
+        x_coords = _require_cuda("x_coords", x_coords, torch.float32)
+        dev = x_coords.device
+        if x_coords.dim() != 3 or x_coords.shape[2] != 3:
+            raise ValueError(f"x_coords must be [B, V, 3], got {tuple(x_coords.shape)}")
+        B, V = x_coords.shape[0], x_coords.shape[1]
+        S = int(num_samples)
+        x_velocs = _require_cuda("x_velocs", x_velocs, torch.float32)
+        atom_types = _require_cuda("atom_types", atom_types, torch.int64)
+        mask = _require_cuda("masked_elements", masked_elements, torch.bool)
+        if x_velocs.shape != x_coords.shape or atom_types.shape != (B, V) or mask.shape != (B, V):
+            raise ValueError("inconsistent input shapes")
+        if want_logp and S > 1 and B > 1:
+            # the reference's prior-mask broadcast (flow.py:326-331) only works for S == 1 or B == 1
+            raise ValueError("conditional_sample_with_logp requires num_samples == 1 or batch size == 1 (flow.py:326-331)")
+        if self.ignore_conditional_velocity:
+            x_velocs = torch.zeros_like(x_velocs)
+        if z_coords is None:
+            # RNG contract (flow.py:274-275): two normal_() draws [S,B,V,3] from the device's default
+            # generator, coords first, each scaled by exp(log_scale).
+            z_coords = torch.empty(S, B, V, 3, dtype=torch.float32, device=dev).normal_() * torch.exp(self.coords_prior_log_scale.detach())
+            z_velocs = torch.empty(S, B, V, 3, dtype=torch.float32, device=dev).normal_() * torch.exp(self.velocs_prior_log_scale.detach())
+        else:
+            z_coords = _require_cuda("z_coords", z_coords, torch.float32)
+            z_velocs = _require_cuda("z_velocs", z_velocs, torch.float32)
+            if z_coords.shape != (S, B, V, 3) or z_velocs.shape != (S, B, V, 3):
+                raise ValueError("latents must be [S, B, V, 3]")
+        lib = _lib.load()
+        table = self._param_table(dev)
+        ws, ws_bytes = self._get_workspace(S * B, B, V, dev)
+        y_coords = torch.empty(S, B, V, 3, dtype=torch.float32, device=dev)
+        y_velocs = torch.empty(S, B, V, 3, dtype=torch.float32, device=dev)
+        logp = torch.empty(S, B, dtype=torch.float32, device=dev) if want_logp else None
+        mask_u8 = mask.view(torch.uint8)
+        _lib.check(
+            lib.tw_flow_sample(
+                C.byref(self._cfg), table, _lib.ptr(atom_types), _lib.ptr(x_coords), _lib.ptr(x_velocs), _lib.ptr(mask_u8),
+                B, V, S, self._flags(), _lib.ptr(z_coords), _lib.ptr(z_velocs), _lib.ptr(y_coords), _lib.ptr(y_velocs),
+                _lib.ptr(logp), _lib.ptr(ws), ws_bytes, self._stream(dev),
+            ),
+            "tw_flow_sample",
+        )  # fmt: skip
+        return y_coords, y_velocs, logp
+
+    # ---------------------------------------------------------------- test / debug hooks
+    def attention_scores(self, x_coords_centred: Tensor, masked_elements: Tensor) -> Tensor:
+        """compute_kernel_attention_scores (kernel_attention.py:69-121) -> [B,H,V,V]."""
+        x = _require_cuda("x_coords", x_coords_centred, torch.float32)
+        mask = _require_cuda("masked_elements", masked_elements, torch.bool).view(torch.uint8)
+        ls = self.flow.chain[0].scale_transformer.encoder_layers[0].self_attn.attention.lengthscales
+        B, V = x.shape[:2]
+        out = torch.empty(B, ls.numel(), V, V, dtype=torch.float32, device=x.device)
+        _lib.check(
+            _lib.load().tw_attn_scores(_lib.ptr(x), _lib.ptr(mask), _lib.ptr(ls), B, V, ls.numel(), _lib.ptr(out), self._stream(x.device)),
+            "tw_attn_scores",
+        )
+        return out
+
+    def scale_and_shift(self, layer_idx, atom_types, z_coords, z_velocs, x_coords_centred, x_velocs, masked_elements):
+        """NVPCouplingLayer._get_scale_and_shift of one coupling layer (custom_transformer_nvp.py:44-93)."""
+        x = _require_cuda("x_coords", x_coords_centred, torch.float32)
+        dev = x.device
+        B, V = x.shape[:2]
+        args = [_require_cuda(n, t, torch.float32) for n, t in (("x_velocs", x_velocs), ("z_coords", z_coords), ("z_velocs", z_velocs))]
+        at = _require_cuda("atom_types", atom_types, torch.int64)
+        mask = _require_cuda("masked_elements", masked_elements, torch.bool).view(torch.uint8)
+        ws, ws_bytes = self._get_workspace(B, B, V, dev)
+        scale, shift = torch.empty_like(x), torch.empty_like(x)
+        _lib.check(
+            _lib.load().tw_flow_scale_shift(
+                C.byref(self._cfg), self._param_table(dev), int(layer_idx), _lib.ptr(at), _lib.ptr(x), _lib.ptr(args[0]),
+                _lib.ptr(args[1]), _lib.ptr(args[2]), _lib.ptr(mask), B, V, _lib.ptr(scale), _lib.ptr(shift), _lib.ptr(ws),
+                ws_bytes, self._stream(dev),
+            ),
+            "tw_flow_scale_shift",
+        )  # fmt: skip
+        return scale, shift

@@ -1,0 +1,235 @@
+"""System description for the energy kernel (replaces the `openmm.System` the reference builds in
+simulation/md.py:128-187 -- OpenMM and the Amber XML parameter files do not exist offline).
+
+`SystemDescription` is the wire format of SURVEY.md Appendix B: bonded term lists, per-atom
+nonbonded / GB parameters, exclusion matrix, 1-4 exceptions and the scalar settings of the
+reference presets (CutoffNonPeriodic 2.0 nm, reaction-field eps 1 with GB, OBC1/OBC2).
+
+`amber_like_system()` derives angles / torsions / exclusions from a bond graph and assigns
+GENERIC Amber-magnitude parameters by element and hybridisation.  It is a SYNTHETIC force field
+(parameters are not ff99SB-ILDN / ff14SB; the reference's golden energies cannot be reproduced
+with it) -- it gives the kernel a realistic workload with the right term counts.  Real parameter
+sets can be supplied by filling a SystemDescription directly.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Dict, List, Tuple
+
+import numpy as np
+
+MOLAR_GAS_CONSTANT_R = 8.31446261815324e-3  # kJ/mol/K (openmm.unit.MOLAR_GAS_CONSTANT_R)
+ONE_4PI_EPS0 = 138.935456  # OpenMM 7.7 SimTKOpenMMRealType.h
+
+GB_PRESETS = {
+    # simulation/md.py:152 ("amber99sbildn.xml","amber99_obc.xml") -> OBC2 ; :159 ("implicit/obc1.xml") -> OBC1
+    "obc2": dict(alpha=1.0, beta=0.8, gamma=4.85),
+    "obc1": dict(alpha=0.8, beta=0.0, gamma=2.909125),
+}
+
+
+@dataclass
+class SystemDescription:
+    n_atoms: int
+    bond_idx: np.ndarray  # [nb,2] int32
+    bond_param: np.ndarray  # [nb,2] r0, k
+    angle_idx: np.ndarray  # [na,3]
+    angle_param: np.ndarray  # [na,2] theta0, k
+    torsion_idx: np.ndarray  # [nt,4]
+    torsion_param: np.ndarray  # [nt,3] periodicity, phase, k
+    charge: np.ndarray  # [N]
+    sigma: np.ndarray  # [N]
+    epsilon: np.ndarray  # [N]
+    excluded: np.ndarray  # [N,N] uint8
+    exception_idx: np.ndarray  # [ne,2]
+    exception_param: np.ndarray  # [ne,3] chargeProd, sigma, epsilon
+    gb_radius: np.ndarray  # [N]
+    gb_scale: np.ndarray  # [N]
+    masses: np.ndarray  # [N] dalton
+    cutoff: float = 2.0
+    reaction_field_eps: float = 1.0
+    one_4pi_eps0: float = ONE_4PI_EPS0
+    use_gb: bool = True
+    gb_alpha: float = 1.0
+    gb_beta: float = 0.8
+    gb_gamma: float = 4.85
+    gb_offset: float = 0.009
+    solute_dielectric: float = 1.0
+    solvent_dielectric: float = 78.5
+    surface_area_energy: float = 28.3919551
+    temperature: float = 310.0  # simulation/md.py:78,86
+
+    def getNumParticles(self) -> int:  # openmm.System API used by the reference (openmm_bridge.py:277)
+        return self.n_atoms
+
+    def getParticleMass(self, i: int) -> float:
+        return float(self.masses[i])
+
+    def as_float32(self) -> "SystemDescription":
+        """Round every parameter to fp32 (what the kernel reads) so that an fp64 oracle fed with the
+        same description sees identical parameters."""
+        import copy
+
+        s = copy.copy(self)
+        for k in ("bond_param", "angle_param", "torsion_param", "charge", "sigma", "epsilon", "exception_param", "gb_radius", "gb_scale"):
+            setattr(s, k, getattr(self, k).astype(np.float32).astype(np.float64))
+        return s
+
+
+def _neighbors(n: int, bonds: np.ndarray) -> List[List[int]]:
+    nb: List[List[int]] = [[] for _ in range(n)]
+    for a, b in bonds:
+        nb[int(a)].append(int(b))
+        nb[int(b)].append(int(a))
+    return [sorted(x) for x in nb]
+
+
+def derive_angles(n: int, bonds: np.ndarray) -> np.ndarray:
+    nb = _neighbors(n, bonds)
+    out = []
+    for j in range(n):
+        for a in range(len(nb[j])):
+            for b in range(a + 1, len(nb[j])):
+                out.append((nb[j][a], j, nb[j][b]))
+    return np.array(out, dtype=np.int32).reshape(-1, 3)
+
+
+def derive_proper_torsions(n: int, bonds: np.ndarray) -> np.ndarray:
+    nb = _neighbors(n, bonds)
+    out = []
+    for j, k in bonds:
+        j, k = int(j), int(k)
+        for i in nb[j]:
+            if i == k:
+                continue
+            for l in nb[k]:
+                if l == j or l == i:
+                    continue
+                out.append((i, j, k, l))
+    return np.array(out, dtype=np.int32).reshape(-1, 4)
+
+
+def amber_like_system(peptide, gb: str = "obc2", total_charge: float = 0.0) -> SystemDescription:
+    """Synthetic Amber-magnitude parameters for a Peptide (timewarp_b200.peptides)."""
+    n = peptide.num_atoms
+    el = peptide.elements
+    bonds = np.asarray(peptide.bonds, dtype=np.int32)
+    nb = _neighbors(n, bonds)
+    deg = [len(x) for x in nb]
+
+    def is_carbonyl_c(i):
+        return el[i] == "C" and deg[i] == 3 and any(el[j] == "O" for j in nb[i])
+
+    # ---- bonds
+    bp = []
+    for a, b in bonds:
+        pair = "".join(sorted((el[a], el[b])))
+        if pair == "CH":
+            r0, k = 0.1090, 284512.0
+        elif pair == "HN":
+            r0, k = 0.1010, 363171.2
+        elif pair == "CC":
+            r0, k = (0.1522, 265265.6) if (is_carbonyl_c(a) or is_carbonyl_c(b)) else (0.1526, 259408.0)
+        elif pair == "CN":
+            r0, k = (0.1335, 410032.0) if (is_carbonyl_c(a) or is_carbonyl_c(b)) else (0.1449, 282001.6)
+        elif pair == "CO":
+            c = a if el[a] == "C" else b
+            n_o = sum(1 for j in nb[c] if el[j] == "O")
+            r0, k = (0.1250, 548940.8) if n_o == 2 else (0.1229, 476976.0)
+        elif pair == "CS":
+            r0, k = 0.1810, 189953.6
+        elif pair == "HS":
+            r0, k = 0.1336, 229283.2
+        else:
+            r0, k = 0.15, 250000.0
+        bp.append((r0, k))
+    # ---- angles
+    angles = derive_angles(n, bonds)
+    ap = []
+    for i, j, k in angles:
+        theta0 = math.radians(109.5 if deg[j] == 4 else (120.0 if deg[j] == 3 else 109.5))
+        n_h = (el[i] == "H") + (el[k] == "H")
+        kk = 292.88 if n_h == 2 else (418.4 if n_h == 1 else 585.76)
+        ap.append((theta0, kk))
+    # ---- torsions: generic X-sp3-sp3-X 3-fold, X-sp2-sp2-X (amide) 2-fold, plus sp2 impropers
+    torsions = derive_proper_torsions(n, bonds)
+    tp = []
+    for i, j, k, l in torsions:
+        n_paths = (deg[j] - 1) * (deg[k] - 1)
+        if deg[j] == 3 and deg[k] == 3:
+            tp.append((2.0, math.pi, 41.84 / n_paths))
+        elif deg[j] == 4 and deg[k] == 4:
+            tp.append((3.0, 0.0, 5.858 / n_paths))
+        else:
+            tp.append((3.0 if deg[j] == 4 or deg[k] == 4 else 2.0, 0.0 if (deg[j] == 4 or deg[k] == 4) else math.pi, 1.0))
+    tors_list = [tuple(t) for t in torsions]
+    for c in range(n):
+        if deg[c] == 3 and el[c] in ("C", "N"):
+            a, b, d = nb[c]
+            tors_list.append((a, b, c, d))  # Amber improper: central atom third
+            tp.append((2.0, math.pi, 43.932 if is_carbonyl_c(c) else 4.6024))
+    torsions = np.array(tors_list, dtype=np.int32).reshape(-1, 4)
+    # ---- per-atom nonbonded
+    q = np.zeros(n)
+    sig = np.zeros(n)
+    eps = np.zeros(n)
+    rad = np.zeros(n)
+    scl = np.zeros(n)
+    for i in range(n):
+        e = el[i]
+        heavy = [j for j in nb[i]]
+        if e == "H":
+            parent = el[heavy[0]] if heavy else "C"
+            if parent == "N":
+                q[i], sig[i], eps[i], rad[i] = 0.30, 0.106908, 0.0656888, 0.13
+            elif parent == "O" or parent == "S":
+                q[i], sig[i], eps[i], rad[i] = 0.40, 0.0, 0.0, 0.12
+            else:
+                q[i], sig[i], eps[i], rad[i] = 0.08, 0.247135, 0.0656888, 0.12
+            scl[i] = 0.85
+        elif e == "C":
+            if is_carbonyl_c(i):
+                q[i], sig[i], eps[i] = 0.60, 0.339967, 0.359824
+            else:
+                q[i], sig[i], eps[i] = -0.05 - 0.04 * sum(1 for j in nb[i] if el[j] == "H"), 0.339967, 0.457730
+            rad[i], scl[i] = 0.17, 0.72
+        elif e == "N":
+            q[i], sig[i], eps[i], rad[i], scl[i] = -0.45 if deg[i] == 3 else -0.15, 0.325000, 0.711280, 0.155, 0.79
+        elif e == "O":
+            q[i], sig[i], eps[i], rad[i], scl[i] = -0.57, 0.295992, 0.878640, 0.15, 0.85
+        else:  # S
+            q[i], sig[i], eps[i], rad[i], scl[i] = -0.11, 0.356359, 1.046000, 0.18, 0.96
+    q += (total_charge - q.sum()) / n  # neutralise (or set the net charge) uniformly
+    # ---- exclusions (1-2, 1-3) and 1-4 exceptions (Coulomb / 1.2, LJ epsilon / 2)
+    excl = np.zeros((n, n), dtype=np.uint8)
+    np.fill_diagonal(excl, 1)
+    for a, b in bonds:
+        excl[a, b] = excl[b, a] = 1
+    for i, j, k in angles:
+        excl[i, k] = excl[k, i] = 1
+    ex_pairs: Dict[Tuple[int, int], None] = {}
+    for i, j, k, l in derive_proper_torsions(n, bonds):
+        a, b = (int(i), int(l)) if i < l else (int(l), int(i))
+        if not excl[a, b]:
+            ex_pairs[(a, b)] = None
+    ex_idx = np.array(sorted(ex_pairs), dtype=np.int32).reshape(-1, 2)
+    for a, b in ex_idx:
+        excl[a, b] = excl[b, a] = 1
+    ex_par = np.array(
+        [(q[a] * q[b] / 1.2, 0.5 * (sig[a] + sig[b]), 0.5 * math.sqrt(eps[a] * eps[b])) for a, b in ex_idx], dtype=np.float64
+    ).reshape(-1, 3)
+    g = GB_PRESETS[gb]
+    return SystemDescription(
+        n_atoms=n,
+        bond_idx=bonds.astype(np.int32),
+        bond_param=np.array(bp, dtype=np.float64).reshape(-1, 2),
+        angle_idx=angles,
+        angle_param=np.array(ap, dtype=np.float64).reshape(-1, 2),
+        torsion_idx=torsions,
+        torsion_param=np.array(tp, dtype=np.float64).reshape(-1, 3),
+        charge=q, sigma=sig, epsilon=eps, excluded=excl,
+        exception_idx=ex_idx, exception_param=ex_par,
+        gb_radius=rad, gb_scale=scl, masses=np.asarray(peptide.masses, dtype=np.float64),
+        gb_alpha=g["alpha"], gb_beta=g["beta"], gb_gamma=g["gamma"],
+    )  # fmt: skip

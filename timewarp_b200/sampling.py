@@ -1,0 +1,320 @@
+"""Sampling drivers on top of the CUDA flow + energy kernels.
+
+* `sample_with_model`  -- the reference's MH chain (utils/evaluation_utils.py:468-745): ONE chain,
+  S parallel proposals per iteration, first-accept truncation, optional adaptive S.  Same argument
+  names, same return tuple `(sampled_coords, sampled_velocs, accepted, ChainStats)`.
+* `MHChains`           -- B independent chains, one proposal per chain per step, everything on the
+  device (no host sync in the loop; the BASELINE "1024 parallel chains" workload).
+* `explore`            -- exploration.py:124-138,229-250: energy-threshold acceptance + chirality veto.
+
+The OpenMM-integrator options of the reference (`openmm_on_current/proposal`, `sim`) are not
+available (no OpenMM) and raise if requested.
+"""
+from __future__ import annotations
+
+import math
+import pickle
+from dataclasses import astuple, dataclass
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+from torch import Tensor
+
+from . import _lib
+from .chirality import check_symmetry_change
+
+
+def compute_num_proposal_steps(current_acceptance_probability: float, target_acceptance_per_step: float = 0.9,
+                               max_num_proposal_steps: int = 100) -> int:
+    """utils/evaluation_utils.py:32-64."""
+    p_rej = min(max(1 - current_acceptance_probability, 1e-3), 1 - 1e-3)
+    with np.errstate(all="ignore"):
+        steps = np.nan_to_num(np.log(1 - target_acceptance_per_step) / np.log(p_rej), nan=np.inf)
+    return max(int(np.ceil(min(steps, max_num_proposal_steps))), 1)
+
+
+@dataclass
+class ChainStats:
+    """utils/evaluation_utils.py:67-114 (same fields, same pickle round trip)."""
+
+    acceptance_indicator: np.ndarray
+    acceptance: np.ndarray
+    p_xy: np.ndarray
+    p_yx: np.ndarray
+    exponent: np.ndarray
+    energies_pot: np.ndarray
+    energies_kin: np.ndarray
+    energies_pot_delta: np.ndarray
+    energies_kin_delta: np.ndarray
+
+    def __len__(self):
+        return len(self.acceptance)
+
+    def __getitem__(self, key):
+        return ChainStats(*map(lambda x: x[key], astuple(self)))
+
+    def thin(self, step):
+        return ChainStats(*map(lambda x: x[0 : x.shape[0] : step], astuple(self)))
+
+    def save(self, path):
+        with open(path, "wb") as f:
+            pickle.dump(self, f)
+
+    @staticmethod
+    def load(path):
+        with open(path, "rb") as f:
+            return pickle.load(f)
+
+
+def _stream(dev) -> int:
+    return torch.cuda.current_stream(dev).cuda_stream
+
+
+def compute_kinetic_energy(velocs: Tensor, masses: Optional[Tensor], random_velocs: bool = False, kbT: Optional[float] = None) -> Tensor:
+    """utils/evaluation_utils.py:416-436 -> [B]."""
+    v = velocs.to(torch.float32).contiguous()
+    B, V = v.shape[:2]
+    out = torch.empty(B, dtype=torch.float32, device=v.device)
+    if random_velocs:
+        m, inv = None, 0.0
+    else:
+        assert kbT, "Requires kbT to compute energy"
+        m, inv = masses.to(device=v.device, dtype=torch.float32).contiguous(), 1.0 / kbT
+    _lib.check(_lib.load().tw_kinetic_energy(_lib.ptr(v), _lib.ptr(m), inv, B, V, _lib.ptr(out), _stream(v.device)), "tw_kinetic_energy")
+    return out
+
+
+def mh_accept(e_pot_x, e_pot_y, e_kin_x, e_kin_y, p_xy, p_yx, u, x_coords=None, x_velocs=None, y_coords=None, y_velocs=None,
+              want_first=False):
+    """Device-side MH decision (utils/evaluation_utils.py:663-689).  Returns (exponent, p_acc, accepted[uint8], first_idx|None)."""
+    n = u.shape[0]
+    dev = u.device
+    V = y_coords.shape[-2] if y_coords is not None else 1
+    ex = torch.empty(n, dtype=torch.float32, device=dev)
+    pa = torch.empty(n, dtype=torch.float32, device=dev)
+    acc = torch.empty(n, dtype=torch.uint8, device=dev)
+    first = torch.empty(1, dtype=torch.int32, device=dev) if want_first else None
+    f = lambda t: _lib.ptr(t.to(torch.float32).contiguous()) if t is not None else None  # noqa: E731
+    for t in (x_coords, x_velocs):
+        assert t is None or (t.is_contiguous() and t.dtype == torch.float32)
+    _lib.check(
+        _lib.load().tw_mh_accept(f(e_pot_x), f(e_pot_y), f(e_kin_x), f(e_kin_y), f(p_xy), f(p_yx), f(u), n, V,
+                                 _lib.ptr(x_coords), _lib.ptr(x_velocs), f(y_coords), f(y_velocs), _lib.ptr(ex), _lib.ptr(pa),
+                                 _lib.ptr(acc), _lib.ptr(first), _stream(dev)),
+        "tw_mh_accept",
+    )
+    return ex, pa, acc, first
+
+
+class MHChains:
+    """B independent Metropolis-Hastings chains advanced in lock-step on one GPU.
+
+    One `step()` = the body of the reference loop (utils/evaluation_utils.py:589-665) with
+    num_proposal_steps == 1 applied to every chain: resample velocities, propose through the flow
+    (reverse pass), evaluate potential/kinetic energies and the reverse-move density (forward
+    pass), accept/reject.  The potential energy of the current state is carried between steps
+    (the reference re-evaluates it every iteration, :628 -- same value).  Nothing in `step()`
+    synchronises with the host."""
+
+    def __init__(self, model, energy, atom_types: Tensor, masked_elements: Tensor, x_coords: Tensor, x_velocs: Optional[Tensor] = None,
+                 masses: Optional[Tensor] = None, random_velocs: bool = True, resample_velocs: bool = True,
+                 chirality_centers: Optional[Tensor] = None, reference_signs: Optional[Tensor] = None, accept: bool = True):
+        assert x_coords.device.type == "cuda", "MHChains runs on CUDA only"
+        self.model, self.energy = model, energy
+        self.B, self.V = x_coords.shape[:2]
+        self.atom_types = atom_types.contiguous()
+        self.mask = masked_elements.contiguous()
+        self.x = x_coords.to(torch.float32).clone().contiguous()
+        self.random_velocs, self.resample_velocs, self.accept = random_velocs, resample_velocs, accept
+        self.xv = torch.randn_like(self.x) if (random_velocs or x_velocs is None) else x_velocs.to(torch.float32).clone().contiguous()
+        self.masses = masses
+        self.kbT = float(energy.kbT)
+        self.centers, self.ref_signs = chirality_centers, reference_signs
+        self.e_pot_x = (energy(self.x) / self.kbT).squeeze(-1).contiguous()
+        dev = self.x.device
+        self.n_accepted = torch.zeros(self.B, dtype=torch.int64, device=dev)
+        self.n_steps = 0
+        self.last = {}
+        self._empty_adj = torch.zeros(0, 2, dtype=torch.long, device=dev)
+        self._empty_ebi = torch.zeros(0, dtype=torch.long, device=dev)
+
+    def step(self):
+        m = self.model
+        if self.random_velocs and self.resample_velocs:
+            self.xv = torch.randn_like(self.xv)  # :590-592
+        y, yv, p_xy = m.conditional_sample_with_logp(
+            atom_types=self.atom_types, x_coords=self.x, x_velocs=self.xv, adj_list=self._empty_adj,
+            edge_batch_idx=self._empty_ebi, masked_elements=self.mask, num_samples=1)  # :609-617
+        y, yv, p_xy = y[0], yv[0], p_xy[0]
+        e_kin_x = compute_kinetic_energy(self.xv, self.masses, self.random_velocs, self.kbT)  # :629
+        e_kin_y = compute_kinetic_energy(yv, self.masses, self.random_velocs, self.kbT)  # :632
+        e_pot_y = (self.energy(y) / self.kbT).squeeze(-1)  # :635
+        if self.centers is not None and self.ref_signs is not None:
+            e_pot_y = e_pot_y + 2000.0 * check_symmetry_change(y, self.centers, self.ref_signs)  # :638-642
+        sgn = 1.0 if self.random_velocs else -1.0  # :651-653
+        p_yx = m.log_likelihood(
+            atom_types=self.atom_types, y_coords=self.x, y_velocs=sgn * self.xv, x_coords=y, x_velocs=sgn * yv,
+            adj_list=self._empty_adj, edge_batch_idx=self._empty_ebi, masked_elements=self.mask)  # :648-657
+        u = torch.rand(self.B, device=self.x.device)  # :668
+        if self.accept:
+            ex, pa, acc, _ = mh_accept(self.e_pot_x, e_pot_y, e_kin_x, e_kin_y, p_xy, p_yx, u, self.x, self.xv, y, yv)
+            accb = acc.view(torch.bool)
+            self.e_pot_x = torch.where(accb, e_pot_y, self.e_pot_x)
+        else:  # accept everything (:698-705)
+            ex, pa, acc, _ = mh_accept(self.e_pot_x, e_pot_y, e_kin_x, e_kin_y, p_xy, p_yx, u)
+            self.x, self.xv, self.e_pot_x = y.contiguous(), yv.contiguous(), e_pot_y
+            accb = torch.ones_like(acc, dtype=torch.bool)
+        self.n_accepted += accb
+        self.n_steps += 1
+        self.last = dict(exponent=ex, acceptance=pa, accepted=accb, p_xy=p_xy, p_yx=p_yx, e_pot_y=e_pot_y, e_kin_y=e_kin_y)
+        return accb
+
+    def acceptance_rate(self) -> Tensor:
+        return self.n_accepted.to(torch.float32) / max(self.n_steps, 1)
+
+
+@torch.no_grad()
+def sample_with_model(batch, model, device, openmm_potential_energy_torch, masses: Tensor, num_samples: int, accept: bool = False,
+                      random_velocs: bool = False, resample_velocs: bool = False, initialize_randomly: bool = False,
+                      num_openmm_steps: int = 0, sim=None, openmm_on_proposal: bool = False, openmm_on_current: bool = False,
+                      num_proposal_steps: int = 1, adaptive_parallelism: bool = False, acceptance_rate_smoothing_factor: float = 0.01,
+                      rotate: bool = False, reference_signs: Optional[Tensor] = None, chirality_centers: Optional[Tensor] = None,
+                      disable_tqdm: Optional[bool] = True):
+    """The reference MH sampler, utils/evaluation_utils.py:468-745 (line numbers cited inline).
+    One 4-byte device->host read per iteration (the first accepted index) is inherent to the
+    reference's variable-length bookkeeping; everything else stays on the device."""
+    assert batch.atom_coords.size(0) == 1, "only batch-size of 1 is supported"  # :517
+    if (openmm_on_current or openmm_on_proposal) and num_openmm_steps > 0 and sim is not None:
+        raise NotImplementedError("OpenMM integrator steps inside the chain are not available (no OpenMM; SURVEY.md section 8f-2)")
+    energy = openmm_potential_energy_torch
+    x_coords = batch.atom_coords.to(device).to(torch.float32).contiguous()
+    x_velocs = torch.randn_like(x_coords) if random_velocs else batch.atom_velocs.to(device).to(torch.float32).contiguous()  # :530-533
+    masked_elements = batch.masked_elements.to(device)
+    adj_list = batch.adj_list.to(device)
+    edge_batch_idx = batch.edge_batch_idx.to(device)
+    atom_types = batch.atom_types.to(device)
+    masses = masses.to(device) if masses is not None else None
+    if initialize_randomly:  # :540-553
+        x_coords, x_velocs = model.conditional_sample(
+            atom_types=atom_types, x_coords=torch.randn_like(x_coords), x_velocs=torch.randn_like(x_velocs), adj_list=adj_list,
+            edge_batch_idx=edge_batch_idx, masked_elements=masked_elements, num_samples=1)
+        x_coords, x_velocs = x_coords.squeeze(0), x_velocs.squeeze(0)
+    kbT = energy.kbT  # :555
+    sampled_coords = [x_coords.cpu().numpy()]
+    sampled_velocs = [x_velocs.cpu().numpy()]
+    accepted = 0
+    current_acceptance_probability = 1e-3  # :574
+    max_num_proposal_steps = num_proposal_steps
+    if adaptive_parallelism:
+        num_proposal_steps = compute_num_proposal_steps(current_acceptance_probability, max_num_proposal_steps=max_num_proposal_steps)
+    stats = {k: [] for k in ("acceptance_indicator", "acceptance", "p_xy", "p_yx", "exponent", "energies_pot", "energies_kin",
+                             "energies_pot_delta", "energies_kin_delta")}
+    i = 0
+    while i < num_samples:  # :589
+        S = num_proposal_steps
+        if random_velocs and resample_velocs:
+            x_velocs = torch.randn_like(x_velocs)  # :590-592
+        if rotate:  # :604-607
+            raise NotImplementedError("rotate=True needs the reference's random_rotation_matrix (equivariance/, out of scope)")
+        y_coords, y_velocs, p_xy = model.conditional_sample_with_logp(
+            atom_types=atom_types, x_coords=x_coords, x_velocs=x_velocs, adj_list=adj_list, edge_batch_idx=edge_batch_idx,
+            masked_elements=masked_elements, num_samples=S)  # :609-617
+        y_coords, y_velocs = y_coords.squeeze(1).contiguous(), y_velocs.squeeze(1).contiguous()
+        x_rep, xv_rep = x_coords.repeat(S, 1, 1), x_velocs.repeat(S, 1, 1)  # :620-621
+        e_pot_x = (energy(x_coords) / kbT).squeeze(-1).repeat(S)  # :628 (S identical evaluations in the reference)
+        e_kin_x = compute_kinetic_energy(xv_rep, masses, random_velocs=random_velocs, kbT=kbT)
+        e_kin_y = compute_kinetic_energy(y_velocs, masses, random_velocs=random_velocs, kbT=kbT)
+        e_pot_y = (energy(y_coords) / kbT).squeeze(-1)  # :635
+        if chirality_centers is not None and reference_signs is not None:
+            e_pot_y = e_pot_y + 2000.0 * check_symmetry_change(y_coords, chirality_centers, reference_signs)  # :638-642
+        sgn = 1.0 if random_velocs else -1.0
+        p_yx = model.log_likelihood(
+            atom_types=atom_types.repeat(S, 1), y_coords=x_rep, y_velocs=sgn * xv_rep, x_coords=y_coords, x_velocs=sgn * y_velocs,
+            adj_list=adj_list, edge_batch_idx=edge_batch_idx, masked_elements=masked_elements.repeat(S, 1))  # :648-657
+        p_xy = p_xy.reshape(p_yx.shape)
+        if accept:
+            u = torch.rand(S, device=device)  # :668
+            exp_, p_acc, acc, first = mh_accept(e_pot_x, e_pot_y, e_kin_x, e_kin_y, p_xy, p_yx, u, want_first=True)
+            first_idx = int(first.item())  # the reference's .cpu() at :674
+            did_not_accept = first_idx < 0
+            if did_not_accept:
+                first_acc_idx = S - 1  # :671-672
+            else:
+                first_acc_idx = first_idx
+                x_rep[first_acc_idx] = y_coords[first_acc_idx]  # :675-676
+                xv_rep[first_acc_idx] = y_velocs[first_acc_idx]
+                accepted += 1
+            first_acc_idx = min(first_acc_idx, num_samples - i)  # :681
+            stats["acceptance_indicator"].append(acc[: first_acc_idx + 1].view(torch.bool).cpu().numpy())
+            current_acceptance_probability = (
+                acceptance_rate_smoothing_factor * (1 - did_not_accept)
+                + (1 - acceptance_rate_smoothing_factor) ** first_acc_idx * current_acceptance_probability)  # :686-690
+            if adaptive_parallelism:
+                num_proposal_steps = compute_num_proposal_steps(current_acceptance_probability, max_num_proposal_steps=max_num_proposal_steps)
+        elif S == 1:  # :698-705
+            u = torch.zeros(S, device=device)
+            exp_, p_acc, acc, _ = mh_accept(e_pot_x, e_pot_y, e_kin_x, e_kin_y, p_xy, p_yx, u)
+            x_rep, xv_rep = y_coords, y_velocs
+            accepted += 1
+            first_acc_idx = 0
+            stats["acceptance_indicator"].append(np.array([True]))
+        else:
+            raise ValueError("Number of proposals has to be one if everything is accepted!")  # :707
+        sampled_coords.append(x_rep[: first_acc_idx + 1].cpu().numpy())  # :709-710
+        sampled_velocs.append(xv_rep[: first_acc_idx + 1].cpu().numpy())
+        x_coords = x_rep[first_acc_idx].unsqueeze(0).contiguous()  # :712-713
+        x_velocs = xv_rep[first_acc_idx].unsqueeze(0).contiguous()
+        i += first_acc_idx + 1
+        k = first_acc_idx + 1
+        stats["acceptance"].append(p_acc.cpu().numpy()[:k])
+        stats["p_xy"].append(p_xy.cpu().numpy()[:k])
+        stats["p_yx"].append(p_yx.cpu().numpy()[:k])
+        stats["exponent"].append(exp_.cpu().numpy()[:k])
+        stats["energies_pot"].append(e_pot_y.cpu().numpy()[:k])
+        stats["energies_kin"].append(e_kin_y.cpu().numpy()[:k])
+        stats["energies_pot_delta"].append((e_pot_y - e_pot_x).cpu().numpy()[:k])
+        stats["energies_kin_delta"].append((e_kin_y - e_kin_x).cpu().numpy()[:k])
+    chain_stats = ChainStats(**{k: np.concatenate(v, axis=0) for k, v in stats.items()})
+    return np.concatenate(sampled_coords, axis=0), np.concatenate(sampled_velocs, axis=0), accepted, chain_stats
+
+
+@torch.no_grad()
+def explore(model, energy, atom_types: Tensor, masked_elements: Tensor, x_coords: Tensor, x_velocs: Tensor, num_steps: int,
+            num_chains: int, threshold: float = 300.0, chirality_centers: Optional[Tensor] = None,
+            reference_signs: Optional[Tensor] = None, keep_trajectory: bool = True):
+    """exploration.py:229-250: `num_chains` copies of one start state; per step one flow sample and
+    one energy per chain, reject where E_new - E_old > threshold (kJ/mol) or chirality flipped (+10000).
+    Returns (positions [steps*chains,V,3] or final [chains,V,3], energies, accept_counts[chains])."""
+    dev = x_coords.device
+    P = num_chains
+    empty_adj = torch.zeros(0, 2, dtype=torch.long, device=dev)
+    empty_ebi = torch.zeros(0, dtype=torch.long, device=dev)
+    at = atom_types.repeat(P, 1).contiguous() if atom_types.shape[0] == 1 else atom_types
+    mask = masked_elements.repeat(P, 1).contiguous() if masked_elements.shape[0] == 1 else masked_elements
+    energies = energy(x_coords).repeat(P, 1).squeeze(-1).contiguous() if x_coords.shape[0] == 1 else energy(x_coords).squeeze(-1).contiguous()
+    y = (x_coords.repeat(P, 1, 1) if x_coords.shape[0] == 1 else x_coords).to(torch.float32).clone().contiguous()
+    yv = (x_velocs.repeat(P, 1, 1) if x_velocs.shape[0] == 1 else x_velocs).to(torch.float32).clone().contiguous()
+    V = y.shape[1]
+    traj, etraj = [], []
+    n_acc = torch.zeros(P, dtype=torch.int64, device=dev)
+    lib = _lib.load()
+    for _ in range(num_steps):
+        y_new, _v = model.conditional_sample(atom_types=at, x_coords=y, x_velocs=yv, adj_list=empty_adj, edge_batch_idx=empty_ebi,
+                                             masked_elements=mask, num_samples=1)  # :126-134
+        y_new = y_new.squeeze(0).contiguous()
+        e_new = energy(y_new).squeeze(-1)  # :239
+        if chirality_centers is not None and reference_signs is not None:
+            e_new = e_new + 10000.0 * check_symmetry_change(y_new, chirality_centers, reference_signs)  # :240-242
+        e_new = e_new.to(torch.float32).contiguous()
+        acc = torch.empty(P, dtype=torch.uint8, device=dev)
+        _lib.check(lib.tw_threshold_accept(_lib.ptr(y), _lib.ptr(energies), _lib.ptr(y_new), _lib.ptr(e_new), float(threshold), P, V,
+                                           _lib.ptr(acc), _stream(dev)), "tw_threshold_accept")  # :243-246
+        n_acc += acc
+        if keep_trajectory:
+            traj.append(y.clone())
+            etraj.append(energies.clone())
+        yv = torch.randn_like(y)  # :250
+    if keep_trajectory:
+        return torch.cat(traj, 0), torch.cat(etraj, 0), n_acc
+    return y, energies, n_acc
