@@ -66,7 +66,7 @@ def test_energy_properties_and_nonfinite():
     assert energy(x.reshape(2, 2, 65, 3)).shape == (4, 1)
     # overlapping atoms / NaN coordinates give non-finite energies, never a crash (a12)
     bad = x.clone()
-    bad[0, 1] = bad[0, 0]
+    bad[0, 40] = bad[0, 0]  # two non-bonded atoms on top of each other: LJ/Coulomb singularity
     bad[1, 3, 0] = float("nan")
     eb = energy(bad)
     assert not torch.isfinite(eb[0]).all() and not torch.isfinite(eb[1]).all() and torch.isfinite(eb[2:]).all()

@@ -196,7 +196,9 @@ using namespace tw;
 
 extern "C" int tw_peptide_energy(const tw_energy_system* sys, const float* coords, int64_t B, float* out_energy,
                                  float* out_forces, float* out_terms, void* stream) {
-  TW_CHECK_ARG(sys && coords && out_energy, "NULL pointer");
+  TW_CHECK_ARG(sys != nullptr, "NULL system");
+  if (B == 0) return TW_OK;
+  TW_CHECK_ARG(coords && out_energy, "NULL pointer");
   TW_CHECK_ARG(sys->n_atoms >= 1 && sys->n_atoms <= 4096, "n_atoms out of range (1..4096)");
   TW_CHECK_ARG(B >= 0 && B <= 2147483647LL, "bad batch size");
   TW_CHECK_ARG(sys->n_bonds == 0 || (sys->bond_idx && sys->bond_param), "bond arrays missing");

@@ -211,8 +211,9 @@ int tw_flow_workspace_bytes(const tw_flow_config* cfg, int64_t n_samples, int64_
 
 int tw_attn_scores(const float* coords, const uint8_t* mask, const float* lengthscales, int64_t B, int64_t V, int32_t H,
                    float* out, void* stream) {
-  TW_CHECK_ARG(coords && mask && lengthscales && out, "NULL pointer");
   TW_CHECK_ARG(B >= 0 && V >= 1 && H >= 1, "bad sizes");
+  if (B == 0) return TW_OK;
+  TW_CHECK_ARG(coords && mask && lengthscales && out, "NULL pointer");
   return launch_scores(coords, mask, lengthscales, B, (int)V, H, out, (cudaStream_t)stream);
 }
 
@@ -222,8 +223,8 @@ int tw_flow_scale_shift(const tw_flow_config* cfg, const void* const* params, in
                         size_t workspace_bytes, void* stream) {
   TW_TRY(check_common(cfg, params, B, B, V));
   TW_CHECK_ARG(layer_idx >= 0 && layer_idx < cfg->num_coupling_layers, "layer_idx out of range");
-  TW_CHECK_ARG(atom_types && x_coords_centred && x_velocs && z_coords && z_velocs && mask && out_scale && out_shift, "NULL pointer");
   if (B == 0) return TW_OK;
+  TW_CHECK_ARG(atom_types && x_coords_centred && x_velocs && z_coords && z_velocs && mask && out_scale && out_shift, "NULL pointer");
   PassCtx p{cfg, ParamView{cfg, params}, {}, atom_types, x_velocs, mask, B, B, (int)V, (cudaStream_t)stream};
   size_t need = carve(cfg, B, B, V, workspace, workspace_bytes, &p.fb);
   if (need > workspace_bytes || !workspace) return fail(TW_ERR_WORKSPACE, "workspace %zu < %zu", workspace_bytes, need);
@@ -242,8 +243,8 @@ int tw_flow_log_likelihood(const tw_flow_config* cfg, const void* const* params,
                            const uint8_t* mask, int64_t B, int64_t V, int32_t flags, float* out_log_prob,
                            float* out_z_coords, float* out_z_velocs, void* workspace, size_t workspace_bytes, void* stream) {
   TW_TRY(check_common(cfg, params, B, B, V));
+  if (B == 0) return TW_OK;  // empty batch: nothing to do (empty tensors have NULL data pointers)
   TW_CHECK_ARG(atom_types && x_coords && x_velocs && y_coords && y_velocs && mask && out_log_prob, "NULL pointer");
-  if (B == 0) return TW_OK;
   PassCtx p{cfg, ParamView{cfg, params}, {}, atom_types, x_velocs, mask, B, B, (int)V, (cudaStream_t)stream};
   size_t need = carve(cfg, B, B, V, workspace, workspace_bytes, &p.fb);
   if (need > workspace_bytes || !workspace) return fail(TW_ERR_WORKSPACE, "workspace %zu < %zu", workspace_bytes, need);
@@ -270,8 +271,8 @@ int tw_flow_sample(const tw_flow_config* cfg, const void* const* params, const i
   TW_CHECK_ARG(S >= 0, "bad num_samples");
   const int64_t n = S * n_cond;
   TW_TRY(check_common(cfg, params, n, n_cond, V));
-  TW_CHECK_ARG(atom_types && x_coords && x_velocs && mask && z_coords && z_velocs && out_y_coords && out_y_velocs, "NULL pointer");
   if (n == 0) return TW_OK;
+  TW_CHECK_ARG(atom_types && x_coords && x_velocs && mask && z_coords && z_velocs && out_y_coords && out_y_velocs, "NULL pointer");
   PassCtx p{cfg, ParamView{cfg, params}, {}, atom_types, x_velocs, mask, n, n_cond, (int)V, (cudaStream_t)stream};
   size_t need = carve(cfg, n, n_cond, V, workspace, workspace_bytes, &p.fb);
   if (need > workspace_bytes || !workspace) return fail(TW_ERR_WORKSPACE, "workspace %zu < %zu", workspace_bytes, need);
