@@ -90,6 +90,14 @@ int tw_flow_num_params(const tw_flow_config* cfg);
 int tw_flow_workspace_bytes(const tw_flow_config* cfg, int64_t n_samples, int64_t n_cond, int64_t n_atoms,
                             size_t* bytes);
 
+/* Tensor-core precisions (TW_PRECISION_BF16X3 / BF16) read the weights from bf16 operand images that
+ * are re-packed from the fp32 parameters once per weight update: query the size, pack into a caller-
+ * owned, 1024-byte-aligned device buffer, and pass that buffer as `packed_weights` to the flow calls
+ * (NULL for TW_PRECISION_FP32).  tw_flow_packed_bytes returns 0 for TW_PRECISION_FP32. */
+int tw_flow_packed_bytes(const tw_flow_config* cfg, size_t* bytes);
+int tw_flow_pack_weights(const tw_flow_config* cfg, const void* const* params, void* packed, size_t packed_bytes,
+                         void* stream);
+
 /* compute_kernel_attention_scores (modules/layers/kernel_attention.py:69-121):
  * out[b,h,i,j] = w / (sum_j |w| + 1e-5),  w = mask_j ? 0 : exp(-(|x_i-x_j| / l_h)^2).
  * coords [B,V,3], mask [B,V], lengthscales [H] (device), out [B,H,V,V]. */
@@ -102,7 +110,8 @@ int tw_attn_scores(const float* coords, const uint8_t* mask, const float* length
 int tw_flow_scale_shift(const tw_flow_config* cfg, const void* const* params, int32_t layer_idx,
                         const int64_t* atom_types, const float* x_coords_centred, const float* x_velocs,
                         const float* z_coords, const float* z_velocs, const uint8_t* mask, int64_t B, int64_t V,
-                        float* out_scale, float* out_shift, void* workspace, size_t workspace_bytes, void* stream);
+                        float* out_scale, float* out_shift, const void* packed_weights, void* workspace,
+                        size_t workspace_bytes, void* stream);
 
 /* flags for the two calls below (ConditionalFlowDensityConfig, flow.py:339-347) */
 #define TW_FLOW_DISPLACEMENT_TARGET 1   /* use_displacement_as_target=True: the flow models y - x */
@@ -112,8 +121,8 @@ int tw_flow_scale_shift(const tw_flow_config* cfg, const void* const* params, in
 int tw_flow_log_likelihood(const tw_flow_config* cfg, const void* const* params, const int64_t* atom_types,
                            const float* x_coords, const float* x_velocs, const float* y_coords,
                            const float* y_velocs, const uint8_t* mask, int64_t B, int64_t V, int32_t flags,
-                           float* out_log_prob, float* out_z_coords, float* out_z_velocs, void* workspace,
-                           size_t workspace_bytes, void* stream);
+                           float* out_log_prob, float* out_z_coords, float* out_z_velocs, const void* packed_weights,
+                           void* workspace, size_t workspace_bytes, void* stream);
 
 /* ConditionalFlowDensityModel.conditional_sample_with_logp (flow.py:242-336) given the latent
  * draws.  Conditioning tensors have n_cond rows; the S*n_cond flow samples are laid out as the
@@ -123,8 +132,8 @@ int tw_flow_log_likelihood(const tw_flow_config* cfg, const void* const* params,
 int tw_flow_sample(const tw_flow_config* cfg, const void* const* params, const int64_t* atom_types,
                    const float* x_coords, const float* x_velocs, const uint8_t* mask, int64_t n_cond, int64_t V,
                    int64_t S, int32_t flags, const float* z_coords, const float* z_velocs, float* out_y_coords,
-                   float* out_y_velocs, float* out_log_prob, void* workspace, size_t workspace_bytes,
-                   void* stream);
+                   float* out_y_velocs, float* out_log_prob, const void* packed_weights, void* workspace,
+                   size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Potential energy.  Replaces OpenmmPotentialEnergyTorch.forward (utils/openmm/openmm_bridge.py:
@@ -187,6 +196,13 @@ int tw_mh_accept(const float* e_pot_x, const float* e_pot_y, const float* e_kin_
  * e_new - e_old > threshold, else take the new one.  Updates x_coords [n,V,3] and e_old [n] in place. */
 int tw_threshold_accept(float* x_coords, float* e_old, const float* y_coords, const float* e_new, float threshold,
                         int64_t n, int64_t V, uint8_t* out_accepted, void* stream);
+
+/* Debug: single-CTA tcgen05 probe, out[128,N] = bf16(A[128,K]) * bf16(B[N,K])^T with selectable operand
+ * placement (a_mode 0 smem K-major SW128 / 1 K-major no swizzle / 2 MN-major SW128 / 3 TMEM; b_mode 0..2),
+ * accumulator at TMEM column d_col.  status[0] = 1 if the MMA never completed.  Used by the GPU tests to
+ * pin the descriptor conventions of the production kernels on the real chip. */
+int tw_debug_umma_probe(const float* A, const float* B, float* out, int N, int K, int a_mode, int b_mode, int d_col,
+                        int a_col, int* status, void* stream);
 
 #ifdef __cplusplus
 }

@@ -90,7 +90,7 @@ def test_config_validation(lib):
     assert b"tensor-core" in lib.tw_last_error()
     # NULL pointers are reported, not dereferenced
     m = tw.custom_transformer_nvp_constructor(model_config(TINY_O, "fp32"))
-    assert lib.tw_flow_log_likelihood(C.byref(m._cfg), None, None, None, None, None, None, None, 1, 3, 1, None, None, None, None, 0, None) == 1
+    assert lib.tw_flow_log_likelihood(C.byref(m._cfg), None, None, None, None, None, None, None, 1, 3, 1, None, None, None, None, None, 0, None) == 1
     assert lib.tw_attn_scores(None, None, None, 1, 3, 2, None, None) == 1
     assert lib.tw_attn_scores(None, None, None, 0, 3, 2, None, None) == 0  # empty batch is a no-op
 

@@ -1,0 +1,65 @@
+"""Tensor-core (tcgen05) path: descriptor conventions on the real chip, and parity of the bf16x3 /
+bf16 conditioner kernels against the fp32 CUDA-core path, the golden vectors and the CPU oracle."""
+import pytest
+import torch
+
+from oracle import flow_oracle as fo
+from tests.common import EMPTY_ADJ, EMPTY_EBI, FULL_O, build_model, load_golden
+from tests.test_gpu_flow import _kw, assert_rel
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("a_mode,b_mode,N,K,d_col", [(0, 0, 128, 128, 0), (0, 0, 256, 128, 128), (3, 0, 128, 128, 384), (0, 1, 80, 80, 8),
+                                                     (1, 1, 48, 48, 0), (2, 2, 128, 64, 0), (3, 1, 64, 256, 64)])
+def test_umma_probe(a_mode, b_mode, N, K, d_col):
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    from umma_probe import run
+    err, status, mx = run(N, K, a_mode, b_mode, d_col)
+    assert status == 0 and err < 1e-3 * mx
+
+
+@pytest.mark.parametrize("name", ["full_ad22", "full_ad22_ragged", "full_2olx65"])
+def test_bf16x3_matches_golden(name):
+    g = load_golden(name)
+    m, _ = build_model(FULL_O, "bf16x3", int(g["weight_seed"]))
+    ll = m.log_likelihood(y_coords=g["y_coords"].cuda(), y_velocs=g["y_velocs"].cuda(), **_kw(g))
+    err64 = assert_rel(ll, g["log_likelihood_f64"], what="bf16x3 ll vs reference fp64")
+    assert_rel(ll, g["log_likelihood"], what="bf16x3 ll vs reference fp32")
+    m32, _ = build_model(FULL_O, "fp32", int(g["weight_seed"]))
+    ll32 = m32.log_likelihood(y_coords=g["y_coords"].cuda(), y_velocs=g["y_velocs"].cuda(), **_kw(g))
+    assert_rel(ll, ll32, rel=2e-5, what="bf16x3 vs fp32 CUDA path")
+    print(name, "bf16x3 rel err vs fp64:", err64)
+    yc, yv, lp = m.sample_from_latents(g["atom_types"].cuda(), g["x_coords"].cuda(), g["x_velocs"].cuda(), g["masked_elements"].cuda(),
+                                       g["s1_z_coords"].cuda(), g["s1_z_velocs"].cuda())
+    keep = (~g["masked_elements"])[None, :, :, None].expand_as(g["s1_y_coords"])
+    assert_rel(yc.cpu()[keep], g["s1_y_coords"][keep], what="bf16x3 samples")
+    assert_rel(lp, g["s1_logp"], what="bf16x3 sample logp")
+
+
+def test_bf16x3_many_tiles_and_tail():
+    """Several 128-token tiles per CTA + a ragged tail tile, against the fp32 CUDA-core path."""
+    torch.manual_seed(0)
+    B, V = 300, 22  # 6600 tokens = 51 full tiles + a 72-row tail
+    m, sd = build_model(FULL_O, "bf16x3", 1)
+    m32, _ = build_model(FULL_O, "fp32", 1)
+    at = torch.randint(0, 5, (B, V), device="cuda")
+    x, xv, y, yv = (torch.randn(B, V, 3, device="cuda") * s for s in (0.3, 1.0, 0.3, 1.0))
+    mask = torch.zeros(B, V, dtype=torch.bool, device="cuda")
+    kw = dict(atom_types=at, x_coords=x, x_velocs=xv, y_coords=y, y_velocs=yv, adj_list=EMPTY_ADJ.cuda(), edge_batch_idx=EMPTY_EBI.cuda(),
+              masked_elements=mask)
+    a, b = m.log_likelihood(**kw), m32.log_likelihood(**kw)
+    assert_rel(a, b, rel=2e-5, what="bf16x3 vs fp32, 52 tiles")
+    # weights modified in place are re-packed
+    with torch.no_grad():
+        m.flow.chain[0].scale_transformer.encoder_layers[0].linear1.weight.mul_(1.5)
+        m32.flow.chain[0].scale_transformer.encoder_layers[0].linear1.weight.mul_(1.5)
+    assert_rel(m.log_likelihood(**kw), m32.log_likelihood(**kw), rel=2e-5, what="after in-place weight update")
+
+
+def test_bf16_plain_is_close():
+    g = load_golden("full_ad22")
+    m, _ = build_model(FULL_O, "bf16", 0)
+    ll = m.log_likelihood(y_coords=g["y_coords"].cuda(), y_velocs=g["y_velocs"].cuda(), **_kw(g))
+    assert_rel(ll, g["log_likelihood"], rel=2e-2, what="plain bf16 (training precision)")

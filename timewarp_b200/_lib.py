@@ -63,13 +63,16 @@ _SIGNATURES = {
     "tw_flow_num_params": (C.c_int, [C.POINTER(FlowConfig)]),
     "tw_flow_workspace_bytes": (C.c_int, [C.POINTER(FlowConfig), _I64, _I64, _I64, C.POINTER(C.c_size_t)]),
     "tw_attn_scores": (C.c_int, [_P, _P, _P, _I64, _I64, _I32, _P, _P]),
-    "tw_flow_scale_shift": (C.c_int, [C.POINTER(FlowConfig), _P, _I32, _P, _P, _P, _P, _P, _P, _I64, _I64, _P, _P, _P, C.c_size_t, _P]),
-    "tw_flow_log_likelihood": (C.c_int, [C.POINTER(FlowConfig), _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I32, _P, _P, _P, _P, C.c_size_t, _P]),
-    "tw_flow_sample": (C.c_int, [C.POINTER(FlowConfig), _P, _P, _P, _P, _P, _I64, _I64, _I64, _I32, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
+    "tw_flow_packed_bytes": (C.c_int, [C.POINTER(FlowConfig), C.POINTER(C.c_size_t)]),
+    "tw_flow_pack_weights": (C.c_int, [C.POINTER(FlowConfig), _P, _P, C.c_size_t, _P]),
+    "tw_flow_scale_shift": (C.c_int, [C.POINTER(FlowConfig), _P, _I32, _P, _P, _P, _P, _P, _P, _I64, _I64, _P, _P, _P, _P, C.c_size_t, _P]),
+    "tw_flow_log_likelihood": (C.c_int, [C.POINTER(FlowConfig), _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I32, _P, _P, _P, _P, _P, C.c_size_t, _P]),
+    "tw_flow_sample": (C.c_int, [C.POINTER(FlowConfig), _P, _P, _P, _P, _P, _I64, _I64, _I64, _I32, _P, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
     "tw_peptide_energy": (C.c_int, [C.POINTER(EnergySystem), _P, _I64, _P, _P, _P, _P]),
     "tw_chirality": (C.c_int, [_P, _P, _P, _I64, _I64, _I32, _P, _P, _P]),
     "tw_kinetic_energy": (C.c_int, [_P, _P, C.c_float, _I64, _I64, _P, _P]),
     "tw_mh_accept": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I64, _I64, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "tw_debug_umma_probe": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
     "tw_threshold_accept": (C.c_int, [_P, _P, _P, _P, C.c_float, _I64, _I64, _P, _P]),
 }  # fmt: skip
 

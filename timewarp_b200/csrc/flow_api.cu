@@ -51,21 +51,17 @@ static size_t carve(const tw_flow_config* c, int64_t n, int64_t n_cond, int64_t 
   for (int i = 0; i < 2; i++) b.st[i] = ar.take<float>(M * 3);
   for (int i = 0; i < 2; i++) b.actA[i] = ar.take<float>(M * D);
   for (int i = 0; i < 2; i++) b.actB[i] = ar.take<float>(M * D);
-  if (c->precision == TW_PRECISION_FP32) {
-    const int hid = max_hidden(c);
-    b.feat = ar.take<float>(M * (E + 9));
-    for (int i = 0; i < 2; i++) {
-      b.hidA[i] = ar.take<float>(M * hid);
-      b.hidB[i] = ar.take<float>(M * hid);
-      b.vals[i] = ar.take<float>(M * H * D);
-      b.att[i] = ar.take<float>(M * H * D);
-      b.ffn[i] = ar.take<float>(M * F);
-    }
-  } else {
-    b.feat = nullptr;
-    for (int i = 0; i < 2; i++) b.hidA[i] = b.hidB[i] = b.vals[i] = b.att[i] = b.ffn[i] = nullptr;
-    tc_carve(c, n, n_cond, V, ar, &b.tc);
+  const int hid = max_hidden(c);
+  b.feat = ar.take<float>(M * (E + 9));
+  for (int i = 0; i < 2; i++) {
+    b.hidA[i] = ar.take<float>(M * hid);
+    b.hidB[i] = ar.take<float>(M * hid);
+    b.vals[i] = ar.take<float>(M * H * D);
+    b.att[i] = ar.take<float>(M * H * D);
+    // the fused tensor-core FFN keeps the hidden activation on chip
+    b.ffn[i] = (c->precision == TW_PRECISION_FP32 || !(tc_stage_mask() & TC_FFN)) ? ar.take<float>(M * F) : nullptr;
   }
+  b.tc = TcScratch{};
   if (fb) *fb = b;
   return align_up(ar.off, 256);
 }
@@ -80,16 +76,20 @@ struct PassCtx {
   int64_t n, n_cond;
   int V;
   cudaStream_t st;
+  const uint8_t* packed = nullptr;  // packed tensor-core weight images (precision != fp32)
 };
 
 // One transformer block pair (scale net, shift net) of coupling layer k on CUDA cores:
 // custom_transformer_block.py:46-82, custom_attention_encoder.py:82-114.
-static int conditioner_fp32(PassCtx& p, int k) {
+static int conditioner(PassCtx& p, int k) {
   const tw_flow_config* c = p.c;
   FlowBuffers& b = p.fb;
   const int64_t M = p.n * p.V;
   const int D = c->d_model, H = c->num_heads, F = c->dim_feedforward, E = c->atom_embedding_dim, nh = c->num_mlp_hidden;
   const bool pos = (k % 2) == c->position_layer_index_mod_2;
+  const uint32_t tcs = (c->precision == TW_PRECISION_FP32) ? 0u : tc_stage_mask();
+  TcScratch tcx{};
+  tcx.packed = p.packed;
   TW_TRY(launch_features(p.pv.embed(), p.atom_types, b.xc, p.x_velocs, pos ? b.zv : b.zc, p.n, p.n_cond, p.V, E,
                          c->num_atom_types, b.feat, p.st));
   // in_mlp
@@ -117,18 +117,22 @@ static int conditioner_fp32(PassCtx& p, int k) {
     TW_TRY(launch_linear(o, 2, M, D, H * D, H * D, D, D, ACT_NONE, p.st));
     TW_TRY(launch_layernorm(b.actB[0], b.actB[1], p.pv.enc(k, 0, t, 7), p.pv.enc(k, 1, t, 7), p.pv.enc(k, 0, t, 8),
                             p.pv.enc(k, 1, t, 8), 2, M, D, c->layer_norm_eps, p.st));
-    {
-      ProfScope prof_ffn(PROF_FFN, p.st);
-      Lin2 f1{};
-      for (int s = 0; s < 2; s++) f1.X[s] = b.actB[s], f1.W[s] = p.pv.enc(k, s, t, 3), f1.b[s] = p.pv.enc(k, s, t, 4), f1.Y[s] = b.ffn[s];
-      TW_TRY(launch_linear(f1, 2, M, F, D, D, 0, F, ACT_RELU, p.st));
-      Lin2 f2{};
-      for (int s = 0; s < 2; s++)
-        f2.X[s] = b.ffn[s], f2.W[s] = p.pv.enc(k, s, t, 5), f2.b[s] = p.pv.enc(k, s, t, 6), f2.R[s] = b.actB[s], f2.Y[s] = b.actA[s];
-      TW_TRY(launch_linear(f2, 2, M, D, F, F, D, D, ACT_NONE, p.st));
+    if (tcs & TC_FFN) {
+      TW_TRY(tc_ffn_layer(c, p.pv, k, t, tcx, b.actB, b.actA, M, p.st));  // fused linear1+ReLU+linear2+residual+LN2
+    } else {
+      {
+        ProfScope prof_ffn(PROF_FFN, p.st);
+        Lin2 f1{};
+        for (int s = 0; s < 2; s++) f1.X[s] = b.actB[s], f1.W[s] = p.pv.enc(k, s, t, 3), f1.b[s] = p.pv.enc(k, s, t, 4), f1.Y[s] = b.ffn[s];
+        TW_TRY(launch_linear(f1, 2, M, F, D, D, 0, F, ACT_RELU, p.st));
+        Lin2 f2{};
+        for (int s = 0; s < 2; s++)
+          f2.X[s] = b.ffn[s], f2.W[s] = p.pv.enc(k, s, t, 5), f2.b[s] = p.pv.enc(k, s, t, 6), f2.R[s] = b.actB[s], f2.Y[s] = b.actA[s];
+        TW_TRY(launch_linear(f2, 2, M, D, F, F, D, D, ACT_NONE, p.st));
+      }
+      TW_TRY(launch_layernorm(b.actA[0], b.actA[1], p.pv.enc(k, 0, t, 9), p.pv.enc(k, 1, t, 9), p.pv.enc(k, 0, t, 10),
+                              p.pv.enc(k, 1, t, 10), 2, M, D, c->layer_norm_eps, p.st));
     }
-    TW_TRY(launch_layernorm(b.actA[0], b.actA[1], p.pv.enc(k, 0, t, 9), p.pv.enc(k, 1, t, 9), p.pv.enc(k, 0, t, 10),
-                            p.pv.enc(k, 1, t, 10), 2, M, D, c->layer_norm_eps, p.st));
   }
   // out_mlp
   cur[0] = b.actA[0], cur[1] = b.actA[1], cur_dim = D;
@@ -146,13 +150,6 @@ static int conditioner_fp32(PassCtx& p, int k) {
   return TW_OK;
 }
 
-static int conditioner(PassCtx& p, int k) {
-  if (p.c->precision == TW_PRECISION_FP32) return conditioner_fp32(p, k);
-  const bool pos = (k % 2) == p.c->position_layer_index_mod_2;
-  return tc_conditioner(p.c, p.pv, k, p.fb.tc, p.atom_types, p.fb.xc, p.x_velocs, pos ? p.fb.zv : p.fb.zc, p.fb.scores,
-                        p.fb.actA, p.fb.actB, p.fb.st, p.n, p.n_cond, p.V, p.st);
-}
-
 // Prepare a pass: centre the conditioning coordinates, attention scores once per pass
 // (the reference's Cache: model_constructor.py:189-196; 1 miss + 47 hits).
 static int begin_pass(PassCtx& p, const float* x_coords) {
@@ -160,7 +157,6 @@ static int begin_pass(PassCtx& p, const float* x_coords) {
   // lengthscales of chain[0].scale_transformer.encoder_layers[0] (cache key maps lengthscales -> 0)
   const float* ls = p.pv.enc(0, 0, 0, 1);
   TW_TRY(launch_scores(p.fb.xc, p.mask, ls, p.n_cond, p.V, p.c->num_heads, p.fb.scores, p.st));
-  if (p.c->precision != TW_PRECISION_FP32) TW_TRY(tc_begin_pass(p.c, p.pv, p.fb.tc, p.fb.scores, p.mask, p.n, p.n_cond, p.V, p.st));
   return TW_OK;
 }
 
@@ -173,6 +169,14 @@ static int run_layers(PassCtx& p, bool reverse) {
     TW_TRY(launch_coupling(p.fb.st[0], p.fb.st[1], pos ? p.fb.zc : p.fb.zv, p.mask, p.fb.delta, p.n, p.n_cond, p.V,
                            reverse ? 1 : 0, nullptr, nullptr, p.st));
   }
+  return TW_OK;
+}
+
+static int set_packed(PassCtx& p, const void* packed) {
+  if (p.c->precision == TW_PRECISION_FP32) return TW_OK;
+  TW_CHECK_ARG(packed != nullptr, "packed_weights is NULL: call tw_flow_pack_weights first (tensor-core precisions)");
+  TW_CHECK_ARG(((uintptr_t)packed & 1023) == 0, "packed_weights must be 1024-byte aligned");
+  p.packed = (const uint8_t*)packed;
   return TW_OK;
 }
 
@@ -209,6 +213,20 @@ int tw_flow_workspace_bytes(const tw_flow_config* cfg, int64_t n_samples, int64_
   return TW_OK;
 }
 
+int tw_flow_packed_bytes(const tw_flow_config* cfg, size_t* bytes) {
+  TW_TRY(validate_cfg(cfg));
+  TW_CHECK_ARG(bytes != nullptr, "bytes is NULL");
+  *bytes = (cfg->precision == TW_PRECISION_FP32) ? 0 : tc_packed_bytes(cfg);
+  return TW_OK;
+}
+
+int tw_flow_pack_weights(const tw_flow_config* cfg, const void* const* params, void* packed, size_t packed_bytes, void* stream) {
+  TW_TRY(validate_cfg(cfg));
+  TW_CHECK_ARG(params != nullptr, "params is NULL");
+  if (cfg->precision == TW_PRECISION_FP32) return TW_OK;
+  return tc_pack_weights(cfg, ParamView{cfg, params}, (uint8_t*)packed, packed_bytes, (cudaStream_t)stream);
+}
+
 int tw_attn_scores(const float* coords, const uint8_t* mask, const float* lengthscales, int64_t B, int64_t V, int32_t H,
                    float* out, void* stream) {
   TW_CHECK_ARG(B >= 0 && V >= 1 && H >= 1, "bad sizes");
@@ -219,13 +237,14 @@ int tw_attn_scores(const float* coords, const uint8_t* mask, const float* length
 
 int tw_flow_scale_shift(const tw_flow_config* cfg, const void* const* params, int32_t layer_idx, const int64_t* atom_types,
                         const float* x_coords_centred, const float* x_velocs, const float* z_coords, const float* z_velocs,
-                        const uint8_t* mask, int64_t B, int64_t V, float* out_scale, float* out_shift, void* workspace,
-                        size_t workspace_bytes, void* stream) {
+                        const uint8_t* mask, int64_t B, int64_t V, float* out_scale, float* out_shift, const void* packed_weights,
+                        void* workspace, size_t workspace_bytes, void* stream) {
   TW_TRY(check_common(cfg, params, B, B, V));
   TW_CHECK_ARG(layer_idx >= 0 && layer_idx < cfg->num_coupling_layers, "layer_idx out of range");
   if (B == 0) return TW_OK;
   TW_CHECK_ARG(atom_types && x_coords_centred && x_velocs && z_coords && z_velocs && mask && out_scale && out_shift, "NULL pointer");
   PassCtx p{cfg, ParamView{cfg, params}, {}, atom_types, x_velocs, mask, B, B, (int)V, (cudaStream_t)stream};
+  TW_TRY(set_packed(p, packed_weights));
   size_t need = carve(cfg, B, B, V, workspace, workspace_bytes, &p.fb);
   if (need > workspace_bytes || !workspace) return fail(TW_ERR_WORKSPACE, "workspace %zu < %zu", workspace_bytes, need);
   const size_t zb = (size_t)B * V * 3 * sizeof(float);
@@ -233,7 +252,6 @@ int tw_flow_scale_shift(const tw_flow_config* cfg, const void* const* params, in
   TW_CUDA(cudaMemcpyAsync(p.fb.zc, z_coords, zb, cudaMemcpyDeviceToDevice, p.st));
   TW_CUDA(cudaMemcpyAsync(p.fb.zv, z_velocs, zb, cudaMemcpyDeviceToDevice, p.st));
   TW_TRY(launch_scores(p.fb.xc, mask, p.pv.enc(0, 0, 0, 1), B, (int)V, cfg->num_heads, p.fb.scores, p.st));
-  if (cfg->precision != TW_PRECISION_FP32) TW_TRY(tc_begin_pass(cfg, p.pv, p.fb.tc, p.fb.scores, mask, B, B, (int)V, p.st));
   TW_TRY(conditioner(p, layer_idx));
   return launch_coupling(p.fb.st[0], p.fb.st[1], nullptr, mask, nullptr, B, B, (int)V, 0, out_scale, out_shift, p.st);
 }
@@ -241,11 +259,13 @@ int tw_flow_scale_shift(const tw_flow_config* cfg, const void* const* params, in
 int tw_flow_log_likelihood(const tw_flow_config* cfg, const void* const* params, const int64_t* atom_types,
                            const float* x_coords, const float* x_velocs, const float* y_coords, const float* y_velocs,
                            const uint8_t* mask, int64_t B, int64_t V, int32_t flags, float* out_log_prob,
-                           float* out_z_coords, float* out_z_velocs, void* workspace, size_t workspace_bytes, void* stream) {
+                           float* out_z_coords, float* out_z_velocs, const void* packed_weights, void* workspace,
+                           size_t workspace_bytes, void* stream) {
   TW_TRY(check_common(cfg, params, B, B, V));
   if (B == 0) return TW_OK;  // empty batch: nothing to do (empty tensors have NULL data pointers)
   TW_CHECK_ARG(atom_types && x_coords && x_velocs && y_coords && y_velocs && mask && out_log_prob, "NULL pointer");
   PassCtx p{cfg, ParamView{cfg, params}, {}, atom_types, x_velocs, mask, B, B, (int)V, (cudaStream_t)stream};
+  TW_TRY(set_packed(p, packed_weights));
   size_t need = carve(cfg, B, B, V, workspace, workspace_bytes, &p.fb);
   if (need > workspace_bytes || !workspace) return fail(TW_ERR_WORKSPACE, "workspace %zu < %zu", workspace_bytes, need);
   const int64_t cnt = B * V * 3;
@@ -266,14 +286,15 @@ int tw_flow_log_likelihood(const tw_flow_config* cfg, const void* const* params,
 
 int tw_flow_sample(const tw_flow_config* cfg, const void* const* params, const int64_t* atom_types, const float* x_coords,
                    const float* x_velocs, const uint8_t* mask, int64_t n_cond, int64_t V, int64_t S, int32_t flags,
-                   const float* z_coords, const float* z_velocs, float* out_y_coords, float* out_y_velocs, float* out_log_prob, void* workspace,
-                   size_t workspace_bytes, void* stream) {
+                   const float* z_coords, const float* z_velocs, float* out_y_coords, float* out_y_velocs, float* out_log_prob,
+                   const void* packed_weights, void* workspace, size_t workspace_bytes, void* stream) {
   TW_CHECK_ARG(S >= 0, "bad num_samples");
   const int64_t n = S * n_cond;
   TW_TRY(check_common(cfg, params, n, n_cond, V));
   if (n == 0) return TW_OK;
   TW_CHECK_ARG(atom_types && x_coords && x_velocs && mask && z_coords && z_velocs && out_y_coords && out_y_velocs, "NULL pointer");
   PassCtx p{cfg, ParamView{cfg, params}, {}, atom_types, x_velocs, mask, n, n_cond, (int)V, (cudaStream_t)stream};
+  TW_TRY(set_packed(p, packed_weights));
   size_t need = carve(cfg, n, n_cond, V, workspace, workspace_bytes, &p.fb);
   if (need > workspace_bytes || !workspace) return fail(TW_ERR_WORKSPACE, "workspace %zu < %zu", workspace_bytes, need);
   const int64_t cnt = n * V * 3;

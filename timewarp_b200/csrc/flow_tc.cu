@@ -1,15 +1,552 @@
+// Tensor-core kernels of the conditioner networks (sm_100a: tcgen05.mma + TMEM + bulk async copy).
+//
+// Arithmetic: every fp32 product a*w is evaluated as hi(a)*hi(w) + lo(a)*hi(w) + hi(a)*lo(w) with
+// bf16 hi/lo parts and fp32 accumulation in TMEM ("bf16x3", ~16 significand bits per operand), or
+// as hi(a)*hi(w) only ("bf16").  Orientation: tokens on the 128 TMEM lanes (MMA M), output
+// features on the columns (MMA N), so bias/activation/LayerNorm run per thread without shuffles.
+#include <stdlib.h>
+
 #include "flow_tc.cuh"
+#include "umma.cuh"
 
 namespace tw {
+using namespace umma;
 
-bool tc_supported(const tw_flow_config* c) { (void)c; return false; }
-void tc_carve(const tw_flow_config*, int64_t, int64_t, int64_t, Arena&, TcScratch* out) { out->packed = nullptr; out->scores_op = nullptr; out->packed_bytes = 0; }
-int tc_begin_pass(const tw_flow_config*, const ParamView&, TcScratch&, const float*, const uint8_t*, int64_t, int64_t, int, cudaStream_t) {
-  return fail(TW_ERR_UNSUPPORTED, "tensor-core path not built");
+// ============================================================================================
+// packed-weight layout
+constexpr int kTileBytes128 = 128 * 128 * 2;  // [128 rows x 128 K] bf16 = two [128 x 64] swizzled K blocks
+constexpr int kFfnChunk = 128;                // hidden units per FFN chunk
+
+TcLayout TcLayout::make(const tw_flow_config* c) {
+  TcLayout L{};
+  L.D = c->d_model, L.F = c->dim_feedforward, L.H = c->num_heads, L.E = c->atom_embedding_dim;
+  L.hid = c->mlp_hidden_dims[0], L.T = c->num_transformer_layers;
+  size_t off = 0;
+  L.in_w1 = off, off += (size_t)2 * L.hid * 128;                    // [hid x 64] hi + lo
+  L.in_w2 = off, off += (size_t)2 * (L.hid / 64) * 128 * 128;       // hid/64 K blocks of [128 x 64], hi + lo
+  L.out_w1 = off, off += (size_t)2 * 2 * L.hid * 128;               // 2 K blocks of [hid x 64], hi + lo
+  L.enc0 = off;
+  L.enc_wc = 0;
+  size_t wc_bytes = (size_t)2 * (L.H * L.D / 64) * 128 * 128;       // H*D/64 K blocks of [128 x 64], hi + lo
+  L.enc_ffn = wc_bytes;
+  size_t ffn_bytes = (size_t)(L.F / kFfnChunk) * 4 * kTileBytes128; // per chunk: W1hi, W1lo, W2hi, W2lo
+  L.enc_stride = wc_bytes + ffn_bytes;
+  off += L.enc_stride * L.T;
+  L.net_bytes = align_up(off, 1024);
+  return L;
 }
-int tc_conditioner(const tw_flow_config*, const ParamView&, int, TcScratch&, const int64_t*, const float*, const float*, const float*,
-                   const float*, float* const*, float* const*, float* const*, int64_t, int64_t, int, cudaStream_t) {
-  return fail(TW_ERR_UNSUPPORTED, "tensor-core path not built");
+
+uint32_t tc_stage_mask() {
+  static int cached = -1;
+  if (cached < 0) {
+    const char* e = getenv("TW_TC_STAGES");
+    cached = e ? (atoi(e) & (int)TC_IMPLEMENTED) : (int)TC_IMPLEMENTED;
+  }
+  return (uint32_t)cached;
+}
+
+bool tc_supported(const tw_flow_config* c) {
+  return c->d_model == 128 && c->num_mlp_hidden == 1 && c->mlp_hidden_dims[0] == 256 && c->dim_feedforward % kFfnChunk == 0 &&
+         c->dim_feedforward >= kFfnChunk && c->atom_embedding_dim + 9 <= 64 && c->num_heads >= 1;
+}
+
+// ---- pack kernels ---------------------------------------------------------------------------
+// One CTA writes one [rows x 64] K-major SW128 tile (hi and lo images) from a row-major fp32 matrix.
+__global__ void __launch_bounds__(256) k_pack_tiles(const float* __restrict__ W, int ldw, int n_rows, int n_cols, int rows,
+                                                    int tiles_k, uint8_t* __restrict__ dst, size_t tile_stride_r,
+                                                    size_t tile_stride_k, size_t lo_offset) {
+  // grid: (tiles_k, tiles_r).  tile (tr, tk) covers W rows tr*rows.., columns tk*64..
+  const int tk = blockIdx.x, tr = blockIdx.y;
+  uint8_t* hi = dst + tr * tile_stride_r + tk * tile_stride_k;
+  uint8_t* lo = hi + lo_offset;
+  for (int e = threadIdx.x; e < rows * 32; e += blockDim.x) {
+    int r = e >> 5, kp = (e & 31) * 2;
+    int gr = tr * rows + r, gc = tk * 64 + kp;
+    float a = (gr < n_rows && gc < n_cols) ? W[(size_t)gr * ldw + gc] : 0.f;
+    float b = (gr < n_rows && gc + 1 < n_cols) ? W[(size_t)gr * ldw + gc + 1] : 0.f;
+    uint32_t h, l;
+    split2(a, b, h, l);
+    uint32_t off = sw128_offset(r, kp, rows);  // single K block: k < 64
+    *reinterpret_cast<uint32_t*>(hi + off) = h;
+    *reinterpret_cast<uint32_t*>(lo + off) = l;
+  }
+}
+
+// W_c[i, h*D + j] = sum_k W_o[i, h*D + k] * W_v[h*D + k, j]   (fp64 accumulate): the out-projection of
+// head h composed with its value projection, so that attention becomes  sum_h W_c,h (A_h x).
+__global__ void __launch_bounds__(128) k_combine_wc(const float* __restrict__ Wo, const float* __restrict__ Wv, int D, int H,
+                                                    float* __restrict__ Wc) {
+  const int h = blockIdx.x, i = blockIdx.y, j = threadIdx.x;
+  if (j >= D) return;
+  double acc = 0;
+  for (int k = 0; k < D; k++) acc += (double)Wo[(size_t)i * H * D + h * D + k] * (double)Wv[(size_t)(h * D + k) * D + j];
+  Wc[(size_t)i * H * D + h * D + j] = (float)acc;
+}
+
+static int pack_matrix(const float* W, int ldw, int n_rows, int n_cols, int rows, uint8_t* dst, size_t tile_stride_r,
+                       size_t tile_stride_k, size_t lo_offset, cudaStream_t st) {
+  dim3 grid((n_cols + 63) / 64, (n_rows + rows - 1) / rows);
+  k_pack_tiles<<<grid, 256, 0, st>>>(W, ldw, n_rows, n_cols, rows, grid.x, dst, tile_stride_r, tile_stride_k, lo_offset);
+  TW_LAUNCH_CHECK();
+  return TW_OK;
+}
+
+static int pack_w2_blocks(const float* W2, int F, int D, uint8_t* dst, cudaStream_t st);
+
+size_t tc_packed_bytes(const tw_flow_config* c) {
+  TcLayout L = TcLayout::make(c);
+  return L.total(c) + (size_t)L.D * L.H * L.D * sizeof(float) + 1024;  // + fp32 scratch for W_c
+}
+
+int tc_pack_weights(const tw_flow_config* c, const ParamView& pv, uint8_t* packed, size_t bytes, cudaStream_t st) {
+  TW_CHECK_ARG(tc_supported(c), "configuration not supported by the tensor-core path");
+  TW_CHECK_ARG(packed && bytes >= tc_packed_bytes(c), "packed buffer too small");
+  TW_CHECK_ARG(((uintptr_t)packed & 1023) == 0, "packed buffer must be 1024-byte aligned");
+  TcLayout L = TcLayout::make(c);
+  float* wc_tmp = reinterpret_cast<float*>(packed + align_up(L.total(c), 1024));
+  const int D = L.D, F = L.F, H = L.H, hid = L.hid, Kin = L.E + 9;
+  for (int k = 0; k < c->num_coupling_layers; k++)
+    for (int net = 0; net < 2; net++) {
+      uint8_t* base = packed + L.net_offset(k, net);
+      // in_mlp L1 [hid x Kin] -> one [hid x 64] tile: hi at 0, lo at hid*128
+      TW_TRY(pack_matrix(pv.in_w(k, net, 0), Kin, hid, Kin, hid, base + L.in_w1, 0, 0, (size_t)hid * 128, st));
+      // in_mlp L2 [D x hid] -> hid/64 K blocks [128 x 64]: block kb at kb*32 KB: hi 16 KB, lo 16 KB
+      TW_TRY(pack_matrix(pv.in_w(k, net, 1), hid, D, hid, 128, base + L.in_w2, 0, 2 * 128 * 128, 128 * 128, st));
+      // out_mlp L1 [hid x D] -> 2 K blocks of [hid x 64]: block kb at kb*(2*hid*128): hi, lo
+      TW_TRY(pack_matrix(pv.out_w(k, net, 0), D, hid, D, hid, base + L.out_w1, 0, (size_t)2 * hid * 128, (size_t)hid * 128, st));
+      for (int t = 0; t < L.T; t++) {
+        uint8_t* eb = base + L.enc0 + (size_t)t * L.enc_stride;
+        k_combine_wc<<<dim3(H, D), 128, 0, st>>>(pv.enc(k, net, t, 2), pv.enc(k, net, t, 0), D, H, wc_tmp);
+        TW_LAUNCH_CHECK();
+        // W_c [D x H*D] -> H*D/64 K blocks [128 x 64]: block kb at kb*32 KB: hi 16 KB, lo 16 KB
+        TW_TRY(pack_matrix(wc_tmp, H * D, D, H * D, 128, eb + L.enc_wc, 0, 2 * 128 * 128, 128 * 128, st));
+        // FFN chunk c: [W1hi | W1lo | W2hi | W2lo], each 32 KB = K blocks kb0, kb1 of [128 x 64]
+        //   W1 [F x D]: rows c*128.., all D=128 columns  -> tile (tr=c, tk) at c*128KB + tk*16KB, lo +32KB
+        TW_TRY(pack_matrix(pv.enc(k, net, t, 3), D, F, D, 128, eb + L.enc_ffn, 4 * kTileBytes128, 128 * 128, kTileBytes128, st));
+        //   W2 [D x F]: K block b (columns b*64..) -> chunk b/2, K block b%2 of the W2hi / W2lo tiles
+        TW_TRY(pack_w2_blocks(pv.enc(k, net, t, 5), F, D, eb + L.enc_ffn + 2 * kTileBytes128, st));
+      }
+    }
+  return TW_OK;
+}
+
+// W2 [D x F] K blocks: block index b = 0..F/64-1 covers columns b*64..; destination chunk = b/2, K block = b%2.
+__global__ void __launch_bounds__(256) k_pack_w2(const float* __restrict__ W2, int F, int D, uint8_t* __restrict__ dst) {
+  const int b = blockIdx.x;
+  uint8_t* hi = dst + (size_t)(b >> 1) * 4 * kTileBytes128 + (b & 1) * (128 * 128);
+  uint8_t* lo = hi + kTileBytes128;
+  for (int e = threadIdx.x; e < 128 * 32; e += blockDim.x) {
+    int r = e >> 5, kp = (e & 31) * 2;
+    float a = 0.f, c = 0.f;
+    if (r < D) {
+      a = W2[(size_t)r * F + b * 64 + kp];
+      c = W2[(size_t)r * F + b * 64 + kp + 1];
+    }
+    uint32_t h, l;
+    split2(a, c, h, l);
+    uint32_t off = sw128_offset(r, kp, 128);
+    *reinterpret_cast<uint32_t*>(hi + off) = h;
+    *reinterpret_cast<uint32_t*>(lo + off) = l;
+  }
+}
+static int pack_w2_blocks(const float* W2, int F, int D, uint8_t* dst, cudaStream_t st) {
+  k_pack_w2<<<F / 64, 256, 0, st>>>(W2, F, D, dst);
+  TW_LAUNCH_CHECK();
+  return TW_OK;
+}
+
+// ============================================================================================
+// Fused FFN:  out = LayerNorm(x + W2 relu(W1 x + b1) + b2)         custom_attention_encoder.py:111-113
+//
+// Persistent CTAs (grid.x per network, grid.y = network), 128-token tiles.  Warp roles:
+//   warp 0  : bulk-copy producer -- streams 32 KB weight tiles (W1hi, W1lo, W2hi, W2lo per chunk of 128
+//             hidden units) through a shared-memory ring
+//   warp 1  : one thread issues tcgen05.mma:  D1[c&1] = X W1c^T (SS),  Y += H_c W2c^T (TS, A from TMEM)
+//   warps 2-5: (a) x tile fp32 -> bf16 hi/lo operand images in shared memory, (b) per chunk: D1 -> +b1,
+//             ReLU, hi/lo split -> H in TMEM, (c) Y -> +b2 + residual -> LayerNorm -> global.
+// The 128x2048 hidden activation never leaves the SM.  TMEM: D1 2x128 | H hi 64 | H lo 64 | Y 128 columns.
+constexpr int kFfnStages = 4;
+constexpr int kStageBytes = kTileBytes128;
+constexpr uint32_t TM_D1 = 0, TM_HHI = 256, TM_HLO = 320, TM_Y = 384;
+
+struct FfnArgs {
+  const float* x[2];       // [M,128] layer input (post-LN1)
+  float* out[2];           // [M,128]
+  const uint8_t* w[2];     // packed FFN chunks of this layer (per net)
+  const float* b1[2];
+  const float* b2[2];
+  const float* gamma[2];
+  const float* beta[2];
+  int64_t M;
+  int F;
+  float eps;
+};
+
+struct FfnSmem {
+  static constexpr int X_HI = 0;
+  static constexpr int X_LO = 32 * 1024;
+  static constexpr int RING = 64 * 1024;
+  static constexpr int B1 = RING + kFfnStages * kStageBytes;       // F floats (<= 4096)
+  static constexpr int VEC = B1 + 4096 * 4;                        // b2, gamma, beta: 3*128 floats
+  static constexpr int BARS = VEC + 3 * 128 * 4;
+  static constexpr int TOTAL = BARS + 256;
+};
+
+template <int kSplit>
+__global__ void __launch_bounds__(192, 1) k_ffn_tc(FfnArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int net = blockIdx.y;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n_chunks = a.F / kFfnChunk;
+  const int64_t n_tiles = (a.M + 127) / 128;
+  constexpr int kTilesPerChunk = (kSplit == 3) ? 4 : 2;
+
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FfnSmem::BARS);
+  uint64_t* full = bars;                  // [kFfnStages]
+  uint64_t* empty = bars + kFfnStages;    // [kFfnStages]
+  uint64_t* d1_full = bars + 2 * kFfnStages;  // [2]
+  uint64_t* h_full = d1_full + 2;
+  uint64_t* h_free = h_full + 1;
+  uint64_t* x_full = h_free + 1;
+  uint64_t* x_free = x_full + 1;
+  uint64_t* y_full = x_free + 1;
+  uint64_t* y_free = y_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(y_free + 1);
+
+  float* b1s = reinterpret_cast<float*>(smem + FfnSmem::B1);
+  float* vecs = reinterpret_cast<float*>(smem + FfnSmem::VEC);
+
+  if (tid == 0) {
+    for (int i = 0; i < kFfnStages; i++) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(&d1_full[0], 1);
+    mbar_init(&d1_full[1], 1);
+    mbar_init(h_full, 128);
+    mbar_init(h_free, 1);
+    mbar_init(x_full, 128);
+    mbar_init(x_free, 1);
+    mbar_init(y_full, 1);
+    mbar_init(y_free, 128);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  for (int i = tid; i < a.F; i += blockDim.x) b1s[i] = a.b1[net][i];
+  for (int i = tid; i < 128; i += blockDim.x) {
+    vecs[i] = a.b2[net][i];
+    vecs[128 + i] = a.gamma[net][i];
+    vecs[256 + i] = a.beta[net][i];
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ producer
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      const uint8_t* wbase = a.w[net];
+      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (int c = 0; c <= n_chunks; c++) {
+          // consumption order: G1(c) then G2(c-1)
+          for (int op = 0; op < 2; op++) {
+            int chunk = (op == 0) ? c : c - 1;
+            if (chunk < 0 || chunk >= n_chunks) continue;
+            for (int part = 0; part < (kSplit == 3 ? 2 : 1); part++) {
+              const uint8_t* src = wbase + (size_t)chunk * 4 * kTileBytes128 + (size_t)(op * 2 + part) * kTileBytes128;
+              mbar_wait(&empty[stage], phase ^ 1);
+              mbar_arrive_expect_tx(&full[stage], kStageBytes);
+              bulk_g2s(smem + FfnSmem::RING + stage * kStageBytes, src, kStageBytes, &full[stage]);
+              if (++stage == kFfnStages) stage = 0, phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      uint32_t ph_x = 0, ph_h = 0, ph_yfree = 0;
+      const uint32_t idesc = make_idesc_bf16(128, 128, 0, 0);
+      const uint32_t xhi = smem_u32(smem + FfnSmem::X_HI), xlo = smem_u32(smem + FfnSmem::X_LO);
+      const uint32_t ring = smem_u32(smem + FfnSmem::RING);
+      bool first_tile = true;
+      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        mbar_wait(x_full, ph_x);
+        ph_x ^= 1;
+        tc_fence_after();
+        for (int c = 0; c <= n_chunks; c++) {
+          if (c < n_chunks) {
+            const uint32_t d1 = tmem + TM_D1 + (c & 1) * 128;
+            // W1 hi tile: Xhi*W1hi, Xlo*W1hi
+            mbar_wait(&full[stage], phase);
+            tc_fence_after();
+            {
+              const uint32_t wt = ring + stage * kStageBytes;
+#pragma unroll
+              for (int k = 0; k < 8; k++) {
+                uint32_t koff = (k >> 2) * 16384 + (k & 3) * 32;
+                mma_ss(d1, desc_kmajor_sw128(xhi + koff), desc_kmajor_sw128(wt + koff), idesc, k > 0);
+              }
+              if (kSplit == 3) {
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                  uint32_t koff = (k >> 2) * 16384 + (k & 3) * 32;
+                  mma_ss(d1, desc_kmajor_sw128(xlo + koff), desc_kmajor_sw128(wt + koff), idesc, 1);
+                }
+              }
+            }
+            mma_commit(&empty[stage]);
+            if (++stage == kFfnStages) stage = 0, phase ^= 1;
+            if (kSplit == 3) {  // W1 lo tile: Xhi*W1lo
+              mbar_wait(&full[stage], phase);
+              tc_fence_after();
+              const uint32_t wt = ring + stage * kStageBytes;
+#pragma unroll
+              for (int k = 0; k < 8; k++) {
+                uint32_t koff = (k >> 2) * 16384 + (k & 3) * 32;
+                mma_ss(d1, desc_kmajor_sw128(xhi + koff), desc_kmajor_sw128(wt + koff), idesc, 1);
+              }
+              mma_commit(&empty[stage]);
+              if (++stage == kFfnStages) stage = 0, phase ^= 1;
+            }
+            mma_commit(&d1_full[c & 1]);
+            if (c == n_chunks - 1) mma_commit(x_free);  // every read of the X images has completed
+          }
+          if (c >= 1) {
+            const int j = c - 1;
+            mbar_wait(h_full, ph_h);  // epilogue warps have written H_j (and drained D1[j&1])
+            ph_h ^= 1;
+            if (j == 0 && !first_tile) {
+              mbar_wait(y_free, ph_yfree);  // previous tile's Y has been read out
+              ph_yfree ^= 1;
+            }
+            tc_fence_after();
+            mbar_wait(&full[stage], phase);
+            tc_fence_after();
+            {
+              const uint32_t wt = ring + stage * kStageBytes;
+#pragma unroll
+              for (int k = 0; k < 8; k++) {
+                uint32_t koff = (k >> 2) * 16384 + (k & 3) * 32;
+                mma_ts(tmem + TM_Y, tmem + TM_HHI + k * 8, desc_kmajor_sw128(wt + koff), idesc, (j > 0 || k > 0) ? 1 : 0);
+              }
+              if (kSplit == 3) {
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                  uint32_t koff = (k >> 2) * 16384 + (k & 3) * 32;
+                  mma_ts(tmem + TM_Y, tmem + TM_HLO + k * 8, desc_kmajor_sw128(wt + koff), idesc, 1);
+                }
+              }
+            }
+            mma_commit(&empty[stage]);
+            if (++stage == kFfnStages) stage = 0, phase ^= 1;
+            if (kSplit == 3) {
+              mbar_wait(&full[stage], phase);
+              tc_fence_after();
+              const uint32_t wt = ring + stage * kStageBytes;
+#pragma unroll
+              for (int k = 0; k < 8; k++) {
+                uint32_t koff = (k >> 2) * 16384 + (k & 3) * 32;
+                mma_ts(tmem + TM_Y, tmem + TM_HHI + k * 8, desc_kmajor_sw128(wt + koff), idesc, 1);
+              }
+              mma_commit(&empty[stage]);
+              if (++stage == kFfnStages) stage = 0, phase ^= 1;
+            }
+            mma_commit(h_free);
+            if (j == n_chunks - 1) mma_commit(y_full);
+          }
+        }
+        first_tile = false;
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ convert / epilogue warps (128 threads)
+    const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;          // token row inside the tile
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    const int ew = warp - 2;                // 0..3: slice of the tile this warp converts
+    uint32_t ph_d1[2] = {0, 0}, ph_hfree = 0, ph_xfree = 0, ph_y = 0;
+    bool first_tile = true, first_chunk_ever = true;
+    const float* x = a.x[net];
+    float* out = a.out[net];
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const int64_t row0 = tile * 128;
+      // ---- (a) x tile -> bf16 hi/lo operand images (K-major, 128B swizzle)
+      if (!first_tile) {
+        mbar_wait(x_free, ph_xfree);
+        ph_xfree ^= 1;
+      }
+#pragma unroll 1
+      for (int it = 0; it < 32; it += 8) {
+        float4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+          int r = ew * 32 + it + u;
+          v[u] = (row0 + r < a.M) ? __ldg(reinterpret_cast<const float4*>(x + (row0 + r) * 128) + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+          int r = ew * 32 + it + u;
+          uint32_t h0, l0, h1, l1;
+          split2(v[u].x, v[u].y, h0, l0);
+          split2(v[u].z, v[u].w, h1, l1);
+          uint32_t off = sw128_offset(r, lane * 4, 128);
+          *reinterpret_cast<uint2*>(smem + FfnSmem::X_HI + off) = make_uint2(h0, h1);
+          *reinterpret_cast<uint2*>(smem + FfnSmem::X_LO + off) = make_uint2(l0, l1);
+        }
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(x_full);
+
+      // ---- (b) per chunk: D1 -> bias + ReLU -> hi/lo -> H (TMEM)
+      for (int c = 0; c < n_chunks; c++) {
+        mbar_wait(&d1_full[c & 1], ph_d1[c & 1]);
+        ph_d1[c & 1] ^= 1;
+        if (!first_chunk_ever) {
+          mbar_wait(h_free, ph_hfree);  // G2 of the previous chunk has consumed H
+          ph_hfree ^= 1;
+        }
+        first_chunk_ever = false;
+        tc_fence_after();
+        const float* bc = b1s + c * kFfnChunk;
+#pragma unroll 1
+        for (int g = 0; g < 4; g++) {
+          uint32_t r[32];
+          tmem_ld32(tmem + lane_base + TM_D1 + (c & 1) * 128 + g * 32, r);
+          tmem_ld_wait();
+          uint32_t hi[16], lo[16];
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            float2 bb = *reinterpret_cast<const float2*>(bc + g * 32 + j);
+            float v0 = fmaxf(__uint_as_float(r[j]) + bb.x, 0.f);
+            float v1 = fmaxf(__uint_as_float(r[j + 1]) + bb.y, 0.f);
+            split2(v0, v1, hi[j >> 1], lo[j >> 1]);
+          }
+          tmem_st16(tmem + lane_base + TM_HHI + g * 16, hi);
+          if (kSplit == 3) tmem_st16(tmem + lane_base + TM_HLO + g * 16, lo);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(h_full);
+      }
+
+      // ---- (c) Y -> + b2 + residual -> LayerNorm -> global
+      mbar_wait(y_full, ph_y);
+      ph_y ^= 1;
+      tc_fence_after();
+      float v[128];
+#pragma unroll
+      for (int g = 0; g < 4; g++) {
+        uint32_t r[32];
+        tmem_ld32(tmem + lane_base + TM_Y + g * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; j++) v[g * 32 + j] = __uint_as_float(r[j]);
+      }
+      tc_fence_before();
+      mbar_arrive(y_free);  // Y is in registers: the next tile may overwrite it
+      const int64_t grow = row0 + row;
+      if (grow < a.M) {
+        const float4* xr = reinterpret_cast<const float4*>(x + grow * 128);
+        float sum = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; j++) {
+          float4 xv = __ldg(xr + j);
+          float4 bv = *reinterpret_cast<const float4*>(vecs + 4 * j);
+          v[4 * j + 0] += bv.x + xv.x;
+          v[4 * j + 1] += bv.y + xv.y;
+          v[4 * j + 2] += bv.z + xv.z;
+          v[4 * j + 3] += bv.w + xv.w;
+          sum += (v[4 * j] + v[4 * j + 1]) + (v[4 * j + 2] + v[4 * j + 3]);
+        }
+        const float mean = sum * (1.f / 128.f);
+        float sq = 0.f;
+#pragma unroll
+        for (int j = 0; j < 128; j++) {
+          float d = v[j] - mean;
+          sq = fmaf(d, d, sq);
+        }
+        const float rstd = 1.0f / sqrtf(sq * (1.f / 128.f) + a.eps);
+        float4* orow = reinterpret_cast<float4*>(out + grow * 128);
+#pragma unroll
+        for (int j = 0; j < 32; j++) {
+          float4 g4 = *reinterpret_cast<const float4*>(vecs + 128 + 4 * j);
+          float4 b4 = *reinterpret_cast<const float4*>(vecs + 256 + 4 * j);
+          float4 o;
+          o.x = (v[4 * j + 0] - mean) * rstd * g4.x + b4.x;
+          o.y = (v[4 * j + 1] - mean) * rstd * g4.y + b4.y;
+          o.z = (v[4 * j + 2] - mean) * rstd * g4.z + b4.z;
+          o.w = (v[4 * j + 3] - mean) * rstd * g4.w + b4.w;
+          orow[j] = o;
+        }
+      }
+      first_tile = false;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(tmem);
+}
+
+static int launch_ffn_tc(const tw_flow_config* c, const FfnArgs& a, cudaStream_t st) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    TW_CUDA(cudaFuncSetAttribute(k_ffn_tc<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, FfnSmem::TOTAL + 1024));
+    TW_CUDA(cudaFuncSetAttribute(k_ffn_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FfnSmem::TOTAL + 1024));
+    attr_done = true;
+  }
+  TW_CHECK_ARG(a.F <= 4096, "dim_feedforward > 4096 not supported by the tensor-core FFN");
+  int sms = 148;
+  int64_t n_tiles = (a.M + 127) / 128;
+  int gx = (int)((n_tiles < sms / 2) ? n_tiles : sms / 2);
+  if (gx < 1) return TW_OK;
+  dim3 grid(gx, 2);
+  ProfScope prof(PROF_FFN, st);
+  if (c->precision == TW_PRECISION_BF16X3)
+    k_ffn_tc<3><<<grid, 192, FfnSmem::TOTAL + 1024, st>>>(a);
+  else
+    k_ffn_tc<1><<<grid, 192, FfnSmem::TOTAL + 1024, st>>>(a);
+  TW_LAUNCH_CHECK();
+  return TW_OK;
+}
+
+// ============================================================================================
+// orchestration of one conditioner pair (scale net, shift net) of coupling layer k
+void tc_carve(const tw_flow_config* c, int64_t n, int64_t n_cond, int64_t V, Arena& ar, TcScratch* out) {
+  (void)n_cond;
+  const int64_t M = n * V;
+  for (int i = 0; i < 2; i++) out->mixed[i] = ar.take<float>(M * c->num_heads * c->d_model);
+  for (int i = 0; i < 2; i++) out->hidden[i] = ar.take<float>(M * c->mlp_hidden_dims[0]);
+  out->feat = ar.take<float>(M * (c->atom_embedding_dim + 9));
+}
+
+int tc_begin_pass(const tw_flow_config*, const ParamView&, TcScratch&, const float*, const uint8_t*, int64_t, int64_t, int,
+                  cudaStream_t) {
+  return TW_OK;
+}
+
+int tc_ffn_layer(const tw_flow_config* c, const ParamView& pv, int k, int t, const TcScratch& tc, float* const x[2],
+                 float* const out[2], int64_t M, cudaStream_t st) {
+  TcLayout L = TcLayout::make(c);
+  FfnArgs a{};
+  for (int s = 0; s < 2; s++) {
+    a.x[s] = x[s];
+    a.out[s] = out[s];
+    a.w[s] = tc.packed + L.net_offset(k, s) + L.enc0 + (size_t)t * L.enc_stride + L.enc_ffn;
+    a.b1[s] = pv.enc(k, s, t, 4);
+    a.b2[s] = pv.enc(k, s, t, 6);
+    a.gamma[s] = pv.enc(k, s, t, 9);
+    a.beta[s] = pv.enc(k, s, t, 10);
+  }
+  a.M = M;
+  a.F = c->dim_feedforward;
+  a.eps = c->layer_norm_eps;
+  return launch_ffn_tc(c, a, st);
 }
 
 }  // namespace tw

@@ -1,22 +1,47 @@
 // Tensor-core (tcgen05 / TMEM / bulk-TMA) path of the conditioner networks for the flagship
-// layer sizes (d_model 128, one MLP hidden layer of 256, dim_feedforward % 128 == 0).
+// layer sizes: d_model 128, one MLP hidden layer of 256, dim_feedforward % 128 == 0,
+// atom_embedding_dim + 9 <= 64, num_heads * 128 = value width.
+//
+// Weights are re-packed once (tw_flow_pack_weights) into bf16 "operand images": [rows x 64] K-major
+// tiles in the 128-byte-swizzled shared-memory layout tcgen05.mma reads, hi part (bf16(w)) and lo
+// part (bf16(w - hi)), so that a kernel fetches a tile with ONE bulk async copy (no tensor map).
 #pragma once
 #include "flow_simt.cuh"
 
 namespace tw {
 
-struct TcScratch {
-  void* packed;     // packed bf16 weight images of the layer in flight
-  void* scores_op;  // attention-score operand images
-  size_t packed_bytes;
+// byte sizes / offsets of the packed image of ONE conditioner network (scale or shift) of ONE coupling layer
+struct TcLayout {
+  int D, F, H, E, hid, T;
+  size_t in_w1, in_w2, out_w1;       // MLP weight images
+  size_t enc0, enc_stride;            // first encoder layer, stride between encoder layers
+  size_t enc_wc, enc_ffn;             // inside an encoder layer: combined attention projection, FFN chunks
+  size_t net_bytes;
+  __host__ static TcLayout make(const tw_flow_config* c);
+  __host__ size_t net_offset(int k, int net) const { return (size_t)(k * 2 + net) * net_bytes; }
+  __host__ size_t total(const tw_flow_config* c) const { return (size_t)c->num_coupling_layers * 2 * net_bytes; }
 };
 
+struct TcScratch {
+  float* mixed[2];   // [M, H*D] fp32: per-head neighbourhood averages of the layer input
+  float* hidden[2];  // [M, hid] fp32 (SIMT stages of the hybrid path)
+  float* feat;       // [M, E+9]
+  const uint8_t* packed;  // packed weights (caller-owned, persistent)
+  uint32_t stages;   // bit mask of stages that run on tensor cores (debug / bring-up)
+};
+
+enum TcStage : uint32_t { TC_FFN = 1, TC_ATTN_PROJ = 2, TC_MIX = 4, TC_IN_MLP = 8, TC_OUT_MLP = 16, TC_ALL = 31 };
+constexpr uint32_t TC_IMPLEMENTED = TC_FFN;  // stages with a tensor-core kernel; the rest run on CUDA cores
+
 bool tc_supported(const tw_flow_config* c);
+uint32_t tc_stage_mask();  // TW_TC_STAGES environment override (bring-up), default: every stage that exists
 void tc_carve(const tw_flow_config* c, int64_t n, int64_t n_cond, int64_t V, Arena& ar, TcScratch* out);
+int tc_pack_weights(const tw_flow_config* c, const ParamView& pv, uint8_t* packed, size_t bytes, cudaStream_t st);
 int tc_begin_pass(const tw_flow_config* c, const ParamView& pv, TcScratch& tc, const float* scores, const uint8_t* mask,
                   int64_t n, int64_t n_cond, int V, cudaStream_t st);
-int tc_conditioner(const tw_flow_config* c, const ParamView& pv, int k, TcScratch& tc, const int64_t* atom_types,
-                   const float* xc, const float* xv, const float* z_other, const float* scores, float* const actA[2],
-                   float* const actB[2], float* const st_out[2], int64_t n, int64_t n_cond, int V, cudaStream_t st);
+size_t tc_packed_bytes(const tw_flow_config* c);
+// fused FFN + residual + LayerNorm of encoder layer t for both networks: out = LN2(x + FFN(x))
+int tc_ffn_layer(const tw_flow_config* c, const ParamView& pv, int k, int t, const TcScratch& tc, float* const x[2],
+                 float* const out[2], int64_t M, cudaStream_t st);
 
 }  // namespace tw

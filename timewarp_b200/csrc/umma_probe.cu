@@ -1,0 +1,142 @@
+// Hardware probe for the tcgen05 building blocks (debug entry point, used by tools/umma_probe.py
+// and tests/test_gpu_umma.py): one CTA computes out[128,N] = A[128,K] * B[N,K]^T with bf16 inputs
+// through a selectable operand placement / layout, so that every descriptor convention the
+// production kernels rely on is checked against a CPU result on the real chip.
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace tw {
+using namespace umma;
+
+struct ProbeArgs {
+  const float* A;  // [128,K]
+  const float* B;  // [N,K]
+  float* out;      // [128,N]
+  int N, K;
+  int a_mode;  // 0 smem K-major SW128, 1 smem K-major no-swizzle, 2 smem MN-major SW128, 3 TMEM (TS)
+  int b_mode;  // 0 K-major SW128, 1 K-major no-swizzle, 2 MN-major SW128
+  int d_col;   // column offset of the accumulator inside the TMEM allocation
+  int a_col;   // column offset of A in TMEM (a_mode 3)
+  int* status;  // 0 ok, 1 timeout
+};
+
+__device__ __forceinline__ uint32_t off_kmajor_none(uint32_t row, uint32_t k, uint32_t K) {
+  return (row >> 3) * ((K >> 3) * 128u) + (k >> 3) * 128u + (row & 7u) * 16u + (k & 7u) * 2u;
+}
+__device__ __forceinline__ uint32_t off_mnmajor_sw128(uint32_t mn, uint32_t k, uint32_t K) {
+  return (mn >> 6) * ((K >> 3) * 1024u) + (k >> 3) * 1024u + (k & 7u) * 128u + ((((mn & 63u) >> 3) ^ (k & 7u)) << 4) + (mn & 7u) * 2u;
+}
+
+__global__ void __launch_bounds__(128, 1) k_umma_probe(ProbeArgs p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;                      // up to 128*256*2 = 64 KB
+  uint8_t* sB = smem + 64 * 1024;          // up to 256*256*2 = 128 KB
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int N = p.N, K = p.K;
+
+  if (warp == 0) tmem_alloc<512>(&tmem_slot);
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    mbar_fence_init();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+
+  // ---- operands -> smem (bf16), zero-filled first
+  for (int i = tid; i < (64 + 128) * 1024 / 16; i += 128) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  __syncthreads();
+  if (p.a_mode != 3) {
+    for (int e = tid; e < 128 * K; e += 128) {
+      int r = e / K, k = e % K;
+      uint32_t off = p.a_mode == 0 ? sw128_offset(r, k, 128) : (p.a_mode == 1 ? off_kmajor_none(r, k, K) : off_mnmajor_sw128(r, k, K));
+      *reinterpret_cast<__nv_bfloat16*>(sA + off) = __float2bfloat16(p.A[r * K + k]);
+    }
+  } else {
+    // A -> TMEM: lane = row, column c holds elements (2c, 2c+1) as packed bf16x2
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    for (int c0 = 0; c0 < K / 2; c0 += 16) {
+      uint32_t r[16];
+#pragma unroll
+      for (int j = 0; j < 16; j++) {
+        int k = 2 * (c0 + j);
+        r[j] = (k < K) ? pack_bf16x2(p.A[tid * K + k], p.A[tid * K + k + 1]) : 0u;
+      }
+      tmem_st16(tmem + lane_base + p.a_col + c0, r);
+    }
+    tmem_st_wait();
+  }
+  for (int e = tid; e < N * K; e += 128) {
+    int r = e / K, k = e % K;
+    uint32_t off = p.b_mode == 0 ? sw128_offset(r, k, N) : (p.b_mode == 1 ? off_kmajor_none(r, k, K) : off_mnmajor_sw128(r, k, K));
+    *reinterpret_cast<__nv_bfloat16*>(sB + off) = __float2bfloat16(p.B[r * K + k]);
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+
+  if (tid == 0) {
+    tc_fence_after();
+    const uint32_t idesc = make_idesc_bf16(128, N, p.a_mode == 2 ? 1 : 0, p.b_mode == 2 ? 1 : 0);
+    const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
+    for (int k0 = 0; k0 < K; k0 += 16) {
+      uint64_t bd;
+      if (p.b_mode == 0) bd = desc_kmajor_sw128(b0 + (k0 >> 6) * (N * 128) + (k0 & 63) * 2);
+      else if (p.b_mode == 1) bd = make_smem_desc(b0 + (k0 >> 3) * 128, 128, (K >> 3) * 128, LAYOUT_NONE);
+      else bd = make_smem_desc(b0 + (k0 >> 3) * 1024, (K >> 3) * 1024, 1024, LAYOUT_SW128);
+      if (p.a_mode == 3) {
+        mma_ts(tmem + p.d_col, tmem + p.a_col + (k0 >> 1), bd, idesc, k0 > 0);
+      } else {
+        uint64_t ad;
+        if (p.a_mode == 0) ad = desc_kmajor_sw128(a0 + (k0 >> 6) * (128 * 128) + (k0 & 63) * 2);
+        else if (p.a_mode == 1) ad = make_smem_desc(a0 + (k0 >> 3) * 128, 128, (K >> 3) * 128, LAYOUT_NONE);
+        else ad = make_smem_desc(a0 + (k0 >> 3) * 1024, (K >> 3) * 1024, 1024, LAYOUT_SW128);
+        mma_ss(tmem + p.d_col, ad, bd, idesc, k0 > 0);
+      }
+    }
+    mma_commit(&bar);
+  }
+  // wait with a timeout so that a wrong assumption cannot hang the box
+  {
+    long long t0 = clock64();
+    bool ok = false;
+    while (!(ok = mbar_try_wait(&bar, 0))) {
+      if (clock64() - t0 > 2000000000LL) break;
+    }
+    if (!ok && tid == 0) *p.status = 1;
+  }
+  tc_fence_after();
+  const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+  for (int c0 = 0; c0 < N; c0 += 16) {
+    uint32_t r[16];
+    tmem_ld16(tmem + lane_base + p.d_col + c0, r);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 16; j++)
+      if (c0 + j < N) p.out[tid * N + c0 + j] = __uint_as_float(r[j]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<512>(tmem);
+}
+
+}  // namespace tw
+
+using namespace tw;
+
+extern "C" int tw_debug_umma_probe(const float* A, const float* B, float* out, int N, int K, int a_mode, int b_mode, int d_col,
+                                   int a_col, int* status, void* stream) {
+  TW_CHECK_ARG(A && B && out && status, "NULL pointer");
+  TW_CHECK_ARG(N >= 8 && N <= 256 && N % 8 == 0 && K >= 16 && K <= 256 && K % 16 == 0, "bad N/K");
+  TW_CHECK_ARG(d_col >= 0 && d_col + N <= 512 && a_col >= 0 && a_col + K / 2 <= 512, "bad TMEM columns");
+  const int smem = (64 + 128) * 1024 + 1024;
+  TW_CUDA(cudaFuncSetAttribute(k_umma_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  ProbeArgs p{A, B, out, N, K, a_mode, b_mode, d_col, a_col, status};
+  k_umma_probe<<<1, 128, smem, (cudaStream_t)stream>>>(p);
+  TW_LAUNCH_CHECK();
+  return TW_OK;
+}

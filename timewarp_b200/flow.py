@@ -47,6 +47,7 @@ class ConditionalFlowDensityModel(nn.Module):
         self._cfg = flow_config
         self._table = None  # (ctypes array, keep-alive list)
         self._workspace: Optional[Tensor] = None
+        self._packed = None  # (buffer, aligned ptr, key): bf16 operand images of the weights (tensor-core precisions)
 
     # ---------------------------------------------------------------- plumbing
     @property
@@ -55,11 +56,13 @@ class ConditionalFlowDensityModel(nn.Module):
 
     def set_precision(self, precision: str) -> "ConditionalFlowDensityModel":
         self._cfg.precision = _lib.PRECISION[precision]
+        self._workspace = None
         return self
 
     def _apply(self, fn, *a, **kw):  # .to()/.cuda()/.float() move the parameters: rebuild the pointer table
         self._table = None
         self._workspace = None
+        self._packed = None
         return super()._apply(fn, *a, **kw)
 
     def load_state_dict(self, *a, **kw):
@@ -101,6 +104,24 @@ class ConditionalFlowDensityModel(nn.Module):
             arr = (C.c_void_p * n)(*[t.data_ptr() for t in tensors])
             self._table = (arr, tensors, device)
         return self._table[0]
+
+    def _packed_weights(self, device) -> Optional[int]:
+        """Device pointer of the packed bf16 weight images (None for fp32).  Re-packed whenever a
+        parameter was modified in place (optimizer step, load_state_dict) or the precision changed."""
+        if self._cfg.precision == _lib.PRECISION["fp32"]:
+            return None
+        table = self._param_table(device)
+        key = (self._cfg.precision, tuple(t._version for t in self._table[1]))
+        if self._packed is None or self._packed[2] != key or self._packed[0].device != device:
+            lib = _lib.load()
+            need = C.c_size_t(0)
+            _lib.check(lib.tw_flow_packed_bytes(C.byref(self._cfg), C.byref(need)), "tw_flow_packed_bytes")
+            buf = self._packed[0] if (self._packed is not None and self._packed[0].numel() >= need.value + 1024
+                                      and self._packed[0].device == device) else torch.empty(need.value + 1024, dtype=torch.uint8, device=device)
+            aligned = (buf.data_ptr() + 1023) // 1024 * 1024
+            _lib.check(lib.tw_flow_pack_weights(C.byref(self._cfg), table, aligned, need.value, self._stream(device)), "tw_flow_pack_weights")
+            self._packed = (buf, aligned, key)
+        return self._packed[1]
 
     def _get_workspace(self, n: int, n_cond: int, V: int, device) -> Tuple[Tensor, int]:
         lib = _lib.load()
@@ -182,7 +203,7 @@ class ConditionalFlowDensityModel(nn.Module):
             lib.tw_flow_log_likelihood(
                 C.byref(self._cfg), table, _lib.ptr(atom_types), _lib.ptr(x_coords), _lib.ptr(x_velocs), _lib.ptr(y_coords),
                 _lib.ptr(y_velocs), _lib.ptr(mask_u8), B, V, self._flags(), _lib.ptr(out), _lib.ptr(zc), _lib.ptr(zv),
-                _lib.ptr(ws), ws_bytes, self._stream(dev),
+                self._packed_weights(dev), _lib.ptr(ws), ws_bytes, self._stream(dev),
             ),
             "tw_flow_log_likelihood",
         )  # fmt: skip
@@ -246,7 +267,7 @@ class ConditionalFlowDensityModel(nn.Module):
             lib.tw_flow_sample(
                 C.byref(self._cfg), table, _lib.ptr(atom_types), _lib.ptr(x_coords), _lib.ptr(x_velocs), _lib.ptr(mask_u8),
                 B, V, S, self._flags(), _lib.ptr(z_coords), _lib.ptr(z_velocs), _lib.ptr(y_coords), _lib.ptr(y_velocs),
-                _lib.ptr(logp), _lib.ptr(ws), ws_bytes, self._stream(dev),
+                _lib.ptr(logp), self._packed_weights(dev), _lib.ptr(ws), ws_bytes, self._stream(dev),
             ),
             "tw_flow_sample",
         )  # fmt: skip
@@ -279,8 +300,8 @@ class ConditionalFlowDensityModel(nn.Module):
         _lib.check(
             _lib.load().tw_flow_scale_shift(
                 C.byref(self._cfg), self._param_table(dev), int(layer_idx), _lib.ptr(at), _lib.ptr(x), _lib.ptr(args[0]),
-                _lib.ptr(args[1]), _lib.ptr(args[2]), _lib.ptr(mask), B, V, _lib.ptr(scale), _lib.ptr(shift), _lib.ptr(ws),
-                ws_bytes, self._stream(dev),
+                _lib.ptr(args[1]), _lib.ptr(args[2]), _lib.ptr(mask), B, V, _lib.ptr(scale), _lib.ptr(shift),
+                self._packed_weights(dev), _lib.ptr(ws), ws_bytes, self._stream(dev),
             ),
             "tw_flow_scale_shift",
         )  # fmt: skip
