@@ -62,6 +62,7 @@ static size_t carve(const tw_flow_config* c, int64_t n, int64_t n_cond, int64_t 
     b.ffn[i] = (c->precision == TW_PRECISION_FP32 || !(tc_stage_mask() & TC_FFN)) ? ar.take<float>(M * F) : nullptr;
   }
   b.tc = TcScratch{};
+  if (c->precision != TW_PRECISION_FP32) tc_carve(c, n, n_cond, V, ar, &b.tc);
   if (fb) *fb = b;
   return align_up(ar.off, 256);
 }
@@ -88,7 +89,7 @@ static int conditioner(PassCtx& p, int k) {
   const int D = c->d_model, H = c->num_heads, F = c->dim_feedforward, E = c->atom_embedding_dim, nh = c->num_mlp_hidden;
   const bool pos = (k % 2) == c->position_layer_index_mod_2;
   const uint32_t tcs = (c->precision == TW_PRECISION_FP32) ? 0u : tc_stage_mask();
-  TcScratch tcx{};
+  TcScratch tcx = b.tc;
   tcx.packed = p.packed;
   TW_TRY(launch_features(p.pv.embed(), p.atom_types, b.xc, p.x_velocs, pos ? b.zv : b.zc, p.n, p.n_cond, p.V, E,
                          c->num_atom_types, b.feat, p.st));
@@ -108,15 +109,19 @@ static int conditioner(PassCtx& p, int k) {
     TW_TRY(launch_linear(a, 2, M, D, cur_dim, cur_dim, 0, D, ACT_NONE, p.st));
   }
   for (int t = 0; t < c->num_transformer_layers; t++) {
-    Lin2 a{};
-    for (int s = 0; s < 2; s++) a.X[s] = b.actA[s], a.W[s] = p.pv.enc(k, s, t, 0), a.Y[s] = b.vals[s];
-    TW_TRY(launch_linear(a, 2, M, H * D, D, D, 0, H * D, ACT_NONE, p.st));
-    TW_TRY(launch_attn_mix(b.scores, b.vals[0], b.vals[1], b.att[0], b.att[1], 2, p.n, p.n_cond, p.V, H, D, p.st));
-    Lin2 o{};
-    for (int s = 0; s < 2; s++) o.X[s] = b.att[s], o.W[s] = p.pv.enc(k, s, t, 2), o.R[s] = b.actA[s], o.Y[s] = b.actB[s];
-    TW_TRY(launch_linear(o, 2, M, D, H * D, H * D, D, D, ACT_NONE, p.st));
-    TW_TRY(launch_layernorm(b.actB[0], b.actB[1], p.pv.enc(k, 0, t, 7), p.pv.enc(k, 1, t, 7), p.pv.enc(k, 0, t, 8),
-                            p.pv.enc(k, 1, t, 8), 2, M, D, c->layer_norm_eps, p.st));
+    if ((tcs & TC_MIX) && (tcs & TC_ATTN_PROJ)) {
+      TW_TRY(tc_attention_layer(c, p.pv, k, t, tcx, b.actA, b.actB, p.n, p.n_cond, p.V, p.st));
+    } else {
+      Lin2 a{};
+      for (int s = 0; s < 2; s++) a.X[s] = b.actA[s], a.W[s] = p.pv.enc(k, s, t, 0), a.Y[s] = b.vals[s];
+      TW_TRY(launch_linear(a, 2, M, H * D, D, D, 0, H * D, ACT_NONE, p.st));
+      TW_TRY(launch_attn_mix(b.scores, b.vals[0], b.vals[1], b.att[0], b.att[1], 2, p.n, p.n_cond, p.V, H, D, p.st));
+      Lin2 o{};
+      for (int s = 0; s < 2; s++) o.X[s] = b.att[s], o.W[s] = p.pv.enc(k, s, t, 2), o.R[s] = b.actA[s], o.Y[s] = b.actB[s];
+      TW_TRY(launch_linear(o, 2, M, D, H * D, H * D, D, D, ACT_NONE, p.st));
+      TW_TRY(launch_layernorm(b.actB[0], b.actB[1], p.pv.enc(k, 0, t, 7), p.pv.enc(k, 1, t, 7), p.pv.enc(k, 0, t, 8),
+                              p.pv.enc(k, 1, t, 8), 2, M, D, c->layer_norm_eps, p.st));
+    }
     if (tcs & TC_FFN) {
       TW_TRY(tc_ffn_layer(c, p.pv, k, t, tcx, b.actB, b.actA, M, p.st));  // fused linear1+ReLU+linear2+residual+LN2
     } else {
@@ -157,6 +162,8 @@ static int begin_pass(PassCtx& p, const float* x_coords) {
   // lengthscales of chain[0].scale_transformer.encoder_layers[0] (cache key maps lengthscales -> 0)
   const float* ls = p.pv.enc(0, 0, 0, 1);
   TW_TRY(launch_scores(p.fb.xc, p.mask, ls, p.n_cond, p.V, p.c->num_heads, p.fb.scores, p.st));
+  if (p.c->precision != TW_PRECISION_FP32)
+    TW_TRY(tc_begin_pass(p.c, p.pv, p.fb.tc, p.fb.scores, p.mask, p.n, p.n_cond, p.V, p.st));
   return TW_OK;
 }
 
@@ -252,6 +259,7 @@ int tw_flow_scale_shift(const tw_flow_config* cfg, const void* const* params, in
   TW_CUDA(cudaMemcpyAsync(p.fb.zc, z_coords, zb, cudaMemcpyDeviceToDevice, p.st));
   TW_CUDA(cudaMemcpyAsync(p.fb.zv, z_velocs, zb, cudaMemcpyDeviceToDevice, p.st));
   TW_TRY(launch_scores(p.fb.xc, mask, p.pv.enc(0, 0, 0, 1), B, (int)V, cfg->num_heads, p.fb.scores, p.st));
+  if (cfg->precision != TW_PRECISION_FP32) TW_TRY(tc_begin_pass(cfg, p.pv, p.fb.tc, p.fb.scores, mask, B, B, (int)V, p.st));
   TW_TRY(conditioner(p, layer_idx));
   return launch_coupling(p.fb.st[0], p.fb.st[1], nullptr, mask, nullptr, B, B, (int)V, 0, out_scale, out_shift, p.st);
 }

@@ -155,6 +155,48 @@ static int pack_w2_blocks(const float* W2, int F, int D, uint8_t* dst, cudaStrea
   return TW_OK;
 }
 
+
+// Row epilogue shared by the token-major kernels: v[128] (+ bias) + residual row -> LayerNorm -> global
+__device__ __forceinline__ void ln_store_row(float (&v)[128], const float* __restrict__ bias, const float* __restrict__ resid_row,
+                                             const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                             float* __restrict__ out_row) {
+  const float4* xr = reinterpret_cast<const float4*>(resid_row);
+  float sum = 0.f;
+#pragma unroll
+  for (int j = 0; j < 32; j++) {
+    float4 xv = __ldg(xr + j);
+    if (bias) {
+      float4 bv = *reinterpret_cast<const float4*>(bias + 4 * j);
+      xv.x += bv.x, xv.y += bv.y, xv.z += bv.z, xv.w += bv.w;
+    }
+    v[4 * j + 0] += xv.x;
+    v[4 * j + 1] += xv.y;
+    v[4 * j + 2] += xv.z;
+    v[4 * j + 3] += xv.w;
+    sum += (v[4 * j] + v[4 * j + 1]) + (v[4 * j + 2] + v[4 * j + 3]);
+  }
+  const float mean = sum * (1.f / 128.f);
+  float sq = 0.f;
+#pragma unroll
+  for (int j = 0; j < 128; j++) {
+    float d = v[j] - mean;
+    sq = fmaf(d, d, sq);
+  }
+  const float rstd = 1.0f / sqrtf(sq * (1.f / 128.f) + eps);
+  float4* orow = reinterpret_cast<float4*>(out_row);
+#pragma unroll
+  for (int j = 0; j < 32; j++) {
+    float4 g4 = *reinterpret_cast<const float4*>(gamma + 4 * j);
+    float4 b4 = *reinterpret_cast<const float4*>(beta + 4 * j);
+    float4 o;
+    o.x = (v[4 * j + 0] - mean) * rstd * g4.x + b4.x;
+    o.y = (v[4 * j + 1] - mean) * rstd * g4.y + b4.y;
+    o.z = (v[4 * j + 2] - mean) * rstd * g4.z + b4.z;
+    o.w = (v[4 * j + 3] - mean) * rstd * g4.w + b4.w;
+    orow[j] = o;
+  }
+}
+
 // ============================================================================================
 // Fused FFN:  out = LayerNorm(x + W2 relu(W1 x + b1) + b2)         custom_attention_encoder.py:111-113
 //
@@ -451,40 +493,7 @@ __global__ void __launch_bounds__(192, 1) k_ffn_tc(FfnArgs a) {
       tc_fence_before();
       mbar_arrive(y_free);  // Y is in registers: the next tile may overwrite it
       const int64_t grow = row0 + row;
-      if (grow < a.M) {
-        const float4* xr = reinterpret_cast<const float4*>(x + grow * 128);
-        float sum = 0.f;
-#pragma unroll
-        for (int j = 0; j < 32; j++) {
-          float4 xv = __ldg(xr + j);
-          float4 bv = *reinterpret_cast<const float4*>(vecs + 4 * j);
-          v[4 * j + 0] += bv.x + xv.x;
-          v[4 * j + 1] += bv.y + xv.y;
-          v[4 * j + 2] += bv.z + xv.z;
-          v[4 * j + 3] += bv.w + xv.w;
-          sum += (v[4 * j] + v[4 * j + 1]) + (v[4 * j + 2] + v[4 * j + 3]);
-        }
-        const float mean = sum * (1.f / 128.f);
-        float sq = 0.f;
-#pragma unroll
-        for (int j = 0; j < 128; j++) {
-          float d = v[j] - mean;
-          sq = fmaf(d, d, sq);
-        }
-        const float rstd = 1.0f / sqrtf(sq * (1.f / 128.f) + a.eps);
-        float4* orow = reinterpret_cast<float4*>(out + grow * 128);
-#pragma unroll
-        for (int j = 0; j < 32; j++) {
-          float4 g4 = *reinterpret_cast<const float4*>(vecs + 128 + 4 * j);
-          float4 b4 = *reinterpret_cast<const float4*>(vecs + 256 + 4 * j);
-          float4 o;
-          o.x = (v[4 * j + 0] - mean) * rstd * g4.x + b4.x;
-          o.y = (v[4 * j + 1] - mean) * rstd * g4.y + b4.y;
-          o.z = (v[4 * j + 2] - mean) * rstd * g4.z + b4.z;
-          o.w = (v[4 * j + 3] - mean) * rstd * g4.w + b4.w;
-          orow[j] = o;
-        }
-      }
+      if (grow < a.M) ln_store_row(v, vecs, x + grow * 128, vecs + 128, vecs + 256, a.eps, out + grow * 128);
       first_tile = false;
     }
   }
@@ -516,17 +525,421 @@ static int launch_ffn_tc(const tw_flow_config* c, const FfnArgs& a, cudaStream_t
 }
 
 // ============================================================================================
-// orchestration of one conditioner pair (scale net, shift net) of coupling layer k
-void tc_carve(const tw_flow_config* c, int64_t n, int64_t n_cond, int64_t V, Arena& ar, TcScratch* out) {
-  (void)n_cond;
-  const int64_t M = n * V;
-  for (int i = 0; i < 2; i++) out->mixed[i] = ar.take<float>(M * c->num_heads * c->d_model);
-  for (int i = 0; i < 2; i++) out->hidden[i] = ar.take<float>(M * c->mlp_hidden_dims[0]);
-  out->feat = ar.take<float>(M * (c->atom_embedding_dim + 9));
+// Attention, step 1 (scores operand images).  The attention weights depend only on the conditioning
+// coordinates, so they are converted ONCE per pass into the B-operand image the mixing kernel reads:
+// per (state b, head h) a [VP x VP] K-major, un-swizzled (8x8 core matrices) bf16 matrix, hi then lo.
+//   element (i, j) at  (i/8)*(VP/8)*128 + (j/8)*128 + (i%8)*16 + (j%8)*2      (VP = V rounded up to 16)
+__global__ void __launch_bounds__(256) k_scores_img(const float* __restrict__ scores, int64_t n_cond, int V, int VP, int H,
+                                                    uint8_t* __restrict__ img) {
+  // one warp per (b, h, i) row, i < VP
+  int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= n_cond * H * VP) return;
+  const int lane = threadIdx.x & 31;
+  const int i = (int)(row % VP);
+  const int64_t bh = row / VP;
+  const float* src = scores + (bh * V + i) * (int64_t)V;
+  const size_t mat = (size_t)VP * VP * 2;
+  uint8_t* hi = img + (size_t)bh * 2 * mat;
+  uint8_t* lo = hi + mat;
+  for (int j = lane; j < VP; j += 32) {
+    float v = (i < V && j < V) ? src[j] : 0.f;
+    __nv_bfloat16 h = __float2bfloat16(v);
+    __nv_bfloat16 l = __float2bfloat16(v - __bfloat162float(h));
+    uint32_t off = (i >> 3) * ((VP >> 3) * 128u) + (j >> 3) * 128u + (i & 7) * 16u + (j & 7) * 2u;
+    *reinterpret_cast<__nv_bfloat16*>(hi + off) = h;
+    *reinterpret_cast<__nv_bfloat16*>(lo + off) = l;
+  }
 }
 
-int tc_begin_pass(const tw_flow_config*, const ParamView&, TcScratch&, const float*, const uint8_t*, int64_t, int64_t, int,
-                  cudaStream_t) {
+// ============================================================================================
+// Attention, step 2 (mixing): for every sample n and head h,   mixed_h = A_h x   (kernel_attention.py:139
+// re-associated with the value projection, see k_combine_wc).  Features on the TMEM lanes:
+//   D^T[128 f, VP tokens] = X^T[128 f, VP atoms] (A operand, TMEM) * A_h^T (B operand [VP i, VP j] K-major)
+// so a sample of ANY atom count uses a full-width MMA.  The result is written straight into the A-operand
+// images ([128 tokens x 64] K-major SW128 tiles, hi/lo) that the projection kernel bulk-copies.
+constexpr uint32_t MX_HS = 0;      // X^T hi/lo, double buffered: [buf][hi 64 | lo 64] columns
+constexpr uint32_t MX_D = 256;     // accumulators, double buffered: 2 x 128 columns
+constexpr int kMixStages = 3;
+
+struct MixArgs {
+  const float* x[2];         // [n*V, 128] layer input
+  uint8_t* img[2];           // mixed operand images: [tile][H*2 K blocks][hi 16K | lo 16K]
+  const uint8_t* scores_img;  // [n_cond][H][hi | lo][VP*VP*2]
+  int64_t n, n_cond;
+  int V, VP, H;
+};
+
+__device__ __forceinline__ void split1(float v, uint16_t& hi, uint16_t& lo) {
+  __nv_bfloat16 h = __float2bfloat16(v);
+  __nv_bfloat16 l = __float2bfloat16(v - __bfloat162float(h));
+  hi = *reinterpret_cast<uint16_t*>(&h);
+  lo = *reinterpret_cast<uint16_t*>(&l);
+}
+
+template <int kSplit>
+__global__ void __launch_bounds__(192, 1) k_mix_tc(MixArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int net = blockIdx.y;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int V = a.V, VP = a.VP, H = a.H;
+  const uint32_t mat_bytes = (uint32_t)VP * VP * 2;
+  const uint32_t stage_bytes = 2 * mat_bytes;
+  uint8_t* ring = smem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kMixStages * ((stage_bytes + 1023) & ~1023u));
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kMixStages;
+  uint64_t* hs_full = empty + kMixStages;  // [2]
+  uint64_t* hs_free = hs_full + 2;         // [2]
+  uint64_t* d_full = hs_free + 2;          // [2]
+  uint64_t* d_free = d_full + 2;           // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d_free + 2);
+  const uint32_t stage_stride = (stage_bytes + 1023) & ~1023u;
+
+  if (tid == 0) {
+    for (int i = 0; i < kMixStages; i++) mbar_init(&full[i], 1), mbar_init(&empty[i], 1);
+    for (int i = 0; i < 2; i++) {
+      mbar_init(&hs_full[i], 128);
+      mbar_init(&hs_free[i], 1);
+      mbar_init(&d_full[i], 1);
+      mbar_init(&d_free[i], 128);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const int ksteps = VP / 16;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int64_t n = blockIdx.x; n < a.n; n += gridDim.x) {
+        const uint8_t* src = a.scores_img + (size_t)(n % a.n_cond) * H * stage_bytes;
+        for (int h = 0; h < H; h++) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full[stage], kSplit == 3 ? stage_bytes : mat_bytes);
+          bulk_g2s(ring + stage * stage_stride, src + (size_t)h * stage_bytes, kSplit == 3 ? stage_bytes : mat_bytes, &full[stage]);
+          if (++stage == kMixStages) stage = 0, phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      uint32_t ph_hs[2] = {0, 0}, ph_dfree[2] = {0, 0};
+      const uint32_t idesc = make_idesc_bf16(128, VP, 0, 0);
+      const uint32_t lbo = 128, sbo = (uint32_t)(VP >> 3) * 128;
+      int64_t it = 0, hcount = 0;
+      for (int64_t n = blockIdx.x; n < a.n; n += gridDim.x, it++) {
+        const int sb = it & 1;
+        mbar_wait(&hs_full[sb], ph_hs[sb]);
+        ph_hs[sb] ^= 1;
+        tc_fence_after();
+        const uint32_t hs_hi = tmem + MX_HS + sb * 128, hs_lo = hs_hi + 64;
+        for (int h = 0; h < H; h++, hcount++) {
+          const int db = hcount & 1;
+          if (hcount >= 2) {
+            mbar_wait(&d_free[db], ph_dfree[db]);
+            ph_dfree[db] ^= 1;
+          }
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t s_hi = smem_u32(ring + stage * stage_stride), s_lo = s_hi + mat_bytes;
+          const uint32_t d = tmem + MX_D + db * 128;
+          for (int k = 0; k < ksteps; k++)
+            mma_ts(d, hs_hi + k * 8, make_smem_desc(s_hi + k * 256, lbo, sbo, LAYOUT_NONE), idesc, k > 0);
+          if (kSplit == 3) {
+            for (int k = 0; k < ksteps; k++)
+              mma_ts(d, hs_lo + k * 8, make_smem_desc(s_hi + k * 256, lbo, sbo, LAYOUT_NONE), idesc, 1);
+            for (int k = 0; k < ksteps; k++)
+              mma_ts(d, hs_hi + k * 8, make_smem_desc(s_lo + k * 256, lbo, sbo, LAYOUT_NONE), idesc, 1);
+          }
+          mma_commit(&empty[stage]);
+          if (++stage == kMixStages) stage = 0, phase ^= 1;
+          mma_commit(&d_full[db]);
+        }
+        mma_commit(&hs_free[sb]);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int f = q * 32 + lane;  // feature = TMEM lane
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    const float* x = a.x[net];
+    uint8_t* img = a.img[net];
+    const size_t tile_bytes = (size_t)H * 2 * 2 * 16384;  // H*2 K blocks x (hi + lo) x 16 KB
+    uint32_t ph_hsfree[2] = {0, 0}, ph_dfull[2] = {0, 0};
+
+    auto load_hs = [&](int64_t n, int64_t it) {
+      const int sb = it & 1;
+      if (it >= 2) {
+        mbar_wait(&hs_free[sb], ph_hsfree[sb]);
+        ph_hsfree[sb] ^= 1;
+      }
+      const float* xs = x + n * V * 128 + f;
+      for (int c0 = 0; c0 < VP / 2; c0 += 16) {  // 16 columns = 32 atoms per store
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+          int a0 = 2 * (c0 + j);
+          float v0 = (a0 < V) ? __ldg(xs + (size_t)a0 * 128) : 0.f;
+          float v1 = (a0 + 1 < V) ? __ldg(xs + (size_t)(a0 + 1) * 128) : 0.f;
+          split2(v0, v1, hi[j], lo[j]);
+        }
+        tmem_st16(tmem + lane_base + MX_HS + sb * 128 + c0, hi);
+        if (kSplit == 3) tmem_st16(tmem + lane_base + MX_HS + sb * 128 + 64 + c0, lo);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&hs_full[sb]);
+    };
+
+    int64_t it = 0, hcount = 0;
+    if ((int64_t)blockIdx.x < a.n) load_hs(blockIdx.x, 0);
+    for (int64_t n = blockIdx.x; n < a.n; n += gridDim.x, it++) {
+      if (n + gridDim.x < a.n) load_hs(n + gridDim.x, it + 1);  // next sample's X^T while this one's heads drain
+      for (int h = 0; h < H; h++, hcount++) {
+        const int db = hcount & 1;
+        mbar_wait(&d_full[db], ph_dfull[db]);
+        ph_dfull[db] ^= 1;
+        tc_fence_after();
+        const int kcol = h * 128 + f;
+        const int kb = kcol >> 6, kk = kcol & 63;
+        for (int c0 = 0; c0 < VP; c0 += 16) {
+          uint32_t r[16];
+          tmem_ld16(tmem + lane_base + MX_D + db * 128 + c0, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; j++) {
+            int i = c0 + j;
+            if (i < V) {
+              int64_t t = n * V + i;
+              int64_t tile = t >> 7;
+              uint32_t row = (uint32_t)(t & 127);
+              uint16_t hi, lo;
+              split1(__uint_as_float(r[j]), hi, lo);
+              uint8_t* dst = img + tile * tile_bytes + (size_t)kb * 32768 + row * 128u + ((((uint32_t)kk >> 3) ^ (row & 7u)) << 4) + (kk & 7) * 2;
+              *reinterpret_cast<uint16_t*>(dst) = hi;
+              if (kSplit == 3) *reinterpret_cast<uint16_t*>(dst + 16384) = lo;
+            }
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(&d_free[db]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(tmem);
+}
+
+// ============================================================================================
+// Attention, step 3 (projection):  out = LayerNorm1(x + sum_h W_c,h mixed_h)     custom_attention_encoder.py:102-110
+// Token-major GEMM, K = H*128: both operands arrive by bulk copy (A = mixed images, B = W_c images).
+constexpr int kProjStages = 3;
+constexpr int kProjStageBytes = 4 * 16384;  // A hi | A lo | W hi | W lo, each [128 x 64]
+
+struct ProjArgs {
+  const uint8_t* a_img[2];
+  const uint8_t* w[2];
+  const float* resid[2];
+  float* out[2];
+  const float* gamma[2];
+  const float* beta[2];
+  int64_t M;
+  int KB;  // K blocks of 64
+  float eps;
+};
+
+template <int kSplit>
+__global__ void __launch_bounds__(192, 1) k_proj_tc(ProjArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int net = blockIdx.y;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t n_tiles = (a.M + 127) / 128;
+  uint8_t* ring = smem;
+  float* vecs = reinterpret_cast<float*>(smem + kProjStages * kProjStageBytes);  // gamma, beta
+  uint64_t* bars = reinterpret_cast<uint64_t*>(vecs + 256);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kProjStages;
+  uint64_t* y_full = empty + kProjStages;  // [2]
+  uint64_t* y_free = y_full + 2;           // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(y_free + 2);
+  if (tid == 0) {
+    for (int i = 0; i < kProjStages; i++) mbar_init(&full[i], 1), mbar_init(&empty[i], 1);
+    for (int i = 0; i < 2; i++) mbar_init(&y_full[i], 1), mbar_init(&y_free[i], 128);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc<256>(tmem_slot);
+  for (int i = tid; i < 128; i += blockDim.x) vecs[i] = a.gamma[net][i], vecs[128 + i] = a.beta[net][i];
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const size_t a_tile_bytes = (size_t)a.KB * 32768;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      const uint32_t a_bytes = kSplit == 3 ? 32768 : 16384;
+      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (int kb = 0; kb < a.KB; kb++) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full[stage], 2 * a_bytes);
+          uint8_t* dst = ring + stage * kProjStageBytes;
+          bulk_g2s(dst, a.a_img[net] + tile * a_tile_bytes + (size_t)kb * 32768, a_bytes, &full[stage]);
+          bulk_g2s(dst + 32768, a.w[net] + (size_t)kb * 32768, a_bytes, &full[stage]);
+          if (++stage == kProjStages) stage = 0, phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0, ph_free[2] = {0, 0};
+      const uint32_t idesc = make_idesc_bf16(128, 128, 0, 0);
+      int64_t it = 0;
+      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, it++) {
+        const int tb = it & 1;
+        if (it >= 2) {
+          mbar_wait(&y_free[tb], ph_free[tb]);
+          ph_free[tb] ^= 1;
+        }
+        tc_fence_after();
+        const uint32_t d = tmem + tb * 128;
+        for (int kb = 0; kb < a.KB; kb++) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t ahi = smem_u32(ring + stage * kProjStageBytes), alo = ahi + 16384, whi = ahi + 32768, wlo = whi + 16384;
+#pragma unroll
+          for (int k = 0; k < 4; k++) mma_ss(d, desc_kmajor_sw128(ahi + k * 32), desc_kmajor_sw128(whi + k * 32), idesc, (kb > 0 || k > 0) ? 1 : 0);
+          if (kSplit == 3) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) mma_ss(d, desc_kmajor_sw128(alo + k * 32), desc_kmajor_sw128(whi + k * 32), idesc, 1);
+#pragma unroll
+            for (int k = 0; k < 4; k++) mma_ss(d, desc_kmajor_sw128(ahi + k * 32), desc_kmajor_sw128(wlo + k * 32), idesc, 1);
+          }
+          mma_commit(&empty[stage]);
+          if (++stage == kProjStages) stage = 0, phase ^= 1;
+        }
+        mma_commit(&y_full[tb]);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    uint32_t ph_full[2] = {0, 0};
+    int64_t it = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, it++) {
+      const int tb = it & 1;
+      mbar_wait(&y_full[tb], ph_full[tb]);
+      ph_full[tb] ^= 1;
+      tc_fence_after();
+      float v[128];
+#pragma unroll
+      for (int g = 0; g < 4; g++) {
+        uint32_t r[32];
+        tmem_ld32(tmem + lane_base + tb * 128 + g * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; j++) v[g * 32 + j] = __uint_as_float(r[j]);
+      }
+      tc_fence_before();
+      mbar_arrive(&y_free[tb]);
+      const int64_t grow = tile * 128 + row;
+      if (grow < a.M) ln_store_row(v, nullptr, a.resid[net] + grow * 128, vecs, vecs + 128, a.eps, a.out[net] + grow * 128);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<256>(tmem);
+}
+
+// ============================================================================================
+// orchestration of one conditioner pair (scale net, shift net) of coupling layer k
+static int pad16(int v) { return (v + 15) / 16 * 16; }
+
+void tc_carve(const tw_flow_config* c, int64_t n, int64_t n_cond, int64_t V, Arena& ar, TcScratch* out) {
+  const int64_t M = n * V;
+  const int64_t tiles = (M + 127) / 128;
+  const int VP = pad16((int)V);
+  const size_t tile_bytes = (size_t)c->num_heads * 2 * 2 * 16384;
+  for (int i = 0; i < 2; i++) {
+    ar.off = align_up(ar.off, 1024);
+    out->mixed_img[i] = ar.take<uint8_t>(tiles * tile_bytes);
+  }
+  ar.off = align_up(ar.off, 1024);
+  out->scores_img = ar.take<uint8_t>((size_t)n_cond * c->num_heads * 2 * VP * VP * 2);
+}
+
+// scores -> operand images, once per pass
+int tc_begin_pass(const tw_flow_config* c, const ParamView&, TcScratch& tc, const float* scores, const uint8_t*, int64_t,
+                  int64_t n_cond, int V, cudaStream_t st) {
+  if (!(tc_stage_mask() & TC_MIX)) return TW_OK;
+  TW_CHECK_ARG(V <= 128, "tensor-core attention supports at most 128 atoms per sample");
+  const int VP = pad16(V);
+  int64_t rows = n_cond * c->num_heads * VP;
+  k_scores_img<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(scores, n_cond, V, VP, c->num_heads, tc.scores_img);
+  TW_LAUNCH_CHECK();
+  return TW_OK;
+}
+
+// out = LN1(x + attention(x)) for both networks of encoder layer t
+int tc_attention_layer(const tw_flow_config* c, const ParamView& pv, int k, int t, const TcScratch& tc, float* const x[2],
+                       float* const out[2], int64_t n, int64_t n_cond, int V, cudaStream_t st) {
+  static bool attr_done = false;
+  const int VP = pad16(V), H = c->num_heads;
+  const uint32_t stage_stride = (uint32_t)((2 * VP * VP * 2 + 1023) & ~1023);
+  const int mix_smem = kMixStages * stage_stride + 256 + 1024;
+  const int proj_smem = kProjStages * kProjStageBytes + 1024 + 256 + 1024;
+  if (!attr_done) {
+    TW_CUDA(cudaFuncSetAttribute(k_mix_tc<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 65536 + 2048));
+    TW_CUDA(cudaFuncSetAttribute(k_mix_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 65536 + 2048));
+    TW_CUDA(cudaFuncSetAttribute(k_proj_tc<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, proj_smem));
+    TW_CUDA(cudaFuncSetAttribute(k_proj_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, proj_smem));
+    attr_done = true;
+  }
+  TcLayout L = TcLayout::make(c);
+  const int64_t M = n * V;
+  ProfScope prof(PROF_ATTN, st);
+  {
+    MixArgs a{};
+    for (int s = 0; s < 2; s++) a.x[s] = x[s], a.img[s] = tc.mixed_img[s];
+    a.scores_img = tc.scores_img;
+    a.n = n, a.n_cond = n_cond, a.V = V, a.VP = VP, a.H = H;
+    int gx = (int)(n < 74 ? n : 74);
+    dim3 grid(gx, 2);
+    if (c->precision == TW_PRECISION_BF16X3)
+      k_mix_tc<3><<<grid, 192, mix_smem, st>>>(a);
+    else
+      k_mix_tc<1><<<grid, 192, mix_smem, st>>>(a);
+    TW_LAUNCH_CHECK();
+  }
+  {
+    ProjArgs a{};
+    for (int s = 0; s < 2; s++) {
+      a.a_img[s] = tc.mixed_img[s];
+      a.w[s] = tc.packed + L.net_offset(k, s) + L.enc0 + (size_t)t * L.enc_stride + L.enc_wc;
+      a.resid[s] = x[s];
+      a.out[s] = out[s];
+      a.gamma[s] = pv.enc(k, s, t, 7);
+      a.beta[s] = pv.enc(k, s, t, 8);
+    }
+    a.M = M, a.KB = H * 2, a.eps = c->layer_norm_eps;
+    int64_t n_tiles = (M + 127) / 128;
+    int gx = (int)(n_tiles < 74 ? n_tiles : 74);
+    dim3 grid(gx, 2);
+    if (c->precision == TW_PRECISION_BF16X3)
+      k_proj_tc<3><<<grid, 192, proj_smem, st>>>(a);
+    else
+      k_proj_tc<1><<<grid, 192, proj_smem, st>>>(a);
+    TW_LAUNCH_CHECK();
+  }
   return TW_OK;
 }
 

@@ -23,15 +23,13 @@ struct TcLayout {
 };
 
 struct TcScratch {
-  float* mixed[2];   // [M, H*D] fp32: per-head neighbourhood averages of the layer input
-  float* hidden[2];  // [M, hid] fp32 (SIMT stages of the hybrid path)
-  float* feat;       // [M, E+9]
+  uint8_t* mixed_img[2];  // A-operand images of the per-head neighbourhood averages: [tile][H*2][hi|lo][16 KB]
+  uint8_t* scores_img;    // B-operand images of the attention weights: [n_cond][H][hi|lo][VP*VP*2]
   const uint8_t* packed;  // packed weights (caller-owned, persistent)
-  uint32_t stages;   // bit mask of stages that run on tensor cores (debug / bring-up)
 };
 
 enum TcStage : uint32_t { TC_FFN = 1, TC_ATTN_PROJ = 2, TC_MIX = 4, TC_IN_MLP = 8, TC_OUT_MLP = 16, TC_ALL = 31 };
-constexpr uint32_t TC_IMPLEMENTED = TC_FFN;  // stages with a tensor-core kernel; the rest run on CUDA cores
+constexpr uint32_t TC_IMPLEMENTED = TC_FFN | TC_MIX | TC_ATTN_PROJ;  // stages with a tensor-core kernel; the rest run on CUDA cores
 
 bool tc_supported(const tw_flow_config* c);
 uint32_t tc_stage_mask();  // TW_TC_STAGES environment override (bring-up), default: every stage that exists
@@ -41,6 +39,9 @@ int tc_begin_pass(const tw_flow_config* c, const ParamView& pv, TcScratch& tc, c
                   int64_t n, int64_t n_cond, int V, cudaStream_t st);
 size_t tc_packed_bytes(const tw_flow_config* c);
 // fused FFN + residual + LayerNorm of encoder layer t for both networks: out = LN2(x + FFN(x))
+// out = LN1(x + sum_h W_c,h (A_h x)) for both networks (tensor-core mixing + projection)
+int tc_attention_layer(const tw_flow_config* c, const ParamView& pv, int k, int t, const TcScratch& tc, float* const x[2],
+                       float* const out[2], int64_t n, int64_t n_cond, int V, cudaStream_t st);
 int tc_ffn_layer(const tw_flow_config* c, const ParamView& pv, int k, int t, const TcScratch& tc, float* const x[2],
                  float* const out[2], int64_t M, cudaStream_t st);
 
