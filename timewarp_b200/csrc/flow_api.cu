@@ -91,19 +91,20 @@ static int conditioner(PassCtx& p, int k) {
   const uint32_t tcs = (c->precision == TW_PRECISION_FP32) ? 0u : tc_stage_mask();
   TcScratch tcx = b.tc;
   tcx.packed = p.packed;
-  TW_TRY(launch_features(p.pv.embed(), p.atom_types, b.xc, p.x_velocs, pos ? b.zv : b.zc, p.n, p.n_cond, p.V, E,
-                         c->num_atom_types, b.feat, p.st));
-  // in_mlp
   const float* cur[2] = {b.feat, b.feat};
   int cur_dim = E + 9;
   float* hid[2][2] = {{b.hidA[0], b.hidA[1]}, {b.hidB[0], b.hidB[1]}};
-  for (int i = 0; i < nh; i++) {
-    Lin2 a{};
-    for (int s = 0; s < 2; s++) a.X[s] = cur[s], a.W[s] = p.pv.in_w(k, s, i), a.b[s] = p.pv.in_b(k, s, i), a.Y[s] = hid[i & 1][s];
-    TW_TRY(launch_linear(a, 2, M, c->mlp_hidden_dims[i], cur_dim, cur_dim, 0, c->mlp_hidden_dims[i], ACT_SILU, p.st));
-    cur[0] = hid[i & 1][0], cur[1] = hid[i & 1][1], cur_dim = c->mlp_hidden_dims[i];
-  }
-  {
+  if (tcs & TC_IN_MLP) {
+    TW_TRY(tc_in_mlp(c, p.pv, k, tcx, p.atom_types, b.xc, p.x_velocs, pos ? b.zv : b.zc, b.actA, p.n, p.n_cond, p.V, p.st));
+  } else {
+    TW_TRY(launch_features(p.pv.embed(), p.atom_types, b.xc, p.x_velocs, pos ? b.zv : b.zc, p.n, p.n_cond, p.V, E,
+                           c->num_atom_types, b.feat, p.st));
+    for (int i = 0; i < nh; i++) {
+      Lin2 a{};
+      for (int s = 0; s < 2; s++) a.X[s] = cur[s], a.W[s] = p.pv.in_w(k, s, i), a.b[s] = p.pv.in_b(k, s, i), a.Y[s] = hid[i & 1][s];
+      TW_TRY(launch_linear(a, 2, M, c->mlp_hidden_dims[i], cur_dim, cur_dim, 0, c->mlp_hidden_dims[i], ACT_SILU, p.st));
+      cur[0] = hid[i & 1][0], cur[1] = hid[i & 1][1], cur_dim = c->mlp_hidden_dims[i];
+    }
     Lin2 a{};
     for (int s = 0; s < 2; s++) a.X[s] = cur[s], a.W[s] = p.pv.in_w(k, s, nh), a.b[s] = p.pv.in_b(k, s, nh), a.Y[s] = b.actA[s];
     TW_TRY(launch_linear(a, 2, M, D, cur_dim, cur_dim, 0, D, ACT_NONE, p.st));
@@ -140,6 +141,10 @@ static int conditioner(PassCtx& p, int k) {
     }
   }
   // out_mlp
+  if (tcs & TC_OUT_MLP) {
+    TW_TRY(tc_out_mlp(c, p.pv, k, tcx, b.actA, b.st, M, p.st));
+    return TW_OK;
+  }
   cur[0] = b.actA[0], cur[1] = b.actA[1], cur_dim = D;
   for (int i = 0; i < nh; i++) {
     Lin2 a{};

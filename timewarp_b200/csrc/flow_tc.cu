@@ -861,6 +861,377 @@ __global__ void __launch_bounds__(192, 1) k_proj_tc(ProjArgs a) {
 }
 
 // ============================================================================================
+// in_mlp: token features (embedding gather + concat, flow.py:172 / custom_transformer_nvp.py:64-71) ->
+// Linear(E+9 -> 256) + SiLU -> Linear(256 -> 128)            (mlp.py:18-23, custom_transformer_block.py:66)
+// Weights stay resident in shared memory for the whole (persistent) CTA; the 256-wide hidden activation
+// goes TMEM -> registers -> TMEM (A operand of the second GEMM).  TMEM: D1 [0,256) (D2 reuses [0,128)), H hi
+// [256,384), H lo [384,512).
+__device__ __forceinline__ float silu_f(float v) { return v / (1.f + expf(-v)); }
+
+struct InMlpArgs {
+  const uint8_t* w1[2];   // [256 x 64] hi 32K | lo 32K
+  const uint8_t* w2[2];   // 4 K blocks x (hi 16K | lo 16K)
+  const float* b1[2];
+  const float* b2[2];
+  float* out[2];          // [M,128]
+  const float* embed;     // [n_types, E]
+  const int64_t* atom_types;
+  const float* xc;
+  const float* xv;
+  const float* z_other;   // [M,3]
+  int64_t M, n_cond;
+  int V, E, n_types;
+};
+
+struct InMlpSmem {
+  static constexpr int A_HI = 0, A_LO = 16384, W1 = 32768, W2 = W1 + 65536, B1 = W2 + 131072, B2 = B1 + 1024, BARS = B2 + 512;
+  static constexpr int TOTAL = BARS + 128;
+};
+
+template <int kSplit>
+__global__ void __launch_bounds__(192, 1) k_in_mlp_tc(InMlpArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int net = blockIdx.y;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t n_tiles = (a.M + 127) / 128;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + InMlpSmem::BARS);
+  uint64_t* w_full = bars;       // weights resident
+  uint64_t* a_full = bars + 1;   // feature operand written (128)
+  uint64_t* d1_full = bars + 2;  // GEMM1 done
+  uint64_t* h_full = bars + 3;   // hidden in TMEM (128)
+  uint64_t* d2_full = bars + 4;  // GEMM2 done
+  uint64_t* d_free = bars + 5;   // D2 drained (128)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+  float* b1s = reinterpret_cast<float*>(smem + InMlpSmem::B1);
+  float* b2s = reinterpret_cast<float*>(smem + InMlpSmem::B2);
+  if (tid == 0) {
+    mbar_init(w_full, 1);
+    mbar_init(a_full, 128);
+    mbar_init(d1_full, 1);
+    mbar_init(h_full, 128);
+    mbar_init(d2_full, 1);
+    mbar_init(d_free, 128);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  for (int i = tid; i < 256; i += blockDim.x) b1s[i] = a.b1[net][i];
+  for (int i = tid; i < 128; i += blockDim.x) b2s[i] = a.b2[net][i];
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  constexpr uint32_t T_D = 0, T_HHI = 256, T_HLO = 384;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint32_t w1b = kSplit == 3 ? 65536 : 32768;
+      mbar_arrive_expect_tx(w_full, w1b + (kSplit == 3 ? 131072 : 4 * 16384));
+      bulk_g2s(smem + InMlpSmem::W1, a.w1[net], w1b, w_full);
+      if (kSplit == 3) {
+        for (int i = 0; i < 4; i++) bulk_g2s(smem + InMlpSmem::W2 + i * 32768, a.w2[net] + i * 32768, 32768, w_full);
+      } else {
+        for (int i = 0; i < 4; i++) bulk_g2s(smem + InMlpSmem::W2 + i * 32768, a.w2[net] + i * 32768, 16384, w_full);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      mbar_wait(w_full, 0);
+      const uint32_t idesc1 = make_idesc_bf16(128, 256, 0, 0), idesc2 = make_idesc_bf16(128, 128, 0, 0);
+      const uint32_t ahi = smem_u32(smem + InMlpSmem::A_HI), alo = smem_u32(smem + InMlpSmem::A_LO);
+      const uint32_t w1hi = smem_u32(smem + InMlpSmem::W1), w1lo = w1hi + 32768, w2 = smem_u32(smem + InMlpSmem::W2);
+      uint32_t ph = 0;
+      int64_t it = 0;
+      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, it++) {
+        mbar_wait(a_full, ph);
+        if (it > 0) mbar_wait(d_free, ph ^ 1);  // previous tile's D2 (aliases D1) has been read
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 4; k++) mma_ss(tmem + T_D, desc_kmajor_sw128(ahi + k * 32), desc_kmajor_sw128(w1hi + k * 32), idesc1, k > 0);
+        if (kSplit == 3) {
+#pragma unroll
+          for (int k = 0; k < 4; k++) mma_ss(tmem + T_D, desc_kmajor_sw128(alo + k * 32), desc_kmajor_sw128(w1hi + k * 32), idesc1, 1);
+#pragma unroll
+          for (int k = 0; k < 4; k++) mma_ss(tmem + T_D, desc_kmajor_sw128(ahi + k * 32), desc_kmajor_sw128(w1lo + k * 32), idesc1, 1);
+        }
+        mma_commit(d1_full);
+        mbar_wait(h_full, ph);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 16; k++)
+          mma_ts(tmem + T_D, tmem + T_HHI + k * 8, desc_kmajor_sw128(w2 + (k >> 2) * 32768 + (k & 3) * 32), idesc2, k > 0);
+        if (kSplit == 3) {
+#pragma unroll
+          for (int k = 0; k < 16; k++)
+            mma_ts(tmem + T_D, tmem + T_HLO + k * 8, desc_kmajor_sw128(w2 + (k >> 2) * 32768 + (k & 3) * 32), idesc2, 1);
+#pragma unroll
+          for (int k = 0; k < 16; k++)
+            mma_ts(tmem + T_D, tmem + T_HHI + k * 8, desc_kmajor_sw128(w2 + (k >> 2) * 32768 + 16384 + (k & 3) * 32), idesc2, 1);
+        }
+        mma_commit(d2_full);
+        ph ^= 1;
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    const int E = a.E;
+    uint32_t ph = 0;
+    auto gather = [&](int64_t tile) {
+      const int64_t m = tile * 128 + row;
+      float f[64];
+#pragma unroll
+      for (int j = 0; j < 64; j++) f[j] = 0.f;
+      if (m < a.M) {
+        const int64_t smp = m / a.V;
+        const int v = (int)(m % a.V);
+        const int64_t mc = (smp % a.n_cond) * a.V + v;
+        int64_t t = a.atom_types[mc];
+        t = t < 0 ? 0 : (t >= a.n_types ? a.n_types - 1 : t);
+        const float* er = a.embed + t * E;
+#pragma unroll
+        for (int j = 0; j < 64; j++) {
+          if (j < E) f[j] = __ldg(er + j);
+          else if (j < E + 3) f[j] = __ldg(a.xc + mc * 3 + (j - E));
+          else if (j < E + 6) f[j] = __ldg(a.xv + mc * 3 + (j - E - 3));
+          else if (j < E + 9) f[j] = __ldg(a.z_other + m * 3 + (j - E - 6));
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 8; c++) {
+        uint32_t h[4], l[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) split2(f[c * 8 + 2 * j], f[c * 8 + 2 * j + 1], h[j], l[j]);
+        uint32_t off = row * 128u + (((uint32_t)c ^ (row & 7u)) << 4);
+        *reinterpret_cast<uint4*>(smem + InMlpSmem::A_HI + off) = make_uint4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<uint4*>(smem + InMlpSmem::A_LO + off) = make_uint4(l[0], l[1], l[2], l[3]);
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(a_full);
+    };
+    if ((int64_t)blockIdx.x < n_tiles) gather(blockIdx.x);
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      // ---- hidden: D1 + b1 -> SiLU -> hi/lo -> TMEM
+      mbar_wait(d1_full, ph);
+      tc_fence_after();
+#pragma unroll 1
+      for (int g = 0; g < 8; g++) {
+        uint32_t r[32];
+        tmem_ld32(tmem + lane_base + T_D + g * 32, r);
+        tmem_ld_wait();
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          float v0 = silu_f(__uint_as_float(r[j]) + b1s[g * 32 + j]);
+          float v1 = silu_f(__uint_as_float(r[j + 1]) + b1s[g * 32 + j + 1]);
+          split2(v0, v1, hi[j >> 1], lo[j >> 1]);
+        }
+        tmem_st16(tmem + lane_base + T_HHI + g * 16, hi);
+        if (kSplit == 3) tmem_st16(tmem + lane_base + T_HLO + g * 16, lo);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(h_full);
+      // the feature operand of the next tile can be written now (GEMM1 of this tile has completed)
+      if (tile + gridDim.x < n_tiles) gather(tile + gridDim.x);
+      // ---- output: D2 + b2 -> global
+      mbar_wait(d2_full, ph);
+      tc_fence_after();
+      const int64_t m = tile * 128 + row;
+      float* orow = a.out[net] + m * 128;
+#pragma unroll 1
+      for (int g = 0; g < 4; g++) {
+        uint32_t r[32];
+        tmem_ld32(tmem + lane_base + T_D + g * 32, r);
+        tmem_ld_wait();
+        if (m < a.M) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 o;
+            o.x = __uint_as_float(r[j]) + b2s[g * 32 + j];
+            o.y = __uint_as_float(r[j + 1]) + b2s[g * 32 + j + 1];
+            o.z = __uint_as_float(r[j + 2]) + b2s[g * 32 + j + 2];
+            o.w = __uint_as_float(r[j + 3]) + b2s[g * 32 + j + 3];
+            *reinterpret_cast<float4*>(orow + g * 32 + j) = o;
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(d_free);
+      ph ^= 1;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(tmem);
+}
+
+// ============================================================================================
+// out_mlp: Linear(128 -> 256) + SiLU -> Linear(256 -> 3)       (mlp.py:18-23, custom_transformer_block.py:82)
+// The 256 -> 3 layer is evaluated in fp32 on the CUDA cores inside the epilogue (768 FMAs per token).
+struct OutMlpArgs {
+  const float* x[2];     // [M,128]
+  const uint8_t* w3[2];  // 2 K blocks x (hi 32K | lo 32K), [256 x 64] each
+  const float* b3[2];
+  const float* w4[2];    // [3,256] fp32
+  const float* b4[2];
+  float* out[2];         // [M,3]
+  int64_t M;
+};
+struct OutMlpSmem {
+  static constexpr int X_HI = 0, X_LO = 32768, W3 = 65536, B3 = W3 + 131072, W4 = B3 + 1024, BARS = W4 + 3 * 1024 + 16;
+  static constexpr int TOTAL = BARS + 128;
+};
+
+template <int kSplit>
+__global__ void __launch_bounds__(192, 1) k_out_mlp_tc(OutMlpArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int net = blockIdx.y;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t n_tiles = (a.M + 127) / 128;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OutMlpSmem::BARS);
+  uint64_t* w_full = bars;
+  uint64_t* x_full = bars + 1;   // 128
+  uint64_t* d_full = bars + 2;   // [2]
+  uint64_t* d_free = bars + 4;   // [2] 128
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+  float* b3s = reinterpret_cast<float*>(smem + OutMlpSmem::B3);
+  float* w4s = reinterpret_cast<float*>(smem + OutMlpSmem::W4);  // [3][256] then b4[3]
+  if (tid == 0) {
+    mbar_init(w_full, 1);
+    mbar_init(x_full, 128);
+    for (int i = 0; i < 2; i++) mbar_init(&d_full[i], 1), mbar_init(&d_free[i], 128);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  for (int i = tid; i < 256; i += blockDim.x) b3s[i] = a.b3[net][i];
+  for (int i = tid; i < 768; i += blockDim.x) w4s[i] = a.w4[net][i];
+  if (tid < 3) w4s[768 + tid] = a.b4[net][tid];
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      if (kSplit == 3) {
+        mbar_arrive_expect_tx(w_full, 131072);
+        bulk_g2s(smem + OutMlpSmem::W3, a.w3[net], 65536, w_full);
+        bulk_g2s(smem + OutMlpSmem::W3 + 65536, a.w3[net] + 65536, 65536, w_full);
+      } else {
+        mbar_arrive_expect_tx(w_full, 65536);
+        bulk_g2s(smem + OutMlpSmem::W3, a.w3[net], 32768, w_full);
+        bulk_g2s(smem + OutMlpSmem::W3 + 65536, a.w3[net] + 65536, 32768, w_full);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      mbar_wait(w_full, 0);
+      const uint32_t idesc = make_idesc_bf16(128, 256, 0, 0);
+      const uint32_t xhi = smem_u32(smem + OutMlpSmem::X_HI), xlo = smem_u32(smem + OutMlpSmem::X_LO), w3 = smem_u32(smem + OutMlpSmem::W3);
+      uint32_t ph_x = 0, ph_free[2] = {0, 0};
+      int64_t it = 0;
+      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, it++) {
+        const int tb = it & 1;
+        mbar_wait(x_full, ph_x);
+        ph_x ^= 1;
+        if (it >= 2) {
+          mbar_wait(&d_free[tb], ph_free[tb]);
+          ph_free[tb] ^= 1;
+        }
+        tc_fence_after();
+        const uint32_t d = tmem + tb * 256;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+          uint32_t ao = (k >> 2) * 16384 + (k & 3) * 32, wo = (k >> 2) * 65536 + (k & 3) * 32;
+          mma_ss(d, desc_kmajor_sw128(xhi + ao), desc_kmajor_sw128(w3 + wo), idesc, k > 0);
+        }
+        if (kSplit == 3) {
+#pragma unroll
+          for (int k = 0; k < 8; k++) {
+            uint32_t ao = (k >> 2) * 16384 + (k & 3) * 32, wo = (k >> 2) * 65536 + (k & 3) * 32;
+            mma_ss(d, desc_kmajor_sw128(xlo + ao), desc_kmajor_sw128(w3 + wo), idesc, 1);
+          }
+#pragma unroll
+          for (int k = 0; k < 8; k++) {
+            uint32_t ao = (k >> 2) * 16384 + (k & 3) * 32, wo = (k >> 2) * 65536 + 32768 + (k & 3) * 32;
+            mma_ss(d, desc_kmajor_sw128(xhi + ao), desc_kmajor_sw128(w3 + wo), idesc, 1);
+          }
+        }
+        mma_commit(&d_full[tb]);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int ew = warp - 2;
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    uint32_t ph_full[2] = {0, 0};
+    const float* x = a.x[net];
+    auto load_x = [&](int64_t tile) {
+      const int64_t row0 = tile * 128;
+#pragma unroll 1
+      for (int it = 0; it < 32; it += 8) {
+        float4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+          int r = ew * 32 + it + u;
+          v[u] = (row0 + r < a.M) ? __ldg(reinterpret_cast<const float4*>(x + (row0 + r) * 128) + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+          int r = ew * 32 + it + u;
+          uint32_t h0, l0, h1, l1;
+          split2(v[u].x, v[u].y, h0, l0);
+          split2(v[u].z, v[u].w, h1, l1);
+          uint32_t off = sw128_offset(r, lane * 4, 128);
+          *reinterpret_cast<uint2*>(smem + OutMlpSmem::X_HI + off) = make_uint2(h0, h1);
+          *reinterpret_cast<uint2*>(smem + OutMlpSmem::X_LO + off) = make_uint2(l0, l1);
+        }
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(x_full);
+    };
+    int64_t it = 0;
+    if ((int64_t)blockIdx.x < n_tiles) load_x(blockIdx.x);
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, it++) {
+      const int tb = it & 1;
+      mbar_wait(&d_full[tb], ph_full[tb]);  // GEMM of this tile complete -> the X images are free again
+      ph_full[tb] ^= 1;
+      tc_fence_after();
+      if (tile + gridDim.x < n_tiles) load_x(tile + gridDim.x);
+      float s0 = w4s[768], s1 = w4s[769], s2 = w4s[770];
+#pragma unroll 1
+      for (int g = 0; g < 8; g++) {
+        uint32_t r[32];
+        tmem_ld32(tmem + lane_base + tb * 256 + g * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; j++) {
+          int col = g * 32 + j;
+          float v = silu_f(__uint_as_float(r[j]) + b3s[col]);
+          s0 = fmaf(v, w4s[col], s0);
+          s1 = fmaf(v, w4s[256 + col], s1);
+          s2 = fmaf(v, w4s[512 + col], s2);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&d_free[tb]);
+      const int64_t m = tile * 128 + row;
+      if (m < a.M) {
+        float* o = a.out[net] + m * 3;
+        o[0] = s0, o[1] = s1, o[2] = s2;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(tmem);
+}
+
+// ============================================================================================
 // orchestration of one conditioner pair (scale net, shift net) of coupling layer k
 static int pad16(int v) { return (v + 15) / 16 * 16; }
 
@@ -960,6 +1331,66 @@ int tc_ffn_layer(const tw_flow_config* c, const ParamView& pv, int k, int t, con
   a.F = c->dim_feedforward;
   a.eps = c->layer_norm_eps;
   return launch_ffn_tc(c, a, st);
+}
+
+int tc_in_mlp(const tw_flow_config* c, const ParamView& pv, int k, const TcScratch& tc, const int64_t* atom_types, const float* xc,
+              const float* xv, const float* z_other, float* const out[2], int64_t n, int64_t n_cond, int V, cudaStream_t st) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    TW_CUDA(cudaFuncSetAttribute(k_in_mlp_tc<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, InMlpSmem::TOTAL + 1024));
+    TW_CUDA(cudaFuncSetAttribute(k_in_mlp_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, InMlpSmem::TOTAL + 1024));
+    attr_done = true;
+  }
+  TcLayout L = TcLayout::make(c);
+  InMlpArgs a{};
+  for (int s = 0; s < 2; s++) {
+    a.w1[s] = tc.packed + L.net_offset(k, s) + L.in_w1;
+    a.w2[s] = tc.packed + L.net_offset(k, s) + L.in_w2;
+    a.b1[s] = pv.in_b(k, s, 0);
+    a.b2[s] = pv.in_b(k, s, 1);
+    a.out[s] = out[s];
+  }
+  a.embed = pv.embed(), a.atom_types = atom_types, a.xc = xc, a.xv = xv, a.z_other = z_other;
+  a.M = n * V, a.n_cond = n_cond, a.V = V, a.E = c->atom_embedding_dim, a.n_types = c->num_atom_types;
+  int64_t n_tiles = (a.M + 127) / 128;
+  dim3 grid((unsigned)(n_tiles < 74 ? n_tiles : 74), 2);
+  ProfScope prof(PROF_MLP, st);
+  if (c->precision == TW_PRECISION_BF16X3)
+    k_in_mlp_tc<3><<<grid, 192, InMlpSmem::TOTAL + 1024, st>>>(a);
+  else
+    k_in_mlp_tc<1><<<grid, 192, InMlpSmem::TOTAL + 1024, st>>>(a);
+  TW_LAUNCH_CHECK();
+  return TW_OK;
+}
+
+int tc_out_mlp(const tw_flow_config* c, const ParamView& pv, int k, const TcScratch& tc, float* const x[2], float* const out[2],
+               int64_t M, cudaStream_t st) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    TW_CUDA(cudaFuncSetAttribute(k_out_mlp_tc<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, OutMlpSmem::TOTAL + 1024));
+    TW_CUDA(cudaFuncSetAttribute(k_out_mlp_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, OutMlpSmem::TOTAL + 1024));
+    attr_done = true;
+  }
+  TcLayout L = TcLayout::make(c);
+  OutMlpArgs a{};
+  for (int s = 0; s < 2; s++) {
+    a.x[s] = x[s];
+    a.w3[s] = tc.packed + L.net_offset(k, s) + L.out_w1;
+    a.b3[s] = pv.out_b(k, s, 0);
+    a.w4[s] = pv.out_w(k, s, 1);
+    a.b4[s] = pv.out_b(k, s, 1);
+    a.out[s] = out[s];
+  }
+  a.M = M;
+  int64_t n_tiles = (M + 127) / 128;
+  dim3 grid((unsigned)(n_tiles < 74 ? n_tiles : 74), 2);
+  ProfScope prof(PROF_MLP, st);
+  if (c->precision == TW_PRECISION_BF16X3)
+    k_out_mlp_tc<3><<<grid, 192, OutMlpSmem::TOTAL + 1024, st>>>(a);
+  else
+    k_out_mlp_tc<1><<<grid, 192, OutMlpSmem::TOTAL + 1024, st>>>(a);
+  TW_LAUNCH_CHECK();
+  return TW_OK;
 }
 
 }  // namespace tw

@@ -29,7 +29,7 @@ struct TcScratch {
 };
 
 enum TcStage : uint32_t { TC_FFN = 1, TC_ATTN_PROJ = 2, TC_MIX = 4, TC_IN_MLP = 8, TC_OUT_MLP = 16, TC_ALL = 31 };
-constexpr uint32_t TC_IMPLEMENTED = TC_FFN | TC_MIX | TC_ATTN_PROJ;  // stages with a tensor-core kernel; the rest run on CUDA cores
+constexpr uint32_t TC_IMPLEMENTED = TC_ALL;  // stages with a tensor-core kernel; the rest run on CUDA cores
 
 bool tc_supported(const tw_flow_config* c);
 uint32_t tc_stage_mask();  // TW_TC_STAGES environment override (bring-up), default: every stage that exists
@@ -42,6 +42,11 @@ size_t tc_packed_bytes(const tw_flow_config* c);
 // out = LN1(x + sum_h W_c,h (A_h x)) for both networks (tensor-core mixing + projection)
 int tc_attention_layer(const tw_flow_config* c, const ParamView& pv, int k, int t, const TcScratch& tc, float* const x[2],
                        float* const out[2], int64_t n, int64_t n_cond, int V, cudaStream_t st);
+// in_mlp (feature gather + 2 linears) and out_mlp (2 linears -> s or t [M,3]) of both networks
+int tc_in_mlp(const tw_flow_config* c, const ParamView& pv, int k, const TcScratch& tc, const int64_t* atom_types, const float* xc,
+              const float* xv, const float* z_other, float* const out[2], int64_t n, int64_t n_cond, int V, cudaStream_t st);
+int tc_out_mlp(const tw_flow_config* c, const ParamView& pv, int k, const TcScratch& tc, float* const x[2], float* const out[2],
+               int64_t M, cudaStream_t st);
 int tc_ffn_layer(const tw_flow_config* c, const ParamView& pv, int k, int t, const TcScratch& tc, float* const x[2],
                  float* const out[2], int64_t M, cudaStream_t st);
 
