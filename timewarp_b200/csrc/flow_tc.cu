@@ -209,7 +209,9 @@ __device__ __forceinline__ void ln_store_row(float (&v)[128], const float* __res
 // The 128x2048 hidden activation never leaves the SM.  TMEM: D1 2x128 | H hi 64 | H lo 64 | Y 128 columns.
 constexpr int kFfnStages = 4;
 constexpr int kStageBytes = kTileBytes128;
-constexpr uint32_t TM_D1 = 0, TM_HHI = 256, TM_HLO = 320, TM_Y = 384;
+constexpr int kFfnThreads = 320;  // warp 0 producer, warp 1 MMA, warps 2-9 epilogue (two groups of four)
+// TMEM columns: D1 double buffer | H (two K halves of 64 hidden units: hi 32 + lo 32 columns each) | Y
+constexpr uint32_t TM_D1 = 0, TM_H = 256, TM_Y = 384;
 
 struct FfnArgs {
   const float* x[2];       // [M,128] layer input (post-LN1)
@@ -222,6 +224,7 @@ struct FfnArgs {
   int64_t M;
   int F;
   float eps;
+  int dbg;  // TW_FFN_DBG experiments (timing only, results invalid): 1 no weight traffic, 2 no chunk-epilogue math, 4 hi-only MMAs
 };
 
 struct FfnSmem {
@@ -234,23 +237,27 @@ struct FfnSmem {
   static constexpr int TOTAL = BARS + 256;
 };
 
+// Warp roles of the fused FFN (see the comment above):
+//   epilogue group 0 (warps 2-5): chunk epilogue for hidden units [0,64) of every chunk + the LayerNorm epilogue
+//   epilogue group 1 (warps 6-9): chunk epilogue for hidden units [64,128) + the x-tile conversion of the next tile
+// The two K halves of H are handed to the MMA warp separately, so the second GEMM of a chunk starts while the
+// other half of the chunk epilogue is still running.
 template <int kSplit>
-__global__ void __launch_bounds__(192, 1) k_ffn_tc(FfnArgs a) {
+__global__ void __launch_bounds__(kFfnThreads, 1) k_ffn_tc(FfnArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int net = blockIdx.y;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n_chunks = a.F / kFfnChunk;
   const int64_t n_tiles = (a.M + 127) / 128;
-  constexpr int kTilesPerChunk = (kSplit == 3) ? 4 : 2;
 
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FfnSmem::BARS);
-  uint64_t* full = bars;                  // [kFfnStages]
-  uint64_t* empty = bars + kFfnStages;    // [kFfnStages]
+  uint64_t* full = bars;                      // [kFfnStages]
+  uint64_t* empty = bars + kFfnStages;        // [kFfnStages]
   uint64_t* d1_full = bars + 2 * kFfnStages;  // [2]
-  uint64_t* h_full = d1_full + 2;
-  uint64_t* h_free = h_full + 1;
-  uint64_t* x_full = h_free + 1;
+  uint64_t* h_full = d1_full + 2;             // [2] per K half, 128 arrivals
+  uint64_t* h_free = h_full + 2;              // [2] per K half
+  uint64_t* x_full = h_free + 2;
   uint64_t* x_free = x_full + 1;
   uint64_t* y_full = x_free + 1;
   uint64_t* y_free = y_full + 1;
@@ -264,10 +271,11 @@ __global__ void __launch_bounds__(192, 1) k_ffn_tc(FfnArgs a) {
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], 1);
     }
-    mbar_init(&d1_full[0], 1);
-    mbar_init(&d1_full[1], 1);
-    mbar_init(h_full, 128);
-    mbar_init(h_free, 1);
+    for (int i = 0; i < 2; i++) {
+      mbar_init(&d1_full[i], 1);
+      mbar_init(&h_full[i], 128);
+      mbar_init(&h_free[i], 1);
+    }
     mbar_init(x_full, 128);
     mbar_init(x_free, 1);
     mbar_init(y_full, 1);
@@ -287,21 +295,29 @@ __global__ void __launch_bounds__(192, 1) k_ffn_tc(FfnArgs a) {
   const uint32_t tmem = *tmem_slot;
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ producer
-    if (lane == 0) {
+    // ------------------------------------------------------------------ producer (whole warp, one elected lane issues)
+    {
       uint32_t stage = 0, phase = 0;
+      int n_loaded = 0;
       const uint8_t* wbase = a.w[net];
       for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         for (int c = 0; c <= n_chunks; c++) {
-          // consumption order: G1(c) then G2(c-1)
-          for (int op = 0; op < 2; op++) {
+          for (int op = 0; op < 2; op++) {  // consumption order: G1(c) then G2(c-1)
             int chunk = (op == 0) ? c : c - 1;
             if (chunk < 0 || chunk >= n_chunks) continue;
             for (int part = 0; part < (kSplit == 3 ? 2 : 1); part++) {
               const uint8_t* src = wbase + (size_t)chunk * 4 * kTileBytes128 + (size_t)(op * 2 + part) * kTileBytes128;
               mbar_wait(&empty[stage], phase ^ 1);
-              mbar_arrive_expect_tx(&full[stage], kStageBytes);
-              bulk_g2s(smem + FfnSmem::RING + stage * kStageBytes, src, kStageBytes, &full[stage]);
+              if (elect_one()) {
+                if ((a.dbg & 1) && n_loaded >= kFfnStages) {
+                  mbar_arrive(&full[stage]);
+                } else {
+                  mbar_arrive_expect_tx(&full[stage], kStageBytes);
+                  bulk_g2s(smem + FfnSmem::RING + stage * kStageBytes, src, kStageBytes, &full[stage]);
+                }
+              }
+              __syncwarp();
+              n_loaded++;
               if (++stage == kFfnStages) stage = 0, phase ^= 1;
             }
           }
@@ -309,10 +325,10 @@ __global__ void __launch_bounds__(192, 1) k_ffn_tc(FfnArgs a) {
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer (whole warp waits, one elected lane issues)
+    {
       uint32_t stage = 0, phase = 0;
-      uint32_t ph_x = 0, ph_h = 0, ph_yfree = 0;
+      uint32_t ph_x = 0, ph_h[2] = {0, 0}, ph_yfree = 0;
       const uint32_t idesc = make_idesc_bf16(128, 128, 0, 0);
       const uint32_t xhi = smem_u32(smem + FfnSmem::X_HI), xlo = smem_u32(smem + FfnSmem::X_LO);
       const uint32_t ring = smem_u32(smem + FfnSmem::RING);
@@ -324,116 +340,121 @@ __global__ void __launch_bounds__(192, 1) k_ffn_tc(FfnArgs a) {
         for (int c = 0; c <= n_chunks; c++) {
           if (c < n_chunks) {
             const uint32_t d1 = tmem + TM_D1 + (c & 1) * 128;
-            // W1 hi tile: Xhi*W1hi, Xlo*W1hi
-            mbar_wait(&full[stage], phase);
+            mbar_wait(&full[stage], phase);  // W1 hi tile: Xhi*W1hi, Xlo*W1hi
             tc_fence_after();
-            {
+            if (elect_one()) {
               const uint32_t wt = ring + stage * kStageBytes;
 #pragma unroll
               for (int k = 0; k < 8; k++) {
                 uint32_t koff = (k >> 2) * 16384 + (k & 3) * 32;
                 mma_ss(d1, desc_kmajor_sw128(xhi + koff), desc_kmajor_sw128(wt + koff), idesc, k > 0);
               }
-              if (kSplit == 3) {
+              if (kSplit == 3 && !(a.dbg & 4)) {
 #pragma unroll
                 for (int k = 0; k < 8; k++) {
                   uint32_t koff = (k >> 2) * 16384 + (k & 3) * 32;
                   mma_ss(d1, desc_kmajor_sw128(xlo + koff), desc_kmajor_sw128(wt + koff), idesc, 1);
                 }
               }
+              mma_commit(&empty[stage]);
             }
-            mma_commit(&empty[stage]);
+            __syncwarp();
             if (++stage == kFfnStages) stage = 0, phase ^= 1;
             if (kSplit == 3) {  // W1 lo tile: Xhi*W1lo
               mbar_wait(&full[stage], phase);
               tc_fence_after();
-              const uint32_t wt = ring + stage * kStageBytes;
+              if (elect_one()) {
+                const uint32_t wt = ring + stage * kStageBytes;
+                if (!(a.dbg & 4)) {
 #pragma unroll
-              for (int k = 0; k < 8; k++) {
-                uint32_t koff = (k >> 2) * 16384 + (k & 3) * 32;
-                mma_ss(d1, desc_kmajor_sw128(xhi + koff), desc_kmajor_sw128(wt + koff), idesc, 1);
+                  for (int k = 0; k < 8; k++) {
+                    uint32_t koff = (k >> 2) * 16384 + (k & 3) * 32;
+                    mma_ss(d1, desc_kmajor_sw128(xhi + koff), desc_kmajor_sw128(wt + koff), idesc, 1);
+                  }
+                }
+                mma_commit(&empty[stage]);
               }
-              mma_commit(&empty[stage]);
+              __syncwarp();
               if (++stage == kFfnStages) stage = 0, phase ^= 1;
             }
-            mma_commit(&d1_full[c & 1]);
-            if (c == n_chunks - 1) mma_commit(x_free);  // every read of the X images has completed
+            if (elect_one()) {
+              mma_commit(&d1_full[c & 1]);
+              if (c == n_chunks - 1) mma_commit(x_free);  // every read of the X images has completed
+            }
+            __syncwarp();
           }
           if (c >= 1) {
             const int j = c - 1;
-            mbar_wait(h_full, ph_h);  // epilogue warps have written H_j (and drained D1[j&1])
-            ph_h ^= 1;
+            // both W2 tiles (hi, lo) of chunk j: K block hf of each tile multiplies H half hf
+            const uint32_t st_hi = stage;
+            mbar_wait(&full[stage], phase);
+            if (++stage == kFfnStages) stage = 0, phase ^= 1;
+            uint32_t st_lo = st_hi;
+            if (kSplit == 3) {
+              st_lo = stage;
+              mbar_wait(&full[stage], phase);
+              if (++stage == kFfnStages) stage = 0, phase ^= 1;
+            }
             if (j == 0 && !first_tile) {
               mbar_wait(y_free, ph_yfree);  // previous tile's Y has been read out
               ph_yfree ^= 1;
             }
-            tc_fence_after();
-            mbar_wait(&full[stage], phase);
-            tc_fence_after();
-            {
-              const uint32_t wt = ring + stage * kStageBytes;
+            const uint32_t whi = ring + st_hi * kStageBytes, wlo = ring + st_lo * kStageBytes;
 #pragma unroll
-              for (int k = 0; k < 8; k++) {
-                uint32_t koff = (k >> 2) * 16384 + (k & 3) * 32;
-                mma_ts(tmem + TM_Y, tmem + TM_HHI + k * 8, desc_kmajor_sw128(wt + koff), idesc, (j > 0 || k > 0) ? 1 : 0);
-              }
-              if (kSplit == 3) {
-#pragma unroll
-                for (int k = 0; k < 8; k++) {
-                  uint32_t koff = (k >> 2) * 16384 + (k & 3) * 32;
-                  mma_ts(tmem + TM_Y, tmem + TM_HLO + k * 8, desc_kmajor_sw128(wt + koff), idesc, 1);
-                }
-              }
-            }
-            mma_commit(&empty[stage]);
-            if (++stage == kFfnStages) stage = 0, phase ^= 1;
-            if (kSplit == 3) {
-              mbar_wait(&full[stage], phase);
+            for (int hf = 0; hf < 2; hf++) {
+              mbar_wait(&h_full[hf], ph_h[hf]);  // epilogue group hf has written its half of H_j
+              ph_h[hf] ^= 1;
               tc_fence_after();
-              const uint32_t wt = ring + stage * kStageBytes;
+              if (elect_one()) {
+                const uint32_t h_hi = tmem + TM_H + hf * 64, h_lo = h_hi + 32;
 #pragma unroll
-              for (int k = 0; k < 8; k++) {
-                uint32_t koff = (k >> 2) * 16384 + (k & 3) * 32;
-                mma_ts(tmem + TM_Y, tmem + TM_HHI + k * 8, desc_kmajor_sw128(wt + koff), idesc, 1);
+                for (int k = 0; k < 4; k++)
+                  mma_ts(tmem + TM_Y, h_hi + k * 8, desc_kmajor_sw128(whi + hf * 16384 + k * 32), idesc, (j > 0 || hf > 0 || k > 0) ? 1 : 0);
+                if (kSplit == 3 && !(a.dbg & 4)) {
+#pragma unroll
+                  for (int k = 0; k < 4; k++) mma_ts(tmem + TM_Y, h_lo + k * 8, desc_kmajor_sw128(whi + hf * 16384 + k * 32), idesc, 1);
+#pragma unroll
+                  for (int k = 0; k < 4; k++) mma_ts(tmem + TM_Y, h_hi + k * 8, desc_kmajor_sw128(wlo + hf * 16384 + k * 32), idesc, 1);
+                }
+                mma_commit(&h_free[hf]);
               }
-              mma_commit(&empty[stage]);
-              if (++stage == kFfnStages) stage = 0, phase ^= 1;
+              __syncwarp();
             }
-            mma_commit(h_free);
-            if (j == n_chunks - 1) mma_commit(y_full);
+            if (elect_one()) {
+              mma_commit(&empty[st_hi]);
+              if (kSplit == 3) mma_commit(&empty[st_lo]);
+              if (j == n_chunks - 1) mma_commit(y_full);
+            }
+            __syncwarp();
           }
         }
         first_tile = false;
       }
     }
   } else {
-    // ------------------------------------------------------------------ convert / epilogue warps (128 threads)
+    // ------------------------------------------------------------------ epilogue warps (2 groups x 128 threads)
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    const int hf = (warp - 2) >> 2;         // epilogue group = K half of H this thread produces
     const int row = q * 32 + lane;          // token row inside the tile
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-    const int ew = warp - 2;                // 0..3: slice of the tile this warp converts
     uint32_t ph_d1[2] = {0, 0}, ph_hfree = 0, ph_xfree = 0, ph_y = 0;
     bool first_tile = true, first_chunk_ever = true;
     const float* x = a.x[net];
     float* out = a.out[net];
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+
+    auto convert_x = [&](int64_t tile) {  // group 1: x tile -> bf16 hi/lo operand images (K-major, 128B swizzle)
       const int64_t row0 = tile * 128;
-      // ---- (a) x tile -> bf16 hi/lo operand images (K-major, 128B swizzle)
-      if (!first_tile) {
-        mbar_wait(x_free, ph_xfree);
-        ph_xfree ^= 1;
-      }
 #pragma unroll 1
       for (int it = 0; it < 32; it += 8) {
         float4 v[8];
 #pragma unroll
         for (int u = 0; u < 8; u++) {
-          int r = ew * 32 + it + u;
+          int r = q * 32 + it + u;
           v[u] = (row0 + r < a.M) ? __ldg(reinterpret_cast<const float4*>(x + (row0 + r) * 128) + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
 #pragma unroll
         for (int u = 0; u < 8; u++) {
-          int r = ew * 32 + it + u;
+          int r = q * 32 + it + u;
           uint32_t h0, l0, h1, l1;
           split2(v[u].x, v[u].y, h0, l0);
           split2(v[u].z, v[u].w, h1, l1);
@@ -444,56 +465,108 @@ __global__ void __launch_bounds__(192, 1) k_ffn_tc(FfnArgs a) {
       }
       fence_proxy_async_smem();
       mbar_arrive(x_full);
+    };
 
-      // ---- (b) per chunk: D1 -> bias + ReLU -> hi/lo -> H (TMEM)
+    if (hf == 1 && (int64_t)blockIdx.x < n_tiles) convert_x(blockIdx.x);
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const int64_t row0 = tile * 128;
+      // ---- per chunk: D1[:, hf*64 .. +64) -> bias + ReLU -> hi/lo -> H half hf (TMEM)
       for (int c = 0; c < n_chunks; c++) {
         mbar_wait(&d1_full[c & 1], ph_d1[c & 1]);
         ph_d1[c & 1] ^= 1;
         if (!first_chunk_ever) {
-          mbar_wait(h_free, ph_hfree);  // G2 of the previous chunk has consumed H
+          mbar_wait(&h_free[hf], ph_hfree);  // the second GEMM of the previous chunk has consumed this half
           ph_hfree ^= 1;
         }
         first_chunk_ever = false;
         tc_fence_after();
-        const float* bc = b1s + c * kFfnChunk;
+        if (a.dbg & 2) {
+          tc_fence_before();
+          mbar_arrive(&h_full[hf]);
+          continue;
+        }
+        const float* bc = b1s + c * kFfnChunk + hf * 64;
+        uint32_t r0[32], r1[32];
+        tmem_ld32(tmem + lane_base + TM_D1 + (c & 1) * 128 + hf * 64, r0);
+        tmem_ld32(tmem + lane_base + TM_D1 + (c & 1) * 128 + hf * 64 + 32, r1);
+        tmem_ld_wait();
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          float2 bb = *reinterpret_cast<const float2*>(bc + j);
+          split2(fmaxf(__uint_as_float(r0[j]) + bb.x, 0.f), fmaxf(__uint_as_float(r0[j + 1]) + bb.y, 0.f), hi[j >> 1], lo[j >> 1]);
+        }
+        tmem_st16(tmem + lane_base + TM_H + hf * 64, hi);
+        if (kSplit == 3) tmem_st16(tmem + lane_base + TM_H + hf * 64 + 32, lo);
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          float2 bb = *reinterpret_cast<const float2*>(bc + 32 + j);
+          split2(fmaxf(__uint_as_float(r1[j]) + bb.x, 0.f), fmaxf(__uint_as_float(r1[j + 1]) + bb.y, 0.f), hi[j >> 1], lo[j >> 1]);
+        }
+        tmem_st16(tmem + lane_base + TM_H + hf * 64 + 16, hi);
+        if (kSplit == 3) tmem_st16(tmem + lane_base + TM_H + hf * 64 + 48, lo);
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(&h_full[hf]);
+      }
+
+      if (hf == 1) {
+        // ---- group 1: operand images of the next tile (after every GEMM-1 of this tile has read the old ones)
+        if (tile + gridDim.x < n_tiles) {
+          mbar_wait(x_free, ph_xfree);
+          ph_xfree ^= 1;
+          convert_x(tile + gridDim.x);
+        }
+      } else {
+        // ---- group 0: Y + b2 + residual -> LayerNorm -> global   (two passes over TMEM, no 128-register row)
+        mbar_wait(y_full, ph_y);
+        ph_y ^= 1;
+        tc_fence_after();
+        const int64_t grow = row0 + row;
+        const bool valid = grow < a.M;
+        const float4* xr = reinterpret_cast<const float4*>(x + (valid ? grow : 0) * 128);
+        float sum = 0.f, sq = 0.f;
 #pragma unroll 1
         for (int g = 0; g < 4; g++) {
           uint32_t r[32];
-          tmem_ld32(tmem + lane_base + TM_D1 + (c & 1) * 128 + g * 32, r);
+          tmem_ld32(tmem + lane_base + TM_Y + g * 32, r);
           tmem_ld_wait();
-          uint32_t hi[16], lo[16];
 #pragma unroll
-          for (int j = 0; j < 32; j += 2) {
-            float2 bb = *reinterpret_cast<const float2*>(bc + g * 32 + j);
-            float v0 = fmaxf(__uint_as_float(r[j]) + bb.x, 0.f);
-            float v1 = fmaxf(__uint_as_float(r[j + 1]) + bb.y, 0.f);
-            split2(v0, v1, hi[j >> 1], lo[j >> 1]);
+          for (int j = 0; j < 8; j++) {
+            float4 xv = __ldg(xr + g * 8 + j);
+            float4 bv = *reinterpret_cast<const float4*>(vecs + g * 32 + 4 * j);
+            float v0 = __uint_as_float(r[4 * j]) + (bv.x + xv.x), v1 = __uint_as_float(r[4 * j + 1]) + (bv.y + xv.y);
+            float v2 = __uint_as_float(r[4 * j + 2]) + (bv.z + xv.z), v3 = __uint_as_float(r[4 * j + 3]) + (bv.w + xv.w);
+            sum += (v0 + v1) + (v2 + v3);
+            sq = fmaf(v0, v0, sq), sq = fmaf(v1, v1, sq), sq = fmaf(v2, v2, sq), sq = fmaf(v3, v3, sq);
           }
-          tmem_st16(tmem + lane_base + TM_HHI + g * 16, hi);
-          if (kSplit == 3) tmem_st16(tmem + lane_base + TM_HLO + g * 16, lo);
         }
-        tmem_st_wait();
+        const float mean = sum * (1.f / 128.f);
+        const float var = fmaxf(sq * (1.f / 128.f) - mean * mean, 0.f);
+        const float rstd = 1.0f / sqrtf(var + a.eps);
+        float4* orow = reinterpret_cast<float4*>(out + (valid ? grow : 0) * 128);
+#pragma unroll 1
+        for (int g = 0; g < 4; g++) {
+          uint32_t r[32];
+          tmem_ld32(tmem + lane_base + TM_Y + g * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 8; j++) {
+            float4 xv = __ldg(xr + g * 8 + j);
+            float4 bv = *reinterpret_cast<const float4*>(vecs + g * 32 + 4 * j);
+            float4 g4 = *reinterpret_cast<const float4*>(vecs + 128 + g * 32 + 4 * j);
+            float4 b4 = *reinterpret_cast<const float4*>(vecs + 256 + g * 32 + 4 * j);
+            float4 o;
+            o.x = ((__uint_as_float(r[4 * j]) + (bv.x + xv.x)) - mean) * rstd * g4.x + b4.x;
+            o.y = ((__uint_as_float(r[4 * j + 1]) + (bv.y + xv.y)) - mean) * rstd * g4.y + b4.y;
+            o.z = ((__uint_as_float(r[4 * j + 2]) + (bv.z + xv.z)) - mean) * rstd * g4.z + b4.z;
+            o.w = ((__uint_as_float(r[4 * j + 3]) + (bv.w + xv.w)) - mean) * rstd * g4.w + b4.w;
+            if (valid) orow[g * 8 + j] = o;
+          }
+        }
         tc_fence_before();
-        mbar_arrive(h_full);
+        mbar_arrive(y_free);
       }
-
-      // ---- (c) Y -> + b2 + residual -> LayerNorm -> global
-      mbar_wait(y_full, ph_y);
-      ph_y ^= 1;
-      tc_fence_after();
-      float v[128];
-#pragma unroll
-      for (int g = 0; g < 4; g++) {
-        uint32_t r[32];
-        tmem_ld32(tmem + lane_base + TM_Y + g * 32, r);
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 32; j++) v[g * 32 + j] = __uint_as_float(r[j]);
-      }
-      tc_fence_before();
-      mbar_arrive(y_free);  // Y is in registers: the next tile may overwrite it
-      const int64_t grow = row0 + row;
-      if (grow < a.M) ln_store_row(v, vecs, x + grow * 128, vecs + 128, vecs + 256, a.eps, out + grow * 128);
       first_tile = false;
     }
   }
@@ -517,9 +590,9 @@ static int launch_ffn_tc(const tw_flow_config* c, const FfnArgs& a, cudaStream_t
   dim3 grid(gx, 2);
   ProfScope prof(PROF_FFN, st);
   if (c->precision == TW_PRECISION_BF16X3)
-    k_ffn_tc<3><<<grid, 192, FfnSmem::TOTAL + 1024, st>>>(a);
+    k_ffn_tc<3><<<grid, kFfnThreads, FfnSmem::TOTAL + 1024, st>>>(a);
   else
-    k_ffn_tc<1><<<grid, 192, FfnSmem::TOTAL + 1024, st>>>(a);
+    k_ffn_tc<1><<<grid, kFfnThreads, FfnSmem::TOTAL + 1024, st>>>(a);
   TW_LAUNCH_CHECK();
   return TW_OK;
 }
@@ -614,20 +687,23 @@ __global__ void __launch_bounds__(192, 1) k_mix_tc(MixArgs a) {
   const int ksteps = VP / 16;
 
   if (warp == 0) {
-    if (lane == 0) {
+    {
       uint32_t stage = 0, phase = 0;
       for (int64_t n = blockIdx.x; n < a.n; n += gridDim.x) {
         const uint8_t* src = a.scores_img + (size_t)(n % a.n_cond) * H * stage_bytes;
         for (int h = 0; h < H; h++) {
           mbar_wait(&empty[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full[stage], kSplit == 3 ? stage_bytes : mat_bytes);
-          bulk_g2s(ring + stage * stage_stride, src + (size_t)h * stage_bytes, kSplit == 3 ? stage_bytes : mat_bytes, &full[stage]);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&full[stage], kSplit == 3 ? stage_bytes : mat_bytes);
+            bulk_g2s(ring + stage * stage_stride, src + (size_t)h * stage_bytes, kSplit == 3 ? stage_bytes : mat_bytes, &full[stage]);
+          }
+          __syncwarp();
           if (++stage == kMixStages) stage = 0, phase ^= 1;
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       uint32_t stage = 0, phase = 0;
       uint32_t ph_hs[2] = {0, 0}, ph_dfree[2] = {0, 0};
       const uint32_t idesc = make_idesc_bf16(128, VP, 0, 0);
@@ -647,21 +723,24 @@ __global__ void __launch_bounds__(192, 1) k_mix_tc(MixArgs a) {
           }
           mbar_wait(&full[stage], phase);
           tc_fence_after();
-          const uint32_t s_hi = smem_u32(ring + stage * stage_stride), s_lo = s_hi + mat_bytes;
-          const uint32_t d = tmem + MX_D + db * 128;
-          for (int k = 0; k < ksteps; k++)
-            mma_ts(d, hs_hi + k * 8, make_smem_desc(s_hi + k * 256, lbo, sbo, LAYOUT_NONE), idesc, k > 0);
-          if (kSplit == 3) {
+          if (elect_one()) {
+            const uint32_t s_hi = smem_u32(ring + stage * stage_stride), s_lo = s_hi + mat_bytes;
+            const uint32_t d = tmem + MX_D + db * 128;
             for (int k = 0; k < ksteps; k++)
-              mma_ts(d, hs_lo + k * 8, make_smem_desc(s_hi + k * 256, lbo, sbo, LAYOUT_NONE), idesc, 1);
-            for (int k = 0; k < ksteps; k++)
-              mma_ts(d, hs_hi + k * 8, make_smem_desc(s_lo + k * 256, lbo, sbo, LAYOUT_NONE), idesc, 1);
+              mma_ts(d, hs_hi + k * 8, make_smem_desc(s_hi + k * 256, lbo, sbo, LAYOUT_NONE), idesc, k > 0);
+            if (kSplit == 3) {
+              for (int k = 0; k < ksteps; k++)
+                mma_ts(d, hs_lo + k * 8, make_smem_desc(s_hi + k * 256, lbo, sbo, LAYOUT_NONE), idesc, 1);
+              for (int k = 0; k < ksteps; k++)
+                mma_ts(d, hs_hi + k * 8, make_smem_desc(s_lo + k * 256, lbo, sbo, LAYOUT_NONE), idesc, 1);
+            }
+            mma_commit(&empty[stage]);
+            mma_commit(&d_full[db]);
+            if (h == H - 1) mma_commit(&hs_free[sb]);
           }
-          mma_commit(&empty[stage]);
+          __syncwarp();
           if (++stage == kMixStages) stage = 0, phase ^= 1;
-          mma_commit(&d_full[db]);
         }
-        mma_commit(&hs_free[sb]);
       }
     }
   } else {
@@ -784,22 +863,25 @@ __global__ void __launch_bounds__(192, 1) k_proj_tc(ProjArgs a) {
   const size_t a_tile_bytes = (size_t)a.KB * 32768;
 
   if (warp == 0) {
-    if (lane == 0) {
+    {
       uint32_t stage = 0, phase = 0;
       const uint32_t a_bytes = kSplit == 3 ? 32768 : 16384;
       for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         for (int kb = 0; kb < a.KB; kb++) {
           mbar_wait(&empty[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full[stage], 2 * a_bytes);
-          uint8_t* dst = ring + stage * kProjStageBytes;
-          bulk_g2s(dst, a.a_img[net] + tile * a_tile_bytes + (size_t)kb * 32768, a_bytes, &full[stage]);
-          bulk_g2s(dst + 32768, a.w[net] + (size_t)kb * 32768, a_bytes, &full[stage]);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&full[stage], 2 * a_bytes);
+            uint8_t* dst = ring + stage * kProjStageBytes;
+            bulk_g2s(dst, a.a_img[net] + tile * a_tile_bytes + (size_t)kb * 32768, a_bytes, &full[stage]);
+            bulk_g2s(dst + 32768, a.w[net] + (size_t)kb * 32768, a_bytes, &full[stage]);
+          }
+          __syncwarp();
           if (++stage == kProjStages) stage = 0, phase ^= 1;
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       uint32_t stage = 0, phase = 0, ph_free[2] = {0, 0};
       const uint32_t idesc = make_idesc_bf16(128, 128, 0, 0);
       int64_t it = 0;
@@ -814,19 +896,22 @@ __global__ void __launch_bounds__(192, 1) k_proj_tc(ProjArgs a) {
         for (int kb = 0; kb < a.KB; kb++) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
-          const uint32_t ahi = smem_u32(ring + stage * kProjStageBytes), alo = ahi + 16384, whi = ahi + 32768, wlo = whi + 16384;
+          if (elect_one()) {
+            const uint32_t ahi = smem_u32(ring + stage * kProjStageBytes), alo = ahi + 16384, whi = ahi + 32768, wlo = whi + 16384;
 #pragma unroll
-          for (int k = 0; k < 4; k++) mma_ss(d, desc_kmajor_sw128(ahi + k * 32), desc_kmajor_sw128(whi + k * 32), idesc, (kb > 0 || k > 0) ? 1 : 0);
-          if (kSplit == 3) {
+            for (int k = 0; k < 4; k++) mma_ss(d, desc_kmajor_sw128(ahi + k * 32), desc_kmajor_sw128(whi + k * 32), idesc, (kb > 0 || k > 0) ? 1 : 0);
+            if (kSplit == 3) {
 #pragma unroll
-            for (int k = 0; k < 4; k++) mma_ss(d, desc_kmajor_sw128(alo + k * 32), desc_kmajor_sw128(whi + k * 32), idesc, 1);
+              for (int k = 0; k < 4; k++) mma_ss(d, desc_kmajor_sw128(alo + k * 32), desc_kmajor_sw128(whi + k * 32), idesc, 1);
 #pragma unroll
-            for (int k = 0; k < 4; k++) mma_ss(d, desc_kmajor_sw128(ahi + k * 32), desc_kmajor_sw128(wlo + k * 32), idesc, 1);
+              for (int k = 0; k < 4; k++) mma_ss(d, desc_kmajor_sw128(ahi + k * 32), desc_kmajor_sw128(wlo + k * 32), idesc, 1);
+            }
+            mma_commit(&empty[stage]);
+            if (kb == a.KB - 1) mma_commit(&y_full[tb]);
           }
-          mma_commit(&empty[stage]);
+          __syncwarp();
           if (++stage == kProjStages) stage = 0, phase ^= 1;
         }
-        mma_commit(&y_full[tb]);
       }
     }
   } else {
@@ -924,7 +1009,7 @@ __global__ void __launch_bounds__(192, 1) k_in_mlp_tc(InMlpArgs a) {
   constexpr uint32_t T_D = 0, T_HHI = 256, T_HLO = 384;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t w1b = kSplit == 3 ? 65536 : 32768;
       mbar_arrive_expect_tx(w_full, w1b + (kSplit == 3 ? 131072 : 4 * 16384));
       bulk_g2s(smem + InMlpSmem::W1, a.w1[net], w1b, w_full);
@@ -935,7 +1020,7 @@ __global__ void __launch_bounds__(192, 1) k_in_mlp_tc(InMlpArgs a) {
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       mbar_wait(w_full, 0);
       const uint32_t idesc1 = make_idesc_bf16(128, 256, 0, 0), idesc2 = make_idesc_bf16(128, 128, 0, 0);
       const uint32_t ahi = smem_u32(smem + InMlpSmem::A_HI), alo = smem_u32(smem + InMlpSmem::A_LO);
@@ -946,29 +1031,35 @@ __global__ void __launch_bounds__(192, 1) k_in_mlp_tc(InMlpArgs a) {
         mbar_wait(a_full, ph);
         if (it > 0) mbar_wait(d_free, ph ^ 1);  // previous tile's D2 (aliases D1) has been read
         tc_fence_after();
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 4; k++) mma_ss(tmem + T_D, desc_kmajor_sw128(ahi + k * 32), desc_kmajor_sw128(w1hi + k * 32), idesc1, k > 0);
-        if (kSplit == 3) {
+          for (int k = 0; k < 4; k++) mma_ss(tmem + T_D, desc_kmajor_sw128(ahi + k * 32), desc_kmajor_sw128(w1hi + k * 32), idesc1, k > 0);
+          if (kSplit == 3) {
 #pragma unroll
-          for (int k = 0; k < 4; k++) mma_ss(tmem + T_D, desc_kmajor_sw128(alo + k * 32), desc_kmajor_sw128(w1hi + k * 32), idesc1, 1);
+            for (int k = 0; k < 4; k++) mma_ss(tmem + T_D, desc_kmajor_sw128(alo + k * 32), desc_kmajor_sw128(w1hi + k * 32), idesc1, 1);
 #pragma unroll
-          for (int k = 0; k < 4; k++) mma_ss(tmem + T_D, desc_kmajor_sw128(ahi + k * 32), desc_kmajor_sw128(w1lo + k * 32), idesc1, 1);
+            for (int k = 0; k < 4; k++) mma_ss(tmem + T_D, desc_kmajor_sw128(ahi + k * 32), desc_kmajor_sw128(w1lo + k * 32), idesc1, 1);
+          }
+          mma_commit(d1_full);
         }
-        mma_commit(d1_full);
+        __syncwarp();
         mbar_wait(h_full, ph);
         tc_fence_after();
-#pragma unroll
-        for (int k = 0; k < 16; k++)
-          mma_ts(tmem + T_D, tmem + T_HHI + k * 8, desc_kmajor_sw128(w2 + (k >> 2) * 32768 + (k & 3) * 32), idesc2, k > 0);
-        if (kSplit == 3) {
+        if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < 16; k++)
-            mma_ts(tmem + T_D, tmem + T_HLO + k * 8, desc_kmajor_sw128(w2 + (k >> 2) * 32768 + (k & 3) * 32), idesc2, 1);
+            mma_ts(tmem + T_D, tmem + T_HHI + k * 8, desc_kmajor_sw128(w2 + (k >> 2) * 32768 + (k & 3) * 32), idesc2, k > 0);
+          if (kSplit == 3) {
 #pragma unroll
-          for (int k = 0; k < 16; k++)
-            mma_ts(tmem + T_D, tmem + T_HHI + k * 8, desc_kmajor_sw128(w2 + (k >> 2) * 32768 + 16384 + (k & 3) * 32), idesc2, 1);
+            for (int k = 0; k < 16; k++)
+              mma_ts(tmem + T_D, tmem + T_HLO + k * 8, desc_kmajor_sw128(w2 + (k >> 2) * 32768 + (k & 3) * 32), idesc2, 1);
+#pragma unroll
+            for (int k = 0; k < 16; k++)
+              mma_ts(tmem + T_D, tmem + T_HHI + k * 8, desc_kmajor_sw128(w2 + (k >> 2) * 32768 + 16384 + (k & 3) * 32), idesc2, 1);
+          }
+          mma_commit(d2_full);
         }
-        mma_commit(d2_full);
+        __syncwarp();
         ph ^= 1;
       }
     }
@@ -1115,7 +1206,7 @@ __global__ void __launch_bounds__(192, 1) k_out_mlp_tc(OutMlpArgs a) {
   const uint32_t tmem = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       if (kSplit == 3) {
         mbar_arrive_expect_tx(w_full, 131072);
         bulk_g2s(smem + OutMlpSmem::W3, a.w3[net], 65536, w_full);
@@ -1127,7 +1218,7 @@ __global__ void __launch_bounds__(192, 1) k_out_mlp_tc(OutMlpArgs a) {
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       mbar_wait(w_full, 0);
       const uint32_t idesc = make_idesc_bf16(128, 256, 0, 0);
       const uint32_t xhi = smem_u32(smem + OutMlpSmem::X_HI), xlo = smem_u32(smem + OutMlpSmem::X_LO), w3 = smem_u32(smem + OutMlpSmem::W3);
@@ -1143,24 +1234,27 @@ __global__ void __launch_bounds__(192, 1) k_out_mlp_tc(OutMlpArgs a) {
         }
         tc_fence_after();
         const uint32_t d = tmem + tb * 256;
-#pragma unroll
-        for (int k = 0; k < 8; k++) {
-          uint32_t ao = (k >> 2) * 16384 + (k & 3) * 32, wo = (k >> 2) * 65536 + (k & 3) * 32;
-          mma_ss(d, desc_kmajor_sw128(xhi + ao), desc_kmajor_sw128(w3 + wo), idesc, k > 0);
-        }
-        if (kSplit == 3) {
+        if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < 8; k++) {
             uint32_t ao = (k >> 2) * 16384 + (k & 3) * 32, wo = (k >> 2) * 65536 + (k & 3) * 32;
-            mma_ss(d, desc_kmajor_sw128(xlo + ao), desc_kmajor_sw128(w3 + wo), idesc, 1);
+            mma_ss(d, desc_kmajor_sw128(xhi + ao), desc_kmajor_sw128(w3 + wo), idesc, k > 0);
           }
+          if (kSplit == 3) {
 #pragma unroll
-          for (int k = 0; k < 8; k++) {
-            uint32_t ao = (k >> 2) * 16384 + (k & 3) * 32, wo = (k >> 2) * 65536 + 32768 + (k & 3) * 32;
-            mma_ss(d, desc_kmajor_sw128(xhi + ao), desc_kmajor_sw128(w3 + wo), idesc, 1);
+            for (int k = 0; k < 8; k++) {
+              uint32_t ao = (k >> 2) * 16384 + (k & 3) * 32, wo = (k >> 2) * 65536 + (k & 3) * 32;
+              mma_ss(d, desc_kmajor_sw128(xlo + ao), desc_kmajor_sw128(w3 + wo), idesc, 1);
+            }
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+              uint32_t ao = (k >> 2) * 16384 + (k & 3) * 32, wo = (k >> 2) * 65536 + 32768 + (k & 3) * 32;
+              mma_ss(d, desc_kmajor_sw128(xhi + ao), desc_kmajor_sw128(w3 + wo), idesc, 1);
+            }
           }
+          mma_commit(&d_full[tb]);
         }
-        mma_commit(&d_full[tb]);
+        __syncwarp();
       }
     }
   } else {
@@ -1330,6 +1424,14 @@ int tc_ffn_layer(const tw_flow_config* c, const ParamView& pv, int k, int t, con
   a.M = M;
   a.F = c->dim_feedforward;
   a.eps = c->layer_norm_eps;
+  {
+    static int dbg = -1;
+    if (dbg < 0) {
+      const char* e = getenv("TW_FFN_DBG");
+      dbg = e ? atoi(e) : 0;
+    }
+    a.dbg = dbg;
+  }
   return launch_ffn_tc(c, a, st);
 }
 

@@ -12,6 +12,16 @@ namespace umma {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// One lane of a CONVERGED warp (elect.sync).  tcgen05.mma / commit / bulk copies take their operands from
+// uniform registers: issuing them under `if (elect_one())` inside warp-uniform control flow lets the compiler
+// keep descriptors on the uniform datapath; a `lane == 0` branch instead makes it emit a per-instruction
+// ELECT / R2UR.BROADCAST / BRA.U.ANY serialisation loop (seen in SASS, ~100+ cycles per MMA).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");

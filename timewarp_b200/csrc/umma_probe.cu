@@ -124,9 +124,73 @@ __global__ void __launch_bounds__(128, 1) k_umma_probe(ProbeArgs p) {
   if (warp == 0) tmem_dealloc<512>(tmem);
 }
 
+// Timing micro-benchmark: one thread issues `n_mma` M128 x N x K16 MMAs (SS or TS) with a tcgen05.commit
+// every `commit_every` MMAs (each commit waited for if `wait_each`), operands are zeros.
+// out[0] = cycles until everything was issued, out[1] = cycles until the last commit arrived.
+__global__ void __launch_bounds__(128, 1) k_umma_timing(int n_mma, int commit_every, int N, int ts, int wait_each, long long* out) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (warp == 0) tmem_alloc<512>(&tmem_slot);
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    mbar_fence_init();
+  }
+  for (int i = tid; i < 96 * 1024 / 16; i += 128) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  if (tid == 0) {
+    const uint32_t idesc = make_idesc_bf16(128, N, 0, 0);
+    const uint32_t a0 = smem_u32(smem), b0 = smem_u32(smem + 32 * 1024);
+    uint32_t phase = 0;
+    int commits = 0, waited = 0;
+    long long t0 = clock64();
+    for (int i = 0; i < n_mma; i++) {
+      uint32_t koff = ((i & 7) >> 2) * 16384 + (i & 3) * 32;
+      if (ts) mma_ts(tmem, tmem + 256 + (i & 7) * 8, desc_kmajor_sw128(b0 + (i & 3) * 32), idesc, 1);
+      else mma_ss(tmem, desc_kmajor_sw128(a0 + koff), desc_kmajor_sw128(b0 + (i & 3) * 32), idesc, 1);
+      if ((i + 1) % commit_every == 0 || i == n_mma - 1) {
+        mma_commit(&bar);
+        commits++;
+        if (wait_each) {
+          mbar_wait(&bar, phase);
+          phase ^= 1;
+          waited++;
+        }
+      }
+    }
+    long long t1 = clock64();
+    while (waited < commits) {
+      mbar_wait(&bar, phase);
+      phase ^= 1;
+      waited++;
+    }
+    long long t2 = clock64();
+    out[0] = t1 - t0;
+    out[1] = t2 - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<512>(tmem);
+}
+
 }  // namespace tw
 
 using namespace tw;
+
+extern "C" int tw_debug_umma_timing(int n_mma, int commit_every, int N, int ts, int wait_each, long long* out, void* stream) {
+  TW_CHECK_ARG(out && n_mma > 0 && commit_every > 0 && N >= 16 && N <= 256, "bad args");
+  const int smem = 97 * 1024 + 1024;
+  TW_CUDA(cudaFuncSetAttribute(k_umma_timing, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  k_umma_timing<<<1, 128, smem, (cudaStream_t)stream>>>(n_mma, commit_every, N, ts, wait_each, out);
+  TW_LAUNCH_CHECK();
+  return TW_OK;
+}
 
 extern "C" int tw_debug_umma_probe(const float* A, const float* B, float* out, int N, int K, int a_mode, int b_mode, int d_col,
                                    int a_col, int* status, void* stream) {
