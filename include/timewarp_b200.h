@@ -204,8 +204,8 @@ int tw_threshold_accept(float* x_coords, float* e_old, const float* y_coords, co
 int tw_debug_umma_probe(const float* A, const float* B, float* out, int N, int K, int a_mode, int b_mode, int d_col,
                         int a_col, int* status, void* stream);
 
-/* Debug: issue/complete timing of n_mma M128xNxK16 MMAs with a commit every `commit_every` MMAs. */
-int tw_debug_umma_timing(int n_mma, int commit_every, int N, int ts, int wait_each, long long* out, void* stream);
+/* Debug: issue/complete cycle counts of n_mma back-to-back M128xNxK16 MMAs (out[0] issue, out[1] done). */
+int tw_debug_umma_timing(int n_mma, int N, int ts, int b_noswizzle, long long* out, void* stream);
 
 #ifdef __cplusplus
 }

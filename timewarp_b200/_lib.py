@@ -73,7 +73,7 @@ _SIGNATURES = {
     "tw_kinetic_energy": (C.c_int, [_P, _P, C.c_float, _I64, _I64, _P, _P]),
     "tw_mh_accept": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I64, _I64, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "tw_debug_umma_probe": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
-    "tw_debug_umma_timing": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
+    "tw_debug_umma_timing": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
     "tw_threshold_accept": (C.c_int, [_P, _P, _P, _P, C.c_float, _I64, _I64, _P, _P]),
 }  # fmt: skip
 

@@ -632,7 +632,6 @@ __global__ void __launch_bounds__(256) k_scores_img(const float* __restrict__ sc
 // images ([128 tokens x 64] K-major SW128 tiles, hi/lo) that the projection kernel bulk-copies.
 constexpr uint32_t MX_HS = 0;      // X^T hi/lo, double buffered: [buf][hi 64 | lo 64] columns
 constexpr uint32_t MX_D = 256;     // accumulators, double buffered: 2 x 128 columns
-constexpr int kMixStages = 3;
 
 struct MixArgs {
   const float* x[2];         // [n*V, 128] layer input
@@ -640,6 +639,7 @@ struct MixArgs {
   const uint8_t* scores_img;  // [n_cond][H][hi | lo][VP*VP*2]
   int64_t n, n_cond;
   int V, VP, H;
+  int n_stages;              // ring depth (3, or 2 when VP > 96)
 };
 
 __device__ __forceinline__ void split1(float v, uint16_t& hi, uint16_t& lo) {
@@ -648,31 +648,37 @@ __device__ __forceinline__ void split1(float v, uint16_t& hi, uint16_t& lo) {
   hi = *reinterpret_cast<uint16_t*>(&h);
   lo = *reinterpret_cast<uint16_t*>(&l);
 }
+__device__ __forceinline__ void group_bar_sync(int g) { asm volatile("bar.sync %0, 128;" ::"r"(g + 1) : "memory"); }
 
+// Warp roles: warp 0 streams the score images, warp 1 issues the MMAs, then `n_groups` (1 or 2) epilogue groups of
+// four warps.  Group g drains accumulator buffer g (every other head): TMEM -> bf16 hi/lo rows in its staging
+// buffer -> 16-byte chunks of the swizzled A-operand images in global memory.
 template <int kSplit>
-__global__ void __launch_bounds__(192, 1) k_mix_tc(MixArgs a) {
+__global__ void __launch_bounds__(320, 1) k_mix_tc(MixArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int net = blockIdx.y;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int V = a.V, VP = a.VP, H = a.H;
+  const int V = a.V, VP = a.VP, H = a.H, n_stages = a.n_stages;
+  const int n_groups = (blockDim.x - 64) / 128;
   const uint32_t mat_bytes = (uint32_t)VP * VP * 2;
   const uint32_t stage_bytes = 2 * mat_bytes;
-  uint8_t* ring = smem;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kMixStages * ((stage_bytes + 1023) & ~1023u));
-  uint64_t* full = bars;
-  uint64_t* empty = bars + kMixStages;
-  uint64_t* hs_full = empty + kMixStages;  // [2]
-  uint64_t* hs_free = hs_full + 2;         // [2]
-  uint64_t* d_full = hs_free + 2;          // [2]
-  uint64_t* d_free = d_full + 2;           // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d_free + 2);
   const uint32_t stage_stride = (stage_bytes + 1023) & ~1023u;
+  uint8_t* ring = smem;
+  uint8_t* staging0 = smem + n_stages * stage_stride;  // per group: [hi: VP x 256 B][lo: VP x 256 B]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging0 + (size_t)n_groups * VP * 512);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + 3;
+  uint64_t* hs_full = empty + 3;   // [2]
+  uint64_t* hs_free = hs_full + 2;  // [2]
+  uint64_t* d_full = hs_free + 2;   // [2]
+  uint64_t* d_free = d_full + 2;    // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d_free + 2);
 
   if (tid == 0) {
-    for (int i = 0; i < kMixStages; i++) mbar_init(&full[i], 1), mbar_init(&empty[i], 1);
+    for (int i = 0; i < 3; i++) mbar_init(&full[i], 1), mbar_init(&empty[i], 1);
     for (int i = 0; i < 2; i++) {
-      mbar_init(&hs_full[i], 128);
+      mbar_init(&hs_full[i], 128 * n_groups);
       mbar_init(&hs_free[i], 1);
       mbar_init(&d_full[i], 1);
       mbar_init(&d_free[i], 128);
@@ -687,79 +693,82 @@ __global__ void __launch_bounds__(192, 1) k_mix_tc(MixArgs a) {
   const int ksteps = VP / 16;
 
   if (warp == 0) {
-    {
-      uint32_t stage = 0, phase = 0;
-      for (int64_t n = blockIdx.x; n < a.n; n += gridDim.x) {
-        const uint8_t* src = a.scores_img + (size_t)(n % a.n_cond) * H * stage_bytes;
-        for (int h = 0; h < H; h++) {
-          mbar_wait(&empty[stage], phase ^ 1);
-          if (elect_one()) {
-            mbar_arrive_expect_tx(&full[stage], kSplit == 3 ? stage_bytes : mat_bytes);
-            bulk_g2s(ring + stage * stage_stride, src + (size_t)h * stage_bytes, kSplit == 3 ? stage_bytes : mat_bytes, &full[stage]);
-          }
-          __syncwarp();
-          if (++stage == kMixStages) stage = 0, phase ^= 1;
+    uint32_t stage = 0, phase = 0;
+    for (int64_t n = blockIdx.x; n < a.n; n += gridDim.x) {
+      const uint8_t* src = a.scores_img + (size_t)(n % a.n_cond) * H * stage_bytes;
+      for (int h = 0; h < H; h++) {
+        mbar_wait(&empty[stage], phase ^ 1);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&full[stage], kSplit == 3 ? stage_bytes : mat_bytes);
+          bulk_g2s(ring + stage * stage_stride, src + (size_t)h * stage_bytes, kSplit == 3 ? stage_bytes : mat_bytes, &full[stage]);
         }
+        __syncwarp();
+        if (++stage == (uint32_t)n_stages) stage = 0, phase ^= 1;
       }
     }
   } else if (warp == 1) {
-    {
-      uint32_t stage = 0, phase = 0;
-      uint32_t ph_hs[2] = {0, 0}, ph_dfree[2] = {0, 0};
-      const uint32_t idesc = make_idesc_bf16(128, VP, 0, 0);
-      const uint32_t lbo = 128, sbo = (uint32_t)(VP >> 3) * 128;
-      int64_t it = 0, hcount = 0;
-      for (int64_t n = blockIdx.x; n < a.n; n += gridDim.x, it++) {
-        const int sb = it & 1;
-        mbar_wait(&hs_full[sb], ph_hs[sb]);
-        ph_hs[sb] ^= 1;
-        tc_fence_after();
-        const uint32_t hs_hi = tmem + MX_HS + sb * 128, hs_lo = hs_hi + 64;
-        for (int h = 0; h < H; h++, hcount++) {
-          const int db = hcount & 1;
-          if (hcount >= 2) {
-            mbar_wait(&d_free[db], ph_dfree[db]);
-            ph_dfree[db] ^= 1;
-          }
-          mbar_wait(&full[stage], phase);
-          tc_fence_after();
-          if (elect_one()) {
-            const uint32_t s_hi = smem_u32(ring + stage * stage_stride), s_lo = s_hi + mat_bytes;
-            const uint32_t d = tmem + MX_D + db * 128;
-            for (int k = 0; k < ksteps; k++)
-              mma_ts(d, hs_hi + k * 8, make_smem_desc(s_hi + k * 256, lbo, sbo, LAYOUT_NONE), idesc, k > 0);
-            if (kSplit == 3) {
-              for (int k = 0; k < ksteps; k++)
-                mma_ts(d, hs_lo + k * 8, make_smem_desc(s_hi + k * 256, lbo, sbo, LAYOUT_NONE), idesc, 1);
-              for (int k = 0; k < ksteps; k++)
-                mma_ts(d, hs_hi + k * 8, make_smem_desc(s_lo + k * 256, lbo, sbo, LAYOUT_NONE), idesc, 1);
-            }
-            mma_commit(&empty[stage]);
-            mma_commit(&d_full[db]);
-            if (h == H - 1) mma_commit(&hs_free[sb]);
-          }
-          __syncwarp();
-          if (++stage == kMixStages) stage = 0, phase ^= 1;
+    uint32_t stage = 0, phase = 0;
+    uint32_t ph_hs[2] = {0, 0}, ph_dfree[2] = {0, 0};
+    const uint32_t idesc = make_idesc_bf16(128, VP, 0, 0);
+    const uint32_t lbo = 128, sbo = (uint32_t)(VP >> 3) * 128;
+    int64_t it = 0, hcount = 0;
+    for (int64_t n = blockIdx.x; n < a.n; n += gridDim.x, it++) {
+      const int sb = it & 1;
+      mbar_wait(&hs_full[sb], ph_hs[sb]);
+      ph_hs[sb] ^= 1;
+      tc_fence_after();
+      const uint32_t hs_hi = tmem + MX_HS + sb * 128, hs_lo = hs_hi + 64;
+      for (int h = 0; h < H; h++, hcount++) {
+        const int db = hcount & 1;
+        if (hcount >= 2) {
+          mbar_wait(&d_free[db], ph_dfree[db]);
+          ph_dfree[db] ^= 1;
         }
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t s_hi = smem_u32(ring + stage * stage_stride), s_lo = s_hi + mat_bytes;
+          const uint32_t d = tmem + MX_D + db * 128;
+          for (int k = 0; k < ksteps; k++)
+            mma_ts(d, hs_hi + k * 8, make_smem_desc(s_hi + k * 256, lbo, sbo, LAYOUT_NONE), idesc, k > 0);
+          if (kSplit == 3) {
+            for (int k = 0; k < ksteps; k++)
+              mma_ts(d, hs_lo + k * 8, make_smem_desc(s_hi + k * 256, lbo, sbo, LAYOUT_NONE), idesc, 1);
+            for (int k = 0; k < ksteps; k++)
+              mma_ts(d, hs_hi + k * 8, make_smem_desc(s_lo + k * 256, lbo, sbo, LAYOUT_NONE), idesc, 1);
+          }
+          mma_commit(&empty[stage]);
+          mma_commit(&d_full[db]);
+          if (h == H - 1) mma_commit(&hs_free[sb]);
+        }
+        __syncwarp();
+        if (++stage == (uint32_t)n_stages) stage = 0, phase ^= 1;
       }
     }
   } else {
     const int q = warp & 3;
-    const int f = q * 32 + lane;  // feature = TMEM lane
+    const int g = (warp - 2) >> 2;  // epilogue group
+    const int f = q * 32 + lane;    // feature = TMEM lane
+    const int et = (tid - 64) & 127;  // index inside the group
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     const float* x = a.x[net];
     uint8_t* img = a.img[net];
     const size_t tile_bytes = (size_t)H * 2 * 2 * 16384;  // H*2 K blocks x (hi + lo) x 16 KB
-    uint32_t ph_hsfree[2] = {0, 0}, ph_dfull[2] = {0, 0};
+    uint8_t* staging = staging0 + (size_t)g * VP * 512;
+    uint8_t* st_hi = staging + f * 2;
+    uint8_t* st_lo = staging + (size_t)VP * 256 + f * 2;
+    uint32_t ph_hsfree[2] = {0, 0}, ph_dfull = 0;
 
-    auto load_hs = [&](int64_t n, int64_t it) {
+    auto load_hs = [&](int64_t n, int64_t it) {  // column blocks of X^T are split between the groups
       const int sb = it & 1;
       if (it >= 2) {
         mbar_wait(&hs_free[sb], ph_hsfree[sb]);
         ph_hsfree[sb] ^= 1;
       }
       const float* xs = x + n * V * 128 + f;
-      for (int c0 = 0; c0 < VP / 2; c0 += 16) {  // 16 columns = 32 atoms per store
+      int blk = 0;
+      for (int c0 = 0; c0 < VP / 2; c0 += 16, blk++) {  // 16 columns = 32 atoms per store
+        if (n_groups == 2 && (blk & 1) != g) continue;
         uint32_t hi[16], lo[16];
 #pragma unroll
         for (int j = 0; j < 16; j++) {
@@ -780,34 +789,52 @@ __global__ void __launch_bounds__(192, 1) k_mix_tc(MixArgs a) {
     if ((int64_t)blockIdx.x < a.n) load_hs(blockIdx.x, 0);
     for (int64_t n = blockIdx.x; n < a.n; n += gridDim.x, it++) {
       if (n + gridDim.x < a.n) load_hs(n + gridDim.x, it + 1);  // next sample's X^T while this one's heads drain
+      const int64_t t0 = n * V;
       for (int h = 0; h < H; h++, hcount++) {
         const int db = hcount & 1;
-        mbar_wait(&d_full[db], ph_dfull[db]);
-        ph_dfull[db] ^= 1;
+        if (n_groups == 2 && db != g) continue;
+        if (n_groups == 2) {
+          mbar_wait(&d_full[db], ph_dfull);
+          ph_dfull ^= 1;
+        } else {
+          mbar_wait(&d_full[db], (uint32_t)((hcount >> 1) & 1));
+        }
         tc_fence_after();
-        const int kcol = h * 128 + f;
-        const int kb = kcol >> 6, kk = kcol & 63;
+        // (1) accumulator -> bf16 hi/lo rows in the staging buffer [token i][feature f]; rows >= V are scratch
         for (int c0 = 0; c0 < VP; c0 += 16) {
           uint32_t r[16];
           tmem_ld16(tmem + lane_base + MX_D + db * 128 + c0, r);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 16; j++) {
-            int i = c0 + j;
-            if (i < V) {
-              int64_t t = n * V + i;
-              int64_t tile = t >> 7;
-              uint32_t row = (uint32_t)(t & 127);
-              uint16_t hi, lo;
-              split1(__uint_as_float(r[j]), hi, lo);
-              uint8_t* dst = img + tile * tile_bytes + (size_t)kb * 32768 + row * 128u + ((((uint32_t)kk >> 3) ^ (row & 7u)) << 4) + (kk & 7) * 2;
-              *reinterpret_cast<uint16_t*>(dst) = hi;
-              if (kSplit == 3) *reinterpret_cast<uint16_t*>(dst + 16384) = lo;
+          for (int j = 0; j < 16; j += 2) {
+            uint32_t hi, lo;
+            split2(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), hi, lo);
+            const int i = c0 + j;
+            *reinterpret_cast<uint16_t*>(st_hi + i * 256) = (uint16_t)hi;
+            *reinterpret_cast<uint16_t*>(st_hi + i * 256 + 256) = (uint16_t)(hi >> 16);
+            if (kSplit == 3) {
+              *reinterpret_cast<uint16_t*>(st_lo + i * 256) = (uint16_t)lo;
+              *reinterpret_cast<uint16_t*>(st_lo + i * 256 + 256) = (uint16_t)(lo >> 16);
             }
           }
         }
         tc_fence_before();
         mbar_arrive(&d_free[db]);
+        group_bar_sync(g);
+        // (2) 16-byte chunks -> swizzled operand images in global memory
+        const int n_chunks = V * (kSplit == 3 ? 32 : 16);
+        for (int cid = et; cid < n_chunks; cid += 128) {
+          const int i = (kSplit == 3) ? (cid >> 5) : (cid >> 4);
+          const int hl = (kSplit == 3) ? ((cid >> 4) & 1) : 0;
+          const int c = cid & 15;
+          const uint4 v = *reinterpret_cast<const uint4*>(staging + (size_t)hl * VP * 256 + i * 256 + c * 16);
+          const int64_t t = t0 + i;
+          const uint32_t row = (uint32_t)(t & 127);
+          uint8_t* dst = img + (t >> 7) * tile_bytes + (size_t)(h * 2 + (c >> 3)) * 32768 + hl * 16384 + row * 128u +
+                         ((((uint32_t)c & 7u) ^ (row & 7u)) << 4);
+          *reinterpret_cast<uint4*>(dst) = v;
+        }
+        group_bar_sync(g);
       }
     }
   }
@@ -951,7 +978,11 @@ __global__ void __launch_bounds__(192, 1) k_proj_tc(ProjArgs a) {
 // Weights stay resident in shared memory for the whole (persistent) CTA; the 256-wide hidden activation
 // goes TMEM -> registers -> TMEM (A operand of the second GEMM).  TMEM: D1 [0,256) (D2 reuses [0,128)), H hi
 // [256,384), H lo [384,512).
-__device__ __forceinline__ float silu_f(float v) { return v / (1.f + expf(-v)); }
+// SiLU with the hardware exp2/rcp approximations (relative error ~1e-7, far inside the 1e-4 parity budget)
+__device__ __forceinline__ float silu_f(float v) { return __fdividef(v, 1.f + __expf(-v)); }
+__device__ __forceinline__ void epi_bar_sync256() { asm volatile("bar.sync 2, 256;" ::: "memory"); }
+
+constexpr int kMlpThreads = 320;  // warp 0 loader, warp 1 MMA, warps 2-9 epilogue (two groups of four)
 
 struct InMlpArgs {
   const uint8_t* w1[2];   // [256 x 64] hi 32K | lo 32K
@@ -974,7 +1005,7 @@ struct InMlpSmem {
 };
 
 template <int kSplit>
-__global__ void __launch_bounds__(192, 1) k_in_mlp_tc(InMlpArgs a) {
+__global__ void __launch_bounds__(kMlpThreads, 1) k_in_mlp_tc(InMlpArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int net = blockIdx.y;
@@ -982,21 +1013,21 @@ __global__ void __launch_bounds__(192, 1) k_in_mlp_tc(InMlpArgs a) {
   const int64_t n_tiles = (a.M + 127) / 128;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + InMlpSmem::BARS);
   uint64_t* w_full = bars;       // weights resident
-  uint64_t* a_full = bars + 1;   // feature operand written (128)
+  uint64_t* a_full = bars + 1;   // feature operand written (256)
   uint64_t* d1_full = bars + 2;  // GEMM1 done
-  uint64_t* h_full = bars + 3;   // hidden in TMEM (128)
+  uint64_t* h_full = bars + 3;   // hidden in TMEM (256)
   uint64_t* d2_full = bars + 4;  // GEMM2 done
-  uint64_t* d_free = bars + 5;   // D2 drained (128)
+  uint64_t* d_free = bars + 5;   // D2 drained (256)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
   float* b1s = reinterpret_cast<float*>(smem + InMlpSmem::B1);
   float* b2s = reinterpret_cast<float*>(smem + InMlpSmem::B2);
   if (tid == 0) {
     mbar_init(w_full, 1);
-    mbar_init(a_full, 128);
+    mbar_init(a_full, 256);
     mbar_init(d1_full, 1);
-    mbar_init(h_full, 128);
+    mbar_init(h_full, 256);
     mbar_init(d2_full, 1);
-    mbar_init(d_free, 128);
+    mbar_init(d_free, 256);
     mbar_fence_init();
   }
   if (warp == 1) tmem_alloc<512>(tmem_slot);
@@ -1013,67 +1044,63 @@ __global__ void __launch_bounds__(192, 1) k_in_mlp_tc(InMlpArgs a) {
       const uint32_t w1b = kSplit == 3 ? 65536 : 32768;
       mbar_arrive_expect_tx(w_full, w1b + (kSplit == 3 ? 131072 : 4 * 16384));
       bulk_g2s(smem + InMlpSmem::W1, a.w1[net], w1b, w_full);
-      if (kSplit == 3) {
-        for (int i = 0; i < 4; i++) bulk_g2s(smem + InMlpSmem::W2 + i * 32768, a.w2[net] + i * 32768, 32768, w_full);
-      } else {
-        for (int i = 0; i < 4; i++) bulk_g2s(smem + InMlpSmem::W2 + i * 32768, a.w2[net] + i * 32768, 16384, w_full);
-      }
+      for (int i = 0; i < 4; i++) bulk_g2s(smem + InMlpSmem::W2 + i * 32768, a.w2[net] + i * 32768, kSplit == 3 ? 32768 : 16384, w_full);
     }
+    __syncwarp();
   } else if (warp == 1) {
-    {
-      mbar_wait(w_full, 0);
-      const uint32_t idesc1 = make_idesc_bf16(128, 256, 0, 0), idesc2 = make_idesc_bf16(128, 128, 0, 0);
-      const uint32_t ahi = smem_u32(smem + InMlpSmem::A_HI), alo = smem_u32(smem + InMlpSmem::A_LO);
-      const uint32_t w1hi = smem_u32(smem + InMlpSmem::W1), w1lo = w1hi + 32768, w2 = smem_u32(smem + InMlpSmem::W2);
-      uint32_t ph = 0;
-      int64_t it = 0;
-      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, it++) {
-        mbar_wait(a_full, ph);
-        if (it > 0) mbar_wait(d_free, ph ^ 1);  // previous tile's D2 (aliases D1) has been read
-        tc_fence_after();
-        if (elect_one()) {
+    mbar_wait(w_full, 0);
+    const uint32_t idesc1 = make_idesc_bf16(128, 256, 0, 0), idesc2 = make_idesc_bf16(128, 128, 0, 0);
+    const uint32_t ahi = smem_u32(smem + InMlpSmem::A_HI), alo = smem_u32(smem + InMlpSmem::A_LO);
+    const uint32_t w1hi = smem_u32(smem + InMlpSmem::W1), w1lo = w1hi + 32768, w2 = smem_u32(smem + InMlpSmem::W2);
+    uint32_t ph = 0;
+    int64_t it = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, it++) {
+      mbar_wait(a_full, ph);
+      if (it > 0) mbar_wait(d_free, ph ^ 1);  // previous tile's D2 (aliases D1) has been read
+      tc_fence_after();
+      if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 4; k++) mma_ss(tmem + T_D, desc_kmajor_sw128(ahi + k * 32), desc_kmajor_sw128(w1hi + k * 32), idesc1, k > 0);
-          if (kSplit == 3) {
+        for (int k = 0; k < 4; k++) mma_ss(tmem + T_D, desc_kmajor_sw128(ahi + k * 32), desc_kmajor_sw128(w1hi + k * 32), idesc1, k > 0);
+        if (kSplit == 3) {
 #pragma unroll
-            for (int k = 0; k < 4; k++) mma_ss(tmem + T_D, desc_kmajor_sw128(alo + k * 32), desc_kmajor_sw128(w1hi + k * 32), idesc1, 1);
+          for (int k = 0; k < 4; k++) mma_ss(tmem + T_D, desc_kmajor_sw128(alo + k * 32), desc_kmajor_sw128(w1hi + k * 32), idesc1, 1);
 #pragma unroll
-            for (int k = 0; k < 4; k++) mma_ss(tmem + T_D, desc_kmajor_sw128(ahi + k * 32), desc_kmajor_sw128(w1lo + k * 32), idesc1, 1);
-          }
-          mma_commit(d1_full);
+          for (int k = 0; k < 4; k++) mma_ss(tmem + T_D, desc_kmajor_sw128(ahi + k * 32), desc_kmajor_sw128(w1lo + k * 32), idesc1, 1);
         }
-        __syncwarp();
-        mbar_wait(h_full, ph);
-        tc_fence_after();
-        if (elect_one()) {
+        mma_commit(d1_full);
+      }
+      __syncwarp();
+      mbar_wait(h_full, ph);
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < 16; k++)
+          mma_ts(tmem + T_D, tmem + T_HHI + k * 8, desc_kmajor_sw128(w2 + (k >> 2) * 32768 + (k & 3) * 32), idesc2, k > 0);
+        if (kSplit == 3) {
 #pragma unroll
           for (int k = 0; k < 16; k++)
-            mma_ts(tmem + T_D, tmem + T_HHI + k * 8, desc_kmajor_sw128(w2 + (k >> 2) * 32768 + (k & 3) * 32), idesc2, k > 0);
-          if (kSplit == 3) {
+            mma_ts(tmem + T_D, tmem + T_HLO + k * 8, desc_kmajor_sw128(w2 + (k >> 2) * 32768 + (k & 3) * 32), idesc2, 1);
 #pragma unroll
-            for (int k = 0; k < 16; k++)
-              mma_ts(tmem + T_D, tmem + T_HLO + k * 8, desc_kmajor_sw128(w2 + (k >> 2) * 32768 + (k & 3) * 32), idesc2, 1);
-#pragma unroll
-            for (int k = 0; k < 16; k++)
-              mma_ts(tmem + T_D, tmem + T_HHI + k * 8, desc_kmajor_sw128(w2 + (k >> 2) * 32768 + 16384 + (k & 3) * 32), idesc2, 1);
-          }
-          mma_commit(d2_full);
+          for (int k = 0; k < 16; k++)
+            mma_ts(tmem + T_D, tmem + T_HHI + k * 8, desc_kmajor_sw128(w2 + (k >> 2) * 32768 + 16384 + (k & 3) * 32), idesc2, 1);
         }
-        __syncwarp();
-        ph ^= 1;
+        mma_commit(d2_full);
       }
+      __syncwarp();
+      ph ^= 1;
     }
   } else {
     const int q = warp & 3;
+    const int hf = (warp - 2) >> 2;  // epilogue group: half of the features / hidden units / outputs
     const int row = q * 32 + lane;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     const int E = a.E;
     uint32_t ph = 0;
-    auto gather = [&](int64_t tile) {
+    auto gather = [&](int64_t tile) {  // features 32*hf .. 32*hf+31 of token `row`
       const int64_t m = tile * 128 + row;
-      float f[64];
+      float f[32];
 #pragma unroll
-      for (int j = 0; j < 64; j++) f[j] = 0.f;
+      for (int j = 0; j < 32; j++) f[j] = 0.f;
       if (m < a.M) {
         const int64_t smp = m / a.V;
         const int v = (int)(m % a.V);
@@ -1081,20 +1108,38 @@ __global__ void __launch_bounds__(192, 1) k_in_mlp_tc(InMlpArgs a) {
         int64_t t = a.atom_types[mc];
         t = t < 0 ? 0 : (t >= a.n_types ? a.n_types - 1 : t);
         const float* er = a.embed + t * E;
+        if (E == 32) {
+          if (hf == 0) {
 #pragma unroll
-        for (int j = 0; j < 64; j++) {
-          if (j < E) f[j] = __ldg(er + j);
-          else if (j < E + 3) f[j] = __ldg(a.xc + mc * 3 + (j - E));
-          else if (j < E + 6) f[j] = __ldg(a.xv + mc * 3 + (j - E - 3));
-          else if (j < E + 9) f[j] = __ldg(a.z_other + m * 3 + (j - E - 6));
+            for (int j = 0; j < 8; j++) {
+              float4 e4 = __ldg(reinterpret_cast<const float4*>(er) + j);
+              f[4 * j] = e4.x, f[4 * j + 1] = e4.y, f[4 * j + 2] = e4.z, f[4 * j + 3] = e4.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+              f[j] = __ldg(a.xc + mc * 3 + j);
+              f[3 + j] = __ldg(a.xv + mc * 3 + j);
+              f[6 + j] = __ldg(a.z_other + m * 3 + j);
+            }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; j++) {
+            const int e = hf * 32 + j;
+            if (e < E) f[j] = __ldg(er + e);
+            else if (e < E + 3) f[j] = __ldg(a.xc + mc * 3 + (e - E));
+            else if (e < E + 6) f[j] = __ldg(a.xv + mc * 3 + (e - E - 3));
+            else if (e < E + 9) f[j] = __ldg(a.z_other + m * 3 + (e - E - 6));
+          }
         }
       }
 #pragma unroll
-      for (int c = 0; c < 8; c++) {
+      for (int c = 0; c < 4; c++) {
         uint32_t h[4], l[4];
 #pragma unroll
         for (int j = 0; j < 4; j++) split2(f[c * 8 + 2 * j], f[c * 8 + 2 * j + 1], h[j], l[j]);
-        uint32_t off = row * 128u + (((uint32_t)c ^ (row & 7u)) << 4);
+        uint32_t off = row * 128u + (((uint32_t)(hf * 4 + c) ^ (row & 7u)) << 4);
         *reinterpret_cast<uint4*>(smem + InMlpSmem::A_HI + off) = make_uint4(h[0], h[1], h[2], h[3]);
         *reinterpret_cast<uint4*>(smem + InMlpSmem::A_LO + off) = make_uint4(l[0], l[1], l[2], l[3]);
       }
@@ -1103,47 +1148,48 @@ __global__ void __launch_bounds__(192, 1) k_in_mlp_tc(InMlpArgs a) {
     };
     if ((int64_t)blockIdx.x < n_tiles) gather(blockIdx.x);
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      // ---- hidden: D1 + b1 -> SiLU -> hi/lo -> TMEM
+      // ---- hidden units hf*128 .. +127: D1 + b1 -> SiLU -> hi/lo -> TMEM
       mbar_wait(d1_full, ph);
       tc_fence_after();
 #pragma unroll 1
-      for (int g = 0; g < 8; g++) {
+      for (int g = 0; g < 4; g++) {
         uint32_t r[32];
-        tmem_ld32(tmem + lane_base + T_D + g * 32, r);
+        tmem_ld32(tmem + lane_base + T_D + hf * 128 + g * 32, r);
         tmem_ld_wait();
         uint32_t hi[16], lo[16];
 #pragma unroll
         for (int j = 0; j < 32; j += 2) {
-          float v0 = silu_f(__uint_as_float(r[j]) + b1s[g * 32 + j]);
-          float v1 = silu_f(__uint_as_float(r[j + 1]) + b1s[g * 32 + j + 1]);
+          float v0 = silu_f(__uint_as_float(r[j]) + b1s[hf * 128 + g * 32 + j]);
+          float v1 = silu_f(__uint_as_float(r[j + 1]) + b1s[hf * 128 + g * 32 + j + 1]);
           split2(v0, v1, hi[j >> 1], lo[j >> 1]);
         }
-        tmem_st16(tmem + lane_base + T_HHI + g * 16, hi);
-        if (kSplit == 3) tmem_st16(tmem + lane_base + T_HLO + g * 16, lo);
+        tmem_st16(tmem + lane_base + T_HHI + hf * 64 + g * 16, hi);
+        if (kSplit == 3) tmem_st16(tmem + lane_base + T_HLO + hf * 64 + g * 16, lo);
       }
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(h_full);
       // the feature operand of the next tile can be written now (GEMM1 of this tile has completed)
       if (tile + gridDim.x < n_tiles) gather(tile + gridDim.x);
-      // ---- output: D2 + b2 -> global
+      // ---- outputs hf*64 .. +63: D2 + b2 -> global
       mbar_wait(d2_full, ph);
       tc_fence_after();
       const int64_t m = tile * 128 + row;
-      float* orow = a.out[net] + m * 128;
+      float* orow = a.out[net] + m * 128 + hf * 64;
 #pragma unroll 1
-      for (int g = 0; g < 4; g++) {
+      for (int g = 0; g < 2; g++) {
         uint32_t r[32];
-        tmem_ld32(tmem + lane_base + T_D + g * 32, r);
+        tmem_ld32(tmem + lane_base + T_D + hf * 64 + g * 32, r);
         tmem_ld_wait();
         if (m < a.M) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
+            const float* bb = b2s + hf * 64 + g * 32 + j;
             float4 o;
-            o.x = __uint_as_float(r[j]) + b2s[g * 32 + j];
-            o.y = __uint_as_float(r[j + 1]) + b2s[g * 32 + j + 1];
-            o.z = __uint_as_float(r[j + 2]) + b2s[g * 32 + j + 2];
-            o.w = __uint_as_float(r[j + 3]) + b2s[g * 32 + j + 3];
+            o.x = __uint_as_float(r[j]) + bb[0];
+            o.y = __uint_as_float(r[j + 1]) + bb[1];
+            o.z = __uint_as_float(r[j + 2]) + bb[2];
+            o.w = __uint_as_float(r[j + 3]) + bb[3];
             *reinterpret_cast<float4*>(orow + g * 32 + j) = o;
           }
         }
@@ -1171,12 +1217,13 @@ struct OutMlpArgs {
   int64_t M;
 };
 struct OutMlpSmem {
-  static constexpr int X_HI = 0, X_LO = 32768, W3 = 65536, B3 = W3 + 131072, W4 = B3 + 1024, BARS = W4 + 3 * 1024 + 16;
+  static constexpr int X_HI = 0, X_LO = 32768, W3 = 65536, B3 = W3 + 131072, W4 = B3 + 1024, RED = W4 + 3 * 1024 + 16;
+  static constexpr int BARS = RED + 2 * 128 * 4 * 4;
   static constexpr int TOTAL = BARS + 128;
 };
 
 template <int kSplit>
-__global__ void __launch_bounds__(192, 1) k_out_mlp_tc(OutMlpArgs a) {
+__global__ void __launch_bounds__(kMlpThreads, 1) k_out_mlp_tc(OutMlpArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int net = blockIdx.y;
@@ -1184,16 +1231,17 @@ __global__ void __launch_bounds__(192, 1) k_out_mlp_tc(OutMlpArgs a) {
   const int64_t n_tiles = (a.M + 127) / 128;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OutMlpSmem::BARS);
   uint64_t* w_full = bars;
-  uint64_t* x_full = bars + 1;   // 128
+  uint64_t* x_full = bars + 1;   // 256
   uint64_t* d_full = bars + 2;   // [2]
-  uint64_t* d_free = bars + 4;   // [2] 128
+  uint64_t* d_free = bars + 4;   // [2] 256
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
   float* b3s = reinterpret_cast<float*>(smem + OutMlpSmem::B3);
   float* w4s = reinterpret_cast<float*>(smem + OutMlpSmem::W4);  // [3][256] then b4[3]
+  float* red = reinterpret_cast<float*>(smem + OutMlpSmem::RED);  // [2][128][4] partial sums of group 1
   if (tid == 0) {
     mbar_init(w_full, 1);
-    mbar_init(x_full, 128);
-    for (int i = 0; i < 2; i++) mbar_init(&d_full[i], 1), mbar_init(&d_free[i], 128);
+    mbar_init(x_full, 256);
+    for (int i = 0; i < 2; i++) mbar_init(&d_full[i], 1), mbar_init(&d_free[i], 256);
     mbar_fence_init();
   }
   if (warp == 1) tmem_alloc<512>(tmem_slot);
@@ -1207,76 +1255,71 @@ __global__ void __launch_bounds__(192, 1) k_out_mlp_tc(OutMlpArgs a) {
 
   if (warp == 0) {
     if (elect_one()) {
-      if (kSplit == 3) {
-        mbar_arrive_expect_tx(w_full, 131072);
-        bulk_g2s(smem + OutMlpSmem::W3, a.w3[net], 65536, w_full);
-        bulk_g2s(smem + OutMlpSmem::W3 + 65536, a.w3[net] + 65536, 65536, w_full);
-      } else {
-        mbar_arrive_expect_tx(w_full, 65536);
-        bulk_g2s(smem + OutMlpSmem::W3, a.w3[net], 32768, w_full);
-        bulk_g2s(smem + OutMlpSmem::W3 + 65536, a.w3[net] + 65536, 32768, w_full);
-      }
+      const uint32_t part = kSplit == 3 ? 65536 : 32768;
+      mbar_arrive_expect_tx(w_full, 2 * part);
+      bulk_g2s(smem + OutMlpSmem::W3, a.w3[net], part, w_full);
+      bulk_g2s(smem + OutMlpSmem::W3 + 65536, a.w3[net] + 65536, part, w_full);
     }
+    __syncwarp();
   } else if (warp == 1) {
-    {
-      mbar_wait(w_full, 0);
-      const uint32_t idesc = make_idesc_bf16(128, 256, 0, 0);
-      const uint32_t xhi = smem_u32(smem + OutMlpSmem::X_HI), xlo = smem_u32(smem + OutMlpSmem::X_LO), w3 = smem_u32(smem + OutMlpSmem::W3);
-      uint32_t ph_x = 0, ph_free[2] = {0, 0};
-      int64_t it = 0;
-      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, it++) {
-        const int tb = it & 1;
-        mbar_wait(x_full, ph_x);
-        ph_x ^= 1;
-        if (it >= 2) {
-          mbar_wait(&d_free[tb], ph_free[tb]);
-          ph_free[tb] ^= 1;
+    mbar_wait(w_full, 0);
+    const uint32_t idesc = make_idesc_bf16(128, 256, 0, 0);
+    const uint32_t xhi = smem_u32(smem + OutMlpSmem::X_HI), xlo = smem_u32(smem + OutMlpSmem::X_LO), w3 = smem_u32(smem + OutMlpSmem::W3);
+    uint32_t ph_x = 0, ph_free[2] = {0, 0};
+    int64_t it = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, it++) {
+      const int tb = it & 1;
+      mbar_wait(x_full, ph_x);
+      ph_x ^= 1;
+      if (it >= 2) {
+        mbar_wait(&d_free[tb], ph_free[tb]);
+        ph_free[tb] ^= 1;
+      }
+      tc_fence_after();
+      const uint32_t d = tmem + tb * 256;
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+          uint32_t ao = (k >> 2) * 16384 + (k & 3) * 32, wo = (k >> 2) * 65536 + (k & 3) * 32;
+          mma_ss(d, desc_kmajor_sw128(xhi + ao), desc_kmajor_sw128(w3 + wo), idesc, k > 0);
         }
-        tc_fence_after();
-        const uint32_t d = tmem + tb * 256;
-        if (elect_one()) {
+        if (kSplit == 3) {
 #pragma unroll
           for (int k = 0; k < 8; k++) {
             uint32_t ao = (k >> 2) * 16384 + (k & 3) * 32, wo = (k >> 2) * 65536 + (k & 3) * 32;
-            mma_ss(d, desc_kmajor_sw128(xhi + ao), desc_kmajor_sw128(w3 + wo), idesc, k > 0);
+            mma_ss(d, desc_kmajor_sw128(xlo + ao), desc_kmajor_sw128(w3 + wo), idesc, 1);
           }
-          if (kSplit == 3) {
 #pragma unroll
-            for (int k = 0; k < 8; k++) {
-              uint32_t ao = (k >> 2) * 16384 + (k & 3) * 32, wo = (k >> 2) * 65536 + (k & 3) * 32;
-              mma_ss(d, desc_kmajor_sw128(xlo + ao), desc_kmajor_sw128(w3 + wo), idesc, 1);
-            }
-#pragma unroll
-            for (int k = 0; k < 8; k++) {
-              uint32_t ao = (k >> 2) * 16384 + (k & 3) * 32, wo = (k >> 2) * 65536 + 32768 + (k & 3) * 32;
-              mma_ss(d, desc_kmajor_sw128(xhi + ao), desc_kmajor_sw128(w3 + wo), idesc, 1);
-            }
+          for (int k = 0; k < 8; k++) {
+            uint32_t ao = (k >> 2) * 16384 + (k & 3) * 32, wo = (k >> 2) * 65536 + 32768 + (k & 3) * 32;
+            mma_ss(d, desc_kmajor_sw128(xhi + ao), desc_kmajor_sw128(w3 + wo), idesc, 1);
           }
-          mma_commit(&d_full[tb]);
         }
-        __syncwarp();
+        mma_commit(&d_full[tb]);
       }
+      __syncwarp();
     }
   } else {
     const int q = warp & 3;
+    const int hf = (warp - 2) >> 2;
     const int row = q * 32 + lane;
-    const int ew = warp - 2;
+    const int ew = warp - 2;  // 0..7: 16 rows of the tile each
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     uint32_t ph_full[2] = {0, 0};
     const float* x = a.x[net];
     auto load_x = [&](int64_t tile) {
       const int64_t row0 = tile * 128;
 #pragma unroll 1
-      for (int it = 0; it < 32; it += 8) {
+      for (int it = 0; it < 16; it += 8) {
         float4 v[8];
 #pragma unroll
         for (int u = 0; u < 8; u++) {
-          int r = ew * 32 + it + u;
+          int r = ew * 16 + it + u;
           v[u] = (row0 + r < a.M) ? __ldg(reinterpret_cast<const float4*>(x + (row0 + r) * 128) + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
 #pragma unroll
         for (int u = 0; u < 8; u++) {
-          int r = ew * 32 + it + u;
+          int r = ew * 16 + it + u;
           uint32_t h0, l0, h1, l1;
           split2(v[u].x, v[u].y, h0, l0);
           split2(v[u].z, v[u].w, h1, l1);
@@ -1296,15 +1339,15 @@ __global__ void __launch_bounds__(192, 1) k_out_mlp_tc(OutMlpArgs a) {
       ph_full[tb] ^= 1;
       tc_fence_after();
       if (tile + gridDim.x < n_tiles) load_x(tile + gridDim.x);
-      float s0 = w4s[768], s1 = w4s[769], s2 = w4s[770];
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f;
 #pragma unroll 1
-      for (int g = 0; g < 8; g++) {
+      for (int g = 0; g < 4; g++) {
         uint32_t r[32];
-        tmem_ld32(tmem + lane_base + tb * 256 + g * 32, r);
+        tmem_ld32(tmem + lane_base + tb * 256 + hf * 128 + g * 32, r);
         tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 32; j++) {
-          int col = g * 32 + j;
+          int col = hf * 128 + g * 32 + j;
           float v = silu_f(__uint_as_float(r[j]) + b3s[col]);
           s0 = fmaf(v, w4s[col], s0);
           s1 = fmaf(v, w4s[256 + col], s1);
@@ -1313,10 +1356,17 @@ __global__ void __launch_bounds__(192, 1) k_out_mlp_tc(OutMlpArgs a) {
       }
       tc_fence_before();
       mbar_arrive(&d_free[tb]);
-      const int64_t m = tile * 128 + row;
-      if (m < a.M) {
-        float* o = a.out[net] + m * 3;
-        o[0] = s0, o[1] = s1, o[2] = s2;
+      float* rr = red + (tb * 128 + row) * 4;
+      if (hf == 1) rr[0] = s0, rr[1] = s1, rr[2] = s2;
+      epi_bar_sync256();
+      if (hf == 0) {
+        const int64_t m = tile * 128 + row;
+        if (m < a.M) {
+          float* o = a.out[net] + m * 3;
+          o[0] = (s0 + rr[0]) + w4s[768];
+          o[1] = (s1 + rr[1]) + w4s[769];
+          o[2] = (s2 + rr[2]) + w4s[770];
+        }
       }
     }
   }
@@ -1360,11 +1410,14 @@ int tc_attention_layer(const tw_flow_config* c, const ParamView& pv, int k, int 
   static bool attr_done = false;
   const int VP = pad16(V), H = c->num_heads;
   const uint32_t stage_stride = (uint32_t)((2 * VP * VP * 2 + 1023) & ~1023);
-  const int mix_smem = kMixStages * stage_stride + 256 + 1024;
+  const int mix_stages = VP > 96 ? 2 : 3;
+  const int mix_groups = VP > 96 ? 1 : 2;  // epilogue groups (a second staging buffer must fit next to the ring)
+  const int mix_smem = mix_stages * stage_stride + mix_groups * VP * 512 + 256 + 1024;
   const int proj_smem = kProjStages * kProjStageBytes + 1024 + 256 + 1024;
   if (!attr_done) {
     TW_CUDA(cudaFuncSetAttribute(k_mix_tc<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 65536 + 2048));
     TW_CUDA(cudaFuncSetAttribute(k_mix_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 65536 + 2048));
+    static_assert(2 * 65536 + 128 * 512 + 2048 <= 3 * 65536 + 2048, "mix smem budget");
     TW_CUDA(cudaFuncSetAttribute(k_proj_tc<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, proj_smem));
     TW_CUDA(cudaFuncSetAttribute(k_proj_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, proj_smem));
     attr_done = true;
@@ -1376,13 +1429,13 @@ int tc_attention_layer(const tw_flow_config* c, const ParamView& pv, int k, int 
     MixArgs a{};
     for (int s = 0; s < 2; s++) a.x[s] = x[s], a.img[s] = tc.mixed_img[s];
     a.scores_img = tc.scores_img;
-    a.n = n, a.n_cond = n_cond, a.V = V, a.VP = VP, a.H = H;
+    a.n = n, a.n_cond = n_cond, a.V = V, a.VP = VP, a.H = H, a.n_stages = mix_stages;
     int gx = (int)(n < 74 ? n : 74);
     dim3 grid(gx, 2);
     if (c->precision == TW_PRECISION_BF16X3)
-      k_mix_tc<3><<<grid, 192, mix_smem, st>>>(a);
+      k_mix_tc<3><<<grid, 64 + 128 * mix_groups, mix_smem, st>>>(a);
     else
-      k_mix_tc<1><<<grid, 192, mix_smem, st>>>(a);
+      k_mix_tc<1><<<grid, 64 + 128 * mix_groups, mix_smem, st>>>(a);
     TW_LAUNCH_CHECK();
   }
   {
@@ -1458,9 +1511,9 @@ int tc_in_mlp(const tw_flow_config* c, const ParamView& pv, int k, const TcScrat
   dim3 grid((unsigned)(n_tiles < 74 ? n_tiles : 74), 2);
   ProfScope prof(PROF_MLP, st);
   if (c->precision == TW_PRECISION_BF16X3)
-    k_in_mlp_tc<3><<<grid, 192, InMlpSmem::TOTAL + 1024, st>>>(a);
+    k_in_mlp_tc<3><<<grid, kMlpThreads, InMlpSmem::TOTAL + 1024, st>>>(a);
   else
-    k_in_mlp_tc<1><<<grid, 192, InMlpSmem::TOTAL + 1024, st>>>(a);
+    k_in_mlp_tc<1><<<grid, kMlpThreads, InMlpSmem::TOTAL + 1024, st>>>(a);
   TW_LAUNCH_CHECK();
   return TW_OK;
 }
@@ -1488,9 +1541,9 @@ int tc_out_mlp(const tw_flow_config* c, const ParamView& pv, int k, const TcScra
   dim3 grid((unsigned)(n_tiles < 74 ? n_tiles : 74), 2);
   ProfScope prof(PROF_MLP, st);
   if (c->precision == TW_PRECISION_BF16X3)
-    k_out_mlp_tc<3><<<grid, 192, OutMlpSmem::TOTAL + 1024, st>>>(a);
+    k_out_mlp_tc<3><<<grid, kMlpThreads, OutMlpSmem::TOTAL + 1024, st>>>(a);
   else
-    k_out_mlp_tc<1><<<grid, 192, OutMlpSmem::TOTAL + 1024, st>>>(a);
+    k_out_mlp_tc<1><<<grid, kMlpThreads, OutMlpSmem::TOTAL + 1024, st>>>(a);
   TW_LAUNCH_CHECK();
   return TW_OK;
 }

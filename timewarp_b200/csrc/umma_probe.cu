@@ -124,10 +124,9 @@ __global__ void __launch_bounds__(128, 1) k_umma_probe(ProbeArgs p) {
   if (warp == 0) tmem_dealloc<512>(tmem);
 }
 
-// Timing micro-benchmark: one thread issues `n_mma` M128 x N x K16 MMAs (SS or TS) with a tcgen05.commit
-// every `commit_every` MMAs (each commit waited for if `wait_each`), operands are zeros.
-// out[0] = cycles until everything was issued, out[1] = cycles until the last commit arrived.
-__global__ void __launch_bounds__(128, 1) k_umma_timing(int n_mma, int commit_every, int N, int ts, int wait_each, long long* out) {
+// Timing micro-benchmark: an elected lane issues `n_mma` back-to-back M128 x N x K16 MMAs (SS or TS, B operand
+// swizzled or not) into one accumulator, ONE commit at the end.  out[0] = cycles to issue, out[1] = cycles until done.
+__global__ void __launch_bounds__(128, 1) k_umma_timing(int n_mma, int N, int ts, int b_noswizzle, long long* out) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   __shared__ uint64_t bar;
@@ -144,35 +143,27 @@ __global__ void __launch_bounds__(128, 1) k_umma_timing(int n_mma, int commit_ev
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
-  if (tid == 0) {
+  if (warp == 1) {
     const uint32_t idesc = make_idesc_bf16(128, N, 0, 0);
     const uint32_t a0 = smem_u32(smem), b0 = smem_u32(smem + 32 * 1024);
-    uint32_t phase = 0;
-    int commits = 0, waited = 0;
-    long long t0 = clock64();
-    for (int i = 0; i < n_mma; i++) {
-      uint32_t koff = ((i & 7) >> 2) * 16384 + (i & 3) * 32;
-      if (ts) mma_ts(tmem, tmem + 256 + (i & 7) * 8, desc_kmajor_sw128(b0 + (i & 3) * 32), idesc, 1);
-      else mma_ss(tmem, desc_kmajor_sw128(a0 + koff), desc_kmajor_sw128(b0 + (i & 3) * 32), idesc, 1);
-      if ((i + 1) % commit_every == 0 || i == n_mma - 1) {
-        mma_commit(&bar);
-        commits++;
-        if (wait_each) {
-          mbar_wait(&bar, phase);
-          phase ^= 1;
-          waited++;
-        }
+    long long t0 = clock64(), t1 = 0;
+    if (elect_one()) {
+      for (int i = 0; i < n_mma; i++) {
+        uint64_t bd = b_noswizzle ? make_smem_desc(b0 + (i & 3) * 256, 128, 1024, LAYOUT_NONE)  // K = 64 wide tile: 32 KB for N = 256
+                                  : desc_kmajor_sw128(b0 + (i & 3) * 32);
+        if (ts) mma_ts(tmem, tmem + 256 + (i & 7) * 8, bd, idesc, 1);
+        else mma_ss(tmem, desc_kmajor_sw128(a0 + (i & 3) * 32), bd, idesc, 1);
       }
+      mma_commit(&bar);
+      t1 = clock64();
     }
-    long long t1 = clock64();
-    while (waited < commits) {
-      mbar_wait(&bar, phase);
-      phase ^= 1;
-      waited++;
-    }
+    __syncwarp();
+    mbar_wait(&bar, 0);
     long long t2 = clock64();
-    out[0] = t1 - t0;
-    out[1] = t2 - t0;
+    if (t1 != 0) {
+      out[0] = t1 - t0;
+      out[1] = t2 - t0;
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -183,15 +174,6 @@ __global__ void __launch_bounds__(128, 1) k_umma_timing(int n_mma, int commit_ev
 
 using namespace tw;
 
-extern "C" int tw_debug_umma_timing(int n_mma, int commit_every, int N, int ts, int wait_each, long long* out, void* stream) {
-  TW_CHECK_ARG(out && n_mma > 0 && commit_every > 0 && N >= 16 && N <= 256, "bad args");
-  const int smem = 97 * 1024 + 1024;
-  TW_CUDA(cudaFuncSetAttribute(k_umma_timing, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  k_umma_timing<<<1, 128, smem, (cudaStream_t)stream>>>(n_mma, commit_every, N, ts, wait_each, out);
-  TW_LAUNCH_CHECK();
-  return TW_OK;
-}
-
 extern "C" int tw_debug_umma_probe(const float* A, const float* B, float* out, int N, int K, int a_mode, int b_mode, int d_col,
                                    int a_col, int* status, void* stream) {
   TW_CHECK_ARG(A && B && out && status, "NULL pointer");
@@ -201,6 +183,15 @@ extern "C" int tw_debug_umma_probe(const float* A, const float* B, float* out, i
   TW_CUDA(cudaFuncSetAttribute(k_umma_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   ProbeArgs p{A, B, out, N, K, a_mode, b_mode, d_col, a_col, status};
   k_umma_probe<<<1, 128, smem, (cudaStream_t)stream>>>(p);
+  TW_LAUNCH_CHECK();
+  return TW_OK;
+}
+
+extern "C" int tw_debug_umma_timing(int n_mma, int N, int ts, int b_noswizzle, long long* out, void* stream) {
+  TW_CHECK_ARG(out && n_mma > 0 && N >= 16 && N <= 256 && N % 16 == 0, "bad args");
+  const int smem = 97 * 1024 + 1024;
+  TW_CUDA(cudaFuncSetAttribute(k_umma_timing, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  k_umma_timing<<<1, 128, smem, (cudaStream_t)stream>>>(n_mma, N, ts, b_noswizzle, out);
   TW_LAUNCH_CHECK();
   return TW_OK;
 }
