@@ -313,11 +313,11 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--chains", type=int, default=1024, help="chains per GPU (BASELINE configs[2]: 1024)")
-    ap.add_argument("--precision", default=os.environ.get("TW_PRECISION", "fp32"), choices=["fp32", "bf16x3", "bf16"])
+    ap.add_argument("--precision", default=os.environ.get("TW_PRECISION", "bf16x3"), choices=["fp32", "bf16x3", "bf16"])
     ap.add_argument("--cpu-sample", type=int, default=32, help="chains in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--seed", type=int, default=0)
