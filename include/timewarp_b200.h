@@ -136,6 +136,36 @@ int tw_flow_sample(const tw_flow_config* cfg, const void* const* params, const i
                    size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Training (NLL loss, losses.py:321-356 -> density_model_base.py:27-42): the `*_backward` twin of
+ * tw_flow_log_likelihood.  The reference differentiates log_likelihood with torch autograd; here
+ * the forward records a tape (every layer boundary, caller-owned memory) and the backward returns
+ * d(sum_b grad_log_prob[b] * log p_b)/d(parameter) for every trainable parameter.  Tensor-core
+ * precisions only (TW_ERR_UNSUPPORTED for TW_PRECISION_FP32 / non-flagship layer sizes).
+ *
+ * tw_flow_train_bytes: sizes of the tape and of the backward workspace (both 1024-byte aligned).
+ * tw_flow_log_likelihood_train: same result as tw_flow_log_likelihood, fills `tape`.
+ * tw_flow_log_likelihood_backward: `grads` is a table parallel to `params` (same order, same shapes,
+ *   fp32); gradients are ACCUMULATED into it (zero it first for a fresh gradient).  Entries of
+ *   lengthscales (buffers, kernel_attention.py:169-171) and of frozen prior log-scales may be NULL.
+ *   Gradients w.r.t. the coordinate inputs are not produced (the NLL loss does not need them). */
+int tw_flow_train_bytes(const tw_flow_config* cfg, int64_t B, int64_t V, size_t* tape_bytes, size_t* workspace_bytes);
+int tw_flow_log_likelihood_train(const tw_flow_config* cfg, const void* const* params, const int64_t* atom_types,
+                                 const float* x_coords, const float* x_velocs, const float* y_coords,
+                                 const float* y_velocs, const uint8_t* mask, int64_t B, int64_t V, int32_t flags,
+                                 float* out_log_prob, const void* packed_weights, void* tape, size_t tape_bytes,
+                                 void* stream);
+int tw_flow_log_likelihood_backward(const tw_flow_config* cfg, const void* const* params, void* const* grads,
+                                    const int64_t* atom_types, const float* x_velocs, const uint8_t* mask, int64_t B,
+                                    int64_t V, const float* grad_log_prob, const void* packed_weights, void* tape,
+                                    size_t tape_bytes, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Debug: one generic operand-image GEMM of the training path on fp32 row-major inputs.
+ * mode 0: C[ar,br] = A B^T; 1: C[ar,bc] = A B; 2: C[ar,128] = sum_h A[:,h*128:(h+1)*128] B[:,h*128:(h+1)*128]
+ * (B is [128, H*128]); 3: C[ac,bc] += A^T B (atomic accumulation, `splits` CTAs per output tile). */
+int tw_debug_gemm(int mode, int precision, const float* A, int a_rows, int a_cols, const float* B, int b_rows,
+                  int b_cols, float* C, int bn, int splits, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Potential energy.  Replaces OpenmmPotentialEnergyTorch.forward (utils/openmm/openmm_bridge.py:
  * 281-294 -> OpenMMBridge.evaluate :170-249 -> OpenMM 7.7 Context.getState) for the implicit-
  * solvent systems built by simulation/md.py:128-173: HarmonicBond + HarmonicAngle +

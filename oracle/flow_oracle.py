@@ -367,3 +367,15 @@ def state_dict_shapes_cache(cfg: OracleConfig):
 
 def to_dtype(sd: StateDict, dtype) -> StateDict:
     return {k: (v.to(dtype) if v.is_floating_point() else v) for k, v in sd.items()}
+
+
+def nll_loss_and_grads(sd: StateDict, cfg: OracleConfig, atom_types, x_coords, x_velocs, y_coords, y_velocs, masked_elements,
+                       distance_mode: str = "cdist"):
+    """Loss of density_model_base.py:27-42 and its torch-autograd gradient w.r.t. every floating-point
+    entry of the state dict that the reference registers as a Parameter (the `lengthscales` entries are
+    buffers, kernel_attention.py:169-171) -- what `loss.backward()` leaves in `.grad` in train.py."""
+    leaves = {k: v.detach().clone().requires_grad_(not k.endswith("lengthscales")) for k, v in sd.items()}
+    loss = nll_loss(leaves, cfg, atom_types, x_coords, x_velocs, y_coords, y_velocs, masked_elements, distance_mode)
+    names = [k for k, v in leaves.items() if v.requires_grad]
+    grads = torch.autograd.grad(loss, [leaves[k] for k in names], allow_unused=True)
+    return loss.detach(), {k: (g if g is not None else torch.zeros_like(leaves[k])) for k, g in zip(names, grads)}

@@ -155,6 +155,42 @@ def run_case(name, cfg, peptide, B, seed, lengths=None, sample_S=3, wseed=0, tra
     return sd
 
 
+GRAD_FULL_KEYS = [
+    "flow.atom_embedder.weight", "coords_prior_log_scale", "velocs_prior_log_scale",
+    "flow.chain.0.scale_transformer.in_mlp._layers.0.weight", "flow.chain.0.scale_transformer.in_mlp._layers.2.bias",
+    "flow.chain.3.shift_transformer.encoder_layers.1.self_attn.values_proj.weight",
+    "flow.chain.3.shift_transformer.encoder_layers.1.self_attn.attention._out_projection.weight",
+    "flow.chain.5.scale_transformer.encoder_layers.2.linear1.bias", "flow.chain.5.scale_transformer.encoder_layers.2.linear2.bias",
+    "flow.chain.5.scale_transformer.encoder_layers.0.norm1.weight", "flow.chain.5.scale_transformer.encoder_layers.0.norm2.bias",
+    "flow.chain.7.shift_transformer.out_mlp._layers.2.weight", "flow.chain.7.shift_transformer.out_mlp._layers.0.bias",
+    "flow.chain.6.shift_transformer.encoder_layers.0.linear2.weight",
+]
+
+
+def grad_case(name, cfg, peptide, B, seed, lengths=None, wseed=0):
+    """NLL loss (density_model_base.py:27-42) and its autograd gradients from the unmodified reference:
+    L2 norm of every parameter gradient + a few full tensors."""
+    model, sd = ref_model(cfg, wseed)
+    model.train()
+    at, x, xv, y, yv, mask = synth_batch(peptide, B, seed, lengths)
+    loss = model(atom_types=at, x_coords=x, x_velocs=xv, y_coords=y, y_velocs=yv, adj_list=EMPTY_ADJ, edge_batch_idx=EMPTY_EBI,
+                 masked_elements=mask)
+    loss.backward()
+    out = dict(atom_types=at.numpy(), x_coords=x.numpy(), x_velocs=xv.numpy(), y_coords=y.numpy(), y_velocs=yv.numpy(),
+               masked_elements=mask.numpy(), weight_seed=np.int64(wseed), loss=loss.detach().numpy())
+    names, norms = [], []
+    for k, p in model.named_parameters():
+        names.append(k)
+        norms.append(0.0 if p.grad is None else float(p.grad.double().norm()))
+    out["grad_names"] = np.array(names)
+    out["grad_norms"] = np.array(norms)
+    for k in GRAD_FULL_KEYS:
+        g = dict(model.named_parameters())[k].grad
+        out["grad::" + k] = (g[:8] if g.numel() > 20000 else g).numpy()  # large matrices: first 8 rows
+    np.savez_compressed(os.path.join(HERE, f"{name}.npz"), **out)
+    print(name, "loss", float(loss), "total grad norm", float(np.sqrt((np.array(norms) ** 2).sum())))
+
+
 TINY = OracleConfig(atom_embedding_dim=8, latent_mlp_hidden_dims=[24], num_coupling_layers=4, num_transformer_layers=2,
                     d_model=16, dim_feedforward=32, lengthscales=[0.3, 1.0])
 FULL = OracleConfig()
@@ -205,3 +241,5 @@ if __name__ == "__main__":
     run_case("full_ad22_ragged", FULL, ad, B=3, seed=1, lengths=[22, 17, 12], sample_S=2)
     run_case("full_2olx65", FULL, olx, B=2, seed=2, sample_S=2)
     chirality_case()
+    grad_case("grads_full_ad22", FULL, ad, B=4, seed=3)
+    grad_case("grads_full_ad22_ragged", FULL, ad, B=3, seed=4, lengths=[22, 17, 12])

@@ -159,7 +159,7 @@ static int pack_w2_blocks(const float* W2, int F, int D, uint8_t* dst, cudaStrea
 // Row epilogue shared by the token-major kernels: v[128] (+ bias) + residual row -> LayerNorm -> global
 __device__ __forceinline__ void ln_store_row(float (&v)[128], const float* __restrict__ bias, const float* __restrict__ resid_row,
                                              const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
-                                             float* __restrict__ out_row) {
+                                             float* __restrict__ out_row, float* __restrict__ pre_row = nullptr) {
   const float4* xr = reinterpret_cast<const float4*>(resid_row);
   float sum = 0.f;
 #pragma unroll
@@ -174,6 +174,7 @@ __device__ __forceinline__ void ln_store_row(float (&v)[128], const float* __res
     v[4 * j + 2] += xv.z;
     v[4 * j + 3] += xv.w;
     sum += (v[4 * j] + v[4 * j + 1]) + (v[4 * j + 2] + v[4 * j + 3]);
+    if (pre_row) reinterpret_cast<float4*>(pre_row)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
   }
   const float mean = sum * (1.f / 128.f);
   float sq = 0.f;
@@ -216,6 +217,7 @@ constexpr uint32_t TM_D1 = 0, TM_H = 256, TM_Y = 384;
 struct FfnArgs {
   const float* x[2];       // [M,128] layer input (post-LN1)
   float* out[2];           // [M,128]
+  float* pre[2];           // optional [M,128]: the pre-LayerNorm sum x + FFN(x) (saved for the training backward)
   const uint8_t* w[2];     // packed FFN chunks of this layer (per net)
   const float* b1[2];
   const float* b2[2];
@@ -545,6 +547,7 @@ __global__ void __launch_bounds__(kFfnThreads, 1) k_ffn_tc(FfnArgs a) {
         const float var = fmaxf(sq * (1.f / 128.f) - mean * mean, 0.f);
         const float rstd = 1.0f / sqrtf(var + a.eps);
         float4* orow = reinterpret_cast<float4*>(out + (valid ? grow : 0) * 128);
+        float4* prow = a.pre[net] ? reinterpret_cast<float4*>(a.pre[net] + (valid ? grow : 0) * 128) : nullptr;
 #pragma unroll 1
         for (int g = 0; g < 4; g++) {
           uint32_t r[32];
@@ -556,12 +559,17 @@ __global__ void __launch_bounds__(kFfnThreads, 1) k_ffn_tc(FfnArgs a) {
             float4 bv = *reinterpret_cast<const float4*>(vecs + g * 32 + 4 * j);
             float4 g4 = *reinterpret_cast<const float4*>(vecs + 128 + g * 32 + 4 * j);
             float4 b4 = *reinterpret_cast<const float4*>(vecs + 256 + g * 32 + 4 * j);
-            float4 o;
-            o.x = ((__uint_as_float(r[4 * j]) + (bv.x + xv.x)) - mean) * rstd * g4.x + b4.x;
-            o.y = ((__uint_as_float(r[4 * j + 1]) + (bv.y + xv.y)) - mean) * rstd * g4.y + b4.y;
-            o.z = ((__uint_as_float(r[4 * j + 2]) + (bv.z + xv.z)) - mean) * rstd * g4.z + b4.z;
-            o.w = ((__uint_as_float(r[4 * j + 3]) + (bv.w + xv.w)) - mean) * rstd * g4.w + b4.w;
+            float4 p, o;
+            p.x = __uint_as_float(r[4 * j]) + (bv.x + xv.x);
+            p.y = __uint_as_float(r[4 * j + 1]) + (bv.y + xv.y);
+            p.z = __uint_as_float(r[4 * j + 2]) + (bv.z + xv.z);
+            p.w = __uint_as_float(r[4 * j + 3]) + (bv.w + xv.w);
+            o.x = (p.x - mean) * rstd * g4.x + b4.x;
+            o.y = (p.y - mean) * rstd * g4.y + b4.y;
+            o.z = (p.z - mean) * rstd * g4.z + b4.z;
+            o.w = (p.w - mean) * rstd * g4.w + b4.w;
             if (valid) orow[g * 8 + j] = o;
+            if (valid && prow) prow[g * 8 + j] = p;
           }
         }
         tc_fence_before();
@@ -603,7 +611,7 @@ static int launch_ffn_tc(const tw_flow_config* c, const FfnArgs& a, cudaStream_t
 // per (state b, head h) a [VP x VP] K-major, un-swizzled (8x8 core matrices) bf16 matrix, hi then lo.
 //   element (i, j) at  (i/8)*(VP/8)*128 + (j/8)*128 + (i%8)*16 + (j%8)*2      (VP = V rounded up to 16)
 __global__ void __launch_bounds__(256) k_scores_img(const float* __restrict__ scores, int64_t n_cond, int V, int VP, int H,
-                                                    uint8_t* __restrict__ img) {
+                                                    uint8_t* __restrict__ img, int transpose) {
   // one warp per (b, h, i) row, i < VP
   int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= n_cond * H * VP) return;
@@ -615,7 +623,7 @@ __global__ void __launch_bounds__(256) k_scores_img(const float* __restrict__ sc
   uint8_t* hi = img + (size_t)bh * 2 * mat;
   uint8_t* lo = hi + mat;
   for (int j = lane; j < VP; j += 32) {
-    float v = (i < V && j < V) ? src[j] : 0.f;
+    float v = (i < V && j < V) ? (transpose ? scores[(bh * V + j) * (int64_t)V + i] : src[j]) : 0.f;  // transpose: A_h^T (backward)
     __nv_bfloat16 h = __float2bfloat16(v);
     __nv_bfloat16 l = __float2bfloat16(v - __bfloat162float(h));
     uint32_t off = (i >> 3) * ((VP >> 3) * 128u) + (j >> 3) * 128u + (i & 7) * 16u + (j & 7) * 2u;
@@ -854,6 +862,7 @@ struct ProjArgs {
   const uint8_t* w[2];
   const float* resid[2];
   float* out[2];
+  float* pre[2];  // optional [M,128]: pre-LayerNorm sum (training)
   const float* gamma[2];
   const float* beta[2];
   int64_t M;
@@ -964,7 +973,9 @@ __global__ void __launch_bounds__(192, 1) k_proj_tc(ProjArgs a) {
       tc_fence_before();
       mbar_arrive(&y_free[tb]);
       const int64_t grow = tile * 128 + row;
-      if (grow < a.M) ln_store_row(v, nullptr, a.resid[net] + grow * 128, vecs, vecs + 128, a.eps, a.out[net] + grow * 128);
+      if (grow < a.M)
+        ln_store_row(v, nullptr, a.resid[net] + grow * 128, vecs, vecs + 128, a.eps, a.out[net] + grow * 128,
+                     a.pre[net] ? a.pre[net] + grow * 128 : nullptr);
     }
   }
   tc_fence_before();
@@ -1393,31 +1404,65 @@ void tc_carve(const tw_flow_config* c, int64_t n, int64_t n_cond, int64_t V, Are
 }
 
 // scores -> operand images, once per pass
-int tc_begin_pass(const tw_flow_config* c, const ParamView&, TcScratch& tc, const float* scores, const uint8_t*, int64_t,
-                  int64_t n_cond, int V, cudaStream_t st) {
-  if (!(tc_stage_mask() & TC_MIX)) return TW_OK;
+int tc_scores_images(const tw_flow_config* c, const float* scores, int64_t n_cond, int V, uint8_t* img, int transpose, cudaStream_t st) {
   TW_CHECK_ARG(V <= 128, "tensor-core attention supports at most 128 atoms per sample");
   const int VP = pad16(V);
   int64_t rows = n_cond * c->num_heads * VP;
-  k_scores_img<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(scores, n_cond, V, VP, c->num_heads, tc.scores_img);
+  if (rows == 0) return TW_OK;
+  k_scores_img<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(scores, n_cond, V, VP, c->num_heads, img, transpose);
   TW_LAUNCH_CHECK();
   return TW_OK;
 }
 
-// out = LN1(x + attention(x)) for both networks of encoder layer t
-int tc_attention_layer(const tw_flow_config* c, const ParamView& pv, int k, int t, const TcScratch& tc, float* const x[2],
-                       float* const out[2], int64_t n, int64_t n_cond, int V, cudaStream_t st) {
+int tc_begin_pass(const tw_flow_config* c, const ParamView&, TcScratch& tc, const float* scores, const uint8_t*, int64_t,
+                  int64_t n_cond, int V, cudaStream_t st) {
+  if (!(tc_stage_mask() & TC_MIX)) return TW_OK;
+  return tc_scores_images(c, scores, n_cond, V, tc.scores_img, 0, st);
+}
+
+size_t tc_scores_img_bytes(const tw_flow_config* c, int64_t n_cond, int V) {
+  const int VP = pad16(V);
+  return (size_t)n_cond * c->num_heads * 2 * VP * VP * 2;
+}
+size_t tc_mixed_img_bytes(const tw_flow_config* c, int64_t M) { return (size_t)((M + 127) / 128) * c->num_heads * 2 * 2 * 16384; }
+
+// mixed_h = A_h x for every head, written as A-operand images (both networks)
+int tc_mix(const tw_flow_config* c, const float* const x[2], uint8_t* const img[2], const uint8_t* scores_img, int64_t n,
+           int64_t n_cond, int V, cudaStream_t st) {
   static bool attr_done = false;
   const int VP = pad16(V), H = c->num_heads;
   const uint32_t stage_stride = (uint32_t)((2 * VP * VP * 2 + 1023) & ~1023);
   const int mix_stages = VP > 96 ? 2 : 3;
   const int mix_groups = VP > 96 ? 1 : 2;  // epilogue groups (a second staging buffer must fit next to the ring)
   const int mix_smem = mix_stages * stage_stride + mix_groups * VP * 512 + 256 + 1024;
-  const int proj_smem = kProjStages * kProjStageBytes + 1024 + 256 + 1024;
   if (!attr_done) {
     TW_CUDA(cudaFuncSetAttribute(k_mix_tc<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 65536 + 2048));
     TW_CUDA(cudaFuncSetAttribute(k_mix_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 65536 + 2048));
     static_assert(2 * 65536 + 128 * 512 + 2048 <= 3 * 65536 + 2048, "mix smem budget");
+    attr_done = true;
+  }
+  MixArgs a{};
+  for (int s = 0; s < 2; s++) a.x[s] = x[s], a.img[s] = img[s];
+  a.scores_img = scores_img;
+  a.n = n, a.n_cond = n_cond, a.V = V, a.VP = VP, a.H = H, a.n_stages = mix_stages;
+  int gx = (int)(n < 74 ? n : 74);
+  if (gx < 1) return TW_OK;
+  dim3 grid(gx, 2);
+  if (c->precision == TW_PRECISION_BF16X3)
+    k_mix_tc<3><<<grid, 64 + 128 * mix_groups, mix_smem, st>>>(a);
+  else
+    k_mix_tc<1><<<grid, 64 + 128 * mix_groups, mix_smem, st>>>(a);
+  TW_LAUNCH_CHECK();
+  return TW_OK;
+}
+
+// out = LN1(x + attention(x)) for both networks of encoder layer t; `pre` (optional) receives the pre-LayerNorm sum
+int tc_attention_layer(const tw_flow_config* c, const ParamView& pv, int k, int t, const TcScratch& tc, float* const x[2],
+                       float* const out[2], int64_t n, int64_t n_cond, int V, cudaStream_t st, float* const* pre) {
+  static bool attr_done = false;
+  const int H = c->num_heads;
+  const int proj_smem = kProjStages * kProjStageBytes + 1024 + 256 + 1024;
+  if (!attr_done) {
     TW_CUDA(cudaFuncSetAttribute(k_proj_tc<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, proj_smem));
     TW_CUDA(cudaFuncSetAttribute(k_proj_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, proj_smem));
     attr_done = true;
@@ -1425,19 +1470,7 @@ int tc_attention_layer(const tw_flow_config* c, const ParamView& pv, int k, int 
   TcLayout L = TcLayout::make(c);
   const int64_t M = n * V;
   ProfScope prof(PROF_ATTN, st);
-  {
-    MixArgs a{};
-    for (int s = 0; s < 2; s++) a.x[s] = x[s], a.img[s] = tc.mixed_img[s];
-    a.scores_img = tc.scores_img;
-    a.n = n, a.n_cond = n_cond, a.V = V, a.VP = VP, a.H = H, a.n_stages = mix_stages;
-    int gx = (int)(n < 74 ? n : 74);
-    dim3 grid(gx, 2);
-    if (c->precision == TW_PRECISION_BF16X3)
-      k_mix_tc<3><<<grid, 64 + 128 * mix_groups, mix_smem, st>>>(a);
-    else
-      k_mix_tc<1><<<grid, 64 + 128 * mix_groups, mix_smem, st>>>(a);
-    TW_LAUNCH_CHECK();
-  }
+  TW_TRY(tc_mix(c, x, tc.mixed_img, tc.scores_img, n, n_cond, V, st));
   {
     ProjArgs a{};
     for (int s = 0; s < 2; s++) {
@@ -1445,6 +1478,7 @@ int tc_attention_layer(const tw_flow_config* c, const ParamView& pv, int k, int 
       a.w[s] = tc.packed + L.net_offset(k, s) + L.enc0 + (size_t)t * L.enc_stride + L.enc_wc;
       a.resid[s] = x[s];
       a.out[s] = out[s];
+      a.pre[s] = pre ? pre[s] : nullptr;
       a.gamma[s] = pv.enc(k, s, t, 7);
       a.beta[s] = pv.enc(k, s, t, 8);
     }
@@ -1462,12 +1496,13 @@ int tc_attention_layer(const tw_flow_config* c, const ParamView& pv, int k, int 
 }
 
 int tc_ffn_layer(const tw_flow_config* c, const ParamView& pv, int k, int t, const TcScratch& tc, float* const x[2],
-                 float* const out[2], int64_t M, cudaStream_t st) {
+                 float* const out[2], int64_t M, cudaStream_t st, float* const* pre) {
   TcLayout L = TcLayout::make(c);
   FfnArgs a{};
   for (int s = 0; s < 2; s++) {
     a.x[s] = x[s];
     a.out[s] = out[s];
+    a.pre[s] = pre ? pre[s] : nullptr;
     a.w[s] = tc.packed + L.net_offset(k, s) + L.enc0 + (size_t)t * L.enc_stride + L.enc_ffn;
     a.b1[s] = pv.enc(k, s, t, 4);
     a.b2[s] = pv.enc(k, s, t, 6);

@@ -41,13 +41,19 @@ size_t tc_packed_bytes(const tw_flow_config* c);
 // fused FFN + residual + LayerNorm of encoder layer t for both networks: out = LN2(x + FFN(x))
 // out = LN1(x + sum_h W_c,h (A_h x)) for both networks (tensor-core mixing + projection)
 int tc_attention_layer(const tw_flow_config* c, const ParamView& pv, int k, int t, const TcScratch& tc, float* const x[2],
-                       float* const out[2], int64_t n, int64_t n_cond, int V, cudaStream_t st);
+                       float* const out[2], int64_t n, int64_t n_cond, int V, cudaStream_t st, float* const* pre = nullptr);
+// the mixing step alone (also used by the backward pass with the transposed score images)
+int tc_mix(const tw_flow_config* c, const float* const x[2], uint8_t* const img[2], const uint8_t* scores_img, int64_t n,
+           int64_t n_cond, int V, cudaStream_t st);
+int tc_scores_images(const tw_flow_config* c, const float* scores, int64_t n_cond, int V, uint8_t* img, int transpose, cudaStream_t st);
+size_t tc_scores_img_bytes(const tw_flow_config* c, int64_t n_cond, int V);
+size_t tc_mixed_img_bytes(const tw_flow_config* c, int64_t M);
 // in_mlp (feature gather + 2 linears) and out_mlp (2 linears -> s or t [M,3]) of both networks
 int tc_in_mlp(const tw_flow_config* c, const ParamView& pv, int k, const TcScratch& tc, const int64_t* atom_types, const float* xc,
               const float* xv, const float* z_other, float* const out[2], int64_t n, int64_t n_cond, int V, cudaStream_t st);
 int tc_out_mlp(const tw_flow_config* c, const ParamView& pv, int k, const TcScratch& tc, float* const x[2], float* const out[2],
                int64_t M, cudaStream_t st);
 int tc_ffn_layer(const tw_flow_config* c, const ParamView& pv, int k, int t, const TcScratch& tc, float* const x[2],
-                 float* const out[2], int64_t M, cudaStream_t st);
+                 float* const out[2], int64_t M, cudaStream_t st, float* const* pre = nullptr);
 
 }  // namespace tw

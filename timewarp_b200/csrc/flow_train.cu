@@ -1,0 +1,1123 @@
+// Training path of the flow: log-likelihood forward that records a tape, and the backward pass
+// (gradients of sum_b g_b * log p(y_b | x_b) w.r.t. every trainable parameter).
+//
+// Reference semantics: torch autograd through ConditionalFlowDensityModel.log_likelihood
+// (modules/model_wrappers/flow.py:131-215) as driven by the NLL loss (losses.py:321-356,
+// density_model_base.py:27-42).  The reference has no hand-written backward; the arithmetic restated
+// here is the chain rule of the forward pass documented in flow_api.cu / flow_tc.cu.
+//
+// Design.  The forward pass is the inference pass (same fused tcgen05 kernels) writing every layer
+// boundary to its own buffer (the tape): layer inputs, post-LN1 activations, the two pre-LayerNorm
+// sums, the per-head neighbourhood averages (already stored as bf16 operand images) and the flow state
+// before each coupling layer.  The backward pass re-computes the wide intermediates it needs (FFN / MLP
+// pre-activations) and evaluates every contraction with ONE generic tcgen05 GEMM over operand images:
+//   NT  C[m,n] = sum_k A[m,k] B[n,k]      forward-shaped (re-computation)
+//   NN  C[m,j] = sum_n A[m,n] W[n,j]      data gradient: the SAME packed weight image read MN-major
+//   TN  C[i,j] = sum_m A[m,i] B[m,j]      weight gradient: both activations read MN-major, split over
+//                                         token blocks, fp32 atomics into the gradient tensor
+// An operand image is a grid of [128 rows x 64 cols] bf16 tiles in the 128-byte-swizzled K-major layout
+// (hi and lo parts); the identical bytes are a valid MN-major SW128 tile for the transposed contraction,
+// so no transposed copy of any weight or activation is ever materialised.
+#include "flow_tc.cuh"
+#include "umma.cuh"
+
+namespace tw {
+using namespace umma;
+
+// ============================================================================================
+// operand images
+struct ImgRef {
+  const uint8_t* base;
+  uint32_t sr;   // bytes between row tiles (128 rows)
+  uint32_t sc1;  // bytes between column tile 2q and 2q+1
+  uint32_t sc2;  // bytes between column tile pairs
+  uint32_t lo;   // offset of the lo part of a tile
+};
+__host__ __device__ __forceinline__ const uint8_t* img_tile(const ImgRef& r, int tr, int tc) {
+  return r.base + (size_t)tr * r.sr + (size_t)(tc >> 1) * r.sc2 + (size_t)(tc & 1) * r.sc1;
+}
+// plain activation image of a [rows x 64*n_ct] matrix: tile (tr, tc) at (tr*n_ct + tc) * 32 KB, hi 16 KB | lo 16 KB
+static ImgRef plain_img(const uint8_t* base, int n_ct) { return ImgRef{base, (uint32_t)n_ct * 32768u, 32768u, 65536u, 16384u}; }
+static size_t plain_img_bytes(int64_t rows, int n_ct) { return (size_t)((rows + 127) / 128) * n_ct * 32768; }
+
+enum GemmMode { GEMM_NT = 0, GEMM_NN = 1, GEMM_NN_HEADED = 2, GEMM_TN = 3 };
+
+struct GemmArgs {
+  ImgRef A[2], B[2];
+  float* C[2];
+  const float* bias[2];
+  const float* resid[2];
+  int ldc, ldr;
+  int mode;
+  int rows, cols;        // valid extent of C
+  int tiles_m, tiles_n;  // output tiles of 128 x bn
+  int bn;                // 128 or 64
+  int KB;                // 64-wide blocks of the contraction
+  int splits;            // TN: the contraction is split over `splits` CTAs per output tile
+  int accumulate;        // NT/NN: C += result
+  int nets;              // grid.y (0 -> 2: scale and shift network in one launch)
+};
+
+constexpr int kGemmStages = 3;
+constexpr int kGemmStageBytes = 65536;  // A hi 16K | A lo 16K | B hi 16K | B lo 16K
+
+// Warp 0 streams operand tiles (bulk async copies), warp 1 issues the MMAs, warps 2-5 drain the
+// double-buffered TMEM accumulator.  Persistent over (output tile, split) work items; blockIdx.y = network.
+template <int kSplit>
+__global__ void __launch_bounds__(192, 1) k_gemm_img(GemmArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int net = blockIdx.y;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  uint8_t* ring = smem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kGemmStages * kGemmStageBytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kGemmStages;
+  uint64_t* acc_full = empty + kGemmStages;  // [2]
+  uint64_t* acc_free = acc_full + 2;         // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_free + 2);
+  if (tid == 0) {
+    for (int i = 0; i < kGemmStages; i++) mbar_init(&full[i], 1), mbar_init(&empty[i], 1);
+    for (int i = 0; i < 2; i++) mbar_init(&acc_full[i], 1), mbar_init(&acc_free[i], 128);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc<256>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  const int mode = a.mode, bn = a.bn;
+  const bool a_mn = (mode == GEMM_TN), b_mn = (mode != GEMM_NT);
+  const int n_work = a.tiles_m * a.tiles_n * a.splits;
+  const int kb_chunk = (a.KB + a.splits - 1) / a.splits;
+  const uint32_t parts = kSplit == 3 ? 2u : 1u;
+
+  if (warp == 0) {
+    uint32_t stage = 0, phase = 0;
+    const ImgRef A = a.A[net], B = a.B[net];
+    for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+      const int sp = w % a.splits, t = w / a.splits, tn = t % a.tiles_n, tm = t / a.tiles_n;
+      const int k0 = sp * kb_chunk, k1 = min(a.KB, k0 + kb_chunk);
+      for (int kb = k0; kb < k1; kb++) {
+        mbar_wait(&empty[stage], phase ^ 1);
+        if (elect_one()) {
+          uint8_t* dst = ring + stage * kGemmStageBytes;
+          mbar_arrive_expect_tx(&full[stage], parts * (16384u + (uint32_t)bn * 128u));
+          if (!a_mn) {
+            const uint8_t* src = img_tile(A, tm, kb);
+            bulk_g2s(dst, src, 16384, &full[stage]);
+            if (kSplit == 3) bulk_g2s(dst + 16384, src + A.lo, 16384, &full[stage]);
+          } else {  // 64 token rows of the two column tiles that hold output rows tm*128 .. +127
+            for (int c = 0; c < 2; c++) {
+              const uint8_t* src = img_tile(A, kb >> 1, 2 * tm + c) + (kb & 1) * 8192;
+              bulk_g2s(dst + c * 8192, src, 8192, &full[stage]);
+              if (kSplit == 3) bulk_g2s(dst + 16384 + c * 8192, src + A.lo, 8192, &full[stage]);
+            }
+          }
+          if (!b_mn) {
+            const uint8_t* src = img_tile(B, tn, kb);
+            bulk_g2s(dst + 32768, src, bn * 128, &full[stage]);
+            if (kSplit == 3) bulk_g2s(dst + 49152, src + B.lo, bn * 128, &full[stage]);
+          } else {
+            const int tr = (mode == GEMM_NN_HEADED) ? 0 : (kb >> 1);
+            const int tc0 = (mode == GEMM_NN_HEADED) ? 2 * (kb >> 1) : (bn == 128 ? 2 * tn : tn);
+            for (int c = 0; c < bn / 64; c++) {
+              const uint8_t* src = img_tile(B, tr, tc0 + c) + (kb & 1) * 8192;
+              bulk_g2s(dst + 32768 + c * 8192, src, 8192, &full[stage]);
+              if (kSplit == 3) bulk_g2s(dst + 49152 + c * 8192, src + B.lo, 8192, &full[stage]);
+            }
+          }
+        }
+        __syncwarp();
+        if (++stage == kGemmStages) stage = 0, phase ^= 1;
+      }
+    }
+  } else if (warp == 1) {
+    uint32_t stage = 0, phase = 0, ph_free[2] = {0, 0};
+    const uint32_t idesc = make_idesc_bf16(128, bn, a_mn ? 1 : 0, b_mn ? 1 : 0);
+    int it = 0;
+    for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+      const int sp = w % a.splits;
+      const int k0 = sp * kb_chunk, k1 = min(a.KB, k0 + kb_chunk);
+      if (k0 >= k1) continue;
+      const int tb = it & 1;
+      if (it >= 2) {
+        mbar_wait(&acc_free[tb], ph_free[tb]);
+        ph_free[tb] ^= 1;
+      }
+      it++;
+      tc_fence_after();
+      const uint32_t d = tmem + tb * 128;
+      for (int kb = k0; kb < k1; kb++) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t base = smem_u32(ring + stage * kGemmStageBytes);
+          const uint32_t ahi = base, alo = base + 16384, bhi = base + 32768, blo = base + 49152;
+#pragma unroll
+          for (int term = 0; term < (kSplit == 3 ? 3 : 1); term++) {
+            const uint32_t ab = (term == 1) ? alo : ahi, bb = (term == 2) ? blo : bhi;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+              const uint64_t ad = a_mn ? make_smem_desc(ab + k * 2048, 8192, 1024, LAYOUT_SW128) : desc_kmajor_sw128(ab + k * 32);
+              const uint64_t bd = b_mn ? make_smem_desc(bb + k * 2048, 8192, 1024, LAYOUT_SW128) : desc_kmajor_sw128(bb + k * 32);
+              mma_ss(d, ad, bd, idesc, (kb > k0 || term > 0 || k > 0) ? 1 : 0);
+            }
+          }
+          mma_commit(&empty[stage]);
+          if (kb == k1 - 1) mma_commit(&acc_full[tb]);
+        }
+        __syncwarp();
+        if (++stage == kGemmStages) stage = 0, phase ^= 1;
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    uint32_t ph_full[2] = {0, 0};
+    float* C = a.C[net];
+    const float* bias = a.bias[net];
+    const float* resid = a.resid[net];
+    int it = 0;
+    for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+      const int sp = w % a.splits, t = w / a.splits, tn = t % a.tiles_n, tm = t / a.tiles_n;
+      const int k0 = sp * kb_chunk, k1 = min(a.KB, k0 + kb_chunk);
+      if (k0 >= k1) continue;
+      const int tb = it & 1;
+      it++;
+      mbar_wait(&acc_full[tb], ph_full[tb]);
+      ph_full[tb] ^= 1;
+      tc_fence_after();
+      const int64_t grow = (int64_t)tm * 128 + row;
+      const bool valid = grow < a.rows;
+#pragma unroll 1
+      for (int g = 0; g < bn / 32; g++) {
+        uint32_t r[32];
+        tmem_ld32(tmem + lane_base + tb * 128 + g * 32, r);
+        tmem_ld_wait();
+        const int col0 = tn * bn + g * 32;
+        float* crow = C + grow * a.ldc + col0;
+        if (!valid) {
+          // rows beyond the matrix: nothing to store (the TMEM load above stays warp-uniform)
+        } else if (mode == GEMM_TN) {
+          if ((a.cols & 3) == 0 && (a.ldc & 3) == 0) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              if (col0 + j < a.cols)
+                atomicAdd(reinterpret_cast<float4*>(crow + j), make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                                                          __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; j++)
+              if (col0 + j < a.cols) atomicAdd(crow + j, __uint_as_float(r[j]));
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            if (col0 + j >= a.cols) continue;
+            float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+            if (bias) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + col0 + j));
+              v.x += b4.x, v.y += b4.y, v.z += b4.z, v.w += b4.w;
+            }
+            if (resid) {
+              const float4 r4 = __ldg(reinterpret_cast<const float4*>(resid + grow * a.ldr + col0 + j));
+              v.x += r4.x, v.y += r4.y, v.z += r4.z, v.w += r4.w;
+            }
+            if (a.accumulate) {
+              const float4 c4 = *reinterpret_cast<const float4*>(crow + j);
+              v.x += c4.x, v.y += c4.y, v.z += c4.z, v.w += c4.w;
+            }
+            *reinterpret_cast<float4*>(crow + j) = v;
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&acc_free[tb]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<256>(tmem);
+}
+
+static int launch_gemm(const tw_flow_config* c, GemmArgs& a, cudaStream_t st) {
+  static bool attr_done = false;
+  const int smem = kGemmStages * kGemmStageBytes + 256 + 1024;
+  if (!attr_done) {
+    TW_CUDA(cudaFuncSetAttribute(k_gemm_img<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    TW_CUDA(cudaFuncSetAttribute(k_gemm_img<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_done = true;
+  }
+  TW_CHECK_ARG(a.bn == 128 || a.bn == 64, "gemm: bn must be 64 or 128");
+  TW_CHECK_ARG(a.mode != GEMM_NN_HEADED || (a.tiles_n == 1 && a.bn == 128), "gemm: headed mode has one column tile");
+  if (a.mode != GEMM_TN) a.splits = 1;
+  if (a.splits < 1) a.splits = 1;
+  if (a.splits > a.KB) a.splits = a.KB > 0 ? a.KB : 1;
+  const int64_t n_work = (int64_t)a.tiles_m * a.tiles_n * a.splits;
+  if (n_work == 0 || a.KB == 0) return TW_OK;
+  const int nets = a.nets ? a.nets : 2;
+  const int per = 148 / nets;
+  dim3 grid((unsigned)(n_work < per ? n_work : per), nets);
+  if (c->precision == TW_PRECISION_BF16X3)
+    k_gemm_img<3><<<grid, 192, smem, st>>>(a);
+  else
+    k_gemm_img<1><<<grid, 192, smem, st>>>(a);
+  TW_LAUNCH_CHECK();
+  return TW_OK;
+}
+
+// ============================================================================================
+// tile-wise element kernels.  One CTA = one [128 rows x 64 cols] image tile, 256 threads; thread e covers
+// row (e >> 5) + 8*i, columns 2*(e & 31), +1  -> 4-byte stores that fill 128-byte swizzled rows.
+__device__ __forceinline__ float silu_fwd(float v) { return v / (1.f + __expf(-v)); }
+__device__ __forceinline__ float silu_grad(float v) {
+  const float s = 1.f / (1.f + __expf(-v));
+  return s * (1.f + v * (1.f - s));
+}
+
+__device__ __forceinline__ void img_store2(uint8_t* tile_hi, uint32_t lo_off, int r, int kp, float v0, float v1) {
+  uint32_t h, l;
+  split2(v0, v1, h, l);
+  const uint32_t off = sw128_offset(r, kp, 128);
+  *reinterpret_cast<uint32_t*>(tile_hi + off) = h;
+  *reinterpret_cast<uint32_t*>(tile_hi + lo_off + off) = l;
+}
+
+// column sums of per-thread pairs (s0, s1) over the 8 warps of the CTA -> atomicAdd into dst[col0 + 2*lane (+1)]
+__device__ __forceinline__ void tile_colsum_add(float s0, float s1, float* red /*[8][64]*/, float* dst, int col0, int n_cols) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  red[w * 64 + 2 * lane] = s0;
+  red[w * 64 + 2 * lane + 1] = s1;
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; i++) t += red[i * 64 + threadIdx.x];
+    if (col0 + (int)threadIdx.x < n_cols) atomicAdd(dst + col0 + threadIdx.x, t);
+  }
+  __syncthreads();
+}
+
+struct PackArgs {
+  const float* X[2];
+  uint8_t* img[2];
+  float* colsum[2];  // optional: += column sums of X
+  int64_t M;
+  int C, ld, n_ct;
+};
+__global__ void __launch_bounds__(256) k_pack_act(PackArgs a) {
+  __shared__ float red[8 * 64];
+  const int net = blockIdx.z, tc = blockIdx.x, tr = blockIdx.y;
+  const float* X = a.X[net];
+  uint8_t* hi = a.img[net] + ((size_t)tr * a.n_ct + tc) * 32768;
+  const int lane = threadIdx.x & 31, kp = lane * 2, gc = tc * 64 + kp;
+  float s0 = 0.f, s1 = 0.f;
+  for (int r = threadIdx.x >> 5; r < 128; r += 8) {
+    const int64_t gr = (int64_t)tr * 128 + r;
+    float v0 = 0.f, v1 = 0.f;
+    if (gr < a.M && gc < a.C) {
+      const float2 v = *reinterpret_cast<const float2*>(X + gr * a.ld + gc);
+      v0 = v.x, v1 = v.y;
+    }
+    s0 += v0, s1 += v1;
+    img_store2(hi, 16384, r, kp, v0, v1);
+  }
+  if (a.colsum[net]) tile_colsum_add(s0, s1, red, a.colsum[net], tc * 64, a.C);
+}
+
+// Backward through an activation: given the pre-activation `pre` (bias included) and the gradient w.r.t.
+// the activation output, write act(pre) and d_pre = d_act * act'(pre) as operand images and add the
+// column sums of d_pre into the bias gradient.
+struct ActBwdArgs {
+  const float* pre[2];
+  const float* dact[2];
+  uint8_t* img_act[2];
+  uint8_t* img_dpre[2];
+  float* dbias[2];
+  int64_t M;
+  int C, n_ct;
+};
+template <int kAct>
+__global__ void __launch_bounds__(256) k_act_bwd(ActBwdArgs a) {
+  __shared__ float red[8 * 64];
+  const int net = blockIdx.z, tc = blockIdx.x, tr = blockIdx.y;
+  const size_t toff = ((size_t)tr * a.n_ct + tc) * 32768;
+  uint8_t* act_hi = a.img_act[net] + toff;
+  uint8_t* dp_hi = a.img_dpre[net] + toff;
+  const int lane = threadIdx.x & 31, kp = lane * 2, gc = tc * 64 + kp;
+  float s0 = 0.f, s1 = 0.f;
+  for (int r = threadIdx.x >> 5; r < 128; r += 8) {
+    const int64_t gr = (int64_t)tr * 128 + r;
+    float a0 = 0.f, a1 = 0.f, d0 = 0.f, d1 = 0.f;
+    if (gr < a.M) {
+      const float2 p = *reinterpret_cast<const float2*>(a.pre[net] + gr * a.C + gc);
+      const float2 g = *reinterpret_cast<const float2*>(a.dact[net] + gr * a.C + gc);
+      if (kAct == ACT_RELU) {
+        a0 = fmaxf(p.x, 0.f), a1 = fmaxf(p.y, 0.f);
+        d0 = p.x > 0.f ? g.x : 0.f, d1 = p.y > 0.f ? g.y : 0.f;
+      } else {
+        a0 = silu_fwd(p.x), a1 = silu_fwd(p.y);
+        d0 = g.x * silu_grad(p.x), d1 = g.y * silu_grad(p.y);
+      }
+    }
+    s0 += d0, s1 += d1;
+    img_store2(act_hi, 16384, r, kp, a0, a1);
+    img_store2(dp_hi, 16384, r, kp, d0, d1);
+  }
+  tile_colsum_add(s0, s1, red, a.dbias[net], tc * 64, a.C);
+}
+
+// Last layer of the out_mlp (hidden -> 3, mlp.py:18-23) backward, fused with the SiLU backward of the hidden
+// layer: pre [M,hid] is the re-computed pre-activation, dst [M,3] the gradient of the network output.
+struct OutLastArgs {
+  const float* pre[2];
+  const float* dst[2];
+  const float* w4[2];   // [3,hid]
+  uint8_t* img_dpre[2];
+  float* dw4[2];        // [3,hid]
+  float* db4[2];        // [3]
+  float* db3[2];        // [hid]
+  int64_t M;
+  int hid, n_ct;
+};
+__global__ void __launch_bounds__(256) k_out_last_bwd(OutLastArgs a) {
+  __shared__ float red[8 * 64];
+  __shared__ float sd[128 * 3];
+  const int net = blockIdx.z, tc = blockIdx.x, tr = blockIdx.y;
+  uint8_t* dp_hi = a.img_dpre[net] + ((size_t)tr * a.n_ct + tc) * 32768;
+  const int lane = threadIdx.x & 31, kp = lane * 2, gc = tc * 64 + kp;
+  for (int i = threadIdx.x; i < 128 * 3; i += 256) {
+    const int64_t gr = (int64_t)tr * 128 + i / 3;
+    sd[i] = gr < a.M ? a.dst[net][gr * 3 + i % 3] : 0.f;
+  }
+  __syncthreads();
+  float w[3][2];
+#pragma unroll
+  for (int i = 0; i < 3; i++) w[i][0] = a.w4[net][i * a.hid + gc], w[i][1] = a.w4[net][i * a.hid + gc + 1];
+  float s0 = 0.f, s1 = 0.f, gw[3][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
+  for (int r = threadIdx.x >> 5; r < 128; r += 8) {
+    const int64_t gr = (int64_t)tr * 128 + r;
+    float d0 = 0.f, d1 = 0.f;
+    if (gr < a.M) {
+      const float2 p = *reinterpret_cast<const float2*>(a.pre[net] + gr * a.hid + gc);
+      const float g0 = sd[r * 3], g1 = sd[r * 3 + 1], g2 = sd[r * 3 + 2];
+      const float act0 = silu_fwd(p.x), act1 = silu_fwd(p.y);
+      gw[0][0] = fmaf(g0, act0, gw[0][0]), gw[0][1] = fmaf(g0, act1, gw[0][1]);
+      gw[1][0] = fmaf(g1, act0, gw[1][0]), gw[1][1] = fmaf(g1, act1, gw[1][1]);
+      gw[2][0] = fmaf(g2, act0, gw[2][0]), gw[2][1] = fmaf(g2, act1, gw[2][1]);
+      d0 = (g0 * w[0][0] + g1 * w[1][0] + g2 * w[2][0]) * silu_grad(p.x);
+      d1 = (g0 * w[0][1] + g1 * w[1][1] + g2 * w[2][1]) * silu_grad(p.y);
+    }
+    s0 += d0, s1 += d1;
+    img_store2(dp_hi, 16384, r, kp, d0, d1);
+  }
+  tile_colsum_add(s0, s1, red, a.db3[net], tc * 64, a.hid);
+#pragma unroll
+  for (int i = 0; i < 3; i++) tile_colsum_add(gw[i][0], gw[i][1], red, a.dw4[net] + i * a.hid, tc * 64, a.hid);
+  if (tc == 0 && threadIdx.x < 3) {
+    float t = 0.f;
+    for (int r = 0; r < 128; r++) t += sd[r * 3 + threadIdx.x];
+    atomicAdd(a.db4[net] + threadIdx.x, t);
+  }
+}
+
+// LayerNorm backward over 128 features (custom_attention_encoder.py:110,113): one CTA per 128-row tile, one
+// warp per row (lane l owns columns 4l..4l+3).  dr = rstd * (g - mean(g) - xhat * mean(g * xhat)), g = dy * gamma.
+// Writes dr (fp32 + operand image) and adds dgamma, dbeta and (optionally) the column sums of dr.
+struct LnBwdArgs {
+  const float* pre[2];   // [M,128] LayerNorm input
+  const float* dy[2];    // [M,128]
+  const float* gamma[2];
+  float* dr[2];          // [M,128]
+  uint8_t* img_dr[2];    // plain image, 2 column tiles
+  float* dgamma[2];
+  float* dbeta[2];
+  float* dbias[2];       // optional
+  int64_t M;
+  float eps;
+};
+__global__ void __launch_bounds__(256) k_ln_bwd(LnBwdArgs a) {
+  __shared__ float red[3][8][128];
+  const int net = blockIdx.y, tr = blockIdx.x;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const float4 gm = *reinterpret_cast<const float4*>(a.gamma[net] + 4 * lane);
+  float4 ag = make_float4(0.f, 0.f, 0.f, 0.f), ab = ag, as = ag;
+  uint8_t* tile_hi = a.img_dr[net] + ((size_t)tr * 2 + (lane >> 4)) * 32768;
+  for (int r = w; r < 128; r += 8) {
+    const int64_t gr = (int64_t)tr * 128 + r;
+    float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (gr < a.M) {
+      const float4 x = *reinterpret_cast<const float4*>(a.pre[net] + gr * 128 + 4 * lane);
+      const float4 dy = *reinterpret_cast<const float4*>(a.dy[net] + gr * 128 + 4 * lane);
+      const float mean = warp_sum((x.x + x.y) + (x.z + x.w)) * (1.f / 128.f);
+      const float4 xc = make_float4(x.x - mean, x.y - mean, x.z - mean, x.w - mean);
+      const float var = warp_sum(xc.x * xc.x + xc.y * xc.y + xc.z * xc.z + xc.w * xc.w) * (1.f / 128.f);
+      const float rstd = 1.0f / sqrtf(var + a.eps);
+      const float4 xh = make_float4(xc.x * rstd, xc.y * rstd, xc.z * rstd, xc.w * rstd);
+      const float4 g = make_float4(dy.x * gm.x, dy.y * gm.y, dy.z * gm.z, dy.w * gm.w);
+      const float mg = warp_sum((g.x + g.y) + (g.z + g.w)) * (1.f / 128.f);
+      const float mgx = warp_sum(g.x * xh.x + g.y * xh.y + g.z * xh.z + g.w * xh.w) * (1.f / 128.f);
+      d = make_float4(rstd * (g.x - mg - xh.x * mgx), rstd * (g.y - mg - xh.y * mgx), rstd * (g.z - mg - xh.z * mgx),
+                      rstd * (g.w - mg - xh.w * mgx));
+      *reinterpret_cast<float4*>(a.dr[net] + gr * 128 + 4 * lane) = d;
+      ag.x = fmaf(dy.x, xh.x, ag.x), ag.y = fmaf(dy.y, xh.y, ag.y), ag.z = fmaf(dy.z, xh.z, ag.z), ag.w = fmaf(dy.w, xh.w, ag.w);
+      ab.x += dy.x, ab.y += dy.y, ab.z += dy.z, ab.w += dy.w;
+      as.x += d.x, as.y += d.y, as.z += d.z, as.w += d.w;
+    }
+    uint32_t h0, l0, h1, l1;
+    split2(d.x, d.y, h0, l0);
+    split2(d.z, d.w, h1, l1);
+    const uint32_t off = sw128_offset(r, (4 * lane) & 63, 128);
+    *reinterpret_cast<uint2*>(tile_hi + off) = make_uint2(h0, h1);
+    *reinterpret_cast<uint2*>(tile_hi + 16384 + off) = make_uint2(l0, l1);
+  }
+  *reinterpret_cast<float4*>(&red[0][w][4 * lane]) = ag;
+  *reinterpret_cast<float4*>(&red[1][w][4 * lane]) = ab;
+  *reinterpret_cast<float4*>(&red[2][w][4 * lane]) = as;
+  __syncthreads();
+  for (int i = threadIdx.x; i < 3 * 128; i += 256) {
+    const int which = i >> 7, col = i & 127;
+    float* dst = which == 0 ? a.dgamma[net] : (which == 1 ? a.dbeta[net] : a.dbias[net]);
+    if (!dst) continue;
+    float t = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; j++) t += red[which][j][col];
+    atomicAdd(dst + col, t);
+  }
+}
+
+// Conditioner input of both networks as an operand image [M, 64] (one column tile): the feature gather of
+// flow.py:172 / custom_transformer_nvp.py:64-71, zero padded from E+9 to 64 columns.
+__global__ void __launch_bounds__(256) k_features_img(const float* __restrict__ embed, const int64_t* __restrict__ atom_types,
+                                                      const float* __restrict__ xc, const float* __restrict__ xv,
+                                                      const float* __restrict__ z_other, int64_t M, int V, int E, int n_types,
+                                                      uint8_t* __restrict__ img) {
+  const int tr = blockIdx.x;
+  uint8_t* hi = img + (size_t)tr * 32768;
+  const int lane = threadIdx.x & 31, kp = lane * 2;
+  for (int r = threadIdx.x >> 5; r < 128; r += 8) {
+    const int64_t m = (int64_t)tr * 128 + r;
+    float v[2] = {0.f, 0.f};
+    if (m < M) {
+      int64_t t = atom_types[m];
+      t = t < 0 ? 0 : (t >= n_types ? n_types - 1 : t);
+#pragma unroll
+      for (int u = 0; u < 2; u++) {
+        const int e = kp + u;
+        if (e < E) v[u] = embed[t * E + e];
+        else if (e < E + 3) v[u] = xc[m * 3 + (e - E)];
+        else if (e < E + 6) v[u] = xv[m * 3 + (e - E - 3)];
+        else if (e < E + 9) v[u] = z_other[m * 3 + (e - E - 6)];
+      }
+    }
+    img_store2(hi, 16384, r, kp, v[0], v[1]);
+  }
+}
+
+// Gradient of the conditioner input [M,64] (both networks) -> flow state (columns E+6..E+8) and atom embedding
+__global__ void __launch_bounds__(256) k_du_scatter(const float* __restrict__ du0, const float* __restrict__ du1,
+                                                    const int64_t* __restrict__ atom_types, int64_t M, int E, int n_types,
+                                                    float* __restrict__ dz_other, float* __restrict__ dembed) {
+  extern __shared__ float acc[];  // [n_types * E]
+  for (int i = threadIdx.x; i < n_types * E; i += blockDim.x) acc[i] = 0.f;
+  __syncthreads();
+  const int64_t m0 = (int64_t)blockIdx.x * 128;
+  for (int idx = threadIdx.x; idx < 128 * 64; idx += blockDim.x) {
+    const int64_t m = m0 + (idx >> 6);
+    const int e = idx & 63;
+    if (m >= M) continue;
+    const float g = du0[m * 64 + e] + du1[m * 64 + e];
+    if (e < E) {
+      int64_t t = atom_types[m];
+      t = t < 0 ? 0 : (t >= n_types ? n_types - 1 : t);
+      atomicAdd(&acc[t * E + e], g);
+    } else if (e >= E + 6 && e < E + 9) {
+      dz_other[m * 3 + (e - E - 6)] += g;
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n_types * E; i += blockDim.x)
+    if (acc[i] != 0.f) atomicAdd(dembed + i, acc[i]);
+}
+
+// Affine coupling backward (nvp.py:127-133): z' = z * exp(s) + t, log-det = sum s over unmasked atoms.
+// In: dz (gradient w.r.t. z'), z (state BEFORE the layer), s, g[n] = d(objective)/d(log p).  Out: dz <- dz * exp(s),
+// ds = dz' * z * exp(s) + g * keep, dt = dz'.
+__global__ void __launch_bounds__(128) k_coupling_bwd(const float* __restrict__ s, const float* __restrict__ z_in,
+                                                      float* __restrict__ dz, const uint8_t* __restrict__ mask,
+                                                      const float* __restrict__ g, int V, float* __restrict__ ds,
+                                                      float* __restrict__ dt) {
+  const int64_t n = blockIdx.x;
+  const float gn = g[n];
+  for (int e = threadIdx.x; e < V * 3; e += blockDim.x) {
+    const int64_t i = n * V * 3 + e;
+    const float sc = expf(s[i]), d = dz[i];
+    ds[i] = d * z_in[i] * sc + (mask[n * V + e / 3] ? 0.f : gn);
+    dt[i] = d;
+    dz[i] = d * sc;
+  }
+}
+
+// Prior backward (flow.py:159-166,191-203): lp = sum keep * (-z^2 / (2 e^{2 sigma}) - sigma - const)
+__global__ void __launch_bounds__(128) k_prior_bwd(const float* __restrict__ zc, const float* __restrict__ zv,
+                                                   const uint8_t* __restrict__ mask, const float* __restrict__ lsc,
+                                                   const float* __restrict__ lsv, const float* __restrict__ g, int V,
+                                                   float* __restrict__ dzc, float* __restrict__ dzv, float* __restrict__ dlsc,
+                                                   float* __restrict__ dlsv) {
+  __shared__ float red[33];
+  const int64_t n = blockIdx.x;
+  const float gn = g[n];
+  const float ivc = expf(-2.f * lsc[0]), ivv = expf(-2.f * lsv[0]);
+  float ac = 0.f, av = 0.f;
+  for (int e = threadIdx.x; e < V * 3; e += blockDim.x) {
+    const int64_t i = n * V * 3 + e;
+    const bool keep = !mask[n * V + e / 3];
+    const float a = zc[i], b = zv[i];
+    dzc[i] = keep ? -gn * a * ivc : 0.f;
+    dzv[i] = keep ? -gn * b * ivv : 0.f;
+    if (keep) ac += gn * (a * a * ivc - 1.f), av += gn * (b * b * ivv - 1.f);
+  }
+  ac = block_sum(ac, red);
+  av = block_sum(av, red);
+  if (threadIdx.x == 0) {
+    if (dlsc) atomicAdd(dlsc, ac);
+    if (dlsv) atomicAdd(dlsv, av);
+  }
+}
+
+// W_c,h = W_o,h W_v,h (k_combine_wc) backward: dW_o[i, hD+k] += sum_j dWc[i, hD+j] W_v[hD+k, j];
+//                                              dW_v[hD+k, j] += sum_i W_o[i, hD+k] dWc[i, hD+j].
+struct WcChainArgs {
+  const float* dwc[2];
+  const float* wo[2];
+  const float* wv[2];
+  float* dwo[2];
+  float* dwv[2];
+};
+__global__ void __launch_bounds__(128) k_wc_chain(WcChainArgs a, int D, int H) {
+  const int net = blockIdx.z, h = blockIdx.x, r = blockIdx.y, c = threadIdx.x;
+  if (c >= D) return;
+  const int HD = H * D;
+  const float* dwc = a.dwc[net];
+  const float* wo = a.wo[net];
+  const float* wv = a.wv[net];
+  // dW_o[i = r, hD + k = c]
+  float acc = 0.f;
+  for (int j = 0; j < D; j++) acc = fmaf(dwc[(size_t)r * HD + h * D + j], wv[(size_t)(h * D + c) * D + j], acc);
+  a.dwo[net][(size_t)r * HD + h * D + c] += acc;
+  // dW_v[hD + k = r, j = c]
+  float acc2 = 0.f;
+  for (int i = 0; i < D; i++) acc2 = fmaf(wo[(size_t)i * HD + h * D + r], dwc[(size_t)i * HD + h * D + c], acc2);
+  a.dwv[net][(size_t)(h * D + r) * D + c] += acc2;
+}
+
+// ============================================================================================
+// tape layout
+struct NetTape {
+  float* st;            // [M,3] network output (s or t)
+  float* h[8];          // h[0] = in_mlp output, h[t+1] = output of encoder layer t
+  float* y1[8];         // post-LN1
+  float* r1[8];         // pre-LN1
+  float* r2[8];         // pre-LN2
+  uint8_t* mixed[8];    // operand images of the per-head averages
+};
+struct Tape {
+  float* xc;            // centred conditioning coordinates [B,V,3]
+  float* com;
+  float* scores;        // [B,H,V,V]
+  uint8_t* scores_img;  // forward images
+  uint8_t* scores_img_t;  // transposed images (backward)
+  float* z[17][2];      // flow state (coords, velocs) before coupling layer k; [L] = final latent
+  float* delta;
+  NetTape net[16][2];
+};
+
+static size_t carve_tape(const tw_flow_config* c, int64_t B, int V, void* base, size_t cap, Tape* out) {
+  Arena ar(base, cap);
+  const int64_t M = B * V;
+  const int L = c->num_coupling_layers, T = c->num_transformer_layers, H = c->num_heads;
+  Tape t{};
+  t.xc = ar.take<float>(M * 3);
+  t.com = ar.take<float>(B * 3);
+  t.scores = ar.take<float>((size_t)B * H * V * V);
+  ar.off = align_up(ar.off, 1024);
+  t.scores_img = ar.take<uint8_t>(tc_scores_img_bytes(c, B, V));
+  ar.off = align_up(ar.off, 1024);
+  t.scores_img_t = ar.take<uint8_t>(tc_scores_img_bytes(c, B, V));
+  t.delta = ar.take<float>(B);
+  for (int k = 0; k <= L; k++)
+    for (int i = 0; i < 2; i++) t.z[k][i] = ar.take<float>(M * 3);
+  for (int k = 0; k < L; k++)
+    for (int s = 0; s < 2; s++) {
+      NetTape& n = t.net[k][s];
+      n.st = ar.take<float>(M * 3);
+      for (int i = 0; i <= T; i++) n.h[i] = ar.take<float>(M * 128);
+      for (int i = 0; i < T; i++) {
+        n.y1[i] = ar.take<float>(M * 128);
+        n.r1[i] = ar.take<float>(M * 128);
+        n.r2[i] = ar.take<float>(M * 128);
+        ar.off = align_up(ar.off, 1024);
+        n.mixed[i] = ar.take<uint8_t>(tc_mixed_img_bytes(c, M));
+      }
+    }
+  if (out) *out = t;
+  return align_up(ar.off, 1024);
+}
+
+static int check_train(const tw_flow_config* c, const void* const* params, int64_t B, int64_t V) {
+  TW_CHECK_ARG(c != nullptr && params != nullptr, "NULL cfg / params");
+  if (c->precision == TW_PRECISION_FP32 || !tc_supported(c))
+    return fail(TW_ERR_UNSUPPORTED, "the training path needs a tensor-core precision (bf16x3 / bf16) and the flagship layer sizes");
+  TW_CHECK_ARG(c->num_coupling_layers <= 16 && c->num_transformer_layers <= 8, "too many layers for the training tape");
+  TW_CHECK_ARG(c->num_coupling_layers % 2 == 0 && c->num_coupling_layers >= 2, "Real NVP should have an even number of coupling layers");
+  TW_CHECK_ARG(B >= 0 && V >= 1 && V <= 128, "bad sizes (training path: at most 128 atoms per sample)");
+  TW_CHECK_ARG(B * V < (1LL << 24), "too many tokens for one training call");
+  return TW_OK;
+}
+
+// ============================================================================================
+// backward workspace
+struct BwdBuffers {
+  float* dz[2];          // gradient w.r.t. the flow state (coords, velocs)
+  float* dst[2];         // gradient w.r.t. the network outputs (s, t)  [M,3]
+  float* dyA[2];         // [M,128] gradient ping
+  float* dyB[2];         // [M,128] gradient pong
+  float* dr[2];          // [M,128] LayerNorm-input gradient
+  float* wide0[2];       // [M,F] fp32 (re-computed pre-activations)
+  float* wide1[2];       // [M,F] fp32 (gradient w.r.t. the wide activation)
+  uint8_t* img_x[2];     // [M,128] image of a saved activation
+  uint8_t* img_d[2];     // [M,128] image of a gradient
+  uint8_t* img_w0[2];    // [M,F] image (activation)
+  uint8_t* img_w1[2];    // [M,F] image (pre-activation gradient)
+  uint8_t* img_g[2];     // [M,H*128] image (transposed mixing of the gradient)
+  uint8_t* img_u;        // [M,64] image of the conditioner input (shared by both networks)
+  float* du[2];          // [M,64]
+  float* dwc[2];         // [128, H*128]
+};
+
+static size_t carve_bwd(const tw_flow_config* c, int64_t B, int V, void* base, size_t cap, BwdBuffers* out) {
+  Arena ar(base, cap);
+  const int64_t M = B * V;
+  const int F = c->dim_feedforward > 256 ? c->dim_feedforward : 256, H = c->num_heads;
+  BwdBuffers b{};
+  for (int i = 0; i < 2; i++) {
+    b.dz[i] = ar.take<float>(M * 3);
+    b.dst[i] = ar.take<float>(M * 3);
+    b.dyA[i] = ar.take<float>(M * 128);
+    b.dyB[i] = ar.take<float>(M * 128);
+    b.dr[i] = ar.take<float>(M * 128);
+    b.wide0[i] = ar.take<float>(M * F);
+    b.wide1[i] = ar.take<float>(M * F);
+    b.du[i] = ar.take<float>(M * 64);
+    b.dwc[i] = ar.take<float>((size_t)128 * H * 128);
+  }
+  auto take_img = [&](int n_ct) {
+    ar.off = align_up(ar.off, 1024);
+    return ar.take<uint8_t>(plain_img_bytes(M, n_ct));
+  };
+  for (int i = 0; i < 2; i++) {
+    b.img_x[i] = take_img(2);
+    b.img_d[i] = take_img(2);
+    b.img_w0[i] = take_img(F / 64);
+    b.img_w1[i] = take_img(F / 64);
+    b.img_g[i] = take_img(H * 2);
+  }
+  b.img_u = take_img(1);
+  if (out) *out = b;
+  return align_up(ar.off, 1024);
+}
+
+// gradient table: same order as the parameter table; entries may be NULL (parameter frozen)
+struct GradView {
+  ParamView pv;  // index arithmetic only
+  void* const* g;
+  float* at(int i) const { return (float*)g[i]; }
+  float* embed() const { return at(0); }
+  float* log_scale_c() const { return at(1); }
+  float* log_scale_v() const { return at(2); }
+  float* in_w(int k, int net, int i) const { return at(pv.net_base(k, net) + 2 * i); }
+  float* in_b(int k, int net, int i) const { return at(pv.net_base(k, net) + 2 * i + 1); }
+  float* enc(int k, int net, int t, int j) const { return at(pv.net_base(k, net) + pv.per_mlp() + 11 * t + j); }
+  float* out_w(int k, int net, int i) const { return at(pv.net_base(k, net) + pv.per_mlp() + 11 * pv.c->num_transformer_layers + 2 * i); }
+  float* out_b(int k, int net, int i) const { return at(pv.net_base(k, net) + pv.per_mlp() + 11 * pv.c->num_transformer_layers + 2 * i + 1); }
+};
+
+struct BwdCtx {
+  const tw_flow_config* c;
+  ParamView pv;
+  GradView gv;
+  TcLayout L;
+  const uint8_t* packed;
+  Tape tp;
+  BwdBuffers b;
+  const int64_t* atom_types;
+  const float* x_velocs;
+  const uint8_t* mask;
+  int64_t B, M;
+  int V;
+  int tiles;  // token tiles
+  cudaStream_t st;
+};
+
+static int pack_act(BwdCtx& x, float* const X[2], uint8_t* const img[2], int C, float* const colsum[2]) {
+  PackArgs a{};
+  for (int s = 0; s < 2; s++) a.X[s] = X[s], a.img[s] = img[s], a.colsum[s] = colsum ? colsum[s] : nullptr;
+  a.M = x.M, a.C = C, a.ld = C, a.n_ct = C / 64;
+  k_pack_act<<<dim3(C / 64, x.tiles, 2), 256, 0, x.st>>>(a);
+  TW_LAUNCH_CHECK();
+  return TW_OK;
+}
+
+static GemmArgs gemm_base(BwdCtx& x, int mode) {
+  GemmArgs g{};
+  g.mode = mode;
+  g.bn = 128;
+  g.splits = 1;
+  return g;
+}
+
+// number of token-range splits for a weight-gradient GEMM with `out_tiles` output tiles
+static int wgrad_splits(const BwdCtx& x, int out_tiles) {
+  int s = 74 / (out_tiles > 0 ? out_tiles : 1);
+  if (s < 1) s = 1;
+  const int kb = x.tiles * 2;
+  if (s > kb) s = kb;
+  return s;
+}
+
+// ---- one conditioner pair (scale + shift network) of coupling layer k, backward -------------------------
+// In: b.dst[s] = gradient w.r.t. the outputs of network s.  Out: gradient of the conditioner input added to
+// dz_other and the embedding gradient; every parameter gradient of both networks accumulated.
+static int conditioner_bwd(BwdCtx& x, int k, float* dz_other, const float* z_other_in) {
+  const tw_flow_config* c = x.c;
+  const int T = c->num_transformer_layers, F = c->dim_feedforward, H = c->num_heads, hid = c->mlp_hidden_dims[0], E = c->atom_embedding_dim;
+  BwdBuffers& b = x.b;
+  const TcLayout& L = x.L;
+  const uint8_t* wbase[2] = {x.packed + L.net_offset(k, 0), x.packed + L.net_offset(k, 1)};
+
+  // ------------------------------------------------------------------ out_mlp
+  {
+    float* h3[2] = {x.tp.net[k][0].h[T], x.tp.net[k][1].h[T]};
+    TW_TRY(pack_act(x, h3, b.img_x, 128, nullptr));
+    GemmArgs g = gemm_base(x, GEMM_NT);  // pre3 = h3 W3^T + b3
+    for (int s = 0; s < 2; s++) {
+      g.A[s] = plain_img(b.img_x[s], 2);
+      g.B[s] = ImgRef{wbase[s] + L.out_w1, 16384u, (uint32_t)(2 * hid * 128), 0u, (uint32_t)(hid * 128)};
+      g.C[s] = b.wide0[s], g.bias[s] = x.pv.out_b(k, s, 0);
+    }
+    g.ldc = hid, g.rows = (int)x.M, g.cols = hid, g.tiles_m = x.tiles, g.tiles_n = hid / 128, g.KB = 2;
+    TW_TRY(launch_gemm(c, g, x.st));
+    OutLastArgs o{};
+    for (int s = 0; s < 2; s++) {
+      o.pre[s] = b.wide0[s], o.dst[s] = b.dst[s], o.w4[s] = x.pv.out_w(k, s, 1), o.img_dpre[s] = b.img_w1[s];
+      o.dw4[s] = x.gv.out_w(k, s, 1), o.db4[s] = x.gv.out_b(k, s, 1), o.db3[s] = x.gv.out_b(k, s, 0);
+    }
+    o.M = x.M, o.hid = hid, o.n_ct = hid / 64;
+    k_out_last_bwd<<<dim3(hid / 64, x.tiles, 2), 256, 0, x.st>>>(o);
+    TW_LAUNCH_CHECK();
+    GemmArgs w = gemm_base(x, GEMM_TN);  // dW3 [hid,128] += dpre3^T h3
+    for (int s = 0; s < 2; s++) w.A[s] = plain_img(b.img_w1[s], hid / 64), w.B[s] = plain_img(b.img_x[s], 2), w.C[s] = x.gv.out_w(k, s, 0);
+    w.ldc = 128, w.rows = hid, w.cols = 128, w.tiles_m = hid / 128, w.tiles_n = 1, w.KB = x.tiles * 2, w.splits = wgrad_splits(x, hid / 128);
+    TW_TRY(launch_gemm(c, w, x.st));
+    GemmArgs d = gemm_base(x, GEMM_NN);  // dh3 = dpre3 W3
+    for (int s = 0; s < 2; s++) {
+      d.A[s] = plain_img(b.img_w1[s], hid / 64);
+      d.B[s] = ImgRef{wbase[s] + L.out_w1, 16384u, (uint32_t)(2 * hid * 128), 0u, (uint32_t)(hid * 128)};
+      d.C[s] = b.dyA[s];
+    }
+    d.ldc = 128, d.rows = (int)x.M, d.cols = 128, d.tiles_m = x.tiles, d.tiles_n = 1, d.KB = hid / 64;
+    TW_TRY(launch_gemm(c, d, x.st));
+  }
+
+  // ------------------------------------------------------------------ encoder layers, last to first
+  for (int t = T - 1; t >= 0; t--) {
+    const uint8_t* eb[2] = {wbase[0] + L.enc0 + (size_t)t * L.enc_stride, wbase[1] + L.enc0 + (size_t)t * L.enc_stride};
+    // LN2 backward: dyA -> dr (+ image), dgamma2, dbeta2, db2
+    {
+      LnBwdArgs a{};
+      for (int s = 0; s < 2; s++) {
+        a.pre[s] = x.tp.net[k][s].r2[t], a.dy[s] = b.dyA[s], a.gamma[s] = x.pv.enc(k, s, t, 9), a.dr[s] = b.dr[s], a.img_dr[s] = b.img_d[s];
+        a.dgamma[s] = x.gv.enc(k, s, t, 9), a.dbeta[s] = x.gv.enc(k, s, t, 10), a.dbias[s] = x.gv.enc(k, s, t, 6);
+      }
+      a.M = x.M, a.eps = c->layer_norm_eps;
+      k_ln_bwd<<<dim3(x.tiles, 2), 256, 0, x.st>>>(a);
+      TW_LAUNCH_CHECK();
+    }
+    // FFN weight images of this layer: W1 [F,128] row tile c at c*128K (+kb*16K), lo +32K; W2 [128,F] col tile b
+    ImgRef w1[2], w2[2];
+    for (int s = 0; s < 2; s++) {
+      w1[s] = ImgRef{eb[s] + L.enc_ffn, 4u * 32768u, 16384u, 0u, 32768u};
+      w2[s] = ImgRef{eb[s] + L.enc_ffn + 2 * 32768, 0u, 16384u, 4u * 32768u, 32768u};
+    }
+    float* y1[2] = {x.tp.net[k][0].y1[t], x.tp.net[k][1].y1[t]};
+    TW_TRY(pack_act(x, y1, b.img_x, 128, nullptr));
+    {
+      GemmArgs g = gemm_base(x, GEMM_NT);  // pre = y1 W1^T + b1
+      for (int s = 0; s < 2; s++) g.A[s] = plain_img(b.img_x[s], 2), g.B[s] = w1[s], g.C[s] = b.wide0[s], g.bias[s] = x.pv.enc(k, s, t, 4);
+      g.ldc = F, g.rows = (int)x.M, g.cols = F, g.tiles_m = x.tiles, g.tiles_n = F / 128, g.KB = 2;
+      TW_TRY(launch_gemm(c, g, x.st));
+      GemmArgs d = gemm_base(x, GEMM_NN);  // dhid = dr W2
+      for (int s = 0; s < 2; s++) d.A[s] = plain_img(b.img_d[s], 2), d.B[s] = w2[s], d.C[s] = b.wide1[s];
+      d.ldc = F, d.rows = (int)x.M, d.cols = F, d.tiles_m = x.tiles, d.tiles_n = F / 128, d.KB = 2;
+      TW_TRY(launch_gemm(c, d, x.st));
+      ActBwdArgs r{};
+      for (int s = 0; s < 2; s++)
+        r.pre[s] = b.wide0[s], r.dact[s] = b.wide1[s], r.img_act[s] = b.img_w0[s], r.img_dpre[s] = b.img_w1[s], r.dbias[s] = x.gv.enc(k, s, t, 4);
+      r.M = x.M, r.C = F, r.n_ct = F / 64;
+      k_act_bwd<ACT_RELU><<<dim3(F / 64, x.tiles, 2), 256, 0, x.st>>>(r);
+      TW_LAUNCH_CHECK();
+      GemmArgs wa = gemm_base(x, GEMM_TN);  // dW2 [128,F] += dr^T hid
+      for (int s = 0; s < 2; s++) wa.A[s] = plain_img(b.img_d[s], 2), wa.B[s] = plain_img(b.img_w0[s], F / 64), wa.C[s] = x.gv.enc(k, s, t, 5);
+      wa.ldc = F, wa.rows = 128, wa.cols = F, wa.tiles_m = 1, wa.tiles_n = F / 128, wa.KB = x.tiles * 2, wa.splits = wgrad_splits(x, F / 128);
+      TW_TRY(launch_gemm(c, wa, x.st));
+      GemmArgs wb = gemm_base(x, GEMM_TN);  // dW1 [F,128] += dpre^T y1
+      for (int s = 0; s < 2; s++) wb.A[s] = plain_img(b.img_w1[s], F / 64), wb.B[s] = plain_img(b.img_x[s], 2), wb.C[s] = x.gv.enc(k, s, t, 3);
+      wb.ldc = 128, wb.rows = F, wb.cols = 128, wb.tiles_m = F / 128, wb.tiles_n = 1, wb.KB = x.tiles * 2, wb.splits = wgrad_splits(x, F / 128);
+      TW_TRY(launch_gemm(c, wb, x.st));
+      GemmArgs e = gemm_base(x, GEMM_NN);  // dy1 = dr + dpre W1
+      for (int s = 0; s < 2; s++) e.A[s] = plain_img(b.img_w1[s], F / 64), e.B[s] = w1[s], e.C[s] = b.dyB[s], e.resid[s] = b.dr[s];
+      e.ldc = 128, e.ldr = 128, e.rows = (int)x.M, e.cols = 128, e.tiles_m = x.tiles, e.tiles_n = 1, e.KB = F / 64;
+      TW_TRY(launch_gemm(c, e, x.st));
+    }
+    // LN1 backward: dyB -> dr (+ image), dgamma1, dbeta1
+    {
+      LnBwdArgs a{};
+      for (int s = 0; s < 2; s++) {
+        a.pre[s] = x.tp.net[k][s].r1[t], a.dy[s] = b.dyB[s], a.gamma[s] = x.pv.enc(k, s, t, 7), a.dr[s] = b.dr[s], a.img_dr[s] = b.img_d[s];
+        a.dgamma[s] = x.gv.enc(k, s, t, 7), a.dbeta[s] = x.gv.enc(k, s, t, 8), a.dbias[s] = nullptr;
+      }
+      a.M = x.M, a.eps = c->layer_norm_eps;
+      k_ln_bwd<<<dim3(x.tiles, 2), 256, 0, x.st>>>(a);
+      TW_LAUNCH_CHECK();
+    }
+    // attention: r1 = x + sum_h W_c,h (A_h x)
+    {
+      const size_t wc_bytes = (size_t)128 * H * 128 * sizeof(float);
+      for (int s = 0; s < 2; s++) TW_CUDA(cudaMemsetAsync(b.dwc[s], 0, wc_bytes, x.st));
+      GemmArgs w = gemm_base(x, GEMM_TN);  // dWc [128, H*128] = dr^T mixed
+      for (int s = 0; s < 2; s++) w.A[s] = plain_img(b.img_d[s], 2), w.B[s] = plain_img(x.tp.net[k][s].mixed[t], H * 2), w.C[s] = b.dwc[s];
+      w.ldc = H * 128, w.rows = 128, w.cols = H * 128, w.tiles_m = 1, w.tiles_n = H, w.KB = x.tiles * 2, w.splits = wgrad_splits(x, H);
+      TW_TRY(launch_gemm(c, w, x.st));
+      WcChainArgs ch{};
+      for (int s = 0; s < 2; s++)
+        ch.dwc[s] = b.dwc[s], ch.wo[s] = x.pv.enc(k, s, t, 2), ch.wv[s] = x.pv.enc(k, s, t, 0), ch.dwo[s] = x.gv.enc(k, s, t, 2), ch.dwv[s] = x.gv.enc(k, s, t, 0);
+      k_wc_chain<<<dim3(H, 128, 2), 128, 0, x.st>>>(ch, 128, H);
+      TW_LAUNCH_CHECK();
+      // G_h = A_h^T dr  (transposed score images), then dx = dr + sum_h G_h W_c,h
+      TW_TRY(tc_mix(c, b.dr, b.img_g, x.tp.scores_img_t, x.B, x.B, x.V, x.st));
+      GemmArgs d = gemm_base(x, GEMM_NN_HEADED);
+      for (int s = 0; s < 2; s++) {
+        d.A[s] = plain_img(b.img_g[s], H * 2);
+        d.B[s] = plain_img(eb[s] + L.enc_wc, H * 2);
+        d.C[s] = b.dyA[s], d.resid[s] = b.dr[s];
+      }
+      d.ldc = 128, d.ldr = 128, d.rows = (int)x.M, d.cols = 128, d.tiles_m = x.tiles, d.tiles_n = 1, d.KB = H * 2;
+      TW_TRY(launch_gemm(c, d, x.st));
+    }
+  }
+
+  // ------------------------------------------------------------------ in_mlp (dyA = gradient w.r.t. h0)
+  {
+    k_features_img<<<x.tiles, 256, 0, x.st>>>(x.pv.embed(), x.atom_types, x.tp.xc, x.x_velocs, z_other_in, x.M, x.V, E, c->num_atom_types, b.img_u);
+    TW_LAUNCH_CHECK();
+    ImgRef w1[2], w2[2];
+    for (int s = 0; s < 2; s++) {
+      w1[s] = ImgRef{wbase[s] + L.in_w1, 16384u, 0u, 0u, (uint32_t)(hid * 128)};  // [hid x 64]: row tile tr at tr*16K
+      w2[s] = plain_img(wbase[s] + L.in_w2, hid / 64);                            // [128 x hid]
+    }
+    GemmArgs g = gemm_base(x, GEMM_NT);  // pre1 = u W1^T + b1
+    for (int s = 0; s < 2; s++) g.A[s] = plain_img(b.img_u, 1), g.B[s] = w1[s], g.C[s] = b.wide0[s], g.bias[s] = x.pv.in_b(k, s, 0);
+    g.ldc = hid, g.rows = (int)x.M, g.cols = hid, g.tiles_m = x.tiles, g.tiles_n = hid / 128, g.KB = 1;
+    TW_TRY(launch_gemm(c, g, x.st));
+    float* db2[2] = {x.gv.in_b(k, 0, 1), x.gv.in_b(k, 1, 1)};
+    TW_TRY(pack_act(x, b.dyA, b.img_d, 128, db2));
+    GemmArgs d = gemm_base(x, GEMM_NN);  // dact1 = dh0 W2
+    for (int s = 0; s < 2; s++) d.A[s] = plain_img(b.img_d[s], 2), d.B[s] = w2[s], d.C[s] = b.wide1[s];
+    d.ldc = hid, d.rows = (int)x.M, d.cols = hid, d.tiles_m = x.tiles, d.tiles_n = hid / 128, d.KB = 2;
+    TW_TRY(launch_gemm(c, d, x.st));
+    ActBwdArgs r{};
+    for (int s = 0; s < 2; s++)
+      r.pre[s] = b.wide0[s], r.dact[s] = b.wide1[s], r.img_act[s] = b.img_w0[s], r.img_dpre[s] = b.img_w1[s], r.dbias[s] = x.gv.in_b(k, s, 0);
+    r.M = x.M, r.C = hid, r.n_ct = hid / 64;
+    k_act_bwd<ACT_SILU><<<dim3(hid / 64, x.tiles, 2), 256, 0, x.st>>>(r);
+    TW_LAUNCH_CHECK();
+    GemmArgs wa = gemm_base(x, GEMM_TN);  // dW2 [128,hid] += dh0^T act1
+    for (int s = 0; s < 2; s++) wa.A[s] = plain_img(b.img_d[s], 2), wa.B[s] = plain_img(b.img_w0[s], hid / 64), wa.C[s] = x.gv.in_w(k, s, 1);
+    wa.ldc = hid, wa.rows = 128, wa.cols = hid, wa.tiles_m = 1, wa.tiles_n = hid / 128, wa.KB = x.tiles * 2, wa.splits = wgrad_splits(x, hid / 128);
+    TW_TRY(launch_gemm(c, wa, x.st));
+    GemmArgs wb = gemm_base(x, GEMM_TN);  // dW1 [hid, E+9] += dpre1^T u
+    for (int s = 0; s < 2; s++) wb.A[s] = plain_img(b.img_w1[s], hid / 64), wb.B[s] = plain_img(b.img_u, 1), wb.C[s] = x.gv.in_w(k, s, 0);
+    wb.bn = 64, wb.ldc = E + 9, wb.rows = hid, wb.cols = E + 9, wb.tiles_m = hid / 128, wb.tiles_n = 1, wb.KB = x.tiles * 2, wb.splits = wgrad_splits(x, hid / 128);
+    TW_TRY(launch_gemm(c, wb, x.st));
+    GemmArgs e = gemm_base(x, GEMM_NN);  // du = dpre1 W1  [M,64]
+    for (int s = 0; s < 2; s++) e.A[s] = plain_img(b.img_w1[s], hid / 64), e.B[s] = w1[s], e.C[s] = b.du[s];
+    e.bn = 64, e.ldc = 64, e.rows = (int)x.M, e.cols = 64, e.tiles_m = x.tiles, e.tiles_n = 1, e.KB = hid / 64;
+    TW_TRY(launch_gemm(c, e, x.st));
+    k_du_scatter<<<x.tiles, 256, c->num_atom_types * E * sizeof(float), x.st>>>(b.du[0], b.du[1], x.atom_types, x.M, E, c->num_atom_types,
+                                                                             dz_other, x.gv.embed());
+    TW_LAUNCH_CHECK();
+  }
+  return TW_OK;
+}
+
+}  // namespace tw
+
+using namespace tw;
+
+extern "C" {
+
+// Debug / test hook: one generic image GEMM on fp32 row-major inputs (packed to operand images first).
+//   mode 0 NT: C[ar,br] = A B^T   1 NN: C[ar,bc] = A B   2 headed NN: C[ar,128] = sum_h A[:,h] B[:,h]   3 TN: C[ac,bc] += A^T B
+int tw_debug_gemm(int mode, int precision, const float* A, int a_rows, int a_cols, const float* B, int b_rows, int b_cols, float* C,
+                  int bn, int splits, void* workspace, size_t workspace_bytes, void* stream) {
+  TW_CHECK_ARG(A && B && C && workspace, "NULL pointer");
+  TW_CHECK_ARG(a_cols % 64 == 0 && b_cols % 64 == 0, "columns must be multiples of 64");
+  TW_CHECK_ARG(precision == TW_PRECISION_BF16X3 || precision == TW_PRECISION_BF16, "tensor-core precisions only");
+  tw_flow_config cfg{};
+  cfg.precision = precision;
+  cudaStream_t st = (cudaStream_t)stream;
+  Arena ar(workspace, workspace_bytes);
+  ar.off = align_up(ar.off, 1024);
+  uint8_t* ia = ar.take<uint8_t>(plain_img_bytes(a_rows, a_cols / 64));
+  ar.off = align_up(ar.off, 1024);
+  uint8_t* ib = ar.take<uint8_t>(plain_img_bytes(b_rows, b_cols / 64));
+  if (!ar.ok()) return fail(TW_ERR_WORKSPACE, "workspace %zu < %zu", workspace_bytes, ar.off);
+  for (int which = 0; which < 2; which++) {
+    PackArgs p{};
+    p.X[0] = which ? B : A, p.img[0] = which ? ib : ia;
+    p.M = which ? b_rows : a_rows, p.C = which ? b_cols : a_cols, p.ld = p.C, p.n_ct = p.C / 64;
+    k_pack_act<<<dim3(p.n_ct, (unsigned)((p.M + 127) / 128), 1), 256, 0, st>>>(p);
+    TW_LAUNCH_CHECK();
+  }
+  GemmArgs g{};
+  g.mode = mode, g.bn = bn, g.splits = splits, g.nets = 1;
+  g.A[0] = plain_img(ia, a_cols / 64), g.B[0] = plain_img(ib, b_cols / 64), g.C[0] = C;
+  const int tiles_a = (a_rows + 127) / 128;
+  if (mode == GEMM_NT) {
+    TW_CHECK_ARG(a_cols == b_cols, "NT: inner dimensions differ");
+    g.rows = a_rows, g.cols = b_rows, g.ldc = b_rows, g.tiles_m = tiles_a, g.tiles_n = (b_rows + bn - 1) / bn, g.KB = a_cols / 64;
+  } else if (mode == GEMM_NN) {
+    TW_CHECK_ARG(a_cols == b_rows, "NN: inner dimensions differ");
+    g.rows = a_rows, g.cols = b_cols, g.ldc = b_cols, g.tiles_m = tiles_a, g.tiles_n = b_cols / bn, g.KB = a_cols / 64;
+  } else if (mode == GEMM_NN_HEADED) {
+    TW_CHECK_ARG(a_cols == b_cols && b_rows == 128, "headed: A [M,H*128], B [128,H*128]");
+    g.rows = a_rows, g.cols = 128, g.ldc = 128, g.tiles_m = tiles_a, g.tiles_n = 1, g.KB = a_cols / 64;
+  } else {
+    TW_CHECK_ARG(a_rows == b_rows && a_cols % 128 == 0, "TN: token counts differ / A columns not a multiple of 128");
+    g.rows = a_cols, g.cols = b_cols, g.ldc = b_cols, g.tiles_m = a_cols / 128, g.tiles_n = b_cols / bn, g.KB = tiles_a * 2;
+  }
+  return launch_gemm(&cfg, g, st);
+}
+
+int tw_flow_train_bytes(const tw_flow_config* cfg, int64_t B, int64_t V, size_t* tape_bytes, size_t* workspace_bytes) {
+  void* dummy = (void*)cfg;
+  TW_TRY(check_train(cfg, &dummy, B, V));
+  if (tape_bytes) *tape_bytes = carve_tape(cfg, B, (int)V, nullptr, 0, nullptr) + 1024;
+  if (workspace_bytes) *workspace_bytes = carve_bwd(cfg, B, (int)V, nullptr, 0, nullptr) + 1024;
+  return TW_OK;
+}
+
+int tw_flow_log_likelihood_train(const tw_flow_config* cfg, const void* const* params, const int64_t* atom_types,
+                                 const float* x_coords, const float* x_velocs, const float* y_coords, const float* y_velocs,
+                                 const uint8_t* mask, int64_t B, int64_t V, int32_t flags, float* out_log_prob,
+                                 const void* packed_weights, void* tape, size_t tape_bytes, void* stream) {
+  TW_TRY(check_train(cfg, params, B, V));
+  if (B == 0) return TW_OK;
+  TW_CHECK_ARG(atom_types && x_coords && x_velocs && y_coords && y_velocs && mask && out_log_prob, "NULL pointer");
+  TW_CHECK_ARG(packed_weights && ((uintptr_t)packed_weights & 1023) == 0, "packed_weights missing or not 1024-byte aligned");
+  TW_CHECK_ARG(tape && ((uintptr_t)tape & 1023) == 0, "tape missing or not 1024-byte aligned");
+  Tape tp;
+  const size_t need = carve_tape(cfg, B, (int)V, tape, tape_bytes, &tp);
+  if (need > tape_bytes) return fail(TW_ERR_WORKSPACE, "tape %zu < %zu", tape_bytes, need);
+  cudaStream_t st = (cudaStream_t)stream;
+  ParamView pv{cfg, params};
+  const int L = cfg->num_coupling_layers, T = cfg->num_transformer_layers;
+  const int64_t M = B * V, cnt = M * 3;
+  TW_TRY(launch_prep(x_coords, mask, B, (int)V, tp.xc, tp.com, st));
+  TW_TRY(launch_scores(tp.xc, mask, pv.enc(0, 0, 0, 1), B, (int)V, cfg->num_heads, tp.scores, st));
+  TW_TRY(tc_scores_images(cfg, tp.scores, B, (int)V, tp.scores_img, 0, st));
+  TW_TRY(tc_scores_images(cfg, tp.scores, B, (int)V, tp.scores_img_t, 1, st));
+  if (flags & TW_FLOW_DISPLACEMENT_TARGET)
+    TW_TRY(launch_sub(y_coords, x_coords, cnt, tp.z[0][0], st));
+  else
+    TW_CUDA(cudaMemcpyAsync(tp.z[0][0], y_coords, cnt * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  TW_CUDA(cudaMemcpyAsync(tp.z[0][1], y_velocs, cnt * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  TW_CUDA(cudaMemsetAsync(tp.delta, 0, B * sizeof(float), st));
+  for (int k = 0; k < L; k++) {
+    const bool pos = (k % 2) == cfg->position_layer_index_mod_2;
+    TcScratch tc{};
+    tc.packed = (const uint8_t*)packed_weights;
+    tc.scores_img = tp.scores_img;
+    float* h0[2] = {tp.net[k][0].h[0], tp.net[k][1].h[0]};
+    TW_TRY(tc_in_mlp(cfg, pv, k, tc, atom_types, tp.xc, x_velocs, pos ? tp.z[k][1] : tp.z[k][0], h0, B, B, (int)V, st));
+    for (int t = 0; t < T; t++) {
+      float* hin[2] = {tp.net[k][0].h[t], tp.net[k][1].h[t]};
+      float* y1[2] = {tp.net[k][0].y1[t], tp.net[k][1].y1[t]};
+      float* r1[2] = {tp.net[k][0].r1[t], tp.net[k][1].r1[t]};
+      float* r2[2] = {tp.net[k][0].r2[t], tp.net[k][1].r2[t]};
+      float* hout[2] = {tp.net[k][0].h[t + 1], tp.net[k][1].h[t + 1]};
+      tc.mixed_img[0] = tp.net[k][0].mixed[t], tc.mixed_img[1] = tp.net[k][1].mixed[t];
+      if (M % 128) {  // rows past the last token of the tail tile are read by the weight-gradient GEMM: keep them zero
+        const size_t tile_bytes = tc_mixed_img_bytes(cfg, 128);
+        for (int s = 0; s < 2; s++) TW_CUDA(cudaMemsetAsync(tc.mixed_img[s] + (size_t)(M / 128) * tile_bytes, 0, tile_bytes, st));
+      }
+      TW_TRY(tc_attention_layer(cfg, pv, k, t, tc, hin, y1, B, B, (int)V, st, r1));
+      TW_TRY(tc_ffn_layer(cfg, pv, k, t, tc, y1, hout, M, st, r2));
+    }
+    float* hl[2] = {tp.net[k][0].h[T], tp.net[k][1].h[T]};
+    float* so[2] = {tp.net[k][0].st, tp.net[k][1].st};
+    TW_TRY(tc_out_mlp(cfg, pv, k, tc, hl, so, M, st));
+    // next state: copy both halves, then transform the target half in place
+    TW_CUDA(cudaMemcpyAsync(tp.z[k + 1][0], tp.z[k][0], cnt * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    TW_CUDA(cudaMemcpyAsync(tp.z[k + 1][1], tp.z[k][1], cnt * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    TW_TRY(launch_coupling(so[0], so[1], pos ? tp.z[k + 1][0] : tp.z[k + 1][1], mask, tp.delta, B, B, (int)V, 0, nullptr, nullptr, st));
+  }
+  TW_TRY(launch_prior(tp.z[L][0], tp.z[L][1], mask, pv.log_scale_c(), pv.log_scale_v(), tp.delta, -1.f, B, B, (int)V, out_log_prob, st));
+  return TW_OK;
+}
+
+int tw_flow_log_likelihood_backward(const tw_flow_config* cfg, const void* const* params, void* const* grads,
+                                    const int64_t* atom_types, const float* x_velocs, const uint8_t* mask, int64_t B, int64_t V,
+                                    const float* grad_log_prob, const void* packed_weights, void* tape, size_t tape_bytes,
+                                    void* workspace, size_t workspace_bytes, void* stream) {
+  TW_TRY(check_train(cfg, params, B, V));
+  if (B == 0) return TW_OK;
+  TW_CHECK_ARG(grads && atom_types && x_velocs && mask && grad_log_prob, "NULL pointer");
+  TW_CHECK_ARG(packed_weights && ((uintptr_t)packed_weights & 1023) == 0, "packed_weights missing or not 1024-byte aligned");
+  TW_CHECK_ARG(tape && ((uintptr_t)tape & 1023) == 0 && workspace && ((uintptr_t)workspace & 1023) == 0, "tape / workspace missing or not 1024-byte aligned");
+  BwdCtx x{};
+  x.c = cfg;
+  x.pv = ParamView{cfg, params};
+  x.gv = GradView{ParamView{cfg, nullptr}, grads};
+  for (int i = 0; i < x.pv.total(); i++) {
+    const bool is_ls = i >= 3 && ((i - 3) % x.pv.per_net()) >= x.pv.per_mlp() && ((i - 3) % x.pv.per_net()) < x.pv.per_mlp() + 11 * cfg->num_transformer_layers &&
+                       (((i - 3) % x.pv.per_net()) - x.pv.per_mlp()) % 11 == 1;
+    TW_CHECK_ARG(is_ls || i == 1 || i == 2 || grads[i] != nullptr, "gradient table entry %d is NULL", i);
+  }
+  x.L = TcLayout::make(cfg);
+  x.packed = (const uint8_t*)packed_weights;
+  size_t need = carve_tape(cfg, B, (int)V, tape, tape_bytes, &x.tp);
+  if (need > tape_bytes) return fail(TW_ERR_WORKSPACE, "tape %zu < %zu", tape_bytes, need);
+  need = carve_bwd(cfg, B, (int)V, workspace, workspace_bytes, &x.b);
+  if (need > workspace_bytes) return fail(TW_ERR_WORKSPACE, "workspace %zu < %zu", workspace_bytes, need);
+  x.atom_types = atom_types, x.x_velocs = x_velocs, x.mask = mask;
+  x.B = B, x.V = (int)V, x.M = B * V, x.tiles = (int)((x.M + 127) / 128);
+  x.st = (cudaStream_t)stream;
+  const int L = cfg->num_coupling_layers;
+  k_prior_bwd<<<(unsigned)B, 128, 0, x.st>>>(x.tp.z[L][0], x.tp.z[L][1], mask, x.pv.log_scale_c(), x.pv.log_scale_v(), grad_log_prob, (int)V,
+                                            x.b.dz[0], x.b.dz[1], x.gv.log_scale_c(), x.gv.log_scale_v());
+  TW_LAUNCH_CHECK();
+  for (int k = L - 1; k >= 0; k--) {
+    const bool pos = (k % 2) == cfg->position_layer_index_mod_2;
+    const int tgt = pos ? 0 : 1, oth = 1 - tgt;
+    k_coupling_bwd<<<(unsigned)B, 128, 0, x.st>>>(x.tp.net[k][0].st, x.tp.z[k][tgt], x.b.dz[tgt], mask, grad_log_prob, (int)V, x.b.dst[0], x.b.dst[1]);
+    TW_LAUNCH_CHECK();
+    TW_TRY(conditioner_bwd(x, k, x.b.dz[oth], x.tp.z[k][oth]));
+  }
+  return TW_OK;
+}
+
+}  // extern "C"

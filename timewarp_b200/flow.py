@@ -29,6 +29,87 @@ def _require_cuda(name: str, t: Tensor, dtype=None) -> Tensor:
     return t.contiguous()
 
 
+def _aligned(buf: Tensor) -> int:
+    return (buf.data_ptr() + 1023) // 1024 * 1024
+
+
+class _LogLikelihoodFn(torch.autograd.Function):
+    """log p(y|x) with a hand-written backward: the forward records a tape in device memory
+    (tw_flow_log_likelihood_train), the backward accumulates the gradient of every trainable
+    parameter (tw_flow_log_likelihood_backward).  The parameters are passed as inputs so that
+    autograd routes the gradients to them; coordinates get no gradient (NLL training, losses.py:321-356)."""
+
+    @staticmethod
+    def forward(ctx, model, atom_types, x_coords, x_velocs, y_coords, y_velocs, mask_u8, *params):
+        lib = _lib.load()
+        dev = x_coords.device
+        B, V = x_coords.shape[0], x_coords.shape[1]
+        cfg = model._cfg
+        tape_b, ws_b = C.c_size_t(0), C.c_size_t(0)
+        _lib.check(lib.tw_flow_train_bytes(C.byref(cfg), B, V, C.byref(tape_b), C.byref(ws_b)), "tw_flow_train_bytes")
+        tape = torch.empty(tape_b.value + 1024, dtype=torch.uint8, device=dev)
+        out = torch.empty(B, dtype=torch.float32, device=dev)
+        table = model._param_table(dev)
+        packed = model._packed_weights(dev)
+        _lib.check(
+            lib.tw_flow_log_likelihood_train(
+                C.byref(cfg), table, _lib.ptr(atom_types), _lib.ptr(x_coords), _lib.ptr(x_velocs), _lib.ptr(y_coords),
+                _lib.ptr(y_velocs), _lib.ptr(mask_u8), B, V, model._flags(), _lib.ptr(out), packed, _aligned(tape),
+                tape_b.value, model._stream(dev),
+            ),
+            "tw_flow_log_likelihood_train",
+        )  # fmt: skip
+        ctx.model, ctx.tape, ctx.sizes = model, tape, (B, V, tape_b.value, ws_b.value)
+        ctx.packed_key = model._packed[2]
+        ctx.save_for_backward(atom_types, x_velocs, mask_u8)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        lib = _lib.load()
+        model = ctx.model
+        atom_types, x_velocs, mask_u8 = ctx.saved_tensors
+        dev = x_velocs.device
+        B, V, tape_b, ws_b = ctx.sizes
+        if model._packed is None or model._packed[2] != ctx.packed_key:
+            raise _lib.TimewarpB200Error("parameters were modified between the forward and the backward pass")
+        tensors = model._ordered_params()
+        grads = [torch.zeros_like(t) if (t.requires_grad and t.is_floating_point()) else None for t in tensors]
+        table = model._param_table(dev)
+        gtable = (C.c_void_p * len(tensors))(*[(g.data_ptr() if g is not None else None) for g in grads])
+        # frozen parameters other than the lengthscale buffers / prior scales still need scratch to accumulate into
+        scratch = []
+        for i, (t, g) in enumerate(zip(tensors, grads)):
+            if g is None and t.is_floating_point() and not _is_optional_grad(model, i):
+                z = torch.zeros_like(t)
+                scratch.append(z)
+                gtable[i] = z.data_ptr()
+        ws = torch.empty(ws_b + 1024, dtype=torch.uint8, device=dev)
+        g_in = grad_out.to(torch.float32).contiguous()
+        _lib.check(
+            lib.tw_flow_log_likelihood_backward(
+                C.byref(model._cfg), table, gtable, _lib.ptr(atom_types), _lib.ptr(x_velocs), _lib.ptr(mask_u8), B, V,
+                _lib.ptr(g_in), model._packed[1], _aligned(ctx.tape), tape_b, _aligned(ws), ws_b, model._stream(dev),
+            ),
+            "tw_flow_log_likelihood_backward",
+        )  # fmt: skip
+        ctx.tape = None
+        return (None,) * 7 + tuple(grads)
+
+
+def _is_optional_grad(model, i: int) -> bool:
+    """Entries of the gradient table that may be NULL: prior log-scales and the lengthscale buffers."""
+    if i in (1, 2):
+        return True
+    if i < 3:
+        return False
+    cfg = model._cfg
+    per_mlp = 2 * (cfg.num_mlp_hidden + 1)
+    per_net = 2 * per_mlp + 11 * cfg.num_transformer_layers
+    j = (i - 3) % per_net
+    return per_mlp <= j < per_mlp + 11 * cfg.num_transformer_layers and (j - per_mlp) % 11 == 1
+
+
 class ConditionalFlowDensityModel(nn.Module):
     def __init__(
         self,
@@ -193,12 +274,16 @@ class ConditionalFlowDensityModel(nn.Module):
         if self.ignore_conditional_velocity:  # flow.py:144-145
             x_velocs = torch.zeros_like(x_velocs)
         lib = _lib.load()
+        mask_u8 = mask.view(torch.uint8)
+        if torch.is_grad_enabled() and not want_latent and any(p.requires_grad for p in self.parameters()):
+            # training: hand-written backward (tensor-core precisions; raises TW_ERR_UNSUPPORTED otherwise)
+            out = _LogLikelihoodFn.apply(self, atom_types, x_coords, x_velocs, y_coords, y_velocs, mask_u8, *self._ordered_params())
+            return out, None, None
         table = self._param_table(dev)
         ws, ws_bytes = self._get_workspace(B, B, V, dev)
         out = torch.empty(B, dtype=torch.float32, device=dev)
         zc = torch.empty_like(x_coords) if want_latent else None
         zv = torch.empty_like(x_coords) if want_latent else None
-        mask_u8 = mask.view(torch.uint8)
         _lib.check(
             lib.tw_flow_log_likelihood(
                 C.byref(self._cfg), table, _lib.ptr(atom_types), _lib.ptr(x_coords), _lib.ptr(x_velocs), _lib.ptr(y_coords),
