@@ -212,6 +212,14 @@ class ConditionalFlowDensityModel(nn.Module):
             self._workspace = torch.empty(need.value, dtype=torch.uint8, device=device)
         return self._workspace, self._workspace.numel()
 
+    def _train_supported(self, B: int, V: int) -> bool:
+        """True when the library has backward kernels for this configuration (tensor-core precision and the
+        flagship layer sizes): tw_flow_train_bytes answers TW_ERR_UNSUPPORTED otherwise."""
+        if self._cfg.precision == _lib.PRECISION["fp32"]:
+            return False
+        a, b = C.c_size_t(0), C.c_size_t(0)
+        return _lib.load().tw_flow_train_bytes(C.byref(self._cfg), B, V, C.byref(a), C.byref(b)) == _lib.TW_OK
+
     @staticmethod
     def _stream(device) -> int:
         return torch.cuda.current_stream(device).cuda_stream
@@ -275,8 +283,11 @@ class ConditionalFlowDensityModel(nn.Module):
             x_velocs = torch.zeros_like(x_velocs)
         lib = _lib.load()
         mask_u8 = mask.view(torch.uint8)
-        if torch.is_grad_enabled() and not want_latent and any(p.requires_grad for p in self.parameters()):
-            # training: hand-written backward (tensor-core precisions; raises TW_ERR_UNSUPPORTED otherwise)
+        trainable = torch.is_grad_enabled() and not want_latent and any(p.requires_grad for p in self.parameters())
+        if trainable and (self.training or self._train_supported(B, V)):
+            # hand-written backward (tensor-core precisions, flagship layer sizes).  Configurations without backward
+            # kernels raise TW_ERR_UNSUPPORTED in .train() mode; in .eval() mode they take the inference path and the
+            # result carries no grad_fn (so .backward() on it fails in autograd).
             out = _LogLikelihoodFn.apply(self, atom_types, x_coords, x_velocs, y_coords, y_velocs, mask_u8, *self._ordered_params())
             return out, None, None
         table = self._param_table(dev)

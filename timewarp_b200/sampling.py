@@ -139,6 +139,7 @@ class MHChains:
         self._empty_adj = torch.zeros(0, 2, dtype=torch.long, device=dev)
         self._empty_ebi = torch.zeros(0, dtype=torch.long, device=dev)
 
+    @torch.no_grad()  # the reference samples under no_grad (evaluation_utils.py:468)
     def step(self):
         m = self.model
         if self.random_velocs and self.resample_velocs:
