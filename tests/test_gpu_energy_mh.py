@@ -211,3 +211,61 @@ def test_explore_rule():
     assert ((e[0] - e0) <= 300.0 + 1e-3).all() and ((e[1:] - e[:-1]) <= 300.0 + 1e-3).all()
     # stored energies are the energies of the stored positions
     torch.testing.assert_close(energy(pos).squeeze(-1), en, rtol=1e-5, atol=2e-2)
+
+
+@pytest.mark.parametrize("random_velocs", [True, False])
+def test_sample_on_batches_against_oracle(random_velocs):
+    """utils/evaluation_utils.py:190-353 on three B=1 dataset pairs: shapes of the 11-tuple, and every log-density /
+    acceptance probability against the CPU oracles on the replayed RNG stream."""
+    pep = alanine_dipeptide()
+    m, sd = build_model(TINY_O, "fp32", 0)
+    sysd = amber_like_system(pep)
+    energy = PeptidePotentialEnergy(sysd)
+    masses = torch.tensor(pep.masses, dtype=torch.float32)
+    g = torch.Generator().manual_seed(5)
+    batches = []
+    for _ in range(3):
+        b = _Batch(pep, "cuda")
+        b.atom_coords = b.atom_coords + 0.01 * torch.randn(1, 22, 3, generator=g)
+        b.atom_velocs = torch.randn(1, 22, 3, generator=g)
+        b.atom_coord_targets = b.atom_coords + 0.02 * torch.randn(1, 22, 3, generator=g)
+        b.atom_veloc_targets = torch.randn(1, 22, 3, generator=g)
+        batches.append(b)
+    torch.manual_seed(21)
+    out = sampling.sample_on_batches(batches, m, torch.device("cuda"), energy, False, masses, random_velocs=random_velocs)
+    y_c, y_v, t_c, t_v, c_c, c_v, ll_rev, ll_fwd, ll_rev_tr, ll_fwd_tr, acc = out
+    for a in (y_c, y_v, t_c, t_v, c_c, c_v):
+        assert a.shape == (3, 22, 3)
+    for a in (ll_rev, ll_fwd, ll_rev_tr, ll_fwd_tr, acc):
+        assert a.shape == (3, 1)
+    # replay
+    torch.manual_seed(21)
+    kbT = energy.kbT
+    sgn = 1.0 if random_velocs else -1.0
+    for i, b in enumerate(batches):
+        x = b.atom_coords
+        if random_velocs:
+            xv = torch.randn(1, 22, 3, device="cuda").cpu()
+            tv = torch.randn(1, 22, 3, device="cuda").cpu()
+        else:
+            xv, tv = b.atom_velocs, b.atom_veloc_targets
+        zc = (torch.empty(1, 1, 22, 3, device="cuda").normal_() * torch.exp(m.coords_prior_log_scale.detach())).cpu()
+        zv = (torch.empty(1, 1, 22, 3, device="cuda").normal_() * torch.exp(m.velocs_prior_log_scale.detach())).cpu()
+        at, mask = b.atom_types, b.masked_elements
+        yc, yv, p_xy = fo.conditional_sample_with_logp(sd, TINY_O, at, x, xv, mask, 1, zc, zv, distance_mode="direct")
+        yc, yv = yc[0], yv[0]
+        np.testing.assert_allclose(y_c[i], yc[0].numpy(), rtol=1e-4, atol=1e-5)
+        np.testing.assert_allclose(c_v[i], xv[0].numpy(), rtol=0, atol=0)
+        p_yx = fo.log_likelihood(sd, TINY_O, at, yc, sgn * yv, x, sgn * xv, mask, distance_mode="direct")
+        p_xy_tr = fo.log_likelihood(sd, TINY_O, at, x, xv, b.atom_coord_targets, tv, mask, distance_mode="direct")
+        p_yx_tr = fo.log_likelihood(sd, TINY_O, at, b.atom_coord_targets, sgn * tv, x, sgn * xv, mask, distance_mode="direct")
+        for got, ref in ((ll_fwd[i], p_xy[0]), (ll_rev[i], p_yx), (ll_fwd_tr[i], p_xy_tr), (ll_rev_tr[i], p_yx_tr)):
+            np.testing.assert_allclose(got, ref.numpy(), rtol=1e-4, atol=1e-4)
+        s32 = sysd.as_float32()
+        e_pot = (eo.potential_energy(s32, yc.numpy().astype(np.float64)) - eo.potential_energy(s32, x.numpy().astype(np.float64))) / kbT
+        ke = lambda v: (0.5 * (v**2).sum((-1, -2)) if random_velocs else 0.5 * (masses * (v**2).sum(-1)).sum(-1) / kbT)  # noqa: E731
+        ex = torch.from_numpy(e_pot).float() + ke(yv) - ke(xv) + p_xy[0] - p_yx
+        p_ref = torch.clamp(torch.exp(-ex), max=1.0).numpy()
+        np.testing.assert_allclose(acc[i], p_ref, rtol=5e-2, atol=1e-6)
+    with pytest.raises(NotImplementedError):
+        sampling.sample_on_batches(batches, m, torch.device("cuda"), energy, True, masses)

@@ -5,6 +5,7 @@
   names, same return tuple `(sampled_coords, sampled_velocs, accepted, ChainStats)`.
 * `MHChains`           -- B independent chains, one proposal per chain per step, everything on the
   device (no host sync in the loop; the BASELINE "1024 parallel chains" workload).
+* `sample_on_batches`  -- one-step acceptance on dataset pairs (utils/evaluation_utils.py:190-353).
 * `explore`            -- exploration.py:124-138,229-250: energy-threshold acceptance + chirality veto.
 
 The OpenMM-integrator options of the reference (`openmm_on_current/proposal`, `sim`) are not
@@ -278,6 +279,56 @@ def sample_with_model(batch, model, device, openmm_potential_energy_torch, masse
         stats["energies_kin_delta"].append((e_kin_y - e_kin_x).cpu().numpy()[:k])
     chain_stats = ChainStats(**{k: np.concatenate(v, axis=0) for k, v in stats.items()})
     return np.concatenate(sampled_coords, axis=0), np.concatenate(sampled_velocs, axis=0), accepted, chain_stats
+
+
+@torch.no_grad()
+def sample_on_batches(batches, model, device, openmm_potential_energy_torch, data_augmentation, masses, random_velocs=False):
+    """One-step acceptance statistics on dataset pairs -- utils/evaluation_utils.py:190-353 (called from
+    evaluate.py:355-375).  Per batch: 1x conditional_sample(S=1) + 4x log_likelihood (p_xy, p_yx of the model's own
+    sample, and both on the training target, :241-311) + the energies of x and y (:267-269).  Same argument names,
+    same draws from the device generator in the same order, same 11-tuple of numpy arrays.  `batch` needs the
+    DenseMolDynBatch attributes used at :229-252 (atom_types, atom_coords, atom_velocs, atom_coord_targets,
+    atom_veloc_targets, adj_list, edge_batch_idx, masked_elements)."""
+    if data_augmentation:
+        raise NotImplementedError("data_augmentation needs the reference's transform_batch (random rotations, equivariance/: out of scope)")
+    energy = openmm_potential_energy_torch
+    masses = masses.to(device) if masses is not None else None
+    cols = {k: [] for k in ("y_c", "y_v", "t_c", "t_v", "c_c", "c_v", "acc", "p_xy", "p_yx", "p_xy_tr", "p_yx_tr", "e_pot", "e_kin")}
+    for batch in batches:
+        x_coords = batch.atom_coords.to(device).to(torch.float32).contiguous()  # :229
+        y_coord_targets = batch.atom_coord_targets.to(device).to(torch.float32).contiguous()
+        if random_velocs:  # :232-234
+            x_velocs = torch.randn_like(x_coords)
+            y_veloc_targets = torch.randn_like(y_coord_targets)
+        else:
+            x_velocs = batch.atom_velocs.to(device).to(torch.float32).contiguous()
+            y_veloc_targets = batch.atom_veloc_targets.to(device).to(torch.float32).contiguous()
+        kw = dict(atom_types=batch.atom_types.to(device), adj_list=batch.adj_list.to(device),
+                  edge_batch_idx=batch.edge_batch_idx.to(device), masked_elements=batch.masked_elements.to(device))
+        y_coords, y_velocs = model.conditional_sample(x_coords=x_coords, x_velocs=x_velocs, num_samples=1, **kw)  # :239-247
+        y_coords, y_velocs = y_coords.squeeze(0), y_velocs.squeeze(0)
+        p_xy = model.log_likelihood(x_coords=x_coords, x_velocs=x_velocs, y_coords=y_coords, y_velocs=y_velocs, **kw)  # :250-259
+        kbT = energy.kbT
+        e_kin = (compute_kinetic_energy(y_velocs, masses, random_velocs=random_velocs, kbT=kbT)
+                 - compute_kinetic_energy(x_velocs, masses, random_velocs=random_velocs, kbT=kbT))  # :262-264
+        e_pot = ((energy(y_coords) - energy(x_coords)) / kbT).view(-1)  # :265-268
+        sgn = 1.0 if random_velocs else -1.0
+        p_yx = model.log_likelihood(y_coords=x_coords, y_velocs=sgn * x_velocs, x_coords=y_coords, x_velocs=sgn * y_velocs, **kw)  # :272-281
+        exp_ = e_pot + e_kin + p_xy - p_yx  # :285
+        p_acc = torch.clamp(torch.exp(-exp_), max=1.0)  # :286  (NaN exponent -> NaN, like torch.min)
+        p_acc = torch.where(torch.isnan(exp_), exp_, p_acc)
+        p_xy_tr = model.log_likelihood(x_coords=x_coords, x_velocs=x_velocs, y_coords=y_coord_targets, y_velocs=y_veloc_targets, **kw)  # :289-298
+        p_yx_tr = model.log_likelihood(x_coords=y_coord_targets, x_velocs=sgn * y_veloc_targets, y_coords=x_coords,
+                                       y_velocs=sgn * x_velocs, **kw)  # :300-309
+        for k, t in (("acc", p_acc), ("p_xy", p_xy), ("p_yx", p_yx), ("p_xy_tr", p_xy_tr), ("p_yx_tr", p_yx_tr), ("e_pot", e_pot),
+                     ("e_kin", e_kin), ("y_c", y_coords), ("y_v", y_velocs), ("c_c", x_coords), ("c_v", x_velocs)):
+            cols[k].append(t.cpu().numpy())
+        cols["t_c"].append(batch.atom_coord_targets.cpu().numpy())
+        cols["t_v"].append(batch.atom_veloc_targets.cpu().numpy())
+    arr = {k: np.array(v) for k, v in cols.items()}
+    sq = lambda a: a.squeeze(1)  # noqa: E731  (:341-346: batches of one datapoint)
+    return (sq(arr["y_c"]), sq(arr["y_v"]), sq(arr["t_c"]), sq(arr["t_v"]), sq(arr["c_c"]), sq(arr["c_v"]), arr["p_yx"], arr["p_xy"],
+            arr["p_yx_tr"], arr["p_xy_tr"], arr["acc"])
 
 
 @torch.no_grad()
