@@ -236,6 +236,9 @@ int tw_debug_umma_probe(const float* A, const float* B, float* out, int N, int K
 
 /* Debug: issue/complete cycle counts of n_mma back-to-back M128xNxK16 MMAs (out[0] issue, out[1] done). */
 int tw_debug_umma_timing(int n_mma, int N, int ts, int b_noswizzle, long long* out, void* stream);
+/* Debug: device buffer of 3*1024*2 + 8 int64 that CTA (0,0) of every following fused-FFN launch fills with
+ * {event | item << 8, clock64} records per warp role (0 MMA issuer, 1/2 epilogue groups); NULL disables. */
+int tw_debug_set_ffn_trace(long long* device_buf);
 
 #ifdef __cplusplus
 }

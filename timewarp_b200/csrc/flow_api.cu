@@ -327,4 +327,9 @@ int tw_flow_sample(const tw_flow_config* cfg, const void* const* params, const i
   return TW_OK;
 }
 
+int tw_debug_set_ffn_trace(long long* device_buf) {
+  tc_set_ffn_trace(device_buf);
+  return TW_OK;
+}
+
 }  // extern "C"

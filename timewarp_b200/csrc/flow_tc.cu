@@ -201,18 +201,27 @@ __device__ __forceinline__ void ln_store_row(float (&v)[128], const float* __res
 // ============================================================================================
 // Fused FFN:  out = LayerNorm(x + W2 relu(W1 x + b1) + b2)         custom_attention_encoder.py:111-113
 //
-// Persistent CTAs (grid.x per network, grid.y = network), 128-token tiles.  Warp roles:
-//   warp 0  : bulk-copy producer -- streams 32 KB weight tiles (W1hi, W1lo, W2hi, W2lo per chunk of 128
-//             hidden units) through a shared-memory ring
-//   warp 1  : one thread issues tcgen05.mma:  D1[c&1] = X W1c^T (SS),  Y += H_c W2c^T (TS, A from TMEM)
-//   warps 2-5: (a) x tile fp32 -> bf16 hi/lo operand images in shared memory, (b) per chunk: D1 -> +b1,
-//             ReLU, hi/lo split -> H in TMEM, (c) Y -> +b2 + residual -> LayerNorm -> global.
-// The 128x2048 hidden activation never leaves the SM.  TMEM: D1 2x128 | H hi 64 | H lo 64 | Y 128 columns.
+// Persistent CTAs (grid.x per network, grid.y = network), 128-token tiles; each CTA works through ONE stream
+// of (tile, 128-hidden-unit chunk) items with no drain between tiles.  Warp roles:
+//   warp 0   : bulk-copy producer -- streams 32 KB weight tiles (W1hi, W1lo, W2hi, W2lo per chunk) through a
+//              shared-memory ring
+//   warp 1   : one elected lane issues tcgen05.mma.  BOTH GEMMs take their A operand from TMEM (TS form: an smem A
+//              operand costs ~32 extra cycles per MMA, tools/umma_timing.py):
+//                  G1(g): DH[g&1]  = X W1c^T          A = bf16 hi/lo images of the x tile in TMEM
+//                  G2(g): Y       += H_c W2c^T        A = H_c, written IN PLACE over DH[g&1] by the epilogue
+//              issue order G1(g), G2(g-1): the tensor pipe executes in issue order, so DH[g&1] is not overwritten by
+//              G1(g+2) before G2(g) has read it, and the chunk epilogue of g overlaps G2(g-1) + G1(g+1).
+//   warps 2-5: group 0 -- chunk epilogue for hidden units [0,64) of every chunk (+b1, ReLU, hi/lo split, in place),
+//              LayerNorm epilogue of the previous tile (Y already holds x + b2 + FFN(x))
+//   warps 6-9: group 1 -- chunk epilogue for hidden units [64,128); stages the next x tile (fp32) in shared memory
+//              while the chunks run, writes its hi/lo images to TMEM as soon as the last G1 of the tile has retired,
+//              and initialises Y with x + b2 once the LayerNorm epilogue has drained the previous tile.
+// The 128x2048 hidden activation never leaves the SM.  TMEM (512 columns): X hi 64 | X lo 64 | Y 128 | DH0 128 | DH1 128.
 constexpr int kFfnStages = 4;
 constexpr int kStageBytes = kTileBytes128;
-constexpr int kFfnThreads = 320;  // warp 0 producer, warp 1 MMA, warps 2-9 epilogue (two groups of four)
-// TMEM columns: D1 double buffer | H (two K halves of 64 hidden units: hi 32 + lo 32 columns each) | Y
-constexpr uint32_t TM_D1 = 0, TM_H = 256, TM_Y = 384;
+constexpr int kFfnThreads = 320;
+constexpr uint32_t TM_X = 0, TM_Y = 128, TM_DH = 256;
+constexpr int kXsRow = 528;  // bytes per staged x row: 512 + 16 padding (conflict-free row-per-thread 16-byte reads)
 
 struct FfnArgs {
   const float* x[2];       // [M,128] layer input (post-LN1)
@@ -227,23 +236,18 @@ struct FfnArgs {
   int F;
   float eps;
   int dbg;  // TW_FFN_DBG experiments (timing only, results invalid): 1 no weight traffic, 2 no chunk-epilogue math, 4 hi-only MMAs
+  long long* trace;  // optional event trace of CTA (0,0) (tw_debug_set_ffn_trace): [role][1024][2] = {event | item << 8, clock64}
 };
 
 struct FfnSmem {
-  static constexpr int X_HI = 0;
-  static constexpr int X_LO = 32 * 1024;
-  static constexpr int RING = 64 * 1024;
-  static constexpr int B1 = RING + kFfnStages * kStageBytes;       // F floats (<= 4096)
+  static constexpr int RING = 0;
+  static constexpr int XS = RING + kFfnStages * kStageBytes;       // staged fp32 x tile, 128 rows of kXsRow bytes
+  static constexpr int B1 = XS + 128 * kXsRow;                     // F floats (<= 4096)
   static constexpr int VEC = B1 + 4096 * 4;                        // b2, gamma, beta: 3*128 floats
   static constexpr int BARS = VEC + 3 * 128 * 4;
   static constexpr int TOTAL = BARS + 256;
 };
 
-// Warp roles of the fused FFN (see the comment above):
-//   epilogue group 0 (warps 2-5): chunk epilogue for hidden units [0,64) of every chunk + the LayerNorm epilogue
-//   epilogue group 1 (warps 6-9): chunk epilogue for hidden units [64,128) + the x-tile conversion of the next tile
-// The two K halves of H are handed to the MMA warp separately, so the second GEMM of a chunk starts while the
-// other half of the chunk epilogue is still running.
 template <int kSplit>
 __global__ void __launch_bounds__(kFfnThreads, 1) k_ffn_tc(FfnArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -252,18 +256,19 @@ __global__ void __launch_bounds__(kFfnThreads, 1) k_ffn_tc(FfnArgs a) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n_chunks = a.F / kFfnChunk;
   const int64_t n_tiles = (a.M + 127) / 128;
+  const int64_t my_tiles = ((int64_t)blockIdx.x < n_tiles) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FfnSmem::BARS);
   uint64_t* full = bars;                      // [kFfnStages]
   uint64_t* empty = bars + kFfnStages;        // [kFfnStages]
-  uint64_t* d1_full = bars + 2 * kFfnStages;  // [2]
-  uint64_t* h_full = d1_full + 2;             // [2] per K half, 128 arrivals
-  uint64_t* h_free = h_full + 2;              // [2] per K half
-  uint64_t* x_full = h_free + 2;
-  uint64_t* x_free = x_full + 1;
-  uint64_t* y_full = x_free + 1;
-  uint64_t* y_free = y_full + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(y_free + 1);
+  uint64_t* d1_full = bars + 2 * kFfnStages;  // [2]   G1 into DH[b] has retired
+  uint64_t* h_full = d1_full + 2;             // [4]   (buffer b, K half hf) of H written: index b*2+hf, 128 arrivals
+  uint64_t* x_full = h_full + 4;              // X images of the next tile are in TMEM (128 arrivals)
+  uint64_t* x_free = x_full + 1;              // last G1 of the tile has retired
+  uint64_t* y_full = x_free + 1;              // last G2 of the tile has retired
+  uint64_t* y_free = y_full + 1;              // LayerNorm epilogue has read Y (128 arrivals)
+  uint64_t* y_init = y_free + 1;              // Y = x + b2 of the next tile written (128 arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(y_init + 1);
 
   float* b1s = reinterpret_cast<float*>(smem + FfnSmem::B1);
   float* vecs = reinterpret_cast<float*>(smem + FfnSmem::VEC);
@@ -273,15 +278,13 @@ __global__ void __launch_bounds__(kFfnThreads, 1) k_ffn_tc(FfnArgs a) {
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], 1);
     }
-    for (int i = 0; i < 2; i++) {
-      mbar_init(&d1_full[i], 1);
-      mbar_init(&h_full[i], 128);
-      mbar_init(&h_free[i], 1);
-    }
+    for (int i = 0; i < 2; i++) mbar_init(&d1_full[i], 1);
+    for (int i = 0; i < 4; i++) mbar_init(&h_full[i], 128);
     mbar_init(x_full, 128);
     mbar_init(x_free, 1);
     mbar_init(y_full, 1);
     mbar_init(y_free, 128);
+    mbar_init(y_init, 128);
     mbar_fence_init();
   }
   if (warp == 1) tmem_alloc<512>(tmem_slot);
@@ -295,312 +298,855 @@ __global__ void __launch_bounds__(kFfnThreads, 1) k_ffn_tc(FfnArgs a) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  const int64_t G = my_tiles * n_chunks;  // (tile, chunk) items of this CTA
 
   if (warp == 0) {
     // ------------------------------------------------------------------ producer (whole warp, one elected lane issues)
-    {
-      uint32_t stage = 0, phase = 0;
-      int n_loaded = 0;
-      const uint8_t* wbase = a.w[net];
-      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        for (int c = 0; c <= n_chunks; c++) {
-          for (int op = 0; op < 2; op++) {  // consumption order: G1(c) then G2(c-1)
-            int chunk = (op == 0) ? c : c - 1;
-            if (chunk < 0 || chunk >= n_chunks) continue;
-            for (int part = 0; part < (kSplit == 3 ? 2 : 1); part++) {
-              const uint8_t* src = wbase + (size_t)chunk * 4 * kTileBytes128 + (size_t)(op * 2 + part) * kTileBytes128;
-              mbar_wait(&empty[stage], phase ^ 1);
-              if (elect_one()) {
-                if ((a.dbg & 1) && n_loaded >= kFfnStages) {
-                  mbar_arrive(&full[stage]);
-                } else {
-                  mbar_arrive_expect_tx(&full[stage], kStageBytes);
-                  bulk_g2s(smem + FfnSmem::RING + stage * kStageBytes, src, kStageBytes, &full[stage]);
-                }
-              }
-              __syncwarp();
-              n_loaded++;
-              if (++stage == kFfnStages) stage = 0, phase ^= 1;
-            }
+    uint32_t stage = 0, phase = 0;
+    int n_loaded = 0;
+    const uint8_t* wbase = a.w[net];
+    auto load = [&](int op, int chunk) {  // op 0: W1 tiles of the chunk, op 1: W2 tiles
+      for (int part = 0; part < (kSplit == 3 ? 2 : 1); part++) {
+        const uint8_t* src = wbase + (size_t)chunk * 4 * kTileBytes128 + (size_t)(op * 2 + part) * kTileBytes128;
+        mbar_wait(&empty[stage], phase ^ 1);
+        if (elect_one()) {
+          if ((a.dbg & 1) && n_loaded >= kFfnStages) {
+            mbar_arrive(&full[stage]);
+          } else {
+            mbar_arrive_expect_tx(&full[stage], kStageBytes);
+            bulk_g2s(smem + FfnSmem::RING + stage * kStageBytes, src, kStageBytes, &full[stage]);
           }
         }
+        __syncwarp();
+        n_loaded++;
+        if (++stage == kFfnStages) stage = 0, phase ^= 1;
       }
+    };
+    for (int64_t g = 0; g < G; g++) {  // consumption order: G1(g), G2(g-1)
+      load(0, (int)(g % n_chunks));
+      if (g >= 1) load(1, (int)((g - 1) % n_chunks));
     }
+    if (G > 0) load(1, n_chunks - 1);
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (whole warp waits, one elected lane issues)
-    {
-      uint32_t stage = 0, phase = 0;
-      uint32_t ph_x = 0, ph_h[2] = {0, 0}, ph_yfree = 0;
-      const uint32_t idesc = make_idesc_bf16(128, 128, 0, 0);
-      const uint32_t xhi = smem_u32(smem + FfnSmem::X_HI), xlo = smem_u32(smem + FfnSmem::X_LO);
-      const uint32_t ring = smem_u32(smem + FfnSmem::RING);
-      bool first_tile = true;
-      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        mbar_wait(x_full, ph_x);
-        ph_x ^= 1;
+    uint32_t stage = 0, phase = 0;
+    uint32_t ph_x = 0, ph_h = 0 /* bit b*2+hf */, ph_yinit = 0;
+    const uint32_t idesc = make_idesc_bf16(128, 128, 0, 0);
+    const uint32_t ring = smem_u32(smem + FfnSmem::RING);
+    const uint32_t x_hi = tmem + TM_X, x_lo = tmem + TM_X + 64;
+
+    auto issue_g2 = [&](int64_t gp) {  // Y += H(gp) W2c^T
+      const int j = (int)(gp % n_chunks), buf = (int)(gp & 1);
+      const uint32_t st_hi = stage;
+      mbar_wait(&full[stage], phase);
+      if (++stage == kFfnStages) stage = 0, phase ^= 1;
+      uint32_t st_lo = st_hi;
+      if (kSplit == 3) {
+        st_lo = stage;
+        mbar_wait(&full[stage], phase);
+        if (++stage == kFfnStages) stage = 0, phase ^= 1;
+      }
+      if (j == 0) {  // Y of this tile has been initialised with x + b2 (after the previous tile's Y was read out)
+        mbar_wait(y_init, ph_yinit);
+        ph_yinit ^= 1;
+      }
+      const uint32_t whi = ring + st_hi * kStageBytes, wlo = ring + st_lo * kStageBytes;
+#pragma unroll
+      for (int hf = 0; hf < 2; hf++) {
+        mbar_wait(&h_full[buf * 2 + hf], (ph_h >> (buf * 2 + hf)) & 1u);  // epilogue group hf has written its half of H
+        ph_h ^= 1u << (buf * 2 + hf);
         tc_fence_after();
-        for (int c = 0; c <= n_chunks; c++) {
-          if (c < n_chunks) {
-            const uint32_t d1 = tmem + TM_D1 + (c & 1) * 128;
-            mbar_wait(&full[stage], phase);  // W1 hi tile: Xhi*W1hi, Xlo*W1hi
-            tc_fence_after();
-            if (elect_one()) {
-              const uint32_t wt = ring + stage * kStageBytes;
+        if (elect_one()) {
+          const uint32_t h_hi = tmem + TM_DH + buf * 128 + hf * 64, h_lo = h_hi + 32;
 #pragma unroll
-              for (int k = 0; k < 8; k++) {
-                uint32_t koff = (k >> 2) * 16384 + (k & 3) * 32;
-                mma_ss(d1, desc_kmajor_sw128(xhi + koff), desc_kmajor_sw128(wt + koff), idesc, k > 0);
-              }
-              if (kSplit == 3 && !(a.dbg & 4)) {
+          for (int k = 0; k < 4; k++) mma_ts(tmem + TM_Y, h_hi + k * 8, desc_kmajor_sw128(whi + hf * 16384 + k * 32), idesc, 1);
+          if (kSplit == 3 && !(a.dbg & 4)) {
 #pragma unroll
-                for (int k = 0; k < 8; k++) {
-                  uint32_t koff = (k >> 2) * 16384 + (k & 3) * 32;
-                  mma_ss(d1, desc_kmajor_sw128(xlo + koff), desc_kmajor_sw128(wt + koff), idesc, 1);
-                }
-              }
-              mma_commit(&empty[stage]);
-            }
-            __syncwarp();
-            if (++stage == kFfnStages) stage = 0, phase ^= 1;
-            if (kSplit == 3) {  // W1 lo tile: Xhi*W1lo
-              mbar_wait(&full[stage], phase);
-              tc_fence_after();
-              if (elect_one()) {
-                const uint32_t wt = ring + stage * kStageBytes;
-                if (!(a.dbg & 4)) {
+            for (int k = 0; k < 4; k++) mma_ts(tmem + TM_Y, h_lo + k * 8, desc_kmajor_sw128(whi + hf * 16384 + k * 32), idesc, 1);
 #pragma unroll
-                  for (int k = 0; k < 8; k++) {
-                    uint32_t koff = (k >> 2) * 16384 + (k & 3) * 32;
-                    mma_ss(d1, desc_kmajor_sw128(xhi + koff), desc_kmajor_sw128(wt + koff), idesc, 1);
-                  }
-                }
-                mma_commit(&empty[stage]);
-              }
-              __syncwarp();
-              if (++stage == kFfnStages) stage = 0, phase ^= 1;
-            }
-            if (elect_one()) {
-              mma_commit(&d1_full[c & 1]);
-              if (c == n_chunks - 1) mma_commit(x_free);  // every read of the X images has completed
-            }
-            __syncwarp();
-          }
-          if (c >= 1) {
-            const int j = c - 1;
-            // both W2 tiles (hi, lo) of chunk j: K block hf of each tile multiplies H half hf
-            const uint32_t st_hi = stage;
-            mbar_wait(&full[stage], phase);
-            if (++stage == kFfnStages) stage = 0, phase ^= 1;
-            uint32_t st_lo = st_hi;
-            if (kSplit == 3) {
-              st_lo = stage;
-              mbar_wait(&full[stage], phase);
-              if (++stage == kFfnStages) stage = 0, phase ^= 1;
-            }
-            if (j == 0 && !first_tile) {
-              mbar_wait(y_free, ph_yfree);  // previous tile's Y has been read out
-              ph_yfree ^= 1;
-            }
-            const uint32_t whi = ring + st_hi * kStageBytes, wlo = ring + st_lo * kStageBytes;
-#pragma unroll
-            for (int hf = 0; hf < 2; hf++) {
-              mbar_wait(&h_full[hf], ph_h[hf]);  // epilogue group hf has written its half of H_j
-              ph_h[hf] ^= 1;
-              tc_fence_after();
-              if (elect_one()) {
-                const uint32_t h_hi = tmem + TM_H + hf * 64, h_lo = h_hi + 32;
-#pragma unroll
-                for (int k = 0; k < 4; k++)
-                  mma_ts(tmem + TM_Y, h_hi + k * 8, desc_kmajor_sw128(whi + hf * 16384 + k * 32), idesc, (j > 0 || hf > 0 || k > 0) ? 1 : 0);
-                if (kSplit == 3 && !(a.dbg & 4)) {
-#pragma unroll
-                  for (int k = 0; k < 4; k++) mma_ts(tmem + TM_Y, h_lo + k * 8, desc_kmajor_sw128(whi + hf * 16384 + k * 32), idesc, 1);
-#pragma unroll
-                  for (int k = 0; k < 4; k++) mma_ts(tmem + TM_Y, h_hi + k * 8, desc_kmajor_sw128(wlo + hf * 16384 + k * 32), idesc, 1);
-                }
-                mma_commit(&h_free[hf]);
-              }
-              __syncwarp();
-            }
-            if (elect_one()) {
-              mma_commit(&empty[st_hi]);
-              if (kSplit == 3) mma_commit(&empty[st_lo]);
-              if (j == n_chunks - 1) mma_commit(y_full);
-            }
-            __syncwarp();
+            for (int k = 0; k < 4; k++) mma_ts(tmem + TM_Y, h_hi + k * 8, desc_kmajor_sw128(wlo + hf * 16384 + k * 32), idesc, 1);
           }
         }
-        first_tile = false;
+        __syncwarp();
+      }
+      if (elect_one()) {
+        mma_commit(&empty[st_hi]);
+        if (kSplit == 3) mma_commit(&empty[st_lo]);
+        if (j == n_chunks - 1) mma_commit(y_full);
+      }
+      __syncwarp();
+    };
+
+    int64_t g = 0;
+    for (int64_t it = 0; it < my_tiles; it++) {
+      mbar_wait(x_full, ph_x);
+      ph_x ^= 1;
+      tc_fence_after();
+      for (int c = 0; c < n_chunks; c++, g++) {
+        const uint32_t d1 = tmem + TM_DH + (uint32_t)(g & 1) * 128;
+        mbar_wait(&full[stage], phase);  // W1 hi tile: Xhi*W1hi, Xlo*W1hi
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t wt = ring + stage * kStageBytes;
+#pragma unroll
+          for (int k = 0; k < 8; k++)
+            mma_ts(d1, x_hi + k * 8, desc_kmajor_sw128(wt + (k >> 2) * 16384 + (k & 3) * 32), idesc, k > 0);
+          if (kSplit == 3 && !(a.dbg & 4)) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) mma_ts(d1, x_lo + k * 8, desc_kmajor_sw128(wt + (k >> 2) * 16384 + (k & 3) * 32), idesc, 1);
+          }
+          mma_commit(&empty[stage]);
+        }
+        __syncwarp();
+        if (++stage == kFfnStages) stage = 0, phase ^= 1;
+        if (kSplit == 3) {  // W1 lo tile: Xhi*W1lo
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t wt = ring + stage * kStageBytes;
+            if (!(a.dbg & 4)) {
+#pragma unroll
+              for (int k = 0; k < 8; k++) mma_ts(d1, x_hi + k * 8, desc_kmajor_sw128(wt + (k >> 2) * 16384 + (k & 3) * 32), idesc, 1);
+            }
+            mma_commit(&empty[stage]);
+          }
+          __syncwarp();
+          if (++stage == kFfnStages) stage = 0, phase ^= 1;
+        }
+        if (elect_one()) {
+          mma_commit(&d1_full[g & 1]);
+          if (c == n_chunks - 1) mma_commit(x_free);  // every read of the X images of this tile has retired
+        }
+        __syncwarp();
+        if (g >= 1) issue_g2(g - 1);
       }
     }
+    if (G > 0) issue_g2(G - 1);
   } else {
     // ------------------------------------------------------------------ epilogue warps (2 groups x 128 threads)
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
     const int hf = (warp - 2) >> 2;         // epilogue group = K half of H this thread produces
     const int row = q * 32 + lane;          // token row inside the tile
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-    uint32_t ph_d1[2] = {0, 0}, ph_hfree = 0, ph_xfree = 0, ph_y = 0;
-    bool first_tile = true, first_chunk_ever = true;
+    uint32_t ph_d1 = 0 /* bit per buffer */, ph_xfree = 0, ph_y = 0, ph_yfree = 0;
     const float* x = a.x[net];
     float* out = a.out[net];
+    uint8_t* xs = smem + FfnSmem::XS;
+    const uint8_t* xs_row = xs + row * kXsRow;
 
-    auto convert_x = [&](int64_t tile) {  // group 1: x tile -> bf16 hi/lo operand images (K-major, 128B swizzle)
-      const int64_t row0 = tile * 128;
-#pragma unroll 1
-      for (int it = 0; it < 32; it += 8) {
-        float4 v[8];
+    // ---- group 1 helpers: staging of an x tile, TMEM images, Y initialisation
+    auto load_rows = [&](int64_t tile, int r0, float4 (&v)[4]) {  // warp q stages rows q*32 + r0 .. +3 (coalesced 512 B each)
+      const int64_t row0 = tile * 128 + q * 32 + r0;
 #pragma unroll
-        for (int u = 0; u < 8; u++) {
-          int r = q * 32 + it + u;
-          v[u] = (row0 + r < a.M) ? __ldg(reinterpret_cast<const float4*>(x + (row0 + r) * 128) + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-#pragma unroll
-        for (int u = 0; u < 8; u++) {
-          int r = q * 32 + it + u;
-          uint32_t h0, l0, h1, l1;
-          split2(v[u].x, v[u].y, h0, l0);
-          split2(v[u].z, v[u].w, h1, l1);
-          uint32_t off = sw128_offset(r, lane * 4, 128);
-          *reinterpret_cast<uint2*>(smem + FfnSmem::X_HI + off) = make_uint2(h0, h1);
-          *reinterpret_cast<uint2*>(smem + FfnSmem::X_LO + off) = make_uint2(l0, l1);
-        }
-      }
-      fence_proxy_async_smem();
-      mbar_arrive(x_full);
+      for (int u = 0; u < 4; u++)
+        v[u] = (row0 + u < a.M) ? __ldg(reinterpret_cast<const float4*>(x + (row0 + u) * 128) + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
     };
-
-    if (hf == 1 && (int64_t)blockIdx.x < n_tiles) convert_x(blockIdx.x);
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      const int64_t row0 = tile * 128;
-      // ---- per chunk: D1[:, hf*64 .. +64) -> bias + ReLU -> hi/lo -> H half hf (TMEM)
-      for (int c = 0; c < n_chunks; c++) {
-        mbar_wait(&d1_full[c & 1], ph_d1[c & 1]);
-        ph_d1[c & 1] ^= 1;
-        if (!first_chunk_ever) {
-          mbar_wait(&h_free[hf], ph_hfree);  // the second GEMM of the previous chunk has consumed this half
-          ph_hfree ^= 1;
-        }
-        first_chunk_ever = false;
-        tc_fence_after();
-        if (a.dbg & 2) {
-          tc_fence_before();
-          mbar_arrive(&h_full[hf]);
-          continue;
-        }
-        const float* bc = b1s + c * kFfnChunk + hf * 64;
-        uint32_t r0[32], r1[32];
-        tmem_ld32(tmem + lane_base + TM_D1 + (c & 1) * 128 + hf * 64, r0);
-        tmem_ld32(tmem + lane_base + TM_D1 + (c & 1) * 128 + hf * 64 + 32, r1);
-        tmem_ld_wait();
+    auto store_rows = [&](int r0, const float4 (&v)[4]) {
+#pragma unroll
+      for (int u = 0; u < 4; u++) *reinterpret_cast<float4*>(xs + (q * 32 + r0 + u) * kXsRow + lane * 16) = v[u];
+    };
+    auto group1_sync = [&]() { asm volatile("bar.sync 1, 128;" ::: "memory"); };
+    auto x_to_tmem = [&]() {  // own row of the staged tile -> bf16 hi/lo A-operand images in TMEM
+#pragma unroll 1
+      for (int b = 0; b < 4; b++) {
         uint32_t hi[16], lo[16];
 #pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-          float2 bb = *reinterpret_cast<const float2*>(bc + j);
-          split2(fmaxf(__uint_as_float(r0[j]) + bb.x, 0.f), fmaxf(__uint_as_float(r0[j + 1]) + bb.y, 0.f), hi[j >> 1], lo[j >> 1]);
+        for (int j = 0; j < 8; j++) {
+          const float4 v = *reinterpret_cast<const float4*>(xs_row + b * 128 + j * 16);
+          split2(v.x, v.y, hi[2 * j], lo[2 * j]);
+          split2(v.z, v.w, hi[2 * j + 1], lo[2 * j + 1]);
         }
-        tmem_st16(tmem + lane_base + TM_H + hf * 64, hi);
-        if (kSplit == 3) tmem_st16(tmem + lane_base + TM_H + hf * 64 + 32, lo);
-#pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-          float2 bb = *reinterpret_cast<const float2*>(bc + 32 + j);
-          split2(fmaxf(__uint_as_float(r1[j]) + bb.x, 0.f), fmaxf(__uint_as_float(r1[j + 1]) + bb.y, 0.f), hi[j >> 1], lo[j >> 1]);
-        }
-        tmem_st16(tmem + lane_base + TM_H + hf * 64 + 16, hi);
-        if (kSplit == 3) tmem_st16(tmem + lane_base + TM_H + hf * 64 + 48, lo);
-        tmem_st_wait();
-        tc_fence_before();
-        mbar_arrive(&h_full[hf]);
+        tmem_st16(tmem + lane_base + TM_X + b * 16, hi);
+        if (kSplit == 3) tmem_st16(tmem + lane_base + TM_X + 64 + b * 16, lo);
       }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(x_full);
+    };
+    auto init_y = [&]() {  // Y <- x + b2: the residual and the second bias ride in the accumulator
+#pragma unroll 1
+      for (int b = 0; b < 8; b++) {
+        uint32_t r[16];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const float4 v = *reinterpret_cast<const float4*>(xs_row + b * 64 + j * 16);
+          const float4 bv = *reinterpret_cast<const float4*>(vecs + b * 16 + 4 * j);
+          r[4 * j] = __float_as_uint(v.x + bv.x), r[4 * j + 1] = __float_as_uint(v.y + bv.y);
+          r[4 * j + 2] = __float_as_uint(v.z + bv.z), r[4 * j + 3] = __float_as_uint(v.w + bv.w);
+        }
+        tmem_st16(tmem + lane_base + TM_Y + b * 16, r);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(y_init);
+    };
+    // ---- group 0 helper: LayerNorm epilogue of a finished tile (two passes over Y in TMEM)
+    auto layer_norm_tile = [&](int64_t tile) {
+      mbar_wait(y_full, ph_y);
+      ph_y ^= 1;
+      tc_fence_after();
+      const int64_t grow = tile * 128 + row;
+      const bool valid = grow < a.M;
+      float sum = 0.f, sq = 0.f;
+#pragma unroll 1
+      for (int g4 = 0; g4 < 4; g4++) {
+        uint32_t r[32];
+        tmem_ld32(tmem + lane_base + TM_Y + g4 * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; j++) {
+          const float v = __uint_as_float(r[j]);
+          sum += v;
+          sq = fmaf(v, v, sq);
+        }
+      }
+      const float mean = sum * (1.f / 128.f);
+      const float var = fmaxf(sq * (1.f / 128.f) - mean * mean, 0.f);
+      const float rstd = 1.0f / sqrtf(var + a.eps);
+      float4* orow = reinterpret_cast<float4*>(out + (valid ? grow : 0) * 128);
+      float4* prow = a.pre[net] ? reinterpret_cast<float4*>(a.pre[net] + (valid ? grow : 0) * 128) : nullptr;
+#pragma unroll 1
+      for (int g4 = 0; g4 < 4; g4++) {
+        uint32_t r[32];
+        tmem_ld32(tmem + lane_base + TM_Y + g4 * 32, r);
+        tmem_ld_wait();
+        if (g4 == 3) {  // Y has been read for the last time: the next tile may initialise it
+          tc_fence_before();
+          mbar_arrive(y_free);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          const float4 gm = *reinterpret_cast<const float4*>(vecs + 128 + g4 * 32 + 4 * j);
+          const float4 bt = *reinterpret_cast<const float4*>(vecs + 256 + g4 * 32 + 4 * j);
+          float4 p, o;
+          p.x = __uint_as_float(r[4 * j]), p.y = __uint_as_float(r[4 * j + 1]);
+          p.z = __uint_as_float(r[4 * j + 2]), p.w = __uint_as_float(r[4 * j + 3]);
+          o.x = (p.x - mean) * rstd * gm.x + bt.x;
+          o.y = (p.y - mean) * rstd * gm.y + bt.y;
+          o.z = (p.z - mean) * rstd * gm.z + bt.z;
+          o.w = (p.w - mean) * rstd * gm.w + bt.w;
+          if (valid) orow[g4 * 8 + j] = o;
+          if (valid && prow) prow[g4 * 8 + j] = p;
+        }
+      }
+    };
 
-      if (hf == 1) {
-        // ---- group 1: operand images of the next tile (after every GEMM-1 of this tile has read the old ones)
-        if (tile + gridDim.x < n_tiles) {
+    if (hf == 1 && my_tiles > 0) {  // first tile: stage, images, (Y is initialised after the first chunk epilogue)
+      for (int r0 = 0; r0 < 32; r0 += 4) {
+        float4 v[4];
+        load_rows(blockIdx.x, r0, v);
+        store_rows(r0, v);
+      }
+      group1_sync();
+      x_to_tmem();
+    }
+    int64_t g = 0;
+    for (int64_t it = 0; it < my_tiles; it++) {
+      const int64_t tile = blockIdx.x + it * gridDim.x;
+      const bool has_next = it + 1 < my_tiles;
+      int staged = 0;  // rows (per warp) of the next tile already staged
+      float4 pf[4];
+      bool pf_valid = false;
+      for (int c = 0; c < n_chunks; c++, g++) {
+        const int buf = (int)(g & 1);
+        if (hf == 1 && n_chunks > 1 && c == n_chunks - 1 && has_next) {
+          // the last G1 of this tile and the release of the X images retire together: publish the next tile's images
+          // FIRST, so that its first GEMM is queued behind G2 of the previous chunk without a bubble
+          while (staged < 32 || pf_valid) {
+            if (pf_valid) store_rows(staged - 4, pf), pf_valid = false;
+            if (staged < 32) load_rows(tile + gridDim.x, staged, pf), staged += 4, pf_valid = true;
+          }
+          group1_sync();
           mbar_wait(x_free, ph_xfree);
           ph_xfree ^= 1;
-          convert_x(tile + gridDim.x);
+          tc_fence_after();
+          x_to_tmem();
         }
-      } else {
-        // ---- group 0: Y + b2 + residual -> LayerNorm -> global   (two passes over TMEM, no 128-register row)
-        mbar_wait(y_full, ph_y);
-        ph_y ^= 1;
+        // ---- DH[buf][:, hf*64 .. +64): + b1, ReLU, hi/lo split, written back in place as the A operand of G2
+        mbar_wait(&d1_full[buf], (ph_d1 >> buf) & 1u);
+        ph_d1 ^= 1u << buf;
         tc_fence_after();
-        const int64_t grow = row0 + row;
-        const bool valid = grow < a.M;
-        const float4* xr = reinterpret_cast<const float4*>(x + (valid ? grow : 0) * 128);
-        float sum = 0.f, sq = 0.f;
-#pragma unroll 1
-        for (int g = 0; g < 4; g++) {
-          uint32_t r[32];
-          tmem_ld32(tmem + lane_base + TM_Y + g * 32, r);
+        if (!(a.dbg & 2)) {
+          const float* bc = b1s + c * kFfnChunk + hf * 64;
+          const uint32_t base = tmem + lane_base + TM_DH + buf * 128 + hf * 64;
+          uint32_t r0[32], r1[32];
+          tmem_ld32(base, r0);
+          tmem_ld32(base + 32, r1);
           tmem_ld_wait();
+          uint32_t hi[16], lo[16];
 #pragma unroll
-          for (int j = 0; j < 8; j++) {
-            float4 xv = __ldg(xr + g * 8 + j);
-            float4 bv = *reinterpret_cast<const float4*>(vecs + g * 32 + 4 * j);
-            float v0 = __uint_as_float(r[4 * j]) + (bv.x + xv.x), v1 = __uint_as_float(r[4 * j + 1]) + (bv.y + xv.y);
-            float v2 = __uint_as_float(r[4 * j + 2]) + (bv.z + xv.z), v3 = __uint_as_float(r[4 * j + 3]) + (bv.w + xv.w);
-            sum += (v0 + v1) + (v2 + v3);
-            sq = fmaf(v0, v0, sq), sq = fmaf(v1, v1, sq), sq = fmaf(v2, v2, sq), sq = fmaf(v3, v3, sq);
+          for (int j = 0; j < 32; j += 2) {
+            float2 bb = *reinterpret_cast<const float2*>(bc + j);
+            split2(fmaxf(__uint_as_float(r0[j]) + bb.x, 0.f), fmaxf(__uint_as_float(r0[j + 1]) + bb.y, 0.f), hi[j >> 1], lo[j >> 1]);
           }
-        }
-        const float mean = sum * (1.f / 128.f);
-        const float var = fmaxf(sq * (1.f / 128.f) - mean * mean, 0.f);
-        const float rstd = 1.0f / sqrtf(var + a.eps);
-        float4* orow = reinterpret_cast<float4*>(out + (valid ? grow : 0) * 128);
-        float4* prow = a.pre[net] ? reinterpret_cast<float4*>(a.pre[net] + (valid ? grow : 0) * 128) : nullptr;
-#pragma unroll 1
-        for (int g = 0; g < 4; g++) {
-          uint32_t r[32];
-          tmem_ld32(tmem + lane_base + TM_Y + g * 32, r);
-          tmem_ld_wait();
+          tmem_st16(base, hi);
+          if (kSplit == 3) tmem_st16(base + 32, lo);
 #pragma unroll
-          for (int j = 0; j < 8; j++) {
-            float4 xv = __ldg(xr + g * 8 + j);
-            float4 bv = *reinterpret_cast<const float4*>(vecs + g * 32 + 4 * j);
-            float4 g4 = *reinterpret_cast<const float4*>(vecs + 128 + g * 32 + 4 * j);
-            float4 b4 = *reinterpret_cast<const float4*>(vecs + 256 + g * 32 + 4 * j);
-            float4 p, o;
-            p.x = __uint_as_float(r[4 * j]) + (bv.x + xv.x);
-            p.y = __uint_as_float(r[4 * j + 1]) + (bv.y + xv.y);
-            p.z = __uint_as_float(r[4 * j + 2]) + (bv.z + xv.z);
-            p.w = __uint_as_float(r[4 * j + 3]) + (bv.w + xv.w);
-            o.x = (p.x - mean) * rstd * g4.x + b4.x;
-            o.y = (p.y - mean) * rstd * g4.y + b4.y;
-            o.z = (p.z - mean) * rstd * g4.z + b4.z;
-            o.w = (p.w - mean) * rstd * g4.w + b4.w;
-            if (valid) orow[g * 8 + j] = o;
-            if (valid && prow) prow[g * 8 + j] = p;
+          for (int j = 0; j < 32; j += 2) {
+            float2 bb = *reinterpret_cast<const float2*>(bc + 32 + j);
+            split2(fmaxf(__uint_as_float(r1[j]) + bb.x, 0.f), fmaxf(__uint_as_float(r1[j + 1]) + bb.y, 0.f), hi[j >> 1], lo[j >> 1]);
           }
+          tmem_st16(base + 16, hi);
+          if (kSplit == 3) tmem_st16(base + 48, lo);
+          tmem_st_wait();
         }
         tc_fence_before();
-        mbar_arrive(y_free);
+        mbar_arrive(&h_full[buf * 2 + hf]);
+
+        if (c == 0) {
+          if (hf == 0) {
+            if (it > 0) layer_norm_tile(tile - gridDim.x);
+          } else {
+            if (it > 0) {
+              mbar_wait(y_free, ph_yfree);
+              ph_yfree ^= 1;
+              tc_fence_after();
+            }
+            init_y();
+            group1_sync();  // every row of the staging buffer has been consumed: it may be refilled
+          }
+        }
+        if (hf == 1 && has_next && c < n_chunks - 1) {  // stage 4 rows per warp per chunk, loads in flight across a chunk
+          if (pf_valid) store_rows(staged - 4, pf), pf_valid = false;
+          if (staged < 32) load_rows(tile + gridDim.x, staged, pf), staged += 4, pf_valid = true;
+        }
       }
-      first_tile = false;
+      if (n_chunks == 1 && hf == 1 && has_next) {  // single-chunk FFN: nothing overlapped, stage and publish here
+        for (int r0 = 0; r0 < 32; r0 += 4) {
+          float4 v[4];
+          load_rows(tile + gridDim.x, r0, v);
+          store_rows(r0, v);
+        }
+        group1_sync();
+        mbar_wait(x_free, ph_xfree);
+        ph_xfree ^= 1;
+        tc_fence_after();
+        x_to_tmem();
+      }
     }
+    if (hf == 0 && my_tiles > 0) layer_norm_tile(blockIdx.x + (my_tiles - 1) * gridDim.x);
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc<512>(tmem);
 }
 
-static int launch_ffn_tc(const tw_flow_config* c, const FfnArgs& a, cudaStream_t st) {
+// ============================================================================================
+// Fused FFN on CTA PAIRS (cta_group::2).  Same pipeline as k_ffn_tc, with one tcgen05.mma spanning the two SMs of a
+// cluster: 256-token tiles (128 rows in each CTA's TMEM), the B operand (weight chunk) split over the pair -- each CTA
+// streams only HALF of every weight tile (rows [64r, 64r+64) of each [128 x 64] K block), which halves the L2 -> SM
+// traffic (at full tensor rate the single-CTA kernel needs ~10 TB/s of L2 reads, the measured cap) and makes the
+// 128 KB ring hold two chunks instead of one.  Rank 0 issues every MMA; commits are multicast to both CTAs; the
+// epilogue threads of both CTAs arrive on rank 0's barriers; rank 1's MMA warp relays its "weights landed" signals.
+constexpr int kPairStages = 8;
+constexpr int kPairThreads = 352;       // warp 0 weight producer, 1 MMA issuer / relay, 2-9 epilogue, 10 activation I/O
+constexpr int kPairStageBytes = 16384;  // two [64 rows x 64 K] K blocks of one weight tile part
+constexpr int kPairMaxF = 2048;         // dim_feedforward limit of the pair kernel (b1 lives in shared memory)
+
+struct FfnPairSmem {
+  static constexpr int RING = 0;
+  static constexpr int XS = RING + kPairStages * kPairStageBytes;
+  static constexpr int STAT = XS + 128 * kXsRow;                  // per-row partial (sum, sum of squares) of each group
+  static constexpr int B1 = STAT + 2 * 128 * 8;                   // F floats (<= kPairMaxF)
+  static constexpr int VEC = B1 + kPairMaxF * 4;
+  static constexpr int BARS = VEC + 3 * 128 * 4;
+  static constexpr int TOTAL = BARS + 512;
+};
+static_assert(FfnPairSmem::TOTAL + 1024 <= 232448, "pair FFN shared memory exceeds 227 KB");
+
+template <int kSplit>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1) k_ffn_pair(FfnArgs a) {  // 11 warps: 3 on one SMSP -> 168 registers
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int net = blockIdx.y;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int n_chunks = a.F / kFfnChunk;
+  const int64_t n_ptiles = (a.M + 255) / 256;  // 256-token tiles of the pair
+  const int64_t pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  const int64_t my_tiles = (pair < n_ptiles) ? (n_ptiles - pair + n_pairs - 1) / n_pairs : 0;
+  constexpr int kParts = (kSplit == 3) ? 2 : 1;
+  const bool tr_on = a.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0;
+  int tr_n = 0;
+#define FFN_TRACE(role, ev, item)                                                   \
+  if (tr_on && tr_n < 1024) {                                                       \
+    a.trace[((role) * 1024 + tr_n) * 2] = (long long)(ev) | ((long long)(item) << 8); \
+    a.trace[((role) * 1024 + tr_n) * 2 + 1] = clock64();                            \
+    tr_n++;                                                                         \
+  }
+
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FfnPairSmem::BARS);
+  uint64_t* full = bars;                         // [8] own half of a weight tile part has landed
+  uint64_t* peer_full = full + kPairStages;      // [8] (rank 0) rank 1's half has landed
+  uint64_t* empty = peer_full + kPairStages;     // [8] multicast commit
+  uint64_t* d1_full = empty + kPairStages;       // [2] multicast commit
+  uint64_t* h_full = d1_full + 2;                // [4] (rank 0) 256 arrivals: both CTAs' epilogue group hf
+  uint64_t* x_full = h_full + 4;                 // (rank 0) 256 arrivals
+  uint64_t* x_free = x_full + 1;                 // multicast commit
+  uint64_t* y_full = x_free + 1;                 // multicast commit
+  uint64_t* y_free = y_full + 1;                 // (unused)
+  uint64_t* y_init = y_free + 1;                 // (rank 0) 512 arrivals: every epilogue thread of both CTAs
+  uint64_t* xs_full = y_init + 1;                // local: the staged x tile has landed (bulk copies, tx bytes)
+  uint64_t* ln_staged = xs_full + 1;             // local, 256 arrivals: Y initialised from the staged rows and the previous
+                                                 // tile's LayerNorm output parked in the staging buffer
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ln_staged + 1);
+
+  float* b1s = reinterpret_cast<float*>(smem + FfnPairSmem::B1);
+  float* vecs = reinterpret_cast<float*>(smem + FfnPairSmem::VEC);
+
+  if (tid == 0) {
+    for (int i = 0; i < kPairStages; i++) {
+      mbar_init(&full[i], 1);
+      mbar_init(&peer_full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; i++) mbar_init(&d1_full[i], 1);
+    for (int i = 0; i < 4; i++) mbar_init(&h_full[i], 256);
+    mbar_init(x_full, 256);
+    mbar_init(x_free, 1);
+    mbar_init(y_full, 1);
+    mbar_init(y_free, 128);
+    mbar_init(y_init, 512);
+    mbar_init(xs_full, 1);
+    mbar_init(ln_staged, 256);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc_pair<512>(tmem_slot);
+  for (int i = tid; i < a.F; i += blockDim.x) b1s[i] = a.b1[net][i];
+  for (int i = tid; i < 128; i += blockDim.x) {
+    vecs[i] = a.b2[net][i];
+    vecs[128 + i] = a.gamma[net][i];
+    vecs[256 + i] = a.beta[net][i];
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // both CTAs' barriers are initialised before any remote arrive / multicast commit
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const int64_t G = my_tiles * n_chunks;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ producer: this CTA's half of every weight tile part
+    uint32_t stage = 0, phase = 0;
+    const uint8_t* wbase = a.w[net] + (size_t)rank * 8192;
+    auto load = [&](int op, int chunk) {
+      for (int part = 0; part < kParts; part++) {
+        const uint8_t* src = wbase + (size_t)chunk * 4 * kTileBytes128 + (size_t)(op * 2 + part) * kTileBytes128;
+        mbar_wait(&empty[stage], phase ^ 1);
+        if (elect_one()) {
+          uint8_t* dst = smem + FfnPairSmem::RING + stage * kPairStageBytes;
+          mbar_arrive_expect_tx(&full[stage], kPairStageBytes);
+          bulk_g2s(dst, src, 8192, &full[stage]);
+          bulk_g2s(dst + 8192, src + 16384, 8192, &full[stage]);
+        }
+        __syncwarp();
+        if (++stage == kPairStages) stage = 0, phase ^= 1;
+      }
+    };
+    for (int64_t g = 0; g < G; g++) {
+      load(0, (int)(g % n_chunks));
+      if (g >= 1) load(1, (int)((g - 1) % n_chunks));
+    }
+    if (G > 0) load(1, n_chunks - 1);
+  } else if (warp == 10) {
+    // ------------------------------------------------------------------ activation I/O warp
+    // The staging buffer XS (128 padded fp32 rows) carries the x tile of the NEXT 256-token tile in (per-row bulk loads)
+    // and, between the accumulator hand-over of a tile boundary and that refill, the LayerNorm output of the PREVIOUS tile
+    // out (per-row bulk stores): the epilogue warps never touch global memory, and the 9.5 MB store burst of 148 CTAs
+    // crossing a tile boundary in lock-step drains through the TMA queues without stalling them or the weight producer.
+    uint32_t ph_staged = 0;
+    auto tile_row0 = [&](int64_t it) -> int64_t { return ((pair + it * n_pairs) * 2 + rank) * 128; };
+    auto valid_rows = [&](int64_t row0) -> int {
+      const int64_t left = a.M - row0;
+      return left >= 128 ? 128 : (left > 0 ? (int)left : 0);
+    };
+    auto stage_x = [&](int64_t it) {
+      const int64_t row0 = tile_row0(it);
+      const int n_valid = valid_rows(row0);
+      if (lane == 0) {
+        mbar_arrive_expect_tx(xs_full, (uint32_t)n_valid * 512u);
+        const float* src = a.x[net] + row0 * 128;
+        for (int r = 0; r < n_valid; r++) bulk_g2s(smem + FfnPairSmem::XS + r * kXsRow, src + (size_t)r * 128, 512, xs_full);
+      }
+      __syncwarp();
+    };
+    auto store_out = [&](int64_t it) {  // parked LayerNorm rows of tile `it` -> global
+      const int64_t row0 = tile_row0(it);
+      const int n_valid = valid_rows(row0);
+      if (lane == 0) {
+        float* dst = a.out[net] + row0 * 128;
+        for (int r = 0; r < n_valid; r++) bulk_s2g(dst + (size_t)r * 128, smem + FfnPairSmem::XS + r * kXsRow, 512);
+        bulk_commit_group();
+      }
+      __syncwarp();
+    };
+    if (my_tiles > 0) stage_x(0);
+    for (int64_t it = 0; it < my_tiles; it++) {
+      mbar_wait(ln_staged, ph_staged);  // boundary of tile `it` done: Y initialised, LayerNorm(it - 1) parked
+      ph_staged ^= 1;
+      if (it > 0) store_out(it - 1);
+      if (lane == 0) bulk_wait_group_read0();  // the parked rows have been read out of shared memory
+      __syncwarp();
+      if (it + 1 < my_tiles) {
+        stage_x(it + 1);
+      } else {  // nothing more to stage: just tell the epilogue warps that the buffer is free for the last LayerNorm
+        if (lane == 0) mbar_arrive(xs_full);
+        __syncwarp();
+      }
+    }
+    if (my_tiles > 0) {
+      mbar_wait(ln_staged, ph_staged);  // LayerNorm of the last tile parked
+      store_out(my_tiles - 1);
+    }
+    if (lane == 0) bulk_wait_group0();
+    __syncwarp();
+  } else if (warp == 1 && rank != 0) {
+    // ------------------------------------------------------------------ rank 1: relay "my half has landed" to rank 0
+    uint32_t stage = 0, phase = 0;
+    const int64_t n_parts = G * 2 * kParts;
+    for (int64_t n = 0; n < n_parts; n++) {
+      mbar_wait(&full[stage], phase);
+      if (elect_one()) mbar_arrive_cluster(&peer_full[stage], 0);
+      __syncwarp();
+      if (++stage == kPairStages) stage = 0, phase ^= 1;
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ rank 0: MMA issuer for the pair
+    uint32_t stage = 0, phase = 0;
+    uint32_t ph_x = 0, ph_h = 0 /* bit b*2+hf */, ph_yinit = 0;
+    const uint32_t idesc = make_idesc_bf16(256, 128, 0, 0);
+    const uint32_t ring = smem_u32(smem + FfnPairSmem::RING);
+    const uint32_t x_hi = tmem + TM_X, x_lo = tmem + TM_X + 64;
+    auto wait_stage = [&]() -> uint32_t {  // both halves of the next weight tile part are in shared memory
+      mbar_wait(&full[stage], phase);
+      mbar_wait(&peer_full[stage], phase);
+      const uint32_t addr = ring + stage * kPairStageBytes;
+      if (++stage == kPairStages) stage = 0, phase ^= 1;
+      return addr;
+    };
+    auto stage_bar = [&](uint32_t addr) -> uint64_t* { return &empty[(addr - ring) / kPairStageBytes]; };
+
+    auto issue_g2 = [&](int64_t gp) {  // Y += H(gp) W2c^T
+      const int j = (int)(gp % n_chunks), buf = (int)(gp & 1);
+      const uint32_t whi = wait_stage();
+      const uint32_t wlo = (kSplit == 3) ? wait_stage() : whi;
+      FFN_TRACE(0, 3, gp);
+      if (j == 0) {
+        mbar_wait(y_init, ph_yinit);
+        ph_yinit ^= 1;
+      }
+#pragma unroll
+      for (int hf = 0; hf < 2; hf++) {
+        mbar_wait(&h_full[buf * 2 + hf], (ph_h >> (buf * 2 + hf)) & 1u);
+        ph_h ^= 1u << (buf * 2 + hf);
+        tc_fence_after();
+        FFN_TRACE(0, 4 + hf, gp);
+        if (elect_one()) {
+          const uint32_t h_hi = tmem + TM_DH + buf * 128 + hf * 64, h_lo = h_hi + 32;
+#pragma unroll
+          for (int k = 0; k < 4; k++) mma_ts_pair(tmem + TM_Y, h_hi + k * 8, desc_kmajor_sw128(whi + hf * 8192 + k * 32), idesc, 1);
+          if (kSplit == 3 && !(a.dbg & 4)) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) mma_ts_pair(tmem + TM_Y, h_lo + k * 8, desc_kmajor_sw128(whi + hf * 8192 + k * 32), idesc, 1);
+#pragma unroll
+            for (int k = 0; k < 4; k++) mma_ts_pair(tmem + TM_Y, h_hi + k * 8, desc_kmajor_sw128(wlo + hf * 8192 + k * 32), idesc, 1);
+          }
+        }
+        __syncwarp();
+      }
+      if (elect_one()) {
+        mma_commit_pair(stage_bar(whi));
+        if (kSplit == 3) mma_commit_pair(stage_bar(wlo));
+        if (j == n_chunks - 1) mma_commit_pair(y_full);
+      }
+      __syncwarp();
+    };
+
+    int64_t g = 0;
+    if (tr_on) {
+      long long gt;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+      a.trace[3 * 2048] = clock64(), a.trace[3 * 2048 + 1] = gt;
+    }
+    for (int64_t it = 0; it < my_tiles; it++) {
+      mbar_wait(x_full, ph_x);
+      ph_x ^= 1;
+      tc_fence_after();
+      for (int c = 0; c < n_chunks; c++, g++) {
+        const uint32_t d1 = tmem + TM_DH + (uint32_t)(g & 1) * 128;
+        FFN_TRACE(0, 0, g);
+        {
+          const uint32_t wt = wait_stage();  // W1 hi: Xhi*W1hi, Xlo*W1hi
+          FFN_TRACE(0, 1, g);
+          tc_fence_after();
+          if (elect_one()) {
+#pragma unroll
+            for (int k = 0; k < 8; k++)
+              mma_ts_pair(d1, x_hi + k * 8, desc_kmajor_sw128(wt + (k >> 2) * 8192 + (k & 3) * 32), idesc, k > 0);
+            if (kSplit == 3 && !(a.dbg & 4)) {
+#pragma unroll
+              for (int k = 0; k < 8; k++) mma_ts_pair(d1, x_lo + k * 8, desc_kmajor_sw128(wt + (k >> 2) * 8192 + (k & 3) * 32), idesc, 1);
+            }
+            mma_commit_pair(stage_bar(wt));
+          }
+          __syncwarp();
+        }
+        if (kSplit == 3) {  // W1 lo: Xhi*W1lo
+          const uint32_t wt = wait_stage();
+          tc_fence_after();
+          if (elect_one()) {
+            if (!(a.dbg & 4)) {
+#pragma unroll
+              for (int k = 0; k < 8; k++) mma_ts_pair(d1, x_hi + k * 8, desc_kmajor_sw128(wt + (k >> 2) * 8192 + (k & 3) * 32), idesc, 1);
+            }
+            mma_commit_pair(stage_bar(wt));
+          }
+          __syncwarp();
+        }
+        if (elect_one()) {
+          mma_commit_pair(&d1_full[g & 1]);
+          if (c == n_chunks - 1) mma_commit_pair(x_free);
+        }
+        __syncwarp();
+        FFN_TRACE(0, 2, g);
+        if (g >= 1) issue_g2(g - 1);
+      }
+    }
+    if (G > 0) issue_g2(G - 1);
+    if (tr_on) {
+      long long gt;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+      a.trace[3 * 2048 + 2] = clock64(), a.trace[3 * 2048 + 3] = gt;
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue warps (2 groups x 128 threads), per CTA
+    const int q = warp & 3;
+    const int hf = (warp - 2) >> 2;
+    const int row = q * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    uint32_t ph_d1 = 0, ph_xfree = 0, ph_y = 0;
+    uint8_t* xs = smem + FfnPairSmem::XS;
+    const uint8_t* xs_row = xs + row * kXsRow;
+    auto tile_row0 = [&](int64_t it) -> int64_t { return ((pair + it * n_pairs) * 2 + rank) * 128; };
+
+    uint32_t ph_xsfull = 0;
+    auto x_to_tmem = [&](bool row_valid) {  // staged row -> bf16 hi/lo A-operand images in TMEM (rows beyond M are zeros)
+      mbar_wait(xs_full, ph_xsfull);
+      ph_xsfull ^= 1;
+#pragma unroll 1
+      for (int b = 0; b < 4; b++) {
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          float4 v = *reinterpret_cast<const float4*>(xs_row + b * 128 + j * 16);
+          if (!row_valid) v = make_float4(0.f, 0.f, 0.f, 0.f);
+          split2(v.x, v.y, hi[2 * j], lo[2 * j]);
+          split2(v.z, v.w, hi[2 * j + 1], lo[2 * j + 1]);
+        }
+        tmem_st16(tmem + lane_base + TM_X + b * 16, hi);
+        if (kSplit == 3) tmem_st16(tmem + lane_base + TM_X + 64 + b * 16, lo);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive_cluster(x_full, 0);
+    };
+    // ---- tile boundary.  Every epilogue thread owns 64 columns (its group's half) of its row of Y: it drains them into
+    // registers as soon as the last G2 of the previous tile has retired and immediately re-initialises the same columns
+    // with x + b2 of the new tile (the residual and the second bias ride in the accumulator), so the accumulator is
+    // handed back to the MMA warp after ~1 k cycles; the LayerNorm of the drained tile then runs out of registers, with
+    // the row statistics combined across the two groups through shared memory.
+    auto drain_y = [&](uint32_t (&ya)[32], uint32_t (&yb)[32]) {
+      mbar_wait(y_full, ph_y);
+      ph_y ^= 1;
+      tc_fence_after();
+      tmem_ld32(tmem + lane_base + TM_Y + hf * 64, ya);
+      tmem_ld32(tmem + lane_base + TM_Y + hf * 64 + 32, yb);
+      tmem_ld_wait();
+    };
+    auto init_y = [&](bool row_valid) {
+#pragma unroll 1
+      for (int b = 0; b < 4; b++) {
+        uint32_t r[16];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          float4 v = *reinterpret_cast<const float4*>(xs_row + hf * 256 + b * 64 + j * 16);
+          if (!row_valid) v = make_float4(0.f, 0.f, 0.f, 0.f);
+          const float4 bv = *reinterpret_cast<const float4*>(vecs + hf * 64 + b * 16 + 4 * j);
+          r[4 * j] = __float_as_uint(v.x + bv.x), r[4 * j + 1] = __float_as_uint(v.y + bv.y);
+          r[4 * j + 2] = __float_as_uint(v.z + bv.z), r[4 * j + 3] = __float_as_uint(v.w + bv.w);
+        }
+        tmem_st16(tmem + lane_base + TM_Y + hf * 64 + b * 16, r);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive_cluster(y_init, 0);
+    };
+    float2* stat = reinterpret_cast<float2*>(smem + FfnPairSmem::STAT);
+    uint8_t* park = xs + row * kXsRow + hf * 256;  // this thread's 64 columns of its row in the staging buffer
+    auto layer_norm_half = [&](int64_t row0t, const uint32_t (&ya)[32], const uint32_t (&yb)[32]) {
+      float sum = 0.f, sq = 0.f;
+#pragma unroll
+      for (int j = 0; j < 32; j++) {
+        const float v0 = __uint_as_float(ya[j]), v1 = __uint_as_float(yb[j]);
+        sum += v0 + v1;
+        sq = fmaf(v0, v0, sq), sq = fmaf(v1, v1, sq);
+      }
+      stat[hf * 128 + row] = make_float2(sum, sq);
+      asm volatile("bar.sync 1, 256;" ::: "memory");  // both epilogue groups
+      const float2 other = stat[(hf ^ 1) * 128 + row];
+      sum += other.x, sq += other.y;
+      const float mean = sum * (1.f / 128.f);
+      const float var = fmaxf(sq * (1.f / 128.f) - mean * mean, 0.f);
+      const float rstd = 1.0f / sqrtf(var + a.eps);
+      if (a.pre[net] && row0t + row < a.M) {  // training tape: the pre-LayerNorm sum (row-per-lane stores; not the MH path)
+        float4* prow = reinterpret_cast<float4*>(a.pre[net] + (row0t + row) * 128 + hf * 64);
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          prow[j] = make_float4(__uint_as_float(ya[4 * j]), __uint_as_float(ya[4 * j + 1]), __uint_as_float(ya[4 * j + 2]), __uint_as_float(ya[4 * j + 3]));
+          prow[8 + j] = make_float4(__uint_as_float(yb[4 * j]), __uint_as_float(yb[4 * j + 1]), __uint_as_float(yb[4 * j + 2]), __uint_as_float(yb[4 * j + 3]));
+        }
+      }
+      auto park32 = [&](const uint32_t (&r)[32], int off) {  // 32 normalised columns -> staging buffer
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          const float4 gm = *reinterpret_cast<const float4*>(vecs + 128 + hf * 64 + off + 4 * j);
+          const float4 bt = *reinterpret_cast<const float4*>(vecs + 256 + hf * 64 + off + 4 * j);
+          float4 o;
+          o.x = (__uint_as_float(r[4 * j]) - mean) * rstd * gm.x + bt.x;
+          o.y = (__uint_as_float(r[4 * j + 1]) - mean) * rstd * gm.y + bt.y;
+          o.z = (__uint_as_float(r[4 * j + 2]) - mean) * rstd * gm.z + bt.z;
+          o.w = (__uint_as_float(r[4 * j + 3]) - mean) * rstd * gm.w + bt.w;
+          *reinterpret_cast<float4*>(park + (off + 4 * j) * 4) = o;
+        }
+      };
+      park32(ya, 0);
+      park32(yb, 32);
+      fence_proxy_async_smem();  // generic-proxy writes -> visible to the bulk stores
+    };
+
+    if (hf == 1 && my_tiles > 0) x_to_tmem(tile_row0(0) + row < a.M);
+    int64_t g = 0;
+    for (int64_t it = 0; it < my_tiles; it++) {
+      const bool has_next = it + 1 < my_tiles;
+      const bool row_valid = tile_row0(it) + row < a.M, next_valid = tile_row0(it + 1) + row < a.M;
+      for (int c = 0; c < n_chunks; c++, g++) {
+        const int buf = (int)(g & 1);
+        if (hf == 1 && n_chunks > 1 && c == n_chunks - 1 && has_next) {
+          // the last G1 of this tile and the release of the X images retire together: publish the next tile's images
+          // FIRST, so that its first GEMM is queued behind G2 of the previous chunk without a bubble
+          mbar_wait(x_free, ph_xfree);
+          ph_xfree ^= 1;
+          tc_fence_after();
+          x_to_tmem(next_valid);
+        }
+        // ---- DH[buf][:, hf*64 .. +64): + b1, ReLU, hi/lo split, written back in place as the A operand of G2
+        if (q == 0) { FFN_TRACE(1 + hf, 0, g); }
+        mbar_wait(&d1_full[buf], (ph_d1 >> buf) & 1u);
+        ph_d1 ^= 1u << buf;
+        tc_fence_after();
+        if (q == 0) { FFN_TRACE(1 + hf, 1, g); }
+        if (!(a.dbg & 2)) {
+          const float* bc = b1s + c * kFfnChunk + hf * 64;
+          const uint32_t base = tmem + lane_base + TM_DH + buf * 128 + hf * 64;
+          uint32_t r0[32], r1[32];
+          tmem_ld32(base, r0);
+          tmem_ld32(base + 32, r1);
+          tmem_ld_wait();
+          if (q == 0) { FFN_TRACE(1 + hf, 2, g); }
+          uint32_t hi[16], lo[16];
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            float2 bb = *reinterpret_cast<const float2*>(bc + j);
+            split2(fmaxf(__uint_as_float(r0[j]) + bb.x, 0.f), fmaxf(__uint_as_float(r0[j + 1]) + bb.y, 0.f), hi[j >> 1], lo[j >> 1]);
+          }
+          tmem_st16(base, hi);
+          if (kSplit == 3) tmem_st16(base + 32, lo);
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            float2 bb = *reinterpret_cast<const float2*>(bc + 32 + j);
+            split2(fmaxf(__uint_as_float(r1[j]) + bb.x, 0.f), fmaxf(__uint_as_float(r1[j + 1]) + bb.y, 0.f), hi[j >> 1], lo[j >> 1]);
+          }
+          tmem_st16(base + 16, hi);
+          if (kSplit == 3) tmem_st16(base + 48, lo);
+          tmem_st_wait();
+        }
+        tc_fence_before();
+        if (q == 0) { FFN_TRACE(1 + hf, 3, g); }
+        mbar_arrive_cluster(&h_full[buf * 2 + hf], 0);
+        if (q == 0) { FFN_TRACE(1 + hf, 4, g); }
+
+        if (c == 0) {  // tile boundary: hand the accumulator back first, LayerNorm of the previous tile afterwards
+          uint32_t ya[32], yb[32];
+          if (it > 0) drain_y(ya, yb);
+          if (hf == 0) {  // group 1 has already waited for this tile's staged rows in x_to_tmem
+            mbar_wait(xs_full, ph_xsfull);
+            ph_xsfull ^= 1;
+          }
+          init_y(row_valid);
+          if (it > 0) layer_norm_half(tile_row0(it - 1), ya, yb);
+          mbar_arrive(ln_staged);
+        }
+      }
+      if (n_chunks == 1 && hf == 1 && has_next) {  // single-chunk FFN: publish the next tile's images here
+        mbar_wait(x_free, ph_xfree);
+        ph_xfree ^= 1;
+        tc_fence_after();
+        x_to_tmem(next_valid);
+      }
+    }
+    if (my_tiles > 0) {
+      uint32_t ya[32], yb[32];
+      drain_y(ya, yb);
+      mbar_wait(xs_full, ph_xsfull);  // the staging buffer is free (the previous tile's rows have been stored)
+      layer_norm_half(tile_row0(my_tiles - 1), ya, yb);
+      mbar_arrive(ln_staged);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // the peer may still read this CTA's shared memory / arrive on its barriers until here
+  if (warp == 1) tmem_dealloc_pair<512>(tmem);
+#undef FFN_TRACE
+}
+
+static long long* g_ffn_trace = nullptr;
+void tc_set_ffn_trace(long long* buf) { g_ffn_trace = buf; }
+
+static int launch_ffn_tc(const tw_flow_config* c, const FfnArgs& a_in, cudaStream_t st) {
+  FfnArgs a = a_in;
+  a.trace = g_ffn_trace;
   static bool attr_done = false;
+  static int use_pair = 1;
   if (!attr_done) {
     TW_CUDA(cudaFuncSetAttribute(k_ffn_tc<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, FfnSmem::TOTAL + 1024));
     TW_CUDA(cudaFuncSetAttribute(k_ffn_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FfnSmem::TOTAL + 1024));
+    TW_CUDA(cudaFuncSetAttribute(k_ffn_pair<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, FfnPairSmem::TOTAL + 1024));
+    TW_CUDA(cudaFuncSetAttribute(k_ffn_pair<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FfnPairSmem::TOTAL + 1024));
+    const char* e = getenv("TW_FFN_PAIR");  // bring-up switch: 0 = single-CTA kernel
+    use_pair = e ? atoi(e) : 1;
     attr_done = true;
   }
   TW_CHECK_ARG(a.F <= 4096, "dim_feedforward > 4096 not supported by the tensor-core FFN");
-  int sms = 148;
-  int64_t n_tiles = (a.M + 127) / 128;
-  int gx = (int)((n_tiles < sms / 2) ? n_tiles : sms / 2);
-  if (gx < 1) return TW_OK;
-  dim3 grid(gx, 2);
+  const int sms = 148;
+  const int64_t n_tiles = (a.M + 127) / 128;
+  if (n_tiles < 1) return TW_OK;
   ProfScope prof(PROF_FFN, st);
-  if (c->precision == TW_PRECISION_BF16X3)
-    k_ffn_tc<3><<<grid, kFfnThreads, FfnSmem::TOTAL + 1024, st>>>(a);
-  else
-    k_ffn_tc<1><<<grid, kFfnThreads, FfnSmem::TOTAL + 1024, st>>>(a);
+  if (use_pair && n_tiles >= 2 && a.F <= kPairMaxF) {  // CTA pairs: 256-token tiles, grid.x = 2 * pairs per network
+    const int64_t n_ptiles = (a.M + 255) / 256;
+    const int pairs = (int)((n_ptiles < sms / 4) ? n_ptiles : sms / 4);
+    dim3 grid(2 * pairs, 2);
+    if (c->precision == TW_PRECISION_BF16X3)
+      k_ffn_pair<3><<<grid, kPairThreads, FfnPairSmem::TOTAL + 1024, st>>>(a);
+    else
+      k_ffn_pair<1><<<grid, kPairThreads, FfnPairSmem::TOTAL + 1024, st>>>(a);
+  } else {
+    const int gx = (int)((n_tiles < sms / 2) ? n_tiles : sms / 2);
+    dim3 grid(gx, 2);
+    if (c->precision == TW_PRECISION_BF16X3)
+      k_ffn_tc<3><<<grid, kFfnThreads, FfnSmem::TOTAL + 1024, st>>>(a);
+    else
+      k_ffn_tc<1><<<grid, kFfnThreads, FfnSmem::TOTAL + 1024, st>>>(a);
+  }
   TW_LAUNCH_CHECK();
   return TW_OK;
 }

@@ -1,0 +1,61 @@
+"""Event timeline of the fused FFN kernel (CTA (0,0)): per (tile, chunk) item, when the MMA warp waited / issued and
+when the epilogue groups ran.  Cycles are clock64 of that SM, printed relative to the first traced event."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import timewarp_b200 as tw
+from timewarp_b200 import _lib
+from oracle import flow_oracle as fo
+from timewarp_b200.peptides import tetrapeptide_2olx
+
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
+lo, hi = (int(sys.argv[2]), int(sys.argv[3])) if len(sys.argv) > 3 else (20, 28)
+pep = tetrapeptide_2olx()
+m = tw.custom_transformer_nvp_constructor(tw.kernel_transformer_nvp_config("bf16x3"))
+m.load_state_dict(fo.synth_state_dict(fo.OracleConfig(), 0))
+m = m.cuda().eval()
+g = torch.Generator().manual_seed(0)
+x = (torch.tensor(pep.coords_nm, dtype=torch.float32)[None] + 0.01 * torch.randn(B, 65, 3, generator=g)).cuda()
+y = x + 0.02 * torch.randn(B, 65, 3, generator=g).cuda()
+xv, yv = torch.randn(B, 65, 3, generator=g).cuda(), torch.randn(B, 65, 3, generator=g).cuda()
+at = torch.tensor(pep.atom_types)[None].repeat(B, 1).cuda()
+mask = torch.zeros(B, 65, dtype=torch.bool).cuda()
+e = torch.zeros(0, 2, dtype=torch.long).cuda()
+kw = dict(atom_types=at, x_coords=x, x_velocs=xv, y_coords=y, y_velocs=yv, adj_list=e, edge_batch_idx=e[:, 0], masked_elements=mask)
+with torch.no_grad():
+    m.log_likelihood(**kw)
+    torch.cuda.synchronize()
+    buf = torch.zeros(3 * 1024 * 2 + 8, dtype=torch.int64, device="cuda")
+    lib = _lib.load()
+    lib.tw_debug_set_ffn_trace(buf.data_ptr())
+    m.log_likelihood(**kw)
+    torch.cuda.synchronize()
+    lib.tw_debug_set_ffn_trace(None)
+raw = buf.cpu().numpy()
+t = raw[:3 * 2048].reshape(3, 1024, 2)
+c0, g0, c1, g1 = (int(v) for v in raw[3 * 2048:3 * 2048 + 4])
+if g1 > g0:
+    print(f"MMA warp: {c1 - c0} cycles in {g1 - g0} ns -> SM clock {1e3 * (c1 - c0) / (g1 - g0):.0f} MHz")
+t0 = min(int(t[r, 0, 1]) for r in range(3) if t[r, 0, 1] > 0)
+names = {0: {0: "mma: loop top", 1: "mma: W1hi landed", 2: "mma: G1 issued+committed", 3: "mma: W2 landed", 4: "mma: h_full[0] -> G2a", 5: "mma: h_full[1] -> G2b"},
+         1: {0: "epi0: wait d1", 1: "epi0: d1_full", 2: "epi0: ld done", 3: "epi0: st done", 4: "epi0: arrived", 5: "epi0: LN got y_full (item=tile128)", 6: "epi0: LN stats done", 7: "epi0: LN y_free"},
+         2: {0: "epi1: wait d1", 1: "epi1: d1_full", 2: "epi1: ld done", 3: "epi1: st done", 4: "epi1: arrived", 5: "epi1: got y_free", 6: "epi1: init_y done"}}
+rows = []
+for r in range(3):
+    for i in range(1024):
+        code, clk = int(t[r, i, 0]), int(t[r, i, 1])
+        if clk == 0:
+            break
+        ev, item = code & 0xFF, code >> 8
+        if lo <= item < hi or (r == 1 and ev >= 5 and lo <= item * 8 + 16 < hi + 16):
+            rows.append((clk - t0, item, names[r][ev]))
+rows.sort()
+prev = rows[0][0] if rows else 0
+for clk, item, name in rows:
+    print(f"{clk:9d} (+{clk - prev:5d})  item {item:3d}  {name}")
+    prev = clk
+# per-item period of the MMA warp
+tops = [(int(t[0, i, 0]) >> 8, int(t[0, i, 1])) for i in range(1024) if t[0, i, 1] > 0 and (int(t[0, i, 0]) & 0xFF) == 0]
+if len(tops) > 20:
+    d = np.diff([c for _, c in tops])
+    print("MMA-warp iteration period: median", np.median(d), "mean", d.mean(), "min", d.min(), "max", d.max(), "n", len(d))
