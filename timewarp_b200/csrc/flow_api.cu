@@ -331,5 +331,9 @@ int tw_debug_set_ffn_trace(long long* device_buf) {
   tc_set_ffn_trace(device_buf);
   return TW_OK;
 }
+int tw_debug_set_trace(int kernel_class, long long* device_buf) {
+  tc_set_trace(kernel_class, device_buf);
+  return TW_OK;
+}
 
 }  // extern "C"

@@ -12,6 +12,14 @@
 namespace tw {
 using namespace umma;
 
+// Debug event trace (tw_debug_set_trace): CTA (0,0) records {event | item << 8, clock64} per warp role.
+#define TW_TRACE(buf, on, cnt, role, ev, item)                                      \
+  if ((on) && (cnt) < 1024) {                                                       \
+    (buf)[((role) * 1024 + (cnt)) * 2] = (long long)(ev) | ((long long)(item) << 8); \
+    (buf)[((role) * 1024 + (cnt)) * 2 + 1] = clock64();                             \
+    (cnt)++;                                                                        \
+  }
+
 // ============================================================================================
 // packed-weight layout
 constexpr int kTileBytes128 = 128 * 128 * 2;  // [128 rows x 128 K] bf16 = two [128 x 64] swizzled K blocks
@@ -1110,7 +1118,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1) k_f
 }
 
 static long long* g_ffn_trace = nullptr;
+static long long* g_mix_trace = nullptr;
 void tc_set_ffn_trace(long long* buf) { g_ffn_trace = buf; }
+void tc_set_trace(int cls, long long* buf) {
+  if (cls == 1) g_ffn_trace = buf;
+  if (cls == 2) g_mix_trace = buf;
+}
 
 static int launch_ffn_tc(const tw_flow_config* c, const FfnArgs& a_in, cudaStream_t st) {
   FfnArgs a = a_in;
@@ -1194,6 +1207,7 @@ struct MixArgs {
   int64_t n, n_cond;
   int V, VP, H;
   int n_stages;              // ring depth (3, or 2 when VP > 96)
+  long long* trace;          // optional event trace (debug)
 };
 
 __device__ __forceinline__ void split1(float v, uint16_t& hi, uint16_t& lo) {
@@ -1245,6 +1259,9 @@ __global__ void __launch_bounds__(320, 1) k_mix_tc(MixArgs a) {
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const int ksteps = VP / 16;
+  const bool tr_on = a.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0;
+  int tr_n = 0;
+#define MIX_TRACE(role, ev, item) TW_TRACE(a.trace, tr_on, tr_n, role, ev, item)
 
   if (warp == 0) {
     uint32_t stage = 0, phase = 0;
@@ -1268,9 +1285,11 @@ __global__ void __launch_bounds__(320, 1) k_mix_tc(MixArgs a) {
     int64_t it = 0, hcount = 0;
     for (int64_t n = blockIdx.x; n < a.n; n += gridDim.x, it++) {
       const int sb = it & 1;
+      MIX_TRACE(0, 0, it);
       mbar_wait(&hs_full[sb], ph_hs[sb]);
       ph_hs[sb] ^= 1;
       tc_fence_after();
+      MIX_TRACE(0, 1, it);
       const uint32_t hs_hi = tmem + MX_HS + sb * 128, hs_lo = hs_hi + 64;
       for (int h = 0; h < H; h++, hcount++) {
         const int db = hcount & 1;
@@ -1278,8 +1297,10 @@ __global__ void __launch_bounds__(320, 1) k_mix_tc(MixArgs a) {
           mbar_wait(&d_free[db], ph_dfree[db]);
           ph_dfree[db] ^= 1;
         }
+        MIX_TRACE(0, 2, hcount);
         mbar_wait(&full[stage], phase);
         tc_fence_after();
+        MIX_TRACE(0, 3, hcount);
         if (elect_one()) {
           const uint32_t s_hi = smem_u32(ring + stage * stage_stride), s_lo = s_hi + mat_bytes;
           const uint32_t d = tmem + MX_D + db * 128;
@@ -1296,6 +1317,7 @@ __global__ void __launch_bounds__(320, 1) k_mix_tc(MixArgs a) {
           if (h == H - 1) mma_commit(&hs_free[sb]);
         }
         __syncwarp();
+        MIX_TRACE(0, 4, hcount);
         if (++stage == (uint32_t)n_stages) stage = 0, phase ^= 1;
       }
     }
@@ -1315,6 +1337,7 @@ __global__ void __launch_bounds__(320, 1) k_mix_tc(MixArgs a) {
 
     auto load_hs = [&](int64_t n, int64_t it) {  // column blocks of X^T are split between the groups
       const int sb = it & 1;
+      if (q == 0) { MIX_TRACE(1 + g, 0, it); }
       if (it >= 2) {
         mbar_wait(&hs_free[sb], ph_hsfree[sb]);
         ph_hsfree[sb] ^= 1;
@@ -1337,6 +1360,7 @@ __global__ void __launch_bounds__(320, 1) k_mix_tc(MixArgs a) {
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&hs_full[sb]);
+      if (q == 0) { MIX_TRACE(1 + g, 1, it); }
     };
 
     int64_t it = 0, hcount = 0;
@@ -1347,6 +1371,7 @@ __global__ void __launch_bounds__(320, 1) k_mix_tc(MixArgs a) {
       for (int h = 0; h < H; h++, hcount++) {
         const int db = hcount & 1;
         if (n_groups == 2 && db != g) continue;
+        if (q == 0) { MIX_TRACE(1 + g, 2, hcount); }
         if (n_groups == 2) {
           mbar_wait(&d_full[db], ph_dfull);
           ph_dfull ^= 1;
@@ -1354,6 +1379,7 @@ __global__ void __launch_bounds__(320, 1) k_mix_tc(MixArgs a) {
           mbar_wait(&d_full[db], (uint32_t)((hcount >> 1) & 1));
         }
         tc_fence_after();
+        if (q == 0) { MIX_TRACE(1 + g, 3, hcount); }
         // (1) accumulator -> bf16 hi/lo rows in the staging buffer [token i][feature f]; rows >= V are scratch
         for (int c0 = 0; c0 < VP; c0 += 16) {
           uint32_t r[16];
@@ -1374,7 +1400,9 @@ __global__ void __launch_bounds__(320, 1) k_mix_tc(MixArgs a) {
         }
         tc_fence_before();
         mbar_arrive(&d_free[db]);
+        if (q == 0) { MIX_TRACE(1 + g, 4, hcount); }
         group_bar_sync(g);
+        if (q == 0) { MIX_TRACE(1 + g, 5, hcount); }
         // (2) 16-byte chunks -> swizzled operand images in global memory
         const int n_chunks = V * (kSplit == 3 ? 32 : 16);
         for (int cid = et; cid < n_chunks; cid += 128) {
@@ -1388,13 +1416,248 @@ __global__ void __launch_bounds__(320, 1) k_mix_tc(MixArgs a) {
                          ((((uint32_t)c & 7u) ^ (row & 7u)) << 4);
           *reinterpret_cast<uint4*>(dst) = v;
         }
+        if (q == 0) { MIX_TRACE(1 + g, 6, hcount); }
         group_bar_sync(g);
+        if (q == 0) { MIX_TRACE(1 + g, 7, hcount); }
       }
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc<512>(tmem);
+#undef MIX_TRACE
+}
+
+// ============================================================================================
+// Attention, step 2, token-major form (atom counts up to 80):  mixed_h = A_h x  with the TOKENS of one sample on the
+// TMEM lanes,
+//   D[128 i, 128 f] = A_h[i, j] (A operand: the [VP x VP] K-major score image, rows >= VP read scratch and are never
+//                                 stored) * X[j, f] (B operand: the sample's x as bf16 hi/lo, MN-major SW128 tiles)
+// so the accumulator row of a thread IS a row of the A-operand image the projection kernel reads: the epilogue only
+// converts to bf16 hi/lo and writes swizzled 16-byte chunks (no transposition through 2-byte shared-memory stores,
+// which bound the feature-major kernel), stages whole image rows and hands them to bulk stores.
+//   warp 0: score images (bulk loads)          warp 1: MMA issuer          warps 2-3: x -> bf16 hi/lo operand tiles
+//   warps 4-7 / 8-11: two epilogue groups draining alternate heads (double-buffered accumulator)
+constexpr int kMixTokThreads = 384;
+constexpr int kMixTokMaxVP = 80;
+
+struct MixTokSmem {
+  int VP;
+  uint32_t stage_stride, xb_bytes, out_bytes;
+  __host__ __device__ explicit MixTokSmem(int vp) : VP(vp) {
+    stage_stride = (uint32_t)((2 * vp * vp * 2 + 1023) & ~1023);
+    xb_bytes = (uint32_t)(4 * vp * 128);   // [hi: 2 N blocks x VP rows x 128 B][lo: same]
+    out_bytes = (uint32_t)(4 * vp * 128);  // [kb0 hi][kb0 lo][kb1 hi][kb1 lo], VP rows x 128 B each
+  }
+  __host__ __device__ uint32_t ring() const { return 0; }
+  __host__ __device__ uint32_t xb(int b) const { return 2 * stage_stride + b * xb_bytes; }
+  __host__ __device__ uint32_t out(int g) const { return 2 * stage_stride + 2 * xb_bytes + g * out_bytes; }
+  __host__ __device__ uint32_t bars() const { return 2 * stage_stride + 2 * xb_bytes + 2 * out_bytes; }
+  __host__ __device__ uint32_t total() const { return bars() + 256; }
+};
+
+template <int kSplit>
+__global__ void __launch_bounds__(kMixTokThreads, 1) k_mix_tok(MixArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int net = blockIdx.y;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int V = a.V, VP = a.VP, H = a.H;
+  const MixTokSmem L(VP);
+  const uint32_t mat_bytes = (uint32_t)VP * VP * 2;
+  const uint32_t stage_bytes = 2 * mat_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bars());
+  uint64_t* full = bars;           // [2] score image of a head landed
+  uint64_t* empty = full + 2;      // [2]
+  uint64_t* xb_full = empty + 2;   // [2] x operand tiles of a sample written (64 arrivals)
+  uint64_t* xb_free = xb_full + 2; // [2] every MMA of that sample has retired
+  uint64_t* d_full = xb_free + 2;  // [2]
+  uint64_t* d_free = d_full + 2;   // [2] 128 arrivals
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d_free + 2);
+
+  if (tid == 0) {
+    for (int i = 0; i < 2; i++) {
+      mbar_init(&full[i], 1), mbar_init(&empty[i], 1);
+      mbar_init(&xb_full[i], 64), mbar_init(&xb_free[i], 1);
+      mbar_init(&d_full[i], 1), mbar_init(&d_free[i], 128);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc<256>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const int ksteps = VP / 16;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ score images
+    uint32_t stage = 0, phase = 0;
+    for (int64_t n = blockIdx.x; n < a.n; n += gridDim.x) {
+      const uint8_t* src = a.scores_img + (size_t)(n % a.n_cond) * H * stage_bytes;
+      for (int h = 0; h < H; h++) {
+        mbar_wait(&empty[stage], phase ^ 1);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&full[stage], kSplit == 3 ? stage_bytes : mat_bytes);
+          bulk_g2s(smem + L.ring() + stage * L.stage_stride, src + (size_t)h * stage_bytes, kSplit == 3 ? stage_bytes : mat_bytes, &full[stage]);
+        }
+        __syncwarp();
+        if (++stage == 2) stage = 0, phase ^= 1;
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    uint32_t stage = 0, phase = 0, ph_xb = 0 /* bit per buffer */, ph_dfree = 0;
+    const uint32_t idesc = make_idesc_bf16(128, 128, 0, 1);  // A K-major, B MN-major
+    const uint32_t a_lbo = 128, a_sbo = (uint32_t)(VP >> 3) * 128;
+    const uint32_t b_lbo = (uint32_t)VP * 128;  // stride between the two 64-feature N blocks
+    int64_t it = 0, hcount = 0;
+    for (int64_t n = blockIdx.x; n < a.n; n += gridDim.x, it++) {
+      const int sb = (int)(it & 1);
+      mbar_wait(&xb_full[sb], (ph_xb >> sb) & 1u);
+      ph_xb ^= 1u << sb;
+      tc_fence_after();
+      const uint32_t x_hi = smem_u32(smem + L.xb(sb)), x_lo = x_hi + L.xb_bytes / 2;
+      for (int h = 0; h < H; h++, hcount++) {
+        const int db = (int)(hcount & 1);
+        if (hcount >= 2) {
+          mbar_wait(&d_free[db], (ph_dfree >> db) & 1u);
+          ph_dfree ^= 1u << db;
+        }
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t s_hi = smem_u32(smem + L.ring() + stage * L.stage_stride), s_lo = s_hi + mat_bytes;
+          const uint32_t d = tmem + db * 128;
+          for (int k = 0; k < ksteps; k++)
+            mma_ss(d, make_smem_desc(s_hi + k * 256, a_lbo, a_sbo, LAYOUT_NONE), make_smem_desc(x_hi + k * 2048, b_lbo, 1024, LAYOUT_SW128), idesc, k > 0);
+          if (kSplit == 3) {
+            for (int k = 0; k < ksteps; k++)
+              mma_ss(d, make_smem_desc(s_lo + k * 256, a_lbo, a_sbo, LAYOUT_NONE), make_smem_desc(x_hi + k * 2048, b_lbo, 1024, LAYOUT_SW128), idesc, 1);
+            for (int k = 0; k < ksteps; k++)
+              mma_ss(d, make_smem_desc(s_hi + k * 256, a_lbo, a_sbo, LAYOUT_NONE), make_smem_desc(x_lo + k * 2048, b_lbo, 1024, LAYOUT_SW128), idesc, 1);
+          }
+          mma_commit(&empty[stage]);
+          mma_commit(&d_full[db]);
+          if (h == H - 1) mma_commit(&xb_free[sb]);
+        }
+        __syncwarp();
+        if (++stage == 2) stage = 0, phase ^= 1;
+      }
+    }
+  } else if (warp < 4) {
+    // ------------------------------------------------------------------ x of a sample -> bf16 hi/lo B-operand tiles
+    // [atom j][64 features] rows of 128 B, 128-byte swizzle: the bytes of a K-major tile, read MN-major (N = feature).
+    const int cw = warp - 2;  // rows j = cw, cw + 2, ...
+    const float* x = a.x[net];
+    uint32_t ph_free = 0;
+    int64_t it = 0;
+    const int nb = lane >> 4;                 // N block of the 4 features this lane converts
+    const uint32_t c16 = (uint32_t)(lane & 15) >> 1, sub = (uint32_t)(lane & 1) * 8;
+    for (int64_t n = blockIdx.x; n < a.n; n += gridDim.x, it++) {
+      const int sb = (int)(it & 1);
+      if (it >= 2) {
+        mbar_wait(&xb_free[sb], (ph_free >> sb) & 1u);
+        ph_free ^= 1u << sb;
+      }
+      uint8_t* hi_base = smem + L.xb(sb) + nb * (VP * 128);
+      uint8_t* lo_base = hi_base + L.xb_bytes / 2;
+      const float4* src = reinterpret_cast<const float4*>(x + n * V * 128) + lane;
+      for (int j0 = cw; j0 < VP; j0 += 16) {  // 8 rows per warp in flight
+        float4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+          const int j = j0 + 2 * u;
+          v[u] = (j < V) ? __ldg(src + (size_t)j * 32) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+          const int j = j0 + 2 * u;
+          if (j < VP) {
+            uint32_t h0, l0, h1, l1;
+            split2(v[u].x, v[u].y, h0, l0);
+            split2(v[u].z, v[u].w, h1, l1);
+            const uint32_t off = (uint32_t)j * 128u + ((c16 ^ ((uint32_t)j & 7u)) << 4) + sub;
+            *reinterpret_cast<uint2*>(hi_base + off) = make_uint2(h0, h1);
+            if (kSplit == 3) *reinterpret_cast<uint2*>(lo_base + off) = make_uint2(l0, l1);
+          }
+        }
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(&xb_full[sb]);
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue groups
+    const int q = warp & 3;
+    const int g = (warp - 4) >> 2;
+    const int i = q * 32 + lane;  // token (atom) of the sample = TMEM lane
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    const bool warp_active = q * 32 < V;
+    const bool leader = (q == 0 && lane == 0);
+    uint8_t* img = a.img[net];
+    const size_t tile_bytes = (size_t)H * 2 * 2 * 16384;
+    uint8_t* stg = smem + L.out(g);
+    const uint32_t region = (uint32_t)VP * 128;  // one (K block, hi/lo) region of the staging buffer
+    uint32_t ph_dfull = 0;
+    int64_t hcount = 0;
+    bool stores_pending = false;
+    for (int64_t n = blockIdx.x; n < a.n; n += gridDim.x) {
+      const int64_t t0 = n * V;
+      const uint32_t sw = (uint32_t)((t0 + i) & 7);  // swizzle phase of this token's row in the global image
+      for (int h = 0; h < H; h++, hcount++) {
+        const int db = (int)(hcount & 1);
+        if (db != g) continue;
+        mbar_wait(&d_full[db], ph_dfull);
+        ph_dfull ^= 1;
+        tc_fence_after();
+        if (leader && stores_pending) bulk_wait_group_read0();  // the previous head's rows have left the staging buffer
+        group_bar_sync(g);
+        if (warp_active) {
+#pragma unroll 1
+          for (int g4 = 0; g4 < 4; g4++) {
+            uint32_t r[32];
+            tmem_ld32(tmem + lane_base + db * 128 + g4 * 32, r);
+            tmem_ld_wait();
+            uint32_t hi[16], lo[16];
+#pragma unroll
+            for (int j = 0; j < 16; j++) split2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]), hi[j], lo[j]);
+            if (i < V) {
+              uint8_t* row_hi = stg + (g4 >> 1) * 2 * region + i * 128;
+              uint8_t* row_lo = row_hi + region;
+#pragma unroll
+              for (int cc = 0; cc < 4; cc++) {
+                const uint32_t pos = ((((uint32_t)(g4 & 1) * 4 + cc) ^ sw) << 4);
+                *reinterpret_cast<uint4*>(row_hi + pos) = make_uint4(hi[4 * cc], hi[4 * cc + 1], hi[4 * cc + 2], hi[4 * cc + 3]);
+                if (kSplit == 3) *reinterpret_cast<uint4*>(row_lo + pos) = make_uint4(lo[4 * cc], lo[4 * cc + 1], lo[4 * cc + 2], lo[4 * cc + 3]);
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(&d_free[db]);
+        fence_proxy_async_smem();
+        group_bar_sync(g);
+        if (leader) {  // whole image rows -> global: per (K block, hi/lo) one piece, two where the sample straddles a tile
+          const int64_t tile = t0 >> 7;
+          const int r0 = (int)(t0 & 127);
+          const int n1 = (V < 128 - r0) ? V : 128 - r0;
+          for (int kb = 0; kb < 2; kb++)
+            for (int hl = 0; hl < (kSplit == 3 ? 2 : 1); hl++) {
+              const uint8_t* src = stg + (kb * 2 + hl) * region;
+              uint8_t* dst = img + tile * tile_bytes + (size_t)(h * 2 + kb) * 32768 + hl * 16384;
+              bulk_s2g(dst + r0 * 128, src, (uint32_t)n1 * 128u);
+              if (n1 < V) bulk_s2g(dst + tile_bytes, src + n1 * 128, (uint32_t)(V - n1) * 128u);
+            }
+          bulk_commit_group();
+          stores_pending = true;
+        }
+      }
+    }
+    if (leader) bulk_wait_group0();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<256>(tmem);
 }
 
 // ============================================================================================
@@ -1991,9 +2254,27 @@ int tc_mix(const tw_flow_config* c, const float* const x[2], uint8_t* const img[
   for (int s = 0; s < 2; s++) a.x[s] = x[s], a.img[s] = img[s];
   a.scores_img = scores_img;
   a.n = n, a.n_cond = n_cond, a.V = V, a.VP = VP, a.H = H, a.n_stages = mix_stages;
+  a.trace = g_mix_trace;
   int gx = (int)(n < 74 ? n : 74);
   if (gx < 1) return TW_OK;
   dim3 grid(gx, 2);
+  static int use_tok = -1;
+  if (use_tok < 0) {
+    const char* e = getenv("TW_MIX_TOK");  // bring-up switch: 0 = feature-major kernel for every atom count
+    use_tok = e ? atoi(e) : 1;
+    const int max_smem = (int)MixTokSmem(kMixTokMaxVP).total() + 1024;
+    TW_CUDA(cudaFuncSetAttribute(k_mix_tok<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    TW_CUDA(cudaFuncSetAttribute(k_mix_tok<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+  }
+  if (use_tok && VP <= kMixTokMaxVP) {
+    const int smem_tok = (int)MixTokSmem(VP).total() + 1024;
+    if (c->precision == TW_PRECISION_BF16X3)
+      k_mix_tok<3><<<grid, kMixTokThreads, smem_tok, st>>>(a);
+    else
+      k_mix_tok<1><<<grid, kMixTokThreads, smem_tok, st>>>(a);
+    TW_LAUNCH_CHECK();
+    return TW_OK;
+  }
   if (c->precision == TW_PRECISION_BF16X3)
     k_mix_tc<3><<<grid, 64 + 128 * mix_groups, mix_smem, st>>>(a);
   else

@@ -38,7 +38,8 @@ int tc_pack_weights(const tw_flow_config* c, const ParamView& pv, uint8_t* packe
 int tc_begin_pass(const tw_flow_config* c, const ParamView& pv, TcScratch& tc, const float* scores, const uint8_t* mask,
                   int64_t n, int64_t n_cond, int V, cudaStream_t st);
 size_t tc_packed_bytes(const tw_flow_config* c);
-void tc_set_ffn_trace(long long* buf);  // debug: event trace of the fused FFN (see FfnArgs::trace)
+void tc_set_ffn_trace(long long* buf);
+void tc_set_trace(int cls, long long* buf);  // 1 fused FFN, 2 mixing kernel  // debug: event trace of the fused FFN (see FfnArgs::trace)
 // fused FFN + residual + LayerNorm of encoder layer t for both networks: out = LN2(x + FFN(x))
 // out = LN1(x + sum_h W_c,h (A_h x)) for both networks (tensor-core mixing + projection)
 int tc_attention_layer(const tw_flow_config* c, const ParamView& pv, int k, int t, const TcScratch& tc, float* const x[2],

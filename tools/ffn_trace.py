@@ -10,6 +10,7 @@ from timewarp_b200.peptides import tetrapeptide_2olx
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 lo, hi = (int(sys.argv[2]), int(sys.argv[3])) if len(sys.argv) > 3 else (20, 28)
+cls = int(sys.argv[4]) if len(sys.argv) > 4 else 1  # 1 fused FFN, 2 mixing kernel
 pep = tetrapeptide_2olx()
 m = tw.custom_transformer_nvp_constructor(tw.kernel_transformer_nvp_config("bf16x3"))
 m.load_state_dict(fo.synth_state_dict(fo.OracleConfig(), 0))
@@ -27,19 +28,24 @@ with torch.no_grad():
     torch.cuda.synchronize()
     buf = torch.zeros(3 * 1024 * 2 + 8, dtype=torch.int64, device="cuda")
     lib = _lib.load()
-    lib.tw_debug_set_ffn_trace(buf.data_ptr())
+    lib.tw_debug_set_trace(cls, buf.data_ptr())
     m.log_likelihood(**kw)
     torch.cuda.synchronize()
-    lib.tw_debug_set_ffn_trace(None)
+    lib.tw_debug_set_trace(cls, None)
 raw = buf.cpu().numpy()
 t = raw[:3 * 2048].reshape(3, 1024, 2)
 c0, g0, c1, g1 = (int(v) for v in raw[3 * 2048:3 * 2048 + 4])
 if g1 > g0:
     print(f"MMA warp: {c1 - c0} cycles in {g1 - g0} ns -> SM clock {1e3 * (c1 - c0) / (g1 - g0):.0f} MHz")
 t0 = min(int(t[r, 0, 1]) for r in range(3) if t[r, 0, 1] > 0)
-names = {0: {0: "mma: loop top", 1: "mma: W1hi landed", 2: "mma: G1 issued+committed", 3: "mma: W2 landed", 4: "mma: h_full[0] -> G2a", 5: "mma: h_full[1] -> G2b"},
-         1: {0: "epi0: wait d1", 1: "epi0: d1_full", 2: "epi0: ld done", 3: "epi0: st done", 4: "epi0: arrived", 5: "epi0: LN got y_full (item=tile128)", 6: "epi0: LN stats done", 7: "epi0: LN y_free"},
-         2: {0: "epi1: wait d1", 1: "epi1: d1_full", 2: "epi1: ld done", 3: "epi1: st done", 4: "epi1: arrived", 5: "epi1: got y_free", 6: "epi1: init_y done"}}
+if cls == 2:
+    names = {0: {0: 'mma: sample top', 1: 'mma: hs_full', 2: 'mma: head top', 3: 'mma: scores landed', 4: 'mma: head issued'},
+             1: {0: 'epi0: load_hs start', 1: 'epi0: load_hs done', 2: 'epi0: wait d_full', 3: 'epi0: d_full', 4: 'epi0: staged', 5: 'epi0: sync1', 6: 'epi0: stores issued', 7: 'epi0: sync2'},
+             2: {0: 'epi1: load_hs start', 1: 'epi1: load_hs done', 2: 'epi1: wait d_full', 3: 'epi1: d_full', 4: 'epi1: staged', 5: 'epi1: sync1', 6: 'epi1: stores issued', 7: 'epi1: sync2'}}
+else:
+  names = {0: {0: "mma: loop top", 1: "mma: W1hi landed", 2: "mma: G1 issued+committed", 3: "mma: W2 landed", 4: "mma: h_full[0] -> G2a", 5: "mma: h_full[1] -> G2b"},
+           1: {0: "epi0: wait d1", 1: "epi0: d1_full", 2: "epi0: ld done", 3: "epi0: st done", 4: "epi0: arrived", 5: "epi0: LN got y_full (item=tile128)", 6: "epi0: LN stats done", 7: "epi0: LN y_free"},
+           2: {0: "epi1: wait d1", 1: "epi1: d1_full", 2: "epi1: ld done", 3: "epi1: st done", 4: "epi1: arrived", 5: "epi1: got y_free", 6: "epi1: init_y done"}}
 rows = []
 for r in range(3):
     for i in range(1024):
