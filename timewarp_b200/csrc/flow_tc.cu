@@ -1441,18 +1441,27 @@ __global__ void __launch_bounds__(320, 1) k_mix_tc(MixArgs a) {
 constexpr int kMixTokThreads = 384;
 constexpr int kMixTokMaxVP = 80;
 
+constexpr int kMixTokStages = 3;  // score-image ring depth (2 when three stages do not fit next to the other buffers)
 struct MixTokSmem {
-  int VP;
-  uint32_t stage_stride, xb_bytes, out_bytes;
-  __host__ __device__ explicit MixTokSmem(int vp) : VP(vp) {
-    stage_stride = (uint32_t)((2 * vp * vp * 2 + 1023) & ~1023);
-    xb_bytes = (uint32_t)(4 * vp * 128);   // [hi: 2 N blocks x VP rows x 128 B][lo: same]
-    out_bytes = (uint32_t)(4 * vp * 128);  // [kb0 hi][kb0 lo][kb1 hi][kb1 lo], VP rows x 128 B each
+  uint32_t stage_bytes, xb_bytes, out_bytes;
+  int n_stages;
+  __host__ __device__ MixTokSmem(int v, int vp, int stages) : n_stages(stages) {
+    stage_bytes = (uint32_t)(2 * vp * vp * 2);  // score image of one head: hi | lo (un-swizzled: 16-byte alignment is enough)
+    xb_bytes = (uint32_t)(4 * vp * 128);        // [hi: 2 N blocks x VP rows x 128 B][lo: same], 1024-byte aligned (128-byte swizzle)
+    out_bytes = (uint32_t)(4 * v * 128);        // [kb0 hi][kb0 lo][kb1 hi][kb1 lo], V rows x 128 B each
+    overread = (uint32_t)(2 * vp * (128 - vp));
   }
-  __host__ __device__ uint32_t ring() const { return 0; }
-  __host__ __device__ uint32_t xb(int b) const { return 2 * stage_stride + b * xb_bytes; }
-  __host__ __device__ uint32_t out(int g) const { return 2 * stage_stride + 2 * xb_bytes + g * out_bytes; }
-  __host__ __device__ uint32_t bars() const { return 2 * stage_stride + 2 * xb_bytes + 2 * out_bytes; }
+  // The MMA reads 128 rows of every score image (A operand, M = 128) although only VP exist: rows >= VP fall up to
+  // 2*VP*(128-VP) bytes behind the ring, so the staging buffers (never read by an MMA) and, for tiny samples, an
+  // explicit pad sit behind it.
+  uint32_t overread;
+  __host__ __device__ uint32_t xb(int b) const { return b * xb_bytes; }
+  __host__ __device__ uint32_t ring() const { return 2 * xb_bytes; }
+  __host__ __device__ uint32_t out(int g) const { return (ring() + n_stages * stage_bytes + 15 & ~15u) + g * out_bytes; }
+  __host__ __device__ uint32_t bars() const {
+    const uint32_t behind = 2 * out_bytes;
+    return (out(0) + (behind > overread ? behind : overread) + 15) & ~15u;
+  }
   __host__ __device__ uint32_t total() const { return bars() + 256; }
 };
 
@@ -1463,21 +1472,22 @@ __global__ void __launch_bounds__(kMixTokThreads, 1) k_mix_tok(MixArgs a) {
   const int net = blockIdx.y;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int V = a.V, VP = a.VP, H = a.H;
-  const MixTokSmem L(VP);
+  const int n_stages = a.n_stages;
+  const MixTokSmem L(V, VP, n_stages);
   const uint32_t mat_bytes = (uint32_t)VP * VP * 2;
   const uint32_t stage_bytes = 2 * mat_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bars());
-  uint64_t* full = bars;           // [2] score image of a head landed
-  uint64_t* empty = full + 2;      // [2]
-  uint64_t* xb_full = empty + 2;   // [2] x operand tiles of a sample written (64 arrivals)
+  uint64_t* full = bars;                      // [kMixTokStages] score image of a head landed
+  uint64_t* empty = full + kMixTokStages;     // [kMixTokStages]
+  uint64_t* xb_full = empty + kMixTokStages;  // [2] x operand tiles of a sample written (64 arrivals)
   uint64_t* xb_free = xb_full + 2; // [2] every MMA of that sample has retired
   uint64_t* d_full = xb_free + 2;  // [2]
   uint64_t* d_free = d_full + 2;   // [2] 128 arrivals
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d_free + 2);
 
   if (tid == 0) {
+    for (int i = 0; i < kMixTokStages; i++) mbar_init(&full[i], 1), mbar_init(&empty[i], 1);
     for (int i = 0; i < 2; i++) {
-      mbar_init(&full[i], 1), mbar_init(&empty[i], 1);
       mbar_init(&xb_full[i], 64), mbar_init(&xb_free[i], 1);
       mbar_init(&d_full[i], 1), mbar_init(&d_free[i], 128);
     }
@@ -1489,6 +1499,9 @@ __global__ void __launch_bounds__(kMixTokThreads, 1) k_mix_tok(MixArgs a) {
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const int ksteps = VP / 16;
+  const bool tr_on = a.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0;
+  int tr_n = 0;
+#define MIX_TRACE(role, ev, item) TW_TRACE(a.trace, tr_on, tr_n, role, ev, item)
 
   if (warp == 0) {
     // ------------------------------------------------------------------ score images
@@ -1499,10 +1512,10 @@ __global__ void __launch_bounds__(kMixTokThreads, 1) k_mix_tok(MixArgs a) {
         mbar_wait(&empty[stage], phase ^ 1);
         if (elect_one()) {
           mbar_arrive_expect_tx(&full[stage], kSplit == 3 ? stage_bytes : mat_bytes);
-          bulk_g2s(smem + L.ring() + stage * L.stage_stride, src + (size_t)h * stage_bytes, kSplit == 3 ? stage_bytes : mat_bytes, &full[stage]);
+          bulk_g2s(smem + L.ring() + stage * L.stage_bytes, src + (size_t)h * stage_bytes, kSplit == 3 ? stage_bytes : mat_bytes, &full[stage]);
         }
         __syncwarp();
-        if (++stage == 2) stage = 0, phase ^= 1;
+        if (++stage == (uint32_t)n_stages) stage = 0, phase ^= 1;
       }
     }
   } else if (warp == 1) {
@@ -1511,38 +1524,50 @@ __global__ void __launch_bounds__(kMixTokThreads, 1) k_mix_tok(MixArgs a) {
     const uint32_t idesc = make_idesc_bf16(128, 128, 0, 1);  // A K-major, B MN-major
     const uint32_t a_lbo = 128, a_sbo = (uint32_t)(VP >> 3) * 128;
     const uint32_t b_lbo = (uint32_t)VP * 128;  // stride between the two 64-feature N blocks
+    const uint64_t a_desc0 = make_smem_desc(0, a_lbo, a_sbo, LAYOUT_NONE), b_desc0 = make_smem_desc(0, b_lbo, 1024, LAYOUT_SW128);
     int64_t it = 0, hcount = 0;
     for (int64_t n = blockIdx.x; n < a.n; n += gridDim.x, it++) {
       const int sb = (int)(it & 1);
+      MIX_TRACE(0, 0, it);
       mbar_wait(&xb_full[sb], (ph_xb >> sb) & 1u);
       ph_xb ^= 1u << sb;
       tc_fence_after();
+      MIX_TRACE(0, 1, it);
       const uint32_t x_hi = smem_u32(smem + L.xb(sb)), x_lo = x_hi + L.xb_bytes / 2;
+      const uint64_t b_hi = b_desc0 | (uint64_t)(x_hi >> 4), b_lo = b_desc0 | (uint64_t)(x_lo >> 4);
       for (int h = 0; h < H; h++, hcount++) {
         const int db = (int)(hcount & 1);
         if (hcount >= 2) {
           mbar_wait(&d_free[db], (ph_dfree >> db) & 1u);
           ph_dfree ^= 1u << db;
         }
+        MIX_TRACE(0, 2, hcount);
         mbar_wait(&full[stage], phase);
         tc_fence_after();
+        MIX_TRACE(0, 3, hcount);
         if (elect_one()) {
-          const uint32_t s_hi = smem_u32(smem + L.ring() + stage * L.stage_stride), s_lo = s_hi + mat_bytes;
+          // descriptors differ only in the 14-bit start-address field (16-byte units): one 64-bit add per k step
+          const uint32_t s_hi = smem_u32(smem + L.ring() + stage * L.stage_bytes), s_lo = s_hi + mat_bytes;
+          const uint64_t a_hi = a_desc0 | (uint64_t)(s_hi >> 4), a_lo = a_desc0 | (uint64_t)(s_lo >> 4);
           const uint32_t d = tmem + db * 128;
-          for (int k = 0; k < ksteps; k++)
-            mma_ss(d, make_smem_desc(s_hi + k * 256, a_lbo, a_sbo, LAYOUT_NONE), make_smem_desc(x_hi + k * 2048, b_lbo, 1024, LAYOUT_SW128), idesc, k > 0);
+#pragma unroll
+          for (int k = 0; k < kMixTokMaxVP / 16; k++)
+            if (k < ksteps) mma_ss(d, a_hi + (uint64_t)(k * 16), b_hi + (uint64_t)(k * 128), idesc, k > 0);
           if (kSplit == 3) {
-            for (int k = 0; k < ksteps; k++)
-              mma_ss(d, make_smem_desc(s_lo + k * 256, a_lbo, a_sbo, LAYOUT_NONE), make_smem_desc(x_hi + k * 2048, b_lbo, 1024, LAYOUT_SW128), idesc, 1);
-            for (int k = 0; k < ksteps; k++)
-              mma_ss(d, make_smem_desc(s_hi + k * 256, a_lbo, a_sbo, LAYOUT_NONE), make_smem_desc(x_lo + k * 2048, b_lbo, 1024, LAYOUT_SW128), idesc, 1);
+#pragma unroll
+            for (int k = 0; k < kMixTokMaxVP / 16; k++)
+              if (k < ksteps) mma_ss(d, a_lo + (uint64_t)(k * 16), b_hi + (uint64_t)(k * 128), idesc, 1);
+#pragma unroll
+            for (int k = 0; k < kMixTokMaxVP / 16; k++)
+              if (k < ksteps) mma_ss(d, a_hi + (uint64_t)(k * 16), b_lo + (uint64_t)(k * 128), idesc, 1);
           }
           mma_commit(&empty[stage]);
           mma_commit(&d_full[db]);
           if (h == H - 1) mma_commit(&xb_free[sb]);
         }
         __syncwarp();
-        if (++stage == 2) stage = 0, phase ^= 1;
+        MIX_TRACE(0, 4, hcount);
+        if (++stage == (uint32_t)n_stages) stage = 0, phase ^= 1;
       }
     }
   } else if (warp < 4) {
@@ -1556,10 +1581,12 @@ __global__ void __launch_bounds__(kMixTokThreads, 1) k_mix_tok(MixArgs a) {
     const uint32_t c16 = (uint32_t)(lane & 15) >> 1, sub = (uint32_t)(lane & 1) * 8;
     for (int64_t n = blockIdx.x; n < a.n; n += gridDim.x, it++) {
       const int sb = (int)(it & 1);
+      if (cw == 0) { MIX_TRACE(2, 0, it); }
       if (it >= 2) {
         mbar_wait(&xb_free[sb], (ph_free >> sb) & 1u);
         ph_free ^= 1u << sb;
       }
+      if (cw == 0) { MIX_TRACE(2, 2, it); }
       uint8_t* hi_base = smem + L.xb(sb) + nb * (VP * 128);
       uint8_t* lo_base = hi_base + L.xb_bytes / 2;
       const float4* src = reinterpret_cast<const float4*>(x + n * V * 128) + lane;
@@ -1585,6 +1612,7 @@ __global__ void __launch_bounds__(kMixTokThreads, 1) k_mix_tok(MixArgs a) {
       }
       fence_proxy_async_smem();
       mbar_arrive(&xb_full[sb]);
+      if (cw == 0) { MIX_TRACE(2, 1, it); }
     }
   } else {
     // ------------------------------------------------------------------ epilogue groups
@@ -1593,11 +1621,11 @@ __global__ void __launch_bounds__(kMixTokThreads, 1) k_mix_tok(MixArgs a) {
     const int i = q * 32 + lane;  // token (atom) of the sample = TMEM lane
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     const bool warp_active = q * 32 < V;
-    const bool leader = (q == 0 && lane == 0);
+    const bool store_lane = q == 0 && lane < 4 && (kSplit == 3 || (lane & 1) == 0);  // one bulk-store issuer per region
     uint8_t* img = a.img[net];
     const size_t tile_bytes = (size_t)H * 2 * 2 * 16384;
     uint8_t* stg = smem + L.out(g);
-    const uint32_t region = (uint32_t)VP * 128;  // one (K block, hi/lo) region of the staging buffer
+    const uint32_t region = (uint32_t)V * 128;  // one (K block, hi/lo) region of the staging buffer
     uint32_t ph_dfull = 0;
     int64_t hcount = 0;
     bool stores_pending = false;
@@ -1607,11 +1635,14 @@ __global__ void __launch_bounds__(kMixTokThreads, 1) k_mix_tok(MixArgs a) {
       for (int h = 0; h < H; h++, hcount++) {
         const int db = (int)(hcount & 1);
         if (db != g) continue;
+        if (q == 0 && g == 0) { MIX_TRACE(1, 2, hcount); }
         mbar_wait(&d_full[db], ph_dfull);
         ph_dfull ^= 1;
         tc_fence_after();
-        if (leader && stores_pending) bulk_wait_group_read0();  // the previous head's rows have left the staging buffer
+        if (q == 0 && g == 0) { MIX_TRACE(1, 3, hcount); }
+        if (store_lane && stores_pending) bulk_wait_group_read0();  // the previous head's rows have left the staging buffer
         group_bar_sync(g);
+        if (q == 0 && g == 0) { MIX_TRACE(1, 5, hcount); }
         if (warp_active) {
 #pragma unroll 1
           for (int g4 = 0; g4 < 4; g4++) {
@@ -1636,28 +1667,30 @@ __global__ void __launch_bounds__(kMixTokThreads, 1) k_mix_tok(MixArgs a) {
         tc_fence_before();
         mbar_arrive(&d_free[db]);
         fence_proxy_async_smem();
+        if (q == 0 && g == 0) { MIX_TRACE(1, 4, hcount); }
         group_bar_sync(g);
-        if (leader) {  // whole image rows -> global: per (K block, hi/lo) one piece, two where the sample straddles a tile
+        if (q == 0 && g == 0) { MIX_TRACE(1, 7, hcount); }
+        if (store_lane) {  // whole image rows -> global: lane = (K block, hi/lo) region; two pieces where the sample straddles a tile
           const int64_t tile = t0 >> 7;
           const int r0 = (int)(t0 & 127);
           const int n1 = (V < 128 - r0) ? V : 128 - r0;
-          for (int kb = 0; kb < 2; kb++)
-            for (int hl = 0; hl < (kSplit == 3 ? 2 : 1); hl++) {
-              const uint8_t* src = stg + (kb * 2 + hl) * region;
-              uint8_t* dst = img + tile * tile_bytes + (size_t)(h * 2 + kb) * 32768 + hl * 16384;
-              bulk_s2g(dst + r0 * 128, src, (uint32_t)n1 * 128u);
-              if (n1 < V) bulk_s2g(dst + tile_bytes, src + n1 * 128, (uint32_t)(V - n1) * 128u);
-            }
+          const int kb = lane >> 1, hl = lane & 1;
+          const uint8_t* src = stg + (kb * 2 + hl) * region;
+          uint8_t* dst = img + tile * tile_bytes + (size_t)(h * 2 + kb) * 32768 + hl * 16384;
+          bulk_s2g(dst + r0 * 128, src, (uint32_t)n1 * 128u);
+          if (n1 < V) bulk_s2g(dst + tile_bytes, src + n1 * 128, (uint32_t)(V - n1) * 128u);
           bulk_commit_group();
           stores_pending = true;
         }
+        if (q == 0 && g == 0) { MIX_TRACE(1, 6, hcount); }
       }
     }
-    if (leader) bulk_wait_group0();
+    if (store_lane) bulk_wait_group0();
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc<256>(tmem);
+#undef MIX_TRACE
 }
 
 // ============================================================================================
@@ -2262,12 +2295,15 @@ int tc_mix(const tw_flow_config* c, const float* const x[2], uint8_t* const img[
   if (use_tok < 0) {
     const char* e = getenv("TW_MIX_TOK");  // bring-up switch: 0 = feature-major kernel for every atom count
     use_tok = e ? atoi(e) : 1;
-    const int max_smem = (int)MixTokSmem(kMixTokMaxVP).total() + 1024;
+    const int max_smem = 232448;
     TW_CUDA(cudaFuncSetAttribute(k_mix_tok<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     TW_CUDA(cudaFuncSetAttribute(k_mix_tok<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
   }
   if (use_tok && VP <= kMixTokMaxVP) {
-    const int smem_tok = (int)MixTokSmem(VP).total() + 1024;
+    int tok_stages = kMixTokStages;
+    if ((int)MixTokSmem(V, VP, tok_stages).total() + 1024 > 232448) tok_stages = 2;
+    const int smem_tok = (int)MixTokSmem(V, VP, tok_stages).total() + 1024;
+    a.n_stages = tok_stages;
     if (c->precision == TW_PRECISION_BF16X3)
       k_mix_tok<3><<<grid, kMixTokThreads, smem_tok, st>>>(a);
     else

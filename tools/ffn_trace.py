@@ -40,8 +40,8 @@ if g1 > g0:
 t0 = min(int(t[r, 0, 1]) for r in range(3) if t[r, 0, 1] > 0)
 if cls == 2:
     names = {0: {0: 'mma: sample top', 1: 'mma: hs_full', 2: 'mma: head top', 3: 'mma: scores landed', 4: 'mma: head issued'},
-             1: {0: 'epi0: load_hs start', 1: 'epi0: load_hs done', 2: 'epi0: wait d_full', 3: 'epi0: d_full', 4: 'epi0: staged', 5: 'epi0: sync1', 6: 'epi0: stores issued', 7: 'epi0: sync2'},
-             2: {0: 'epi1: load_hs start', 1: 'epi1: load_hs done', 2: 'epi1: wait d_full', 3: 'epi1: d_full', 4: 'epi1: staged', 5: 'epi1: sync1', 6: 'epi1: stores issued', 7: 'epi1: sync2'}}
+             1: {2: 'epi0: wait d_full', 3: 'epi0: d_full', 5: 'epi0: staging free', 4: 'epi0: staged', 7: 'epi0: sync2', 6: 'epi0: stores issued'},
+             2: {0: 'conv: sample top (item=sample)', 2: 'conv: buffer free', 1: 'conv: done'}}
 else:
   names = {0: {0: "mma: loop top", 1: "mma: W1hi landed", 2: "mma: G1 issued+committed", 3: "mma: W2 landed", 4: "mma: h_full[0] -> G2a", 5: "mma: h_full[1] -> G2b"},
            1: {0: "epi0: wait d1", 1: "epi0: d1_full", 2: "epi0: ld done", 3: "epi0: st done", 4: "epi0: arrived", 5: "epi0: LN got y_full (item=tile128)", 6: "epi0: LN stats done", 7: "epi0: LN y_free"},
