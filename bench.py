@@ -92,6 +92,25 @@ def synthetic_chains(pep, n_chains, seed):
     return x, at, mask
 
 
+def bench_state_dict(o, mode):
+    """Synthetic weights of the full architecture.  mode "init": random-init-scale parameters (proposals of a random
+    flow are never accepted).  mode "proposal" (default): the same tensors with the last layer of every out_mlp scaled by
+    1e-5 (shifts far below the proposal width) and the prior scales set to (5e-4 nm, 1): a near-identity flow whose
+    proposals are local moves, so the accept
+    branch of the MH rule is exercised.  Identical arithmetic and shapes either way."""
+    from oracle import flow_oracle as fo
+
+    sd = fo.synth_state_dict(o, 0)
+    if mode == "proposal":
+        last = 2 * len(o.latent_mlp_hidden_dims)
+        for k in list(sd):
+            if f".out_mlp._layers.{last}." in k:
+                sd[k] = sd[k] * 1e-5
+        sd["coords_prior_log_scale"] = torch.tensor(float(np.log(5e-4)))
+        sd["velocs_prior_log_scale"] = torch.tensor(0.0)
+    return sd
+
+
 # --------------------------------------------------------------------------------------------
 def cpu_reference_iteration(sd, o, sysd, kbT, x, at, mask, gen):
     """One MH iteration on the CPU through the oracle port of the reference path (flow in torch fp32
@@ -114,7 +133,7 @@ def cpu_reference_iteration(sd, o, sysd, kbT, x, at, mask, gen):
     return torch.where(acc[:, None, None], yc[0], x), acc
 
 
-def time_cpu_reference(sample_chains, iters, warmup, seed=0):
+def time_cpu_reference(sample_chains, iters, warmup, seed=0, weights="proposal"):
     from oracle import flow_oracle as fo
     from timewarp_b200.forcefield import MOLAR_GAS_CONSTANT_R, amber_like_system
     from timewarp_b200.peptides import tetrapeptide_2olx
@@ -122,7 +141,7 @@ def time_cpu_reference(sample_chains, iters, warmup, seed=0):
     torch.set_num_threads(os.cpu_count() or 1)
     pep = tetrapeptide_2olx()
     o = fo.OracleConfig()
-    sd = fo.synth_state_dict(o, 0)
+    sd = bench_state_dict(o, weights)
     sysd = amber_like_system(pep).as_float32()
     kbT = 310.0 * MOLAR_GAS_CONSTANT_R
     x, at, mask = synthetic_chains(pep, sample_chains, seed)
@@ -143,7 +162,7 @@ def run_reference(args):
         return
     S = args.cpu_sample
     w = min(args.warmup, 1)
-    value, cores, ms = time_cpu_reference(S, args.steps, w)
+    value, cores, ms = time_cpu_reference(S, args.steps, w, weights=args.weights)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": w,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -158,6 +177,49 @@ def run_reference(args):
 
 
 # --------------------------------------------------------------------------------------------
+def time_nll_training(dev, precision, batch=256, steps=5, warmup=3):
+    """BASELINE.json configs[1]: alanine-dipeptide (22 atoms) NLL training, batch 256 on one GPU: forward (taped) +
+    hand-written backward + Adam step.  Returns atoms/s (B * V / step time, CUDA events)."""
+    import timewarp_b200 as tw
+    from oracle import flow_oracle as fo
+    from timewarp_b200.peptides import alanine_dipeptide
+
+    pep = alanine_dipeptide()
+    V = pep.num_atoms
+    model = tw.custom_transformer_nvp_constructor(tw.kernel_transformer_nvp_config(precision))
+    model.load_state_dict(fo.synth_state_dict(fo.OracleConfig(), 0))
+    model = model.to(dev).train()
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+    g = torch.Generator().manual_seed(0)
+    x = torch.tensor(pep.coords_nm, dtype=torch.float32)[None] + 0.01 * torch.randn(batch, V, 3, generator=g)
+    y = x + 0.02 * torch.randn(batch, V, 3, generator=g)
+    kw = dict(atom_types=torch.tensor(pep.atom_types)[None].repeat(batch, 1).to(dev), x_coords=x.to(dev),
+              x_velocs=torch.randn(batch, V, 3, generator=g).to(dev), y_coords=y.to(dev), y_velocs=torch.randn(batch, V, 3, generator=g).to(dev),
+              adj_list=torch.zeros(0, 2, dtype=torch.long, device=dev), edge_batch_idx=torch.zeros(0, dtype=torch.long, device=dev),
+              masked_elements=torch.zeros(batch, V, dtype=torch.bool, device=dev))
+
+    def step():
+        opt.zero_grad(set_to_none=False)
+        loss = model(**kw)
+        loss.backward()
+        opt.step()
+        return loss
+
+    for _ in range(warmup):
+        step()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(steps):
+        loss = step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    return {"metric": "nll_train_atoms_per_sec", "value": batch * V / (ms / 1e3), "unit": "atoms/s", "ms_per_step": ms,
+            "config": {"workload": f"nll_train_ad22_batch{batch}", "atoms": V, "batch": batch, "optimizer": "Adam", "precision": precision},
+            "final_loss": float(loss)}
+
+
 def run_ours(args):
     import ctypes as C
 
@@ -192,7 +254,7 @@ def run_ours(args):
     V = pep.num_atoms
     o = fo.OracleConfig()
     model = tw.custom_transformer_nvp_constructor(tw.kernel_transformer_nvp_config(args.precision))
-    model.load_state_dict(fo.synth_state_dict(o, 0))
+    model.load_state_dict(bench_state_dict(o, args.weights))
     model = model.to(dev).eval()
     energy = PeptidePotentialEnergy(amber_like_system(pep))
     x0, at, mask = synthetic_chains(pep, args.chains, seed=1000 + rank)
@@ -282,13 +344,13 @@ def run_ours(args):
             except Exception:
                 traffic = None
         step_flops = args.chains * 2 * V * f_atom(V)
-        cpu_val, cpu_cores, _ = time_cpu_reference(args.cpu_sample, 2, 1) if not args.no_cpu_baseline else (None, None, None)
+        cpu_val, cpu_cores, _ = time_cpu_reference(args.cpu_sample, 2, 1, weights=args.weights) if not args.no_cpu_baseline else (None, None, None)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": {"fp32": "f32", "bf16x3": "bf16x3(f32-accumulate)", "bf16": "bf16"}[args.precision], "data": "synthetic",
             "config": {"workload": f"mh_2olx65_chains{args.chains}_per_gpu", "atoms": V, "chains_per_gpu": args.chains,
-                       "model": "kernel_transformer_nvp (35.97M params, synthetic weights)", "precision": args.precision,
+                       "model": f"kernel_transformer_nvp (35.97M params, synthetic weights: {args.weights})", "precision": args.precision,
                        "energy": "synthetic Amber-like + GB-OBC2, on-GPU fp64",
                        "l2": "working set per step (activations+workspace) >> 126 MB L2; no explicit flush",
                        "algorithmic_tflops_per_step": step_flops / 1e12},
@@ -302,6 +364,11 @@ def run_ours(args):
             "whole_step_algorithmic_tflops": step_flops * args.steps / (ms_total / 1e3) / 1e12,
             "acceptance_rate_mean": float(acc_rate.mean().item()),
         }
+        if not args.no_nll:
+            try:
+                line["secondary"] = time_nll_training(dev, args.precision)
+            except Exception as e:  # the MH line must not depend on the training path
+                line["secondary"] = {"metric": "nll_train_atoms_per_sec", "error": str(e)[:200]}
         if cpu_val is not None:
             line["cpu_baseline"] = {"value": cpu_val, "unit": UNIT, "cores": cpu_cores, "kind": "port",
                                     "sample": f"{args.cpu_sample} chains x 2 MH iterations of the same workload through oracle/ (torch-CPU fp32 flow + numpy fp64 energy)"}
@@ -321,6 +388,8 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=32, help="chains in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--weights", default="proposal", choices=["proposal", "init"], help="synthetic weight set (see bench_state_dict)")
+    ap.add_argument("--no-nll", action="store_true", help="skip the secondary NLL-training throughput measurement")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
