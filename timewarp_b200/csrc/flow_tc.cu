@@ -1826,6 +1826,407 @@ __global__ void __launch_bounds__(192, 1) k_proj_tc(ProjArgs a) {
 }
 
 // ============================================================================================
+// Fused attention layer (inference):  out = LayerNorm1(x + sum_h (A_h x) W_c,h^T)   for ONE sample per CTA iteration.
+// The two-kernel form (k_mix_tok -> 3 KB/token of operand images in HBM -> k_proj_tc) is bound by that round trip
+// (409 MB written + 409 MB read per layer).  Here the per-head neighbourhood averages never leave the SM:
+//   MMA1(h): DM[h&1][128 i, 128 f] = A_h (A operand: score image, smem) * X (B operand: the sample's x, bf16 hi/lo, MN-major)
+//   epilogue: DM -> bf16 hi/lo IN PLACE (TMEM) -- the A operand of
+//   MMA2(h): DO[n&1][128 i, 128 out] += mixed_h * W_c,h^T (B operand: [128 out x 128 K] K-major, streamed per sample)
+// with DO pre-initialised with x (the residual rides in the accumulator), exactly the chunk pipeline of the fused FFN with
+// heads as chunks (issue order MMA1(g), MMA2(g-1) over a global head counter).  Only V of the 128 token rows are real
+// (51 % of the MMA rows for 65 atoms): the price of sample-aligned tiles; the kernel is tensor-bound, not HBM-bound.
+//   warp 0 score-image + W_c producer   warp 1 MMA issuer   warp 2 activation I/O (x in, LayerNorm rows out, bulk copies)
+//   warp 3 x -> operand tiles           warps 4-7 / 8-11 epilogue groups (feature halves [0,64) / [64,128))
+// TMEM: DM0 | DM1 | DO0 | DO1, 128 columns each.
+constexpr int kAttnThreads = 384;
+constexpr int kAttnWcStages = 3;
+constexpr int kAttnScStages = 2;
+constexpr uint32_t AT_DM = 0, AT_DO = 256;
+
+struct AttnArgs {
+  const float* x[2];
+  float* out[2];
+  const uint8_t* scores_img;
+  const uint8_t* wc[2];
+  const float* gamma[2];
+  const float* beta[2];
+  int64_t n, n_cond;
+  int V, VP, H;
+  float eps;
+};
+
+struct AttnSmem {
+  uint32_t xb_bytes, sc_stage, xs_bytes, pad;
+  __host__ __device__ AttnSmem(int v, int vp) {
+    xb_bytes = (uint32_t)(4 * vp * 128);
+    sc_stage = (uint32_t)(2 * vp * vp * 2);
+    xs_bytes = (uint32_t)(v * kXsRow);
+    const uint32_t overread = (uint32_t)(2 * vp * (128 - vp));  // MMA1 reads 128 rows of a VP-row score image
+    pad = xs_bytes >= overread ? 0u : ((overread - xs_bytes + 15) & ~15u);
+  }
+  __host__ __device__ uint32_t xb() const { return 0; }
+  __host__ __device__ uint32_t wc() const { return xb_bytes; }
+  __host__ __device__ uint32_t sc() const { return wc() + kAttnWcStages * 32768; }
+  __host__ __device__ uint32_t xs() const { return sc() + kAttnScStages * sc_stage; }
+  __host__ __device__ uint32_t stat() const { return xs() + xs_bytes + pad; }
+  __host__ __device__ uint32_t vec() const { return stat() + 2 * 128 * 8; }
+  __host__ __device__ uint32_t bars() const { return vec() + 2 * 128 * 4; }
+  __host__ __device__ uint32_t total() const { return bars() + 256; }
+};
+
+template <int kSplit>
+__global__ void __launch_bounds__(kAttnThreads, 1) k_attn_fused(AttnArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int net = blockIdx.y;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int V = a.V, VP = a.VP, H = a.H;
+  const AttnSmem L(V, VP);
+  const uint32_t mat_bytes = (uint32_t)VP * VP * 2;
+  const int64_t my_n = ((int64_t)blockIdx.x < a.n) ? (a.n - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const int64_t G = my_n * H;
+  constexpr int kParts = kSplit == 3 ? 2 : 1;
+
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bars());
+  uint64_t* sc_full = bars;                       // [2]
+  uint64_t* sc_empty = sc_full + kAttnScStages;   // [2]
+  uint64_t* wc_full = sc_empty + kAttnScStages;   // [3]
+  uint64_t* wc_empty = wc_full + kAttnWcStages;   // [3]
+  uint64_t* dm_full = wc_empty + kAttnWcStages;   // [2] MMA1 into DM[b] retired
+  uint64_t* h_full = dm_full + 2;                 // [4] (b, K half) of the mixed operand written in place, 128 arrivals
+  uint64_t* xs_full = h_full + 4;                 // the sample's x rows landed in the staging buffer (tx bytes)
+  uint64_t* xs_used = xs_full + 1;                // 32 + 256 arrivals: converted to operand tiles AND used to initialise DO
+  uint64_t* xb_full = xs_used + 1;                // 32 arrivals: operand tiles written
+  uint64_t* xb_free = xb_full + 1;                // commit: last MMA1 of the sample retired
+  uint64_t* do_init = xb_free + 1;                // 256 arrivals: DO initialised with x
+  uint64_t* do_full = do_init + 1;                // commit: last MMA2 of the sample retired
+  uint64_t* ln_staged = do_full + 1;              // 256 arrivals: LayerNorm rows parked in the staging buffer
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ln_staged + 1);
+  float* vecs = reinterpret_cast<float*>(smem + L.vec());
+
+  if (tid == 0) {
+    for (int i = 0; i < kAttnScStages; i++) mbar_init(&sc_full[i], 1), mbar_init(&sc_empty[i], 1);
+    for (int i = 0; i < kAttnWcStages; i++) mbar_init(&wc_full[i], 1), mbar_init(&wc_empty[i], 1);
+    for (int i = 0; i < 2; i++) mbar_init(&dm_full[i], 1);
+    for (int i = 0; i < 4; i++) mbar_init(&h_full[i], 128);
+    mbar_init(xs_full, 1);
+    mbar_init(xs_used, 32 + 256);
+    mbar_init(xb_full, 32);
+    mbar_init(xb_free, 1);
+    mbar_init(do_init, 256);
+    mbar_init(do_full, 1);
+    mbar_init(ln_staged, 256);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  for (int i = tid; i < 128; i += blockDim.x) vecs[i] = a.gamma[net][i], vecs[128 + i] = a.beta[net][i];
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const int ksteps = VP / 16;
+  auto sample_of = [&](int64_t it) -> int64_t { return blockIdx.x + it * gridDim.x; };
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ score images and W_c tiles, in consumption order
+    uint32_t ss = 0, sp = 0, ws = 0, wp = 0;
+    auto load_scores = [&](int64_t g) {
+      const int64_t n = sample_of(g / H);
+      const uint8_t* src = a.scores_img + ((size_t)(n % a.n_cond) * H + (size_t)(g % H)) * (2 * mat_bytes);
+      mbar_wait(&sc_empty[ss], sp ^ 1);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&sc_full[ss], kParts * mat_bytes);
+        bulk_g2s(smem + L.sc() + ss * L.sc_stage, src, kParts * mat_bytes, &sc_full[ss]);
+      }
+      __syncwarp();
+      if (++ss == kAttnScStages) ss = 0, sp ^= 1;
+    };
+    auto load_wc = [&](int64_t g) {  // the two K blocks (hi | lo, 32 KB each) of W_c,h
+      const int h = (int)(g % H);
+      for (int kb = 0; kb < 2; kb++) {
+        mbar_wait(&wc_empty[ws], wp ^ 1);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&wc_full[ws], kParts * 16384u);
+          bulk_g2s(smem + L.wc() + ws * 32768, a.wc[net] + (size_t)(h * 2 + kb) * 32768, kParts * 16384u, &wc_full[ws]);
+        }
+        __syncwarp();
+        if (++ws == kAttnWcStages) ws = 0, wp ^= 1;
+      }
+    };
+    for (int64_t g = 0; g < G; g++) {
+      load_scores(g);
+      if (g >= 1) load_wc(g - 1);
+    }
+    if (G > 0) load_wc(G - 1);
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    uint32_t ss = 0, sp = 0, ws = 0, wp = 0, ph_xb = 0, ph_h = 0, ph_doinit = 0;
+    const uint32_t idesc1 = make_idesc_bf16(128, 128, 0, 1);  // A K-major (scores), B MN-major (x)
+    const uint32_t idesc2 = make_idesc_bf16(128, 128, 0, 0);
+    const uint64_t a_desc0 = make_smem_desc(0, 128, (uint32_t)(VP >> 3) * 128, LAYOUT_NONE);
+    const uint64_t b_desc0 = make_smem_desc(0, (uint32_t)VP * 128, 1024, LAYOUT_SW128);
+    const uint32_t x_hi = smem_u32(smem + L.xb()), x_lo = x_hi + L.xb_bytes / 2;
+    const uint64_t b_hi = b_desc0 | (uint64_t)(x_hi >> 4), b_lo = b_desc0 | (uint64_t)(x_lo >> 4);
+
+    auto issue_mma2 = [&](int64_t gp) {  // DO += mixed(gp) W_c^T
+      const int hp = (int)(gp % H), b = (int)(gp & 1), dob = (int)((gp / H) & 1);
+      if (hp == 0) {
+        mbar_wait(do_init, ph_doinit);
+        ph_doinit ^= 1;
+      }
+      for (int kb = 0; kb < 2; kb++) {
+        mbar_wait(&wc_full[ws], wp);
+        mbar_wait(&h_full[b * 2 + kb], (ph_h >> (b * 2 + kb)) & 1u);
+        ph_h ^= 1u << (b * 2 + kb);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t w_hi = smem_u32(smem + L.wc() + ws * 32768), w_lo = w_hi + 16384;
+          const uint32_t m_hi = tmem + AT_DM + b * 128 + kb * 64, m_lo = m_hi + 32;
+          const uint32_t d = tmem + AT_DO + dob * 128;
+#pragma unroll
+          for (int k = 0; k < 4; k++) mma_ts(d, m_hi + k * 8, desc_kmajor_sw128(w_hi + k * 32), idesc2, 1);
+          if (kSplit == 3) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) mma_ts(d, m_lo + k * 8, desc_kmajor_sw128(w_hi + k * 32), idesc2, 1);
+#pragma unroll
+            for (int k = 0; k < 4; k++) mma_ts(d, m_hi + k * 8, desc_kmajor_sw128(w_lo + k * 32), idesc2, 1);
+          }
+          mma_commit(&wc_empty[ws]);
+          if (kb == 1 && hp == H - 1) mma_commit(do_full);
+        }
+        __syncwarp();
+        if (++ws == kAttnWcStages) ws = 0, wp ^= 1;
+      }
+    };
+
+    int64_t g = 0;
+    for (int64_t it = 0; it < my_n; it++) {
+      mbar_wait(xb_full, ph_xb);
+      ph_xb ^= 1;
+      tc_fence_after();
+      for (int h = 0; h < H; h++, g++) {
+        mbar_wait(&sc_full[ss], sp);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t s_hi = smem_u32(smem + L.sc() + ss * L.sc_stage), s_lo = s_hi + mat_bytes;
+          const uint64_t a_hi = a_desc0 | (uint64_t)(s_hi >> 4), a_lo = a_desc0 | (uint64_t)(s_lo >> 4);
+          const uint32_t d = tmem + AT_DM + (uint32_t)(g & 1) * 128;
+#pragma unroll
+          for (int k = 0; k < kMixTokMaxVP / 16; k++)
+            if (k < ksteps) mma_ss(d, a_hi + (uint64_t)(k * 16), b_hi + (uint64_t)(k * 128), idesc1, k > 0);
+          if (kSplit == 3) {
+#pragma unroll
+            for (int k = 0; k < kMixTokMaxVP / 16; k++)
+              if (k < ksteps) mma_ss(d, a_lo + (uint64_t)(k * 16), b_hi + (uint64_t)(k * 128), idesc1, 1);
+#pragma unroll
+            for (int k = 0; k < kMixTokMaxVP / 16; k++)
+              if (k < ksteps) mma_ss(d, a_hi + (uint64_t)(k * 16), b_lo + (uint64_t)(k * 128), idesc1, 1);
+          }
+          mma_commit(&sc_empty[ss]);
+          mma_commit(&dm_full[g & 1]);
+          if (h == H - 1) mma_commit(xb_free);
+        }
+        __syncwarp();
+        if (++ss == kAttnScStages) ss = 0, sp ^= 1;
+        if (g >= 1) issue_mma2(g - 1);
+      }
+    }
+    if (G > 0) issue_mma2(G - 1);
+  } else if (warp == 2) {
+    // ------------------------------------------------------------------ activation I/O: x rows in, LayerNorm rows out
+    uint32_t ph_used = 0, ph_staged = 0;
+    auto load_x = [&](int64_t n) {
+      if (lane == 0) {
+        mbar_arrive_expect_tx(xs_full, (uint32_t)V * 512u);
+        const float* src = a.x[net] + n * V * 128;
+        for (int r = 0; r < V; r++) bulk_g2s(smem + L.xs() + r * kXsRow, src + (size_t)r * 128, 512, xs_full);
+      }
+      __syncwarp();
+    };
+    auto store_out = [&](int64_t n) {
+      if (lane == 0) {
+        float* dst = a.out[net] + n * V * 128;
+        for (int r = 0; r < V; r++) bulk_s2g(dst + (size_t)r * 128, smem + L.xs() + r * kXsRow, 512);
+        bulk_commit_group();
+      }
+      __syncwarp();
+    };
+    if (my_n > 0) load_x(sample_of(0));
+    for (int64_t it = 0; it < my_n; it++) {
+      mbar_wait(xs_used, ph_used);  // x(it) converted and used for the accumulator: the buffer may carry other rows
+      ph_used ^= 1;
+      if (it >= 1) {
+        mbar_wait(ln_staged, ph_staged);
+        ph_staged ^= 1;
+        store_out(sample_of(it - 1));
+        if (lane == 0) bulk_wait_group_read0();
+        __syncwarp();
+      }
+      if (it + 1 < my_n) {
+        load_x(sample_of(it + 1));
+      } else {
+        if (lane == 0) mbar_arrive(xs_full);  // nothing more to load: the buffer is free for the last LayerNorm
+        __syncwarp();
+      }
+    }
+    if (my_n > 0) {
+      mbar_wait(ln_staged, ph_staged);
+      store_out(sample_of(my_n - 1));
+    }
+    if (lane == 0) bulk_wait_group0();
+    __syncwarp();
+  } else if (warp == 3) {
+    // ------------------------------------------------------------------ staged x rows -> bf16 hi/lo MN-major operand tiles
+    uint32_t ph_xs = 0, ph_free = 0;
+    const int nb = lane >> 4;
+    const uint32_t c16 = (uint32_t)(lane & 15) >> 1, sub = (uint32_t)(lane & 1) * 8;
+    uint8_t* hi_base = smem + L.xb() + nb * (VP * 128);
+    uint8_t* lo_base = hi_base + L.xb_bytes / 2;
+    for (int64_t it = 0; it < my_n; it++) {
+      mbar_wait(xs_full, ph_xs);
+      ph_xs ^= 1;
+      if (it >= 1) {
+        mbar_wait(xb_free, ph_free);
+        ph_free ^= 1;
+      }
+      for (int j = 0; j < VP; j++) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (j < V) v = *reinterpret_cast<const float4*>(smem + L.xs() + j * kXsRow + lane * 16);
+        uint32_t h0, l0, h1, l1;
+        split2(v.x, v.y, h0, l0);
+        split2(v.z, v.w, h1, l1);
+        const uint32_t off = (uint32_t)j * 128u + ((c16 ^ ((uint32_t)j & 7u)) << 4) + sub;
+        *reinterpret_cast<uint2*>(hi_base + off) = make_uint2(h0, h1);
+        if (kSplit == 3) *reinterpret_cast<uint2*>(lo_base + off) = make_uint2(l0, l1);
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(xb_full);
+      mbar_arrive(xs_used);
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue groups (kb = feature half)
+    const int q = warp & 3;
+    const int kb = (warp - 4) >> 2;
+    const int row = q * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    const bool row_valid = row < V;
+    uint32_t ph_dm = 0, ph_xs = 0, ph_used = 1 /* first wait is for the SECOND sample's phase */, ph_dofull = 0;
+    uint8_t* my_xs = smem + L.xs() + row * kXsRow + kb * 256;  // this thread's 64 columns of its row in the staging buffer
+    float2* stat = reinterpret_cast<float2*>(smem + L.stat());
+
+    auto init_do = [&](int64_t it) {  // DO[it & 1][:, kb half] <- x (rows >= V: zeros)
+      mbar_wait(xs_full, ph_xs);
+      ph_xs ^= 1;
+      const uint32_t base = tmem + lane_base + AT_DO + (uint32_t)(it & 1) * 128 + kb * 64;
+#pragma unroll 1
+      for (int b = 0; b < 4; b++) {
+        uint32_t r[16];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (row_valid) v = *reinterpret_cast<const float4*>(my_xs + b * 64 + j * 16);
+          r[4 * j] = __float_as_uint(v.x), r[4 * j + 1] = __float_as_uint(v.y);
+          r[4 * j + 2] = __float_as_uint(v.z), r[4 * j + 3] = __float_as_uint(v.w);
+        }
+        tmem_st16(base + b * 16, r);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(do_init);
+      mbar_arrive(xs_used);
+    };
+    auto layer_norm = [&](int64_t it, bool last) {  // sample `it` finished: drain, normalise, park for the bulk store
+      mbar_wait(do_full, ph_dofull);
+      ph_dofull ^= 1;
+      tc_fence_after();
+      uint32_t ya[32], yb[32];
+      const uint32_t base = tmem + lane_base + AT_DO + (uint32_t)(it & 1) * 128 + kb * 64;
+      tmem_ld32(base, ya);
+      tmem_ld32(base + 32, yb);
+      tmem_ld_wait();
+      float sum = 0.f, sq = 0.f;
+#pragma unroll
+      for (int j = 0; j < 32; j++) {
+        const float v0 = __uint_as_float(ya[j]), v1 = __uint_as_float(yb[j]);
+        sum += v0 + v1;
+        sq = fmaf(v0, v0, sq), sq = fmaf(v1, v1, sq);
+      }
+      stat[kb * 128 + row] = make_float2(sum, sq);
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const float2 other = stat[(kb ^ 1) * 128 + row];
+      sum += other.x, sq += other.y;
+      const float mean = sum * (1.f / 128.f);
+      const float var = fmaxf(sq * (1.f / 128.f) - mean * mean, 0.f);
+      const float rstd = 1.0f / sqrtf(var + a.eps);
+      // the staging buffer is free once the NEXT sample's rows have been consumed (or, after the last sample, once the
+      // I/O warp has read the previous rows out)
+      if (last) {
+        mbar_wait(xs_full, ph_xs);
+      } else {
+        mbar_wait(xs_used, ph_used);
+        ph_used ^= 1;
+      }
+      if (row_valid) {
+        auto park32 = [&](const uint32_t (&r)[32], int off) {
+#pragma unroll
+          for (int j = 0; j < 8; j++) {
+            const float4 gm = *reinterpret_cast<const float4*>(vecs + kb * 64 + off + 4 * j);
+            const float4 bt = *reinterpret_cast<const float4*>(vecs + 128 + kb * 64 + off + 4 * j);
+            float4 o;
+            o.x = (__uint_as_float(r[4 * j]) - mean) * rstd * gm.x + bt.x;
+            o.y = (__uint_as_float(r[4 * j + 1]) - mean) * rstd * gm.y + bt.y;
+            o.z = (__uint_as_float(r[4 * j + 2]) - mean) * rstd * gm.z + bt.z;
+            o.w = (__uint_as_float(r[4 * j + 3]) - mean) * rstd * gm.w + bt.w;
+            *reinterpret_cast<float4*>(my_xs + (off + 4 * j) * 4) = o;
+          }
+        };
+        park32(ya, 0);
+        park32(yb, 32);
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(ln_staged);
+    };
+
+    if (my_n > 0) init_do(0);
+    const int init_slot = H >= 2 ? H - 2 : 0;
+    int64_t g = 0;
+    for (int64_t it = 0; it < my_n; it++) {
+      for (int h = 0; h < H; h++, g++) {
+        const int b = (int)(g & 1);
+        mbar_wait(&dm_full[b], (ph_dm >> b) & 1u);
+        ph_dm ^= 1u << b;
+        tc_fence_after();
+        {
+          const uint32_t base = tmem + lane_base + AT_DM + b * 128 + kb * 64;
+          uint32_t r0[32], r1[32];
+          tmem_ld32(base, r0);
+          tmem_ld32(base + 32, r1);
+          tmem_ld_wait();
+          uint32_t hi[16], lo[16];
+#pragma unroll
+          for (int j = 0; j < 16; j++) split2(__uint_as_float(r0[2 * j]), __uint_as_float(r0[2 * j + 1]), hi[j], lo[j]);
+          tmem_st16(base, hi);
+          if (kSplit == 3) tmem_st16(base + 32, lo);
+#pragma unroll
+          for (int j = 0; j < 16; j++) split2(__uint_as_float(r1[2 * j]), __uint_as_float(r1[2 * j + 1]), hi[j], lo[j]);
+          tmem_st16(base + 16, hi);
+          if (kSplit == 3) tmem_st16(base + 48, lo);
+          tmem_st_wait();
+        }
+        tc_fence_before();
+        mbar_arrive(&h_full[b * 2 + kb]);
+        if (h == 0 && it > 0) layer_norm(it - 1, false);
+        if (h == init_slot && it + 1 < my_n) init_do(it + 1);
+      }
+    }
+    if (my_n > 0) layer_norm(my_n - 1, true);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(tmem);
+}
+
+// ============================================================================================
 // in_mlp: token features (embedding gather + concat, flow.py:172 / custom_transformer_nvp.py:64-71) ->
 // Linear(E+9 -> 256) + SiLU -> Linear(256 -> 128)            (mlp.py:18-23, custom_transformer_block.py:66)
 // Weights stay resident in shared memory for the whole (persistent) CTA; the 256-wide hidden activation
@@ -2333,6 +2734,35 @@ int tc_attention_layer(const tw_flow_config* c, const ParamView& pv, int k, int 
   TcLayout L = TcLayout::make(c);
   const int64_t M = n * V;
   ProfScope prof(PROF_ATTN, st);
+  {
+    static int use_fused = -1;
+    if (use_fused < 0) {
+      const char* e = getenv("TW_ATTN_FUSED");  // bring-up switch: 0 = mixing + projection kernels
+      use_fused = e ? atoi(e) : 1;
+      TW_CUDA(cudaFuncSetAttribute(k_attn_fused<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+      TW_CUDA(cudaFuncSetAttribute(k_attn_fused<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    }
+    const int VP = pad16(V);
+    const int fused_smem = (int)AttnSmem(V, VP).total() + 1024;
+    // the training tape needs the per-head mixed images, so the taped forward keeps the two-kernel form
+    if (use_fused && !pre && VP <= kMixTokMaxVP && fused_smem <= 232448 && n >= 1) {
+      AttnArgs a{};
+      for (int s = 0; s < 2; s++) {
+        a.x[s] = x[s], a.out[s] = out[s];
+        a.wc[s] = tc.packed + L.net_offset(k, s) + L.enc0 + (size_t)t * L.enc_stride + L.enc_wc;
+        a.gamma[s] = pv.enc(k, s, t, 7), a.beta[s] = pv.enc(k, s, t, 8);
+      }
+      a.scores_img = tc.scores_img;
+      a.n = n, a.n_cond = n_cond, a.V = V, a.VP = VP, a.H = H, a.eps = c->layer_norm_eps;
+      dim3 grid((unsigned)(n < 74 ? n : 74), 2);
+      if (c->precision == TW_PRECISION_BF16X3)
+        k_attn_fused<3><<<grid, kAttnThreads, fused_smem, st>>>(a);
+      else
+        k_attn_fused<1><<<grid, kAttnThreads, fused_smem, st>>>(a);
+      TW_LAUNCH_CHECK();
+      return TW_OK;
+    }
+  }
   TW_TRY(tc_mix(c, x, tc.mixed_img, tc.scores_img, n, n_cond, V, st));
   {
     ProjArgs a{};
