@@ -239,7 +239,7 @@ int tw_debug_umma_timing(int n_mma, int N, int ts, int b_noswizzle, long long* o
 /* Debug: device buffer of 3*1024*2 + 8 int64 that CTA (0,0) of every following fused-FFN launch fills with
  * {event | item << 8, clock64} records per warp role (0 MMA issuer, 1/2 epilogue groups); NULL disables. */
 int tw_debug_set_ffn_trace(long long* device_buf);
-/* Same for kernel_class 1 = fused FFN, 2 = attention mixing kernel. */
+/* Same for kernel_class 1 = fused FFN, 2 = attention mixing kernel, 3 = fused attention layer. */
 int tw_debug_set_trace(int kernel_class, long long* device_buf);
 
 #ifdef __cplusplus

@@ -330,10 +330,11 @@ __global__ void __launch_bounds__(kFfnThreads, 1) k_ffn_tc(FfnArgs a) {
         if (++stage == kFfnStages) stage = 0, phase ^= 1;
       }
     };
-    for (int64_t g = 0; g < G; g++) {  // consumption order: G1(g), G2(g-1)
-      load(0, (int)(g % n_chunks));
-      if (g >= 1) load(1, (int)((g - 1) % n_chunks));
-    }
+    for (int64_t it = 0; it < my_tiles; it++)  // consumption order: G1(g), G2(g-1); no 64-bit div/mod in the loops
+      for (int c = 0; c < n_chunks; c++) {
+        load(0, c);
+        if (it > 0 || c > 0) load(1, c > 0 ? c - 1 : n_chunks - 1);
+      }
     if (G > 0) load(1, n_chunks - 1);
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (whole warp waits, one elected lane issues)
@@ -343,8 +344,8 @@ __global__ void __launch_bounds__(kFfnThreads, 1) k_ffn_tc(FfnArgs a) {
     const uint32_t ring = smem_u32(smem + FfnSmem::RING);
     const uint32_t x_hi = tmem + TM_X, x_lo = tmem + TM_X + 64;
 
-    auto issue_g2 = [&](int64_t gp) {  // Y += H(gp) W2c^T
-      const int j = (int)(gp % n_chunks), buf = (int)(gp & 1);
+    auto issue_g2 = [&](int64_t gp, int j) {  // Y += H(gp) W2c^T; j = chunk index of item gp
+      const int buf = (int)(gp & 1);
       const uint32_t st_hi = stage;
       mbar_wait(&full[stage], phase);
       if (++stage == kFfnStages) stage = 0, phase ^= 1;
@@ -426,10 +427,10 @@ __global__ void __launch_bounds__(kFfnThreads, 1) k_ffn_tc(FfnArgs a) {
           if (c == n_chunks - 1) mma_commit(x_free);  // every read of the X images of this tile has retired
         }
         __syncwarp();
-        if (g >= 1) issue_g2(g - 1);
+        if (g >= 1) issue_g2(g - 1, c > 0 ? c - 1 : n_chunks - 1);
       }
     }
-    if (G > 0) issue_g2(G - 1);
+    if (G > 0) issue_g2(G - 1, n_chunks - 1);
   } else {
     // ------------------------------------------------------------------ epilogue warps (2 groups x 128 threads)
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
@@ -751,10 +752,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1) k_f
         if (++stage == kPairStages) stage = 0, phase ^= 1;
       }
     };
-    for (int64_t g = 0; g < G; g++) {
-      load(0, (int)(g % n_chunks));
-      if (g >= 1) load(1, (int)((g - 1) % n_chunks));
-    }
+    for (int64_t it = 0; it < my_tiles; it++)  // no 64-bit div/mod in the loops
+      for (int c = 0; c < n_chunks; c++) {
+        load(0, c);
+        if (it > 0 || c > 0) load(1, c > 0 ? c - 1 : n_chunks - 1);
+      }
     if (G > 0) load(1, n_chunks - 1);
   } else if (warp == 10) {
     // ------------------------------------------------------------------ activation I/O warp
@@ -834,8 +836,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1) k_f
     };
     auto stage_bar = [&](uint32_t addr) -> uint64_t* { return &empty[(addr - ring) / kPairStageBytes]; };
 
-    auto issue_g2 = [&](int64_t gp) {  // Y += H(gp) W2c^T
-      const int j = (int)(gp % n_chunks), buf = (int)(gp & 1);
+    auto issue_g2 = [&](int64_t gp, int j) {  // Y += H(gp) W2c^T; j = chunk index of item gp
+      const int buf = (int)(gp & 1);
       const uint32_t whi = wait_stage();
       const uint32_t wlo = (kSplit == 3) ? wait_stage() : whi;
       FFN_TRACE(0, 3, gp);
@@ -917,10 +919,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1) k_f
         }
         __syncwarp();
         FFN_TRACE(0, 2, g);
-        if (g >= 1) issue_g2(g - 1);
+        if (g >= 1) issue_g2(g - 1, c > 0 ? c - 1 : n_chunks - 1);
       }
     }
-    if (G > 0) issue_g2(G - 1);
+    if (G > 0) issue_g2(G - 1, n_chunks - 1);
     if (tr_on) {
       long long gt;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
@@ -1119,10 +1121,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1) k_f
 
 static long long* g_ffn_trace = nullptr;
 static long long* g_mix_trace = nullptr;
+static long long* g_attn_trace = nullptr;
 void tc_set_ffn_trace(long long* buf) { g_ffn_trace = buf; }
 void tc_set_trace(int cls, long long* buf) {
   if (cls == 1) g_ffn_trace = buf;
   if (cls == 2) g_mix_trace = buf;
+  if (cls == 3) g_attn_trace = buf;
 }
 
 static int launch_ffn_tc(const tw_flow_config* c, const FfnArgs& a_in, cudaStream_t st) {
@@ -1836,10 +1840,12 @@ __global__ void __launch_bounds__(192, 1) k_proj_tc(ProjArgs a) {
 // heads as chunks (issue order MMA1(g), MMA2(g-1) over a global head counter).  Only V of the 128 token rows are real
 // (51 % of the MMA rows for 65 atoms): the price of sample-aligned tiles; the kernel is tensor-bound, not HBM-bound.
 //   warp 0 score-image + W_c producer   warp 1 MMA issuer   warp 2 activation I/O (x in, LayerNorm rows out, bulk copies)
-//   warp 3 x -> operand tiles           warps 4-7 / 8-11 epilogue groups (feature halves [0,64) / [64,128))
+//   warps 3-6 / 7-10 epilogue groups (feature halves [0,64) / [64,128)): in-place conversion of the mixed operand, sample
+//   hand-over (accumulator initialisation + x -> bf16 hi/lo operand tiles), LayerNorm
 // TMEM: DM0 | DM1 | DO0 | DO1, 128 columns each.
-constexpr int kAttnThreads = 384;
-constexpr int kAttnWcStages = 3;
+constexpr int kAttnThreads = 352;
+constexpr int kAttnWcStages = 6;   // ring units of 16 KB: the hi or the lo image of one [128 out x 64 K] block of W_c,h
+constexpr int kAttnWcStage = 16384;
 constexpr int kAttnScStages = 2;
 constexpr uint32_t AT_DM = 0, AT_DO = 256;
 
@@ -1853,6 +1859,7 @@ struct AttnArgs {
   int64_t n, n_cond;
   int V, VP, H;
   float eps;
+  long long* trace;
 };
 
 struct AttnSmem {
@@ -1866,7 +1873,7 @@ struct AttnSmem {
   }
   __host__ __device__ uint32_t xb() const { return 0; }
   __host__ __device__ uint32_t wc() const { return xb_bytes; }
-  __host__ __device__ uint32_t sc() const { return wc() + kAttnWcStages * 32768; }
+  __host__ __device__ uint32_t sc() const { return wc() + kAttnWcStages * kAttnWcStage; }
   __host__ __device__ uint32_t xs() const { return sc() + kAttnScStages * sc_stage; }
   __host__ __device__ uint32_t stat() const { return xs() + xs_bytes + pad; }
   __host__ __device__ uint32_t vec() const { return stat() + 2 * 128 * 8; }
@@ -1895,9 +1902,9 @@ __global__ void __launch_bounds__(kAttnThreads, 1) k_attn_fused(AttnArgs a) {
   uint64_t* dm_full = wc_empty + kAttnWcStages;   // [2] MMA1 into DM[b] retired
   uint64_t* h_full = dm_full + 2;                 // [4] (b, K half) of the mixed operand written in place, 128 arrivals
   uint64_t* xs_full = h_full + 4;                 // the sample's x rows landed in the staging buffer (tx bytes)
-  uint64_t* xs_used = xs_full + 1;                // 32 + 256 arrivals: converted to operand tiles AND used to initialise DO
-  uint64_t* xb_full = xs_used + 1;                // 32 arrivals: operand tiles written
-  uint64_t* xb_free = xb_full + 1;                // commit: last MMA1 of the sample retired
+  uint64_t* xs_used = xs_full + 1;                // 256 arrivals: rows converted to operand tiles and used to initialise DO
+  uint64_t* xb_full = xs_used + 1;                // 256 arrivals: operand tiles written
+  uint64_t* xb_free = xb_full + 1;                // (unused: dm_full of a sample's last head implies it)
   uint64_t* do_init = xb_free + 1;                // 256 arrivals: DO initialised with x
   uint64_t* do_full = do_init + 1;                // commit: last MMA2 of the sample retired
   uint64_t* ln_staged = do_full + 1;              // 256 arrivals: LayerNorm rows parked in the staging buffer
@@ -1910,8 +1917,8 @@ __global__ void __launch_bounds__(kAttnThreads, 1) k_attn_fused(AttnArgs a) {
     for (int i = 0; i < 2; i++) mbar_init(&dm_full[i], 1);
     for (int i = 0; i < 4; i++) mbar_init(&h_full[i], 128);
     mbar_init(xs_full, 1);
-    mbar_init(xs_used, 32 + 256);
-    mbar_init(xb_full, 32);
+    mbar_init(xs_used, 256);
+    mbar_init(xb_full, 256);
     mbar_init(xb_free, 1);
     mbar_init(do_init, 256);
     mbar_init(do_full, 1);
@@ -1925,39 +1932,40 @@ __global__ void __launch_bounds__(kAttnThreads, 1) k_attn_fused(AttnArgs a) {
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const int ksteps = VP / 16;
+  const bool tr_on = a.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0;
+  int tr_n = 0;
+#define AT_TRACE(role, ev, item) TW_TRACE(a.trace, tr_on, tr_n, role, ev, item)
   auto sample_of = [&](int64_t it) -> int64_t { return blockIdx.x + it * gridDim.x; };
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ score images and W_c tiles, in consumption order
-    uint32_t ss = 0, sp = 0, ws = 0, wp = 0;
-    auto load_scores = [&](int64_t g) {
-      const int64_t n = sample_of(g / H);
-      const uint8_t* src = a.scores_img + ((size_t)(n % a.n_cond) * H + (size_t)(g % H)) * (2 * mat_bytes);
-      mbar_wait(&sc_empty[ss], sp ^ 1);
-      if (elect_one()) {
-        mbar_arrive_expect_tx(&sc_full[ss], kParts * mat_bytes);
-        bulk_g2s(smem + L.sc() + ss * L.sc_stage, src, kParts * mat_bytes, &sc_full[ss]);
-      }
-      __syncwarp();
-      if (++ss == kAttnScStages) ss = 0, sp ^= 1;
-    };
-    auto load_wc = [&](int64_t g) {  // the two K blocks (hi | lo, 32 KB each) of W_c,h
-      const int h = (int)(g % H);
-      for (int kb = 0; kb < 2; kb++) {
-        mbar_wait(&wc_empty[ws], wp ^ 1);
-        if (elect_one()) {
-          mbar_arrive_expect_tx(&wc_full[ws], kParts * 16384u);
-          bulk_g2s(smem + L.wc() + ws * 32768, a.wc[net] + (size_t)(h * 2 + kb) * 32768, kParts * 16384u, &wc_full[ws]);
+    // ------------------------------------------------------------------ score images (lane 1) and W_c tiles (lane 0)
+    // Two INDEPENDENT producer loops on two lanes of one warp: a single in-order producer would hold back W_c loads
+    // whose ring stage is already free while it waits for a score stage (and vice versa).
+    if (lane == 1) {
+      uint32_t ss = 0, sp = 0;
+      for (int64_t it = 0; it < my_n; it++) {
+        const int64_t n = sample_of(it);
+        const uint8_t* src0 = a.scores_img + (size_t)(a.n_cond == a.n ? n : n % a.n_cond) * H * (2 * mat_bytes);
+        for (int h = 0; h < H; h++) {
+          mbar_wait(&sc_empty[ss], sp ^ 1);
+          mbar_arrive_expect_tx(&sc_full[ss], kParts * mat_bytes);
+          bulk_g2s(smem + L.sc() + ss * L.sc_stage, src0 + (size_t)h * (2 * mat_bytes), kParts * mat_bytes, &sc_full[ss]);
+          if (++ss == kAttnScStages) ss = 0, sp ^= 1;
         }
-        __syncwarp();
-        if (++ws == kAttnWcStages) ws = 0, wp ^= 1;
       }
-    };
-    for (int64_t g = 0; g < G; g++) {
-      load_scores(g);
-      if (g >= 1) load_wc(g - 1);
+    } else if (lane == 0) {
+      uint32_t ws = 0, wp = 0;
+      for (int64_t g = 0, h = 0; g < G; g++, h = (h + 1 == H ? 0 : h + 1)) {  // W_c,h: per K block the hi image, then the lo image
+        for (int u = 0; u < 2 * kParts; u++) {
+          const int kb = u / kParts, part = u % kParts;
+          mbar_wait(&wc_empty[ws], wp ^ 1);
+          mbar_arrive_expect_tx(&wc_full[ws], (uint32_t)kAttnWcStage);
+          bulk_g2s(smem + L.wc() + ws * kAttnWcStage, a.wc[net] + (size_t)(h * 2 + kb) * 32768 + part * 16384, kAttnWcStage, &wc_full[ws]);
+          if (++ws == kAttnWcStages) ws = 0, wp ^= 1;
+        }
+      }
     }
-    if (G > 0) load_wc(G - 1);
+    __syncwarp();
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     uint32_t ss = 0, sp = 0, ws = 0, wp = 0, ph_xb = 0, ph_h = 0, ph_doinit = 0;
@@ -1968,45 +1976,62 @@ __global__ void __launch_bounds__(kAttnThreads, 1) k_attn_fused(AttnArgs a) {
     const uint32_t x_hi = smem_u32(smem + L.xb()), x_lo = x_hi + L.xb_bytes / 2;
     const uint64_t b_hi = b_desc0 | (uint64_t)(x_hi >> 4), b_lo = b_desc0 | (uint64_t)(x_lo >> 4);
 
-    auto issue_mma2 = [&](int64_t gp) {  // DO += mixed(gp) W_c^T
-      const int hp = (int)(gp % H), b = (int)(gp & 1), dob = (int)((gp / H) & 1);
+    auto issue_mma2 = [&](int64_t gp, int hp, int dob) {  // DO[dob] += mixed(gp) W_c,hp^T
+      const int b = (int)(gp & 1);
       if (hp == 0) {
         mbar_wait(do_init, ph_doinit);
         ph_doinit ^= 1;
       }
       for (int kb = 0; kb < 2; kb++) {
-        mbar_wait(&wc_full[ws], wp);
+        mbar_wait(&wc_full[ws], wp);  // hi image of this K block
+        AT_TRACE(0, 3 + 2 * kb, gp);
         mbar_wait(&h_full[b * 2 + kb], (ph_h >> (b * 2 + kb)) & 1u);
         ph_h ^= 1u << (b * 2 + kb);
         tc_fence_after();
+        AT_TRACE(0, 4 + 2 * kb, gp);
+        const uint32_t m_hi = tmem + AT_DM + b * 128 + kb * 64, m_lo = m_hi + 32;
+        const uint32_t d = tmem + AT_DO + dob * 128;
         if (elect_one()) {
-          const uint32_t w_hi = smem_u32(smem + L.wc() + ws * 32768), w_lo = w_hi + 16384;
-          const uint32_t m_hi = tmem + AT_DM + b * 128 + kb * 64, m_lo = m_hi + 32;
-          const uint32_t d = tmem + AT_DO + dob * 128;
+          const uint32_t w_hi = smem_u32(smem + L.wc() + ws * kAttnWcStage);
 #pragma unroll
           for (int k = 0; k < 4; k++) mma_ts(d, m_hi + k * 8, desc_kmajor_sw128(w_hi + k * 32), idesc2, 1);
           if (kSplit == 3) {
 #pragma unroll
             for (int k = 0; k < 4; k++) mma_ts(d, m_lo + k * 8, desc_kmajor_sw128(w_hi + k * 32), idesc2, 1);
-#pragma unroll
-            for (int k = 0; k < 4; k++) mma_ts(d, m_hi + k * 8, desc_kmajor_sw128(w_lo + k * 32), idesc2, 1);
           }
           mma_commit(&wc_empty[ws]);
-          if (kb == 1 && hp == H - 1) mma_commit(do_full);
+          if (kSplit != 3 && kb == 1 && hp == H - 1) mma_commit(do_full);
         }
         __syncwarp();
         if (++ws == kAttnWcStages) ws = 0, wp ^= 1;
+        if (kSplit == 3) {
+          mbar_wait(&wc_full[ws], wp);  // lo image
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t w_lo = smem_u32(smem + L.wc() + ws * kAttnWcStage);
+#pragma unroll
+            for (int k = 0; k < 4; k++) mma_ts(d, m_hi + k * 8, desc_kmajor_sw128(w_lo + k * 32), idesc2, 1);
+            mma_commit(&wc_empty[ws]);
+            if (kb == 1 && hp == H - 1) mma_commit(do_full);
+          }
+          __syncwarp();
+          if (++ws == kAttnWcStages) ws = 0, wp ^= 1;
+        }
       }
     };
 
     int64_t g = 0;
     for (int64_t it = 0; it < my_n; it++) {
+      AT_TRACE(0, 7, it);
       mbar_wait(xb_full, ph_xb);
       ph_xb ^= 1;
       tc_fence_after();
+      AT_TRACE(0, 8, it);
       for (int h = 0; h < H; h++, g++) {
+        AT_TRACE(0, 0, g);
         mbar_wait(&sc_full[ss], sp);
         tc_fence_after();
+        AT_TRACE(0, 1, g);
         if (elect_one()) {
           const uint32_t s_hi = smem_u32(smem + L.sc() + ss * L.sc_stage), s_lo = s_hi + mat_bytes;
           const uint64_t a_hi = a_desc0 | (uint64_t)(s_hi >> 4), a_lo = a_desc0 | (uint64_t)(s_lo >> 4);
@@ -2024,14 +2049,14 @@ __global__ void __launch_bounds__(kAttnThreads, 1) k_attn_fused(AttnArgs a) {
           }
           mma_commit(&sc_empty[ss]);
           mma_commit(&dm_full[g & 1]);
-          if (h == H - 1) mma_commit(xb_free);
         }
         __syncwarp();
+        AT_TRACE(0, 2, g);
         if (++ss == kAttnScStages) ss = 0, sp ^= 1;
-        if (g >= 1) issue_mma2(g - 1);
+        if (g >= 1) issue_mma2(g - 1, h > 0 ? h - 1 : H - 1, (int)((h > 0 ? it : it - 1) & 1));
       }
     }
-    if (G > 0) issue_mma2(G - 1);
+    if (G > 0) issue_mma2(G - 1, H - 1, (int)((my_n - 1) & 1));
   } else if (warp == 2) {
     // ------------------------------------------------------------------ activation I/O: x rows in, LayerNorm rows out
     uint32_t ph_used = 0, ph_staged = 0;
@@ -2075,38 +2100,10 @@ __global__ void __launch_bounds__(kAttnThreads, 1) k_attn_fused(AttnArgs a) {
     }
     if (lane == 0) bulk_wait_group0();
     __syncwarp();
-  } else if (warp == 3) {
-    // ------------------------------------------------------------------ staged x rows -> bf16 hi/lo MN-major operand tiles
-    uint32_t ph_xs = 0, ph_free = 0;
-    const int nb = lane >> 4;
-    const uint32_t c16 = (uint32_t)(lane & 15) >> 1, sub = (uint32_t)(lane & 1) * 8;
-    uint8_t* hi_base = smem + L.xb() + nb * (VP * 128);
-    uint8_t* lo_base = hi_base + L.xb_bytes / 2;
-    for (int64_t it = 0; it < my_n; it++) {
-      mbar_wait(xs_full, ph_xs);
-      ph_xs ^= 1;
-      if (it >= 1) {
-        mbar_wait(xb_free, ph_free);
-        ph_free ^= 1;
-      }
-      for (int j = 0; j < VP; j++) {
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (j < V) v = *reinterpret_cast<const float4*>(smem + L.xs() + j * kXsRow + lane * 16);
-        uint32_t h0, l0, h1, l1;
-        split2(v.x, v.y, h0, l0);
-        split2(v.z, v.w, h1, l1);
-        const uint32_t off = (uint32_t)j * 128u + ((c16 ^ ((uint32_t)j & 7u)) << 4) + sub;
-        *reinterpret_cast<uint2*>(hi_base + off) = make_uint2(h0, h1);
-        if (kSplit == 3) *reinterpret_cast<uint2*>(lo_base + off) = make_uint2(l0, l1);
-      }
-      fence_proxy_async_smem();
-      mbar_arrive(xb_full);
-      mbar_arrive(xs_used);
-    }
   } else {
     // ------------------------------------------------------------------ epilogue groups (kb = feature half)
     const int q = warp & 3;
-    const int kb = (warp - 4) >> 2;
+    const int kb = (warp - 3) >> 2;
     const int row = q * 32 + lane;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     const bool row_valid = row < V;
@@ -2114,7 +2111,13 @@ __global__ void __launch_bounds__(kAttnThreads, 1) k_attn_fused(AttnArgs a) {
     uint8_t* my_xs = smem + L.xs() + row * kXsRow + kb * 256;  // this thread's 64 columns of its row in the staging buffer
     float2* stat = reinterpret_cast<float2*>(smem + L.stat());
 
-    auto init_do = [&](int64_t it) {  // DO[it & 1][:, kb half] <- x (rows >= V: zeros)
+    // Sample hand-over (every epilogue thread: its token row, its group's 64 features): DO[it & 1] <- x (the residual rides
+    // in the accumulator) and the row of the MN-major bf16 hi/lo operand tile of MMA1 -- [atom][64 features] = one swizzled
+    // 128-byte row per (thread, hi/lo).  Called after dm_full of the previous sample's LAST head, i.e. when every MMA1 that
+    // read the old tiles has retired.
+    uint8_t* xb_hi = smem + L.xb() + kb * (VP * 128) + row * 128;
+    uint8_t* xb_lo = xb_hi + L.xb_bytes / 2;
+    auto prepare_sample = [&](int64_t it) {
       mbar_wait(xs_full, ph_xs);
       ph_xs ^= 1;
       const uint32_t base = tmem + lane_base + AT_DO + (uint32_t)(it & 1) * 128 + kb * 64;
@@ -2129,10 +2132,23 @@ __global__ void __launch_bounds__(kAttnThreads, 1) k_attn_fused(AttnArgs a) {
           r[4 * j + 2] = __float_as_uint(v.z), r[4 * j + 3] = __float_as_uint(v.w);
         }
         tmem_st16(base + b * 16, r);
+        if (row < VP) {
+          uint32_t hi[8], lo[8];
+#pragma unroll
+          for (int j = 0; j < 8; j++) split2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]), hi[j], lo[j]);
+#pragma unroll
+          for (int cc = 0; cc < 2; cc++) {
+            const uint32_t pos = (((uint32_t)(b * 2 + cc)) ^ ((uint32_t)row & 7u)) << 4;
+            *reinterpret_cast<uint4*>(xb_hi + pos) = make_uint4(hi[4 * cc], hi[4 * cc + 1], hi[4 * cc + 2], hi[4 * cc + 3]);
+            if (kSplit == 3) *reinterpret_cast<uint4*>(xb_lo + pos) = make_uint4(lo[4 * cc], lo[4 * cc + 1], lo[4 * cc + 2], lo[4 * cc + 3]);
+          }
+        }
       }
       tmem_st_wait();
       tc_fence_before();
+      fence_proxy_async_smem();
       mbar_arrive(do_init);
+      mbar_arrive(xb_full);
       mbar_arrive(xs_used);
     };
     auto layer_norm = [&](int64_t it, bool last) {  // sample `it` finished: drain, normalise, park for the bulk store
@@ -2187,15 +2203,16 @@ __global__ void __launch_bounds__(kAttnThreads, 1) k_attn_fused(AttnArgs a) {
       mbar_arrive(ln_staged);
     };
 
-    if (my_n > 0) init_do(0);
-    const int init_slot = H >= 2 ? H - 2 : 0;
+    if (my_n > 0) prepare_sample(0);
     int64_t g = 0;
     for (int64_t it = 0; it < my_n; it++) {
       for (int h = 0; h < H; h++, g++) {
         const int b = (int)(g & 1);
+        if (q == 0 && kb == 0) { AT_TRACE(1, 0, g); }
         mbar_wait(&dm_full[b], (ph_dm >> b) & 1u);
         ph_dm ^= 1u << b;
         tc_fence_after();
+        if (q == 0 && kb == 0) { AT_TRACE(1, 1, g); }
         {
           const uint32_t base = tmem + lane_base + AT_DM + b * 128 + kb * 64;
           uint32_t r0[32], r1[32];
@@ -2215,8 +2232,11 @@ __global__ void __launch_bounds__(kAttnThreads, 1) k_attn_fused(AttnArgs a) {
         }
         tc_fence_before();
         mbar_arrive(&h_full[b * 2 + kb]);
+        if (q == 0 && kb == 0) { AT_TRACE(1, 2, g); }
         if (h == 0 && it > 0) layer_norm(it - 1, false);
-        if (h == init_slot && it + 1 < my_n) init_do(it + 1);
+        if (q == 0 && kb == 0 && h == 0 && it > 0) { AT_TRACE(1, 3, g); }
+        if (h == H - 1 && it + 1 < my_n) prepare_sample(it + 1);
+        if (q == 0 && kb == 0 && h == H - 1) { AT_TRACE(1, 4, g); }
       }
     }
     if (my_n > 0) layer_norm(my_n - 1, true);
@@ -2224,6 +2244,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) k_attn_fused(AttnArgs a) {
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc<512>(tmem);
+#undef AT_TRACE
 }
 
 // ============================================================================================
@@ -2754,6 +2775,7 @@ int tc_attention_layer(const tw_flow_config* c, const ParamView& pv, int k, int 
       }
       a.scores_img = tc.scores_img;
       a.n = n, a.n_cond = n_cond, a.V = V, a.VP = VP, a.H = H, a.eps = c->layer_norm_eps;
+      a.trace = g_attn_trace;
       dim3 grid((unsigned)(n < 74 ? n : 74), 2);
       if (c->precision == TW_PRECISION_BF16X3)
         k_attn_fused<3><<<grid, kAttnThreads, fused_smem, st>>>(a);

@@ -10,7 +10,7 @@ from timewarp_b200.peptides import tetrapeptide_2olx
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 lo, hi = (int(sys.argv[2]), int(sys.argv[3])) if len(sys.argv) > 3 else (20, 28)
-cls = int(sys.argv[4]) if len(sys.argv) > 4 else 1  # 1 fused FFN, 2 mixing kernel
+cls = int(sys.argv[4]) if len(sys.argv) > 4 else 1  # 1 fused FFN, 2 mixing kernel, 3 fused attention
 pep = tetrapeptide_2olx()
 m = tw.custom_transformer_nvp_constructor(tw.kernel_transformer_nvp_config("bf16x3"))
 m.load_state_dict(fo.synth_state_dict(fo.OracleConfig(), 0))
@@ -38,7 +38,11 @@ c0, g0, c1, g1 = (int(v) for v in raw[3 * 2048:3 * 2048 + 4])
 if g1 > g0:
     print(f"MMA warp: {c1 - c0} cycles in {g1 - g0} ns -> SM clock {1e3 * (c1 - c0) / (g1 - g0):.0f} MHz")
 t0 = min(int(t[r, 0, 1]) for r in range(3) if t[r, 0, 1] > 0)
-if cls == 2:
+if cls == 3:
+    names = {0: {0: 'mma: head top', 1: 'mma: scores landed', 2: 'mma: MMA1 issued', 3: 'mma2: Wc kb0 landed', 4: 'mma2: h_full kb0', 5: 'mma2: Wc kb1 landed', 6: 'mma2: h_full kb1', 7: 'mma: sample top (item=sample)', 8: 'mma: xb_full (item=sample)'},
+             1: {0: 'epi: wait dm', 1: 'epi: dm_full', 2: 'epi: h arrived', 3: 'epi: LN done', 4: 'epi: init_do done'},
+             2: {0: 'conv: wait xs (item=sample)', 1: 'conv: xs_full', 2: 'conv: xb_free', 3: 'conv: done'}}
+elif cls == 2:
     names = {0: {0: 'mma: sample top', 1: 'mma: hs_full', 2: 'mma: head top', 3: 'mma: scores landed', 4: 'mma: head issued'},
              1: {2: 'epi0: wait d_full', 3: 'epi0: d_full', 5: 'epi0: staging free', 4: 'epi0: staged', 7: 'epi0: sync2', 6: 'epi0: stores issued'},
              2: {0: 'conv: sample top (item=sample)', 2: 'conv: buffer free', 1: 'conv: done'}}
@@ -53,7 +57,7 @@ for r in range(3):
         if clk == 0:
             break
         ev, item = code & 0xFF, code >> 8
-        if lo <= item < hi or (r == 1 and ev >= 5 and lo <= item * 8 + 16 < hi + 16):
+        if lo <= item < hi or (cls == 3 and ((r == 2) or (r == 0 and ev >= 7)) and lo <= item * 6 < hi):
             rows.append((clk - t0, item, names[r][ev]))
 rows.sort()
 prev = rows[0][0] if rows else 0
