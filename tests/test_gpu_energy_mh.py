@@ -269,3 +269,31 @@ def test_sample_on_batches_against_oracle(random_velocs):
         np.testing.assert_allclose(acc[i], p_ref, rtol=5e-2, atol=1e-6)
     with pytest.raises(NotImplementedError):
         sampling.sample_on_batches(batches, m, torch.device("cuda"), energy, True, masses)
+
+
+def test_mh_chains_graph_replay_matches_eager():
+    """One MH iteration replayed as a CUDA graph == the same iteration launched eagerly (same RNG stream, same state)."""
+    pep = alanine_dipeptide()
+    m, _ = build_model(TINY_O, "fp32", 0)
+    energy = PeptidePotentialEnergy(amber_like_system(pep))
+    B = 8
+    x0 = torch.from_numpy(_confs(pep, B, 5)).cuda()
+    at = torch.tensor(pep.atom_types)[None].repeat(B, 1).cuda()
+    mask = torch.zeros(B, 22, dtype=torch.bool, device="cuda")
+    results = []
+    for use_graph in (False, True):
+        torch.manual_seed(3)
+        chains = sampling.MHChains(m, energy, at, mask, x0, accept=False)  # accept everything: the state moves every step
+        if use_graph:
+            chains.capture_graph(warmup=2)
+        else:
+            chains.step(), chains.step()  # a capture pass records kernels without running them: no state / RNG change
+        torch.manual_seed(4)
+        for _ in range(3):
+            acc = chains.step()
+        torch.cuda.synchronize()
+        results.append((chains.x.clone(), chains.last["exponent"].clone(), acc.clone(), chains.n_steps))
+    assert results[0][3] == results[1][3] == 5
+    torch.testing.assert_close(results[0][0], results[1][0], rtol=0, atol=0)
+    torch.testing.assert_close(results[0][1], results[1][1], rtol=0, atol=0, equal_nan=True)
+    assert torch.equal(results[0][2], results[1][2])

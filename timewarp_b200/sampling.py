@@ -137,14 +137,26 @@ class MHChains:
         self.n_accepted = torch.zeros(self.B, dtype=torch.int64, device=dev)
         self.n_steps = 0
         self.last = {}
+        self._graph, self._graph_last = None, None
         self._empty_adj = torch.zeros(0, 2, dtype=torch.long, device=dev)
         self._empty_ebi = torch.zeros(0, dtype=torch.long, device=dev)
 
     @torch.no_grad()  # the reference samples under no_grad (evaluation_utils.py:468)
     def step(self):
+        """One MH iteration of every chain.  After `capture_graph()` the iteration is replayed as ONE CUDA graph
+        (≈210 kernel launches, no host work between them); the state tensors keep their addresses either way."""
+        if self._graph is not None:
+            self._graph.replay()
+            self.last = self._graph_last  # the graph's static output tensors
+        else:
+            self._step_impl()
+        self.n_steps += 1
+        return self.last["accepted"]
+
+    def _step_impl(self):
         m = self.model
         if self.random_velocs and self.resample_velocs:
-            self.xv = torch.randn_like(self.xv)  # :590-592
+            self.xv.normal_()  # :590-592 (same draw as torch.randn_like, in place: the state keeps its address)
         y, yv, p_xy = m.conditional_sample_with_logp(
             atom_types=self.atom_types, x_coords=self.x, x_velocs=self.xv, adj_list=self._empty_adj,
             edge_batch_idx=self._empty_ebi, masked_elements=self.mask, num_samples=1)  # :609-617
@@ -162,15 +174,30 @@ class MHChains:
         if self.accept:
             ex, pa, acc, _ = mh_accept(self.e_pot_x, e_pot_y, e_kin_x, e_kin_y, p_xy, p_yx, u, self.x, self.xv, y, yv)
             accb = acc.view(torch.bool)
-            self.e_pot_x = torch.where(accb, e_pot_y, self.e_pot_x)
+            self.e_pot_x.copy_(torch.where(accb, e_pot_y, self.e_pot_x))
         else:  # accept everything (:698-705)
             ex, pa, acc, _ = mh_accept(self.e_pot_x, e_pot_y, e_kin_x, e_kin_y, p_xy, p_yx, u)
-            self.x, self.xv, self.e_pot_x = y.contiguous(), yv.contiguous(), e_pot_y
+            self.x.copy_(y), self.xv.copy_(yv), self.e_pot_x.copy_(e_pot_y)
             accb = torch.ones_like(acc, dtype=torch.bool)
         self.n_accepted += accb
-        self.n_steps += 1
         self.last = dict(exponent=ex, acceptance=pa, accepted=accb, p_xy=p_xy, p_yx=p_yx, e_pot_y=e_pot_y, e_kin_y=e_kin_y)
         return accb
+
+    def capture_graph(self, warmup: int = 2):
+        """Capture one iteration into a CUDA graph (torch.cuda.graph: the torch RNG draws stay graph-safe, outputs live
+        in the graph's private pool).  `warmup` eager iterations run first so that every lazy initialisation (weight
+        packing, workspace, kernel attributes) happens outside the capture.  Returns self."""
+        for _ in range(max(int(warmup), 1)):
+            self.step()
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            self._step_impl()
+        self._graph, self._graph_last = graph, self.last
+        return self
+
+    def release_graph(self):
+        self._graph = None
 
     def acceptance_rate(self) -> Tensor:
         return self.n_accepted.to(torch.float32) / max(self.n_steps, 1)
