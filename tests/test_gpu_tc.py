@@ -27,6 +27,12 @@ def test_bf16x3_matches_golden(name):
     ll = m.log_likelihood(y_coords=g["y_coords"].cuda(), y_velocs=g["y_velocs"].cuda(), **_kw(g))
     err64 = assert_rel(ll, g["log_likelihood_f64"], what="bf16x3 ll vs reference fp64")
     assert_rel(ll, g["log_likelihood"], what="bf16x3 ll vs reference fp32")
+    assert ll.requires_grad  # grad mode: the taped forward (two-kernel attention, tape written)
+    with torch.no_grad():  # inference path: fused attention kernel, nothing taped
+        ll_inf = m.log_likelihood(y_coords=g["y_coords"].cuda(), y_velocs=g["y_velocs"].cuda(), **_kw(g))
+    assert not ll_inf.requires_grad
+    assert_rel(ll_inf, g["log_likelihood_f64"], what="bf16x3 inference-path ll vs reference fp64")
+    assert_rel(ll_inf, ll.detach(), rel=1e-5, what="inference path vs taped path")
     m32, _ = build_model(FULL_O, "fp32", int(g["weight_seed"]))
     ll32 = m32.log_likelihood(y_coords=g["y_coords"].cuda(), y_velocs=g["y_velocs"].cuda(), **_kw(g))
     assert_rel(ll, ll32, rel=2e-5, what="bf16x3 vs fp32 CUDA path")
@@ -51,6 +57,8 @@ def test_bf16x3_many_tiles_and_tail():
               masked_elements=mask)
     a, b = m.log_likelihood(**kw), m32.log_likelihood(**kw)
     assert_rel(a, b, rel=2e-5, what="bf16x3 vs fp32, 52 tiles")
+    with torch.no_grad():
+        assert_rel(m.log_likelihood(**kw), b, rel=2e-5, what="bf16x3 inference path vs fp32, 52 tiles")
     # weights modified in place are re-packed
     with torch.no_grad():
         m.flow.chain[0].scale_transformer.encoder_layers[0].linear1.weight.mul_(1.5)
@@ -63,3 +71,29 @@ def test_bf16_plain_is_close():
     m, _ = build_model(FULL_O, "bf16", 0)
     ll = m.log_likelihood(y_coords=g["y_coords"].cuda(), y_velocs=g["y_velocs"].cuda(), **_kw(g))
     assert_rel(ll, g["log_likelihood"], rel=2e-2, what="plain bf16 (training precision)")
+
+
+@pytest.mark.parametrize("B,V,lengths", [(37, 65, None), (9, 65, [65, 64, 33, 65, 1, 17, 65, 48, 65]), (3, 80, [80, 79, 66]), (130, 22, None)])
+def test_bf16x3_inference_path_odd_sizes_vs_oracle(B, V, lengths):
+    """The inference kernels (CTA-pair FFN with a partial last 256-token tile, fused attention with ragged / masked
+    samples, samples straddling tile boundaries) against the CPU oracle: log_likelihood, and sample -> density round trip."""
+    torch.manual_seed(B * 1000 + V)
+    mask = torch.zeros(B, V, dtype=torch.bool)
+    if lengths is not None:
+        for b, n in enumerate(lengths):
+            mask[b, n:] = True
+    keep = (~mask)[:, :, None]
+    x = 0.3 * torch.randn(B, V, 3) * keep
+    y = (x + 0.02 * torch.randn(B, V, 3)) * keep
+    xv, yv = torch.randn(B, V, 3) * keep, torch.randn(B, V, 3) * keep
+    at = torch.randint(0, 5, (B, V)) * (~mask)
+    m, sd = build_model(FULL_O, "bf16x3", 3)
+    ll_ref = fo.log_likelihood(sd, FULL_O, at, x, xv, y, yv, mask, distance_mode="direct")
+    kw = dict(atom_types=at.cuda(), x_coords=x.cuda(), x_velocs=xv.cuda(), adj_list=EMPTY_ADJ.cuda(), edge_batch_idx=EMPTY_EBI.cuda(),
+              masked_elements=mask.cuda())
+    with torch.no_grad():
+        ll = m.log_likelihood(y_coords=y.cuda(), y_velocs=yv.cuda(), **kw)
+        assert_rel(ll, ll_ref, what="inference path vs oracle")
+        yc, yvel, lp = m.conditional_sample_with_logp(num_samples=1, **kw)
+        ll2 = m.log_likelihood(y_coords=yc[0], y_velocs=yvel[0], **kw)
+    torch.testing.assert_close(ll2, lp[0], rtol=1e-4, atol=2e-3)
