@@ -73,10 +73,11 @@ def test_bf16_plain_is_close():
     assert_rel(ll, g["log_likelihood"], rel=2e-2, what="plain bf16 (training precision)")
 
 
-@pytest.mark.parametrize("B,V,lengths", [(37, 65, None), (9, 65, [65, 64, 33, 65, 1, 17, 65, 48, 65]), (3, 80, [80, 79, 66]), (130, 22, None)])
+@pytest.mark.parametrize("B,V,lengths", [(37, 65, None), (9, 65, [65, 64, 33, 65, 1, 17, 65, 48, 65]), (3, 80, [80, 79, 66]), (130, 22, None), (150, 65, None)])
 def test_bf16x3_inference_path_odd_sizes_vs_oracle(B, V, lengths):
     """The inference kernels (CTA-pair FFN with a partial last 256-token tile, fused attention with ragged / masked
-    samples, samples straddling tile boundaries) against the CPU oracle: log_likelihood, and sample -> density round trip."""
+    samples, samples straddling tile boundaries; 150 x 65 tokens = 39 pair tiles over 37 pairs: two leftover tiles split
+    along the hidden dimension) against the CPU oracle: log_likelihood, and sample -> density round trip."""
     torch.manual_seed(B * 1000 + V)
     mask = torch.zeros(B, V, dtype=torch.bool)
     if lengths is not None:

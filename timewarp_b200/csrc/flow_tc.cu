@@ -245,6 +245,8 @@ struct FfnArgs {
   float eps;
   int dbg;  // TW_FFN_DBG experiments (timing only, results invalid): 1 no weight traffic, 2 no chunk-epilogue math, 4 hi-only MMAs
   long long* trace;  // optional event trace of CTA (0,0) (tw_debug_set_ffn_trace): [role][1024][2] = {event | item << 8, clock64}
+  float* tail[2];    // pair kernel: split-tile partial sums [tile][rank][128][128] (nullptr: leftover tiles are not split)
+  int* tail_cnt[2];  // arrival counters [tile][rank]
 };
 
 struct FfnSmem {
@@ -673,7 +675,29 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1) k_f
   const int n_chunks = a.F / kFfnChunk;
   const int64_t n_ptiles = (a.M + 255) / 256;  // 256-token tiles of the pair
   const int64_t pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
-  const int64_t my_tiles = (pair < n_ptiles) ? (n_ptiles - pair + n_pairs - 1) / n_pairs : 0;
+  // Work schedule.  Every pair runs R = n_ptiles / n_pairs full tiles; the Lft leftover tiles (7.03 rounds would cost 8)
+  // are SPLIT along the hidden dimension: S pairs each run n_chunks / S chunks of a leftover tile, add their partial
+  // accumulator to a global scratch tile, and the last pair to arrive normalises and stores it.
+  const int64_t R = n_ptiles / n_pairs;
+  const int Lft = (int)(n_ptiles - R * n_pairs);
+  int S = 1;
+  if (a.tail[net] != nullptr && Lft > 0 && 2 * Lft <= (int)n_pairs && Lft <= kFfnTailTiles)
+    for (int d = n_chunks; d >= 2; d--)
+      if (n_chunks % d == 0 && (int64_t)d * Lft <= n_pairs) {
+        S = d;
+        break;
+      }
+  const bool split = S > 1;
+  const int cps = n_chunks / S;  // chunks per part
+  const bool has_partial = split && pair < (int64_t)Lft * S;
+  const int part_l = has_partial ? (int)pair / S : 0, part_p = has_partial ? (int)pair % S : 0;
+  const int pc0 = part_p * cps, pc1 = pc0 + cps;
+  const int64_t my_regular = split ? R : ((pair < n_ptiles) ? (n_ptiles - pair + n_pairs - 1) / n_pairs : 0);
+  const int64_t my_tiles = my_regular + (has_partial ? 1 : 0);  // tile iterations of this pair (the partial one is last)
+  auto tile_index = [&](int64_t it) -> int64_t { return it < my_regular ? pair + it * n_pairs : R * n_pairs + part_l; };
+  auto c_begin = [&](int64_t it) -> int { return it < my_regular ? 0 : pc0; };
+  auto c_end = [&](int64_t it) -> int { return it < my_regular ? n_chunks : pc1; };
+  int* tail_flag = reinterpret_cast<int*>(smem + FfnPairSmem::BARS + 448);  // 1: this CTA normalises the split tile
   constexpr int kParts = (kSplit == 3) ? 2 : 1;
   const bool tr_on = a.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0;
   int tr_n = 0;
@@ -732,7 +756,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1) k_f
   cluster_sync_all();  // both CTAs' barriers are initialised before any remote arrive / multicast commit
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const int64_t G = my_tiles * n_chunks;
+  const int64_t G = my_regular * n_chunks + (has_partial ? cps : 0);
 
   if (warp == 0) {
     // ------------------------------------------------------------------ producer: this CTA's half of every weight tile part
@@ -752,12 +776,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1) k_f
         if (++stage == kPairStages) stage = 0, phase ^= 1;
       }
     };
-    for (int64_t it = 0; it < my_tiles; it++)  // no 64-bit div/mod in the loops
-      for (int c = 0; c < n_chunks; c++) {
+    bool have_prev = false;
+    int prev_c = 0;
+    for (int64_t it = 0; it < my_tiles; it++)  // consumption order: G1(item), G2(previous item)
+      for (int c = c_begin(it); c < c_end(it); c++) {
         load(0, c);
-        if (it > 0 || c > 0) load(1, c > 0 ? c - 1 : n_chunks - 1);
+        if (have_prev) load(1, prev_c);
+        have_prev = true, prev_c = c;
       }
-    if (G > 0) load(1, n_chunks - 1);
+    if (have_prev) load(1, prev_c);
   } else if (warp == 10) {
     // ------------------------------------------------------------------ activation I/O warp
     // The staging buffer XS (128 padded fp32 rows) carries the x tile of the NEXT 256-token tile in (per-row bulk loads)
@@ -765,7 +792,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1) k_f
     // out (per-row bulk stores): the epilogue warps never touch global memory, and the 9.5 MB store burst of 148 CTAs
     // crossing a tile boundary in lock-step drains through the TMA queues without stalling them or the weight producer.
     uint32_t ph_staged = 0;
-    auto tile_row0 = [&](int64_t it) -> int64_t { return ((pair + it * n_pairs) * 2 + rank) * 128; };
+    auto tile_row0 = [&](int64_t it) -> int64_t { return (tile_index(it) * 2 + rank) * 128; };
     auto valid_rows = [&](int64_t row0) -> int {
       const int64_t left = a.M - row0;
       return left >= 128 ? 128 : (left > 0 ? (int)left : 0);
@@ -805,8 +832,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1) k_f
       }
     }
     if (my_tiles > 0) {
-      mbar_wait(ln_staged, ph_staged);  // LayerNorm of the last tile parked
-      store_out(my_tiles - 1);
+      mbar_wait(ln_staged, ph_staged);  // LayerNorm of the last tile parked (split tile: only by the last pair to arrive)
+      if (!has_partial || *reinterpret_cast<volatile int*>(tail_flag)) store_out(my_tiles - 1);
     }
     if (lane == 0) bulk_wait_group0();
     __syncwarp();
@@ -836,12 +863,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1) k_f
     };
     auto stage_bar = [&](uint32_t addr) -> uint64_t* { return &empty[(addr - ring) / kPairStageBytes]; };
 
-    auto issue_g2 = [&](int64_t gp, int j) {  // Y += H(gp) W2c^T; j = chunk index of item gp
+    auto issue_g2 = [&](int64_t gp, bool first, bool last) {  // Y += H(gp) W2c^T; first / last item of its tile iteration
       const int buf = (int)(gp & 1);
       const uint32_t whi = wait_stage();
       const uint32_t wlo = (kSplit == 3) ? wait_stage() : whi;
       FFN_TRACE(0, 3, gp);
-      if (j == 0) {
+      if (first) {
         mbar_wait(y_init, ph_yinit);
         ph_yinit ^= 1;
       }
@@ -867,7 +894,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1) k_f
       if (elect_one()) {
         mma_commit_pair(stage_bar(whi));
         if (kSplit == 3) mma_commit_pair(stage_bar(wlo));
-        if (j == n_chunks - 1) mma_commit_pair(y_full);
+        if (last) mma_commit_pair(y_full);
       }
       __syncwarp();
     };
@@ -878,11 +905,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1) k_f
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
       a.trace[3 * 2048] = clock64(), a.trace[3 * 2048 + 1] = gt;
     }
+    bool prev_first = false, prev_last = false;
     for (int64_t it = 0; it < my_tiles; it++) {
       mbar_wait(x_full, ph_x);
       ph_x ^= 1;
       tc_fence_after();
-      for (int c = 0; c < n_chunks; c++, g++) {
+      const int cb = c_begin(it), ce = c_end(it);
+      for (int c = cb; c < ce; c++, g++) {
         const uint32_t d1 = tmem + TM_DH + (uint32_t)(g & 1) * 128;
         FFN_TRACE(0, 0, g);
         {
@@ -915,14 +944,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1) k_f
         }
         if (elect_one()) {
           mma_commit_pair(&d1_full[g & 1]);
-          if (c == n_chunks - 1) mma_commit_pair(x_free);
+          if (c == ce - 1) mma_commit_pair(x_free);
         }
         __syncwarp();
         FFN_TRACE(0, 2, g);
-        if (g >= 1) issue_g2(g - 1, c > 0 ? c - 1 : n_chunks - 1);
+        if (g >= 1) issue_g2(g - 1, prev_first, prev_last);
+        prev_first = (c == cb), prev_last = (c == ce - 1);
       }
     }
-    if (G > 0) issue_g2(G - 1, n_chunks - 1);
+    if (G > 0) issue_g2(G - 1, prev_first, prev_last);
     if (tr_on) {
       long long gt;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
@@ -937,7 +967,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1) k_f
     uint32_t ph_d1 = 0, ph_xfree = 0, ph_y = 0;
     uint8_t* xs = smem + FfnPairSmem::XS;
     const uint8_t* xs_row = xs + row * kXsRow;
-    auto tile_row0 = [&](int64_t it) -> int64_t { return ((pair + it * n_pairs) * 2 + rank) * 128; };
+    auto tile_row0 = [&](int64_t it) -> int64_t { return (tile_index(it) * 2 + rank) * 128; };
 
     uint32_t ph_xsfull = 0;
     auto x_to_tmem = [&](bool row_valid) {  // staged row -> bf16 hi/lo A-operand images in TMEM (rows beyond M are zeros)
@@ -973,15 +1003,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1) k_f
       tmem_ld32(tmem + lane_base + TM_Y + hf * 64 + 32, yb);
       tmem_ld_wait();
     };
-    auto init_y = [&](bool row_valid) {
+    auto init_y = [&](bool row_valid, bool with_residual) {  // with_residual false: a later part of a split tile starts from 0
 #pragma unroll 1
       for (int b = 0; b < 4; b++) {
         uint32_t r[16];
 #pragma unroll
         for (int j = 0; j < 4; j++) {
           float4 v = *reinterpret_cast<const float4*>(xs_row + hf * 256 + b * 64 + j * 16);
-          if (!row_valid) v = make_float4(0.f, 0.f, 0.f, 0.f);
-          const float4 bv = *reinterpret_cast<const float4*>(vecs + hf * 64 + b * 16 + 4 * j);
+          if (!row_valid || !with_residual) v = make_float4(0.f, 0.f, 0.f, 0.f);
+          float4 bv = *reinterpret_cast<const float4*>(vecs + hf * 64 + b * 16 + 4 * j);
+          if (!with_residual) bv = make_float4(0.f, 0.f, 0.f, 0.f);
           r[4 * j] = __float_as_uint(v.x + bv.x), r[4 * j + 1] = __float_as_uint(v.y + bv.y);
           r[4 * j + 2] = __float_as_uint(v.z + bv.z), r[4 * j + 3] = __float_as_uint(v.w + bv.w);
         }
@@ -1038,10 +1069,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1) k_f
     int64_t g = 0;
     for (int64_t it = 0; it < my_tiles; it++) {
       const bool has_next = it + 1 < my_tiles;
-      const bool row_valid = tile_row0(it) + row < a.M, next_valid = tile_row0(it + 1) + row < a.M;
-      for (int c = 0; c < n_chunks; c++, g++) {
+      const bool row_valid = tile_row0(it) + row < a.M, next_valid = has_next && tile_row0(it + 1) + row < a.M;
+      const int cb = c_begin(it), ce = c_end(it);
+      for (int c = cb; c < ce; c++, g++) {
         const int buf = (int)(g & 1);
-        if (hf == 1 && n_chunks > 1 && c == n_chunks - 1 && has_next) {
+        if (hf == 1 && ce - cb > 1 && c == ce - 1 && has_next) {
           // the last G1 of this tile and the release of the X images retire together: publish the next tile's images
           // FIRST, so that its first GEMM is queued behind G2 of the previous chunk without a bubble
           mbar_wait(x_free, ph_xfree);
@@ -1085,19 +1117,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1) k_f
         mbar_arrive_cluster(&h_full[buf * 2 + hf], 0);
         if (q == 0) { FFN_TRACE(1 + hf, 4, g); }
 
-        if (c == 0) {  // tile boundary: hand the accumulator back first, LayerNorm of the previous tile afterwards
+        if (c == cb) {  // tile boundary: hand the accumulator back first, LayerNorm of the previous tile afterwards
           uint32_t ya[32], yb[32];
           if (it > 0) drain_y(ya, yb);
           if (hf == 0) {  // group 1 has already waited for this tile's staged rows in x_to_tmem
             mbar_wait(xs_full, ph_xsfull);
             ph_xsfull ^= 1;
           }
-          init_y(row_valid);
+          init_y(row_valid, cb == 0);
           if (it > 0) layer_norm_half(tile_row0(it - 1), ya, yb);
           mbar_arrive(ln_staged);
         }
       }
-      if (n_chunks == 1 && hf == 1 && has_next) {  // single-chunk FFN: publish the next tile's images here
+      if (ce - cb == 1 && hf == 1 && has_next) {  // single-chunk iteration: publish the next tile's images here
         mbar_wait(x_free, ph_xfree);
         ph_xfree ^= 1;
         tc_fence_after();
@@ -1107,8 +1139,42 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1) k_f
     if (my_tiles > 0) {
       uint32_t ya[32], yb[32];
       drain_y(ya, yb);
-      mbar_wait(xs_full, ph_xsfull);  // the staging buffer is free (the previous tile's rows have been stored)
-      layer_norm_half(tile_row0(my_tiles - 1), ya, yb);
+      const int64_t row0t = tile_row0(my_tiles - 1);
+      bool normalise = true;
+      if (has_partial) {
+        // split tile: add this part's accumulator to the scratch tile; the last of the S pairs to arrive owns the result
+        float4* srow = reinterpret_cast<float4*>(a.tail[net] + ((size_t)(part_l * 2 + rank) * 128 + row) * 128 + hf * 64);
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          atomicAdd(srow + j, make_float4(__uint_as_float(ya[4 * j]), __uint_as_float(ya[4 * j + 1]), __uint_as_float(ya[4 * j + 2]), __uint_as_float(ya[4 * j + 3])));
+          atomicAdd(srow + 8 + j, make_float4(__uint_as_float(yb[4 * j]), __uint_as_float(yb[4 * j + 1]), __uint_as_float(yb[4 * j + 2]), __uint_as_float(yb[4 * j + 3])));
+        }
+        __threadfence();
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (warp == 2 && lane == 0) {
+          int* cnt = a.tail_cnt[net] + part_l * 2 + rank;
+          const int old = atomicAdd(cnt, 1);
+          if (old == S - 1) atomicExch(cnt, 0);  // self-cleaning: ready for the next layer
+          *tail_flag = (old == S - 1);
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        normalise = *reinterpret_cast<volatile int*>(tail_flag) != 0;
+        if (normalise) {
+          __threadfence();
+#pragma unroll
+          for (int j = 0; j < 8; j++) {
+            const float4 v0 = __ldcg(srow + j), v1 = __ldcg(srow + 8 + j);
+            ya[4 * j] = __float_as_uint(v0.x), ya[4 * j + 1] = __float_as_uint(v0.y), ya[4 * j + 2] = __float_as_uint(v0.z), ya[4 * j + 3] = __float_as_uint(v0.w);
+            yb[4 * j] = __float_as_uint(v1.x), yb[4 * j + 1] = __float_as_uint(v1.y), yb[4 * j + 2] = __float_as_uint(v1.z), yb[4 * j + 3] = __float_as_uint(v1.w);
+            __stcg(srow + j, make_float4(0.f, 0.f, 0.f, 0.f));
+            __stcg(srow + 8 + j, make_float4(0.f, 0.f, 0.f, 0.f));
+          }
+        }
+      }
+      if (normalise) {
+        mbar_wait(xs_full, ph_xsfull);  // the staging buffer is free (the previous tile's rows have been stored)
+        layer_norm_half(row0t, ya, yb);
+      }
       mbar_arrive(ln_staged);
     }
   }
@@ -2219,6 +2285,10 @@ __global__ void __launch_bounds__(kAttnThreads, 1) k_attn_fused(AttnArgs a) {
           tmem_ld32(base, r0);
           tmem_ld32(base + 32, r1);
           tmem_ld_wait();
+          if (!row_valid) {  // rows >= V hold scratch: feed zeros to MMA2 (the GPU is power-limited: idle multipliers are cheaper)
+#pragma unroll
+            for (int j = 0; j < 32; j++) r0[j] = 0u, r1[j] = 0u;
+          }
           uint32_t hi[16], lo[16];
 #pragma unroll
           for (int j = 0; j < 16; j++) split2(__uint_as_float(r0[2 * j]), __uint_as_float(r0[2 * j + 1]), hi[j], lo[j]);
@@ -2665,6 +2735,8 @@ void tc_carve(const tw_flow_config* c, int64_t n, int64_t n_cond, int64_t V, Are
   }
   ar.off = align_up(ar.off, 1024);
   out->scores_img = ar.take<uint8_t>((size_t)n_cond * c->num_heads * 2 * VP * VP * 2);
+  ar.off = align_up(ar.off, 1024);
+  out->ffn_tail = reinterpret_cast<float*>(ar.take<uint8_t>(kFfnTailBytes));
 }
 
 // scores -> operand images, once per pass
@@ -2680,6 +2752,7 @@ int tc_scores_images(const tw_flow_config* c, const float* scores, int64_t n_con
 
 int tc_begin_pass(const tw_flow_config* c, const ParamView&, TcScratch& tc, const float* scores, const uint8_t*, int64_t,
                   int64_t n_cond, int V, cudaStream_t st) {
+  if (tc.ffn_tail) TW_CUDA(cudaMemsetAsync(tc.ffn_tail, 0, kFfnTailBytes, st));
   if (!(tc_stage_mask() & TC_MIX)) return TW_OK;
   return tc_scores_images(c, scores, n_cond, V, tc.scores_img, 0, st);
 }
@@ -2827,6 +2900,18 @@ int tc_ffn_layer(const tw_flow_config* c, const ParamView& pv, int k, int t, con
   a.M = M;
   a.F = c->dim_feedforward;
   a.eps = c->layer_norm_eps;
+  static int use_split = -1;
+  if (use_split < 0) {
+    const char* e = getenv("TW_FFN_SPLIT");  // bring-up switch: 0 = leftover tiles run whole on a few pairs
+    use_split = e ? atoi(e) : 1;
+  }
+  if (tc.ffn_tail && use_split) {
+    int* cnt = reinterpret_cast<int*>(tc.ffn_tail + kFfnTailFloats);
+    for (int s = 0; s < 2; s++) {
+      a.tail[s] = tc.ffn_tail + (size_t)s * (kFfnTailFloats / 2);
+      a.tail_cnt[s] = cnt + s * kFfnTailTiles * 2;
+    }
+  }
   {
     static int dbg = -1;
     if (dbg < 0) {
