@@ -297,3 +297,34 @@ def test_mh_chains_graph_replay_matches_eager():
     torch.testing.assert_close(results[0][0], results[1][0], rtol=0, atol=0)
     torch.testing.assert_close(results[0][1], results[1][1], rtol=0, atol=0, equal_nan=True)
     assert torch.equal(results[0][2], results[1][2])
+
+
+@pytest.mark.parametrize("pep_fn,gb", [(alanine_dipeptide, "obc2"), (tetrapeptide_2olx, "obc2"), (tetrapeptide_2olx, "obc1")])
+def test_forces_match_finite_differences(pep_fn, gb):
+    """Analytic forces of the CUDA kernel == -dU/dx by central differences of the fp64 oracle (every term incl. the
+    chain rule through the OBC Born radii); autograd through the energy module returns the same gradient."""
+    pep = pep_fn()
+    sysd = amber_like_system(pep, gb=gb)
+    energy = PeptidePotentialEnergy(sysd)
+    x = _confs(pep, 2, 11, noise=0.01)
+    xt = torch.from_numpy(x).cuda()
+    e, f = energy.energy_and_forces(xt)
+    s32 = sysd.as_float32()
+    h = 1e-5
+    rng = np.random.default_rng(0)
+    picks = [(b, int(i), int(k)) for b in range(2) for i, k in zip(rng.integers(0, pep.num_atoms, 12), rng.integers(0, 3, 12))]
+    fmax = float(f.abs().max())
+    for b, i, k in picks:
+        xp, xm = x[b:b + 1].astype(np.float64).copy(), x[b:b + 1].astype(np.float64).copy()
+        xp[0, i, k] += h
+        xm[0, i, k] -= h
+        num = -(eo.potential_energy(s32, xp)[0] - eo.potential_energy(s32, xm)[0]) / (2 * h)
+        assert abs(float(f[b, i, k]) - num) < 2e-5 * fmax + 1e-2, (b, i, k, float(f[b, i, k]), num)
+    # autograd: d(sum w_b U_b)/dx = -w_b F_b
+    xg = xt.clone().requires_grad_(True)
+    w = torch.tensor([[0.5], [-2.0]], device="cuda")
+    (energy(xg) * w).sum().backward()
+    torch.testing.assert_close(xg.grad, -f * w[:, :, None], rtol=1e-6, atol=1e-6)
+    torch.testing.assert_close(energy(xt), e, rtol=0, atol=0)  # the no-grad path gives the same energies
+    # translation invariance: forces sum to zero
+    assert float(f.sum(1).abs().max()) < 1e-3 * fmax

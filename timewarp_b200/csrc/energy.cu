@@ -30,17 +30,35 @@ __device__ __forceinline__ double warp_sum_d(double v) {
 
 constexpr int ENERGY_THREADS = 128;
 
+__device__ __forceinline__ void add3(double* g, int i, const Vec3& v, double w) {  // g[i] += w * v  (shared-memory fp64 atomics)
+  atomicAdd(&g[3 * i], w * v.x);
+  atomicAdd(&g[3 * i + 1], w * v.y);
+  atomicAdd(&g[3 * i + 2], w * v.z);
+}
+
+// kForces: also accumulate the analytic gradient dE/dx of every term in shared memory (fp64) and write the forces
+// F = -dE/dx (what OpenMM returns and bgflow feeds back as the gradient, openmm_bridge.py:56-60).  The GB term needs the
+// chain rule through the Born radii: dE/dB_i is accumulated with the pair energies, then a second pair loop applies
+// dB_i/dr_ij (derivative of the OBC descreening integral).  Formulas checked against central differences of the fp64
+// oracle (tests/test_gpu_energy_mh.py::test_forces_match_finite_differences).
+template <bool kForces>
 __global__ void __launch_bounds__(ENERGY_THREADS) k_energy(tw_energy_system s, const float* __restrict__ coords,
-                                                           float* __restrict__ out_energy, float* __restrict__ out_terms) {
+                                                           float* __restrict__ out_energy, float* __restrict__ out_terms,
+                                                           float* __restrict__ out_forces) {
   extern __shared__ double sm[];
   const int N = s.n_atoms;
   Vec3* pos = reinterpret_cast<Vec3*>(sm);            // [N]
   double* born = sm + 3 * (size_t)N;                  // [N]
+  double* grad = born + N;                            // [3N]  dE/dx          (kForces)
+  double* dEdB = grad + 3 * (size_t)N;                // [N]   dE/dBorn_i     (kForces)
+  double* dBds = dEdB + N;                            // [N]   dBorn_i/ds_i * 0.5 * (r_i - offset)   (kForces)
   __shared__ double red[ENERGY_THREADS / 32][5];
   const int tid = threadIdx.x, nt = blockDim.x;
   const int64_t b = blockIdx.x;
   const float* cb = coords + b * (int64_t)N * 3;
   for (int i = tid; i < N; i += nt) pos[i] = {(double)cb[i * 3], (double)cb[i * 3 + 1], (double)cb[i * 3 + 2]};
+  if (kForces)
+    for (int i = tid; i < 5 * N; i += nt) grad[i] = 0.0;  // grad, dEdB, dBds are contiguous
   __syncthreads();
 
   double e_bond = 0, e_angle = 0, e_tors = 0, e_nb = 0, e_gb = 0;
@@ -50,15 +68,29 @@ __global__ void __launch_bounds__(ENERGY_THREADS) k_energy(tw_energy_system s, c
     Vec3 d = sub(pos[s.bond_idx[2 * i]], pos[s.bond_idx[2 * i + 1]]);
     double r = sqrt(dot(d, d)), dr = r - (double)s.bond_param[2 * i];
     e_bond += 0.5 * (double)s.bond_param[2 * i + 1] * dr * dr;
+    if (kForces) {
+      const double f = (double)s.bond_param[2 * i + 1] * dr / r;
+      add3(grad, s.bond_idx[2 * i], d, f);
+      add3(grad, s.bond_idx[2 * i + 1], d, -f);
+    }
   }
   // HarmonicAngleForce: 1/2 k (theta - theta0)^2
   for (int i = tid; i < s.n_angles; i += nt) {
     Vec3 pj = pos[s.angle_idx[3 * i + 1]];
     Vec3 a = sub(pos[s.angle_idx[3 * i]], pj), c = sub(pos[s.angle_idx[3 * i + 2]], pj);
-    double cs = dot(a, c) / sqrt(dot(a, a) * dot(c, c));
+    const double la2 = dot(a, a), lc2 = dot(c, c), inv = 1.0 / sqrt(la2 * lc2);
+    double cs = dot(a, c) * inv;
     cs = fmin(1.0, fmax(-1.0, cs));
     double dth = acos(cs) - (double)s.angle_param[2 * i];
     e_angle += 0.5 * (double)s.angle_param[2 * i + 1] * dth * dth;
+    if (kForces) {  // dE/dcos = -k (theta - theta0) / sin(theta)
+      const double de = -(double)s.angle_param[2 * i + 1] * dth / fmax(sqrt(1.0 - cs * cs), 1e-12);
+      const Vec3 ga = {de * (c.x * inv - cs * a.x / la2), de * (c.y * inv - cs * a.y / la2), de * (c.z * inv - cs * a.z / la2)};
+      const Vec3 gc = {de * (a.x * inv - cs * c.x / lc2), de * (a.y * inv - cs * c.y / lc2), de * (a.z * inv - cs * c.z / lc2)};
+      add3(grad, s.angle_idx[3 * i], ga, 1.0);
+      add3(grad, s.angle_idx[3 * i + 2], gc, 1.0);
+      add3(grad, s.angle_idx[3 * i + 1], {ga.x + gc.x, ga.y + gc.y, ga.z + gc.z}, -1.0);
+    }
   }
   // PeriodicTorsionForce: k (1 + cos(n phi - phase)); phi with the IUPAC sign (OpenMM Reference:
   // cross products of (p0-p1),(p2-p1),(p2-p3); sign from (p0-p1).cross2)
@@ -73,6 +105,22 @@ __global__ void __launch_bounds__(ENERGY_THREADS) k_energy(tw_energy_system s, c
     if (dot(d0, c2) < 0) phi = -phi;
     e_tors += (double)s.torsion_param[3 * i + 2] *
               (1.0 + cos((double)s.torsion_param[3 * i] * phi - (double)s.torsion_param[3 * i + 1]));
+    if (kForces) {  // dphi/dp (Blondel & Karplus) with F = d0, G = p1 - p2 = -d1, H = p3 - p2 = -d2, A = c1, B = c2
+      const double n = (double)s.torsion_param[3 * i];
+      const double dE = -(double)s.torsion_param[3 * i + 2] * n * sin(n * phi - (double)s.torsion_param[3 * i + 1]);
+      const double lG = sqrt(dot(d1, d1)), A2 = dot(c1, c1), B2 = dot(c2, c2);
+      const double fg = -dot(d0, d1), hg = dot(d2, d1);
+      const double wa0 = lG / A2, wb3 = -lG / B2;
+      const double wa1 = -lG / A2 - fg / (A2 * lG), wb1 = hg / (B2 * lG);
+      const Vec3 g0 = {wa0 * c1.x, wa0 * c1.y, wa0 * c1.z};
+      const Vec3 g3 = {wb3 * c2.x, wb3 * c2.y, wb3 * c2.z};
+      const Vec3 g1 = {wa1 * c1.x + wb1 * c2.x, wa1 * c1.y + wb1 * c2.y, wa1 * c1.z + wb1 * c2.z};
+      const Vec3 g2 = {-(g0.x + g1.x + g3.x), -(g0.y + g1.y + g3.y), -(g0.z + g1.z + g3.z)};
+      add3(grad, s.torsion_idx[4 * i], g0, dE);
+      add3(grad, s.torsion_idx[4 * i + 1], g1, dE);
+      add3(grad, s.torsion_idx[4 * i + 2], g2, dE);
+      add3(grad, s.torsion_idx[4 * i + 3], g3, dE);
+    }
   }
   // 1-4 exceptions: plain Coulomb + LJ with the exception parameters, no cutoff
   for (int i = tid; i < s.n_exceptions; i += nt) {
@@ -81,6 +129,11 @@ __global__ void __launch_bounds__(ENERGY_THREADS) k_energy(tw_energy_system s, c
     double sig = (double)s.exception_param[3 * i + 1], eps = (double)s.exception_param[3 * i + 2];
     double sr2 = sig * sig / r2, sr6 = sr2 * sr2 * sr2;
     e_nb += 4.0 * eps * (sr6 * sr6 - sr6) + s.one_4pi_eps0 * (double)s.exception_param[3 * i] * inv_r;
+    if (kForces) {  // (dE/dr) / r
+      const double f = ((-48.0 * eps * sr6 * sr6 + 24.0 * eps * sr6) - s.one_4pi_eps0 * (double)s.exception_param[3 * i] * inv_r) / r2;
+      add3(grad, s.exception_idx[2 * i], d, f);
+      add3(grad, s.exception_idx[2 * i + 1], d, -f);
+    }
   }
   // NonbondedForce, CutoffNonPeriodic: LJ (Lorentz-Berthelot) truncated at the cutoff + Coulomb
   // with reaction field  qq (1/r + k_rf r^2 - c_rf).
@@ -100,6 +153,11 @@ __global__ void __launch_bounds__(ENERGY_THREADS) k_energy(tw_energy_system s, c
       double sig = 0.5 * (si + (double)s.sigma[j]), eps = sqrt(ei * (double)s.epsilon[j]);
       double sr2 = sig * sig / r2, sr6 = sr2 * sr2 * sr2;
       e_nb += 4.0 * eps * (sr6 * sr6 - sr6) + s.one_4pi_eps0 * qi * (double)s.charge[j] * (1.0 / r + krf * r2 - crf);
+      if (kForces) {
+        const double f = (-48.0 * eps * sr6 * sr6 + 24.0 * eps * sr6) / r2 + s.one_4pi_eps0 * qi * (double)s.charge[j] * (-1.0 / (r2 * r) + 2.0 * krf);
+        add3(grad, i, d, f);
+        add3(grad, j, d, -f);
+      }
     }
   }
 
@@ -134,6 +192,8 @@ __global__ void __launch_bounds__(ENERGY_THREADS) k_energy(tw_energy_system s, c
         double s2 = sum * sum, s3 = sum * s2;
         double th = tanh(s.gb_alpha * sum - s.gb_beta * s2 + s.gb_gamma * s3);
         born[i] = 1.0 / (1.0 / ori - th / ri);
+        if (kForces)
+          dBds[i] = born[i] * born[i] * (1.0 - th * th) * (s.gb_alpha - 2.0 * s.gb_beta * sum + 3.0 * s.gb_gamma * s2) / ri * 0.5 * ori;
       }
     }
     __syncthreads();
@@ -143,7 +203,9 @@ __global__ void __launch_bounds__(ENERGY_THREADS) k_energy(tw_energy_system s, c
         if (born[i] > 0) {
           double ri = (double)s.gb_radius[i], rr = ri + 0.14, q = ri / born[i];
           double q2 = q * q;
-          e_gb += s.surface_area_energy * rr * rr * q2 * q2 * q2;
+          const double e_sa = s.surface_area_energy * rr * rr * q2 * q2 * q2;
+          e_gb += e_sa;
+          if (kForces) atomicAdd(&dEdB[i], -6.0 * e_sa / born[i]);
         }
       }
     }
@@ -159,14 +221,62 @@ __global__ void __launch_bounds__(ENERGY_THREADS) k_energy(tw_energy_system s, c
         double r2 = dot(d, d);
         if (use_cut && r2 > rc * rc) continue;
         double a2 = bi * born[j];
-        double den = sqrt(r2 + a2 * exp(-r2 / (4.0 * a2)));
+        const double ex = exp(-r2 / (4.0 * a2));
+        const double D = r2 + a2 * ex;
+        double den = sqrt(D);
         double g = qi * (double)s.charge[j] / den;
+        if (kForces) {  // E = c / sqrt(D):  dD/dr^2 = 1 - ex/4,  dD/d(B_i B_j) = ex (1 + r^2 / (4 B_i B_j))
+          const double cc = qi * (double)s.charge[j] * (j == i ? 0.5 : 1.0);
+          const double dEdD = -0.5 * cc / (D * den);
+          const double dDa2 = ex * (1.0 + r2 / (4.0 * a2));
+          if (j != i) {
+            const double f = dEdD * (1.0 - 0.25 * ex) * 2.0;
+            add3(grad, i, d, f);
+            add3(grad, j, d, -f);
+            atomicAdd(&dEdB[i], dEdD * dDa2 * born[j]);
+            atomicAdd(&dEdB[j], dEdD * dDa2 * bi);
+          } else {
+            atomicAdd(&dEdB[i], dEdD * dDa2 * 2.0 * bi);
+          }
+        }
         if (j != i) {
           if (use_cut) g -= qi * (double)s.charge[j] / rc;
         } else {
           g *= 0.5;
         }
         e_gb += g;
+      }
+    }
+    if (kForces) {
+      // ---- chain rule through the Born radii: s_i = 0.5 (r_i - offset) sum_j term(r_ij) ----
+      __syncthreads();
+      for (int i = warp; i < N; i += nwarps) {
+        const Vec3 pi = pos[i];
+        const double ori = (double)s.gb_radius[i] - s.gb_offset;
+        const double w = dEdB[i] * dBds[i];
+        for (int j = lane; j < N; j += 32) {
+          if (j == i) continue;
+          Vec3 d = sub(pi, pos[j]);
+          double r = sqrt(dot(d, d));
+          if (use_cut && r > rc) continue;
+          double srj = ((double)s.gb_radius[j] - s.gb_offset) * (double)s.gb_scale[j];
+          double rsr = r + srj;
+          if (ori < rsr) {
+            const double ad = fabs(r - srj);
+            double l, dl;
+            if (ori > ad) l = 1.0 / ori, dl = 0.0;
+            else l = 1.0 / ad, dl = -l * l * (r >= srj ? 1.0 : -1.0);
+            const double u = 1.0 / rsr, du = -u * u;
+            const double rinv = 1.0 / r, l2 = l * l, u2 = u * u;
+            double dterm = dl - du + 0.25 * (u2 - l2) + 0.5 * r * (u * du - l * dl) - 0.5 * rinv * rinv * log(u / l) +
+                           0.5 * rinv * (du / u - dl / l) - 0.25 * srj * srj * rinv * rinv * (l2 - u2) +
+                           0.5 * srj * srj * rinv * (l * dl - u * du);
+            if (ori < (srj - r)) dterm -= 2.0 * dl;
+            const double f = w * dterm * rinv;
+            add3(grad, i, d, f);
+            add3(grad, j, d, -f);
+          }
+        }
       }
     }
   }
@@ -188,6 +298,11 @@ __global__ void __launch_bounds__(ENERGY_THREADS) k_energy(tw_energy_system s, c
     }
     out_energy[b] = (float)tot;
   }
+  if (kForces) {
+    __syncthreads();  // (the reduction above already separated the last accumulation from here; kept for clarity)
+    float* fb = out_forces + b * (int64_t)N * 3;
+    for (int i = tid; i < 3 * N; i += nt) fb[i] = (float)(-grad[i]);
+  }
 }
 
 }  // namespace tw
@@ -207,17 +322,20 @@ extern "C" int tw_peptide_energy(const tw_energy_system* sys, const float* coord
   TW_CHECK_ARG(sys->n_exceptions == 0 || (sys->exception_idx && sys->exception_param), "exception arrays missing");
   TW_CHECK_ARG(sys->charge && sys->sigma && sys->epsilon && sys->excluded, "nonbonded arrays missing");
   TW_CHECK_ARG(!sys->use_gb || (sys->gb_radius && sys->gb_scale), "GB arrays missing");
-  if (out_forces) return fail(TW_ERR_UNSUPPORTED, "forces are not implemented yet (SURVEY.md section 8f-1)");
-  if (B == 0) return TW_OK;
-  size_t smem = (size_t)sys->n_atoms * 4 * sizeof(double);
+  TW_CHECK_ARG(!out_forces || sys->n_atoms <= 2048, "forces: n_atoms out of range (1..2048)");
+  size_t smem = (size_t)sys->n_atoms * (out_forces ? 9 : 4) * sizeof(double);
   static bool attr_set = false;
   if (smem > 48 * 1024 && !attr_set) {
-    TW_CUDA(cudaFuncSetAttribute(k_energy, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * 4 * (int)sizeof(double)));
+    TW_CUDA(cudaFuncSetAttribute(k_energy<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * 4 * (int)sizeof(double)));
+    TW_CUDA(cudaFuncSetAttribute(k_energy<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2048 * 9 * (int)sizeof(double)));
     attr_set = true;
   }
   {
     ProfScope prof(PROF_ENERGY, (cudaStream_t)stream);
-    k_energy<<<(unsigned)B, ENERGY_THREADS, smem, (cudaStream_t)stream>>>(*sys, coords, out_energy, out_terms);
+    if (out_forces)
+      k_energy<true><<<(unsigned)B, ENERGY_THREADS, smem, (cudaStream_t)stream>>>(*sys, coords, out_energy, out_terms, out_forces);
+    else
+      k_energy<false><<<(unsigned)B, ENERGY_THREADS, smem, (cudaStream_t)stream>>>(*sys, coords, out_energy, out_terms, nullptr);
   }
   TW_LAUNCH_CHECK();
   return TW_OK;

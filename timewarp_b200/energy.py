@@ -26,6 +26,24 @@ class _Integrator:
         return self._t
 
 
+class _EnergyFn(torch.autograd.Function):
+    """U(x) with the gradient bgflow attaches to the OpenMM energy (openmm_bridge.py:56-60): dU/dx = -force, forces from
+    the same kernel launch (analytic, fp64 accumulation)."""
+
+    @staticmethod
+    def forward(ctx, module, coords):
+        energy, forces = module._evaluate(coords, want_forces=True)
+        ctx.save_for_backward(forces)
+        ctx.in_shape, ctx.in_dtype = coords.shape, coords.dtype
+        return energy
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (forces,) = ctx.saved_tensors  # [B,N,3] float32
+        g = -forces * grad_out.reshape(-1, 1, 1).to(forces.dtype)
+        return None, g.reshape(ctx.in_shape).to(ctx.in_dtype)
+
+
 class PeptidePotentialEnergy(nn.Module):
     def __init__(self, system: SystemDescription, temperature: Optional[float] = None):
         super().__init__()
@@ -80,29 +98,44 @@ class PeptidePotentialEnergy(nn.Module):
         es.surface_area_energy = s.surface_area_energy
         self._dev_arrays, self._struct, self._struct_device = d, es, device
 
-    def forward(self, coords: Tensor, return_terms: bool = False) -> Tensor:
+    def _evaluate(self, coords: Tensor, want_forces: bool = False, want_terms: bool = False):
         assert coords.size(-1) == 3, f"last dimension is expected to be of size 3 but it is {coords.size(-1)}"
         assert (
             coords.size(-2) == self.num_particles
         ), f"size {coords.size()} does not align with expected number of particles {self.num_particles}"
         if coords.device.type != "cuda":
             raise _lib.TimewarpB200Error(f"coords are on {coords.device}: the energy kernel runs on CUDA only (no CPU fallback)")
-        if coords.requires_grad:
-            raise NotImplementedError("forces / backward through the energy are not implemented yet (SURVEY.md section 8f-1)")
         dev = coords.device
         if self._struct is None or self._struct_device != dev:
             self._build(dev)
-        x = coords.reshape(-1, self.num_particles, 3).to(torch.float32).contiguous()
+        x = coords.detach().reshape(-1, self.num_particles, 3).to(torch.float32).contiguous()
         B = x.shape[0]
         out = torch.empty(B, dtype=torch.float32, device=dev)
-        terms = torch.empty(B, 5, dtype=torch.float32, device=dev) if return_terms else None
+        forces = torch.empty(B, self.num_particles, 3, dtype=torch.float32, device=dev) if want_forces else None
+        terms = torch.empty(B, 5, dtype=torch.float32, device=dev) if want_terms else None
         _lib.check(
-            _lib.load().tw_peptide_energy(C.byref(self._struct), _lib.ptr(x), B, _lib.ptr(out), None, _lib.ptr(terms),
+            _lib.load().tw_peptide_energy(C.byref(self._struct), _lib.ptr(x), B, _lib.ptr(out), _lib.ptr(forces), _lib.ptr(terms),
                                           torch.cuda.current_stream(dev).cuda_stream),
             "tw_peptide_energy",
         )
         energy = out.to(coords.dtype).reshape(-1, 1)  # [B,1], input dtype/device (openmm_bridge.py:228)
-        return (energy, terms) if return_terms else energy
+        if want_terms:
+            return energy, forces, terms
+        return energy, forces
+
+    def forward(self, coords: Tensor, return_terms: bool = False) -> Tensor:
+        """U(coords[..., N, 3]) -> [B, 1] kJ/mol.  Differentiable w.r.t. coords (gradient = -force) like the reference's
+        bgflow-bridged energy; without grad the force computation is skipped."""
+        if return_terms:
+            energy, _, terms = self._evaluate(coords, want_terms=True)
+            return energy, terms
+        if coords.requires_grad and torch.is_grad_enabled():
+            return _EnergyFn.apply(self, coords)
+        return self._evaluate(coords)[0]
+
+    def energy_and_forces(self, coords: Tensor):
+        """(U [B,1] kJ/mol, F [B,N,3] kJ/mol/nm = -dU/dx) from one kernel launch (OpenMMBridge.evaluate, openmm_bridge.py:170-249)."""
+        return self._evaluate(coords, want_forces=True)
 
 
 class OpenmmPotentialEnergyTorch(PeptidePotentialEnergy):
