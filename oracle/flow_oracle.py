@@ -37,6 +37,8 @@ class OracleConfig:
     lengthscales: List[float] = field(default_factory=lambda: [0.1, 0.2, 0.5, 0.7, 1.0, 1.2])
     position_layer_index_mod_2: int = 0
     layer_norm_eps: float = 1e-5
+    # "kernel" | "learnable_kernel" (LearnableLengthscaleKernelAttention, kernel_attention.py:217-253)
+    attention_type: str = "kernel"
 
 
 StateDict = Dict[str, Tensor]
@@ -149,8 +151,16 @@ def sequential_flow(
     trace: Optional[list] = None,
 ) -> Tuple[Tensor, Tensor, Tensor]:
     # The reference evaluates the scores once per pass through its Cache
-    # (model_constructor.py:189-196; kernel_attention.py:197-206): lengthscales of layer 0.
-    ls = sd["flow.chain.0.scale_transformer.encoder_layers.0.self_attn.attention.lengthscales"].to(x_coords.dtype)
+    # (model_constructor.py:189-196; kernel_attention.py:197-206): the cache key maps `lengthscales` to 0, so the scores
+    # of the FIRST attention layer executed in the pass are reused by every layer.  For `kernel` all layers hold the same
+    # buffer; for `learnable_kernel` (lengthscales = exp(log_lengthscales), a Parameter per layer) that is the scale
+    # network's first encoder layer of coupling layer 0 in the density direction and of the LAST coupling layer when sampling.
+    first = cfg.num_coupling_layers - 1 if reverse else 0
+    att = f"flow.chain.{first}.scale_transformer.encoder_layers.0.self_attn.attention"
+    if cfg.attention_type == "learnable_kernel":
+        ls = torch.exp(sd[f"{att}.log_lengthscales"]).to(x_coords.dtype)
+    else:
+        ls = sd[f"{att}.lengthscales"].to(x_coords.dtype)
     scores = kernel_attention_scores(x_coords, masked_elements, ls, distance_mode)
     idxs = range(cfg.num_coupling_layers)
     idxs = idxs[::-1] if reverse else idxs
@@ -314,6 +324,8 @@ def state_dict_shapes(cfg: OracleConfig) -> Dict[str, Tuple[int, ...]]:
                 q = f"{p}.encoder_layers.{t}"
                 out[f"{q}.self_attn.values_proj.weight"] = (H * D, D)
                 out[f"{q}.self_attn.attention.lengthscales"] = (H,)
+                if cfg.attention_type == "learnable_kernel":
+                    out[f"{q}.self_attn.attention.log_lengthscales"] = (H,)
                 out[f"{q}.self_attn.attention._out_projection.weight"] = (D, H * D)
                 out[f"{q}.linear1.weight"] = (F, D)
                 out[f"{q}.linear1.bias"] = (F,)
@@ -337,7 +349,9 @@ def synth_state_dict(cfg: OracleConfig, seed: int = 0, dtype=torch.float32) -> S
     sd: StateDict = {}
     for key, shape in state_dict_shapes(cfg).items():
         g = torch.Generator().manual_seed((zlib.crc32(key.encode()) + 7919 * seed) % (2**31))
-        if key.endswith("lengthscales"):
+        if key.endswith("log_lengthscales"):  # a different value in every layer (the reference uses only the first executed one)
+            t = torch.log(torch.tensor(cfg.lengthscales, dtype=torch.float32)) + 0.3 * (torch.rand(shape, generator=g) * 2 - 1)
+        elif key.endswith("lengthscales"):
             t = torch.tensor(cfg.lengthscales, dtype=torch.float32)
         elif key.endswith("prior_log_scale"):
             t = 0.2 * (torch.rand((), generator=g) - 0.5)
@@ -374,7 +388,7 @@ def nll_loss_and_grads(sd: StateDict, cfg: OracleConfig, atom_types, x_coords, x
     """Loss of density_model_base.py:27-42 and its torch-autograd gradient w.r.t. every floating-point
     entry of the state dict that the reference registers as a Parameter (the `lengthscales` entries are
     buffers, kernel_attention.py:169-171) -- what `loss.backward()` leaves in `.grad` in train.py."""
-    leaves = {k: v.detach().clone().requires_grad_(not k.endswith("lengthscales")) for k, v in sd.items()}
+    leaves = {k: v.detach().clone().requires_grad_(not k.endswith(".lengthscales")) for k, v in sd.items()}
     loss = nll_loss(leaves, cfg, atom_types, x_coords, x_velocs, y_coords, y_velocs, masked_elements, distance_mode)
     names = [k for k, v in leaves.items() if v.requires_grad]
     grads = torch.autograd.grad(loss, [leaves[k] for k in names], allow_unused=True)

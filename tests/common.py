@@ -12,6 +12,10 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 TINY_O = fo.OracleConfig(atom_embedding_dim=8, latent_mlp_hidden_dims=[24], num_coupling_layers=4,
                          num_transformer_layers=2, d_model=16, dim_feedforward=32, lengthscales=[0.3, 1.0])
 FULL_O = fo.OracleConfig()
+# `learnable_kernel` attention (per-layer log_lengthscales)
+TINY_L = fo.OracleConfig(atom_embedding_dim=8, latent_mlp_hidden_dims=[24], num_coupling_layers=4, num_transformer_layers=2,
+                         d_model=16, dim_feedforward=32, lengthscales=[0.3, 1.0], attention_type="learnable_kernel")
+FULL_L = fo.OracleConfig(attention_type="learnable_kernel")
 
 
 def model_config(o: fo.OracleConfig, precision: str):
@@ -22,7 +26,7 @@ def model_config(o: fo.OracleConfig, precision: str):
         num_transformer_layers=o.num_transformer_layers,
         encoder_layer_config=tw.CustomAttentionEncoderLayerConfig(
             d_model=o.d_model, dim_feedforward=o.dim_feedforward, dropout=0.0, num_heads=len(o.lengthscales),
-            attention_type="kernel", lengthscales=list(o.lengthscales), normalise_kernel_values=True),
+            attention_type=getattr(o, "attention_type", "kernel"), lengthscales=list(o.lengthscales), normalise_kernel_values=True),
         position_layer_index_mod_2=o.position_layer_index_mod_2,
         precision=precision,
     )

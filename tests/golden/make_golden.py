@@ -52,7 +52,7 @@ def ref_model(cfg: OracleConfig, seed: int):
         dim_feedforward=cfg.dim_feedforward,
         dropout=0.0,
         num_heads=len(cfg.lengthscales),
-        attention_type="kernel",
+        attention_type=cfg.attention_type,
         lengthscales=list(cfg.lengthscales),
         normalise_kernel_values=True,
     )
@@ -112,6 +112,8 @@ def run_case(name, cfg, peptide, B, seed, lengths=None, sample_S=3, wseed=0, tra
         # attention scores straight from the reference function
         com = (x * (~mask)[:, :, None]).sum(1, keepdim=True) / (~mask).sum(1)[:, None, None]
         ls = torch.tensor(cfg.lengthscales, dtype=torch.float32)
+        if cfg.attention_type == "learnable_kernel":  # density direction: the first attention layer executed (cache quirk)
+            ls = torch.exp(sd["flow.chain.0.scale_transformer.encoder_layers.0.self_attn.attention.log_lengthscales"])
         out["scores"] = compute_kernel_attention_scores(query=x - com, key=x - com, masked_elements=mask, lengthscales=ls).numpy()
 
         # sampling, S=1 over the whole batch (exploration.py shape) -- same RNG consumption as the reference
@@ -231,8 +233,24 @@ def init_case():
     print("init case:", len(sd), "tensors")
 
 
+FULL_LEARNABLE = OracleConfig(attention_type="learnable_kernel")
+TINY_LEARNABLE = OracleConfig(atom_embedding_dim=8, latent_mlp_hidden_dims=[24], num_coupling_layers=4, num_transformer_layers=2,
+                              d_model=16, dim_feedforward=32, lengthscales=[0.3, 1.0], attention_type="learnable_kernel")
+
+
+def learnable_cases():
+    """`learnable_kernel` attention: per-layer log_lengthscales, of which the reference uses only
+    the first executed layer's (cache key quirk) -- layer 0 for log_likelihood, the last coupling layer when sampling."""
+    ad = alanine_dipeptide()
+    run_case("tiny_ad_learnable", TINY_LEARNABLE, ad, B=3, seed=21, lengths=[22, 15, 9], sample_S=3, trace_layer0=False)
+    run_case("full_ad22_learnable", FULL_LEARNABLE, ad, B=3, seed=22, sample_S=2, trace_layer0=False)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
+    if len(sys.argv) > 1 and sys.argv[1] == "learnable":
+        learnable_cases()
+        sys.exit(0)
     init_case()
     ad, olx = alanine_dipeptide(), tetrapeptide_2olx()
     run_case("tiny_ad_ragged", TINY, ad, B=3, seed=11, lengths=[22, 15, 9], sample_S=4)
@@ -243,3 +261,4 @@ if __name__ == "__main__":
     chirality_case()
     grad_case("grads_full_ad22", FULL, ad, B=4, seed=3)
     grad_case("grads_full_ad22_ragged", FULL, ad, B=3, seed=4, lengths=[22, 17, 12])
+    learnable_cases()

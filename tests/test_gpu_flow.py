@@ -6,13 +6,15 @@ import pytest
 import torch
 
 from oracle import flow_oracle as fo
-from tests.common import EMPTY_ADJ, EMPTY_EBI, FULL_O, TINY_O, build_model, load_golden
+from tests.common import EMPTY_ADJ, EMPTY_EBI, FULL_L, FULL_O, TINY_L, TINY_O, build_model, load_golden
 
 pytestmark = pytest.mark.gpu
 REL = 1e-4  # north_star tolerance
 
 CASES = [("tiny_ad_ragged", TINY_O, "fp32"), ("tiny_ad", TINY_O, "fp32"), ("full_ad22", FULL_O, "fp32"),
          ("full_ad22_ragged", FULL_O, "fp32"), ("full_2olx65", FULL_O, "fp32")]
+# learnable_kernel attention: the golden files carry no layer-0 trace; the lengthscales differ per layer and direction
+LEARNABLE = [("tiny_ad_learnable", TINY_L, "fp32"), ("full_ad22_learnable", FULL_L, "fp32"), ("full_ad22_learnable", FULL_L, "bf16x3")]
 
 
 def _kw(g, dev="cuda", rows=slice(None)):
@@ -29,7 +31,8 @@ def assert_rel(actual, expected, rel=REL, what=""):
     return float(err)
 
 
-@pytest.mark.parametrize("name,cfg,prec", CASES)
+@pytest.mark.parametrize("name,cfg,prec", CASES + LEARNABLE)
+@torch.no_grad()
 def test_golden_log_likelihood_and_loss(name, cfg, prec):
     g = load_golden(name)
     m, _ = build_model(cfg, prec, int(g["weight_seed"]))
@@ -62,7 +65,8 @@ def test_golden_scores_and_layer0(name, cfg, prec):
     assert_rel(shift.cpu()[keep], g["layer0_shift"][keep], what="layer0 shift")
 
 
-@pytest.mark.parametrize("name,cfg,prec", CASES)
+@pytest.mark.parametrize("name,cfg,prec", CASES + LEARNABLE)
+@torch.no_grad()
 def test_golden_sampling(name, cfg, prec):
     g = load_golden(name)
     m, _ = build_model(cfg, prec, int(g["weight_seed"]))
@@ -181,3 +185,18 @@ def test_state_dict_roundtrip_changes_output():
     assert not torch.allclose(a, b)
     m.load_state_dict(fo.synth_state_dict(TINY_O, 0))
     assert torch.equal(m.log_likelihood(**kw), a)
+
+
+def test_learnable_kernel_module_surface():
+    """State-dict keys of the reference's LearnableLengthscaleKernelAttention, scores from layer 0's exp(log_lengthscales),
+    and the training path refusing to drop the log_lengthscales gradient silently."""
+    g = load_golden("tiny_ad_learnable")
+    m, sd = build_model(TINY_L, "fp32", int(g["weight_seed"]))
+    assert set(m.state_dict().keys()) == set(sd.keys())
+    assert "flow.chain.1.shift_transformer.encoder_layers.1.self_attn.attention.log_lengthscales" in dict(m.named_parameters())
+    mask = g["masked_elements"]
+    xc = g["x_coords"] - fo.centre_of_mass(g["x_coords"], mask)
+    assert (m.attention_scores(xc.cuda(), mask.cuda()).cpu() - g["scores"]).abs().max() < 2e-3
+    m.train()
+    with pytest.raises(NotImplementedError):
+        m(y_coords=g["y_coords"].cuda(), y_velocs=g["y_velocs"].cuda(), **_kw(g))

@@ -12,6 +12,11 @@ TINY = fo.OracleConfig(atom_embedding_dim=8, latent_mlp_hidden_dims=[24], num_co
                        num_transformer_layers=2, d_model=16, dim_feedforward=32, lengthscales=[0.3, 1.0])
 FULL = fo.OracleConfig()
 CASES = [("tiny_ad_ragged", TINY), ("tiny_ad", TINY), ("full_ad22", FULL), ("full_ad22_ragged", FULL), ("full_2olx65", FULL)]
+# `learnable_kernel` attention: per-layer log_lengthscales, only the first executed layer's are used (cache-key quirk)
+TINY_L = fo.OracleConfig(atom_embedding_dim=8, latent_mlp_hidden_dims=[24], num_coupling_layers=4, num_transformer_layers=2,
+                         d_model=16, dim_feedforward=32, lengthscales=[0.3, 1.0], attention_type="learnable_kernel")
+FULL_L = fo.OracleConfig(attention_type="learnable_kernel")
+LEARNABLE = [("tiny_ad_learnable", TINY_L), ("full_ad22_learnable", FULL_L)]
 
 
 def load(golden_dir, name):
@@ -19,7 +24,7 @@ def load(golden_dir, name):
     return {k: torch.from_numpy(d[k]) for k in d.files}
 
 
-@pytest.mark.parametrize("name,cfg", CASES)
+@pytest.mark.parametrize("name,cfg", CASES + LEARNABLE)
 def test_log_likelihood_and_loss(golden_dir, name, cfg):
     g = load(golden_dir, name)
     sd = fo.synth_state_dict(cfg, int(g["weight_seed"]))
@@ -55,7 +60,7 @@ def test_scores_and_layer0(golden_dir, name, cfg):
     torch.testing.assert_close(shift, g["layer0_shift"], rtol=1e-5, atol=1e-6)
 
 
-@pytest.mark.parametrize("name,cfg", CASES)
+@pytest.mark.parametrize("name,cfg", CASES + LEARNABLE)
 def test_sampling(golden_dir, name, cfg):
     g = load(golden_dir, name)
     sd = fo.synth_state_dict(cfg, int(g["weight_seed"]))
@@ -94,3 +99,16 @@ def test_sample_then_density_roundtrip(golden_dir):
     yc, yv, lp = fo.conditional_sample_with_logp(sd, FULL, at, x, xv, mask, 1, g["s1_z_coords"], g["s1_z_velocs"])
     ll = fo.log_likelihood(sd, FULL, at, x, xv, yc[0], yv[0], mask)
     torch.testing.assert_close(ll, lp[0], rtol=1e-5, atol=2e-3)
+
+
+@pytest.mark.parametrize("name,cfg", LEARNABLE)
+def test_learnable_scores_use_first_executed_layer(golden_dir, name, cfg):
+    g = load(golden_dir, name)
+    sd = fo.synth_state_dict(cfg, int(g["weight_seed"]))
+    mask = g["masked_elements"]
+    xc = g["x_coords"] - fo.centre_of_mass(g["x_coords"], mask)
+    ls0 = torch.exp(sd["flow.chain.0.scale_transformer.encoder_layers.0.self_attn.attention.log_lengthscales"])
+    torch.testing.assert_close(fo.kernel_attention_scores(xc, mask, ls0), g["scores"], rtol=1e-6, atol=1e-7)
+    # the layers really differ (otherwise the quirk would be untested)
+    ls_last = torch.exp(sd[f"flow.chain.{cfg.num_coupling_layers - 1}.scale_transformer.encoder_layers.0.self_attn.attention.log_lengthscales"])
+    assert (ls0 - ls_last).abs().max() > 1e-2

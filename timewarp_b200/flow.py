@@ -126,6 +126,11 @@ class ConditionalFlowDensityModel(nn.Module):
         self.ignore_conditional_velocity = ignore_conditional_velocity
         self.use_displacement_as_target = use_displacement_as_target
         self._cfg = flow_config
+        # `learnable_kernel` attention: exp(log_lengthscales) of the first attention layer executed in the pass, written
+        # here before every pass; every lengthscale entry of the parameter table points at this buffer (the reference's
+        # cache key maps `lengthscales` to 0, so one layer's scores serve the whole pass -- SURVEY.md quirk B)
+        self._learnable = hasattr(flow.chain[0].scale_transformer.encoder_layers[0].self_attn.attention, "log_lengthscales")
+        self._ls_eff: Optional[Tensor] = None
         self._table = None  # (ctypes array, keep-alive list)
         self._workspace: Optional[Tensor] = None
         self._packed = None  # (buffer, aligned ptr, key): bf16 operand images of the weights (tensor-core precisions)
@@ -142,6 +147,7 @@ class ConditionalFlowDensityModel(nn.Module):
 
     def _apply(self, fn, *a, **kw):  # .to()/.cuda()/.float() move the parameters: rebuild the pointer table
         self._table = None
+        self._ls_eff = None
         self._workspace = None
         self._packed = None
         return super()._apply(fn, *a, **kw)
@@ -153,13 +159,17 @@ class ConditionalFlowDensityModel(nn.Module):
     def _ordered_params(self):
         """Tensors in the order of the C-ABI parameter table (include/timewarp_b200.h)."""
         out = [self.flow.atom_embedder.weight, self.coords_prior_log_scale, self.velocs_prior_log_scale]
+        if self._learnable:
+            first = self.flow.chain[0].scale_transformer.encoder_layers[0].self_attn.attention.log_lengthscales
+            if self._ls_eff is None or self._ls_eff.device != first.device:
+                self._ls_eff = torch.exp(first.detach()).contiguous()
         for layer in self.flow.chain:
             for block in (layer.scale_transformer, layer.shift_transformer):
                 for lin in block.in_mlp.linears():
                     out += [lin.weight, lin.bias]
                 for enc in block.encoder_layers:
                     out += [
-                        enc.self_attn.values_proj.weight, enc.self_attn.attention.lengthscales,
+                        enc.self_attn.values_proj.weight, self._ls_eff if self._learnable else enc.self_attn.attention.lengthscales,
                         enc.self_attn.attention._out_projection.weight, enc.linear1.weight, enc.linear1.bias,
                         enc.linear2.weight, enc.linear2.bias, enc.norm1.weight, enc.norm1.bias, enc.norm2.weight,
                         enc.norm2.bias,
@@ -192,7 +202,7 @@ class ConditionalFlowDensityModel(nn.Module):
         if self._cfg.precision == _lib.PRECISION["fp32"]:
             return None
         table = self._param_table(device)
-        key = (self._cfg.precision, tuple(t._version for t in self._table[1]))
+        key = (self._cfg.precision, tuple(t._version for t in self._table[1] if t is not self._ls_eff))
         if self._packed is None or self._packed[2] != key or self._packed[0].device != device:
             lib = _lib.load()
             need = C.c_size_t(0)
@@ -219,6 +229,14 @@ class ConditionalFlowDensityModel(nn.Module):
             return False
         a, b = C.c_size_t(0), C.c_size_t(0)
         return _lib.load().tw_flow_train_bytes(C.byref(self._cfg), B, V, C.byref(a), C.byref(b)) == _lib.TW_OK
+
+    def _set_pass_lengthscales(self, reverse: bool) -> None:
+        """learnable_kernel: lengthscales of the first attention layer the reference executes in this direction."""
+        if not self._learnable:
+            return
+        layer = self.flow.chain[len(self.flow.chain) - 1 if reverse else 0]
+        log_ls = layer.scale_transformer.encoder_layers[0].self_attn.attention.log_lengthscales
+        self._ls_eff.copy_(torch.exp(log_ls.detach()))
 
     @staticmethod
     def _stream(device) -> int:
@@ -283,7 +301,14 @@ class ConditionalFlowDensityModel(nn.Module):
             x_velocs = torch.zeros_like(x_velocs)
         lib = _lib.load()
         mask_u8 = mask.view(torch.uint8)
+        self._param_table(dev)
+        self._set_pass_lengthscales(reverse=False)
         trainable = torch.is_grad_enabled() and not want_latent and any(p.requires_grad for p in self.parameters())
+        if trainable and self._learnable and any(p.requires_grad for n, p in self.named_parameters() if n.endswith("log_lengthscales")):
+            if self.training:
+                raise NotImplementedError("training `learnable_kernel` attention needs the gradient w.r.t. log_lengthscales (not built); "
+                                          "freeze them with requires_grad_(False) or evaluate under torch.no_grad()")
+            trainable = False
         if trainable and (self.training or self._train_supported(B, V)):
             # hand-written backward (tensor-core precisions, flagship layer sizes).  Configurations without backward
             # kernels raise TW_ERR_UNSUPPORTED in .train() mode; in .eval() mode they take the inference path and the
@@ -354,6 +379,7 @@ class ConditionalFlowDensityModel(nn.Module):
                 raise ValueError("latents must be [S, B, V, 3]")
         lib = _lib.load()
         table = self._param_table(dev)
+        self._set_pass_lengthscales(reverse=True)
         ws, ws_bytes = self._get_workspace(S * B, B, V, dev)
         y_coords = torch.empty(S, B, V, 3, dtype=torch.float32, device=dev)
         y_velocs = torch.empty(S, B, V, 3, dtype=torch.float32, device=dev)
@@ -374,7 +400,8 @@ class ConditionalFlowDensityModel(nn.Module):
         """compute_kernel_attention_scores (kernel_attention.py:69-121) -> [B,H,V,V]."""
         x = _require_cuda("x_coords", x_coords_centred, torch.float32)
         mask = _require_cuda("masked_elements", masked_elements, torch.bool).view(torch.uint8)
-        ls = self.flow.chain[0].scale_transformer.encoder_layers[0].self_attn.attention.lengthscales
+        att = self.flow.chain[0].scale_transformer.encoder_layers[0].self_attn.attention
+        ls = torch.exp(att.log_lengthscales.detach()).contiguous() if self._learnable else att.lengthscales
         B, V = x.shape[:2]
         out = torch.empty(B, ls.numel(), V, V, dtype=torch.float32, device=x.device)
         _lib.check(
@@ -392,6 +419,8 @@ class ConditionalFlowDensityModel(nn.Module):
         at = _require_cuda("atom_types", atom_types, torch.int64)
         mask = _require_cuda("masked_elements", masked_elements, torch.bool).view(torch.uint8)
         ws, ws_bytes = self._get_workspace(B, B, V, dev)
+        self._param_table(dev)
+        self._set_pass_lengthscales(reverse=False)
         scale, shift = torch.empty_like(x), torch.empty_like(x)
         _lib.check(
             _lib.load().tw_flow_scale_shift(

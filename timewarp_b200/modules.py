@@ -53,6 +53,18 @@ class KernelAttention(_Container):
         self._out_projection = nn.Linear(value_dim * len(lengthscales), output_dim, bias=False)
 
 
+class LearnableLengthscaleKernelAttention(KernelAttention):
+    """modules/layers/kernel_attention.py:217-253: lengthscales = exp(log_lengthscales), a Parameter per layer.  Same
+    construction order as the reference (buffer + projection in the base class, the Parameter, a SECOND projection that
+    replaces the first) so that seeded initialisation consumes the RNG identically."""
+
+    def __init__(self, *, value_dim: int, output_dim: int, lengthscales: Sequence[float], normalise_kernel_values: bool):
+        super().__init__(value_dim=value_dim, output_dim=output_dim, lengthscales=lengthscales,
+                         normalise_kernel_values=normalise_kernel_values)
+        self.log_lengthscales = nn.Parameter(torch.log(torch.tensor(lengthscales, dtype=torch.float32)), requires_grad=True)
+        self._out_projection = nn.Linear(value_dim * len(lengthscales), output_dim, bias=False)
+
+
 class KernelSelfAttention(_Container):
     """modules/layers/kernel_self_attention.py:12-48."""
 
@@ -77,10 +89,11 @@ class CustomTransformerEncoderLayer(_Container):
 
 
 def custom_attention_transformer_encoder_constructor(config) -> CustomTransformerEncoderLayer:
-    """modules/layers/custom_attention_encoder.py:140-219, `kernel` attention only."""
-    if config.attention_type != "kernel":
+    """modules/layers/custom_attention_encoder.py:140-219: `kernel` and `learnable_kernel` attention."""
+    if config.attention_type not in ("kernel", "learnable_kernel"):
         raise NotImplementedError(
-            f"attention_type={config.attention_type!r}: only 'kernel' is built (the variants are SURVEY.md section 8f-3)"
+            f"attention_type={config.attention_type!r}: 'kernel' and 'learnable_kernel' are built ('chebyshev_kernel' and "
+            "'local' are SURVEY.md section 8f-3)"
         )
     if float(config.dropout) != 0.0:
         raise NotImplementedError("dropout must be 0 (configs/kernel_transformer_nvp.yaml:27); no dropout kernel exists")
@@ -88,7 +101,8 @@ def custom_attention_transformer_encoder_constructor(config) -> CustomTransforme
     assert len(config.lengthscales) > 0
     assert config.normalise_kernel_values is not None
     # construction order == reference (attention first) so that seeded init is identical
-    attention = KernelAttention(
+    attention_cls = {"kernel": KernelAttention, "learnable_kernel": LearnableLengthscaleKernelAttention}[config.attention_type]
+    attention = attention_cls(
         value_dim=config.d_model,
         output_dim=config.d_model,
         lengthscales=list(config.lengthscales),
