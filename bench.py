@@ -177,7 +177,7 @@ def run_reference(args):
 
 
 # --------------------------------------------------------------------------------------------
-def time_nll_training(dev, precision, batch=256, steps=5, warmup=3):
+def time_nll_training(dev, precision, batch=256, steps=5, warmup=3, use_graph=True):
     """BASELINE.json configs[1]: alanine-dipeptide (22 atoms) NLL training, batch 256 on one GPU: forward (taped) +
     hand-written backward + Adam step.  Returns atoms/s (B * V / step time, CUDA events)."""
     import timewarp_b200 as tw
@@ -189,7 +189,7 @@ def time_nll_training(dev, precision, batch=256, steps=5, warmup=3):
     model = tw.custom_transformer_nvp_constructor(tw.kernel_transformer_nvp_config(precision))
     model.load_state_dict(fo.synth_state_dict(fo.OracleConfig(), 0))
     model = model.to(dev).train()
-    opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4, capturable=True, fused=True)
     g = torch.Generator().manual_seed(0)
     x = torch.tensor(pep.coords_nm, dtype=torch.float32)[None] + 0.01 * torch.randn(batch, V, 3, generator=g)
     y = x + 0.02 * torch.randn(batch, V, 3, generator=g)
@@ -199,7 +199,7 @@ def time_nll_training(dev, precision, batch=256, steps=5, warmup=3):
               masked_elements=torch.zeros(batch, V, dtype=torch.bool, device=dev))
 
     def step():
-        opt.zero_grad(set_to_none=False)
+        opt.zero_grad(set_to_none=True)  # the backward hands out views of one flat, freshly zeroed gradient buffer
         loss = model(**kw)
         loss.backward()
         opt.step()
@@ -207,16 +207,44 @@ def time_nll_training(dev, precision, batch=256, steps=5, warmup=3):
 
     for _ in range(warmup):
         step()
+    torch.cuda.synchronize()
+    # The step is launch-bound at this size (5632 tokens, ~1500 kernel launches): replay it as ONE CUDA graph
+    # (forward with tape + hand-written backward + capturable Adam).  Falls back to eager launches if capture fails.
+    launch = "eager"
+    graph_step = None
+    if use_graph:
+        try:
+            static_loss = None
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    step()
+            torch.cuda.current_stream().wait_stream(side)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                static_loss = step()
+            graph_step = lambda: (g.replay(), static_loss)[1]  # noqa: E731
+            for _ in range(2):
+                graph_step()
+            torch.cuda.synchronize()
+            launch = "one CUDA graph per training step"
+        except Exception as e:  # pragma: no cover
+            graph_step = None
+            launch = f"eager (graph capture failed: {str(e)[:80]})"
+            torch.cuda.synchronize()
+    run = graph_step or step
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     e0.record()
     for _ in range(steps):
-        loss = step()
+        loss = run()
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
     return {"metric": "nll_train_atoms_per_sec", "value": batch * V / (ms / 1e3), "unit": "atoms/s", "ms_per_step": ms,
-            "config": {"workload": f"nll_train_ad22_batch{batch}", "atoms": V, "batch": batch, "optimizer": "Adam", "precision": precision},
+            "config": {"workload": f"nll_train_ad22_batch{batch}", "atoms": V, "batch": batch, "optimizer": "Adam", "precision": precision,
+                       "launch": launch},
             "final_loss": float(loss)}
 
 

@@ -174,3 +174,32 @@ def test_fp32_precision_has_no_training_path():
         m(**kw)
     m.eval()  # evaluation mode: the result is computed, but carries no graph
     assert not m.log_likelihood(**kw).requires_grad
+
+
+def test_fused_optimizer_updates_reach_the_packed_weights():
+    """torch.optim.Adam(fused=True) updates the parameters without bumping their version counters: the taped forward must
+    re-pack the bf16 weight images anyway (regression: the big GEMM weights stayed stale and only biases / LayerNorm trained)."""
+    g = _load("grads_full_ad22")
+    kw = dict(atom_types=g["atom_types"].cuda(), x_coords=g["x_coords"].cuda(), x_velocs=g["x_velocs"].cuda(), y_coords=g["y_coords"].cuda(),
+              y_velocs=g["y_velocs"].cuda(), adj_list=EMPTY_ADJ.cuda(), edge_batch_idx=EMPTY_EBI.cuda(), masked_elements=g["masked_elements"].cuda())
+    traj = {}
+    for name, okw in (("foreach", dict()), ("fused", dict(fused=True))):
+        m, _ = build_model(FULL_O, "bf16x3", 0)
+        m.train()
+        opt = torch.optim.Adam(m.parameters(), lr=1e-4, **okw)
+        losses = []
+        for _ in range(4):
+            opt.zero_grad(set_to_none=True)
+            loss = m(**kw)
+            loss.backward()
+            opt.step()
+            losses.append(float(loss.detach()))
+        traj[name] = losses
+        with torch.no_grad():  # the inference path sees the trained weights too
+            m.eval()
+            traj[name + "_eval"] = float(m(**kw))
+    assert abs(traj["foreach"][0] - traj["fused"][0]) < 1e-6
+    assert abs(traj["foreach"][1] - traj["foreach"][0]) > 1e-3  # the step really moves the loss
+    for a, b in zip(traj["foreach"], traj["fused"]):
+        assert abs(a - b) < 2e-3 * max(1.0, abs(a)), traj
+    assert abs(traj["foreach_eval"] - traj["fused_eval"]) < 2e-3 * max(1.0, abs(traj["foreach_eval"])), traj

@@ -599,16 +599,25 @@ struct WcChainArgs {
 };
 __global__ void __launch_bounds__(128) k_wc_chain(WcChainArgs a, int D, int H) {
   const int net = blockIdx.z, h = blockIdx.x, r = blockIdx.y, c = threadIdx.x;
-  if (c >= D) return;
+  const int warp = c >> 5, lane = c & 31;
   const int HD = H * D;
   const float* dwc = a.dwc[net];
   const float* wo = a.wo[net];
   const float* wv = a.wv[net];
-  // dW_o[i = r, hD + k = c]
-  float acc = 0.f;
-  for (int j = 0; j < D; j++) acc = fmaf(dwc[(size_t)r * HD + h * D + j], wv[(size_t)(h * D + c) * D + j], acc);
-  a.dwo[net][(size_t)r * HD + h * D + c] += acc;
-  // dW_v[hD + k = r, j = c]
+  __shared__ float srow[128];  // dWc[r, hD + :]  (D == 128, checked by the caller)
+  srow[c] = dwc[(size_t)r * HD + h * D + c];
+  __syncthreads();
+  // dW_o[i = r, hD + k] += sum_j dWc[r, hD + j] W_v[hD + k, j]: one warp per k, lanes over j (coalesced rows of W_v)
+  for (int k = warp * 32; k < warp * 32 + 32; k++) {
+    const float* wrow = wv + (size_t)(h * D + k) * D;
+    float p = 0.f;
+#pragma unroll
+    for (int j = lane; j < 128; j += 32) p = fmaf(srow[j], wrow[j], p);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
+    if (lane == 0) a.dwo[net][(size_t)r * HD + h * D + k] += p;
+  }
+  // dW_v[hD + k = r, j = c] += sum_i W_o[i, hD + r] dWc[i, hD + c]   (coalesced over c, W_o element broadcast)
   float acc2 = 0.f;
   for (int i = 0; i < D; i++) acc2 = fmaf(wo[(size_t)i * HD + h * D + r], dwc[(size_t)i * HD + h * D + c], acc2);
   a.dwv[net][(size_t)(h * D + r) * D + c] += acc2;

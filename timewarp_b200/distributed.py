@@ -194,7 +194,7 @@ class DataParallelTrainer:
 
     def step(self, local_batch: dict) -> Tensor:
         self.model.train()
-        self.optimizer.zero_grad(set_to_none=False)
+        self.optimizer.zero_grad(set_to_none=True)
         loss = self.loss_fn(self.model, local_batch)
         loss.backward()
         self.buckets.all_reduce(average=True)

@@ -50,7 +50,8 @@ class _LogLikelihoodFn(torch.autograd.Function):
         tape = torch.empty(tape_b.value + 1024, dtype=torch.uint8, device=dev)
         out = torch.empty(B, dtype=torch.float32, device=dev)
         table = model._param_table(dev)
-        packed = model._packed_weights(dev)
+        packed = model._packed_weights(dev, force=True)  # the optimizer may have stepped without a version bump
+        model._stale_after_train = True  # ... and will probably step again before the next inference-path call
         _lib.check(
             lib.tw_flow_log_likelihood_train(
                 C.byref(cfg), table, _lib.ptr(atom_types), _lib.ptr(x_coords), _lib.ptr(x_velocs), _lib.ptr(y_coords),
@@ -71,19 +72,23 @@ class _LogLikelihoodFn(torch.autograd.Function):
         atom_types, x_velocs, mask_u8 = ctx.saved_tensors
         dev = x_velocs.device
         B, V, tape_b, ws_b = ctx.sizes
-        if model._packed is None or model._packed[2] != ctx.packed_key:
+        # (the re-pack epoch may differ: an inference call in between re-packs the same parameters into the same buffer)
+        if model._packed is None or (model._packed[2][0], model._packed[2][2]) != (ctx.packed_key[0], ctx.packed_key[2]):
             raise _lib.TimewarpB200Error("parameters were modified between the forward and the backward pass")
         tensors = model._ordered_params()
-        grads = [torch.zeros_like(t) if (t.requires_grad and t.is_floating_point()) else None for t in tensors]
+        # ONE zero-filled flat buffer for every gradient (and for the scratch of frozen parameters the kernels still
+        # accumulate into): 659 zeros_like fills cost more than the backward GEMMs at small batch sizes
+        need = [t.requires_grad and t.is_floating_point() for t in tensors]
+        wants = [n or (t.is_floating_point() and not _is_optional_grad(model, i)) for i, (t, n) in enumerate(zip(tensors, need))]
+        sizes = [((t.numel() + 3) // 4 * 4 if w else 0) for t, w in zip(tensors, wants)]  # 16-byte aligned slices
+        flat = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
+        views, off = [], 0
+        for t, w, n in zip(tensors, wants, sizes):
+            views.append(flat[off:off + t.numel()].view(t.shape) if w else None)
+            off += n
+        grads = [v if nd else None for v, nd in zip(views, need)]
         table = model._param_table(dev)
-        gtable = (C.c_void_p * len(tensors))(*[(g.data_ptr() if g is not None else None) for g in grads])
-        # frozen parameters other than the lengthscale buffers / prior scales still need scratch to accumulate into
-        scratch = []
-        for i, (t, g) in enumerate(zip(tensors, grads)):
-            if g is None and t.is_floating_point() and not _is_optional_grad(model, i):
-                z = torch.zeros_like(t)
-                scratch.append(z)
-                gtable[i] = z.data_ptr()
+        gtable = (C.c_void_p * len(tensors))(*[(v.data_ptr() if v is not None else None) for v in views])
         ws = torch.empty(ws_b + 1024, dtype=torch.uint8, device=dev)
         g_in = grad_out.to(torch.float32).contiguous()
         _lib.check(
@@ -134,6 +139,8 @@ class ConditionalFlowDensityModel(nn.Module):
         self._table = None  # (ctypes array, keep-alive list)
         self._workspace: Optional[Tensor] = None
         self._packed = None  # (buffer, aligned ptr, key): bf16 operand images of the weights (tensor-core precisions)
+        self._pack_epoch = 0
+        self._stale_after_train = False  # a taped forward ran since the last pack: re-pack once on the next pass
 
     # ---------------------------------------------------------------- plumbing
     @property
@@ -196,13 +203,23 @@ class ConditionalFlowDensityModel(nn.Module):
             self._table = (arr, tensors, device)
         return self._table[0]
 
-    def _packed_weights(self, device) -> Optional[int]:
-        """Device pointer of the packed bf16 weight images (None for fp32).  Re-packed whenever a
-        parameter was modified in place (optimizer step, load_state_dict) or the precision changed."""
+    def invalidate_packed_weights(self) -> None:
+        """Force a re-pack of the bf16 weight images at the next pass.  Needed only after parameter updates that do not
+        bump the tensors' version counters (e.g. writes through raw pointers); in-place torch ops are detected, and
+        every taped (training) forward re-packs unconditionally."""
+        self._pack_epoch += 1
+
+    def _packed_weights(self, device, force: bool = False) -> Optional[int]:
+        """Device pointer of the packed bf16 weight images (None for fp32).  Re-packed whenever a parameter was modified
+        in place (version counters), the precision changed, or `force` (taped training forward: fused optimizers such as
+        torch.optim.Adam(fused=True) update the parameters WITHOUT bumping their version counters)."""
         if self._cfg.precision == _lib.PRECISION["fp32"]:
             return None
         table = self._param_table(device)
-        key = (self._cfg.precision, tuple(t._version for t in self._table[1] if t is not self._ls_eff))
+        if force or self._stale_after_train:
+            self._pack_epoch += 1
+            self._stale_after_train = False
+        key = (self._cfg.precision, self._pack_epoch, tuple(t._version for t in self._table[1] if t is not self._ls_eff))
         if self._packed is None or self._packed[2] != key or self._packed[0].device != device:
             lib = _lib.load()
             need = C.c_size_t(0)
