@@ -248,6 +248,77 @@ def time_nll_training(dev, precision, batch=256, steps=5, warmup=3, use_graph=Tr
             "final_loss": float(loss)}
 
 
+def run_nll(args):
+    """`--workload nll`: data-parallel NLL training (BASELINE.json configs[3]: dipeptide set, batch 2048 over 8 GPUs =
+    256 per GPU, one gradient all-reduce per step).  Synthetic 2AA-like ragged batches: atom counts uniform in [17, 51],
+    padded to the batch maximum with `masked_elements`.  Prints ONE JSON line (atoms/s = un-padded atoms of all ranks)."""
+    import timewarp_b200 as tw
+    from oracle import flow_oracle as fo
+    from timewarp_b200 import distributed as twd
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    twd.init_from_env("nccl", dev)
+    prec = args.precision
+    model = tw.custom_transformer_nvp_constructor(tw.kernel_transformer_nvp_config(prec))
+    model.load_state_dict(fo.synth_state_dict(fo.OracleConfig(), 0))
+    model = model.to(dev).train()
+    twd.broadcast_parameters(model.parameters())
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4, fused=True)
+    trainer = twd.DataParallelTrainer(model, opt)
+    B = args.batch
+    g = torch.Generator().manual_seed(100 + rank)
+    lengths = torch.randint(17, 52, (B,), generator=g)
+    V = int(lengths.max())
+    mask = torch.arange(V)[None, :] >= lengths[:, None]
+    keep = (~mask)[:, :, None]
+    x = 0.3 * torch.randn(B, V, 3, generator=g) * keep
+    y = (x + 0.02 * torch.randn(B, V, 3, generator=g)) * keep
+    batch = dict(atom_types=(torch.randint(0, 5, (B, V), generator=g) * (~mask)).to(dev), x_coords=x.to(dev),
+                 x_velocs=(torch.randn(B, V, 3, generator=g) * keep).to(dev), y_coords=y.to(dev),
+                 y_velocs=(torch.randn(B, V, 3, generator=g) * keep).to(dev), adj_list=torch.zeros(0, 2, dtype=torch.long, device=dev),
+                 edge_batch_idx=torch.zeros(0, dtype=torch.long, device=dev), masked_elements=mask.to(dev))
+    atoms = torch.tensor([float(lengths.sum())], device=dev, dtype=torch.float64)
+    for _ in range(args.warmup):
+        trainer.step(batch)
+    if world > 1:
+        torch.distributed.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        loss = trainer.step(batch)
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    # replicas must stay bit-identical: compare a parameter checksum across ranks
+    chk = torch.stack([p.detach().double().sum() for p in model.parameters()]).sum().reshape(1)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        torch.distributed.all_reduce(atoms)
+        lo, hi = chk.clone(), chk.clone()
+        torch.distributed.all_reduce(lo, op=torch.distributed.ReduceOp.MIN)
+        torch.distributed.all_reduce(hi, op=torch.distributed.ReduceOp.MAX)
+        in_sync = bool((lo == hi).item())
+    else:
+        in_sync = True
+    if rank == 0:
+        ms = float(t.item()) / args.steps
+        print(json.dumps({
+            "metric": "nll_train_atoms_per_sec", "value": float(atoms.item()) / (ms / 1e3), "unit": "atoms/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": prec, "data": "synthetic",
+            "config": {"workload": f"nll_train_2aa_like_batch{B}_per_gpu", "batch_per_gpu": B, "padded_atoms": V,
+                       "atoms_per_step_all_ranks": float(atoms.item()), "optimizer": "Adam(fused)",
+                       "collective": "one NCCL all-reduce over the flat gradient buffer per step"},
+            "final_loss": float(loss), "replicas_in_sync": in_sync}), flush=True)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
 def run_ours(args):
     import ctypes as C
 
@@ -437,12 +508,16 @@ def main():
     ap.add_argument("--weights", default="proposal", choices=["proposal", "init"], help="synthetic weight set (see bench_state_dict)")
     ap.add_argument("--graph", action="store_true", help="replay one CUDA graph per MH step instead of launching every kernel from the host "
                     "(measured slower on the power-capped B200: 29.2 vs 27.0 ms/step -- the host launches are already hidden)")
+    ap.add_argument("--workload", default="mh", choices=["mh", "nll"], help="mh: the headline MH benchmark; nll: data-parallel NLL training")
+    ap.add_argument("--batch", type=int, default=256, help="--workload nll: samples per GPU")
     ap.add_argument("--no-nll", action="store_true", help="skip the secondary NLL-training throughput measurement")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "nll":
+        run_nll(args)
     else:
         run_ours(args)
 

@@ -192,12 +192,30 @@ class DataParallelTrainer:
         self.buckets = GradientBuckets(model.parameters(), bucket_bytes)
         self.loss_fn = loss_fn or (lambda m, batch: m(**batch))
 
+    @torch.no_grad()
+    def _all_reduce_flat(self) -> bool:
+        """The CUDA model's backward hands out every gradient as a view of ONE flat buffer: reduce that buffer in place
+        (a single collective, no per-parameter copies).  False when the gradients do not live in such a buffer."""
+        flat = getattr(self.model, "_last_flat_grad", None)
+        if flat is None:
+            return False
+        base = flat.untyped_storage().data_ptr()
+        for p in self.model.parameters():
+            if p.requires_grad and (p.grad is None or p.grad.untyped_storage().data_ptr() != base):
+                return False
+        rank, world = world_info()
+        if world > 1:
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+            flat.mul_(1.0 / world)
+        return True
+
     def step(self, local_batch: dict) -> Tensor:
         self.model.train()
         self.optimizer.zero_grad(set_to_none=True)
         loss = self.loss_fn(self.model, local_batch)
         loss.backward()
-        self.buckets.all_reduce(average=True)
+        if not self._all_reduce_flat():
+            self.buckets.all_reduce(average=True)
         if self.clip:
             clip_grad_norm(self.model.parameters(), self.clip)
         self.optimizer.step()

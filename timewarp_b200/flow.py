@@ -87,6 +87,7 @@ class _LogLikelihoodFn(torch.autograd.Function):
             views.append(flat[off:off + t.numel()].view(t.shape) if w else None)
             off += n
         grads = [v if nd else None for v, nd in zip(views, need)]
+        model._last_flat_grad = flat  # data-parallel training all-reduces this buffer directly (distributed.py)
         table = model._param_table(dev)
         gtable = (C.c_void_p * len(tensors))(*[(v.data_ptr() if v is not None else None) for v in views])
         ws = torch.empty(ws_b + 1024, dtype=torch.uint8, device=dev)
@@ -140,6 +141,7 @@ class ConditionalFlowDensityModel(nn.Module):
         self._workspace: Optional[Tensor] = None
         self._packed = None  # (buffer, aligned ptr, key): bf16 operand images of the weights (tensor-core precisions)
         self._pack_epoch = 0
+        self._last_flat_grad: Optional[Tensor] = None
         self._stale_after_train = False  # a taped forward ran since the last pack: re-pack once on the next pass
 
     # ---------------------------------------------------------------- plumbing
