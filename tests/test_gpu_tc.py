@@ -98,3 +98,34 @@ def test_bf16x3_inference_path_odd_sizes_vs_oracle(B, V, lengths):
         yc, yvel, lp = m.conditional_sample_with_logp(num_samples=1, **kw)
         ll2 = m.log_likelihood(y_coords=yc[0], y_velocs=yvel[0], **kw)
     torch.testing.assert_close(ll2, lp[0], rtol=1e-4, atol=2e-3)
+
+
+@pytest.mark.parametrize("name", ["full_ad22", "full_2olx65"])
+@torch.no_grad()
+def test_bf16x3_shared_conditioning_proposals(name):
+    """S proposals from ONE conditioning state (sample_with_model shape: n_cond = 1, every sample shares the score images)
+    and the reverse-move density of those proposals (distinct conditioning per sample), inference kernels vs the reference."""
+    g = load_golden(name)
+    m, _ = build_model(FULL_O, "bf16x3", int(g["weight_seed"]))
+    mask = g["masked_elements"]
+    S = g["sS_z_coords"].shape[0]
+    yc, yv, lp = m.sample_from_latents(g["atom_types"][:1].cuda(), g["x_coords"][:1].cuda(), g["x_velocs"][:1].cuda(), mask[:1].cuda(),
+                                       g["sS_z_coords"].cuda(), g["sS_z_velocs"].cuda())
+    keepS = (~mask[:1])[None, :, :, None].expand_as(g["sS_y_coords"])
+    assert_rel(yc.cpu()[keepS], g["sS_y_coords"][keepS], what="S proposals: y_coords")
+    assert_rel(lp, g["sS_logp"], what="S proposals: logp")
+    p_yx = m.log_likelihood(atom_types=g["atom_types"][:1].repeat(S, 1).cuda(), y_coords=g["x_coords"][:1].repeat(S, 1, 1).cuda(),
+                            y_velocs=g["x_velocs"][:1].repeat(S, 1, 1).cuda(), x_coords=yc.squeeze(1), x_velocs=yv.squeeze(1),
+                            adj_list=EMPTY_ADJ.cuda(), edge_batch_idx=EMPTY_EBI.cuda(), masked_elements=mask[:1].repeat(S, 1).cuda())
+    assert_rel(p_yx, g["sS_p_yx"], what="reverse-move density")
+    # a larger S: 300 proposals from one state == the same proposals evaluated as 300 independent samples
+    torch.manual_seed(5)
+    S2 = 300
+    V = g["x_coords"].shape[1]
+    zc, zv = 0.05 * torch.randn(S2, 1, V, 3, device="cuda"), torch.randn(S2, 1, V, 3, device="cuda")
+    a = m.sample_from_latents(g["atom_types"][:1].cuda(), g["x_coords"][:1].cuda(), g["x_velocs"][:1].cuda(), mask[:1].cuda(), zc, zv)
+    b = m.sample_from_latents(g["atom_types"][:1].repeat(S2, 1).cuda(), g["x_coords"][:1].repeat(S2, 1, 1).cuda(),
+                              g["x_velocs"][:1].repeat(S2, 1, 1).cuda(), mask[:1].repeat(S2, 1).cuda(),
+                              zc.transpose(0, 1).contiguous(), zv.transpose(0, 1).contiguous())
+    torch.testing.assert_close(a[0].squeeze(1), b[0].squeeze(0), rtol=1e-5, atol=2e-5)
+    torch.testing.assert_close(a[2].squeeze(1), b[2].squeeze(0), rtol=1e-5, atol=1e-3)
