@@ -246,10 +246,64 @@ def learnable_cases():
     run_case("full_ad22_learnable", FULL_LEARNABLE, ad, B=3, seed=22, sample_S=2, trace_layer0=False)
 
 
+def dataloader_case():
+    """Batch / wire formats: the reference's own dense collate on ragged synthetic datapoints, and
+    its conditioning/target pairing (`load_pdb_trace_data`) on a small synthetic log-spaced trajectory file.  mdtraj is
+    not installed: `md.load` is replaced by a stand-in topology built from the alanine-dipeptide template (the pairing
+    logic under test does not depend on it)."""
+    import timewarp.dataloader as ref_dl
+
+    ad = alanine_dipeptide()
+    g = torch.Generator().manual_seed(31)
+    pts = []
+    for i, n in enumerate([22, 15, 9]):
+        f = lambda: torch.randn(n, 3, generator=g)  # noqa: E731
+        bonds = torch.tensor([b for b in ad.bonds.tolist() if max(b) < n], dtype=torch.int64)
+        pts.append(ref_dl.MolDynDatapoint(name=f"mol{i}", atom_types=torch.tensor(ad.atom_types[:n]), adj_list=bonds, atom_coords=f(),
+                                          atom_velocs=f(), atom_forces=f(), atom_coord_targets=f(), atom_veloc_targets=f(),
+                                          atom_force_targets=f()))
+    batch = ref_dl.moldyn_dense_collate_fn(pts)
+    out = {f"in{i}_{k}": getattr(p, k).numpy() for i, p in enumerate(pts) for k in
+           ("atom_types", "adj_list", "atom_coords", "atom_velocs", "atom_forces", "atom_coord_targets", "atom_veloc_targets", "atom_force_targets")}
+    out.update({f"batch_{k}": getattr(batch, k).numpy() for k in
+                ("atom_types", "adj_list", "edge_batch_idx", "atom_coords", "atom_velocs", "atom_forces", "atom_coord_targets",
+                 "atom_veloc_targets", "atom_force_targets", "masked_elements")})
+    out["lengths_mask"] = ref_dl.lengths_to_mask(torch.tensor([3, 1, 4])).numpy()
+
+    # synthetic trajectory: log-spaced steps like simulation output (1, 10, 100, 1000 after every 10000-step block)
+    rng = np.random.default_rng(7)
+    steps = np.array(sorted({base + off for base in range(0, 60000, 10000) for off in (0, 1, 10, 100, 1000)}), dtype=np.int64)
+    T, V = len(steps), ad.num_atoms
+    traj = dict(step=steps, positions=rng.standard_normal((T, V, 3)).astype(np.float32),
+                velocities=rng.standard_normal((T, V, 3)).astype(np.float32), forces=rng.standard_normal((T, V, 3)).astype(np.float32))
+    traj_path = os.path.join(HERE, "synthetic_ad-traj-arrays.npz")
+    np.savez_compressed(traj_path, **traj)
+
+    class _A:
+        def __init__(self, i, sym):
+            self.index, self.element = i, types.SimpleNamespace(symbol=sym)
+
+    atoms = [_A(i, e) for i, e in enumerate(ad.elements)]
+    topo = types.SimpleNamespace(atoms=atoms, bonds=[types.SimpleNamespace(atom1=atoms[a], atom2=atoms[b]) for a, b in ad.bonds.tolist()])
+    ref_dl.md.load = lambda path: types.SimpleNamespace(topology=topo)
+    for sw, eq in ((1, False), (10, False), (100, True), (1000, False)):
+        info = ref_dl.load_pdb_trace_data("synthetic_ad", "unused.pdb", traj_path, step_width=sw, equal_data_spacing=eq)
+        out[f"pairs_sw{sw}_eq{int(eq)}_coord_features"] = np.stack(info.coord_features) if info.coord_features else np.zeros((0, V, 3), np.float32)
+        out[f"pairs_sw{sw}_eq{int(eq)}_veloc_targets"] = np.stack(info.veloc_targets) if info.veloc_targets else np.zeros((0, V, 3), np.float32)
+        out[f"pairs_sw{sw}_eq{int(eq)}_node_types"] = info.node_types
+        out[f"pairs_sw{sw}_eq{int(eq)}_adj_list"] = info.adj_list
+        print("pairs", sw, eq, len(info.coord_features))
+    np.savez_compressed(os.path.join(HERE, "dataloader_collate.npz"), **out)
+
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
     if len(sys.argv) > 1 and sys.argv[1] == "learnable":
         learnable_cases()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "dataloader":
+        dataloader_case()
         sys.exit(0)
     init_case()
     ad, olx = alanine_dipeptide(), tetrapeptide_2olx()
@@ -262,3 +316,5 @@ if __name__ == "__main__":
     grad_case("grads_full_ad22", FULL, ad, B=4, seed=3)
     grad_case("grads_full_ad22_ragged", FULL, ad, B=3, seed=4, lengths=[22, 17, 12])
     learnable_cases()
+    dataloader_case()
+
