@@ -245,7 +245,7 @@ def sample_with_model(batch, model, device, openmm_potential_energy_torch, masse
         if random_velocs and resample_velocs:
             x_velocs = torch.randn_like(x_velocs)  # :590-592
         if rotate:  # :604-607
-            raise NotImplementedError("rotate=True needs the reference's random_rotation_matrix (equivariance/, out of scope)")
+            raise NotImplementedError("rotate=True: the reference applies `(Q @ x_coords.T).T` to [1, V, 3] tensors (evaluation_utils.py:604-607), which only type-checks for V == 3; not reproduced")
         y_coords, y_velocs, p_xy = model.conditional_sample_with_logp(
             atom_types=atom_types, x_coords=x_coords, x_velocs=x_velocs, adj_list=adj_list, edge_batch_idx=edge_batch_idx,
             masked_elements=masked_elements, num_samples=S)  # :609-617
