@@ -166,6 +166,8 @@ static int begin_pass(PassCtx& p, const float* x_coords) {
   TW_TRY(launch_prep(x_coords, p.mask, p.n_cond, p.V, p.fb.xc, p.fb.com, p.st));
   // lengthscales of chain[0].scale_transformer.encoder_layers[0] (cache key maps lengthscales -> 0)
   const float* ls = p.pv.enc(0, 0, 0, 1);
+  if (p.c->precision != TW_PRECISION_FP32 && tc_supported(p.c) && tc_scores_direct_supported(p.V))
+    return tc_begin_pass_direct(p.c, p.fb.tc, p.fb.xc, p.mask, ls, p.n_cond, p.V, p.st);  // no fp32 score tensor
   TW_TRY(launch_scores(p.fb.xc, p.mask, ls, p.n_cond, p.V, p.c->num_heads, p.fb.scores, p.st));
   if (p.c->precision != TW_PRECISION_FP32)
     TW_TRY(tc_begin_pass(p.c, p.pv, p.fb.tc, p.fb.scores, p.mask, p.n, p.n_cond, p.V, p.st));

@@ -1261,6 +1261,65 @@ __global__ void __launch_bounds__(256) k_scores_img(const float* __restrict__ sc
   }
 }
 
+// Scores straight to operand images (inference): the fp32 score tensor [n_cond, H, V, V] (104 MB at 1024 x 65 atoms) is
+// only an intermediate of the tensor-core path, so one CTA per conditioning state computes
+//   w_hij = exp(-(|x_i - x_j| / l_h)^2), key-masked, L1-row-normalised (+1e-5)      kernel_attention.py:98-119
+// with exactly the arithmetic of k_scores (same operation order, same warp reduction) and writes the bf16 hi/lo
+// image of k_scores_img through a shared-memory staging buffer (16-byte coalesced stores).
+__global__ void __launch_bounds__(256) k_scores_direct_img(const float* __restrict__ xc, const uint8_t* __restrict__ mask,
+                                                           const float* __restrict__ ls, int V, int VP, int H,
+                                                           uint8_t* __restrict__ img) {
+  extern __shared__ __align__(16) uint8_t sm_raw[];
+  float* xs = reinterpret_cast<float*>(sm_raw);                  // [V][3]
+  uint8_t* ms = sm_raw + (((size_t)V * 12 + 15) & ~(size_t)15);  // [V]
+  uint8_t* stg = ms + (((size_t)V + 15) & ~(size_t)15);          // [hi: VP*VP*2][lo: VP*VP*2]
+  const int64_t b = blockIdx.x;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < V * 3; i += blockDim.x) xs[i] = xc[b * V * 3 + i];
+  for (int i = tid; i < V; i += blockDim.x) ms[i] = mask[b * V + i];
+  const uint32_t mat = (uint32_t)VP * VP * 2;
+  __syncthreads();
+  for (int h = 0; h < H; h++) {
+    const float l = ls[h];
+    for (uint32_t o = tid * 16; o < 2 * mat; o += blockDim.x * 16) *reinterpret_cast<uint4*>(stg + o) = make_uint4(0, 0, 0, 0);
+    __syncthreads();
+    for (int i = warp; i < V; i += 8) {
+      const float xi = xs[i * 3], yi = xs[i * 3 + 1], zi = xs[i * 3 + 2];
+      float w[4];  // V <= 128: at most four columns per lane
+      float sum = 0.f;
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int j = lane + 32 * u;
+        w[u] = 0.f;
+        if (j < V) {
+          float dx = xi - xs[j * 3], dy = yi - xs[j * 3 + 1], dz = zi - xs[j * 3 + 2];
+          float d = sqrtf(dx * dx + dy * dy + dz * dz);
+          float a = d / l;
+          w[u] = ms[j] ? 0.f : expf(-(a * a));
+          sum += fabsf(w[u]);
+        }
+      }
+      sum = warp_sum(sum) + 1e-5f;
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int j = lane + 32 * u;
+        if (j < V) {
+          const float v = w[u] / sum;
+          __nv_bfloat16 hb = __float2bfloat16(v);
+          __nv_bfloat16 lb = __float2bfloat16(v - __bfloat162float(hb));
+          const uint32_t off = (i >> 3) * ((VP >> 3) * 128u) + (j >> 3) * 128u + (i & 7) * 16u + (j & 7) * 2u;
+          *reinterpret_cast<__nv_bfloat16*>(stg + off) = hb;
+          *reinterpret_cast<__nv_bfloat16*>(stg + mat + off) = lb;
+        }
+      }
+    }
+    __syncthreads();
+    uint8_t* dst = img + ((size_t)b * H + h) * 2 * mat;
+    for (uint32_t o = tid * 16; o < 2 * mat; o += blockDim.x * 16) *reinterpret_cast<uint4*>(dst + o) = *reinterpret_cast<const uint4*>(stg + o);
+    __syncthreads();
+  }
+}
+
 // ============================================================================================
 // Attention, step 2 (mixing): for every sample n and head h,   mixed_h = A_h x   (kernel_attention.py:139
 // re-associated with the value projection, see k_combine_wc).  Features on the TMEM lanes:
@@ -2755,6 +2814,27 @@ int tc_begin_pass(const tw_flow_config* c, const ParamView&, TcScratch& tc, cons
   if (tc.ffn_tail) TW_CUDA(cudaMemsetAsync(tc.ffn_tail, 0, kFfnTailBytes, st));
   if (!(tc_stage_mask() & TC_MIX)) return TW_OK;
   return tc_scores_images(c, scores, n_cond, V, tc.scores_img, 0, st);
+}
+
+bool tc_scores_direct_supported(int V) {  // the CUDA-core attention fallback (bring-up switch TW_TC_STAGES) still reads fp32 scores
+  return (tc_stage_mask() & TC_MIX) && (tc_stage_mask() & TC_ATTN_PROJ) && V <= 128;
+}
+
+// Inference: score images straight from the centred conditioning coordinates (no fp32 score tensor).
+int tc_begin_pass_direct(const tw_flow_config* c, TcScratch& tc, const float* xc, const uint8_t* mask, const float* lengthscales,
+                         int64_t n_cond, int V, cudaStream_t st) {
+  if (tc.ffn_tail) TW_CUDA(cudaMemsetAsync(tc.ffn_tail, 0, kFfnTailBytes, st));
+  const int VP = pad16(V);
+  const size_t smem = (((size_t)V * 12 + 15) & ~(size_t)15) + (((size_t)V + 15) & ~(size_t)15) + (size_t)VP * VP * 4;
+  static bool attr_done = false;
+  if (!attr_done) {
+    TW_CUDA(cudaFuncSetAttribute(k_scores_direct_img, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 128 * 4 + 4096));
+    attr_done = true;
+  }
+  if (n_cond < 1) return TW_OK;
+  k_scores_direct_img<<<(unsigned)n_cond, 256, smem, st>>>(xc, mask, lengthscales, V, VP, c->num_heads, tc.scores_img);
+  TW_LAUNCH_CHECK();
+  return TW_OK;
 }
 
 size_t tc_scores_img_bytes(const tw_flow_config* c, int64_t n_cond, int V) {

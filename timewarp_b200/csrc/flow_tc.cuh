@@ -42,6 +42,9 @@ void tc_carve(const tw_flow_config* c, int64_t n, int64_t n_cond, int64_t V, Are
 int tc_pack_weights(const tw_flow_config* c, const ParamView& pv, uint8_t* packed, size_t bytes, cudaStream_t st);
 int tc_begin_pass(const tw_flow_config* c, const ParamView& pv, TcScratch& tc, const float* scores, const uint8_t* mask,
                   int64_t n, int64_t n_cond, int V, cudaStream_t st);
+bool tc_scores_direct_supported(int V);
+int tc_begin_pass_direct(const tw_flow_config* c, TcScratch& tc, const float* xc, const uint8_t* mask, const float* lengthscales,
+                         int64_t n_cond, int V, cudaStream_t st);
 size_t tc_packed_bytes(const tw_flow_config* c);
 void tc_set_ffn_trace(long long* buf);
 void tc_set_trace(int cls, long long* buf);  // 1 fused FFN, 2 mixing kernel  // debug: event trace of the fused FFN (see FfnArgs::trace)

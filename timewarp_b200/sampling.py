@@ -153,6 +153,7 @@ class MHChains:
         self.n_steps += 1
         return self.last["accepted"]
 
+    @torch.no_grad()
     def _step_impl(self):
         m = self.model
         if self.random_velocs and self.resample_velocs:
@@ -183,6 +184,7 @@ class MHChains:
         self.last = dict(exponent=ex, acceptance=pa, accepted=accb, p_xy=p_xy, p_yx=p_yx, e_pot_y=e_pot_y, e_kin_y=e_kin_y)
         return accb
 
+    @torch.no_grad()
     def capture_graph(self, warmup: int = 2):
         """Capture one iteration into a CUDA graph (torch.cuda.graph: the torch RNG draws stay graph-safe, outputs live
         in the graph's private pool).  `warmup` eager iterations run first so that every lazy initialisation (weight
