@@ -245,7 +245,7 @@ def time_nll_training(dev, precision, batch=256, steps=5, warmup=3, use_graph=Tr
     return {"metric": "nll_train_atoms_per_sec", "value": batch * V / (ms / 1e3), "unit": "atoms/s", "ms_per_step": ms,
             "config": {"workload": f"nll_train_ad22_batch{batch}", "atoms": V, "batch": batch, "optimizer": "Adam", "precision": precision,
                        "launch": launch},
-            "final_loss": float(loss)}
+            "final_loss": float(loss.detach())}
 
 
 def run_nll(args):
@@ -314,7 +314,7 @@ def run_nll(args):
             "config": {"workload": f"nll_train_2aa_like_batch{B}_per_gpu", "batch_per_gpu": B, "padded_atoms": V,
                        "atoms_per_step_all_ranks": float(atoms.item()), "optimizer": "Adam(fused)",
                        "collective": "one NCCL all-reduce over the flat gradient buffer per step"},
-            "final_loss": float(loss), "replicas_in_sync": in_sync}), flush=True)
+            "final_loss": float(loss.detach()), "replicas_in_sync": in_sync}), flush=True)
     if world > 1:
         torch.distributed.destroy_process_group()
 
