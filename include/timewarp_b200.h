@@ -60,11 +60,20 @@ typedef struct tw_flow_config {
   int32_t num_atom_types;                     /* rows of the atom embedding (5)                 */
   float layer_norm_eps;                       /* 1e-5                                           */
   int32_t precision;                          /* TW_PRECISION_*                                 */
+  int32_t attention_type;                     /* TW_ATTENTION_*: 0 kernel (also learnable_kernel: the caller passes the effective
+                                                 lengthscales), 2 chebyshev_kernel (kernel_attention.py:255-339)   */
+  int32_t cheb_order;                         /* chebyshev_kernel: 1..32 coefficients per head                     */
+  int32_t force_asymptotic_zero;              /* chebyshev_kernel: subtract the per-head mean of the coefficients  */
 } tw_flow_config;
+#define TW_ATTENTION_KERNEL 0
+#define TW_ATTENTION_CHEBYSHEV 2
+#define TW_MAX_CHEB_ORDER 32
 
 /* Parameter table: an array of device pointers to fp32 tensors in the reference's own shapes
  * ([out,in] Linear weights), in this order (state_dict keys of SURVEY.md section 2.1):
  *   [0] flow.atom_embedder.weight   [1] coords_prior_log_scale   [2] velocs_prior_log_scale
+ *   (chebyshev_kernel only: AFTER everything below, 2*L*T more pointers -- for k, for net, for t:
+ *    self_attn.attention.cheb_coeffs [H, cheb_order])
  *   then for k in 0..L-1, for net in (scale_transformer, shift_transformer):
  *     in_mlp._layers.{0,2,..}.{weight,bias}                      2*(num_mlp_hidden+1) pointers
  *     for t in 0..T-1: self_attn.values_proj.weight, self_attn.attention.lengthscales,

@@ -38,7 +38,10 @@ class OracleConfig:
     position_layer_index_mod_2: int = 0
     layer_norm_eps: float = 1e-5
     # "kernel" | "learnable_kernel" (LearnableLengthscaleKernelAttention, kernel_attention.py:217-253)
+    # | "chebyshev_kernel" (LearnableChebyshevKernelAttention, :255-339)
     attention_type: str = "kernel"
+    cheb_order: int = 0
+    force_asymptotic_zero: bool = False
 
 
 StateDict = Dict[str, Tensor]
@@ -53,12 +56,42 @@ def centre_of_mass(coords: Tensor, masked_elements: Tensor) -> Tensor:
     return c.sum(dim=-2, keepdim=True) / num_points
 
 
+# Chebyshev-rational coefficients of exp(-s), the initial value of every layer's `cheb_coeffs`
+# (kernel_attention.py:291-327; numerical-quadrature constants of the reference, data not code).
+CHEB_COEFFS_EXPMX = [
+    4.275836e-01, -5.464240e-01, 7.106222e-02, 5.473271e-02, 5.744192e-03, -7.926410e-03, -5.392865e-03, -1.210823e-03,
+    6.996851e-04, 8.686655e-04, 4.459163e-04, 7.084817e-05, -9.620444e-05, -1.110469e-04, -6.551055e-05, -1.875292e-05,
+    7.930955e-06, 1.553729e-05, 1.246072e-05, 6.282442e-06, 1.216243e-06, -1.468327e-06, -2.141963e-06, -1.694741e-06,
+    -9.063254e-07, -2.337215e-07, 1.609271e-07, 2.978384e-07, 2.700519e-07, 1.730454e-07, 7.272222e-08, 1.192814e-09,
+]  # fmt: skip
+
+
+# kernel_attention.py:13-66: F(x) = sum_c coeff[h, c] R_c(x^2), R_n(y) = T_n((y - 1) / (y + 1)) by the three-term recursion
+def chebyshev_basis(scaled: Tensor, coeffs: Tensor, force_asymptotic_zero: bool) -> Tensor:
+    if force_asymptotic_zero:
+        coeffs = coeffs - coeffs.mean(dim=1, keepdim=True)  # :27-28
+    y = scaled**2
+    order = coeffs.shape[1]
+    rprev = torch.ones_like(y)
+    rfactor = (y - 1.0) / (y + 1.0)
+    rcur = rfactor
+    terms = [rprev] + ([rcur] if order >= 2 else [])
+    for _ in range(2, order):
+        rnext = 2.0 * rfactor * rcur - rprev
+        terms.append(rnext)
+        rcur, rprev = rnext, rcur
+    cheb = torch.stack(terms, dim=2)  # [B, H, order, Q, M]
+    return torch.einsum("bhcqm,hc->bhqm", cheb, coeffs.to(y.dtype))  # :34
+
+
 # modules/layers/kernel_attention.py:9-10,69-121
 def kernel_attention_scores(
     positions: Tensor,  # [B, V, 3]
     masked_elements: Tensor,  # [B, V] bool, True = padding
     lengthscales: Tensor,  # [H]
     distance_mode: str = "cdist",
+    cheb_coeffs: Optional[Tensor] = None,  # [H, order]: Chebyshev basis instead of the Gaussian
+    force_asymptotic_zero: bool = False,
 ) -> Tensor:  # [B, H, V, V]
     if distance_mode == "cdist":
         # literal reference call (kernel_attention.py:98-102)
@@ -69,7 +102,10 @@ def kernel_attention_scores(
     else:
         raise ValueError(distance_mode)
     scaled = d.unsqueeze(-3) / lengthscales[None, :, None, None]  # :105-110
-    w = torch.exp(-(scaled**2))  # gaussian_basis_function :9-10
+    if cheb_coeffs is not None:
+        w = chebyshev_basis(scaled, cheb_coeffs, force_asymptotic_zero)
+    else:
+        w = torch.exp(-(scaled**2))  # gaussian_basis_function :9-10
     w = w.masked_fill(masked_elements[:, None, None, :], 0.0)  # :114
     w = w / (torch.abs(w).sum(dim=-1, keepdim=True) + 1e-5)  # :116-119
     return w
@@ -93,8 +129,10 @@ def layer_norm(x: Tensor, w: Tensor, b: Tensor, eps: float) -> Tensor:
 
 # modules/layers/custom_attention_encoder.py:82-114 + kernel_self_attention.py:29-48
 # + kernel_attention.py:124-156,185-214
-def encoder_layer(sd: StateDict, prefix: str, cfg: OracleConfig, src: Tensor, scores: Tensor) -> Tensor:
+def encoder_layer(sd: StateDict, prefix: str, cfg: OracleConfig, src: Tensor, scores) -> Tensor:
     B, V, D = src.shape
+    if callable(scores):  # chebyshev_kernel: every attention layer has its own basis function -> its own scores
+        scores = scores(prefix)
     H = scores.shape[1]
     values = torch.nn.functional.linear(src, sd[f"{prefix}.self_attn.values_proj.weight"])  # [B,V,H*Dv]
     Dv = values.shape[-1] // H
@@ -161,7 +199,14 @@ def sequential_flow(
         ls = torch.exp(sd[f"{att}.log_lengthscales"]).to(x_coords.dtype)
     else:
         ls = sd[f"{att}.lengthscales"].to(x_coords.dtype)
-    scores = kernel_attention_scores(x_coords, masked_elements, ls, distance_mode)
+    if cfg.attention_type == "chebyshev_kernel":
+        # the basis function (a lambda per module, kernel_attention.py:333-335) is part of the cache key: no sharing
+        def scores(prefix):
+            return kernel_attention_scores(x_coords, masked_elements, ls, distance_mode,
+                                           cheb_coeffs=sd[f"{prefix}.self_attn.attention.cheb_coeffs"].to(x_coords.dtype),
+                                           force_asymptotic_zero=cfg.force_asymptotic_zero)
+    else:
+        scores = kernel_attention_scores(x_coords, masked_elements, ls, distance_mode)
     idxs = range(cfg.num_coupling_layers)
     idxs = idxs[::-1] if reverse else idxs
     keep = ~masked_elements[:, :, None]
@@ -326,6 +371,8 @@ def state_dict_shapes(cfg: OracleConfig) -> Dict[str, Tuple[int, ...]]:
                 out[f"{q}.self_attn.attention.lengthscales"] = (H,)
                 if cfg.attention_type == "learnable_kernel":
                     out[f"{q}.self_attn.attention.log_lengthscales"] = (H,)
+                if cfg.attention_type == "chebyshev_kernel":
+                    out[f"{q}.self_attn.attention.cheb_coeffs"] = (H, cfg.cheb_order)
                 out[f"{q}.self_attn.attention._out_projection.weight"] = (D, H * D)
                 out[f"{q}.linear1.weight"] = (F, D)
                 out[f"{q}.linear1.bias"] = (F,)
@@ -349,7 +396,10 @@ def synth_state_dict(cfg: OracleConfig, seed: int = 0, dtype=torch.float32) -> S
     sd: StateDict = {}
     for key, shape in state_dict_shapes(cfg).items():
         g = torch.Generator().manual_seed((zlib.crc32(key.encode()) + 7919 * seed) % (2**31))
-        if key.endswith("log_lengthscales"):  # a different value in every layer (the reference uses only the first executed one)
+        if key.endswith("cheb_coeffs"):  # the reference's initial value + a different perturbation in every layer and head
+            base = torch.tensor((CHEB_COEFFS_EXPMX + [0.0] * max(0, shape[1] - len(CHEB_COEFFS_EXPMX)))[: shape[1]])
+            t = base[None, :].expand(shape) + 0.02 * (torch.rand(shape, generator=g) * 2 - 1)
+        elif key.endswith("log_lengthscales"):  # a different value in every layer (the reference uses only the first executed one)
             t = torch.log(torch.tensor(cfg.lengthscales, dtype=torch.float32)) + 0.3 * (torch.rand(shape, generator=g) * 2 - 1)
         elif key.endswith("lengthscales"):
             t = torch.tensor(cfg.lengthscales, dtype=torch.float32)

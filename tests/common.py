@@ -16,6 +16,11 @@ FULL_O = fo.OracleConfig()
 TINY_L = fo.OracleConfig(atom_embedding_dim=8, latent_mlp_hidden_dims=[24], num_coupling_layers=4, num_transformer_layers=2,
                          d_model=16, dim_feedforward=32, lengthscales=[0.3, 1.0], attention_type="learnable_kernel")
 FULL_L = fo.OracleConfig(attention_type="learnable_kernel")
+# `chebyshev_kernel` attention (a Chebyshev-rational basis per attention layer, no score sharing)
+TINY_C = fo.OracleConfig(atom_embedding_dim=8, latent_mlp_hidden_dims=[24], num_coupling_layers=4, num_transformer_layers=2,
+                         d_model=16, dim_feedforward=32, lengthscales=[0.3, 1.0], attention_type="chebyshev_kernel", cheb_order=6,
+                         force_asymptotic_zero=True)
+FULL_C = fo.OracleConfig(attention_type="chebyshev_kernel", cheb_order=12, force_asymptotic_zero=False)
 
 
 def model_config(o: fo.OracleConfig, precision: str):
@@ -26,7 +31,9 @@ def model_config(o: fo.OracleConfig, precision: str):
         num_transformer_layers=o.num_transformer_layers,
         encoder_layer_config=tw.CustomAttentionEncoderLayerConfig(
             d_model=o.d_model, dim_feedforward=o.dim_feedforward, dropout=0.0, num_heads=len(o.lengthscales),
-            attention_type=getattr(o, "attention_type", "kernel"), lengthscales=list(o.lengthscales), normalise_kernel_values=True),
+            attention_type=getattr(o, "attention_type", "kernel"), lengthscales=list(o.lengthscales), normalise_kernel_values=True,
+            cheb_order=(o.cheb_order if getattr(o, "attention_type", "kernel") == "chebyshev_kernel" else None),
+            force_asymptotic_zero=(o.force_asymptotic_zero if getattr(o, "attention_type", "kernel") == "chebyshev_kernel" else None)),
         position_layer_index_mod_2=o.position_layer_index_mod_2,
         precision=precision,
     )

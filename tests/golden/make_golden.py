@@ -55,6 +55,8 @@ def ref_model(cfg: OracleConfig, seed: int):
         attention_type=cfg.attention_type,
         lengthscales=list(cfg.lengthscales),
         normalise_kernel_values=True,
+        cheb_order=cfg.cheb_order if cfg.attention_type == "chebyshev_kernel" else None,
+        force_asymptotic_zero=cfg.force_asymptotic_zero if cfg.attention_type == "chebyshev_kernel" else None,
     )
     mc = CustomAttentionTransformerNVPConfig(
         atom_embedding_dim=cfg.atom_embedding_dim,
@@ -66,7 +68,16 @@ def ref_model(cfg: OracleConfig, seed: int):
     )
     model = custom_transformer_nvp_constructor(mc)
     sd = synth_state_dict(cfg, seed)
-    model.load_state_dict(sd, strict=True)
+    if cfg.attention_type == "chebyshev_kernel":
+        # the reference builds `cheb_coeffs` as an EXPANDED tensor (stride 0 over heads, kernel_attention.py:328-330): the
+        # heads share storage and load_state_dict cannot copy into it.  Give every module a real [H, order] tensor instead.
+        named = dict(model.named_parameters())
+        for k in [k for k in sd if k.endswith("cheb_coeffs")]:
+            named[k].data = sd[k].clone()
+        missing = model.load_state_dict({k: v for k, v in sd.items() if not k.endswith("cheb_coeffs")}, strict=False)
+        assert all(k.endswith("cheb_coeffs") for k in missing.missing_keys) and not missing.unexpected_keys
+    else:
+        model.load_state_dict(sd, strict=True)
     model.eval()
     return model, sd
 
@@ -105,7 +116,7 @@ def run_case(name, cfg, peptide, B, seed, lengths=None, sample_S=3, wseed=0, tra
         out["log_likelihood"] = model.log_likelihood(y_coords=y, y_velocs=yv, **kw).numpy()
         out["loss"] = model(y_coords=y, y_velocs=yv, **kw).numpy()
         # fp64 truth from the same reference code
-        m64 = __import__("copy").deepcopy(model).double()
+        m64 = ref_model(cfg, wseed)[0].double()  # (a deepcopy would keep the Chebyshev basis lambdas bound to the fp32 module)
         kw64 = dict(atom_types=at, x_coords=x.double(), x_velocs=xv.double(), adj_list=EMPTY_ADJ,
                     edge_batch_idx=EMPTY_EBI, masked_elements=mask)
         out["log_likelihood_f64"] = m64.log_likelihood(y_coords=y.double(), y_velocs=yv.double(), **kw64).numpy()
@@ -114,7 +125,14 @@ def run_case(name, cfg, peptide, B, seed, lengths=None, sample_S=3, wseed=0, tra
         ls = torch.tensor(cfg.lengthscales, dtype=torch.float32)
         if cfg.attention_type == "learnable_kernel":  # density direction: the first attention layer executed (cache quirk)
             ls = torch.exp(sd["flow.chain.0.scale_transformer.encoder_layers.0.self_attn.attention.log_lengthscales"])
-        out["scores"] = compute_kernel_attention_scores(query=x - com, key=x - com, masked_elements=mask, lengthscales=ls).numpy()
+        if cfg.attention_type == "chebyshev_kernel":  # scores of the first attention layer (every layer has its own)
+            from timewarp.modules.layers.kernel_attention import chebyshev_basis_function
+            cc = sd["flow.chain.0.scale_transformer.encoder_layers.0.self_attn.attention.cheb_coeffs"]
+            out["scores"] = compute_kernel_attention_scores(
+                query=x - com, key=x - com, masked_elements=mask, lengthscales=ls,
+                basis_function=lambda s_: chebyshev_basis_function(s_, cfg.cheb_order, cc, cfg.force_asymptotic_zero)).numpy()
+        else:
+          out["scores"] = compute_kernel_attention_scores(query=x - com, key=x - com, masked_elements=mask, lengthscales=ls).numpy()
 
         # sampling, S=1 over the whole batch (exploration.py shape) -- same RNG consumption as the reference
         torch.manual_seed(1234 + seed)
@@ -238,6 +256,19 @@ TINY_LEARNABLE = OracleConfig(atom_embedding_dim=8, latent_mlp_hidden_dims=[24],
                               d_model=16, dim_feedforward=32, lengthscales=[0.3, 1.0], attention_type="learnable_kernel")
 
 
+TINY_CHEB = OracleConfig(atom_embedding_dim=8, latent_mlp_hidden_dims=[24], num_coupling_layers=4, num_transformer_layers=2,
+                         d_model=16, dim_feedforward=32, lengthscales=[0.3, 1.0], attention_type="chebyshev_kernel", cheb_order=6,
+                         force_asymptotic_zero=True)
+FULL_CHEB = OracleConfig(attention_type="chebyshev_kernel", cheb_order=12, force_asymptotic_zero=False)
+
+
+def chebyshev_cases():
+    """`chebyshev_kernel` attention: per-layer Chebyshev-rational basis functions, no score sharing."""
+    ad = alanine_dipeptide()
+    run_case("tiny_ad_chebyshev", TINY_CHEB, ad, B=3, seed=23, lengths=[22, 15, 9], sample_S=3, trace_layer0=False)
+    run_case("full_ad22_chebyshev", FULL_CHEB, ad, B=3, seed=24, sample_S=2, trace_layer0=False)
+
+
 def learnable_cases():
     """`learnable_kernel` attention: per-layer log_lengthscales, of which the reference uses only
     the first executed layer's (cache key quirk) -- layer 0 for log_likelihood, the last coupling layer when sampling."""
@@ -302,6 +333,9 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "learnable":
         learnable_cases()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "chebyshev":
+        chebyshev_cases()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "dataloader":
         dataloader_case()
         sys.exit(0)
@@ -316,5 +350,6 @@ if __name__ == "__main__":
     grad_case("grads_full_ad22", FULL, ad, B=4, seed=3)
     grad_case("grads_full_ad22_ragged", FULL, ad, B=3, seed=4, lengths=[22, 17, 12])
     learnable_cases()
+    chebyshev_cases()
     dataloader_case()
 

@@ -6,7 +6,7 @@ import pytest
 import torch
 
 from oracle import flow_oracle as fo
-from tests.common import EMPTY_ADJ, EMPTY_EBI, FULL_L, FULL_O, TINY_L, TINY_O, build_model, load_golden
+from tests.common import EMPTY_ADJ, EMPTY_EBI, FULL_C, FULL_L, FULL_O, TINY_C, TINY_L, TINY_O, build_model, load_golden
 
 pytestmark = pytest.mark.gpu
 REL = 1e-4  # north_star tolerance
@@ -14,7 +14,8 @@ REL = 1e-4  # north_star tolerance
 CASES = [("tiny_ad_ragged", TINY_O, "fp32"), ("tiny_ad", TINY_O, "fp32"), ("full_ad22", FULL_O, "fp32"),
          ("full_ad22_ragged", FULL_O, "fp32"), ("full_2olx65", FULL_O, "fp32")]
 # learnable_kernel attention: the golden files carry no layer-0 trace; the lengthscales differ per layer and direction
-LEARNABLE = [("tiny_ad_learnable", TINY_L, "fp32"), ("full_ad22_learnable", FULL_L, "fp32"), ("full_ad22_learnable", FULL_L, "bf16x3")]
+LEARNABLE = [("tiny_ad_learnable", TINY_L, "fp32"), ("full_ad22_learnable", FULL_L, "fp32"), ("full_ad22_learnable", FULL_L, "bf16x3"),
+             ("tiny_ad_chebyshev", TINY_C, "fp32"), ("full_ad22_chebyshev", FULL_C, "fp32"), ("full_ad22_chebyshev", FULL_C, "bf16x3")]
 
 
 def _kw(g, dev="cuda", rows=slice(None)):
@@ -200,3 +201,27 @@ def test_learnable_kernel_module_surface():
     m.train()
     with pytest.raises(NotImplementedError):
         m(y_coords=g["y_coords"].cuda(), y_velocs=g["y_velocs"].cuda(), **_kw(g))
+
+
+def test_chebyshev_kernel_module_surface():
+    """State-dict keys / shapes of the reference's LearnableChebyshevKernelAttention; the initial coefficients are the
+    exp(-s) expansion, so a freshly built chebyshev model scores like the Gaussian kernel (tests/test_kernel_attention.py:163-208)."""
+    g = load_golden("tiny_ad_chebyshev")
+    m, sd = build_model(TINY_C, "fp32", int(g["weight_seed"]))
+    assert set(m.state_dict().keys()) == set(sd.keys())
+    assert m.state_dict()["flow.chain.2.shift_transformer.encoder_layers.1.self_attn.attention.cheb_coeffs"].shape == (2, 6)
+    import timewarp_b200 as tw
+    from tests.common import model_config
+    import dataclasses
+    full = dataclasses.replace(TINY_C, cheb_order=32, force_asymptotic_zero=False)
+    fresh = tw.custom_transformer_nvp_constructor(model_config(full, "fp32")).cuda().eval()
+    gauss = tw.custom_transformer_nvp_constructor(model_config(TINY_O, "fp32")).cuda().eval()
+    gauss.load_state_dict({k: v for k, v in fresh.state_dict().items() if not k.endswith("cheb_coeffs")})
+    kw = _kw(g)
+    with torch.no_grad():
+        a = fresh.log_likelihood(y_coords=g["y_coords"].cuda(), y_velocs=g["y_velocs"].cuda(), **kw)
+        b = gauss.log_likelihood(y_coords=g["y_coords"].cuda(), y_velocs=g["y_velocs"].cuda(), **kw)
+    assert_rel(a, b, rel=1e-4, what="initial Chebyshev coefficients == Gaussian kernel")
+    m.train()
+    with pytest.raises(Exception):
+        m(y_coords=g["y_coords"].cuda(), y_velocs=g["y_velocs"].cuda(), **kw)

@@ -17,6 +17,12 @@ TINY_L = fo.OracleConfig(atom_embedding_dim=8, latent_mlp_hidden_dims=[24], num_
                          d_model=16, dim_feedforward=32, lengthscales=[0.3, 1.0], attention_type="learnable_kernel")
 FULL_L = fo.OracleConfig(attention_type="learnable_kernel")
 LEARNABLE = [("tiny_ad_learnable", TINY_L), ("full_ad22_learnable", FULL_L)]
+# `chebyshev_kernel` attention: a Chebyshev-rational basis function per attention layer, no score sharing between layers
+TINY_C = fo.OracleConfig(atom_embedding_dim=8, latent_mlp_hidden_dims=[24], num_coupling_layers=4, num_transformer_layers=2,
+                         d_model=16, dim_feedforward=32, lengthscales=[0.3, 1.0], attention_type="chebyshev_kernel", cheb_order=6,
+                         force_asymptotic_zero=True)
+FULL_C = fo.OracleConfig(attention_type="chebyshev_kernel", cheb_order=12, force_asymptotic_zero=False)
+CHEBYSHEV = [("tiny_ad_chebyshev", TINY_C), ("full_ad22_chebyshev", FULL_C)]
 
 
 def load(golden_dir, name):
@@ -24,7 +30,7 @@ def load(golden_dir, name):
     return {k: torch.from_numpy(d[k]) for k in d.files}
 
 
-@pytest.mark.parametrize("name,cfg", CASES + LEARNABLE)
+@pytest.mark.parametrize("name,cfg", CASES + LEARNABLE + CHEBYSHEV)
 def test_log_likelihood_and_loss(golden_dir, name, cfg):
     g = load(golden_dir, name)
     sd = fo.synth_state_dict(cfg, int(g["weight_seed"]))
@@ -60,7 +66,7 @@ def test_scores_and_layer0(golden_dir, name, cfg):
     torch.testing.assert_close(shift, g["layer0_shift"], rtol=1e-5, atol=1e-6)
 
 
-@pytest.mark.parametrize("name,cfg", CASES + LEARNABLE)
+@pytest.mark.parametrize("name,cfg", CASES + LEARNABLE + CHEBYSHEV)
 def test_sampling(golden_dir, name, cfg):
     g = load(golden_dir, name)
     sd = fo.synth_state_dict(cfg, int(g["weight_seed"]))
@@ -112,3 +118,20 @@ def test_learnable_scores_use_first_executed_layer(golden_dir, name, cfg):
     # the layers really differ (otherwise the quirk would be untested)
     ls_last = torch.exp(sd[f"flow.chain.{cfg.num_coupling_layers - 1}.scale_transformer.encoder_layers.0.self_attn.attention.log_lengthscales"])
     assert (ls0 - ls_last).abs().max() > 1e-2
+
+
+@pytest.mark.parametrize("name,cfg", CHEBYSHEV)
+def test_chebyshev_scores(golden_dir, name, cfg):
+    """Scores of the first attention layer vs the reference's chebyshev_basis_function; the known answer of the reference's
+    tests/test_kernel_attention.py:163-208 -- the initial coefficients reproduce exp(-s) -- holds for the restated basis."""
+    g = load(golden_dir, name)
+    sd = fo.synth_state_dict(cfg, int(g["weight_seed"]))
+    mask = g["masked_elements"]
+    xc = g["x_coords"] - fo.centre_of_mass(g["x_coords"], mask)
+    cc = sd["flow.chain.0.scale_transformer.encoder_layers.0.self_attn.attention.cheb_coeffs"]
+    sc = fo.kernel_attention_scores(xc, mask, torch.tensor(cfg.lengthscales), cheb_coeffs=cc, force_asymptotic_zero=cfg.force_asymptotic_zero)
+    torch.testing.assert_close(sc, g["scores"], rtol=1e-5, atol=1e-6)
+    s_ = torch.linspace(0.0, 3.0, 50)[None, None, None, :]
+    full = torch.tensor(fo.CHEB_COEFFS_EXPMX)[None, :]
+    approx = fo.chebyshev_basis(s_, full, False)
+    assert (approx - torch.exp(-(s_**2))).abs().max() < 1e-5

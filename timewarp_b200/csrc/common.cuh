@@ -68,6 +68,31 @@ struct Arena {
   bool ok() const { return off <= cap; }
 };
 
+// Basis function of the kernel attention weights for a scaled distance a = d / l  (kernel_attention.py:9-66):
+// Gaussian exp(-a^2), or (coef != nullptr) the Chebyshev-rational expansion sum_c coef[c] R_c(a^2),
+// R_n(y) = T_n((y - 1) / (y + 1)) by the three-term recursion; `mean` = per-head coefficient mean when the
+// expansion is forced to vanish at infinity.
+__device__ __forceinline__ float attention_basis(float a, const float* __restrict__ coef, int order, float mean) {
+  if (coef == nullptr) return expf(-(a * a));
+  const float y = a * a;
+  const float rf = (y - 1.0f) / (y + 1.0f);
+  float rprev = 1.0f, rcur = rf;
+  float acc = (coef[0] - mean);
+  if (order >= 2) acc = fmaf(coef[1] - mean, rcur, acc);
+  for (int c = 2; c < order; c++) {
+    const float rnext = 2.0f * rf * rcur - rprev;
+    acc = fmaf(coef[c] - mean, rnext, acc);
+    rprev = rcur, rcur = rnext;
+  }
+  return acc;
+}
+__device__ __forceinline__ float cheb_mean(const float* __restrict__ coef, int order, int force_zero) {
+  if (coef == nullptr || !force_zero) return 0.f;
+  float m = 0.f;
+  for (int c = 0; c < order; c++) m += coef[c];
+  return m / (float)order;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

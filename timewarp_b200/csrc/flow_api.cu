@@ -31,6 +31,9 @@ static int validate_cfg(const tw_flow_config* c) {
   TW_CHECK_ARG(c->num_heads >= 1 && c->num_heads <= TW_MAX_HEADS, "num_heads out of range");
   TW_CHECK_ARG(c->num_atom_types >= 1, "bad num_atom_types");
   TW_CHECK_ARG(c->precision >= TW_PRECISION_FP32 && c->precision <= TW_PRECISION_BF16, "unknown precision");
+  TW_CHECK_ARG(c->attention_type == TW_ATTENTION_KERNEL || c->attention_type == TW_ATTENTION_CHEBYSHEV, "unknown attention_type");
+  TW_CHECK_ARG(c->attention_type != TW_ATTENTION_CHEBYSHEV || (c->cheb_order >= 1 && c->cheb_order <= TW_MAX_CHEB_ORDER),
+               "cheb_order out of range (1..32)");
   if (c->precision != TW_PRECISION_FP32 && !tc_supported(c))
     return fail(TW_ERR_UNSUPPORTED, "tensor-core path needs d_model=128, dim_feedforward%%128==0, one MLP hidden layer of 256");
   return TW_OK;
@@ -109,19 +112,34 @@ static int conditioner(PassCtx& p, int k) {
     for (int s = 0; s < 2; s++) a.X[s] = cur[s], a.W[s] = p.pv.in_w(k, s, nh), a.b[s] = p.pv.in_b(k, s, nh), a.Y[s] = b.actA[s];
     TW_TRY(launch_linear(a, 2, M, D, cur_dim, cur_dim, 0, D, ACT_NONE, p.st));
   }
+  const bool cheb = p.pv.chebyshev();
+  const float* ls = p.pv.enc(0, 0, 0, 1);
   for (int t = 0; t < c->num_transformer_layers; t++) {
-    if ((tcs & TC_MIX) && (tcs & TC_ATTN_PROJ)) {
-      TW_TRY(tc_attention_layer(c, p.pv, k, t, tcx, b.actA, b.actB, p.n, p.n_cond, p.V, p.st));
-    } else {
-      Lin2 a{};
-      for (int s = 0; s < 2; s++) a.X[s] = b.actA[s], a.W[s] = p.pv.enc(k, s, t, 0), a.Y[s] = b.vals[s];
-      TW_TRY(launch_linear(a, 2, M, H * D, D, D, 0, H * D, ACT_NONE, p.st));
-      TW_TRY(launch_attn_mix(b.scores, b.vals[0], b.vals[1], b.att[0], b.att[1], 2, p.n, p.n_cond, p.V, H, D, p.st));
-      Lin2 o{};
-      for (int s = 0; s < 2; s++) o.X[s] = b.att[s], o.W[s] = p.pv.enc(k, s, t, 2), o.R[s] = b.actA[s], o.Y[s] = b.actB[s];
-      TW_TRY(launch_linear(o, 2, M, D, H * D, H * D, D, D, ACT_NONE, p.st));
-      TW_TRY(launch_layernorm(b.actB[0], b.actB[1], p.pv.enc(k, 0, t, 7), p.pv.enc(k, 1, t, 7), p.pv.enc(k, 0, t, 8),
-                              p.pv.enc(k, 1, t, 8), 2, M, D, c->layer_norm_eps, p.st));
+    // chebyshev_kernel: every attention layer of every network has its own basis function, hence its own scores
+    // (the reference's cache key contains the per-module basis lambda, kernel_attention.py:333-335): the scores are
+    // recomputed here and the two networks run one after the other.  Otherwise one score set serves the whole pass.
+    for (int pass = 0; pass < (cheb ? 2 : 1); pass++) {
+      const int only = cheb ? pass : -1;
+      if ((tcs & TC_MIX) && (tcs & TC_ATTN_PROJ)) {
+        if (cheb) TW_TRY(tc_begin_pass_direct(c, tcx, b.xc, p.mask, ls, p.n_cond, p.V, p.st, p.pv.cheb(k, only, t), false));
+        TW_TRY(tc_attention_layer(c, p.pv, k, t, tcx, b.actA, b.actB, p.n, p.n_cond, p.V, p.st, nullptr, only));
+      } else {
+        if (cheb)
+          TW_TRY(launch_scores(b.xc, p.mask, ls, p.n_cond, p.V, H, b.scores, p.st, p.pv.cheb(k, only, t), c->cheb_order,
+                               c->force_asymptotic_zero));
+        const int s0 = cheb ? only : 0, s1 = cheb ? only : 1, nets = cheb ? 1 : 2;
+        Lin2 a{};
+        a.X[0] = b.actA[s0], a.W[0] = p.pv.enc(k, s0, t, 0), a.Y[0] = b.vals[s0];
+        a.X[1] = b.actA[s1], a.W[1] = p.pv.enc(k, s1, t, 0), a.Y[1] = b.vals[s1];
+        TW_TRY(launch_linear(a, nets, M, H * D, D, D, 0, H * D, ACT_NONE, p.st));
+        TW_TRY(launch_attn_mix(b.scores, b.vals[s0], b.vals[s1], b.att[s0], b.att[s1], nets, p.n, p.n_cond, p.V, H, D, p.st));
+        Lin2 o{};
+        o.X[0] = b.att[s0], o.W[0] = p.pv.enc(k, s0, t, 2), o.R[0] = b.actA[s0], o.Y[0] = b.actB[s0];
+        o.X[1] = b.att[s1], o.W[1] = p.pv.enc(k, s1, t, 2), o.R[1] = b.actA[s1], o.Y[1] = b.actB[s1];
+        TW_TRY(launch_linear(o, nets, M, D, H * D, H * D, D, D, ACT_NONE, p.st));
+        TW_TRY(launch_layernorm(b.actB[s0], b.actB[s1], p.pv.enc(k, s0, t, 7), p.pv.enc(k, s1, t, 7), p.pv.enc(k, s0, t, 8),
+                                p.pv.enc(k, s1, t, 8), nets, M, D, c->layer_norm_eps, p.st));
+      }
     }
     if (tcs & TC_FFN) {
       TW_TRY(tc_ffn_layer(c, p.pv, k, t, tcx, b.actB, b.actA, M, p.st));  // fused linear1+ReLU+linear2+residual+LN2
@@ -166,6 +184,10 @@ static int begin_pass(PassCtx& p, const float* x_coords) {
   TW_TRY(launch_prep(x_coords, p.mask, p.n_cond, p.V, p.fb.xc, p.fb.com, p.st));
   // lengthscales of chain[0].scale_transformer.encoder_layers[0] (cache key maps lengthscales -> 0)
   const float* ls = p.pv.enc(0, 0, 0, 1);
+  if (p.pv.chebyshev()) {  // scores are per attention layer (conditioner()); only the per-pass scratch reset happens here
+    if (p.c->precision != TW_PRECISION_FP32) TW_TRY(tc_begin_pass(p.c, p.pv, p.fb.tc, nullptr, p.mask, p.n, p.n_cond, p.V, p.st));
+    return TW_OK;
+  }
   if (p.c->precision != TW_PRECISION_FP32 && tc_supported(p.c) && tc_scores_direct_supported(p.V))
     return tc_begin_pass_direct(p.c, p.fb.tc, p.fb.xc, p.mask, ls, p.n_cond, p.V, p.st);  // no fp32 score tensor
   TW_TRY(launch_scores(p.fb.xc, p.mask, ls, p.n_cond, p.V, p.c->num_heads, p.fb.scores, p.st));
@@ -265,8 +287,12 @@ int tw_flow_scale_shift(const tw_flow_config* cfg, const void* const* params, in
   TW_CUDA(cudaMemcpyAsync(p.fb.xc, x_coords_centred, zb, cudaMemcpyDeviceToDevice, p.st));
   TW_CUDA(cudaMemcpyAsync(p.fb.zc, z_coords, zb, cudaMemcpyDeviceToDevice, p.st));
   TW_CUDA(cudaMemcpyAsync(p.fb.zv, z_velocs, zb, cudaMemcpyDeviceToDevice, p.st));
-  TW_TRY(launch_scores(p.fb.xc, mask, p.pv.enc(0, 0, 0, 1), B, (int)V, cfg->num_heads, p.fb.scores, p.st));
-  if (cfg->precision != TW_PRECISION_FP32) TW_TRY(tc_begin_pass(cfg, p.pv, p.fb.tc, p.fb.scores, mask, B, B, (int)V, p.st));
+  if (p.pv.chebyshev()) {
+    if (cfg->precision != TW_PRECISION_FP32) TW_TRY(tc_begin_pass(cfg, p.pv, p.fb.tc, nullptr, mask, B, B, (int)V, p.st));
+  } else {
+    TW_TRY(launch_scores(p.fb.xc, mask, p.pv.enc(0, 0, 0, 1), B, (int)V, cfg->num_heads, p.fb.scores, p.st));
+    if (cfg->precision != TW_PRECISION_FP32) TW_TRY(tc_begin_pass(cfg, p.pv, p.fb.tc, p.fb.scores, mask, B, B, (int)V, p.st));
+  }
   TW_TRY(conditioner(p, layer_idx));
   return launch_coupling(p.fb.st[0], p.fb.st[1], nullptr, mask, nullptr, B, B, (int)V, 0, out_scale, out_shift, p.st);
 }

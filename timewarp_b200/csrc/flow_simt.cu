@@ -256,7 +256,7 @@ int launch_prep(const float* x, const uint8_t* mask, int64_t n_cond, int V, floa
 // distances from direct differences (exactly 0 on the diagonal).
 __global__ void __launch_bounds__(256) k_scores(const float* __restrict__ xc, const uint8_t* __restrict__ mask,
                                                 const float* __restrict__ ls, int64_t B, int V, int H,
-                                                float* __restrict__ out) {
+                                                float* __restrict__ out, const float* __restrict__ cheb, int order, int force_zero) {
   int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= B * V) return;
   const int lane = threadIdx.x & 31;
@@ -267,13 +267,15 @@ __global__ void __launch_bounds__(256) k_scores(const float* __restrict__ xc, co
   const float xi = xb[i * 3], yi = xb[i * 3 + 1], zi = xb[i * 3 + 2];
   for (int h = 0; h < H; h++) {
     const float l = ls[h];
+    const float* coef = cheb ? cheb + (size_t)h * order : nullptr;
+    const float cmean = cheb_mean(coef, order, force_zero);
     float* o = out + ((b * H + h) * V + i) * (int64_t)V;
     float sum = 0.f;
     for (int j = lane; j < V; j += 32) {
       float dx = xi - xb[j * 3], dy = yi - xb[j * 3 + 1], dz = zi - xb[j * 3 + 2];
       float d = sqrtf(dx * dx + dy * dy + dz * dz);
       float a = d / l;
-      float w = mb[j] ? 0.f : expf(-(a * a));
+      float w = mb[j] ? 0.f : attention_basis(a, coef, order, cmean);
       o[j] = w;
       sum += fabsf(w);
     }
@@ -282,10 +284,11 @@ __global__ void __launch_bounds__(256) k_scores(const float* __restrict__ xc, co
   }
 }
 
-int launch_scores(const float* xc, const uint8_t* mask, const float* ls, int64_t B, int V, int H, float* out, cudaStream_t st) {
+int launch_scores(const float* xc, const uint8_t* mask, const float* ls, int64_t B, int V, int H, float* out, cudaStream_t st,
+                  const float* cheb, int order, int force_zero) {
   if (B == 0) return TW_OK;
   int64_t rows = B * V;
-  k_scores<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(xc, mask, ls, B, V, H, out);
+  k_scores<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(xc, mask, ls, B, V, H, out, cheb, order, force_zero);
   TW_LAUNCH_CHECK();
   return TW_OK;
 }

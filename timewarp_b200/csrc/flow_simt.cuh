@@ -12,7 +12,11 @@ struct ParamView {
   const void* const* p;
   __host__ int per_mlp() const { return 2 * (c->num_mlp_hidden + 1); }
   __host__ int per_net() const { return 2 * per_mlp() + 11 * c->num_transformer_layers; }
-  __host__ int total() const { return 3 + c->num_coupling_layers * 2 * per_net(); }
+  __host__ int regular() const { return 3 + c->num_coupling_layers * 2 * per_net(); }
+  __host__ bool chebyshev() const { return c->attention_type == TW_ATTENTION_CHEBYSHEV; }
+  __host__ int total() const { return regular() + (chebyshev() ? c->num_coupling_layers * 2 * c->num_transformer_layers : 0); }
+  // chebyshev_kernel: cheb_coeffs [H, cheb_order] of encoder layer t of network `net` of coupling layer k (trailing section)
+  __host__ const float* cheb(int k, int net, int t) const { return at(regular() + (k * 2 + net) * c->num_transformer_layers + t); }
   __host__ const float* at(int i) const { return (const float*)p[i]; }
   __host__ int net_base(int k, int net) const { return 3 + (k * 2 + net) * per_net(); }
   __host__ const float* embed() const { return at(0); }
@@ -48,7 +52,9 @@ int launch_layernorm(float* x0, float* x1, const float* g0, const float* g1, con
 int launch_attn_mix(const float* scores, const float* v0, const float* v1, float* o0, float* o1, int nets, int64_t n,
                     int64_t n_cond, int V, int H, int Dv, cudaStream_t st);
 int launch_prep(const float* x, const uint8_t* mask, int64_t n_cond, int V, float* xc, float* com, cudaStream_t st);
-int launch_scores(const float* xc, const uint8_t* mask, const float* ls, int64_t B, int V, int H, float* out, cudaStream_t st);
+// cheb != nullptr: Chebyshev-rational basis with coefficients [H, order] instead of the Gaussian
+int launch_scores(const float* xc, const uint8_t* mask, const float* ls, int64_t B, int V, int H, float* out, cudaStream_t st,
+                  const float* cheb = nullptr, int order = 0, int force_zero = 0);
 int launch_features(const float* embed, const int64_t* atom_types, const float* xc, const float* xv, const float* z_other,
                     int64_t n, int64_t n_cond, int V, int E, int n_types, float* feat, cudaStream_t st);
 // forward: z = z*exp(s)+t ; reverse: z = (z-t)/exp(s); delta -= (+/-) sum log(exp(s)) over unmasked atoms

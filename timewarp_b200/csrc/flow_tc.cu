@@ -1268,7 +1268,8 @@ __global__ void __launch_bounds__(256) k_scores_img(const float* __restrict__ sc
 // image of k_scores_img through a shared-memory staging buffer (16-byte coalesced stores).
 __global__ void __launch_bounds__(256) k_scores_direct_img(const float* __restrict__ xc, const uint8_t* __restrict__ mask,
                                                            const float* __restrict__ ls, int V, int VP, int H,
-                                                           uint8_t* __restrict__ img) {
+                                                           uint8_t* __restrict__ img, const float* __restrict__ cheb, int order,
+                                                           int force_zero) {
   extern __shared__ __align__(16) uint8_t sm_raw[];
   float* xs = reinterpret_cast<float*>(sm_raw);                  // [V][3]
   uint8_t* ms = sm_raw + (((size_t)V * 12 + 15) & ~(size_t)15);  // [V]
@@ -1281,6 +1282,8 @@ __global__ void __launch_bounds__(256) k_scores_direct_img(const float* __restri
   __syncthreads();
   for (int h = 0; h < H; h++) {
     const float l = ls[h];
+    const float* coef = cheb ? cheb + (size_t)h * order : nullptr;
+    const float cmean = cheb_mean(coef, order, force_zero);
     for (uint32_t o = tid * 16; o < 2 * mat; o += blockDim.x * 16) *reinterpret_cast<uint4*>(stg + o) = make_uint4(0, 0, 0, 0);
     __syncthreads();
     for (int i = warp; i < V; i += 8) {
@@ -1295,7 +1298,7 @@ __global__ void __launch_bounds__(256) k_scores_direct_img(const float* __restri
           float dx = xi - xs[j * 3], dy = yi - xs[j * 3 + 1], dz = zi - xs[j * 3 + 2];
           float d = sqrtf(dx * dx + dy * dy + dz * dz);
           float a = d / l;
-          w[u] = ms[j] ? 0.f : expf(-(a * a));
+          w[u] = ms[j] ? 0.f : attention_basis(a, coef, order, cmean);
           sum += fabsf(w[u]);
         }
       }
@@ -2812,7 +2815,7 @@ int tc_scores_images(const tw_flow_config* c, const float* scores, int64_t n_con
 int tc_begin_pass(const tw_flow_config* c, const ParamView&, TcScratch& tc, const float* scores, const uint8_t*, int64_t,
                   int64_t n_cond, int V, cudaStream_t st) {
   if (tc.ffn_tail) TW_CUDA(cudaMemsetAsync(tc.ffn_tail, 0, kFfnTailBytes, st));
-  if (!(tc_stage_mask() & TC_MIX)) return TW_OK;
+  if (!(tc_stage_mask() & TC_MIX) || scores == nullptr) return TW_OK;
   return tc_scores_images(c, scores, n_cond, V, tc.scores_img, 0, st);
 }
 
@@ -2822,8 +2825,8 @@ bool tc_scores_direct_supported(int V) {  // the CUDA-core attention fallback (b
 
 // Inference: score images straight from the centred conditioning coordinates (no fp32 score tensor).
 int tc_begin_pass_direct(const tw_flow_config* c, TcScratch& tc, const float* xc, const uint8_t* mask, const float* lengthscales,
-                         int64_t n_cond, int V, cudaStream_t st) {
-  if (tc.ffn_tail) TW_CUDA(cudaMemsetAsync(tc.ffn_tail, 0, kFfnTailBytes, st));
+                         int64_t n_cond, int V, cudaStream_t st, const float* cheb, bool clear_tail) {
+  if (tc.ffn_tail && clear_tail) TW_CUDA(cudaMemsetAsync(tc.ffn_tail, 0, kFfnTailBytes, st));
   const int VP = pad16(V);
   const size_t smem = (((size_t)V * 12 + 15) & ~(size_t)15) + (((size_t)V + 15) & ~(size_t)15) + (size_t)VP * VP * 4;
   static bool attr_done = false;
@@ -2832,7 +2835,8 @@ int tc_begin_pass_direct(const tw_flow_config* c, TcScratch& tc, const float* xc
     attr_done = true;
   }
   if (n_cond < 1) return TW_OK;
-  k_scores_direct_img<<<(unsigned)n_cond, 256, smem, st>>>(xc, mask, lengthscales, V, VP, c->num_heads, tc.scores_img);
+  k_scores_direct_img<<<(unsigned)n_cond, 256, smem, st>>>(xc, mask, lengthscales, V, VP, c->num_heads, tc.scores_img, cheb,
+                                                           c->cheb_order, c->force_asymptotic_zero);
   TW_LAUNCH_CHECK();
   return TW_OK;
 }
@@ -2845,7 +2849,7 @@ size_t tc_mixed_img_bytes(const tw_flow_config* c, int64_t M) { return (size_t)(
 
 // mixed_h = A_h x for every head, written as A-operand images (both networks)
 int tc_mix(const tw_flow_config* c, const float* const x[2], uint8_t* const img[2], const uint8_t* scores_img, int64_t n,
-           int64_t n_cond, int V, cudaStream_t st) {
+           int64_t n_cond, int V, cudaStream_t st, int nets) {
   static bool attr_done = false;
   const int VP = pad16(V), H = c->num_heads;
   const uint32_t stage_stride = (uint32_t)((2 * VP * VP * 2 + 1023) & ~1023);
@@ -2863,9 +2867,10 @@ int tc_mix(const tw_flow_config* c, const float* const x[2], uint8_t* const img[
   a.scores_img = scores_img;
   a.n = n, a.n_cond = n_cond, a.V = V, a.VP = VP, a.H = H, a.n_stages = mix_stages;
   a.trace = g_mix_trace;
-  int gx = (int)(n < 74 ? n : 74);
+  const int per_net = nets == 1 ? 148 : 74;  // one network alone (chebyshev_kernel: per-network scores) gets every SM
+  int gx = (int)(n < per_net ? n : per_net);
   if (gx < 1) return TW_OK;
-  dim3 grid(gx, 2);
+  dim3 grid(gx, nets);
   static int use_tok = -1;
   if (use_tok < 0) {
     const char* e = getenv("TW_MIX_TOK");  // bring-up switch: 0 = feature-major kernel for every atom count
@@ -2895,10 +2900,17 @@ int tc_mix(const tw_flow_config* c, const float* const x[2], uint8_t* const img[
 }
 
 // out = LN1(x + attention(x)) for both networks of encoder layer t; `pre` (optional) receives the pre-LayerNorm sum
-int tc_attention_layer(const tw_flow_config* c, const ParamView& pv, int k, int t, const TcScratch& tc, float* const x[2],
-                       float* const out[2], int64_t n, int64_t n_cond, int V, cudaStream_t st, float* const* pre) {
+int tc_attention_layer(const tw_flow_config* c, const ParamView& pv, int k, int t, const TcScratch& tc, float* const x_in[2],
+                       float* const out_in[2], int64_t n, int64_t n_cond, int V, cudaStream_t st, float* const* pre, int only_net) {
   static bool attr_done = false;
   const int H = c->num_heads;
+  // only_net >= 0: run ONE network (its pointers in both slots, grid.y = 1) -- chebyshev_kernel attention has a different
+  // score image per network and layer, written to tc.scores_img right before this call
+  const int nets = only_net >= 0 ? 1 : 2;
+  const int net_of[2] = {only_net >= 0 ? only_net : 0, only_net >= 0 ? only_net : 1};
+  float* const x[2] = {x_in[net_of[0]], x_in[net_of[1]]};
+  float* const out[2] = {out_in[net_of[0]], out_in[net_of[1]]};
+  const int per_net = nets == 1 ? 148 : 74;
   const int proj_smem = kProjStages * kProjStageBytes + 1024 + 256 + 1024;
   if (!attr_done) {
     TW_CUDA(cudaFuncSetAttribute(k_proj_tc<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, proj_smem));
@@ -2923,13 +2935,13 @@ int tc_attention_layer(const tw_flow_config* c, const ParamView& pv, int k, int 
       AttnArgs a{};
       for (int s = 0; s < 2; s++) {
         a.x[s] = x[s], a.out[s] = out[s];
-        a.wc[s] = tc.packed + L.net_offset(k, s) + L.enc0 + (size_t)t * L.enc_stride + L.enc_wc;
-        a.gamma[s] = pv.enc(k, s, t, 7), a.beta[s] = pv.enc(k, s, t, 8);
+        a.wc[s] = tc.packed + L.net_offset(k, net_of[s]) + L.enc0 + (size_t)t * L.enc_stride + L.enc_wc;
+        a.gamma[s] = pv.enc(k, net_of[s], t, 7), a.beta[s] = pv.enc(k, net_of[s], t, 8);
       }
       a.scores_img = tc.scores_img;
       a.n = n, a.n_cond = n_cond, a.V = V, a.VP = VP, a.H = H, a.eps = c->layer_norm_eps;
       a.trace = g_attn_trace;
-      dim3 grid((unsigned)(n < 74 ? n : 74), 2);
+      dim3 grid((unsigned)(n < per_net ? n : per_net), nets);
       if (c->precision == TW_PRECISION_BF16X3)
         k_attn_fused<3><<<grid, kAttnThreads, fused_smem, st>>>(a);
       else
@@ -2938,22 +2950,23 @@ int tc_attention_layer(const tw_flow_config* c, const ParamView& pv, int k, int 
       return TW_OK;
     }
   }
-  TW_TRY(tc_mix(c, x, tc.mixed_img, tc.scores_img, n, n_cond, V, st));
+  uint8_t* const mixed[2] = {tc.mixed_img[net_of[0]], tc.mixed_img[net_of[1]]};
+  TW_TRY(tc_mix(c, x, mixed, tc.scores_img, n, n_cond, V, st, nets));
   {
     ProjArgs a{};
     for (int s = 0; s < 2; s++) {
-      a.a_img[s] = tc.mixed_img[s];
-      a.w[s] = tc.packed + L.net_offset(k, s) + L.enc0 + (size_t)t * L.enc_stride + L.enc_wc;
+      a.a_img[s] = mixed[s];
+      a.w[s] = tc.packed + L.net_offset(k, net_of[s]) + L.enc0 + (size_t)t * L.enc_stride + L.enc_wc;
       a.resid[s] = x[s];
       a.out[s] = out[s];
-      a.pre[s] = pre ? pre[s] : nullptr;
-      a.gamma[s] = pv.enc(k, s, t, 7);
-      a.beta[s] = pv.enc(k, s, t, 8);
+      a.pre[s] = pre ? pre[net_of[s]] : nullptr;
+      a.gamma[s] = pv.enc(k, net_of[s], t, 7);
+      a.beta[s] = pv.enc(k, net_of[s], t, 8);
     }
     a.M = M, a.KB = H * 2, a.eps = c->layer_norm_eps;
     int64_t n_tiles = (M + 127) / 128;
-    int gx = (int)(n_tiles < 74 ? n_tiles : 74);
-    dim3 grid(gx, 2);
+    int gx = (int)(n_tiles < per_net ? n_tiles : per_net);
+    dim3 grid(gx, nets);
     if (c->precision == TW_PRECISION_BF16X3)
       k_proj_tc<3><<<grid, 192, proj_smem, st>>>(a);
     else

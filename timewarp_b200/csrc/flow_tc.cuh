@@ -44,17 +44,18 @@ int tc_begin_pass(const tw_flow_config* c, const ParamView& pv, TcScratch& tc, c
                   int64_t n, int64_t n_cond, int V, cudaStream_t st);
 bool tc_scores_direct_supported(int V);
 int tc_begin_pass_direct(const tw_flow_config* c, TcScratch& tc, const float* xc, const uint8_t* mask, const float* lengthscales,
-                         int64_t n_cond, int V, cudaStream_t st);
+                         int64_t n_cond, int V, cudaStream_t st, const float* cheb = nullptr, bool clear_tail = true);
 size_t tc_packed_bytes(const tw_flow_config* c);
 void tc_set_ffn_trace(long long* buf);
 void tc_set_trace(int cls, long long* buf);  // 1 fused FFN, 2 mixing kernel  // debug: event trace of the fused FFN (see FfnArgs::trace)
 // fused FFN + residual + LayerNorm of encoder layer t for both networks: out = LN2(x + FFN(x))
 // out = LN1(x + sum_h W_c,h (A_h x)) for both networks (tensor-core mixing + projection)
 int tc_attention_layer(const tw_flow_config* c, const ParamView& pv, int k, int t, const TcScratch& tc, float* const x[2],
-                       float* const out[2], int64_t n, int64_t n_cond, int V, cudaStream_t st, float* const* pre = nullptr);
+                       float* const out[2], int64_t n, int64_t n_cond, int V, cudaStream_t st, float* const* pre = nullptr,
+                       int only_net = -1);
 // the mixing step alone (also used by the backward pass with the transposed score images)
 int tc_mix(const tw_flow_config* c, const float* const x[2], uint8_t* const img[2], const uint8_t* scores_img, int64_t n,
-           int64_t n_cond, int V, cudaStream_t st);
+           int64_t n_cond, int V, cudaStream_t st, int nets = 2);
 int tc_scores_images(const tw_flow_config* c, const float* scores, int64_t n_cond, int V, uint8_t* img, int transpose, cudaStream_t st);
 size_t tc_scores_img_bytes(const tw_flow_config* c, int64_t n_cond, int V);
 size_t tc_mixed_img_bytes(const tw_flow_config* c, int64_t M);

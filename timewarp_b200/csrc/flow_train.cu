@@ -677,6 +677,8 @@ static size_t carve_tape(const tw_flow_config* c, int64_t B, int V, void* base, 
 }
 
 static int check_train(const tw_flow_config* c, const void* const* params, int64_t B, int64_t V) {
+  if (c && c->attention_type != TW_ATTENTION_KERNEL)
+    return fail(TW_ERR_UNSUPPORTED, "the training path is built for the `kernel` attention only");
   TW_CHECK_ARG(c != nullptr && params != nullptr, "NULL cfg / params");
   if (c->precision == TW_PRECISION_FP32 || !tc_supported(c))
     return fail(TW_ERR_UNSUPPORTED, "the training path needs a tensor-core precision (bf16x3 / bf16) and the flagship layer sizes");

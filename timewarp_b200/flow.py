@@ -112,6 +112,8 @@ def _is_optional_grad(model, i: int) -> bool:
     cfg = model._cfg
     per_mlp = 2 * (cfg.num_mlp_hidden + 1)
     per_net = 2 * per_mlp + 11 * cfg.num_transformer_layers
+    if i >= 3 + cfg.num_coupling_layers * 2 * per_net:
+        return True  # trailing cheb_coeffs section
     j = (i - 3) % per_net
     return per_mlp <= j < per_mlp + 11 * cfg.num_transformer_layers and (j - per_mlp) % 11 == 1
 
@@ -185,6 +187,10 @@ class ConditionalFlowDensityModel(nn.Module):
                     ]  # fmt: skip
                 for lin in block.out_mlp.linears():
                     out += [lin.weight, lin.bias]
+        if self._cfg.attention_type == _lib.TW_ATTENTION_CHEBYSHEV:  # trailing section of the table (include/timewarp_b200.h)
+            for layer in self.flow.chain:
+                for block in (layer.scale_transformer, layer.shift_transformer):
+                    out += [enc.self_attn.attention.cheb_coeffs for enc in block.encoder_layers]
         return out
 
     def _param_table(self, device):

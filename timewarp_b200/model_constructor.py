@@ -43,6 +43,13 @@ def flow_config_from(config, precision=None) -> _lib.FlowConfig:
     c.num_atom_types = ELEMENT_VOCAB_SIZE
     c.layer_norm_eps = 1e-5
     c.precision = _lib.PRECISION[prec]
+    if enc.attention_type == "chebyshev_kernel":
+        assert enc.cheb_order is not None and enc.cheb_order >= 1 and enc.force_asymptotic_zero is not None
+        c.attention_type = _lib.TW_ATTENTION_CHEBYSHEV
+        c.cheb_order = int(enc.cheb_order)
+        c.force_asymptotic_zero = int(bool(enc.force_asymptotic_zero))
+    else:
+        c.attention_type = _lib.TW_ATTENTION_KERNEL
     return c
 
 

@@ -65,6 +65,33 @@ class LearnableLengthscaleKernelAttention(KernelAttention):
         self._out_projection = nn.Linear(value_dim * len(lengthscales), output_dim, bias=False)
 
 
+# Chebyshev-rational coefficients of exp(-s): the initial value of `cheb_coeffs` (kernel_attention.py:291-327; numerical
+# constants of the reference, data not code)
+CHEB_COEFFS_EXPMX = [
+    4.275836e-01, -5.464240e-01, 7.106222e-02, 5.473271e-02, 5.744192e-03, -7.926410e-03, -5.392865e-03, -1.210823e-03,
+    6.996851e-04, 8.686655e-04, 4.459163e-04, 7.084817e-05, -9.620444e-05, -1.110469e-04, -6.551055e-05, -1.875292e-05,
+    7.930955e-06, 1.553729e-05, 1.246072e-05, 6.282442e-06, 1.216243e-06, -1.468327e-06, -2.141963e-06, -1.694741e-06,
+    -9.063254e-07, -2.337215e-07, 1.609271e-07, 2.978384e-07, 2.700519e-07, 1.730454e-07, 7.272222e-08, 1.192814e-09,
+]  # fmt: skip
+
+
+class LearnableChebyshevKernelAttention(KernelAttention):
+    """modules/layers/kernel_attention.py:255-339: the basis function is a learnable Chebyshev-rational expansion
+    `sum_c cheb_coeffs[h, c] R_c((d / l_h)^2)`.  Same state-dict key and shape as the reference ([H, cheb_order]); the
+    reference builds the Parameter as an EXPANDED tensor whose heads share storage -- here every head owns its row."""
+
+    def __init__(self, *, value_dim: int, output_dim: int, lengthscales: Sequence[float], cheb_order: int,
+                 normalise_kernel_values: bool, force_asymptotic_zero: bool):
+        assert cheb_order >= 1
+        super().__init__(value_dim=value_dim, output_dim=output_dim, lengthscales=lengthscales,
+                         normalise_kernel_values=normalise_kernel_values)
+        take = min(len(CHEB_COEFFS_EXPMX), cheb_order)
+        coeffs = torch.tensor(CHEB_COEFFS_EXPMX[:take] + [0.0] * max(0, cheb_order - len(CHEB_COEFFS_EXPMX)), dtype=torch.float32)
+        self.cheb_coeffs = nn.Parameter(coeffs[None, :].repeat(len(lengthscales), 1), requires_grad=True)
+        self.cheb_order, self.force_asymptotic_zero = cheb_order, force_asymptotic_zero
+        self._out_projection = nn.Linear(value_dim * len(lengthscales), output_dim, bias=False)
+
+
 class KernelSelfAttention(_Container):
     """modules/layers/kernel_self_attention.py:12-48."""
 
@@ -89,11 +116,11 @@ class CustomTransformerEncoderLayer(_Container):
 
 
 def custom_attention_transformer_encoder_constructor(config) -> CustomTransformerEncoderLayer:
-    """modules/layers/custom_attention_encoder.py:140-219: `kernel` and `learnable_kernel` attention."""
-    if config.attention_type not in ("kernel", "learnable_kernel"):
+    """modules/layers/custom_attention_encoder.py:140-219: `kernel`, `learnable_kernel` and `chebyshev_kernel` attention."""
+    if config.attention_type not in ("kernel", "learnable_kernel", "chebyshev_kernel"):
         raise NotImplementedError(
-            f"attention_type={config.attention_type!r}: 'kernel' and 'learnable_kernel' are built ('chebyshev_kernel' and "
-            "'local' are SURVEY.md section 8f-3)"
+            f"attention_type={config.attention_type!r}: 'kernel', 'learnable_kernel' and 'chebyshev_kernel' are built "
+            "('local' is SURVEY.md section 8f-3)"
         )
     if float(config.dropout) != 0.0:
         raise NotImplementedError("dropout must be 0 (configs/kernel_transformer_nvp.yaml:27); no dropout kernel exists")
@@ -101,13 +128,21 @@ def custom_attention_transformer_encoder_constructor(config) -> CustomTransforme
     assert len(config.lengthscales) > 0
     assert config.normalise_kernel_values is not None
     # construction order == reference (attention first) so that seeded init is identical
-    attention_cls = {"kernel": KernelAttention, "learnable_kernel": LearnableLengthscaleKernelAttention}[config.attention_type]
-    attention = attention_cls(
-        value_dim=config.d_model,
-        output_dim=config.d_model,
-        lengthscales=list(config.lengthscales),
-        normalise_kernel_values=config.normalise_kernel_values,
-    )
+    if config.attention_type == "chebyshev_kernel":
+        assert config.cheb_order is not None and config.cheb_order >= 1
+        assert config.force_asymptotic_zero is not None
+        attention = LearnableChebyshevKernelAttention(
+            value_dim=config.d_model, output_dim=config.d_model, lengthscales=list(config.lengthscales),
+            cheb_order=config.cheb_order, normalise_kernel_values=config.normalise_kernel_values,
+            force_asymptotic_zero=config.force_asymptotic_zero)
+    else:
+        attention_cls = {"kernel": KernelAttention, "learnable_kernel": LearnableLengthscaleKernelAttention}[config.attention_type]
+        attention = attention_cls(
+            value_dim=config.d_model,
+            output_dim=config.d_model,
+            lengthscales=list(config.lengthscales),
+            normalise_kernel_values=config.normalise_kernel_values,
+        )
     self_attention = KernelSelfAttention(
         input_dim=config.d_model, num_heads=len(config.lengthscales), value_dim=config.d_model, attention=attention
     )
