@@ -61,11 +61,14 @@ typedef struct tw_flow_config {
   float layer_norm_eps;                       /* 1e-5                                           */
   int32_t precision;                          /* TW_PRECISION_*                                 */
   int32_t attention_type;                     /* TW_ATTENTION_*: 0 kernel (also learnable_kernel: the caller passes the effective
-                                                 lengthscales), 2 chebyshev_kernel (kernel_attention.py:255-339)   */
+                                                 lengthscales), 1 local, 2 chebyshev_kernel (kernel_attention.py:255-339) */
   int32_t cheb_order;                         /* chebyshev_kernel: 1..32 coefficients per head                     */
   int32_t force_asymptotic_zero;              /* chebyshev_kernel: subtract the per-head mean of the coefficients  */
+  float max_radius;                           /* local: neighbourhood radius in nm (local_self_attention.py:26)    */
 } tw_flow_config;
 #define TW_ATTENTION_KERNEL 0
+#define TW_ATTENTION_LOCAL 1 /* dot-product attention over the atoms within max_radius; per encoder layer the table slots
+                                [wv, lengthscales, wo] hold [qkv_proj.weight (H*3D x D), (ignored), output_proj.weight (D x H*D)] */
 #define TW_ATTENTION_CHEBYSHEV 2
 #define TW_MAX_CHEB_ORDER 32
 

@@ -42,6 +42,10 @@ class OracleConfig:
     attention_type: str = "kernel"
     cheb_order: int = 0
     force_asymptotic_zero: bool = False
+    # "local" (LocalSelfAttention, modules/layers/local_self_attention.py): dot-product attention over the atoms within
+    # max_radius; num_heads heads (no lengthscales)
+    max_radius: float = 0.0
+    num_heads: int = 0
 
 
 StateDict = Dict[str, Tensor]
@@ -129,8 +133,35 @@ def layer_norm(x: Tensor, w: Tensor, b: Tensor, eps: float) -> Tensor:
 
 # modules/layers/custom_attention_encoder.py:82-114 + kernel_self_attention.py:29-48
 # + kernel_attention.py:124-156,185-214
+# modules/layers/local_self_attention.py:46-119.  The reference gathers the (at most K) atoms within max_radius with topk and
+# softmaxes over them; restated as a dense masked softmax over all atoms (identical weights: every gathered atom beyond the
+# radius is masked to -inf there, and atoms not gathered are beyond the radius by construction of K).
+def local_self_attention(sd: StateDict, prefix: str, cfg: OracleConfig, src: Tensor, positions: Tensor, masked_elements: Tensor) -> Tensor:
+    B, V, D = src.shape
+    H = cfg.num_heads
+    qkv = torch.nn.functional.linear(src, sd[f"{prefix}.self_attn.qkv_proj.weight"]).reshape(B, V, H, 3 * D)
+    q, k, v = torch.split(qkv, [D, D, D], dim=-1)  # [B,V,H,D] each (key_query_dim = value_dim = d_model, custom_attention_encoder.py:146-153)
+    diff = positions[:, :, None, :] - positions[:, None, :, :]
+    dist = torch.sqrt((diff * diff).sum(-1))  # cdist(..., "donot_use_mm_for_euclid_dist") :62-64
+    pad = masked_elements[:, None, :] | masked_elements[:, :, None]
+    dist = dist.masked_fill(pad, math.inf)  # :67-70
+    outside = dist > cfg.max_radius  # :87-89 (neighbor_mask)
+    scores = torch.einsum("bihd,bjhd->bijh", q, k) / math.sqrt(D)  # :99-100
+    scores = scores.masked_fill(outside[..., None], -math.inf)
+    w = torch.softmax(scores, dim=-2)
+    w = torch.nan_to_num(w, nan=0.0).masked_fill(outside[..., None], 0.0)  # :104-109 (rows with no neighbour: zeros)
+    out = torch.einsum("bijh,bjhd->bihd", w, v).reshape(B, V, H * D)
+    return torch.nn.functional.linear(out, sd[f"{prefix}.self_attn.output_proj.weight"])
+
+
 def encoder_layer(sd: StateDict, prefix: str, cfg: OracleConfig, src: Tensor, scores) -> Tensor:
     B, V, D = src.shape
+    if isinstance(scores, tuple):  # ("local", positions, masked_elements)
+        src2 = local_self_attention(sd, prefix, cfg, src, scores[1], scores[2])
+        src = layer_norm(src + src2, sd[f"{prefix}.norm1.weight"], sd[f"{prefix}.norm1.bias"], cfg.layer_norm_eps)
+        h = torch.relu(torch.nn.functional.linear(src, sd[f"{prefix}.linear1.weight"], sd[f"{prefix}.linear1.bias"]))
+        src2 = torch.nn.functional.linear(h, sd[f"{prefix}.linear2.weight"], sd[f"{prefix}.linear2.bias"])
+        return layer_norm(src + src2, sd[f"{prefix}.norm2.weight"], sd[f"{prefix}.norm2.bias"], cfg.layer_norm_eps)
     if callable(scores):  # chebyshev_kernel: every attention layer has its own basis function -> its own scores
         scores = scores(prefix)
     H = scores.shape[1]
@@ -195,11 +226,15 @@ def sequential_flow(
     # network's first encoder layer of coupling layer 0 in the density direction and of the LAST coupling layer when sampling.
     first = cfg.num_coupling_layers - 1 if reverse else 0
     att = f"flow.chain.{first}.scale_transformer.encoder_layers.0.self_attn.attention"
-    if cfg.attention_type == "learnable_kernel":
+    if cfg.attention_type == "local":
+        ls = None
+    elif cfg.attention_type == "learnable_kernel":
         ls = torch.exp(sd[f"{att}.log_lengthscales"]).to(x_coords.dtype)
     else:
         ls = sd[f"{att}.lengthscales"].to(x_coords.dtype)
-    if cfg.attention_type == "chebyshev_kernel":
+    if cfg.attention_type == "local":
+        scores = ("local", x_coords, masked_elements)
+    elif cfg.attention_type == "chebyshev_kernel":
         # the basis function (a lambda per module, kernel_attention.py:333-335) is part of the cache key: no sharing
         def scores(prefix):
             return kernel_attention_scores(x_coords, masked_elements, ls, distance_mode,
@@ -347,7 +382,7 @@ def conditional_sample_with_logp(
 def state_dict_shapes(cfg: OracleConfig) -> Dict[str, Tuple[int, ...]]:
     """Key -> shape of the reference model's state_dict for `cfg`."""
     E, D, F = cfg.atom_embedding_dim, cfg.d_model, cfg.dim_feedforward
-    H = len(cfg.lengthscales)
+    H = cfg.num_heads if cfg.attention_type == "local" else len(cfg.lengthscales)
     hid = list(cfg.latent_mlp_hidden_dims)
     out: Dict[str, Tuple[int, ...]] = {
         "coords_prior_log_scale": (),
@@ -367,13 +402,18 @@ def state_dict_shapes(cfg: OracleConfig) -> Dict[str, Tuple[int, ...]]:
             add_mlp(f"{p}.in_mlp", E + 9, D)
             for t in range(cfg.num_transformer_layers):
                 q = f"{p}.encoder_layers.{t}"
-                out[f"{q}.self_attn.values_proj.weight"] = (H * D, D)
-                out[f"{q}.self_attn.attention.lengthscales"] = (H,)
+                if cfg.attention_type == "local":
+                    out[f"{q}.self_attn.qkv_proj.weight"] = (H * 3 * D, D)
+                    out[f"{q}.self_attn.output_proj.weight"] = (D, H * D)
+                else:
+                    out[f"{q}.self_attn.values_proj.weight"] = (H * D, D)
+                    out[f"{q}.self_attn.attention.lengthscales"] = (H,)
                 if cfg.attention_type == "learnable_kernel":
                     out[f"{q}.self_attn.attention.log_lengthscales"] = (H,)
                 if cfg.attention_type == "chebyshev_kernel":
                     out[f"{q}.self_attn.attention.cheb_coeffs"] = (H, cfg.cheb_order)
-                out[f"{q}.self_attn.attention._out_projection.weight"] = (D, H * D)
+                if cfg.attention_type != "local":
+                    out[f"{q}.self_attn.attention._out_projection.weight"] = (D, H * D)
                 out[f"{q}.linear1.weight"] = (F, D)
                 out[f"{q}.linear1.bias"] = (F,)
                 out[f"{q}.linear2.weight"] = (D, F)

@@ -21,9 +21,20 @@ TINY_C = fo.OracleConfig(atom_embedding_dim=8, latent_mlp_hidden_dims=[24], num_
                          d_model=16, dim_feedforward=32, lengthscales=[0.3, 1.0], attention_type="chebyshev_kernel", cheb_order=6,
                          force_asymptotic_zero=True)
 FULL_C = fo.OracleConfig(attention_type="chebyshev_kernel", cheb_order=12, force_asymptotic_zero=False)
+# `local` attention: dot-product attention over the atoms within max_radius (modules/layers/local_self_attention.py)
+TINY_LOC = fo.OracleConfig(atom_embedding_dim=8, latent_mlp_hidden_dims=[24], num_coupling_layers=4, num_transformer_layers=2,
+                           d_model=16, dim_feedforward=32, lengthscales=[], attention_type="local", max_radius=0.3, num_heads=3)
+FULL_LOC = fo.OracleConfig(lengthscales=[], attention_type="local", max_radius=0.45, num_heads=6)
 
 
 def model_config(o: fo.OracleConfig, precision: str):
+    if getattr(o, "attention_type", "kernel") == "local":
+        enc = tw.CustomAttentionEncoderLayerConfig(d_model=o.d_model, dim_feedforward=o.dim_feedforward, dropout=0.0,
+                                                   num_heads=o.num_heads, attention_type="local", max_radius=o.max_radius)
+        return tw.CustomAttentionTransformerNVPConfig(
+            atom_embedding_dim=o.atom_embedding_dim, latent_mlp_hidden_dims=list(o.latent_mlp_hidden_dims),
+            num_coupling_layers=o.num_coupling_layers, num_transformer_layers=o.num_transformer_layers, encoder_layer_config=enc,
+            position_layer_index_mod_2=o.position_layer_index_mod_2, precision=precision)
     return tw.CustomAttentionTransformerNVPConfig(
         atom_embedding_dim=o.atom_embedding_dim,
         latent_mlp_hidden_dims=list(o.latent_mlp_hidden_dims),

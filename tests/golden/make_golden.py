@@ -51,10 +51,11 @@ def ref_model(cfg: OracleConfig, seed: int):
         d_model=cfg.d_model,
         dim_feedforward=cfg.dim_feedforward,
         dropout=0.0,
-        num_heads=len(cfg.lengthscales),
+        num_heads=cfg.num_heads if cfg.attention_type == "local" else len(cfg.lengthscales),
         attention_type=cfg.attention_type,
-        lengthscales=list(cfg.lengthscales),
-        normalise_kernel_values=True,
+        lengthscales=None if cfg.attention_type == "local" else list(cfg.lengthscales),
+        normalise_kernel_values=None if cfg.attention_type == "local" else True,
+        max_radius=cfg.max_radius if cfg.attention_type == "local" else None,
         cheb_order=cfg.cheb_order if cfg.attention_type == "chebyshev_kernel" else None,
         force_asymptotic_zero=cfg.force_asymptotic_zero if cfg.attention_type == "chebyshev_kernel" else None,
     )
@@ -125,7 +126,9 @@ def run_case(name, cfg, peptide, B, seed, lengths=None, sample_S=3, wseed=0, tra
         ls = torch.tensor(cfg.lengthscales, dtype=torch.float32)
         if cfg.attention_type == "learnable_kernel":  # density direction: the first attention layer executed (cache quirk)
             ls = torch.exp(sd["flow.chain.0.scale_transformer.encoder_layers.0.self_attn.attention.log_lengthscales"])
-        if cfg.attention_type == "chebyshev_kernel":  # scores of the first attention layer (every layer has its own)
+        if cfg.attention_type == "local":
+            out["scores"] = np.zeros((0,), np.float32)  # dot-product attention: no position-only score tensor
+        elif cfg.attention_type == "chebyshev_kernel":  # scores of the first attention layer (every layer has its own)
             from timewarp.modules.layers.kernel_attention import chebyshev_basis_function
             cc = sd["flow.chain.0.scale_transformer.encoder_layers.0.self_attn.attention.cheb_coeffs"]
             out["scores"] = compute_kernel_attention_scores(
@@ -269,6 +272,28 @@ def chebyshev_cases():
     run_case("full_ad22_chebyshev", FULL_CHEB, ad, B=3, seed=24, sample_S=2, trace_layer0=False)
 
 
+TINY_LOCAL = OracleConfig(atom_embedding_dim=8, latent_mlp_hidden_dims=[24], num_coupling_layers=4, num_transformer_layers=2,
+                          d_model=16, dim_feedforward=32, lengthscales=[], attention_type="local", max_radius=0.3, num_heads=3)
+FULL_LOCAL = OracleConfig(lengthscales=[], attention_type="local", max_radius=0.45, num_heads=6)
+
+
+def local_cases():
+    """`local` attention: dot-product attention over the atoms within max_radius."""
+    ad = alanine_dipeptide()
+    # construction-order contract of the `local` module tree: reference default initialisation under a fixed torch seed
+    enc = CustomAttentionEncoderLayerConfig(d_model=TINY_LOCAL.d_model, dim_feedforward=TINY_LOCAL.dim_feedforward, dropout=0.0,
+                                            num_heads=TINY_LOCAL.num_heads, attention_type="local", max_radius=TINY_LOCAL.max_radius)
+    mc = CustomAttentionTransformerNVPConfig(atom_embedding_dim=TINY_LOCAL.atom_embedding_dim,
+                                             latent_mlp_hidden_dims=list(TINY_LOCAL.latent_mlp_hidden_dims),
+                                             num_coupling_layers=TINY_LOCAL.num_coupling_layers,
+                                             num_transformer_layers=TINY_LOCAL.num_transformer_layers, encoder_layer_config=enc)
+    torch.manual_seed(0)
+    sd = {k: v.numpy() for k, v in custom_transformer_nvp_constructor(mc).state_dict().items()}
+    np.savez_compressed(os.path.join(HERE, "tiny_local_init_seed0.npz"), **sd)
+    run_case("tiny_ad_local", TINY_LOCAL, ad, B=3, seed=25, lengths=[22, 15, 9], sample_S=3, trace_layer0=False)
+    run_case("full_ad22_local", FULL_LOCAL, ad, B=3, seed=26, sample_S=2, trace_layer0=False)
+
+
 def learnable_cases():
     """`learnable_kernel` attention: per-layer log_lengthscales, of which the reference uses only
     the first executed layer's (cache key quirk) -- layer 0 for log_likelihood, the last coupling layer when sampling."""
@@ -333,6 +358,9 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "learnable":
         learnable_cases()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "local":
+        local_cases()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "chebyshev":
         chebyshev_cases()
         sys.exit(0)
@@ -351,5 +379,6 @@ if __name__ == "__main__":
     grad_case("grads_full_ad22_ragged", FULL, ad, B=3, seed=4, lengths=[22, 17, 12])
     learnable_cases()
     chebyshev_cases()
+    local_cases()
     dataloader_case()
 

@@ -70,6 +70,17 @@ def test_seeded_init_matches_reference():
         assert np.array_equal(sd[k].numpy(), ref[k]), k
 
 
+def test_seeded_init_matches_reference_local():
+    """`local` attention module tree (qkv_proj before output_proj, local_self_attention.py:33-41)."""
+    from tests.common import TINY_LOC
+    ref = np.load(os.path.join(GOLDEN, "tiny_local_init_seed0.npz"))
+    torch.manual_seed(0)
+    sd = tw.custom_transformer_nvp_constructor(model_config(TINY_LOC, "fp32")).state_dict()
+    assert sorted(sd.keys()) == sorted(ref.files)
+    for k in ref.files:
+        assert np.array_equal(sd[k].numpy(), ref[k]), k
+
+
 def test_config_validation(lib):
     bad = model_config(TINY_O, "fp32")
     bad.num_coupling_layers = 3
@@ -80,8 +91,8 @@ def test_config_validation(lib):
     with pytest.raises(AssertionError):
         tw.custom_transformer_nvp_constructor(bad)
     bad = model_config(TINY_O, "fp32")
-    bad.encoder_layer_config.attention_type = "local"
-    with pytest.raises(NotImplementedError):
+    bad.encoder_layer_config.attention_type = "global"
+    with pytest.raises(RuntimeError, match="Unknown attention type"):  # custom_attention_encoder.py:211-212
         tw.custom_transformer_nvp_constructor(bad)
     # tensor-core precisions reject layer sizes they do not cover (status TW_ERR_UNSUPPORTED)
     m = tw.custom_transformer_nvp_constructor(model_config(TINY_O, "bf16x3"))

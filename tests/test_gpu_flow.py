@@ -6,7 +6,8 @@ import pytest
 import torch
 
 from oracle import flow_oracle as fo
-from tests.common import EMPTY_ADJ, EMPTY_EBI, FULL_C, FULL_L, FULL_O, TINY_C, TINY_L, TINY_O, build_model, load_golden
+from tests.common import (EMPTY_ADJ, EMPTY_EBI, FULL_C, FULL_L, FULL_LOC, FULL_O, TINY_C, TINY_L, TINY_LOC, TINY_O, build_model,
+                          load_golden)
 
 pytestmark = pytest.mark.gpu
 REL = 1e-4  # north_star tolerance
@@ -15,7 +16,9 @@ CASES = [("tiny_ad_ragged", TINY_O, "fp32"), ("tiny_ad", TINY_O, "fp32"), ("full
          ("full_ad22_ragged", FULL_O, "fp32"), ("full_2olx65", FULL_O, "fp32")]
 # learnable_kernel attention: the golden files carry no layer-0 trace; the lengthscales differ per layer and direction
 LEARNABLE = [("tiny_ad_learnable", TINY_L, "fp32"), ("full_ad22_learnable", FULL_L, "fp32"), ("full_ad22_learnable", FULL_L, "bf16x3"),
-             ("tiny_ad_chebyshev", TINY_C, "fp32"), ("full_ad22_chebyshev", FULL_C, "fp32"), ("full_ad22_chebyshev", FULL_C, "bf16x3")]
+             ("tiny_ad_chebyshev", TINY_C, "fp32"), ("full_ad22_chebyshev", FULL_C, "fp32"), ("full_ad22_chebyshev", FULL_C, "bf16x3"),
+             # local (dot-product) attention: CUDA-core attention kernels; with bf16x3 the MLPs and the FFN run on the tensor cores
+             ("tiny_ad_local", TINY_LOC, "fp32"), ("full_ad22_local", FULL_LOC, "fp32"), ("full_ad22_local", FULL_LOC, "bf16x3")]
 
 
 def _kw(g, dev="cuda", rows=slice(None)):
@@ -200,6 +203,33 @@ def test_learnable_kernel_module_surface():
     assert (m.attention_scores(xc.cuda(), mask.cuda()).cpu() - g["scores"]).abs().max() < 2e-3
     m.train()
     with pytest.raises(NotImplementedError):
+        m(y_coords=g["y_coords"].cuda(), y_velocs=g["y_velocs"].cuda(), **_kw(g))
+
+
+def test_local_attention_module_surface():
+    """State-dict keys of the reference's LocalSelfAttention; oracle parity on a seeded ragged batch whose radius leaves some
+    atoms without any neighbour but themselves; shared conditioning (S proposals from one state); no training path."""
+    g = load_golden("tiny_ad_local")
+    m, sd = build_model(TINY_LOC, "fp32", int(g["weight_seed"]))
+    assert set(m.state_dict().keys()) == set(sd.keys())
+    assert m.state_dict()["flow.chain.0.scale_transformer.encoder_layers.0.self_attn.qkv_proj.weight"].shape == (3 * 3 * 16, 16)
+    with pytest.raises(TypeError):
+        m.attention_scores(g["x_coords"].cuda(), g["masked_elements"].cuda())
+    gen = torch.Generator().manual_seed(5)
+    B, V = 5, 13
+    lengths = torch.tensor([13, 7, 1, 10, 4])
+    mask = torch.arange(V)[None, :] >= lengths[:, None]
+    at = torch.randint(0, 5, (B, V), generator=gen)
+    xc = torch.randn(B, V, 3, generator=gen) * 0.25  # many pairs beyond max_radius = 0.3
+    xv, yv = torch.randn(B, V, 3, generator=gen), torch.randn(B, V, 3, generator=gen)
+    yc = xc + 0.02 * torch.randn(B, V, 3, generator=gen)
+    want = fo.log_likelihood(sd, TINY_LOC, at, xc, xv, yc, yv, mask)
+    with torch.no_grad():
+        got = m.log_likelihood(atom_types=at.cuda(), x_coords=xc.cuda(), x_velocs=xv.cuda(), y_coords=yc.cuda(), y_velocs=yv.cuda(),
+                               adj_list=EMPTY_ADJ.cuda(), edge_batch_idx=EMPTY_EBI.cuda(), masked_elements=mask.cuda())
+    assert_rel(got, want, what="local attention vs oracle (ragged, sparse neighbourhoods)")
+    m.train()
+    with pytest.raises(Exception):
         m(y_coords=g["y_coords"].cuda(), y_velocs=g["y_velocs"].cuda(), **_kw(g))
 
 

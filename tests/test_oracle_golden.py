@@ -23,6 +23,11 @@ TINY_C = fo.OracleConfig(atom_embedding_dim=8, latent_mlp_hidden_dims=[24], num_
                          force_asymptotic_zero=True)
 FULL_C = fo.OracleConfig(attention_type="chebyshev_kernel", cheb_order=12, force_asymptotic_zero=False)
 CHEBYSHEV = [("tiny_ad_chebyshev", TINY_C), ("full_ad22_chebyshev", FULL_C)]
+# `local` attention: dot-product attention over the atoms within max_radius (modules/layers/local_self_attention.py)
+TINY_LOC = fo.OracleConfig(atom_embedding_dim=8, latent_mlp_hidden_dims=[24], num_coupling_layers=4, num_transformer_layers=2,
+                           d_model=16, dim_feedforward=32, lengthscales=[], attention_type="local", max_radius=0.3, num_heads=3)
+FULL_LOC = fo.OracleConfig(lengthscales=[], attention_type="local", max_radius=0.45, num_heads=6)
+LOCAL = [("tiny_ad_local", TINY_LOC), ("full_ad22_local", FULL_LOC)]
 
 
 def load(golden_dir, name):
@@ -30,7 +35,7 @@ def load(golden_dir, name):
     return {k: torch.from_numpy(d[k]) for k in d.files}
 
 
-@pytest.mark.parametrize("name,cfg", CASES + LEARNABLE + CHEBYSHEV)
+@pytest.mark.parametrize("name,cfg", CASES + LEARNABLE + CHEBYSHEV + LOCAL)
 def test_log_likelihood_and_loss(golden_dir, name, cfg):
     g = load(golden_dir, name)
     sd = fo.synth_state_dict(cfg, int(g["weight_seed"]))
@@ -66,7 +71,7 @@ def test_scores_and_layer0(golden_dir, name, cfg):
     torch.testing.assert_close(shift, g["layer0_shift"], rtol=1e-5, atol=1e-6)
 
 
-@pytest.mark.parametrize("name,cfg", CASES + LEARNABLE + CHEBYSHEV)
+@pytest.mark.parametrize("name,cfg", CASES + LEARNABLE + CHEBYSHEV + LOCAL)
 def test_sampling(golden_dir, name, cfg):
     g = load(golden_dir, name)
     sd = fo.synth_state_dict(cfg, int(g["weight_seed"]))

@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libtimewarp_b200.so")
 
 TW_OK = 0
-TW_ATTENTION_KERNEL, TW_ATTENTION_CHEBYSHEV = 0, 2
+TW_ATTENTION_KERNEL, TW_ATTENTION_LOCAL, TW_ATTENTION_CHEBYSHEV = 0, 1, 2
 TW_MAX_MLP_HIDDEN = 4
 TW_MAX_HEADS = 16
 PRECISION = {"fp32": 0, "bf16x3": 1, "bf16": 2}
@@ -34,9 +34,10 @@ class FlowConfig(C.Structure):
         ("num_atom_types", C.c_int32),
         ("layer_norm_eps", C.c_float),
         ("precision", C.c_int32),
-        ("attention_type", C.c_int32),  # TW_ATTENTION_*: 0 kernel / learnable_kernel, 2 chebyshev_kernel
+        ("attention_type", C.c_int32),  # TW_ATTENTION_*: 0 kernel / learnable_kernel, 1 local, 2 chebyshev_kernel
         ("cheb_order", C.c_int32),
         ("force_asymptotic_zero", C.c_int32),
+        ("max_radius", C.c_float),  # local: neighbourhood radius in nm
     ]
 
 

@@ -31,7 +31,9 @@ static int validate_cfg(const tw_flow_config* c) {
   TW_CHECK_ARG(c->num_heads >= 1 && c->num_heads <= TW_MAX_HEADS, "num_heads out of range");
   TW_CHECK_ARG(c->num_atom_types >= 1, "bad num_atom_types");
   TW_CHECK_ARG(c->precision >= TW_PRECISION_FP32 && c->precision <= TW_PRECISION_BF16, "unknown precision");
-  TW_CHECK_ARG(c->attention_type == TW_ATTENTION_KERNEL || c->attention_type == TW_ATTENTION_CHEBYSHEV, "unknown attention_type");
+  TW_CHECK_ARG(c->attention_type == TW_ATTENTION_KERNEL || c->attention_type == TW_ATTENTION_CHEBYSHEV ||
+                   c->attention_type == TW_ATTENTION_LOCAL, "unknown attention_type");
+  TW_CHECK_ARG(c->attention_type != TW_ATTENTION_LOCAL || c->max_radius > 0.f, "local attention needs max_radius > 0");
   TW_CHECK_ARG(c->attention_type != TW_ATTENTION_CHEBYSHEV || (c->cheb_order >= 1 && c->cheb_order <= TW_MAX_CHEB_ORDER),
                "cheb_order out of range (1..32)");
   if (c->precision != TW_PRECISION_FP32 && !tc_supported(c))
@@ -59,7 +61,7 @@ static size_t carve(const tw_flow_config* c, int64_t n, int64_t n_cond, int64_t 
   for (int i = 0; i < 2; i++) {
     b.hidA[i] = ar.take<float>(M * hid);
     b.hidB[i] = ar.take<float>(M * hid);
-    b.vals[i] = ar.take<float>(M * H * D);
+    b.vals[i] = ar.take<float>(M * H * D * (c->attention_type == TW_ATTENTION_LOCAL ? 3 : 1));  // local: q | k | v per head
     b.att[i] = ar.take<float>(M * H * D);
     // the fused tensor-core FFN keeps the hidden activation on chip
     b.ffn[i] = (c->precision == TW_PRECISION_FP32 || !(tc_stage_mask() & TC_FFN)) ? ar.take<float>(M * F) : nullptr;
@@ -91,7 +93,8 @@ static int conditioner(PassCtx& p, int k) {
   const int64_t M = p.n * p.V;
   const int D = c->d_model, H = c->num_heads, F = c->dim_feedforward, E = c->atom_embedding_dim, nh = c->num_mlp_hidden;
   const bool pos = (k % 2) == c->position_layer_index_mod_2;
-  const uint32_t tcs = (c->precision == TW_PRECISION_FP32) ? 0u : tc_stage_mask();
+  uint32_t tcs = (c->precision == TW_PRECISION_FP32) ? 0u : tc_stage_mask();
+  if (p.pv.local()) tcs &= ~(uint32_t)(TC_MIX | TC_ATTN_PROJ);  // dot-product attention runs on the CUDA-core kernels
   TcScratch tcx = b.tc;
   tcx.packed = p.packed;
   const float* cur[2] = {b.feat, b.feat};
@@ -118,7 +121,18 @@ static int conditioner(PassCtx& p, int k) {
     // chebyshev_kernel: every attention layer of every network has its own basis function, hence its own scores
     // (the reference's cache key contains the per-module basis lambda, kernel_attention.py:333-335): the scores are
     // recomputed here and the two networks run one after the other.  Otherwise one score set serves the whole pass.
-    for (int pass = 0; pass < (cheb ? 2 : 1); pass++) {
+    if (p.pv.local()) {  // qkv projection -> masked softmax attention within max_radius -> output projection + residual -> LN1
+      Lin2 a{};
+      for (int s = 0; s < 2; s++) a.X[s] = b.actA[s], a.W[s] = p.pv.enc(k, s, t, 0), a.Y[s] = b.vals[s];
+      TW_TRY(launch_linear(a, 2, M, H * 3 * D, D, D, 0, H * 3 * D, ACT_NONE, p.st));
+      TW_TRY(launch_local_attn(b.vals[0], b.vals[1], b.att[0], b.att[1], 2, p.n, p.n_cond, p.V, H, D, b.xc, p.mask, c->max_radius, p.st));
+      Lin2 o{};
+      for (int s = 0; s < 2; s++) o.X[s] = b.att[s], o.W[s] = p.pv.enc(k, s, t, 2), o.R[s] = b.actA[s], o.Y[s] = b.actB[s];
+      TW_TRY(launch_linear(o, 2, M, D, H * D, H * D, D, D, ACT_NONE, p.st));
+      TW_TRY(launch_layernorm(b.actB[0], b.actB[1], p.pv.enc(k, 0, t, 7), p.pv.enc(k, 1, t, 7), p.pv.enc(k, 0, t, 8),
+                              p.pv.enc(k, 1, t, 8), 2, M, D, c->layer_norm_eps, p.st));
+    }
+    for (int pass = 0; pass < (p.pv.local() ? 0 : (cheb ? 2 : 1)); pass++) {
       const int only = cheb ? pass : -1;
       if ((tcs & TC_MIX) && (tcs & TC_ATTN_PROJ)) {
         if (cheb) TW_TRY(tc_begin_pass_direct(c, tcx, b.xc, p.mask, ls, p.n_cond, p.V, p.st, p.pv.cheb(k, only, t), false));
@@ -184,7 +198,7 @@ static int begin_pass(PassCtx& p, const float* x_coords) {
   TW_TRY(launch_prep(x_coords, p.mask, p.n_cond, p.V, p.fb.xc, p.fb.com, p.st));
   // lengthscales of chain[0].scale_transformer.encoder_layers[0] (cache key maps lengthscales -> 0)
   const float* ls = p.pv.enc(0, 0, 0, 1);
-  if (p.pv.chebyshev()) {  // scores are per attention layer (conditioner()); only the per-pass scratch reset happens here
+  if (p.pv.chebyshev() || p.pv.local()) {  // scores are per attention layer (conditioner()) / not position-only at all
     if (p.c->precision != TW_PRECISION_FP32) TW_TRY(tc_begin_pass(p.c, p.pv, p.fb.tc, nullptr, p.mask, p.n, p.n_cond, p.V, p.st));
     return TW_OK;
   }
@@ -287,7 +301,7 @@ int tw_flow_scale_shift(const tw_flow_config* cfg, const void* const* params, in
   TW_CUDA(cudaMemcpyAsync(p.fb.xc, x_coords_centred, zb, cudaMemcpyDeviceToDevice, p.st));
   TW_CUDA(cudaMemcpyAsync(p.fb.zc, z_coords, zb, cudaMemcpyDeviceToDevice, p.st));
   TW_CUDA(cudaMemcpyAsync(p.fb.zv, z_velocs, zb, cudaMemcpyDeviceToDevice, p.st));
-  if (p.pv.chebyshev()) {
+  if (p.pv.chebyshev() || p.pv.local()) {
     if (cfg->precision != TW_PRECISION_FP32) TW_TRY(tc_begin_pass(cfg, p.pv, p.fb.tc, nullptr, mask, B, B, (int)V, p.st));
   } else {
     TW_TRY(launch_scores(p.fb.xc, mask, p.pv.enc(0, 0, 0, 1), B, (int)V, cfg->num_heads, p.fb.scores, p.st));

@@ -223,6 +223,84 @@ int launch_attn_mix(const float* scores, const float* v0, const float* v1, float
 }
 
 // ------------------------------------------------------------------------------------------
+// LocalSelfAttention (modules/layers/local_self_attention.py:46-119).  The reference gathers the atoms within max_radius
+// (topk) and softmaxes over them; equivalently a masked softmax over all atoms of the sample.  One CTA per (sample, head,
+// network): K and V of the head in shared memory, one warp per query row (lane = 4 features of d_model = 128... generic D).
+__global__ void __launch_bounds__(128) k_local_attn(const float* __restrict__ qkv0, const float* __restrict__ qkv1,
+                                                    float* __restrict__ o0, float* __restrict__ o1, int64_t n_cond, int V, int H,
+                                                    int D, const float* __restrict__ xc, const uint8_t* __restrict__ mask,
+                                                    float max_radius, float inv_sqrt_d) {
+  extern __shared__ float sm[];
+  float* sK = sm;                    // [V][D]
+  float* sV = sK + (size_t)V * D;    // [V][D]
+  float* sX = sV + (size_t)V * D;    // [V][3]
+  float* sW = sX + (size_t)V * 3;    // [4 warps][V] attention weights of the row in flight
+  const int64_t n = blockIdx.x;
+  const int h = blockIdx.y, net = blockIdx.z;
+  const int64_t nc = n % n_cond;
+  const int ld = H * 3 * D;
+  const float* qkv = (net ? qkv1 : qkv0) + n * (int64_t)V * ld + (size_t)h * 3 * D;
+  float* out = (net ? o1 : o0) + n * (int64_t)V * (H * D) + (size_t)h * D;
+  const uint8_t* mb = mask + nc * V;
+  for (int e = threadIdx.x; e < V * D; e += blockDim.x) {
+    const int j = e / D, d = e % D;
+    sK[e] = qkv[(int64_t)j * ld + D + d];
+    sV[e] = qkv[(int64_t)j * ld + 2 * D + d];
+  }
+  for (int e = threadIdx.x; e < V * 3; e += blockDim.x) sX[e] = xc[nc * V * 3 + e];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* w = sW + warp * V;
+  for (int i = warp; i < V; i += 4) {
+    const float* q = qkv + (int64_t)i * ld;
+    const float xi = sX[i * 3], yi = sX[i * 3 + 1], zi = sX[i * 3 + 2];
+    float mx = -INFINITY;
+    for (int j = 0; j < V; j++) {
+      float part = 0.f;
+      for (int d = lane; d < D; d += 32) part = fmaf(q[d], sK[j * D + d], part);
+      part = warp_sum(part) * inv_sqrt_d;
+      const float dx = xi - sX[j * 3], dy = yi - sX[j * 3 + 1], dz = zi - sX[j * 3 + 2];
+      const bool outside = mb[i] || mb[j] || sqrtf(dx * dx + dy * dy + dz * dz) > max_radius;
+      const float sc = outside ? -INFINITY : part;
+      if (lane == 0) w[j] = sc;
+      mx = fmaxf(mx, sc);
+    }
+    __syncwarp();
+    float den = 0.f;
+    for (int j = lane; j < V; j += 32) {
+      const float e = (w[j] == -INFINITY) ? 0.f : expf(w[j] - mx);  // a row with no neighbour (padding) stays all zero
+      w[j] = e;
+      den += e;
+    }
+    den = warp_sum(den);
+    const float inv = den > 0.f ? 1.f / den : 0.f;
+    __syncwarp();
+    for (int d = lane; d < D; d += 32) {
+      float acc = 0.f;
+      for (int j = 0; j < V; j++) acc = fmaf(w[j] * inv, sV[j * D + d], acc);
+      out[(int64_t)i * (H * D) + d] = acc;
+    }
+    __syncwarp();
+  }
+}
+
+int launch_local_attn(const float* qkv0, const float* qkv1, float* o0, float* o1, int nets, int64_t n, int64_t n_cond, int V, int H,
+                      int D, const float* xc, const uint8_t* mask, float max_radius, cudaStream_t st) {
+  if (n == 0) return TW_OK;
+  const size_t smem = ((size_t)2 * V * D + (size_t)V * 3 + (size_t)4 * V) * sizeof(float);
+  TW_CHECK_ARG(smem <= 200 * 1024, "local attention: V * d_model too large for shared memory (V=%d)", V);
+  static bool attr_done = false;
+  if (!attr_done) {
+    TW_CUDA(cudaFuncSetAttribute(k_local_attn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_done = true;
+  }
+  dim3 grid((unsigned)n, H, nets);
+  k_local_attn<<<grid, 128, smem, st>>>(qkv0, qkv1, o0, o1, n_cond, V, H, D, xc, mask, max_radius, 1.0f / sqrtf((float)D));
+  TW_LAUNCH_CHECK();
+  return TW_OK;
+}
+
+// ------------------------------------------------------------------------------------------
 // get_centre_of_mass + centring (utils/molecule_utils.py:15-29, flow.py:156-157): one block / state
 __global__ void __launch_bounds__(128) k_prep(const float* __restrict__ x, const uint8_t* __restrict__ mask, int V,
                                               float* __restrict__ xc, float* __restrict__ com) {

@@ -14,6 +14,7 @@ struct ParamView {
   __host__ int per_net() const { return 2 * per_mlp() + 11 * c->num_transformer_layers; }
   __host__ int regular() const { return 3 + c->num_coupling_layers * 2 * per_net(); }
   __host__ bool chebyshev() const { return c->attention_type == TW_ATTENTION_CHEBYSHEV; }
+  __host__ bool local() const { return c->attention_type == TW_ATTENTION_LOCAL; }
   __host__ int total() const { return regular() + (chebyshev() ? c->num_coupling_layers * 2 * c->num_transformer_layers : 0); }
   // chebyshev_kernel: cheb_coeffs [H, cheb_order] of encoder layer t of network `net` of coupling layer k (trailing section)
   __host__ const float* cheb(int k, int net, int t) const { return at(regular() + (k * 2 + net) * c->num_transformer_layers + t); }
@@ -51,6 +52,10 @@ int launch_layernorm(float* x0, float* x1, const float* g0, const float* g1, con
                      int64_t M, int D, float eps, cudaStream_t st);
 int launch_attn_mix(const float* scores, const float* v0, const float* v1, float* o0, float* o1, int nets, int64_t n,
                     int64_t n_cond, int V, int H, int Dv, cudaStream_t st);
+// LocalSelfAttention (local_self_attention.py:46-119) on qkv [n*V, H*3*D] (per head: q | k | v): masked softmax over the
+// atoms within max_radius of the conditioning positions xc [n_cond, V, 3]; out [n*V, H*D]
+int launch_local_attn(const float* qkv0, const float* qkv1, float* o0, float* o1, int nets, int64_t n, int64_t n_cond, int V, int H,
+                      int D, const float* xc, const uint8_t* mask, float max_radius, cudaStream_t st);
 int launch_prep(const float* x, const uint8_t* mask, int64_t n_cond, int V, float* xc, float* com, cudaStream_t st);
 // cheb != nullptr: Chebyshev-rational basis with coefficients [H, order] instead of the Gaussian
 int launch_scores(const float* xc, const uint8_t* mask, const float* ls, int64_t B, int V, int H, float* out, cudaStream_t st,

@@ -124,10 +124,12 @@ int tc_pack_weights(const tw_flow_config* c, const ParamView& pv, uint8_t* packe
       TW_TRY(pack_matrix(pv.out_w(k, net, 0), D, hid, D, hid, base + L.out_w1, 0, (size_t)2 * hid * 128, (size_t)hid * 128, st));
       for (int t = 0; t < L.T; t++) {
         uint8_t* eb = base + L.enc0 + (size_t)t * L.enc_stride;
-        k_combine_wc<<<dim3(H, D), 128, 0, st>>>(pv.enc(k, net, t, 2), pv.enc(k, net, t, 0), D, H, wc_tmp);
-        TW_LAUNCH_CHECK();
-        // W_c [D x H*D] -> H*D/64 K blocks [128 x 64]: block kb at kb*32 KB: hi 16 KB, lo 16 KB
-        TW_TRY(pack_matrix(wc_tmp, H * D, D, H * D, 128, eb + L.enc_wc, 0, 2 * 128 * 128, 128 * 128, st));
+        if (!pv.local()) {  // (local attention runs on the CUDA-core kernels straight from the fp32 weights)
+          k_combine_wc<<<dim3(H, D), 128, 0, st>>>(pv.enc(k, net, t, 2), pv.enc(k, net, t, 0), D, H, wc_tmp);
+          TW_LAUNCH_CHECK();
+          // W_c [D x H*D] -> H*D/64 K blocks [128 x 64]: block kb at kb*32 KB: hi 16 KB, lo 16 KB
+          TW_TRY(pack_matrix(wc_tmp, H * D, D, H * D, 128, eb + L.enc_wc, 0, 2 * 128 * 128, 128 * 128, st));
+        }
         // FFN chunk c: [W1hi | W1lo | W2hi | W2lo], each 32 KB = K blocks kb0, kb1 of [128 x 64]
         //   W1 [F x D]: rows c*128.., all D=128 columns  -> tile (tr=c, tk) at c*128KB + tk*16KB, lo +32KB
         TW_TRY(pack_matrix(pv.enc(k, net, t, 3), D, F, D, 128, eb + L.enc_ffn, 4 * kTileBytes128, 128 * 128, kTileBytes128, st));

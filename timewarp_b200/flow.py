@@ -137,7 +137,9 @@ class ConditionalFlowDensityModel(nn.Module):
         # `learnable_kernel` attention: exp(log_lengthscales) of the first attention layer executed in the pass, written
         # here before every pass; every lengthscale entry of the parameter table points at this buffer (the reference's
         # cache key maps `lengthscales` to 0, so one layer's scores serve the whole pass -- SURVEY.md quirk B)
-        self._learnable = hasattr(flow.chain[0].scale_transformer.encoder_layers[0].self_attn.attention, "log_lengthscales")
+        self._local = flow_config.attention_type == _lib.TW_ATTENTION_LOCAL
+        self._learnable = not self._local and hasattr(
+            flow.chain[0].scale_transformer.encoder_layers[0].self_attn.attention, "log_lengthscales")
         self._ls_eff: Optional[Tensor] = None
         self._table = None  # (ctypes array, keep-alive list)
         self._workspace: Optional[Tensor] = None
@@ -179,6 +181,11 @@ class ConditionalFlowDensityModel(nn.Module):
                 for lin in block.in_mlp.linears():
                     out += [lin.weight, lin.bias]
                 for enc in block.encoder_layers:
+                    if self._local:  # slots [wv, lengthscales, wo] = [qkv_proj.weight, (ignored), output_proj.weight]
+                        out += [enc.self_attn.qkv_proj.weight, enc.norm1.bias, enc.self_attn.output_proj.weight, enc.linear1.weight,
+                                enc.linear1.bias, enc.linear2.weight, enc.linear2.bias, enc.norm1.weight, enc.norm1.bias,
+                                enc.norm2.weight, enc.norm2.bias]  # fmt: skip
+                        continue
                     out += [
                         enc.self_attn.values_proj.weight, self._ls_eff if self._learnable else enc.self_attn.attention.lengthscales,
                         enc.self_attn.attention._out_projection.weight, enc.linear1.weight, enc.linear1.bias,
@@ -423,6 +430,8 @@ class ConditionalFlowDensityModel(nn.Module):
     # ---------------------------------------------------------------- test / debug hooks
     def attention_scores(self, x_coords_centred: Tensor, masked_elements: Tensor) -> Tensor:
         """compute_kernel_attention_scores (kernel_attention.py:69-121) -> [B,H,V,V]."""
+        if self._local:
+            raise TypeError("`local` attention has no position-only scores (dot-product attention, local_self_attention.py:99-100)")
         x = _require_cuda("x_coords", x_coords_centred, torch.float32)
         mask = _require_cuda("masked_elements", masked_elements, torch.bool).view(torch.uint8)
         att = self.flow.chain[0].scale_transformer.encoder_layers[0].self_attn.attention

@@ -20,7 +20,7 @@ class CustomAttentionEncoderLayerConfig:
     dim_feedforward: int  # Dimension of hidden layer in the pointwise MLP in transformer block
     dropout: float  # Dropout rate in transformer block (must be 0: configs/kernel_transformer_nvp.yaml:27)
     num_heads: int  # Number of heads in multihead attention.
-    attention_type: str  # "kernel" | "learnable_kernel" | "chebyshev_kernel" (built); "local" is SURVEY section 8f-3
+    attention_type: str  # "kernel" | "learnable_kernel" | "chebyshev_kernel" | "local"
     lengthscales: Optional[List[float]] = None
     max_radius: Optional[float] = None
     normalise_kernel_values: Optional[bool] = None

@@ -19,9 +19,11 @@ def flow_config_from(config, precision=None) -> _lib.FlowConfig:
     hidden = list(config.latent_mlp_hidden_dims)
     if len(hidden) > _lib.TW_MAX_MLP_HIDDEN:
         raise ValueError(f"at most {_lib.TW_MAX_MLP_HIDDEN} hidden MLP layers are supported")
-    if len(enc.lengthscales) > _lib.TW_MAX_HEADS:
+    local = enc.attention_type == "local"
+    num_heads = enc.num_heads if local else len(enc.lengthscales)
+    if num_heads > _lib.TW_MAX_HEADS:
         raise ValueError(f"at most {_lib.TW_MAX_HEADS} heads are supported")
-    if enc.num_heads != len(enc.lengthscales):
+    if not local and enc.num_heads != len(enc.lengthscales):
         import warnings
 
         warnings.warn(  # custom_attention_encoder.py:158-161: the lengthscales win
@@ -38,12 +40,16 @@ def flow_config_from(config, precision=None) -> _lib.FlowConfig:
     c.num_transformer_layers = config.num_transformer_layers
     c.d_model = enc.d_model
     c.dim_feedforward = enc.dim_feedforward
-    c.num_heads = len(enc.lengthscales)
+    c.num_heads = num_heads
     c.position_layer_index_mod_2 = config.position_layer_index_mod_2
     c.num_atom_types = ELEMENT_VOCAB_SIZE
     c.layer_norm_eps = 1e-5
     c.precision = _lib.PRECISION[prec]
-    if enc.attention_type == "chebyshev_kernel":
+    if local:
+        assert enc.max_radius is not None and enc.max_radius > 0
+        c.attention_type = _lib.TW_ATTENTION_LOCAL
+        c.max_radius = float(enc.max_radius)
+    elif enc.attention_type == "chebyshev_kernel":
         assert enc.cheb_order is not None and enc.cheb_order >= 1 and enc.force_asymptotic_zero is not None
         c.attention_type = _lib.TW_ATTENTION_CHEBYSHEV
         c.cheb_order = int(enc.cheb_order)

@@ -102,6 +102,17 @@ class KernelSelfAttention(_Container):
         self.attention = attention
 
 
+class LocalSelfAttention(_Container):
+    """modules/layers/local_self_attention.py:14-119: dot-product attention over the atoms within `max_radius` of each atom
+    (bias-free fused q|k|v projection per head, bias-free output projection; same construction order as the reference)."""
+
+    def __init__(self, *, input_dim: int, output_dim: int, num_heads: int, value_dim: int, key_query_dim: int, max_radius: float):
+        super().__init__()
+        self.num_heads, self.value_dim, self.key_query_dim, self.max_radius = num_heads, value_dim, key_query_dim, max_radius
+        self.qkv_proj = nn.Linear(input_dim, num_heads * (value_dim + 2 * key_query_dim), bias=False)
+        self.output_proj = nn.Linear(num_heads * value_dim, output_dim, bias=False)
+
+
 class CustomTransformerEncoderLayer(_Container):
     """modules/layers/custom_attention_encoder.py:24-114 (post-LN, ReLU FFN, dropout must be 0)."""
 
@@ -116,14 +127,16 @@ class CustomTransformerEncoderLayer(_Container):
 
 
 def custom_attention_transformer_encoder_constructor(config) -> CustomTransformerEncoderLayer:
-    """modules/layers/custom_attention_encoder.py:140-219: `kernel`, `learnable_kernel` and `chebyshev_kernel` attention."""
-    if config.attention_type not in ("kernel", "learnable_kernel", "chebyshev_kernel"):
-        raise NotImplementedError(
-            f"attention_type={config.attention_type!r}: 'kernel', 'learnable_kernel' and 'chebyshev_kernel' are built "
-            "('local' is SURVEY.md section 8f-3)"
-        )
+    """modules/layers/custom_attention_encoder.py:140-219: `local`, `kernel`, `learnable_kernel` and `chebyshev_kernel`."""
+    if config.attention_type not in ("local", "kernel", "learnable_kernel", "chebyshev_kernel"):
+        raise RuntimeError(f"Unknown attention type: {config.attention_type}.")  # custom_attention_encoder.py:211-212
     if float(config.dropout) != 0.0:
         raise NotImplementedError("dropout must be 0 (configs/kernel_transformer_nvp.yaml:27); no dropout kernel exists")
+    if config.attention_type == "local":
+        assert config.max_radius is not None
+        local = LocalSelfAttention(input_dim=config.d_model, output_dim=config.d_model, num_heads=config.num_heads,
+                                   value_dim=config.d_model, key_query_dim=config.d_model, max_radius=config.max_radius)
+        return CustomTransformerEncoderLayer(d_model=config.d_model, self_attention=local, dim_feedforward=config.dim_feedforward)
     assert config.lengthscales is not None
     assert len(config.lengthscales) > 0
     assert config.normalise_kernel_values is not None
