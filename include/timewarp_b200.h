@@ -211,6 +211,19 @@ typedef struct tw_energy_system {
 int tw_peptide_energy(const tw_energy_system* sys, const float* coords, int64_t B, float* out_energy,
                       float* out_forces, float* out_terms, void* stream);
 
+/* `sim.step(n_steps)` of openmm_step (utils/evaluation_utils.py:439-464) for the integrators of
+ * simulation/md.py:116-123 (constraints=None), B conformations at once, in place on coords / velocs
+ * [B,n_atoms,3] (nm, nm/ps); masses [n_atoms] dalton; timestep ps; friction 1/ps; kT kJ/mol.
+ *   TW_INTEGRATOR_LANGEVIN         v' = a v + (1-a)/g F/m + sqrt(kT(1-a^2)/m) xi;  x' = x + dt v'   (a = exp(-g dt))
+ *   TW_INTEGRATOR_LANGEVIN_MIDDLE  v += dt F/m; x += dt/2 v; v = a v + sqrt(kT(1-a^2)/m) xi; x += dt/2 v
+ * xi = noise[n_steps,B,n_atoms,3] (standard normals supplied by the caller) or, noise == NULL,
+ * Philox4x32-10(seed, conformation*128 + thread) starting at `offset`. */
+#define TW_INTEGRATOR_LANGEVIN 0
+#define TW_INTEGRATOR_LANGEVIN_MIDDLE 1
+int tw_langevin_steps(const tw_energy_system* sys, float* coords, float* velocs, const float* masses, int64_t B,
+                      int32_t n_steps, int32_t integrator, double timestep, double friction, double kT,
+                      const float* noise, uint64_t seed, uint64_t offset, void* stream);
+
 /* compute_chirality_sign + check_symmetry_change (utils/chirality.py:41-80): centers [C,4] int64
  * (centre, 3 neighbours).  out_signs [B,C] fp32 (optional) = sign of the triple product;
  * out_changed [B] uint8 (optional, needs ref_signs [C] fp32) = any(sign != ref_sign). */

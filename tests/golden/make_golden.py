@@ -353,7 +353,34 @@ def dataloader_case():
 
 
 
+def md_case():
+    """Consecutive integrator steps and kinetic energies recorded in the reference's OpenMM trajectory fixtures (preset
+    "T1-peptides": LangevinIntegrator 310 K, 0.3 / ps, 0.5 fs, simulation/md.py:75-82) -> tests/golden/langevin_2olx_pairs.npz.
+    Pins oracle/md_oracle.py (update rule, noise scale, leapfrog kinetic energy, OpenMM element masses)."""
+    pdb = open(os.path.join(REF, "simulation/testdata/implicit-2olx-traj-cpu-state0.pdb")).read().splitlines()
+    elements = np.array([l[76:78].strip() for l in pdb if l.startswith(("ATOM", "HETATM"))])
+    out = {"elements": elements, "timestep_ps": 0.0005, "friction_per_ps": 0.3, "temperature_K": 310.0}
+    x0, v0, f0, x1, v1 = [], [], [], [], []
+    for rel in ("simulation/testdata/implicit-2olx-traj-cpu-arrays.npz", "simulation/testdata/implicit-2olx-traj-arrays.npz",
+                "testdata/output/2olx-traj-arrays.npz"):
+        d = np.load(os.path.join(REF, rel))
+        st = d["step"]
+        first = [i for i in range(len(st) - 1) if st[i + 1] == st[i] + 1][:10]  # 10 steps per fixture keep the file small
+        for i in first:
+            if True:
+                x0.append(d["positions"][i]), v0.append(d["velocities"][i]), f0.append(d["forces"][i])
+                x1.append(d["positions"][i + 1]), v1.append(d["velocities"][i + 1])
+    out.update(x0=np.stack(x0), v0=np.stack(v0), f0=np.stack(f0), x1=np.stack(x1), v1=np.stack(v1))
+    d = np.load(os.path.join(REF, "simulation/testdata/implicit-2olx-traj-cpu-arrays.npz"))  # checked by simulation/tests/test_md.py:35-47
+    out.update(ke_velocities=d["velocities"], ke_forces=d["forces"], ke_openmm=d["energies"][:, 1])
+    np.savez_compressed(os.path.join(HERE, "langevin_2olx_pairs.npz"), **out)
+    print("md case:", len(x0), "consecutive steps,", len(d["step"]), "kinetic energies")
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "md":
+        md_case()
+        sys.exit(0)
     torch.set_num_threads(8)
     if len(sys.argv) > 1 and sys.argv[1] == "learnable":
         learnable_cases()
@@ -380,5 +407,6 @@ if __name__ == "__main__":
     learnable_cases()
     chebyshev_cases()
     local_cases()
+    md_case()
     dataloader_case()
 

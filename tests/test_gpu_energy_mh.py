@@ -328,3 +328,132 @@ def test_forces_match_finite_differences(pep_fn, gb):
     torch.testing.assert_close(energy(xt), e, rtol=0, atol=0)  # the no-grad path gives the same energies
     # translation invariance: forces sum to zero
     assert float(f.sum(1).abs().max()) < 1e-3 * fmax
+
+
+# ------------------------------------------------------------------------------------------
+# OpenMM integrator steps inside the chain: tw_langevin_steps vs oracle/md_oracle.py (itself pinned to
+# the reference's trajectory fixtures, tests/test_md_oracle.py)
+def _md_setup(pep, friction=0.3, middle=False, temperature=310.0):
+    from timewarp_b200 import md
+
+    sysd = amber_like_system(pep)
+    cls = md.LangevinMiddleIntegrator if middle else md.LangevinIntegrator
+    return sysd, md.Simulation(sysd, cls(temperature, friction, 0.0005), seed=7)
+
+
+@pytest.mark.parametrize("middle", [False, True])
+def test_langevin_kernel_matches_oracle(middle):
+    from oracle import md_oracle as mo
+
+    pep = alanine_dipeptide()
+    sysd, sim = _md_setup(pep, middle=middle)
+    s32 = sysd.as_float32()
+    m32 = np.asarray(sysd.masses, dtype=np.float32).astype(np.float64)
+    rng = np.random.default_rng(3)
+    B, steps = 3, 3
+    x = _confs(pep, B, 4, noise=0.005)
+    v = (rng.standard_normal(x.shape) * np.sqrt(sim.kbT / m32)[:, None]).astype(np.float32)
+    noise = rng.standard_normal((steps, B, pep.num_atoms, 3)).astype(np.float32)
+    xg, vg = sim.step(torch.from_numpy(x).cuda(), torch.from_numpy(v).cuda(), steps, noise=torch.from_numpy(noise).cuda())
+    assert xg.shape == x.shape and xg.dtype == torch.float32
+    xo, vo = mo.integrate(lambda c: eo.potential_energy(s32, c), x, v, noise, m32, 0.0005, 0.3, sim.kbT, middle=middle)
+    np.testing.assert_allclose(xg.cpu().numpy(), xo, rtol=0, atol=5e-7)
+    np.testing.assert_allclose(vg.cpu().numpy(), vo, rtol=0, atol=5e-5)
+    assert np.abs(xo - x).max() > 1e-3  # the steps moved the atoms well beyond the tolerance
+    # zero steps / empty batch are no-ops; inputs are not modified
+    x_t = torch.from_numpy(x).cuda()
+    x0, v0 = sim.step(x_t, torch.from_numpy(v).cuda(), 0)
+    assert torch.equal(x0, x_t) and torch.equal(x_t.cpu(), torch.from_numpy(x))
+    xe, _ = sim.step(x_t[:0], torch.from_numpy(v).cuda()[:0], 2)
+    assert xe.shape == (0, pep.num_atoms, 3)
+
+
+def test_langevin_kernel_conserves_energy_without_friction():
+    """friction = 0 turns both rules into leapfrog / velocity Verlet: the total energy (kinetic part at the half-kicked
+    velocities, as OpenMM reports it) has no drift over 2000 steps."""
+    from oracle import md_oracle as mo
+
+    pep = tetrapeptide_2olx()
+    for middle in (False, True):
+        sysd, sim = _md_setup(pep, friction=0.0, middle=middle)
+        energy = PeptidePotentialEnergy(sysd)
+        m = np.asarray(sysd.masses, dtype=np.float64)
+        x = torch.from_numpy(_confs(pep, 4, 5, noise=0.002)).cuda()
+        v = sim.velocities_to_temperature(x)
+
+        def total(x, v):
+            u, f = energy.energy_and_forces(x)
+            vv, ff = v.cpu().numpy().astype(np.float64), f.cpu().numpy().astype(np.float64)
+            # both rules kick first: the stored velocity is half a kick short of the velocity that belongs to x
+            ke = mo.leapfrog_kinetic_energy(vv, ff, m, 0.0005)
+            return u.cpu().numpy()[:, 0].astype(np.float64) + ke, ke
+
+        e0, ke0 = total(x, v)
+        x1, v1 = sim.step(x, v, 2000)
+        e1, _ = total(x1, v1)
+        assert np.isfinite(e1).all()
+        assert np.abs(e1 - e0).max() < 0.02 * ke0.mean(), (middle, e0, e1, ke0)
+        assert (x1 - x).abs().max() > 0.01  # 1 ps of dynamics
+
+
+def test_langevin_kernel_thermostat_and_rng_stream():
+    """In-kernel Philox noise: reproducible per (seed, offset), advancing between calls, and the friction + noise pair
+    equilibrates the kinetic energy to kT/2 per degree of freedom."""
+    pep = alanine_dipeptide()
+    sysd, sim = _md_setup(pep, friction=20.0)
+    x = torch.from_numpy(_confs(pep, 256, 6, noise=0.002)).cuda()
+    v = torch.zeros_like(x)
+    xa, va = sim.step(x, v, 50)
+    xb, vb = sim.step(x, v, 50)  # the stream advanced: different noise
+    assert not torch.equal(va, vb)
+    _, sim2 = _md_setup(pep, friction=20.0)
+    xc, vc = sim2.step(x, v, 50)  # same seed, same offset: identical
+    assert torch.equal(xa, xc) and torch.equal(va, vc)
+    x1, v1 = sim.step(x, v, 3000)  # 1.5 ps, gamma t = 30
+    m = sim.masses(x.device)
+    ke_per_dof = (0.5 * m[None, :, None] * v1 * v1).mean().item()
+    assert abs(ke_per_dof / (0.5 * sim.kbT) - 1.0) < 0.03, ke_per_dof / (0.5 * sim.kbT)
+
+
+def test_sample_with_model_with_integrator_steps():
+    """openmm_on_current / openmm_on_proposal (utils/evaluation_utils.py:594-602,623-626): integrator steps inside the MH loop."""
+    from timewarp_b200 import md
+
+    pep = alanine_dipeptide()
+    sysd = amber_like_system(pep)
+    energy = PeptidePotentialEnergy(sysd)
+    sim = md.Simulation(sysd, md.get_simulation_environment_integrator("T1-peptides"))
+    assert isinstance(sim.integrator, md.LangevinIntegrator) and not isinstance(sim.integrator, md.LangevinMiddleIntegrator)
+    assert isinstance(md.get_simulation_environment_integrator("T1B-peptides"), md.LangevinMiddleIntegrator)
+    m, _ = build_model(TINY_O, "fp32", 0)
+    batch = _Batch(pep, "cuda")
+    masses = torch.as_tensor(pep.masses, dtype=torch.float32)
+    # (accept=False with the proposal-side steps: a rejected proposal would leave no trace of them in the chain)
+    for kw in (dict(openmm_on_current=True, accept=True), dict(openmm_on_proposal=True, accept=False)):
+        torch.manual_seed(0)
+        coords, velocs, accepted, stats = sampling.sample_with_model(
+            batch, m, torch.device("cuda"), energy, masses, num_samples=6, random_velocs=True, resample_velocs=True,
+            num_openmm_steps=5, sim=sim, num_proposal_steps=1, **kw)
+        assert coords.shape == (7, pep.num_atoms, 3) and np.isfinite(coords).all() and len(stats) == 6
+        torch.manual_seed(0)
+        plain = sampling.sample_with_model(batch, m, torch.device("cuda"), energy, masses, num_samples=6, accept=kw["accept"],
+                                           random_velocs=True, resample_velocs=True, num_proposal_steps=1)[0]
+        assert not np.allclose(plain, coords)
+    with pytest.raises(ValueError):
+        md.openmm_step(sim, torch.zeros(1, pep.num_atoms, 3, device="cuda"))
+
+
+def test_kinetic_energy_matches_openmm_fixture():
+    """compute_kinetic_energy with masses (utils/evaluation_utils.py:432-436) on the velocities of the reference's OpenMM
+    trajectory fixture reproduces the kinetic energies OpenMM recorded (simulation/tests/test_md.py:35-47 data)."""
+    import os
+    from tests.common import GOLDEN
+
+    g = np.load(os.path.join(GOLDEN, "langevin_2olx_pairs.npz"))
+    pep = tetrapeptide_2olx()
+    m = pep.masses
+    v = g["ke_velocities"].astype(np.float64) + 0.5 * float(g["timestep_ps"]) * g["ke_forces"].astype(np.float64) / m[:, None]
+    kbT = 2.577483411627504
+    ke = sampling.compute_kinetic_energy(torch.from_numpy(v.astype(np.float32)).cuda(), torch.from_numpy(m.astype(np.float32)).cuda(),
+                                         random_velocs=False, kbT=kbT)
+    np.testing.assert_allclose(ke.cpu().numpy() * kbT, g["ke_openmm"], rtol=3e-6, atol=0)

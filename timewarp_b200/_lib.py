@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(HERE, "libtimewarp_b200.so")
 
 TW_OK = 0
 TW_ATTENTION_KERNEL, TW_ATTENTION_LOCAL, TW_ATTENTION_CHEBYSHEV = 0, 1, 2
+TW_INTEGRATOR_LANGEVIN, TW_INTEGRATOR_LANGEVIN_MIDDLE = 0, 1
 TW_MAX_MLP_HIDDEN = 4
 TW_MAX_HEADS = 16
 PRECISION = {"fp32": 0, "bf16x3": 1, "bf16": 2}
@@ -74,6 +75,8 @@ _SIGNATURES = {
     "tw_flow_log_likelihood": (C.c_int, [C.POINTER(FlowConfig), _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I32, _P, _P, _P, _P, _P, C.c_size_t, _P]),
     "tw_flow_sample": (C.c_int, [C.POINTER(FlowConfig), _P, _P, _P, _P, _P, _I64, _I64, _I64, _I32, _P, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
     "tw_peptide_energy": (C.c_int, [C.POINTER(EnergySystem), _P, _I64, _P, _P, _P, _P]),
+    "tw_langevin_steps": (C.c_int, [C.POINTER(EnergySystem), _P, _P, _P, _I64, _I32, _I32, C.c_double, C.c_double, C.c_double, _P,
+                                    C.c_uint64, C.c_uint64, _P]),
     "tw_chirality": (C.c_int, [_P, _P, _P, _I64, _I64, _I32, _P, _P, _P]),
     "tw_kinetic_energy": (C.c_int, [_P, _P, C.c_float, _I64, _I64, _P, _P]),
     "tw_mh_accept": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I64, _I64, _P, _P, _P, _P, _P, _P, _P, _P, _P]),

@@ -10,6 +10,7 @@
 // PARITY UNPINNED against the reference's golden energies (no force-field parameter files on
 // this machine); pinned against oracle/energy_oracle.py (independent fp64 numpy restatement).
 #include "common.cuh"
+#include <curand_kernel.h>
 
 namespace tw {
 
@@ -36,31 +37,18 @@ __device__ __forceinline__ void add3(double* g, int i, const Vec3& v, double w) 
   atomicAdd(&g[3 * i + 2], w * v.z);
 }
 
-// kForces: also accumulate the analytic gradient dE/dx of every term in shared memory (fp64) and write the forces
-// F = -dE/dx (what OpenMM returns and bgflow feeds back as the gradient, openmm_bridge.py:56-60).  The GB term needs the
-// chain rule through the Born radii: dE/dB_i is accumulated with the pair energies, then a second pair loop applies
-// dB_i/dr_ij (derivative of the OBC descreening integral).  Formulas checked against central differences of the fp64
-// oracle (tests/test_gpu_energy_mh.py::test_forces_match_finite_differences).
+// Energy terms (and, kForces, dE/dx in `grad`) of the conformation held in shared memory (`pos`); every thread of the block
+// calls it; e[5] = this thread's partial sums of bond, angle, torsion, nonbonded(+exceptions), GB/SA.  `grad`, `dEdB`, `dBds`
+// are contiguous (5N doubles) and are zeroed here.
 template <bool kForces>
-__global__ void __launch_bounds__(ENERGY_THREADS) k_energy(tw_energy_system s, const float* __restrict__ coords,
-                                                           float* __restrict__ out_energy, float* __restrict__ out_terms,
-                                                           float* __restrict__ out_forces) {
-  extern __shared__ double sm[];
+__device__ __forceinline__ void energy_terms(const tw_energy_system& s, const Vec3* pos, double* born, double* grad, double* dEdB,
+                                             double* dBds, double (&e)[5]) {
   const int N = s.n_atoms;
-  Vec3* pos = reinterpret_cast<Vec3*>(sm);            // [N]
-  double* born = sm + 3 * (size_t)N;                  // [N]
-  double* grad = born + N;                            // [3N]  dE/dx          (kForces)
-  double* dEdB = grad + 3 * (size_t)N;                // [N]   dE/dBorn_i     (kForces)
-  double* dBds = dEdB + N;                            // [N]   dBorn_i/ds_i * 0.5 * (r_i - offset)   (kForces)
-  __shared__ double red[ENERGY_THREADS / 32][5];
   const int tid = threadIdx.x, nt = blockDim.x;
-  const int64_t b = blockIdx.x;
-  const float* cb = coords + b * (int64_t)N * 3;
-  for (int i = tid; i < N; i += nt) pos[i] = {(double)cb[i * 3], (double)cb[i * 3 + 1], (double)cb[i * 3 + 2]};
-  if (kForces)
+  if (kForces) {
     for (int i = tid; i < 5 * N; i += nt) grad[i] = 0.0;  // grad, dEdB, dBds are contiguous
-  __syncthreads();
-
+    __syncthreads();
+  }
   double e_bond = 0, e_angle = 0, e_tors = 0, e_nb = 0, e_gb = 0;
 
   // HarmonicBondForce: 1/2 k (r - r0)^2
@@ -281,7 +269,35 @@ __global__ void __launch_bounds__(ENERGY_THREADS) k_energy(tw_energy_system s, c
     }
   }
 
-  double v[5] = {e_bond, e_angle, e_tors, e_nb, e_gb};
+  e[0] = e_bond, e[1] = e_angle, e[2] = e_tors, e[3] = e_nb, e[4] = e_gb;
+  if (kForces) __syncthreads();  // every contribution to grad has landed
+}
+
+// kForces: also accumulate the analytic gradient dE/dx of every term in shared memory (fp64) and write the forces
+// F = -dE/dx (what OpenMM returns and bgflow feeds back as the gradient, openmm_bridge.py:56-60).  The GB term needs the
+// chain rule through the Born radii: dE/dB_i is accumulated with the pair energies, then a second pair loop applies
+// dB_i/dr_ij (derivative of the OBC descreening integral).  Formulas checked against central differences of the fp64
+// oracle (tests/test_gpu_energy_mh.py::test_forces_match_finite_differences).
+template <bool kForces>
+__global__ void __launch_bounds__(ENERGY_THREADS) k_energy(tw_energy_system s, const float* __restrict__ coords,
+                                                           float* __restrict__ out_energy, float* __restrict__ out_terms,
+                                                           float* __restrict__ out_forces) {
+  extern __shared__ double sm[];
+  const int N = s.n_atoms;
+  Vec3* pos = reinterpret_cast<Vec3*>(sm);            // [N]
+  double* born = sm + 3 * (size_t)N;                  // [N]
+  double* grad = born + N;                            // [3N]  dE/dx          (kForces)
+  double* dEdB = grad + 3 * (size_t)N;                // [N]   dE/dBorn_i     (kForces)
+  double* dBds = dEdB + N;                            // [N]   dBorn_i/ds_i * 0.5 * (r_i - offset)   (kForces)
+  __shared__ double red[ENERGY_THREADS / 32][5];
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int warp = tid >> 5, lane = tid & 31, nwarps = nt >> 5;
+  const int64_t b = blockIdx.x;
+  const float* cb = coords + b * (int64_t)N * 3;
+  for (int i = tid; i < N; i += nt) pos[i] = {(double)cb[i * 3], (double)cb[i * 3 + 1], (double)cb[i * 3 + 2]};
+  __syncthreads();
+  double v[5];
+  energy_terms<kForces>(s, pos, born, grad, dEdB, dBds, v);
 #pragma unroll
   for (int k = 0; k < 5; k++) {
     double t = warp_sum_d(v[k]);
@@ -299,10 +315,73 @@ __global__ void __launch_bounds__(ENERGY_THREADS) k_energy(tw_energy_system s, c
     out_energy[b] = (float)tot;
   }
   if (kForces) {
-    __syncthreads();  // (the reduction above already separated the last accumulation from here; kept for clarity)
     float* fb = out_forces + b * (int64_t)N * 3;
     for (int i = tid; i < 3 * N; i += nt) fb[i] = (float)(-grad[i]);
   }
+}
+
+
+// ------------------------------------------------------------------------------------------
+// OpenMM integrator steps on the device: the `sim.step(num_steps)` of openmm_step (utils/evaluation_utils.py:439-464) for the
+// integrators of simulation/md.py:116-123, constraints=None (md.py:171,180).  One thread block per conformation; positions,
+// velocities and forces stay in shared memory (fp64) for all n_steps; the force evaluation is energy_terms<true>.
+//   kMiddle = false, LangevinIntegrator (OpenMM ReferenceStochasticDynamics / langevin.cu):
+//       v' = a v + (1 - a)/gamma * F(x)/m + sqrt(kT (1 - a^2) / m) * xi,   x' = x + dt v',      a = exp(-gamma dt)
+//     (gamma = 0: (1 - a)/gamma -> dt).  PINNED by the reference's trajectory fixtures: consecutive frames of
+//     simulation/testdata/implicit-2olx-traj*-arrays.npz satisfy x' = x + dt v' to fp32 round-off and the implied xi has
+//     unit variance (tests/test_md_oracle.py).
+//   kMiddle = true, LangevinMiddleIntegrator (OpenMM >= 7.5, LangevinMiddleIntegrator docs / langevinMiddle.cu):
+//       v += dt F(x)/m;  x += dt/2 v;  v = a v + sqrt(kT (1 - a^2) / m) * xi;  x += dt/2 v
+//     restated from OpenMM's documentation (no fixture of the reference was generated with it that contains consecutive frames).
+// xi: the caller's standard normals noise[step, b, atom, 3] (torch RNG), or, noise == NULL, Philox4x32-10 keyed by
+// (seed, conformation * blockDim + thread) at `offset`.
+template <bool kMiddle>
+__global__ void __launch_bounds__(ENERGY_THREADS) k_langevin(tw_energy_system s, float* __restrict__ coords, float* __restrict__ velocs,
+                                                             const float* __restrict__ masses, const float* __restrict__ noise,
+                                                             int64_t B, int n_steps, double dt, double vscale, double fscale,
+                                                             double kT, unsigned long long seed, unsigned long long offset) {
+  extern __shared__ double sm[];
+  const int N = s.n_atoms;
+  Vec3* pos = reinterpret_cast<Vec3*>(sm);  // [N]
+  double* born = sm + 3 * (size_t)N;        // [N]
+  double* grad = born + N;                  // [3N]
+  double* dEdB = grad + 3 * (size_t)N;      // [N]
+  double* dBds = dEdB + N;                  // [N]
+  double* vel = dBds + N;                   // [3N]
+  double* invm = vel + 3 * (size_t)N;       // [N]
+  double* x = sm;                           // pos as a flat [3N] array
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int64_t b = blockIdx.x;
+  float* cb = coords + b * (int64_t)N * 3;
+  float* vb = velocs + b * (int64_t)N * 3;
+  for (int i = tid; i < 3 * N; i += nt) x[i] = (double)cb[i], vel[i] = (double)vb[i];
+  for (int i = tid; i < N; i += nt) invm[i] = 1.0 / (double)masses[i];
+  curandStatePhilox4_32_10_t rng;
+  if (!noise) curand_init(seed, (unsigned long long)b * nt + tid, offset, &rng);
+  const double nscale = sqrt(kT * (1.0 - vscale * vscale));
+  __syncthreads();
+  double e[5];
+  for (int step = 0; step < n_steps; step++) {
+    energy_terms<true>(s, pos, born, grad, dEdB, dBds, e);  // grad = dE/dx = -F; ends with a block barrier
+    const float* nz = noise ? noise + ((int64_t)step * B + b) * (int64_t)N * 3 : nullptr;
+    for (int i = tid; i < 3 * N; i += nt) {
+      const double im = invm[i / 3];
+      const double xi = nz ? (double)nz[i] : (double)curand_normal(&rng);
+      double v = vel[i];
+      if (kMiddle) {
+        v -= dt * grad[i] * im;
+        double xx = x[i] + 0.5 * dt * v;
+        v = vscale * v + nscale * sqrt(im) * xi;
+        x[i] = xx + 0.5 * dt * v;
+      } else {
+        v = vscale * v - fscale * grad[i] * im + nscale * sqrt(im) * xi;
+        x[i] += dt * v;
+      }
+      vel[i] = v;
+    }
+    __syncthreads();
+  }
+  for (int i = tid; i < 3 * N; i += nt) cb[i] = (float)x[i], vb[i] = (float)vel[i];
 }
 
 }  // namespace tw
@@ -337,6 +416,47 @@ extern "C" int tw_peptide_energy(const tw_energy_system* sys, const float* coord
     else
       k_energy<false><<<(unsigned)B, ENERGY_THREADS, smem, (cudaStream_t)stream>>>(*sys, coords, out_energy, out_terms, nullptr);
   }
+  TW_LAUNCH_CHECK();
+  return TW_OK;
+}
+
+static int check_system(const tw_energy_system* sys) {
+  TW_CHECK_ARG(sys != nullptr, "NULL system");
+  TW_CHECK_ARG(sys->n_atoms >= 1 && sys->n_atoms <= 4096, "n_atoms out of range (1..4096)");
+  TW_CHECK_ARG(sys->n_bonds == 0 || (sys->bond_idx && sys->bond_param), "bond arrays missing");
+  TW_CHECK_ARG(sys->n_angles == 0 || (sys->angle_idx && sys->angle_param), "angle arrays missing");
+  TW_CHECK_ARG(sys->n_torsions == 0 || (sys->torsion_idx && sys->torsion_param), "torsion arrays missing");
+  TW_CHECK_ARG(sys->n_exceptions == 0 || (sys->exception_idx && sys->exception_param), "exception arrays missing");
+  TW_CHECK_ARG(sys->charge && sys->sigma && sys->epsilon && sys->excluded, "nonbonded arrays missing");
+  TW_CHECK_ARG(!sys->use_gb || (sys->gb_radius && sys->gb_scale), "GB arrays missing");
+  return TW_OK;
+}
+
+extern "C" int tw_langevin_steps(const tw_energy_system* sys, float* coords, float* velocs, const float* masses, int64_t B,
+                                 int32_t n_steps, int32_t integrator, double timestep, double friction, double kT,
+                                 const float* noise, uint64_t seed, uint64_t offset, void* stream) {
+  TW_TRY(check_system(sys));
+  TW_CHECK_ARG(integrator == TW_INTEGRATOR_LANGEVIN || integrator == TW_INTEGRATOR_LANGEVIN_MIDDLE, "unknown integrator");
+  TW_CHECK_ARG(n_steps >= 0 && timestep > 0 && friction >= 0 && kT >= 0, "bad integrator parameters");
+  if (B == 0 || n_steps == 0) return TW_OK;
+  TW_CHECK_ARG(coords && velocs && masses, "NULL pointer");
+  TW_CHECK_ARG(B >= 0 && B <= 2147483647LL, "bad batch size");
+  TW_CHECK_ARG(sys->n_atoms <= 1536, "integrator: n_atoms out of range (1..1536)");
+  const size_t smem = (size_t)sys->n_atoms * 13 * sizeof(double);
+  static bool attr_set = false;
+  if (smem > 48 * 1024 && !attr_set) {
+    TW_CUDA(cudaFuncSetAttribute(k_langevin<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 1536 * 13 * (int)sizeof(double)));
+    TW_CUDA(cudaFuncSetAttribute(k_langevin<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 1536 * 13 * (int)sizeof(double)));
+    attr_set = true;
+  }
+  const double vscale = exp(-timestep * friction);
+  const double fscale = friction == 0 ? timestep : (1.0 - vscale) / friction;
+  if (integrator == TW_INTEGRATOR_LANGEVIN_MIDDLE)
+    k_langevin<true><<<(unsigned)B, ENERGY_THREADS, smem, (cudaStream_t)stream>>>(*sys, coords, velocs, masses, noise, B, n_steps, timestep,
+                                                                                 vscale, fscale, kT, seed, offset);
+  else
+    k_langevin<false><<<(unsigned)B, ENERGY_THREADS, smem, (cudaStream_t)stream>>>(*sys, coords, velocs, masses, noise, B, n_steps, timestep,
+                                                                                  vscale, fscale, kT, seed, offset);
   TW_LAUNCH_CHECK();
   return TW_OK;
 }

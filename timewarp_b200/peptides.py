@@ -17,7 +17,10 @@ from typing import Dict, List, Sequence, Tuple
 import numpy as np
 
 ELEMENT_VOCAB: Dict[str, int] = {"C": 0, "H": 1, "N": 2, "O": 3, "S": 4}
-ATOMIC_MASS: Dict[str, float] = {"H": 1.008, "C": 12.011, "N": 14.007, "O": 15.999, "S": 32.06}
+# OpenMM's element masses (dalton): what `system.getParticleMass` returns in the reference (evaluate.py:303-305).  H, C, N, O are
+# pinned to 1e-5 kJ/mol by the kinetic energies recorded in simulation/testdata/implicit-2olx-traj-cpu-arrays.npz
+# (tests/test_md_oracle.py); S is OpenMM's tabulated value.
+ATOMIC_MASS: Dict[str, float] = {"H": 1.007947, "C": 12.01078, "N": 14.00672, "O": 15.99943, "S": 32.0655}
 
 # intra-residue bonds by atom name
 _BACKBONE = [("N", "H"), ("N", "CA"), ("CA", "HA"), ("CA", "C"), ("C", "O"), ("CA", "CB")]

@@ -216,8 +216,7 @@ def sample_with_model(batch, model, device, openmm_potential_energy_torch, masse
     One 4-byte device->host read per iteration (the first accepted index) is inherent to the
     reference's variable-length bookkeeping; everything else stays on the device."""
     assert batch.atom_coords.size(0) == 1, "only batch-size of 1 is supported"  # :517
-    if (openmm_on_current or openmm_on_proposal) and num_openmm_steps > 0 and sim is not None:
-        raise NotImplementedError("OpenMM integrator steps inside the chain are not available (no OpenMM; SURVEY.md section 8f-2)")
+    from .md import openmm_step  # `sim` is a timewarp_b200.md.Simulation (integrator steps run in the tw_langevin_steps kernel)
     energy = openmm_potential_energy_torch
     x_coords = batch.atom_coords.to(device).to(torch.float32).contiguous()
     x_velocs = torch.randn_like(x_coords) if random_velocs else batch.atom_velocs.to(device).to(torch.float32).contiguous()  # :530-533
@@ -232,6 +231,14 @@ def sample_with_model(batch, model, device, openmm_potential_energy_torch, masse
             edge_batch_idx=edge_batch_idx, masked_elements=masked_elements, num_samples=1)
         x_coords, x_velocs = x_coords.squeeze(0), x_velocs.squeeze(0)
     kbT = energy.kbT  # :555
+    md_steps = num_openmm_steps > 0 and sim is not None
+    if md_steps and (openmm_on_current or openmm_on_proposal):
+        velocs_std = torch.sqrt(kbT / masses)[None, :, None]  # :556
+    if openmm_on_current and md_steps:  # :559-565
+        if random_velocs:
+            x_coords, _ = openmm_step(sim, x_coords, x_velocs * velocs_std, num_steps=num_openmm_steps)
+        else:
+            x_coords, x_velocs = openmm_step(sim, x_coords, x_velocs, num_steps=num_openmm_steps)
     sampled_coords = [x_coords.cpu().numpy()]
     sampled_velocs = [x_velocs.cpu().numpy()]
     accepted = 0
@@ -246,6 +253,11 @@ def sample_with_model(batch, model, device, openmm_potential_energy_torch, masse
         S = num_proposal_steps
         if random_velocs and resample_velocs:
             x_velocs = torch.randn_like(x_velocs)  # :590-592
+        if openmm_on_current and md_steps:  # :594-602
+            if random_velocs:
+                x_coords, _ = openmm_step(sim, x_coords, x_velocs * velocs_std, num_steps=num_openmm_steps)
+            else:
+                x_coords, x_velocs = openmm_step(sim, x_coords, x_velocs, num_steps=num_openmm_steps)
         if rotate:  # :604-607
             raise NotImplementedError("rotate=True: the reference applies `(Q @ x_coords.T).T` to [1, V, 3] tensors (evaluation_utils.py:604-607), which only type-checks for V == 3; not reproduced")
         y_coords, y_velocs, p_xy = model.conditional_sample_with_logp(
@@ -253,6 +265,8 @@ def sample_with_model(batch, model, device, openmm_potential_energy_torch, masse
             masked_elements=masked_elements, num_samples=S)  # :609-617
         y_coords, y_velocs = y_coords.squeeze(1).contiguous(), y_velocs.squeeze(1).contiguous()
         x_rep, xv_rep = x_coords.repeat(S, 1, 1), x_velocs.repeat(S, 1, 1)  # :620-621
+        if openmm_on_proposal and md_steps:  # :623-626 (the reference's openmm_step handles S == 1 only; here every proposal steps)
+            y_coords, _ = openmm_step(sim, y_coords, y_velocs * velocs_std, num_steps=num_openmm_steps)
         e_pot_x = (energy(x_coords) / kbT).squeeze(-1).repeat(S)  # :628 (S identical evaluations in the reference)
         e_kin_x = compute_kinetic_energy(xv_rep, masses, random_velocs=random_velocs, kbT=kbT)
         e_kin_y = compute_kinetic_energy(y_velocs, masses, random_velocs=random_velocs, kbT=kbT)
