@@ -353,6 +353,18 @@ def dataloader_case():
 
 
 
+def checkpoint_case():
+    """A checkpoint written by the reference's own `save_model` (utilities/model_utils.py:12-29) for the model of the
+    `tiny_ad` case -> tests/golden/ckpt/run0/best_model.pt."""
+    from utilities.model_utils import save_model
+
+    model = ref_model(TINY, 0)[0]
+    d = os.path.join(HERE, "ckpt", "run0")
+    os.makedirs(d, exist_ok=True)
+    save_model(os.path.join(d, "best_model.pt"), model, step=123)
+    print("checkpoint case written")
+
+
 def md_case():
     """Consecutive integrator steps and kinetic energies recorded in the reference's OpenMM trajectory fixtures (preset
     "T1-peptides": LangevinIntegrator 310 K, 0.3 / ps, 0.5 fs, simulation/md.py:75-82) -> tests/golden/langevin_2olx_pairs.npz.
@@ -378,6 +390,9 @@ def md_case():
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "checkpoint":
+        checkpoint_case()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "md":
         md_case()
         sys.exit(0)
@@ -408,5 +423,6 @@ if __name__ == "__main__":
     chebyshev_cases()
     local_cases()
     md_case()
+    checkpoint_case()
     dataloader_case()
 

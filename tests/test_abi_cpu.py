@@ -81,6 +81,35 @@ def test_seeded_init_matches_reference_local():
         assert np.array_equal(sd[k].numpy(), ref[k]), k
 
 
+def test_reference_checkpoint_loads(tmp_path):
+    """utilities/model_utils.py:32-63: a checkpoint written by the reference's own save_model (tests/golden/ckpt, made by
+    make_golden.py::checkpoint_case) loads verbatim, from the file or from a run directory; DeepSpeed-style "module" key too."""
+    from oracle import flow_oracle as fo
+    from timewarp_b200 import checkpoint as ck
+
+    def ctor(data):
+        assert "module" in data or data["step"] == 123  # extra keys of save_model(**kwargs) are handed to the constructor
+        return tw.custom_transformer_nvp_constructor(model_config(TINY_O, "fp32"))
+
+    want = fo.synth_state_dict(TINY_O, 0)
+    for path in (os.path.join(GOLDEN, "ckpt"), os.path.join(GOLDEN, "ckpt", "run0", "best_model.pt")):
+        m = ck.load_model(path, ctor, weights_only=True)
+        sd = m.state_dict()
+        assert set(sd) == set(want)
+        for k in want:
+            assert torch.equal(sd[k], want[k]), k
+    ck.save_model(tmp_path / "best_model.pt", m, step=123)  # round trip through our writer
+    assert set(ck.load_model_state_dict(tmp_path)) == set(want)
+    torch.save({"module": m.state_dict()}, tmp_path / "ds.pt")
+    m2 = ck.load_model(tmp_path / "ds.pt", ctor)
+    assert torch.equal(m2.state_dict()["flow.atom_embedder.weight"], want["flow.atom_embedder.weight"])
+    os.makedirs(tmp_path / "a"), os.makedirs(tmp_path / "b")
+    for d in "ab":
+        torch.save({}, tmp_path / d / "x.pt")
+    with pytest.raises(AssertionError):
+        ck.load_checkpoint_in_subdir(tmp_path, "x.pt")  # two candidates: unique_item fails like the reference
+
+
 def test_config_validation(lib):
     bad = model_config(TINY_O, "fp32")
     bad.num_coupling_layers = 3

@@ -457,3 +457,27 @@ def test_kinetic_energy_matches_openmm_fixture():
     ke = sampling.compute_kinetic_energy(torch.from_numpy(v.astype(np.float32)).cuda(), torch.from_numpy(m.astype(np.float32)).cuda(),
                                          random_velocs=False, kbT=kbT)
     np.testing.assert_allclose(ke.cpu().numpy() * kbT, g["ke_openmm"], rtol=3e-6, atol=0)
+
+
+def test_sample_trajectory_writes_and_resumes(tmp_path):
+    """sample_trajectory.py:217-281: chunk files `{protein}_trajectory_model_{i}.npz` (positions[::10], time); a second call
+    with a larger budget resumes after the chunks on disk, starting from the last saved position."""
+    pep = alanine_dipeptide()
+    m, _ = build_model(TINY_O, "fp32", 0)
+    energy = PeptidePotentialEnergy(amber_like_system(pep))
+    masses = torch.tensor(pep.masses, dtype=torch.float32)
+    out = str(tmp_path / "chain")
+    batch = _Batch(pep, "cuda")
+    assert sampling.sample_trajectory(batch, m, torch.device("cuda"), energy, masses, out, "ad", num_samples=40, saving_interval=20,
+                                      mh=False, conserve_chirality=True) == 0
+    import os
+    assert sorted(os.listdir(out)) == ["ad_trajectory_model_0.npz", "ad_trajectory_model_1.npz"]
+    z1 = np.load(os.path.join(out, "ad_trajectory_model_1.npz"))
+    assert z1["positions"].shape == (3, 22, 3) and float(z1["time"]) > 0  # 21 states thinned by 10
+    batch2 = _Batch(pep, "cuda")
+    sampling.sample_trajectory(batch2, m, torch.device("cuda"), energy, masses, out, "ad", num_samples=60, saving_interval=20, mh=False)
+    assert sorted(os.listdir(out))[-1] == "ad_trajectory_model_2.npz" and len(os.listdir(out)) == 3
+    z2 = np.load(os.path.join(out, "ad_trajectory_model_2.npz"))
+    np.testing.assert_array_equal(z2["positions"][0], z1["positions"][-1])  # resumed from the last saved position
+    with pytest.raises(AssertionError):
+        sampling.sample_trajectory(batch, m, torch.device("cuda"), energy, masses, out, "ad", num_samples=5, saving_interval=20)

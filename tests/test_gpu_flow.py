@@ -255,3 +255,19 @@ def test_chebyshev_kernel_module_surface():
     m.train()
     with pytest.raises(Exception):
         m(y_coords=g["y_coords"].cuda(), y_velocs=g["y_velocs"].cuda(), **kw)
+
+
+@torch.no_grad()
+def test_reference_checkpoint_reproduces_reference_log_likelihood():
+    """End to end drop-in: a checkpoint written by the reference's save_model (tests/golden/ckpt) loaded through
+    checkpoint.load_model gives the log-likelihoods the reference computed with those weights (tiny_ad golden)."""
+    import os
+    import timewarp_b200 as tw
+    from tests.common import GOLDEN, model_config
+    from timewarp_b200 import checkpoint as ck
+
+    m = ck.load_model(os.path.join(GOLDEN, "ckpt"), lambda data: tw.custom_transformer_nvp_constructor(model_config(TINY_O, "fp32")),
+                      weights_only=True).cuda().eval()
+    g = load_golden("tiny_ad")
+    ll = m.log_likelihood(y_coords=g["y_coords"].cuda(), y_velocs=g["y_velocs"].cuda(), **_kw(g))
+    assert_rel(ll, g["log_likelihood"], what="log_likelihood from a reference checkpoint")

@@ -413,3 +413,44 @@ def explore(model, energy, atom_types: Tensor, masked_elements: Tensor, x_coords
     if keep_trajectory:
         return torch.cat(traj, 0), torch.cat(etraj, 0), n_acc
     return y, energies, n_acc
+
+
+def sample_trajectory(batch, model, device, openmm_potential_energy_torch, masses: Tensor, output_dir: str, protein: str,
+                      num_samples: int, saving_interval: int, mh: bool = True, random_velocities: bool = True,
+                      resample_velocities: bool = True, initialize_randomly: bool = False, sim=None, openmm_on_current: bool = False,
+                      openmm_on_proposal: bool = False, num_openmm_steps: int = 0, num_proposal_steps: int = 1,
+                      adaptive_parallelism: bool = False, conserve_chirality: bool = False, thin: int = 10) -> int:
+    """The chunked, resumable sampling loop of sample_trajectory.py:217-281: `num_samples // saving_interval` calls of
+    sample_with_model, each written to `{output_dir}/{protein}_trajectory_model_{i}.npz` (positions[::10], wall time) -- the
+    files the paper notebooks read; a chain whose directory already holds chunks resumes from the last saved position."""
+    import os
+    from timeit import default_timer as timer
+
+    from .chirality import compute_chirality_sign, find_chirality_centers
+
+    num_iters = num_samples // saving_interval
+    assert num_iters > 0, "num_samples must be larger than saving_interval."  # :221
+    os.makedirs(output_dir, exist_ok=True)
+    chirality_centers = reference_signs = None
+    if conserve_chirality:  # :228-232
+        chirality_centers = find_chirality_centers(batch.adj_list, batch.atom_types).to(device)
+        reference_signs = compute_chirality_sign(batch.atom_coords.to(device), chirality_centers)
+    try:  # :235-241
+        n_saved_iterations = len(os.listdir(output_dir))
+        npz = np.load(os.path.join(output_dir, f"{protein}_trajectory_model_{n_saved_iterations - 1}.npz"))
+        batch.atom_coords = torch.from_numpy(npz["positions"][-1:])
+    except FileNotFoundError:
+        n_saved_iterations = 0
+    needs_sim = openmm_on_proposal or openmm_on_current
+    for i in range(n_saved_iterations, num_iters):
+        start = timer()
+        sampled_coords, _, _, _ = sample_with_model(
+            batch, model, device, openmm_potential_energy_torch, masses, saving_interval, mh, random_velocs=random_velocities,
+            resample_velocs=resample_velocities, initialize_randomly=initialize_randomly, sim=sim if needs_sim else None,
+            openmm_on_current=openmm_on_current, openmm_on_proposal=openmm_on_proposal, num_openmm_steps=num_openmm_steps,
+            num_proposal_steps=num_proposal_steps, adaptive_parallelism=adaptive_parallelism,
+            reference_signs=reference_signs, chirality_centers=chirality_centers, disable_tqdm=True)
+        duration = timer() - start
+        np.savez(os.path.join(output_dir, f"{protein}_trajectory_model_{i}.npz"), positions=sampled_coords[::thin], time=duration)  # :270-278
+        batch.atom_coords = torch.from_numpy(sampled_coords[-1:])  # :279
+    return 0
