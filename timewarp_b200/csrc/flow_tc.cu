@@ -1668,7 +1668,7 @@ __global__ void __launch_bounds__(kMixTokThreads, 1) k_mix_tok(MixArgs a) {
       tc_fence_after();
       MIX_TRACE(0, 1, it);
       const uint32_t x_hi = smem_u32(smem + L.xb(sb)), x_lo = x_hi + L.xb_bytes / 2;
-      const uint64_t b_hi = b_desc0 | (uint64_t)(x_hi >> 4), b_lo = b_desc0 | (uint64_t)(x_lo >> 4);
+      const uint64_t b_hi = b_desc0 | (uint64_t)((x_hi >> 4) & 0x3FFF), b_lo = b_desc0 | (uint64_t)((x_lo >> 4) & 0x3FFF);
       for (int h = 0; h < H; h++, hcount++) {
         const int db = (int)(hcount & 1);
         if (hcount >= 2) {
@@ -1682,7 +1682,7 @@ __global__ void __launch_bounds__(kMixTokThreads, 1) k_mix_tok(MixArgs a) {
         if (elect_one()) {
           // descriptors differ only in the 14-bit start-address field (16-byte units): one 64-bit add per k step
           const uint32_t s_hi = smem_u32(smem + L.ring() + stage * L.stage_bytes), s_lo = s_hi + mat_bytes;
-          const uint64_t a_hi = a_desc0 | (uint64_t)(s_hi >> 4), a_lo = a_desc0 | (uint64_t)(s_lo >> 4);
+          const uint64_t a_hi = a_desc0 | (uint64_t)((s_hi >> 4) & 0x3FFF), a_lo = a_desc0 | (uint64_t)((s_lo >> 4) & 0x3FFF);  // (mask: inside a cluster the shared-window address carries the CTA rank)
           const uint32_t d = tmem + db * 128;
 #pragma unroll
           for (int k = 0; k < kMixTokMaxVP / 16; k++)
@@ -2104,7 +2104,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) k_attn_fused(AttnArgs a) {
     const uint64_t a_desc0 = make_smem_desc(0, 128, (uint32_t)(VP >> 3) * 128, LAYOUT_NONE);
     const uint64_t b_desc0 = make_smem_desc(0, (uint32_t)VP * 128, 1024, LAYOUT_SW128);
     const uint32_t x_hi = smem_u32(smem + L.xb()), x_lo = x_hi + L.xb_bytes / 2;
-    const uint64_t b_hi = b_desc0 | (uint64_t)(x_hi >> 4), b_lo = b_desc0 | (uint64_t)(x_lo >> 4);
+    const uint64_t b_hi = b_desc0 | (uint64_t)((x_hi >> 4) & 0x3FFF), b_lo = b_desc0 | (uint64_t)((x_lo >> 4) & 0x3FFF);
 
     auto issue_mma2 = [&](int64_t gp, int hp, int dob) {  // DO[dob] += mixed(gp) W_c,hp^T
       const int b = (int)(gp & 1);
@@ -2164,7 +2164,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) k_attn_fused(AttnArgs a) {
         AT_TRACE(0, 1, g);
         if (elect_one()) {
           const uint32_t s_hi = smem_u32(smem + L.sc() + ss * L.sc_stage), s_lo = s_hi + mat_bytes;
-          const uint64_t a_hi = a_desc0 | (uint64_t)(s_hi >> 4), a_lo = a_desc0 | (uint64_t)(s_lo >> 4);
+          const uint64_t a_hi = a_desc0 | (uint64_t)((s_hi >> 4) & 0x3FFF), a_lo = a_desc0 | (uint64_t)((s_lo >> 4) & 0x3FFF);  // (mask: inside a cluster the shared-window address carries the CTA rank)
           const uint32_t d = tmem + AT_DM + (uint32_t)(g & 1) * 128;
 #pragma unroll
           for (int k = 0; k < kMixTokMaxVP / 16; k++)
