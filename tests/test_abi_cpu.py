@@ -100,9 +100,23 @@ def test_reference_checkpoint_loads(tmp_path):
             assert torch.equal(sd[k], want[k]), k
     ck.save_model(tmp_path / "best_model.pt", m, step=123)  # round trip through our writer
     assert set(ck.load_model_state_dict(tmp_path)) == set(want)
+    # optimizer state survives exactly (reference tests/test_training_utils.py:23-67)
+    opt = torch.optim.Adam(m.parameters(), lr=1e-3)
+    for q in m.parameters():
+        q.grad = torch.full_like(q, 0.01)
+    opt.step()
+    os.makedirs(tmp_path / "opt")
+    ck.save_model(tmp_path / "opt" / "best_model.pt", m, optimizer=opt)
+    data = ck.load_checkpoint_in_subdir(tmp_path / "opt")
+    opt2 = torch.optim.Adam(ctor({"module": None}).parameters(), lr=1e-3)
+    opt2.load_state_dict(data["optimizer_state_dict"])
+    for a, b in zip(opt.state_dict()["state"].values(), opt2.state_dict()["state"].values()):
+        assert torch.equal(a["exp_avg"], b["exp_avg"]) and torch.equal(a["exp_avg_sq"], b["exp_avg_sq"])
+    for k, v in m.state_dict().items():
+        assert torch.equal(data["model_state_dict"][k], v)
     torch.save({"module": m.state_dict()}, tmp_path / "ds.pt")
     m2 = ck.load_model(tmp_path / "ds.pt", ctor)
-    assert torch.equal(m2.state_dict()["flow.atom_embedder.weight"], want["flow.atom_embedder.weight"])
+    assert torch.equal(m2.state_dict()["flow.atom_embedder.weight"], m.state_dict()["flow.atom_embedder.weight"])
     os.makedirs(tmp_path / "a"), os.makedirs(tmp_path / "b")
     for d in "ab":
         torch.save({}, tmp_path / d / "x.pt")

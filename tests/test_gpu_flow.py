@@ -271,3 +271,48 @@ def test_reference_checkpoint_reproduces_reference_log_likelihood():
     g = load_golden("tiny_ad")
     ll = m.log_likelihood(y_coords=g["y_coords"].cuda(), y_velocs=g["y_velocs"].cuda(), **_kw(g))
     assert_rel(ll, g["log_likelihood"], what="log_likelihood from a reference checkpoint")
+
+
+@pytest.mark.parametrize("attention_type", ["local", "kernel", "learnable_kernel"])
+def test_batching_reference_models(attention_type):
+    """The reference's own batching test (tests/test_batching.py:50-122,132-177) with its model configurations -- d_model 4,
+    dim_feedforward 8, two hidden MLP layers [8, 8], 2 coupling x 2 transformer layers; local: 2 heads, max_radius 0.5;
+    kernel / learnable_kernel: lengthscales [0.1, 0.2, 0.5, 1.0] -- on a ragged batch of two peptides (22 and 65 atoms):
+    batched log_likelihood == per-sample loop at rtol / atol 1e-4, and == the oracle."""
+    import timewarp_b200 as tw
+    from timewarp_b200.peptides import alanine_dipeptide, tetrapeptide_2olx
+
+    local = attention_type == "local"
+    enc = tw.CustomAttentionEncoderLayerConfig(
+        d_model=4, dim_feedforward=8, dropout=0.0, num_heads=2 if local else 4, attention_type=attention_type,
+        lengthscales=None if local else [0.1, 0.2, 0.5, 1.0], max_radius=0.5 if local else None,
+        normalise_kernel_values=None if local else False)
+    cfg = tw.CustomAttentionTransformerNVPConfig(atom_embedding_dim=4, latent_mlp_hidden_dims=[8, 8], num_coupling_layers=2,
+                                                 num_transformer_layers=2, encoder_layer_config=enc, precision="fp32")
+    torch.manual_seed(1)
+    m = tw.custom_transformer_nvp_constructor(cfg).cuda().eval()
+    peps = [alanine_dipeptide(), tetrapeptide_2olx()]
+    V = max(p.num_atoms for p in peps)
+    gen = torch.Generator().manual_seed(2)
+    at = torch.zeros(2, V, dtype=torch.long)
+    xc, mask = torch.zeros(2, V, 3), torch.ones(2, V, dtype=torch.bool)
+    for b, p in enumerate(peps):
+        n = p.num_atoms
+        at[b, :n], xc[b, :n], mask[b, :n] = torch.tensor(p.atom_types), torch.tensor(p.coords_nm, dtype=torch.float32), False
+    xv, yv = torch.randn(2, V, 3, generator=gen), torch.randn(2, V, 3, generator=gen)
+    yc = xc + 0.02 * torch.randn(2, V, 3, generator=gen)
+
+    def ll_of(rows, n):
+        return m.log_likelihood(atom_types=at[rows, :n].cuda(), x_coords=xc[rows, :n].cuda(), x_velocs=xv[rows, :n].cuda(),
+                                y_coords=yc[rows, :n].cuda(), y_velocs=yv[rows, :n].cuda(), adj_list=EMPTY_ADJ.cuda(),
+                                edge_batch_idx=EMPTY_EBI.cuda(), masked_elements=mask[rows, :n].cuda())
+
+    with torch.no_grad():
+        batched = ll_of(slice(0, 2), V)
+        for b, p in enumerate(peps):
+            torch.testing.assert_close(ll_of(slice(b, b + 1), p.num_atoms)[0], batched[b], rtol=1e-4, atol=1e-4)
+    ocfg = fo.OracleConfig(atom_embedding_dim=4, latent_mlp_hidden_dims=[8, 8], num_coupling_layers=2, num_transformer_layers=2,
+                           d_model=4, dim_feedforward=8, lengthscales=[] if local else [0.1, 0.2, 0.5, 1.0],
+                           attention_type=attention_type, max_radius=0.5 if local else 0.0, num_heads=2 if local else 0)
+    want = fo.log_likelihood({k: v.detach().cpu() for k, v in m.state_dict().items()}, ocfg, at, xc, xv, yc, yv, mask)
+    assert_rel(batched, want, what=f"{attention_type}: reference test configuration vs oracle")

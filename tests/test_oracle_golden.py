@@ -140,3 +140,20 @@ def test_chebyshev_scores(golden_dir, name, cfg):
     full = torch.tensor(fo.CHEB_COEFFS_EXPMX)[None, :]
     approx = fo.chebyshev_basis(s_, full, False)
     assert (approx - torch.exp(-(s_**2))).abs().max() < 1e-5
+
+
+def test_chebyshev_known_answers():
+    """The reference's own known answers for the Chebyshev-rational basis (tests/test_kernel_attention.py:163-208): five
+    expansion values from the Julia implementation, exp(-s^2) reproduced to 1e-2 on [0, 10] by the first six coefficients,
+    and the asymptotic-zero option."""
+    eye = torch.eye(5)
+    s = torch.full((1, 1, 1, 1), 0.7).sqrt()  # the basis squares its argument; the reference expands 0.7 directly
+    vals = torch.stack([fo.chebyshev_basis(s, eye[c][None], False).flatten()[0] for c in range(5)])
+    ref = torch.tensor([1.0, -0.17647058823529416, -0.9377162629757785, 0.507429269285569, 0.7586235796985188])
+    assert torch.allclose(vals, ref)
+    coeffs = torch.tensor([0.42758357, -0.54642403, 0.07106222, 0.05473271, 0.00574419, -0.00792641])[None].expand(3, -1)
+    torch.manual_seed(0)
+    d = 10.0 * torch.rand((2, 3, 64, 128))
+    assert torch.allclose(torch.exp(-(d**2.0)), fo.chebyshev_basis(d, coeffs, False), atol=1.0e-2, rtol=0.0)
+    far = fo.chebyshev_basis(1000.0 * torch.ones((1, 3, 1, 1)), coeffs, True).flatten()
+    assert torch.allclose(torch.zeros_like(far), far, atol=1.0e-6, rtol=0.0)
