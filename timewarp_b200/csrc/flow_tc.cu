@@ -58,15 +58,33 @@ bool tc_supported(const tw_flow_config* c) {
          c->dim_feedforward >= kFfnChunk && c->atom_embedding_dim + 9 <= 64 && c->num_heads >= 1;
 }
 
-// ---- pack kernels ---------------------------------------------------------------------------
-// One CTA writes one [rows x 64] K-major SW128 tile (hi and lo images) from a row-major fp32 matrix.
-__global__ void __launch_bounds__(256) k_pack_tiles(const float* __restrict__ W, int ldw, int n_rows, int n_cols, int rows,
-                                                    int tiles_k, uint8_t* __restrict__ dst, size_t tile_stride_r,
-                                                    size_t tile_stride_k, size_t lo_offset) {
-  // grid: (tiles_k, tiles_r).  tile (tr, tk) covers W rows tr*rows.., columns tk*64..
-  const int tk = blockIdx.x, tr = blockIdx.y;
-  uint8_t* hi = dst + tr * tile_stride_r + tk * tile_stride_k;
-  uint8_t* lo = hi + lo_offset;
+size_t tc_packed_bytes(const tw_flow_config* c) {
+  TcLayout L = TcLayout::make(c);
+  return L.total(c) + (size_t)L.D * L.H * L.D * sizeof(float) + 1024;  // + fp32 scratch for W_c
+}
+
+// ---- all weight images in ONE launch ----------------------------------------------------------
+// A training step re-packs every weight (the fp32 parameters changed): per-matrix launches are 240 kernels of ~12 us each
+// (latency, not bandwidth: 144 MB read, 150 MB written) = 2.75 ms of a 19 ms step.  k_pack_all does the same work with one CTA
+// per image tile; the job is decoded from blockIdx.x, the pointers travel in the kernel parameter block (groups of up to
+// kPackGroup conditioner networks).  The W_c tiles are computed in place (fp64 accumulation, so that attention becomes sum_h W_c,h (A_h x)).
+constexpr int kPackGroup = 16, kPackMaxT = 4;
+struct PackGroup {
+  const float* in_w1[kPackGroup];
+  const float* in_w2[kPackGroup];
+  const float* out_w1[kPackGroup];
+  const float* wv[kPackGroup][kPackMaxT];
+  const float* wo[kPackGroup][kPackMaxT];
+  const float* w1[kPackGroup][kPackMaxT];
+  const float* w2[kPackGroup][kPackMaxT];
+  uint8_t* base[kPackGroup];
+  int T, D, F, H, hid, Kin, local;
+  int n_fixed, n_wc, n_w1, n_w2, per_net;
+  unsigned long long in_w1_off, in_w2_off, out_w1_off, enc0, enc_stride, enc_wc, enc_ffn;
+};
+
+__device__ __forceinline__ void pack_tile_dev(const float* __restrict__ W, int ldw, int n_rows, int n_cols, int rows, int tr, int tk,
+                                              uint8_t* hi, uint8_t* lo) {
   for (int e = threadIdx.x; e < rows * 32; e += blockDim.x) {
     int r = e >> 5, kp = (e & 31) * 2;
     int gr = tr * rows + r, gc = tk * 64 + kp;
@@ -74,97 +92,128 @@ __global__ void __launch_bounds__(256) k_pack_tiles(const float* __restrict__ W,
     float b = (gr < n_rows && gc + 1 < n_cols) ? W[(size_t)gr * ldw + gc + 1] : 0.f;
     uint32_t h, l;
     split2(a, b, h, l);
-    uint32_t off = sw128_offset(r, kp, rows);  // single K block: k < 64
+    uint32_t off = sw128_offset(r, kp, rows);
     *reinterpret_cast<uint32_t*>(hi + off) = h;
     *reinterpret_cast<uint32_t*>(lo + off) = l;
   }
 }
 
-// W_c[i, h*D + j] = sum_k W_o[i, h*D + k] * W_v[h*D + k, j]   (fp64 accumulate): the out-projection of
-// head h composed with its value projection, so that attention becomes  sum_h W_c,h (A_h x).
-__global__ void __launch_bounds__(128) k_combine_wc(const float* __restrict__ Wo, const float* __restrict__ Wv, int D, int H,
-                                                    float* __restrict__ Wc) {
-  const int h = blockIdx.x, i = blockIdx.y, j = threadIdx.x;
-  if (j >= D) return;
-  double acc = 0;
-  for (int k = 0; k < D; k++) acc += (double)Wo[(size_t)i * H * D + h * D + k] * (double)Wv[(size_t)(h * D + k) * D + j];
-  Wc[(size_t)i * H * D + h * D + j] = (float)acc;
-}
-
-static int pack_matrix(const float* W, int ldw, int n_rows, int n_cols, int rows, uint8_t* dst, size_t tile_stride_r,
-                       size_t tile_stride_k, size_t lo_offset, cudaStream_t st) {
-  dim3 grid((n_cols + 63) / 64, (n_rows + rows - 1) / rows);
-  k_pack_tiles<<<grid, 256, 0, st>>>(W, ldw, n_rows, n_cols, rows, grid.x, dst, tile_stride_r, tile_stride_k, lo_offset);
-  TW_LAUNCH_CHECK();
-  return TW_OK;
-}
-
-static int pack_w2_blocks(const float* W2, int F, int D, uint8_t* dst, cudaStream_t st);
-
-size_t tc_packed_bytes(const tw_flow_config* c) {
-  TcLayout L = TcLayout::make(c);
-  return L.total(c) + (size_t)L.D * L.H * L.D * sizeof(float) + 1024;  // + fp32 scratch for W_c
+__global__ void __launch_bounds__(256) k_pack_all(const __grid_constant__ PackGroup g) {
+  const int nb = blockIdx.x / g.per_net;
+  int j = blockIdx.x % g.per_net;
+  uint8_t* base = g.base[nb];
+  const int D = g.D, F = g.F, H = g.H, hid = g.hid;
+  if (j < g.n_fixed) {
+    if (j == 0) {  // in_mlp L1 [hid x Kin] -> one [hid x 64] tile: hi at 0, lo at hid*128
+      pack_tile_dev(g.in_w1[nb], g.Kin, hid, g.Kin, hid, 0, 0, base + g.in_w1_off, base + g.in_w1_off + (size_t)hid * 128);
+    } else if (j < 1 + hid / 64) {  // in_mlp L2 [D x hid] -> hid/64 K blocks [128 x 64]: block kb at kb*32 KB: hi 16 KB, lo 16 KB
+      const int tk = j - 1;
+      uint8_t* hi = base + g.in_w2_off + (size_t)tk * (2 * 128 * 128);
+      pack_tile_dev(g.in_w2[nb], hid, D, hid, 128, 0, tk, hi, hi + 128 * 128);
+    } else {  // out_mlp L1 [hid x D] -> D/64 K blocks of [hid x 64]: block kb at kb*(2*hid*128): hi, lo
+      const int tk = j - 1 - hid / 64;
+      uint8_t* hi = base + g.out_w1_off + (size_t)tk * (2 * hid * 128);
+      pack_tile_dev(g.out_w1[nb], D, hid, D, hid, 0, tk, hi, hi + (size_t)hid * 128);
+    }
+    return;
+  }
+  j -= g.n_fixed;
+  const int per_layer = g.n_wc + g.n_w1 + g.n_w2;
+  const int t = j / per_layer;
+  j %= per_layer;
+  uint8_t* eb = base + g.enc0 + (size_t)t * g.enc_stride;
+  if (j < g.n_wc) {
+    // W_c[i, h*D + c] = sum_k W_o[i, h*D + k] W_v[h*D + k, c] (fp64 accumulate) -> K block kb = j of [D x H*D]:
+    // [128 x 64] tile at kb*32 KB: hi 16 KB, lo 16 KB.  A warp shares the row i (broadcast W_o loads, coalesced W_v loads).
+    const int kb = j;
+    uint8_t* hi = eb + g.enc_wc + (size_t)kb * (2 * 128 * 128);
+    uint8_t* lo = hi + 128 * 128;
+    const float* __restrict__ Wo = g.wo[nb][t];
+    const float* __restrict__ Wv = g.wv[nb][t];
+    const int h = (kb * 64) / D, c0 = (kb * 64) % D;
+    for (int e = threadIdx.x; e < 128 * 32; e += blockDim.x) {
+      const int r = e >> 5, kp = (e & 31) * 2;
+      double a0 = 0, a1 = 0;
+      if (r < D) {
+        const float* wo = Wo + (size_t)r * H * D + h * D;
+        const float* wv = Wv + (size_t)(h * D) * D + c0 + kp;
+        for (int k = 0; k < D; k++) {
+          const double o = (double)wo[k];
+          const float2 v = *reinterpret_cast<const float2*>(wv + (size_t)k * D);
+          a0 += o * (double)v.x, a1 += o * (double)v.y;
+        }
+      }
+      uint32_t hh, ll;
+      split2((float)a0, (float)a1, hh, ll);
+      const uint32_t off = sw128_offset(r, kp, 128);
+      *reinterpret_cast<uint32_t*>(hi + off) = hh;
+      *reinterpret_cast<uint32_t*>(lo + off) = ll;
+    }
+    return;
+  }
+  j -= g.n_wc;
+  if (j < g.n_w1) {
+    // FFN chunk c: [W1hi | W1lo | W2hi | W2lo], each 32 KB = K blocks kb0, kb1 of [128 x 64];
+    // W1 [F x D]: tile (tr = chunk, tk) at chunk*128KB + tk*16KB, lo +32KB
+    const int tiles_k = D / 64, tr = j / tiles_k, tk = j % tiles_k;
+    uint8_t* hi = eb + g.enc_ffn + (size_t)tr * (4 * kTileBytes128) + (size_t)tk * (128 * 128);
+    pack_tile_dev(g.w1[nb][t], D, F, D, 128, tr, tk, hi, hi + kTileBytes128);
+    return;
+  }
+  j -= g.n_w1;
+  {  // W2 [D x F]: K block b (columns b*64..) -> chunk b/2, K block b%2 of the W2hi / W2lo tiles
+    const int b = j;
+    const float* __restrict__ W2 = g.w2[nb][t];
+    uint8_t* hi = eb + g.enc_ffn + 2 * kTileBytes128 + (size_t)(b >> 1) * 4 * kTileBytes128 + (b & 1) * (128 * 128);
+    uint8_t* lo = hi + kTileBytes128;
+    for (int e = threadIdx.x; e < 128 * 32; e += blockDim.x) {
+      int r = e >> 5, kp = (e & 31) * 2;
+      float a = 0.f, c = 0.f;
+      if (r < D) {
+        a = W2[(size_t)r * F + b * 64 + kp];
+        c = W2[(size_t)r * F + b * 64 + kp + 1];
+      }
+      uint32_t h, l;
+      split2(a, c, h, l);
+      uint32_t off = sw128_offset(r, kp, 128);
+      *reinterpret_cast<uint32_t*>(hi + off) = h;
+      *reinterpret_cast<uint32_t*>(lo + off) = l;
+    }
+  }
 }
 
 int tc_pack_weights(const tw_flow_config* c, const ParamView& pv, uint8_t* packed, size_t bytes, cudaStream_t st) {
   TW_CHECK_ARG(tc_supported(c), "configuration not supported by the tensor-core path");
   TW_CHECK_ARG(packed && bytes >= tc_packed_bytes(c), "packed buffer too small");
   TW_CHECK_ARG(((uintptr_t)packed & 1023) == 0, "packed buffer must be 1024-byte aligned");
+  TW_CHECK_ARG(c->num_transformer_layers <= kPackMaxT, "tensor-core weight packing supports at most %d encoder layers per network", kPackMaxT);
   TcLayout L = TcLayout::make(c);
-  float* wc_tmp = reinterpret_cast<float*>(packed + align_up(L.total(c), 1024));
-  const int D = L.D, F = L.F, H = L.H, hid = L.hid, Kin = L.E + 9;
-  for (int k = 0; k < c->num_coupling_layers; k++)
-    for (int net = 0; net < 2; net++) {
-      uint8_t* base = packed + L.net_offset(k, net);
-      // in_mlp L1 [hid x Kin] -> one [hid x 64] tile: hi at 0, lo at hid*128
-      TW_TRY(pack_matrix(pv.in_w(k, net, 0), Kin, hid, Kin, hid, base + L.in_w1, 0, 0, (size_t)hid * 128, st));
-      // in_mlp L2 [D x hid] -> hid/64 K blocks [128 x 64]: block kb at kb*32 KB: hi 16 KB, lo 16 KB
-      TW_TRY(pack_matrix(pv.in_w(k, net, 1), hid, D, hid, 128, base + L.in_w2, 0, 2 * 128 * 128, 128 * 128, st));
-      // out_mlp L1 [hid x D] -> 2 K blocks of [hid x 64]: block kb at kb*(2*hid*128): hi, lo
-      TW_TRY(pack_matrix(pv.out_w(k, net, 0), D, hid, D, hid, base + L.out_w1, 0, (size_t)2 * hid * 128, (size_t)hid * 128, st));
+  PackGroup g{};
+  g.T = L.T, g.D = L.D, g.F = L.F, g.H = L.H, g.hid = L.hid, g.Kin = L.E + 9, g.local = pv.local() ? 1 : 0;
+  g.n_fixed = 1 + L.hid / 64 + L.D / 64;
+  g.n_wc = pv.local() ? 0 : L.H * L.D / 64;  // (local attention runs on the CUDA-core kernels straight from the fp32 weights)
+  g.n_w1 = (L.F / 128) * (L.D / 64);
+  g.n_w2 = L.F / 64;
+  g.per_net = g.n_fixed + L.T * (g.n_wc + g.n_w1 + g.n_w2);
+  g.in_w1_off = L.in_w1, g.in_w2_off = L.in_w2, g.out_w1_off = L.out_w1;
+  g.enc0 = L.enc0, g.enc_stride = L.enc_stride, g.enc_wc = L.enc_wc, g.enc_ffn = L.enc_ffn;
+  const int n_nets = c->num_coupling_layers * 2;
+  for (int first = 0; first < n_nets; first += kPackGroup) {
+    const int count = n_nets - first < kPackGroup ? n_nets - first : kPackGroup;
+    for (int i = 0; i < count; i++) {
+      const int k = (first + i) / 2, net = (first + i) % 2;
+      g.base[i] = packed + L.net_offset(k, net);
+      g.in_w1[i] = pv.in_w(k, net, 0), g.in_w2[i] = pv.in_w(k, net, 1), g.out_w1[i] = pv.out_w(k, net, 0);
       for (int t = 0; t < L.T; t++) {
-        uint8_t* eb = base + L.enc0 + (size_t)t * L.enc_stride;
-        if (!pv.local()) {  // (local attention runs on the CUDA-core kernels straight from the fp32 weights)
-          k_combine_wc<<<dim3(H, D), 128, 0, st>>>(pv.enc(k, net, t, 2), pv.enc(k, net, t, 0), D, H, wc_tmp);
-          TW_LAUNCH_CHECK();
-          // W_c [D x H*D] -> H*D/64 K blocks [128 x 64]: block kb at kb*32 KB: hi 16 KB, lo 16 KB
-          TW_TRY(pack_matrix(wc_tmp, H * D, D, H * D, 128, eb + L.enc_wc, 0, 2 * 128 * 128, 128 * 128, st));
-        }
-        // FFN chunk c: [W1hi | W1lo | W2hi | W2lo], each 32 KB = K blocks kb0, kb1 of [128 x 64]
-        //   W1 [F x D]: rows c*128.., all D=128 columns  -> tile (tr=c, tk) at c*128KB + tk*16KB, lo +32KB
-        TW_TRY(pack_matrix(pv.enc(k, net, t, 3), D, F, D, 128, eb + L.enc_ffn, 4 * kTileBytes128, 128 * 128, kTileBytes128, st));
-        //   W2 [D x F]: K block b (columns b*64..) -> chunk b/2, K block b%2 of the W2hi / W2lo tiles
-        TW_TRY(pack_w2_blocks(pv.enc(k, net, t, 5), F, D, eb + L.enc_ffn + 2 * kTileBytes128, st));
+        g.wv[i][t] = pv.enc(k, net, t, 0), g.wo[i][t] = pv.enc(k, net, t, 2);
+        g.w1[i][t] = pv.enc(k, net, t, 3), g.w2[i][t] = pv.enc(k, net, t, 5);
       }
     }
-  return TW_OK;
-}
-
-// W2 [D x F] K blocks: block index b = 0..F/64-1 covers columns b*64..; destination chunk = b/2, K block = b%2.
-__global__ void __launch_bounds__(256) k_pack_w2(const float* __restrict__ W2, int F, int D, uint8_t* __restrict__ dst) {
-  const int b = blockIdx.x;
-  uint8_t* hi = dst + (size_t)(b >> 1) * 4 * kTileBytes128 + (b & 1) * (128 * 128);
-  uint8_t* lo = hi + kTileBytes128;
-  for (int e = threadIdx.x; e < 128 * 32; e += blockDim.x) {
-    int r = e >> 5, kp = (e & 31) * 2;
-    float a = 0.f, c = 0.f;
-    if (r < D) {
-      a = W2[(size_t)r * F + b * 64 + kp];
-      c = W2[(size_t)r * F + b * 64 + kp + 1];
-    }
-    uint32_t h, l;
-    split2(a, c, h, l);
-    uint32_t off = sw128_offset(r, kp, 128);
-    *reinterpret_cast<uint32_t*>(hi + off) = h;
-    *reinterpret_cast<uint32_t*>(lo + off) = l;
+    k_pack_all<<<(unsigned)(count * g.per_net), 256, 0, st>>>(g);
+    TW_LAUNCH_CHECK();
   }
-}
-static int pack_w2_blocks(const float* W2, int F, int D, uint8_t* dst, cudaStream_t st) {
-  k_pack_w2<<<F / 64, 256, 0, st>>>(W2, F, D, dst);
-  TW_LAUNCH_CHECK();
   return TW_OK;
 }
-
 
 // Row epilogue shared by the token-major kernels: v[128] (+ bias) + residual row -> LayerNorm -> global
 __device__ __forceinline__ void ln_store_row(float (&v)[128], const float* __restrict__ bias, const float* __restrict__ resid_row,
@@ -1327,7 +1376,7 @@ __global__ void __launch_bounds__(256) k_scores_direct_img(const float* __restri
 
 // ============================================================================================
 // Attention, step 2 (mixing): for every sample n and head h,   mixed_h = A_h x   (kernel_attention.py:139
-// re-associated with the value projection, see k_combine_wc).  Features on the TMEM lanes:
+// re-associated with the value projection, see k_pack_all).  Features on the TMEM lanes:
 //   D^T[128 f, VP tokens] = X^T[128 f, VP atoms] (A operand, TMEM) * A_h^T (B operand [VP i, VP j] K-major)
 // so a sample of ANY atom count uses a full-width MMA.  The result is written straight into the A-operand
 // images ([128 tokens x 64] K-major SW128 tiles, hi/lo) that the projection kernel bulk-copies.

@@ -588,7 +588,7 @@ __global__ void __launch_bounds__(128) k_prior_bwd(const float* __restrict__ zc,
   }
 }
 
-// W_c,h = W_o,h W_v,h (k_combine_wc) backward: dW_o[i, hD+k] += sum_j dWc[i, hD+j] W_v[hD+k, j];
+// W_c,h = W_o,h W_v,h (k_pack_all) backward: dW_o[i, hD+k] += sum_j dWc[i, hD+j] W_v[hD+k, j];
 //                                              dW_v[hD+k, j] += sum_i W_o[i, hD+k] dWc[i, hD+j].
 struct WcChainArgs {
   const float* dwc[2];
