@@ -92,17 +92,26 @@ def synthetic_chains(pep, n_chains, seed):
     return x, at, mask
 
 
-def bench_state_dict(o, mode):
-    """Synthetic weights of the full architecture.  mode "init": random-init-scale parameters (proposals of a random
+def bench_state_dict(src, mode):
+    """Synthetic weights of the full architecture.  `src` is the product model (GPU arm: timewarp_b200.synthetic) or an
+    oracle config (CPU-baseline / reference arm: oracle.flow_oracle) -- the two generators give identical tensors
+    (tests/test_abi_cpu.py::test_synthetic_weights_match_oracle_generator).  mode "init": random-init-scale parameters (proposals of a random
     flow are never accepted).  mode "proposal" (default): the same tensors with the last layer of every out_mlp scaled by
     1e-5 (shifts far below the proposal width) and the prior scales set to (5e-4 nm, 1): a near-identity flow whose
     proposals are local moves, so the accept
     branch of the MH rule is exercised.  Identical arithmetic and shapes either way."""
-    from oracle import flow_oracle as fo
+    if isinstance(src, torch.nn.Module):
+        from timewarp_b200.synthetic import synth_state_dict
 
-    sd = fo.synth_state_dict(o, 0)
+        sd = synth_state_dict(src, 0)
+        n_hidden = len(src.flow.chain[0].scale_transformer.out_mlp.linears()) - 1
+    else:  # CPU legs only: the oracle is the thing being timed there
+        from oracle import flow_oracle as fo
+
+        sd = fo.synth_state_dict(src, 0)
+        n_hidden = len(src.latent_mlp_hidden_dims)
     if mode == "proposal":
-        last = 2 * len(o.latent_mlp_hidden_dims)
+        last = 2 * n_hidden
         for k in list(sd):
             if f".out_mlp._layers.{last}." in k:
                 sd[k] = sd[k] * 1e-5
@@ -181,13 +190,13 @@ def time_nll_training(dev, precision, batch=256, steps=5, warmup=3, use_graph=Tr
     """BASELINE.json configs[1]: alanine-dipeptide (22 atoms) NLL training, batch 256 on one GPU: forward (taped) +
     hand-written backward + Adam step.  Returns atoms/s (B * V / step time, CUDA events)."""
     import timewarp_b200 as tw
-    from oracle import flow_oracle as fo
     from timewarp_b200.peptides import alanine_dipeptide
+    from timewarp_b200.synthetic import synth_state_dict
 
     pep = alanine_dipeptide()
     V = pep.num_atoms
     model = tw.custom_transformer_nvp_constructor(tw.kernel_transformer_nvp_config(precision))
-    model.load_state_dict(fo.synth_state_dict(fo.OracleConfig(), 0))
+    model.load_state_dict(synth_state_dict(model, 0))
     model = model.to(dev).train()
     opt = torch.optim.Adam(model.parameters(), lr=1e-4, capturable=True, fused=True)
     g = torch.Generator().manual_seed(0)
@@ -253,8 +262,8 @@ def run_nll(args):
     256 per GPU, one gradient all-reduce per step).  Synthetic 2AA-like ragged batches: atom counts uniform in [17, 51],
     padded to the batch maximum with `masked_elements`.  Prints ONE JSON line (atoms/s = un-padded atoms of all ranks)."""
     import timewarp_b200 as tw
-    from oracle import flow_oracle as fo
     from timewarp_b200 import distributed as twd
+    from timewarp_b200.synthetic import synth_state_dict
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -264,7 +273,7 @@ def run_nll(args):
     twd.init_from_env("nccl", dev)
     prec = args.precision
     model = tw.custom_transformer_nvp_constructor(tw.kernel_transformer_nvp_config(prec))
-    model.load_state_dict(fo.synth_state_dict(fo.OracleConfig(), 0))
+    model.load_state_dict(synth_state_dict(model, 0))
     model = model.to(dev).train()
     twd.broadcast_parameters(model.parameters())
     opt = torch.optim.Adam(model.parameters(), lr=1e-4, fused=True)
@@ -323,7 +332,6 @@ def run_ours(args):
     import ctypes as C
 
     import timewarp_b200 as tw
-    from oracle import flow_oracle as fo  # weights generator only (synthetic, random-init-scale parameters)
     from timewarp_b200 import _lib
     from timewarp_b200.energy import PeptidePotentialEnergy
     from timewarp_b200.forcefield import amber_like_system
@@ -351,9 +359,8 @@ def run_ours(args):
     lib = _lib.load()
     pep = tetrapeptide_2olx()
     V = pep.num_atoms
-    o = fo.OracleConfig()
     model = tw.custom_transformer_nvp_constructor(tw.kernel_transformer_nvp_config(args.precision))
-    model.load_state_dict(bench_state_dict(o, args.weights))
+    model.load_state_dict(bench_state_dict(model, args.weights))
     model = model.to(dev).eval()
     energy = PeptidePotentialEnergy(amber_like_system(pep))
     x0, at, mask = synthetic_chains(pep, args.chains, seed=1000 + rank)

@@ -124,6 +124,23 @@ def test_reference_checkpoint_loads(tmp_path):
         ck.load_checkpoint_in_subdir(tmp_path, "x.pt")  # two candidates: unique_item fails like the reference
 
 
+def test_synthetic_weights_match_oracle_generator():
+    """bench.py loads the product model from timewarp_b200.synthetic and its CPU baseline from the oracle's generator: the two
+    must give identical parameters (every attention variant, two seeds)."""
+    from oracle import flow_oracle as fo
+    from tests.common import TINY_C, TINY_L, TINY_LOC
+    from timewarp_b200.synthetic import synth_state_dict
+
+    for o in (TINY_O, TINY_L, TINY_C, TINY_LOC):
+        m = tw.custom_transformer_nvp_constructor(model_config(o, "fp32"))
+        for seed in (0, 3):
+            a, b = synth_state_dict(m, seed), fo.synth_state_dict(o, seed)
+            assert set(a) == set(b)
+            for k in a:
+                assert torch.equal(a[k], b[k]), (o.attention_type, seed, k)
+            m.load_state_dict(a, strict=True)
+
+
 def test_config_validation(lib):
     bad = model_config(TINY_O, "fp32")
     bad.num_coupling_layers = 3

@@ -4,7 +4,7 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import timewarp_b200 as tw
-from oracle import flow_oracle as fo
+from timewarp_b200.synthetic import synth_state_dict
 from timewarp_b200.energy import PeptidePotentialEnergy
 from timewarp_b200.forcefield import amber_like_system
 from timewarp_b200.peptides import tetrapeptide_2olx
@@ -15,7 +15,7 @@ prec = sys.argv[2] if len(sys.argv) > 2 else "bf16x3"
 steps = int(sys.argv[3]) if len(sys.argv) > 3 else 1
 pep = tetrapeptide_2olx()
 m = tw.custom_transformer_nvp_constructor(tw.kernel_transformer_nvp_config(prec))
-m.load_state_dict(fo.synth_state_dict(fo.OracleConfig(), 0))
+m.load_state_dict(synth_state_dict(m, 0))
 m = m.cuda().eval()
 g = torch.Generator().manual_seed(0)
 x = (torch.tensor(pep.coords_nm, dtype=torch.float32)[None] + 0.005 * torch.randn(B, pep.num_atoms, 3, generator=g)).cuda()

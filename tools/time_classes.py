@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import timewarp_b200 as tw
 from timewarp_b200 import _lib
-from oracle import flow_oracle as fo
+from timewarp_b200.synthetic import synth_state_dict
 from timewarp_b200.energy import PeptidePotentialEnergy
 from timewarp_b200.forcefield import amber_like_system
 from timewarp_b200.peptides import tetrapeptide_2olx
@@ -15,7 +15,7 @@ B = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 pep = tetrapeptide_2olx()
 m = tw.custom_transformer_nvp_constructor(tw.kernel_transformer_nvp_config("bf16x3"))
-m.load_state_dict(fo.synth_state_dict(fo.OracleConfig(), 0))
+m.load_state_dict(synth_state_dict(m, 0))
 m = m.cuda().eval()
 g = torch.Generator().manual_seed(0)
 x = (torch.tensor(pep.coords_nm, dtype=torch.float32)[None] + 0.005 * torch.randn(B, pep.num_atoms, 3, generator=g)).cuda()
