@@ -129,3 +129,44 @@ def test_bf16x3_shared_conditioning_proposals(name):
                               zc.transpose(0, 1).contiguous(), zv.transpose(0, 1).contiguous())
     torch.testing.assert_close(a[0].squeeze(1), b[0].squeeze(0), rtol=1e-5, atol=2e-5)
     torch.testing.assert_close(a[2].squeeze(1), b[2].squeeze(0), rtol=1e-5, atol=1e-3)
+
+
+@torch.no_grad()
+def test_bench_size_properties():
+    """BASELINE.json configs[2] at FULL size (1024 chains x 65 atoms, bf16x3 inference kernels) through size-independent
+    properties: proposal -> density round trip, invariance of every row to how the batch is cut, the MH step's reverse-move
+    density == per-row evaluation, and the CPU oracle on a handful of rows."""
+    from timewarp_b200.peptides import tetrapeptide_2olx
+
+    pep = tetrapeptide_2olx()
+    B, V = 1024, pep.num_atoms
+    m, sd = build_model(FULL_O, "bf16x3", 0)
+    gen = torch.Generator().manual_seed(11)
+    x = torch.tensor(pep.coords_nm, dtype=torch.float32)[None] + 0.005 * torch.randn(B, V, 3, generator=gen)
+    xv = torch.randn(B, V, 3, generator=gen)
+    at = torch.tensor(pep.atom_types)[None].repeat(B, 1)
+    mask = torch.zeros(B, V, dtype=torch.bool)
+    zc, zv = 0.05 * torch.randn(1, B, V, 3, generator=gen), torch.randn(1, B, V, 3, generator=gen)
+    kw = dict(adj_list=EMPTY_ADJ.cuda(), edge_batch_idx=EMPTY_EBI.cuda())
+    yc, yv, lp = m.sample_from_latents(at.cuda(), x.cuda(), xv.cuda(), mask.cuda(), zc.cuda(), zv.cuda())
+    assert yc.shape == (1, B, V, 3) and lp.shape == (1, B) and torch.isfinite(lp).all()
+    # (1) proposal -> density round trip on all 1024 chains
+    ll = m.log_likelihood(atom_types=at.cuda(), x_coords=x.cuda(), x_velocs=xv.cuda(), y_coords=yc[0], y_velocs=yv[0],
+                          masked_elements=mask.cuda(), **kw)
+    assert_rel(ll, lp[0], what="1024 x 65: sample -> density round trip")
+    # (2) a row does not depend on how the batch is cut (tiles / CTA assignment / tail handling differ)
+    for rows in (slice(0, 1), slice(100, 357), slice(1000, 1024)):
+        part = m.log_likelihood(atom_types=at[rows].cuda(), x_coords=x[rows].cuda(), x_velocs=xv[rows].cuda(), y_coords=yc[0, rows],
+                                y_velocs=yv[0, rows], masked_elements=mask[rows].cuda(), **kw)
+        torch.testing.assert_close(part, ll[rows], rtol=1e-6, atol=2e-4)  # |ll| ~ 1e3: a few fp32 ulps
+    # (3) the reverse-move density of the MH rule (conditioning = the proposals) is finite and row-wise reproducible
+    p_yx = m.log_likelihood(atom_types=at.cuda(), x_coords=yc[0], x_velocs=yv[0], y_coords=x.cuda(), y_velocs=xv.cuda(),
+                            masked_elements=mask.cuda(), **kw)
+    one = m.log_likelihood(atom_types=at[7:8].cuda(), x_coords=yc[0, 7:8], x_velocs=yv[0, 7:8], y_coords=x[7:8].cuda(),
+                           y_velocs=xv[7:8].cuda(), masked_elements=mask[7:8].cuda(), **kw)
+    assert torch.isfinite(p_yx).all()
+    torch.testing.assert_close(one, p_yx[7:8], rtol=1e-6, atol=2e-4)
+    # (4) the CPU oracle on five rows spread over the batch
+    pick = torch.tensor([0, 255, 511, 768, 1023])
+    want = fo.log_likelihood(sd, FULL_O, at[pick], x[pick], xv[pick], yc[0].cpu()[pick], yv[0].cpu()[pick], mask[pick], distance_mode="direct")
+    assert_rel(ll.cpu()[pick], want, what="1024 x 65: oracle on five rows")
