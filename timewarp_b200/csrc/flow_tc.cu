@@ -1331,7 +1331,7 @@ __global__ void __launch_bounds__(256) k_scores_direct_img(const float* __restri
   for (int i = tid; i < V; i += blockDim.x) ms[i] = mask[b * V + i];
   const uint32_t mat = (uint32_t)VP * VP * 2;
   __syncthreads();
-  for (int h = 0; h < H; h++) {
+  for (int h = blockIdx.y; h < H; h += gridDim.y) {  // grid.y = H: one (state, head) image per CTA, several CTAs per SM
     const float l = ls[h];
     const float* coef = cheb ? cheb + (size_t)h * order : nullptr;
     const float cmean = cheb_mean(coef, order, force_zero);
@@ -2886,7 +2886,7 @@ int tc_begin_pass_direct(const tw_flow_config* c, TcScratch& tc, const float* xc
     attr_done = true;
   }
   if (n_cond < 1) return TW_OK;
-  k_scores_direct_img<<<(unsigned)n_cond, 256, smem, st>>>(xc, mask, lengthscales, V, VP, c->num_heads, tc.scores_img, cheb,
+  k_scores_direct_img<<<dim3((unsigned)n_cond, (unsigned)c->num_heads), 256, smem, st>>>(xc, mask, lengthscales, V, VP, c->num_heads, tc.scores_img, cheb,
                                                            c->cheb_order, c->force_asymptotic_zero);
   TW_LAUNCH_CHECK();
   return TW_OK;
