@@ -190,7 +190,7 @@ GRAD_FULL_KEYS = [
 ]
 
 
-def grad_case(name, cfg, peptide, B, seed, lengths=None, wseed=0):
+def grad_case(name, cfg, peptide, B, seed, lengths=None, wseed=0, extra_keys=()):
     """NLL loss (density_model_base.py:27-42) and its autograd gradients from the unmodified reference:
     L2 norm of every parameter gradient + a few full tensors."""
     model, sd = ref_model(cfg, wseed)
@@ -207,7 +207,7 @@ def grad_case(name, cfg, peptide, B, seed, lengths=None, wseed=0):
         norms.append(0.0 if p.grad is None else float(p.grad.double().norm()))
     out["grad_names"] = np.array(names)
     out["grad_norms"] = np.array(norms)
-    for k in GRAD_FULL_KEYS:
+    for k in list(GRAD_FULL_KEYS) + list(extra_keys):
         g = dict(model.named_parameters())[k].grad
         out["grad::" + k] = (g[:8] if g.numel() > 20000 else g).numpy()  # large matrices: first 8 rows
     np.savez_compressed(os.path.join(HERE, f"{name}.npz"), **out)
@@ -389,7 +389,18 @@ def md_case():
     print("md case:", len(x0), "consecutive steps,", len(d["step"]), "kinetic energies")
 
 
+def learnable_grad_case():
+    """learnable_kernel training: the gradient reaches the log_lengthscales of the first attention layer the pass executes
+    (flow.chain.0.scale_transformer.encoder_layers.0) and no other (cache quirk: their .grad stays None -> norm 0)."""
+    ad = alanine_dipeptide()
+    grad_case("grads_full_ad22_learnable", FULL_LEARNABLE, ad, B=3, seed=31, lengths=[22, 17, 12],
+              extra_keys=["flow.chain.0.scale_transformer.encoder_layers.0.self_attn.attention.log_lengthscales"])
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "learnable_grad":
+        learnable_grad_case()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "checkpoint":
         checkpoint_case()
         sys.exit(0)
@@ -420,6 +431,7 @@ if __name__ == "__main__":
     grad_case("grads_full_ad22", FULL, ad, B=4, seed=3)
     grad_case("grads_full_ad22_ragged", FULL, ad, B=3, seed=4, lengths=[22, 17, 12])
     learnable_cases()
+    learnable_grad_case()
     chebyshev_cases()
     local_cases()
     md_case()

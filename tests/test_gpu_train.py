@@ -9,7 +9,7 @@ import pytest
 import torch
 
 from oracle import flow_oracle as fo
-from tests.common import EMPTY_ADJ, EMPTY_EBI, FULL_O, GOLDEN, build_model
+from tests.common import EMPTY_ADJ, EMPTY_EBI, FULL_L, FULL_O, GOLDEN, build_model
 from timewarp_b200 import _lib
 
 pytestmark = pytest.mark.gpu
@@ -97,13 +97,20 @@ def _load(name):
     return {k: (torch.from_numpy(d[k]) if d[k].dtype.kind != "U" else d[k]) for k in d.files}
 
 
-@pytest.mark.parametrize("name", ["grads_full_ad22", "grads_full_ad22_ragged"])
+@pytest.mark.parametrize("name", ["grads_full_ad22", "grads_full_ad22_ragged", "grads_full_ad22_learnable"])
 def test_backward_matches_reference_gradients(name):
     g = _load(name)
-    m, _ = build_model(FULL_O, "bf16x3", int(g["weight_seed"]))
+    learnable = name.endswith("learnable")
+    m, _ = build_model(FULL_L if learnable else FULL_O, "bf16x3", int(g["weight_seed"]))
     loss, grads = _loss_and_grads(m, g)
     assert abs(float(loss) - float(g["loss"])) < 1e-4 * abs(float(g["loss"]))
     names = [str(n) for n in g["grad_names"]]
+    if learnable:
+        # the reference leaves .grad = None on every log_lengthscales but the first executed layer's (recorded norm 0); so do we
+        unused = {n for n, v in zip(names, g["grad_norms"].tolist()) if n.endswith("log_lengthscales") and v == 0.0}
+        assert len(unused) == 47 and not (unused & set(grads))
+        names = [n for n in names if n not in unused]
+        g["grad_norms"] = torch.tensor([v for n, v in zip([str(n) for n in g["grad_names"]], g["grad_norms"].tolist()) if n not in unused])
     assert set(names) == set(grads)
     worst = 0.0
     for n, ref_norm in zip(names, g["grad_norms"].tolist()):
@@ -150,6 +157,44 @@ def test_backward_matches_oracle_autograd_every_tensor():
         assert err <= _tol(k) * scale, (k, err, float(ref.norm()))
     assert float(np.median(errs)) < GRAD_MEDIAN_RTOL
     print("worst per-tensor gradient rel err", worst, "median", float(np.median(errs)))
+
+
+def test_learnable_lengthscale_gradient_matches_oracle_autograd():
+    """learnable_kernel: d(loss)/d(log_lengthscales) of the first executed attention layer on a ragged batch (padding in the
+    key mask, several tiles), against the oracle's fp64 autograd; frozen lengthscales skip the extra kernels."""
+    torch.manual_seed(9)
+    B, V = 6, 40
+    lengths = [40, 22, 31, 40, 9, 17]
+    mask = torch.zeros(B, V, dtype=torch.bool)
+    for b, n in enumerate(lengths):
+        mask[b, n:] = True
+    keep = (~mask)[:, :, None]
+    x = 0.25 * torch.randn(B, V, 3) * keep
+    y = (x + 0.02 * torch.randn(B, V, 3)) * keep
+    xv, yv = torch.randn(B, V, 3) * keep, torch.randn(B, V, 3) * keep
+    at = torch.randint(0, 5, (B, V)) * (~mask)
+    g = dict(atom_types=at, x_coords=x, x_velocs=xv, y_coords=y, y_velocs=yv, masked_elements=mask)
+    m, sd = build_model(FULL_L, "bf16x3", 4)
+    loss, grads = _loss_and_grads(m, g)
+    loss_ref, grads_ref = fo.nll_loss_and_grads(fo.to_dtype(sd, torch.float64), FULL_L, at, x.double(), xv.double(), y.double(),
+                                                yv.double(), mask, distance_mode="direct")
+    assert abs(float(loss) - float(loss_ref)) < 1e-4 * abs(float(loss_ref))
+    key = "flow.chain.0.scale_transformer.encoder_layers.0.self_attn.attention.log_lengthscales"
+    ref = grads_ref[key].double()
+    assert float(ref.norm()) > 0
+    err = float((grads[key].double() - ref).norm() / ref.norm())
+    assert err < GRAD_RTOL, (err, grads[key], ref)
+    assert [k for k in grads if k.endswith("log_lengthscales")] == [key]
+    # the other gradients are unaffected by the extra kernels
+    k2 = "flow.chain.3.shift_transformer.encoder_layers.1.self_attn.values_proj.weight"
+    assert _rel(grads[k2], grads_ref[k2]) < GRAD_RTOL
+    # frozen lengthscales: no gradient, same loss
+    for n, p in m.named_parameters():
+        if n.endswith("log_lengthscales"):
+            p.requires_grad_(False)
+    loss2, grads2 = _loss_and_grads(m, g)
+    assert float(loss2) == float(loss) and not any(k.endswith("log_lengthscales") for k in grads2)
+    assert _rel(grads2[k2], grads[k2]) < 1e-5  # (weight gradients accumulate with fp32 atomics: not bit-reproducible)
 
 
 def test_inference_result_unchanged_and_no_grad_path():

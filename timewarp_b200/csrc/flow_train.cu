@@ -624,6 +624,87 @@ __global__ void __launch_bounds__(128) k_wc_chain(WcChainArgs a, int D, int H) {
 }
 
 // ============================================================================================
+// Gradient w.r.t. the attention lengthscales (`learnable_kernel`, kernel_attention.py:217-253).  One score set A_h(l_h)
+// serves every attention layer of a pass (the reference's cache quirk), so
+//   dL/dl_h = sum_{b,i,j} S_h[b,i,j] * dA_h[b,i,j]/dl_h,    S_h[b] = sum_{layers, nets} Q_h[b] X[b]^T,   Q_h = dr W_c,h
+// (r1 = x + sum_h W_c,h (A_h x)  =>  dL/dA_h[i,j] = <dr_i W_c,h, x_j>).  Q comes from one NN GEMM per layer over the W_c
+// image (all heads at once); k_score_grad accumulates S; k_ls_grad applies the derivative of the normalised Gaussian scores.
+struct ScoreGradArgs {
+  const float* q[2];  // [M, H*128]
+  const float* x[2];  // [M, 128] layer input
+  float* S;           // [B, H, V, V]
+};
+__global__ void __launch_bounds__(128) k_score_grad(ScoreGradArgs a, int V, int H) {
+  extern __shared__ float sg[];
+  float* sX = sg;                       // [V][129]
+  float* sQ = sX + (size_t)V * 129;     // [4 warps][128]
+  const int64_t b = blockIdx.x;
+  const int h = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* S = a.S + ((size_t)b * H + h) * V * V;
+  for (int net = 0; net < 2; net++) {
+    const float* X = a.x[net] + b * V * 128;
+    for (int e = threadIdx.x; e < V * 128; e += blockDim.x) sX[(e >> 7) * 129 + (e & 127)] = X[e];
+    __syncthreads();
+    for (int i = warp; i < V; i += 4) {
+      const float* qrow = a.q[net] + ((size_t)b * V + i) * (size_t)(H * 128) + h * 128;
+      for (int f = lane; f < 128; f += 32) sQ[warp * 128 + f] = qrow[f];
+      __syncwarp();
+      for (int j = lane; j < V; j += 32) {
+        float acc = 0.f;
+#pragma unroll 8
+        for (int f = 0; f < 128; f++) acc = fmaf(sQ[warp * 128 + f], sX[j * 129 + f], acc);
+        S[(size_t)i * V + j] += acc;
+      }
+      __syncwarp();
+    }
+    __syncthreads();
+  }
+}
+
+// A_ij = K_ij / (s_i + eps), K_ij = exp(-(d_ij / l)^2) [j not padding], s_i = sum_j K_ij (kernel_attention.py:105-119):
+//   dA_ij/dl = K'_ij / (s_i + eps) - K_ij s'_i / (s_i + eps)^2,   K'_ij = K_ij * 2 d_ij^2 / l^3,   s'_i = sum_j K'_ij
+__global__ void __launch_bounds__(256) k_ls_grad(const float* __restrict__ xc, const uint8_t* __restrict__ mask, const float* __restrict__ ls,
+                                                 const float* __restrict__ S, int V, int H, float* __restrict__ dls) {
+  const int64_t b = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float* xb = xc + b * V * 3;
+  const uint8_t* mb = mask + b * V;
+  __shared__ float red[8];
+  for (int h = 0; h < H; h++) {
+    const float l = ls[h], inv_l3 = 2.f / (l * l * l);
+    const float* Sh = S + ((size_t)b * H + h) * V * V;
+    float part = 0.f;
+    for (int i = warp; i < V; i += 8) {
+      const float xi = xb[i * 3], yi = xb[i * 3 + 1], zi = xb[i * 3 + 2];
+      float s = 0.f, sp = 0.f, a1 = 0.f, a2 = 0.f;  // s, s', sum S K', sum S K
+      for (int j = lane; j < V; j += 32) {
+        if (mb[j]) continue;
+        const float dx = xi - xb[j * 3], dy = yi - xb[j * 3 + 1], dz = zi - xb[j * 3 + 2];
+        const float d2 = dx * dx + dy * dy + dz * dz;
+        const float k = expf(-d2 / (l * l)), kp = k * d2 * inv_l3;
+        const float sv = Sh[(size_t)i * V + j];
+        s += k, sp += kp, a1 = fmaf(sv, kp, a1), a2 = fmaf(sv, k, a2);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o), sp += __shfl_xor_sync(0xffffffffu, sp, o);
+        a1 += __shfl_xor_sync(0xffffffffu, a1, o), a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+      }
+      const float den = s + 1e-5f;
+      part += a1 / den - a2 * sp / (den * den);
+    }
+    if (lane == 0) red[warp] = part;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float t = 0.f;
+      for (int w = 0; w < 8; w++) t += red[w];
+      atomicAdd(&dls[h], t);
+    }
+    __syncthreads();
+  }
+}
+
+// ============================================================================================
 // tape layout
 struct NetTape {
   float* st;            // [M,3] network output (s or t)
@@ -707,6 +788,7 @@ struct BwdBuffers {
   uint8_t* img_u;        // [M,64] image of the conditioner input (shared by both networks)
   float* du[2];          // [M,64]
   float* dwc[2];         // [128, H*128]
+  float* sgrad;          // [B,H,V,V] gradient w.r.t. the attention scores, summed over layers and networks (learnable lengthscales)
 };
 
 static size_t carve_bwd(const tw_flow_config* c, int64_t B, int V, void* base, size_t cap, BwdBuffers* out) {
@@ -737,6 +819,7 @@ static size_t carve_bwd(const tw_flow_config* c, int64_t B, int V, void* base, s
     b.img_g[i] = take_img(H * 2);
   }
   b.img_u = take_img(1);
+  b.sgrad = ar.take<float>((size_t)B * H * V * V);
   if (out) *out = b;
   return align_up(ar.off, 1024);
 }
@@ -770,6 +853,7 @@ struct BwdCtx {
   int64_t B, M;
   int V;
   int tiles;  // token tiles
+  float* dls;  // [H] gradient w.r.t. the lengthscales of the pass (NULL: not requested)
   cudaStream_t st;
 };
 
@@ -905,6 +989,17 @@ static int conditioner_bwd(BwdCtx& x, int k, float* dz_other, const float* z_oth
       TW_LAUNCH_CHECK();
     }
     // attention: r1 = x + sum_h W_c,h (A_h x)
+    if (x.dls) {  // S_h += (dr W_c,h) x^T; the [M, F] scratch of the FFN block is free here
+      GemmArgs q = gemm_base(x, GEMM_NN);  // Q [M, H*128] = dr W_c
+      for (int s = 0; s < 2; s++) q.A[s] = plain_img(b.img_d[s], 2), q.B[s] = plain_img(eb[s] + L.enc_wc, H * 2), q.C[s] = b.wide0[s];
+      q.ldc = H * 128, q.rows = (int)x.M, q.cols = H * 128, q.tiles_m = x.tiles, q.tiles_n = H, q.KB = 2;
+      TW_TRY(launch_gemm(c, q, x.st));
+      ScoreGradArgs sa{};
+      for (int s = 0; s < 2; s++) sa.q[s] = b.wide0[s], sa.x[s] = x.tp.net[k][s].h[t];
+      sa.S = b.sgrad;
+      k_score_grad<<<dim3((unsigned)x.B, H), 128, ((size_t)x.V * 129 + 4 * 128) * sizeof(float), x.st>>>(sa, x.V, H);
+      TW_LAUNCH_CHECK();
+    }
     {
       const size_t wc_bytes = (size_t)128 * H * 128 * sizeof(float);
       for (int s = 0; s < 2; s++) TW_CUDA(cudaMemsetAsync(b.dwc[s], 0, wc_bytes, x.st));
@@ -1118,6 +1213,18 @@ int tw_flow_log_likelihood_backward(const tw_flow_config* cfg, const void* const
   x.B = B, x.V = (int)V, x.M = B * V, x.tiles = (int)((x.M + 127) / 128);
   x.st = (cudaStream_t)stream;
   const int L = cfg->num_coupling_layers;
+  // lengthscale gradient (learnable_kernel): requested by a non-NULL entry for the lengthscales of chain[0].scale.layer[0]
+  x.dls = x.gv.enc(0, 0, 0, 1);
+  if (x.dls) {
+    TW_CHECK_ARG(cfg->num_heads * 128 <= (cfg->dim_feedforward > 256 ? cfg->dim_feedforward : 256),
+                 "lengthscale gradient: H * 128 exceeds the [M, dim_feedforward] scratch");
+    static bool attr_done = false;
+    if (!attr_done) {
+      TW_CUDA(cudaFuncSetAttribute(k_score_grad, cudaFuncAttributeMaxDynamicSharedMemorySize, (128 * 129 + 4 * 128) * (int)sizeof(float)));
+      attr_done = true;
+    }
+    TW_CUDA(cudaMemsetAsync(x.b.sgrad, 0, (size_t)B * cfg->num_heads * V * V * sizeof(float), x.st));
+  }
   k_prior_bwd<<<(unsigned)B, 128, 0, x.st>>>(x.tp.z[L][0], x.tp.z[L][1], mask, x.pv.log_scale_c(), x.pv.log_scale_v(), grad_log_prob, (int)V,
                                             x.b.dz[0], x.b.dz[1], x.gv.log_scale_c(), x.gv.log_scale_v());
   TW_LAUNCH_CHECK();
@@ -1127,6 +1234,10 @@ int tw_flow_log_likelihood_backward(const tw_flow_config* cfg, const void* const
     k_coupling_bwd<<<(unsigned)B, 128, 0, x.st>>>(x.tp.net[k][0].st, x.tp.z[k][tgt], x.b.dz[tgt], mask, grad_log_prob, (int)V, x.b.dst[0], x.b.dst[1]);
     TW_LAUNCH_CHECK();
     TW_TRY(conditioner_bwd(x, k, x.b.dz[oth], x.tp.z[k][oth]));
+  }
+  if (x.dls) {
+    k_ls_grad<<<(unsigned)B, 256, 0, x.st>>>(x.tp.xc, mask, x.pv.enc(0, 0, 0, 1), x.b.sgrad, (int)V, cfg->num_heads, x.dls);
+    TW_LAUNCH_CHECK();
   }
   return TW_OK;
 }

@@ -41,6 +41,9 @@ class _LogLikelihoodFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, model, atom_types, x_coords, x_velocs, y_coords, y_velocs, mask_u8, *params):
+        # learnable_kernel: the LAST input is log_lengthscales of the first attention layer (the only one the reference's
+        # pass reads, and the only one that receives a gradient); the table itself holds exp() of it
+        ctx.n_extra = 1 if model._learnable else 0
         lib = _lib.load()
         dev = x_coords.device
         B, V = x_coords.shape[0], x_coords.shape[1]
@@ -80,6 +83,10 @@ class _LogLikelihoodFn(torch.autograd.Function):
         # accumulate into): 659 zeros_like fills cost more than the backward GEMMs at small batch sizes
         need = [t.requires_grad and t.is_floating_point() for t in tensors]
         wants = [n or (t.is_floating_point() and not _is_optional_grad(model, i)) for i, (t, n) in enumerate(zip(tensors, need))]
+        ls_slot = 3 + 2 * (model._cfg.num_mlp_hidden + 1) + 1  # lengthscales of chain[0].scale_transformer.encoder_layers[0]
+        ls_grad = ctx.n_extra == 1 and ctx.needs_input_grad[-1]
+        if ls_grad:
+            wants[ls_slot] = True  # a non-NULL entry asks the backward for dL/d(lengthscales of the pass)
         sizes = [((t.numel() + 3) // 4 * 4 if w else 0) for t, w in zip(tensors, wants)]  # 16-byte aligned slices
         flat = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
         views, off = [], 0
@@ -100,6 +107,11 @@ class _LogLikelihoodFn(torch.autograd.Function):
             "tw_flow_log_likelihood_backward",
         )  # fmt: skip
         ctx.tape = None
+        if ctx.n_extra:
+            g_log_ls = None
+            if ls_grad:  # d/d(log l) = l * d/dl, in place inside the flat buffer (data-parallel training all-reduces it)
+                g_log_ls = views[ls_slot].mul_(tensors[ls_slot])
+            return (None,) * 7 + tuple(grads) + (g_log_ls,)
         return (None,) * 7 + tuple(grads)
 
 
@@ -336,16 +348,14 @@ class ConditionalFlowDensityModel(nn.Module):
         self._param_table(dev)
         self._set_pass_lengthscales(reverse=False)
         trainable = torch.is_grad_enabled() and not want_latent and any(p.requires_grad for p in self.parameters())
-        if trainable and self._learnable and any(p.requires_grad for n, p in self.named_parameters() if n.endswith("log_lengthscales")):
-            if self.training:
-                raise NotImplementedError("training `learnable_kernel` attention needs the gradient w.r.t. log_lengthscales (not built); "
-                                          "freeze them with requires_grad_(False) or evaluate under torch.no_grad()")
-            trainable = False
         if trainable and (self.training or self._train_supported(B, V)):
             # hand-written backward (tensor-core precisions, flagship layer sizes).  Configurations without backward
             # kernels raise TW_ERR_UNSUPPORTED in .train() mode; in .eval() mode they take the inference path and the
             # result carries no grad_fn (so .backward() on it fails in autograd).
-            out = _LogLikelihoodFn.apply(self, atom_types, x_coords, x_velocs, y_coords, y_velocs, mask_u8, *self._ordered_params())
+            extra = ()
+            if self._learnable:  # the log_lengthscales the pass reads (flow.chain[0]...: the reference's cache quirk)
+                extra = (self.flow.chain[0].scale_transformer.encoder_layers[0].self_attn.attention.log_lengthscales,)
+            out = _LogLikelihoodFn.apply(self, atom_types, x_coords, x_velocs, y_coords, y_velocs, mask_u8, *self._ordered_params(), *extra)
             return out, None, None
         table = self._param_table(dev)
         ws, ws_bytes = self._get_workspace(B, B, V, dev)
