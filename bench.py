@@ -257,6 +257,45 @@ def time_nll_training(dev, precision, batch=256, steps=5, warmup=3, use_graph=Tr
             "final_loss": float(loss.detach())}
 
 
+def time_reference_s_mode(model, energy, pep, dev, S, num_samples=96):
+    """`sample_with_model` exactly as evaluate.py --mh drives it (utils/evaluation_utils.py:468-745): one chain, S parallel
+    proposals from the current state per iteration, the chain advances to the first accepted one (one 4-byte host read per
+    iteration).  Throughput = proposals evaluated per second (iterations x S / wall time incl. the host bookkeeping)."""
+    from timewarp_b200 import sampling
+
+    class _Batch:
+        atom_coords = torch.tensor(pep.coords_nm, dtype=torch.float32)[None]
+        atom_velocs = torch.zeros(1, pep.num_atoms, 3)
+        atom_types = torch.tensor(pep.atom_types)[None]
+        masked_elements = torch.zeros(1, pep.num_atoms, dtype=torch.bool)
+        adj_list = torch.tensor(pep.bonds)
+        edge_batch_idx = torch.zeros(len(pep.bonds), dtype=torch.long)
+
+    calls = [0]
+    inner = model.conditional_sample_with_logp
+
+    def counted(*a, **kw):
+        calls[0] += 1
+        return inner(*a, **kw)
+
+    model.conditional_sample_with_logp = counted
+    try:
+        masses = torch.tensor(pep.masses, dtype=torch.float32)
+        kw = dict(accept=True, random_velocs=True, resample_velocs=True, num_proposal_steps=S)
+        sampling.sample_with_model(_Batch(), model, dev, energy, masses, 4, **kw)  # warm-up (workspace for S samples)
+        torch.cuda.synchronize()
+        calls[0] = 0
+        t0 = time.perf_counter()
+        coords, _, accepted, stats = sampling.sample_with_model(_Batch(), model, dev, energy, masses, num_samples, **kw)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+    finally:
+        del model.conditional_sample_with_logp
+    return {"metric": "mh_proposals_per_sec", "value": calls[0] * S / dt, "unit": "proposals/s", "iterations": calls[0],
+            "proposals_per_iteration": S, "chain_states": int(len(stats)), "accepted": int(accepted), "ms_per_iteration": dt / calls[0] * 1e3,
+            "note": "sample_with_model, 1 chain x S proposals per iteration (shared conditioning), host bookkeeping and per-iteration sync included"}
+
+
 def run_nll(args):
     """`--workload nll`: data-parallel NLL training (BASELINE.json configs[3]: dipeptide set, batch 2048 over 8 GPUs =
     256 per GPU, one gradient all-reduce per step).  Synthetic 2AA-like ragged batches: atom counts uniform in [17, 51],
@@ -488,6 +527,11 @@ def run_ours(args):
             "whole_step_algorithmic_tflops": step_flops * args.steps / (ms_total / 1e3) / 1e12,
             "acceptance_rate_mean": float(acc_rate.mean().item()),
         }
+        if world == 1 and not args.no_nll:
+            try:  # the reference's own driver shape: ONE chain, S = chains proposals per iteration
+                line["reference_s_mode"] = time_reference_s_mode(model, energy, pep, dev, args.chains)
+            except Exception as e:
+                line["reference_s_mode"] = {"error": str(e)[:200]}
         if not args.no_nll:
             try:
                 line["secondary"] = time_nll_training(dev, args.precision)
