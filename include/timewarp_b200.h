@@ -159,6 +159,9 @@ int tw_flow_sample(const tw_flow_config* cfg, const void* const* params, const i
  * tw_flow_log_likelihood_backward: `grads` is a table parallel to `params` (same order, same shapes,
  *   fp32); gradients are ACCUMULATED into it (zero it first for a fresh gradient).  Entries of
  *   lengthscales (buffers, kernel_attention.py:169-171) and of frozen prior log-scales may be NULL.
+ *   A NON-NULL entry for the lengthscales of coupling layer 0 / scale network / encoder layer 0 (the
+ *   ones the pass reads) requests dL/d(lengthscale) [H] there -- learnable_kernel attention
+ *   (kernel_attention.py:217-253; the caller applies d/d(log l) = l * d/dl).
  *   Gradients w.r.t. the coordinate inputs are not produced (the NLL loss does not need them). */
 int tw_flow_train_bytes(const tw_flow_config* cfg, int64_t B, int64_t V, size_t* tape_bytes, size_t* workspace_bytes);
 int tw_flow_log_likelihood_train(const tw_flow_config* cfg, const void* const* params, const int64_t* atom_types,
