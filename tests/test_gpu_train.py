@@ -248,3 +248,34 @@ def test_fused_optimizer_updates_reach_the_packed_weights():
     for a, b in zip(traj["foreach"], traj["fused"]):
         assert abs(a - b) < 2e-3 * max(1.0, abs(a)), traj
     assert abs(traj["foreach_eval"] - traj["fused_eval"]) < 2e-3 * max(1.0, abs(traj["foreach_eval"])), traj
+
+
+def test_training_trajectory_matches_oracle():
+    """three Adam steps of NLL training (forward + hand-written backward + optimizer, weights
+    re-packed every step) against the same three steps of the CPU oracle (fp64 autograd + torch Adam): the loss trajectory."""
+    g = _load("grads_full_ad22_ragged")
+    kw = dict(atom_types=g["atom_types"].cuda(), x_coords=g["x_coords"].cuda(), x_velocs=g["x_velocs"].cuda(), y_coords=g["y_coords"].cuda(),
+              y_velocs=g["y_velocs"].cuda(), adj_list=EMPTY_ADJ.cuda(), edge_batch_idx=EMPTY_EBI.cuda(), masked_elements=g["masked_elements"].cuda())
+    m, sd = build_model(FULL_O, "bf16x3", int(g["weight_seed"]))
+    m.train()
+    opt = torch.optim.Adam(m.parameters(), lr=1e-5)
+    ours = []
+    for _ in range(3):
+        opt.zero_grad(set_to_none=True)
+        loss = m(**kw)
+        loss.backward()
+        opt.step()
+        ours.append(float(loss.detach()))
+    leaves = {k: v.double().clone().requires_grad_(not k.endswith(".lengthscales")) for k, v in sd.items()}
+    opt_ref = torch.optim.Adam([v for v in leaves.values() if v.requires_grad], lr=1e-5)
+    ref = []
+    for _ in range(3):
+        opt_ref.zero_grad(set_to_none=True)
+        loss = fo.nll_loss(leaves, FULL_O, g["atom_types"], g["x_coords"].double(), g["x_velocs"].double(), g["y_coords"].double(),
+                           g["y_velocs"].double(), g["masked_elements"], "direct")
+        loss.backward()
+        opt_ref.step()
+        ref.append(float(loss.detach()))
+    assert abs(ref[2] - ref[0]) > 0.05  # the three steps move the loss well beyond the tolerance
+    for a, b in zip(ours, ref):
+        assert abs(a - b) < 2e-4 * max(1.0, abs(b)), (ours, ref)
