@@ -385,6 +385,9 @@ def md_case():
     out.update(x0=np.stack(x0), v0=np.stack(v0), f0=np.stack(f0), x1=np.stack(x1), v1=np.stack(v1))
     d = np.load(os.path.join(REF, "simulation/testdata/implicit-2olx-traj-cpu-arrays.npz"))  # checked by simulation/tests/test_md.py:35-47
     out.update(ke_velocities=d["velocities"], ke_forces=d["forces"], ke_openmm=d["energies"][:, 1])
+    # the reference's golden potential energies (simulation/tests/test_md.py:35-47, atol 1e-3 kJ/mol) + the topology they
+    # belong to: reproducible wherever OpenMM 7.7 + amber99sbildn/amber99_obc exist (tests/test_forcefield_cpu.py, skipped here)
+    out.update(pot_positions=d["positions"], pot_openmm=d["energies"][:, 0], state0_pdb=np.array("\n".join(pdb)))
     np.savez_compressed(os.path.join(HERE, "langevin_2olx_pairs.npz"), **out)
     print("md case:", len(x0), "consecutive steps,", len(d["step"]), "kinetic energies")
 

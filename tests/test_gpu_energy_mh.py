@@ -481,3 +481,22 @@ def test_sample_trajectory_writes_and_resumes(tmp_path):
     np.testing.assert_array_equal(z2["positions"][0], z1["positions"][-1])  # resumed from the last saved position
     with pytest.raises(AssertionError):
         sampling.sample_trajectory(batch, m, torch.device("cuda"), energy, masses, out, "ad", num_samples=5, saving_interval=20)
+
+
+def test_energy_kernel_reference_golden_energies_with_openmm():
+    """The reference's golden potential energies (simulation/tests/test_md.py:35-47, atol 1e-3 kJ/mol) through the CUDA kernel;
+    needs OpenMM + its Amber XML files to build the System (skipped otherwise; the CPU twin is in tests/test_forcefield_cpu.py)."""
+    pytest.importorskip("openmm")
+    import io
+    import os
+    from openmm import app, unit
+    from tests.common import GOLDEN
+    from timewarp_b200.forcefield import system_description_from_openmm
+
+    g = np.load(os.path.join(GOLDEN, "langevin_2olx_pairs.npz"))
+    pdb = app.PDBFile(io.StringIO(str(g["state0_pdb"])))
+    ff = app.ForceField("amber99sbildn.xml", "amber99_obc.xml")
+    system = ff.createSystem(pdb.topology, nonbondedMethod=app.CutoffNonPeriodic, nonbondedCutoff=2.0 * unit.nanometer, constraints=None)
+    energy = PeptidePotentialEnergy(system_description_from_openmm(system))
+    e = energy(torch.from_numpy(g["pot_positions"]).cuda()).cpu().numpy()[:, 0]
+    np.testing.assert_allclose(e, g["pot_openmm"], rtol=0, atol=1e-3)

@@ -233,3 +233,79 @@ def amber_like_system(peptide, gb: str = "obc2", total_charge: float = 0.0) -> S
         gb_radius=rad, gb_scale=scl, masses=np.asarray(peptide.masses, dtype=np.float64),
         gb_alpha=g["alpha"], gb_beta=g["beta"], gb_gamma=g["gamma"],
     )  # fmt: skip
+
+
+# ------------------------------------------------------------------------------------------------
+# openmm.System -> SystemDescription (where OpenMM exists: the reference builds the System in simulation/md.py:128-187)
+def _val(q):
+    """Plain float of an OpenMM Quantity in its default MD unit system (nm, ps, kJ/mol, radian, elementary charge, dalton)."""
+    if hasattr(q, "value_in_unit_system"):
+        try:
+            import openmm.unit as u  # noqa: WPS433 (only reachable where OpenMM is installed)
+
+            return float(q.value_in_unit_system(u.md_unit_system))
+        except ImportError:
+            pass
+    return float(getattr(q, "_value", q))
+
+
+def system_description_from_openmm(system, temperature: float = 310.0) -> SystemDescription:
+    """Read the forces of an `openmm.System` created by `simulation.md.get_system` (simulation/md.py:128-187) for the
+    implicit-solvent presets: HarmonicBondForce, HarmonicAngleForce, PeriodicTorsionForce, NonbondedForce (NoCutoff /
+    CutoffNonPeriodic) and GBSAOBCForce; CMMotionRemover carries no energy.  Forces are dispatched on their class NAME, so
+    anything exposing the same getters works (tests/test_forcefield_cpu.py feeds an OpenMM-shaped stand-in).  Explicit-solvent
+    systems (PME) and CustomGBForce-based GB models (`implicit/obc1.xml` of OpenMM >= 7.6) are rejected, not approximated."""
+    n = int(system.getNumParticles())
+    kw: Dict[str, object] = dict(
+        n_atoms=n, masses=np.array([_val(system.getParticleMass(i)) for i in range(n)], dtype=np.float64),
+        bond_idx=np.zeros((0, 2), np.int32), bond_param=np.zeros((0, 2)), angle_idx=np.zeros((0, 3), np.int32),
+        angle_param=np.zeros((0, 2)), torsion_idx=np.zeros((0, 4), np.int32), torsion_param=np.zeros((0, 3)),
+        charge=np.zeros(n), sigma=np.ones(n), epsilon=np.zeros(n), excluded=np.zeros((n, n), np.uint8),
+        exception_idx=np.zeros((0, 2), np.int32), exception_param=np.zeros((0, 3)), gb_radius=np.zeros(n), gb_scale=np.zeros(n),
+        use_gb=False, cutoff=0.0, temperature=float(temperature))
+    for force in system.getForces():
+        name = type(force).__name__
+        if name == "HarmonicBondForce":
+            p = [force.getBondParameters(i) for i in range(force.getNumBonds())]
+            kw["bond_idx"] = np.array([[a, b] for a, b, _, _ in p], np.int32).reshape(-1, 2)
+            kw["bond_param"] = np.array([[_val(r0), _val(k)] for _, _, r0, k in p], np.float64).reshape(-1, 2)
+        elif name == "HarmonicAngleForce":
+            p = [force.getAngleParameters(i) for i in range(force.getNumAngles())]
+            kw["angle_idx"] = np.array([[a, b, c] for a, b, c, _, _ in p], np.int32).reshape(-1, 3)
+            kw["angle_param"] = np.array([[_val(t0), _val(k)] for _, _, _, t0, k in p], np.float64).reshape(-1, 2)
+        elif name == "PeriodicTorsionForce":
+            p = [force.getTorsionParameters(i) for i in range(force.getNumTorsions())]
+            kw["torsion_idx"] = np.array([[a, b, c, d] for a, b, c, d, _, _, _ in p], np.int32).reshape(-1, 4)
+            kw["torsion_param"] = np.array([[float(per), _val(ph), _val(k)] for _, _, _, _, per, ph, k in p], np.float64).reshape(-1, 3)
+        elif name == "NonbondedForce":
+            method = int(force.getNonbondedMethod())  # 0 NoCutoff, 1 CutoffNonPeriodic, 2 CutoffPeriodic, 3 Ewald, 4 PME, 5 LJPME
+            if method not in (0, 1):
+                raise NotImplementedError("periodic / PME NonbondedForce (explicit solvent) is outside the energy kernel's scope")
+            pp = [force.getParticleParameters(i) for i in range(n)]
+            kw["charge"] = np.array([_val(q) for q, _, _ in pp])
+            kw["sigma"] = np.array([_val(s) for _, s, _ in pp])
+            kw["epsilon"] = np.array([_val(e) for _, _, e in pp])
+            excluded = np.eye(n, dtype=np.uint8)  # (self pairs are never interactions; amber_like_system marks them too)
+            ex_idx, ex_par = [], []
+            for i in range(force.getNumExceptions()):
+                a, b, qq, sig, eps = force.getExceptionParameters(i)
+                excluded[a, b] = excluded[b, a] = 1  # every exception pair leaves the regular pair loop
+                if _val(qq) != 0.0 or _val(eps) != 0.0:
+                    ex_idx.append((a, b))
+                    ex_par.append((_val(qq), _val(sig), _val(eps)))
+            kw["excluded"] = excluded
+            kw["exception_idx"] = np.array(ex_idx, np.int32).reshape(-1, 2)
+            kw["exception_param"] = np.array(ex_par, np.float64).reshape(-1, 3)
+            kw["cutoff"] = _val(force.getCutoffDistance()) if method == 1 else 0.0
+            kw["reaction_field_eps"] = float(force.getReactionFieldDielectric())
+        elif name == "GBSAOBCForce":  # OBC2 (amber99_obc.xml): alpha, beta, gamma = 1, 0.8, 4.85
+            pp = [force.getParticleParameters(i) for i in range(n)]
+            kw["gb_radius"] = np.array([_val(r) for _, r, _ in pp])
+            kw["gb_scale"] = np.array([float(s) for _, _, s in pp])
+            kw.update(use_gb=True, gb_alpha=1.0, gb_beta=0.8, gb_gamma=4.85, solute_dielectric=float(force.getSoluteDielectric()),
+                      solvent_dielectric=float(force.getSolventDielectric()), surface_area_energy=_val(force.getSurfaceAreaEnergy()))
+        elif name == "CMMotionRemover":
+            continue
+        else:
+            raise NotImplementedError(f"{name}: no counterpart in the energy kernel (see SystemDescription)")
+    return SystemDescription(**kw)
