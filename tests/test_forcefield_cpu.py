@@ -100,7 +100,7 @@ class GBSAOBCForce:
         return self.d.solvent_dielectric
 
     def getSurfaceAreaEnergy(self):
-        return _Q(self.d.surface_area_energy)
+        return _Q(self.d.surface_area_energy / (4.0 * np.pi))  # OpenMM reports sigma; the kernel field is 4 pi sigma
 
 
 class CMMotionRemover:
@@ -133,9 +133,9 @@ def test_extraction_round_trip():
               "gb_radius", "gb_scale", "masses"):
         np.testing.assert_array_equal(getattr(got, f), getattr(d, f), err_msg=f)
     assert sorted(map(tuple, got.exception_idx.tolist())) == sorted(tuple(sorted(p)) for p in d.exception_idx.tolist())
-    for f in ("cutoff", "reaction_field_eps", "use_gb", "gb_alpha", "gb_beta", "gb_gamma", "solute_dielectric", "solvent_dielectric",
-              "surface_area_energy", "n_atoms"):
+    for f in ("cutoff", "reaction_field_eps", "use_gb", "gb_alpha", "gb_beta", "gb_gamma", "solute_dielectric", "solvent_dielectric", "n_atoms"):
         assert getattr(got, f) == getattr(d, f), f
+    assert abs(got.surface_area_energy - d.surface_area_energy) < 1e-12 and abs(d.surface_area_energy / (4 * np.pi) - 2.25936) < 1e-5
     x = pep.coords_nm[None].astype(np.float64) + 0.01 * np.random.default_rng(0).standard_normal((3, pep.num_atoms, 3))
     np.testing.assert_allclose(eo.potential_energy(got, x), eo.potential_energy(d, x), rtol=1e-12)
 

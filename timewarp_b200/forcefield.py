@@ -303,7 +303,10 @@ def system_description_from_openmm(system, temperature: float = 310.0) -> System
             kw["gb_radius"] = np.array([_val(r) for _, r, _ in pp])
             kw["gb_scale"] = np.array([float(s) for _, _, s in pp])
             kw.update(use_gb=True, gb_alpha=1.0, gb_beta=0.8, gb_gamma=4.85, solute_dielectric=float(force.getSoluteDielectric()),
-                      solvent_dielectric=float(force.getSolventDielectric()), surface_area_energy=_val(force.getSurfaceAreaEnergy()))
+                      solvent_dielectric=float(force.getSolventDielectric()),
+                      # OpenMM's ACE term is 4 pi sigma (r + 0.14)^2 (r / B)^6 with sigma = getSurfaceAreaEnergy() (2.25936 kJ/mol/nm^2
+                      # by default); the kernel's `surface_area_energy` is the prefactor 4 pi sigma (28.3919551)
+                      surface_area_energy=4.0 * math.pi * _val(force.getSurfaceAreaEnergy()))
         elif name == "CMMotionRemover":
             continue
         else:
