@@ -174,6 +174,22 @@ int tw_flow_log_likelihood_backward(const tw_flow_config* cfg, const void* const
                                     int64_t V, const float* grad_log_prob, const void* packed_weights, void* tape,
                                     size_t tape_bytes, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Sampling direction under autograd (conditional_sample_with_logp inside the energy-based losses, losses.py:396-664; the
+ * reference differentiates flow.py:242-336 with torch autograd).  tw_flow_sample_train = tw_flow_sample for S = 1 with a tape
+ * (same tape / workspace sizes as tw_flow_train_bytes): z_coords / z_velocs [B,V,3] are the scaled latent draws;
+ * out_delta [B] = sum of the log-scales, i.e. log p(y|x) = prior(z) + out_delta (the caller adds the prior term, which
+ * also carries the gradient of the prior log-scales).  tw_flow_sample_backward: given d/dy_coords, d/dy_velocs and
+ * d/d(delta) it ACCUMULATES the parameter gradients into `grads` (layout as above) and returns d/dz_coords, d/dz_velocs. */
+int tw_flow_sample_train(const tw_flow_config* cfg, const void* const* params, const int64_t* atom_types, const float* x_coords,
+                         const float* x_velocs, const uint8_t* mask, int64_t B, int64_t V, int32_t flags, const float* z_coords,
+                         const float* z_velocs, float* out_y_coords, float* out_y_velocs, float* out_delta,
+                         const void* packed_weights, void* tape, size_t tape_bytes, void* stream);
+int tw_flow_sample_backward(const tw_flow_config* cfg, const void* const* params, void* const* grads, const int64_t* atom_types,
+                            const float* x_velocs, const uint8_t* mask, int64_t B, int64_t V, const float* grad_y_coords,
+                            const float* grad_y_velocs, const float* grad_delta, const void* packed_weights, void* tape,
+                            size_t tape_bytes, void* workspace, size_t workspace_bytes, float* out_grad_z_coords,
+                            float* out_grad_z_velocs, void* stream);
+
 /* Debug: one generic operand-image GEMM of the training path on fp32 row-major inputs.
  * mode 0: C[ar,br] = A B^T; 1: C[ar,bc] = A B; 2: C[ar,128] = sum_h A[:,h*128:(h+1)*128] B[:,h*128:(h+1)*128]
  * (B is [128, H*128]); 3: C[ac,bc] += A^T B (atomic accumulation, `splits` CTAs per output tile). */

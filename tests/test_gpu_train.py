@@ -279,3 +279,112 @@ def test_training_trajectory_matches_oracle():
     assert abs(ref[2] - ref[0]) > 0.05  # the three steps move the loss well beyond the tolerance
     for a, b in zip(ours, ref):
         assert abs(a - b) < 2e-4 * max(1.0, abs(b)), (ours, ref)
+
+
+def test_sampling_backward_matches_oracle_autograd():
+    """conditional_sample_with_logp under autograd (the energy-based losses, losses.py:396-664): gradients of a generic scalar
+    L = <y_coords, G1> + <y_velocs, G2> + <log p, g3> w.r.t. every parameter, against the oracle's fp64 autograd through its
+    own sampling pass with the same latent draws -- ragged batch, prior log-scales included (the draws are eps * exp(log_scale))."""
+    torch.manual_seed(13)
+    B, V = 5, 30
+    lengths = [30, 22, 17, 30, 9]
+    mask = torch.zeros(B, V, dtype=torch.bool)
+    for b, n in enumerate(lengths):
+        mask[b, n:] = True
+    keep = (~mask)[:, :, None]
+    x = 0.3 * torch.randn(B, V, 3) * keep
+    xv = torch.randn(B, V, 3) * keep
+    at = torch.randint(0, 5, (B, V)) * (~mask)
+    eps_c, eps_v = torch.randn(1, B, V, 3), torch.randn(1, B, V, 3)
+    G1, G2, g3 = torch.randn(B, V, 3) * keep, 0.1 * torch.randn(B, V, 3) * keep, torch.randn(B) / V
+    m, sd = build_model(FULL_O, "bf16x3", 5)
+    m.train()
+    m.zero_grad(set_to_none=True)
+    zc = eps_c.cuda() * torch.exp(m.coords_prior_log_scale)
+    zv = eps_v.cuda() * torch.exp(m.velocs_prior_log_scale)
+    yc, yv, lp = m.sample_from_latents(at.cuda(), x.cuda(), xv.cuda(), mask.cuda(), zc, zv)
+    assert yc.requires_grad and lp.shape == (1, B)
+    loss = (yc[0] * G1.cuda()).sum() + (yv[0] * G2.cuda()).sum() + (lp[0] * g3.cuda()).sum()
+    loss.backward()
+    torch.cuda.synchronize()
+    grads = {k: p.grad.detach().cpu() for k, p in m.named_parameters() if p.grad is not None}
+    # the same under no_grad (inference kernels): identical samples and densities
+    with torch.no_grad():
+        yc0, yv0, lp0 = m.sample_from_latents(at.cuda(), x.cuda(), xv.cuda(), mask.cuda(), zc.detach(), zv.detach())
+    torch.testing.assert_close(yc.detach(), yc0, rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(lp.detach(), lp0, rtol=1e-6, atol=2e-4)
+    # oracle, fp64
+    leaves = {k: v.double().clone().requires_grad_(not k.endswith(".lengthscales")) for k, v in sd.items()}
+    zc64 = eps_c.double() * torch.exp(leaves["coords_prior_log_scale"])
+    zv64 = eps_v.double() * torch.exp(leaves["velocs_prior_log_scale"])
+    ryc, ryv, rlp = fo.conditional_sample_with_logp(leaves, FULL_O, at, x.double(), xv.double(), mask, 1, zc64, zv64, distance_mode="direct")
+    rloss = (ryc[0] * G1.double()).sum() + (ryv[0] * G2.double()).sum() + (rlp[0] * g3.double()).sum()
+    assert abs(float(loss) - float(rloss)) < 1e-4 * max(1.0, abs(float(rloss)))
+    names = [k for k, v in leaves.items() if v.requires_grad]
+    ref = dict(zip(names, torch.autograd.grad(rloss, [leaves[k] for k in names], allow_unused=True)))
+    total = float(torch.sqrt(sum(g.norm() ** 2 for g in ref.values() if g is not None)))
+    errs = []
+    for k, r in ref.items():
+        r = torch.zeros_like(leaves[k]) if r is None else r
+        err = float((grads[k].double() - r).norm())
+        scale = max(float(r.norm()), 1e-4 * total)
+        errs.append(err / scale)
+        assert err <= _tol(k) * scale, (k, err, float(r.norm()))
+    assert float(np.median(errs)) < GRAD_MEDIAN_RTOL
+    print("sampling backward: worst", max(errs), "median", float(np.median(errs)))
+
+
+def test_energy_loss_trains_through_the_sampler():
+    """EnergyLoss (losses.py:558-664) on the GPU path: value == the hand-composed E(y)/kT + KE + log p with the fp64 energy
+    oracle on the same samples; its gradient == the generic sampling backward fed with -F/kT, v and 1/n_atoms; one Adam step
+    on it lowers the loss."""
+    from oracle import energy_oracle as eo
+    from timewarp_b200 import losses
+    from timewarp_b200.energy import PeptidePotentialEnergy
+    from timewarp_b200.forcefield import amber_like_system
+    from timewarp_b200.peptides import alanine_dipeptide
+
+    pep = alanine_dipeptide()
+    sysd = amber_like_system(pep)
+    energy = PeptidePotentialEnergy(sysd)
+    provider = losses.EnergyProvider({"ad": energy}, {"ad": torch.tensor(pep.masses, dtype=torch.float32)})
+    B, V = 6, pep.num_atoms
+    g = torch.Generator().manual_seed(3)
+
+    class Batch:
+        atom_coords = torch.tensor(pep.coords_nm, dtype=torch.float32)[None] + 0.005 * torch.randn(B, V, 3, generator=g)
+        atom_velocs = torch.zeros(B, V, 3)
+        atom_types = torch.tensor(pep.atom_types)[None].repeat(B, 1)
+        masked_elements = torch.zeros(B, V, dtype=torch.bool)
+        adj_list, edge_batch_idx = EMPTY_ADJ, EMPTY_EBI
+        names, segments = ["ad"] * B, [0, B]
+
+    import bench
+    m, _ = build_model(FULL_O, "bf16x3", 0)
+    m.load_state_dict({k: v.cuda() for k, v in bench.bench_state_dict(m, "proposal").items()})  # local moves: finite energies
+    m.train()
+    spec = losses.EnergyLoss(provider, random_velocs=True, num_samples=1)
+    torch.manual_seed(21)
+    loss = losses.energy_loss(spec, m, Batch, device="cuda")
+    m.zero_grad(set_to_none=True)
+    loss.backward()
+    grads = {k: p.grad.detach().clone() for k, p in m.named_parameters() if p.grad is not None}
+    assert len(grads) == len(list(m.parameters())) and all(torch.isfinite(v).all() for v in grads.values())
+    # value: replay the draws (x_velocs, then the two latent draws) and compose the loss by hand with the fp64 energy oracle
+    torch.manual_seed(21)
+    xv = torch.randn_like(Batch.atom_coords.cuda())
+    with torch.no_grad():
+        yc, yv, lp = m.conditional_sample_with_logp(atom_types=Batch.atom_types.cuda(), x_coords=Batch.atom_coords.cuda(), x_velocs=xv,
+                                                    adj_list=EMPTY_ADJ.cuda(), edge_batch_idx=EMPTY_EBI.cuda(),
+                                                    masked_elements=Batch.masked_elements.cuda(), num_samples=1)
+    u = eo.potential_energy(sysd.as_float32(), yc[0].cpu().numpy().astype(np.float64)) / energy.kbT
+    ke = 0.5 * (yv[0].double() ** 2).sum((-1, -2)).cpu().numpy()
+    want = float(((u + ke + lp[0].double().cpu().numpy()) / V).mean())
+    assert abs(float(loss) - want) < 2e-4 * max(1.0, abs(want)), (float(loss), want)
+    # one optimizer step on the energy loss lowers it (same draws)
+    opt = torch.optim.Adam(m.parameters(), lr=1e-5)
+    opt.step()
+    torch.manual_seed(21)
+    with torch.no_grad():
+        after = losses.energy_loss(spec, m, Batch, device="cuda")
+    assert float(after) < float(loss), (float(loss), float(after))

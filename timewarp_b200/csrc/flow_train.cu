@@ -561,6 +561,22 @@ __global__ void __launch_bounds__(128) k_coupling_bwd(const float* __restrict__ 
   }
 }
 
+// Sampling direction (nvp.py:137-183): z_out = (z_in - t) e^{-s}, delta += sum s.  Given d/dz_out in dz and g = d/d(delta):
+__global__ void __launch_bounds__(128) k_coupling_rev_bwd(const float* __restrict__ s, const float* __restrict__ z_out,
+                                                          float* __restrict__ dz, const uint8_t* __restrict__ mask,
+                                                          const float* __restrict__ g, int V, float* __restrict__ ds,
+                                                          float* __restrict__ dt) {
+  const int64_t n = blockIdx.x;
+  const float gn = g[n];
+  for (int e = threadIdx.x; e < V * 3; e += blockDim.x) {
+    const int64_t i = n * V * 3 + e;
+    const float isc = expf(-s[i]), d = dz[i];
+    ds[i] = -d * z_out[i] + (mask[n * V + e / 3] ? 0.f : gn);
+    dt[i] = -d * isc;
+    dz[i] = d * isc;
+  }
+}
+
 // Prior backward (flow.py:159-166,191-203): lp = sum keep * (-z^2 / (2 e^{2 sigma}) - sigma - const)
 __global__ void __launch_bounds__(128) k_prior_bwd(const float* __restrict__ zc, const float* __restrict__ zv,
                                                    const uint8_t* __restrict__ mask, const float* __restrict__ lsc,
@@ -1126,6 +1142,47 @@ int tw_flow_train_bytes(const tw_flow_config* cfg, int64_t B, int64_t V, size_t*
   return TW_OK;
 }
 
+// conditioner pair of coupling layer k on `z_other`, every layer boundary written to the tape; (s, t) end up in net[k][.].st
+static int taped_conditioner(const tw_flow_config* cfg, const ParamView& pv, const void* packed_weights, Tape& tp, int k,
+                             const float* z_other, const int64_t* atom_types, const float* x_velocs, int64_t B, int64_t V,
+                             cudaStream_t st) {
+  const int T = cfg->num_transformer_layers;
+  const int64_t M = B * V;
+  TcScratch tc{};
+  tc.packed = (const uint8_t*)packed_weights;
+  tc.scores_img = tp.scores_img;
+  float* h0[2] = {tp.net[k][0].h[0], tp.net[k][1].h[0]};
+  TW_TRY(tc_in_mlp(cfg, pv, k, tc, atom_types, tp.xc, x_velocs, z_other, h0, B, B, (int)V, st));
+  for (int t = 0; t < T; t++) {
+    float* hin[2] = {tp.net[k][0].h[t], tp.net[k][1].h[t]};
+    float* y1[2] = {tp.net[k][0].y1[t], tp.net[k][1].y1[t]};
+    float* r1[2] = {tp.net[k][0].r1[t], tp.net[k][1].r1[t]};
+    float* r2[2] = {tp.net[k][0].r2[t], tp.net[k][1].r2[t]};
+    float* hout[2] = {tp.net[k][0].h[t + 1], tp.net[k][1].h[t + 1]};
+    tc.mixed_img[0] = tp.net[k][0].mixed[t], tc.mixed_img[1] = tp.net[k][1].mixed[t];
+    if (M % 128) {  // rows past the last token of the tail tile are read by the weight-gradient GEMM: keep them zero
+      const size_t tile_bytes = tc_mixed_img_bytes(cfg, 128);
+      for (int s = 0; s < 2; s++) TW_CUDA(cudaMemsetAsync(tc.mixed_img[s] + (size_t)(M / 128) * tile_bytes, 0, tile_bytes, st));
+    }
+    TW_TRY(tc_attention_layer(cfg, pv, k, t, tc, hin, y1, B, B, (int)V, st, r1));
+    TW_TRY(tc_ffn_layer(cfg, pv, k, t, tc, y1, hout, M, st, r2));
+  }
+  float* hl[2] = {tp.net[k][0].h[T], tp.net[k][1].h[T]};
+  float* so[2] = {tp.net[k][0].st, tp.net[k][1].st};
+  TW_TRY(tc_out_mlp(cfg, pv, k, tc, hl, so, M, st));
+  return TW_OK;
+}
+
+static int begin_taped_pass(const tw_flow_config* cfg, const ParamView& pv, Tape& tp, const float* x_coords, const uint8_t* mask,
+                            int64_t B, int64_t V, cudaStream_t st) {
+  TW_TRY(launch_prep(x_coords, mask, B, (int)V, tp.xc, tp.com, st));
+  TW_TRY(launch_scores(tp.xc, mask, pv.enc(0, 0, 0, 1), B, (int)V, cfg->num_heads, tp.scores, st));
+  TW_TRY(tc_scores_images(cfg, tp.scores, B, (int)V, tp.scores_img, 0, st));
+  TW_TRY(tc_scores_images(cfg, tp.scores, B, (int)V, tp.scores_img_t, 1, st));
+  TW_CUDA(cudaMemsetAsync(tp.delta, 0, B * sizeof(float), st));
+  return TW_OK;
+}
+
 int tw_flow_log_likelihood_train(const tw_flow_config* cfg, const void* const* params, const int64_t* atom_types,
                                  const float* x_coords, const float* x_velocs, const float* y_coords, const float* y_velocs,
                                  const uint8_t* mask, int64_t B, int64_t V, int32_t flags, float* out_log_prob,
@@ -1140,61 +1197,73 @@ int tw_flow_log_likelihood_train(const tw_flow_config* cfg, const void* const* p
   if (need > tape_bytes) return fail(TW_ERR_WORKSPACE, "tape %zu < %zu", tape_bytes, need);
   cudaStream_t st = (cudaStream_t)stream;
   ParamView pv{cfg, params};
-  const int L = cfg->num_coupling_layers, T = cfg->num_transformer_layers;
+  const int L = cfg->num_coupling_layers;
   const int64_t M = B * V, cnt = M * 3;
-  TW_TRY(launch_prep(x_coords, mask, B, (int)V, tp.xc, tp.com, st));
-  TW_TRY(launch_scores(tp.xc, mask, pv.enc(0, 0, 0, 1), B, (int)V, cfg->num_heads, tp.scores, st));
-  TW_TRY(tc_scores_images(cfg, tp.scores, B, (int)V, tp.scores_img, 0, st));
-  TW_TRY(tc_scores_images(cfg, tp.scores, B, (int)V, tp.scores_img_t, 1, st));
+  TW_TRY(begin_taped_pass(cfg, pv, tp, x_coords, mask, B, V, st));
   if (flags & TW_FLOW_DISPLACEMENT_TARGET)
     TW_TRY(launch_sub(y_coords, x_coords, cnt, tp.z[0][0], st));
   else
     TW_CUDA(cudaMemcpyAsync(tp.z[0][0], y_coords, cnt * sizeof(float), cudaMemcpyDeviceToDevice, st));
   TW_CUDA(cudaMemcpyAsync(tp.z[0][1], y_velocs, cnt * sizeof(float), cudaMemcpyDeviceToDevice, st));
-  TW_CUDA(cudaMemsetAsync(tp.delta, 0, B * sizeof(float), st));
   for (int k = 0; k < L; k++) {
     const bool pos = (k % 2) == cfg->position_layer_index_mod_2;
-    TcScratch tc{};
-    tc.packed = (const uint8_t*)packed_weights;
-    tc.scores_img = tp.scores_img;
-    float* h0[2] = {tp.net[k][0].h[0], tp.net[k][1].h[0]};
-    TW_TRY(tc_in_mlp(cfg, pv, k, tc, atom_types, tp.xc, x_velocs, pos ? tp.z[k][1] : tp.z[k][0], h0, B, B, (int)V, st));
-    for (int t = 0; t < T; t++) {
-      float* hin[2] = {tp.net[k][0].h[t], tp.net[k][1].h[t]};
-      float* y1[2] = {tp.net[k][0].y1[t], tp.net[k][1].y1[t]};
-      float* r1[2] = {tp.net[k][0].r1[t], tp.net[k][1].r1[t]};
-      float* r2[2] = {tp.net[k][0].r2[t], tp.net[k][1].r2[t]};
-      float* hout[2] = {tp.net[k][0].h[t + 1], tp.net[k][1].h[t + 1]};
-      tc.mixed_img[0] = tp.net[k][0].mixed[t], tc.mixed_img[1] = tp.net[k][1].mixed[t];
-      if (M % 128) {  // rows past the last token of the tail tile are read by the weight-gradient GEMM: keep them zero
-        const size_t tile_bytes = tc_mixed_img_bytes(cfg, 128);
-        for (int s = 0; s < 2; s++) TW_CUDA(cudaMemsetAsync(tc.mixed_img[s] + (size_t)(M / 128) * tile_bytes, 0, tile_bytes, st));
-      }
-      TW_TRY(tc_attention_layer(cfg, pv, k, t, tc, hin, y1, B, B, (int)V, st, r1));
-      TW_TRY(tc_ffn_layer(cfg, pv, k, t, tc, y1, hout, M, st, r2));
-    }
-    float* hl[2] = {tp.net[k][0].h[T], tp.net[k][1].h[T]};
-    float* so[2] = {tp.net[k][0].st, tp.net[k][1].st};
-    TW_TRY(tc_out_mlp(cfg, pv, k, tc, hl, so, M, st));
+    TW_TRY(taped_conditioner(cfg, pv, packed_weights, tp, k, pos ? tp.z[k][1] : tp.z[k][0], atom_types, x_velocs, B, V, st));
     // next state: copy both halves, then transform the target half in place
     TW_CUDA(cudaMemcpyAsync(tp.z[k + 1][0], tp.z[k][0], cnt * sizeof(float), cudaMemcpyDeviceToDevice, st));
     TW_CUDA(cudaMemcpyAsync(tp.z[k + 1][1], tp.z[k][1], cnt * sizeof(float), cudaMemcpyDeviceToDevice, st));
-    TW_TRY(launch_coupling(so[0], so[1], pos ? tp.z[k + 1][0] : tp.z[k + 1][1], mask, tp.delta, B, B, (int)V, 0, nullptr, nullptr, st));
+    TW_TRY(launch_coupling(tp.net[k][0].st, tp.net[k][1].st, pos ? tp.z[k + 1][0] : tp.z[k + 1][1], mask, tp.delta, B, B, (int)V, 0, nullptr,
+                           nullptr, st));
   }
   TW_TRY(launch_prior(tp.z[L][0], tp.z[L][1], mask, pv.log_scale_c(), pv.log_scale_v(), tp.delta, -1.f, B, B, (int)V, out_log_prob, st));
   return TW_OK;
 }
 
-int tw_flow_log_likelihood_backward(const tw_flow_config* cfg, const void* const* params, void* const* grads,
-                                    const int64_t* atom_types, const float* x_velocs, const uint8_t* mask, int64_t B, int64_t V,
-                                    const float* grad_log_prob, const void* packed_weights, void* tape, size_t tape_bytes,
-                                    void* workspace, size_t workspace_bytes, void* stream) {
+// Sampling direction with a tape (conditional_sample_with_logp under autograd: the energy-based losses, losses.py:396-664):
+// z[L] = the latent draws, layers L-1 .. 0 in reverse mode; the tape ends up holding exactly what a density pass on the
+// resulting y would record (layer k's conditioner reads the half that layer k leaves unchanged), so the backward shares
+// conditioner_bwd.  out_delta = sum of log-scales (log p(y|x) = prior(z) + delta; the caller adds the prior term).
+int tw_flow_sample_train(const tw_flow_config* cfg, const void* const* params, const int64_t* atom_types, const float* x_coords,
+                         const float* x_velocs, const uint8_t* mask, int64_t B, int64_t V, int32_t flags, const float* z_coords,
+                         const float* z_velocs, float* out_y_coords, float* out_y_velocs, float* out_delta,
+                         const void* packed_weights, void* tape, size_t tape_bytes, void* stream) {
   TW_TRY(check_train(cfg, params, B, V));
   if (B == 0) return TW_OK;
-  TW_CHECK_ARG(grads && atom_types && x_velocs && mask && grad_log_prob, "NULL pointer");
+  TW_CHECK_ARG(atom_types && x_coords && x_velocs && z_coords && z_velocs && mask && out_y_coords && out_y_velocs && out_delta, "NULL pointer");
+  TW_CHECK_ARG(packed_weights && ((uintptr_t)packed_weights & 1023) == 0, "packed_weights missing or not 1024-byte aligned");
+  TW_CHECK_ARG(tape && ((uintptr_t)tape & 1023) == 0, "tape missing or not 1024-byte aligned");
+  Tape tp;
+  const size_t need = carve_tape(cfg, B, (int)V, tape, tape_bytes, &tp);
+  if (need > tape_bytes) return fail(TW_ERR_WORKSPACE, "tape %zu < %zu", tape_bytes, need);
+  cudaStream_t st = (cudaStream_t)stream;
+  ParamView pv{cfg, params};
+  const int L = cfg->num_coupling_layers;
+  const int64_t cnt = B * V * 3;
+  TW_TRY(begin_taped_pass(cfg, pv, tp, x_coords, mask, B, V, st));
+  TW_CUDA(cudaMemcpyAsync(tp.z[L][0], z_coords, cnt * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  TW_CUDA(cudaMemcpyAsync(tp.z[L][1], z_velocs, cnt * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  for (int k = L - 1; k >= 0; k--) {
+    const bool pos = (k % 2) == cfg->position_layer_index_mod_2;
+    TW_TRY(taped_conditioner(cfg, pv, packed_weights, tp, k, pos ? tp.z[k + 1][1] : tp.z[k + 1][0], atom_types, x_velocs, B, V, st));
+    TW_CUDA(cudaMemcpyAsync(tp.z[k][0], tp.z[k + 1][0], cnt * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    TW_CUDA(cudaMemcpyAsync(tp.z[k][1], tp.z[k + 1][1], cnt * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    TW_TRY(launch_coupling(tp.net[k][0].st, tp.net[k][1].st, pos ? tp.z[k][0] : tp.z[k][1], mask, tp.delta, B, B, (int)V, 1, nullptr, nullptr, st));
+  }
+  if (flags & TW_FLOW_DISPLACEMENT_TARGET)
+    TW_TRY(launch_uncentre(tp.xc, tp.com, tp.z[0][0], B, B, (int)V, out_y_coords, st));
+  else
+    TW_CUDA(cudaMemcpyAsync(out_y_coords, tp.z[0][0], cnt * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  TW_CUDA(cudaMemcpyAsync(out_y_velocs, tp.z[0][1], cnt * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  TW_CUDA(cudaMemcpyAsync(out_delta, tp.delta, B * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return TW_OK;
+}
+
+// shared set-up of the two backward entry points
+static int begin_backward(BwdCtx& x, const tw_flow_config* cfg, const void* const* params, void* const* grads, const int64_t* atom_types,
+                          const float* x_velocs, const uint8_t* mask, int64_t B, int64_t V, const void* packed_weights, void* tape,
+                          size_t tape_bytes, void* workspace, size_t workspace_bytes, void* stream) {
+  TW_CHECK_ARG(grads && atom_types && x_velocs && mask, "NULL pointer");
   TW_CHECK_ARG(packed_weights && ((uintptr_t)packed_weights & 1023) == 0, "packed_weights missing or not 1024-byte aligned");
   TW_CHECK_ARG(tape && ((uintptr_t)tape & 1023) == 0 && workspace && ((uintptr_t)workspace & 1023) == 0, "tape / workspace missing or not 1024-byte aligned");
-  BwdCtx x{};
   x.c = cfg;
   x.pv = ParamView{cfg, params};
   x.gv = GradView{ParamView{cfg, nullptr}, grads};
@@ -1212,7 +1281,6 @@ int tw_flow_log_likelihood_backward(const tw_flow_config* cfg, const void* const
   x.atom_types = atom_types, x.x_velocs = x_velocs, x.mask = mask;
   x.B = B, x.V = (int)V, x.M = B * V, x.tiles = (int)((x.M + 127) / 128);
   x.st = (cudaStream_t)stream;
-  const int L = cfg->num_coupling_layers;
   // lengthscale gradient (learnable_kernel): requested by a non-NULL entry for the lengthscales of chain[0].scale.layer[0]
   x.dls = x.gv.enc(0, 0, 0, 1);
   if (x.dls) {
@@ -1225,6 +1293,27 @@ int tw_flow_log_likelihood_backward(const tw_flow_config* cfg, const void* const
     }
     TW_CUDA(cudaMemsetAsync(x.b.sgrad, 0, (size_t)B * cfg->num_heads * V * V * sizeof(float), x.st));
   }
+  return TW_OK;
+}
+
+static int finish_backward(BwdCtx& x) {
+  if (x.dls) {
+    k_ls_grad<<<(unsigned)x.B, 256, 0, x.st>>>(x.tp.xc, x.mask, x.pv.enc(0, 0, 0, 1), x.b.sgrad, x.V, x.c->num_heads, x.dls);
+    TW_LAUNCH_CHECK();
+  }
+  return TW_OK;
+}
+
+int tw_flow_log_likelihood_backward(const tw_flow_config* cfg, const void* const* params, void* const* grads,
+                                    const int64_t* atom_types, const float* x_velocs, const uint8_t* mask, int64_t B, int64_t V,
+                                    const float* grad_log_prob, const void* packed_weights, void* tape, size_t tape_bytes,
+                                    void* workspace, size_t workspace_bytes, void* stream) {
+  TW_TRY(check_train(cfg, params, B, V));
+  if (B == 0) return TW_OK;
+  TW_CHECK_ARG(grad_log_prob, "NULL pointer");
+  BwdCtx x{};
+  TW_TRY(begin_backward(x, cfg, params, grads, atom_types, x_velocs, mask, B, V, packed_weights, tape, tape_bytes, workspace, workspace_bytes, stream));
+  const int L = cfg->num_coupling_layers;
   k_prior_bwd<<<(unsigned)B, 128, 0, x.st>>>(x.tp.z[L][0], x.tp.z[L][1], mask, x.pv.log_scale_c(), x.pv.log_scale_v(), grad_log_prob, (int)V,
                                             x.b.dz[0], x.b.dz[1], x.gv.log_scale_c(), x.gv.log_scale_v());
   TW_LAUNCH_CHECK();
@@ -1235,11 +1324,36 @@ int tw_flow_log_likelihood_backward(const tw_flow_config* cfg, const void* const
     TW_LAUNCH_CHECK();
     TW_TRY(conditioner_bwd(x, k, x.b.dz[oth], x.tp.z[k][oth]));
   }
-  if (x.dls) {
-    k_ls_grad<<<(unsigned)B, 256, 0, x.st>>>(x.tp.xc, mask, x.pv.enc(0, 0, 0, 1), x.b.sgrad, (int)V, cfg->num_heads, x.dls);
+  return finish_backward(x);
+}
+
+// Backward of tw_flow_sample_train: given d/dy_coords, d/dy_velocs [B,V,3] and d/d(delta) [B], accumulates the parameter
+// gradients into `grads` and returns d/dz_coords, d/dz_velocs (the latent draws).  The layers are walked in the order
+// 0 .. L-1, the reverse of the order the sampling pass applied them.
+int tw_flow_sample_backward(const tw_flow_config* cfg, const void* const* params, void* const* grads, const int64_t* atom_types,
+                            const float* x_velocs, const uint8_t* mask, int64_t B, int64_t V, const float* grad_y_coords,
+                            const float* grad_y_velocs, const float* grad_delta, const void* packed_weights, void* tape,
+                            size_t tape_bytes, void* workspace, size_t workspace_bytes, float* out_grad_z_coords,
+                            float* out_grad_z_velocs, void* stream) {
+  TW_TRY(check_train(cfg, params, B, V));
+  if (B == 0) return TW_OK;
+  TW_CHECK_ARG(grad_y_coords && grad_y_velocs && grad_delta && out_grad_z_coords && out_grad_z_velocs, "NULL pointer");
+  BwdCtx x{};
+  TW_TRY(begin_backward(x, cfg, params, grads, atom_types, x_velocs, mask, B, V, packed_weights, tape, tape_bytes, workspace, workspace_bytes, stream));
+  const int L = cfg->num_coupling_layers;
+  const size_t bytes = (size_t)B * V * 3 * sizeof(float);
+  TW_CUDA(cudaMemcpyAsync(x.b.dz[0], grad_y_coords, bytes, cudaMemcpyDeviceToDevice, x.st));  // y = (x +) z[0]
+  TW_CUDA(cudaMemcpyAsync(x.b.dz[1], grad_y_velocs, bytes, cudaMemcpyDeviceToDevice, x.st));
+  for (int k = 0; k < L; k++) {
+    const bool pos = (k % 2) == cfg->position_layer_index_mod_2;
+    const int tgt = pos ? 0 : 1, oth = 1 - tgt;
+    k_coupling_rev_bwd<<<(unsigned)B, 128, 0, x.st>>>(x.tp.net[k][0].st, x.tp.z[k][tgt], x.b.dz[tgt], mask, grad_delta, (int)V, x.b.dst[0], x.b.dst[1]);
     TW_LAUNCH_CHECK();
+    TW_TRY(conditioner_bwd(x, k, x.b.dz[oth], x.tp.z[k][oth]));
   }
-  return TW_OK;
+  TW_CUDA(cudaMemcpyAsync(out_grad_z_coords, x.b.dz[0], bytes, cudaMemcpyDeviceToDevice, x.st));
+  TW_CUDA(cudaMemcpyAsync(out_grad_z_velocs, x.b.dz[1], bytes, cudaMemcpyDeviceToDevice, x.st));
+  return finish_backward(x);
 }
 
 }  // extern "C"

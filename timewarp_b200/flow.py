@@ -7,6 +7,7 @@ every flow pass is ONE call into libtimewarp_b200.so on the current CUDA stream.
 from __future__ import annotations
 
 import ctypes as C
+import math
 from typing import Optional, Tuple
 
 import torch
@@ -31,6 +32,28 @@ def _require_cuda(name: str, t: Tensor, dtype=None) -> Tensor:
 
 def _aligned(buf: Tensor) -> int:
     return (buf.data_ptr() + 1023) // 1024 * 1024
+
+
+def _gradient_table(model, dev, ls_grad: bool):
+    """ONE zero-filled flat buffer for every gradient (and for the scratch of frozen parameters the kernels still accumulate
+    into) -- 659 zeros_like fills cost more than the backward GEMMs at small batch sizes -- and the table of pointers into it.
+    ls_grad: also request dL/d(lengthscales of the pass) (learnable_kernel)."""
+    tensors = model._ordered_params()
+    need = [t.requires_grad and t.is_floating_point() for t in tensors]
+    wants = [n or (t.is_floating_point() and not _is_optional_grad(model, i)) for i, (t, n) in enumerate(zip(tensors, need))]
+    ls_slot = 3 + 2 * (model._cfg.num_mlp_hidden + 1) + 1  # lengthscales of chain[0].scale_transformer.encoder_layers[0]
+    if ls_grad:
+        wants[ls_slot] = True  # a non-NULL entry asks the backward for dL/d(lengthscales of the pass)
+    sizes = [((t.numel() + 3) // 4 * 4 if w else 0) for t, w in zip(tensors, wants)]  # 16-byte aligned slices
+    flat = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
+    views, off = [], 0
+    for t, w, n in zip(tensors, wants, sizes):
+        views.append(flat[off:off + t.numel()].view(t.shape) if w else None)
+        off += n
+    grads = [v if nd else None for v, nd in zip(views, need)]
+    model._last_flat_grad = flat  # data-parallel training all-reduces this buffer directly (distributed.py)
+    gtable = (C.c_void_p * len(tensors))(*[(v.data_ptr() if v is not None else None) for v in views])
+    return tensors, views, grads, gtable, ls_slot, ls_grad
 
 
 class _LogLikelihoodFn(torch.autograd.Function):
@@ -78,25 +101,8 @@ class _LogLikelihoodFn(torch.autograd.Function):
         # (the re-pack epoch may differ: an inference call in between re-packs the same parameters into the same buffer)
         if model._packed is None or (model._packed[2][0], model._packed[2][2]) != (ctx.packed_key[0], ctx.packed_key[2]):
             raise _lib.TimewarpB200Error("parameters were modified between the forward and the backward pass")
-        tensors = model._ordered_params()
-        # ONE zero-filled flat buffer for every gradient (and for the scratch of frozen parameters the kernels still
-        # accumulate into): 659 zeros_like fills cost more than the backward GEMMs at small batch sizes
-        need = [t.requires_grad and t.is_floating_point() for t in tensors]
-        wants = [n or (t.is_floating_point() and not _is_optional_grad(model, i)) for i, (t, n) in enumerate(zip(tensors, need))]
-        ls_slot = 3 + 2 * (model._cfg.num_mlp_hidden + 1) + 1  # lengthscales of chain[0].scale_transformer.encoder_layers[0]
-        ls_grad = ctx.n_extra == 1 and ctx.needs_input_grad[-1]
-        if ls_grad:
-            wants[ls_slot] = True  # a non-NULL entry asks the backward for dL/d(lengthscales of the pass)
-        sizes = [((t.numel() + 3) // 4 * 4 if w else 0) for t, w in zip(tensors, wants)]  # 16-byte aligned slices
-        flat = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
-        views, off = [], 0
-        for t, w, n in zip(tensors, wants, sizes):
-            views.append(flat[off:off + t.numel()].view(t.shape) if w else None)
-            off += n
-        grads = [v if nd else None for v, nd in zip(views, need)]
-        model._last_flat_grad = flat  # data-parallel training all-reduces this buffer directly (distributed.py)
+        tensors, views, grads, gtable, ls_slot, ls_grad = _gradient_table(model, dev, ctx.n_extra == 1 and ctx.needs_input_grad[-1])
         table = model._param_table(dev)
-        gtable = (C.c_void_p * len(tensors))(*[(v.data_ptr() if v is not None else None) for v in views])
         ws = torch.empty(ws_b + 1024, dtype=torch.uint8, device=dev)
         g_in = grad_out.to(torch.float32).contiguous()
         _lib.check(
@@ -113,6 +119,76 @@ class _LogLikelihoodFn(torch.autograd.Function):
                 g_log_ls = views[ls_slot].mul_(tensors[ls_slot])
             return (None,) * 7 + tuple(grads) + (g_log_ls,)
         return (None,) * 7 + tuple(grads)
+
+
+class _SampleFn(torch.autograd.Function):
+    """conditional_sample_with_logp under autograd (the energy-based losses, losses.py:396-664): y and delta = log p(y|x) -
+    prior(z) from the taped sampling pass (tw_flow_sample_train); the backward (tw_flow_sample_backward) returns the gradient
+    of every trainable parameter and of the latent draws z.  The prior term and the scaling of the draws by exp(log_scale)
+    stay in torch, so the prior log-scales get their gradient from autograd."""
+
+    @staticmethod
+    def forward(ctx, model, atom_types, x_coords, x_velocs, mask_u8, z_coords, z_velocs, *params):
+        ctx.n_extra = 1 if model._learnable else 0
+        lib = _lib.load()
+        dev = x_coords.device
+        B, V = x_coords.shape[0], x_coords.shape[1]
+        cfg = model._cfg
+        tape_b, ws_b = C.c_size_t(0), C.c_size_t(0)
+        _lib.check(lib.tw_flow_train_bytes(C.byref(cfg), B, V, C.byref(tape_b), C.byref(ws_b)), "tw_flow_train_bytes")
+        tape = torch.empty(tape_b.value + 1024, dtype=torch.uint8, device=dev)
+        y_coords, y_velocs = torch.empty_like(x_coords), torch.empty_like(x_coords)
+        delta = torch.empty(B, dtype=torch.float32, device=dev)
+        table = model._param_table(dev)
+        packed = model._packed_weights(dev, force=True)
+        model._stale_after_train = True
+        zc, zv = z_coords.detach().contiguous(), z_velocs.detach().contiguous()
+        _lib.check(
+            lib.tw_flow_sample_train(
+                C.byref(cfg), table, _lib.ptr(atom_types), _lib.ptr(x_coords), _lib.ptr(x_velocs), _lib.ptr(mask_u8), B, V,
+                model._flags(), _lib.ptr(zc), _lib.ptr(zv), _lib.ptr(y_coords), _lib.ptr(y_velocs), _lib.ptr(delta), packed,
+                _aligned(tape), tape_b.value, model._stream(dev),
+            ),
+            "tw_flow_sample_train",
+        )  # fmt: skip
+        ctx.model, ctx.tape, ctx.sizes = model, tape, (B, V, tape_b.value, ws_b.value)
+        ctx.packed_key = model._packed[2]
+        ctx.save_for_backward(atom_types, x_velocs, mask_u8)
+        return y_coords, y_velocs, delta
+
+    @staticmethod
+    def backward(ctx, g_yc, g_yv, g_delta):
+        lib = _lib.load()
+        model = ctx.model
+        atom_types, x_velocs, mask_u8 = ctx.saved_tensors
+        dev = x_velocs.device
+        B, V, tape_b, ws_b = ctx.sizes
+        if model._packed is None or (model._packed[2][0], model._packed[2][2]) != (ctx.packed_key[0], ctx.packed_key[2]):
+            raise _lib.TimewarpB200Error("parameters were modified between the forward and the backward pass")
+        tensors, views, grads, gtable, ls_slot, ls_grad = _gradient_table(model, dev, ctx.n_extra == 1 and ctx.needs_input_grad[-1])
+        table = model._param_table(dev)
+        ws = torch.empty(ws_b + 1024, dtype=torch.uint8, device=dev)
+
+        def dense(g, shape):
+            if g is None:
+                return torch.zeros(shape, dtype=torch.float32, device=dev)
+            return g.to(torch.float32).contiguous()
+
+        g_yc, g_yv, g_delta = dense(g_yc, (B, V, 3)), dense(g_yv, (B, V, 3)), dense(g_delta, (B,))
+        dzc, dzv = torch.empty(B, V, 3, dtype=torch.float32, device=dev), torch.empty(B, V, 3, dtype=torch.float32, device=dev)
+        _lib.check(
+            lib.tw_flow_sample_backward(
+                C.byref(model._cfg), table, gtable, _lib.ptr(atom_types), _lib.ptr(x_velocs), _lib.ptr(mask_u8), B, V,
+                _lib.ptr(g_yc), _lib.ptr(g_yv), _lib.ptr(g_delta), model._packed[1], _aligned(ctx.tape), tape_b, _aligned(ws), ws_b,
+                _lib.ptr(dzc), _lib.ptr(dzv), model._stream(dev),
+            ),
+            "tw_flow_sample_backward",
+        )  # fmt: skip
+        ctx.tape = None
+        out = (None,) * 5 + (dzc, dzv) + tuple(grads)
+        if ctx.n_extra:
+            out += ((views[ls_slot].mul_(tensors[ls_slot]) if ls_grad else None),)
+        return out
 
 
 def _is_optional_grad(model, i: int) -> bool:
@@ -409,6 +485,9 @@ class ConditionalFlowDensityModel(nn.Module):
             raise ValueError("conditional_sample_with_logp requires num_samples == 1 or batch size == 1 (flow.py:326-331)")
         if self.ignore_conditional_velocity:
             x_velocs = torch.zeros_like(x_velocs)
+        trainable = want_logp and S == 1 and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+        if trainable and (self.training or self._train_supported(B, V)):
+            return self._sample_taped(atom_types, x_coords, x_velocs, mask, z_coords, z_velocs)
         if z_coords is None:
             # RNG contract (flow.py:274-275): two normal_() draws [S,B,V,3] from the device's default
             # generator, coords first, each scaled by exp(log_scale).
@@ -436,6 +515,32 @@ class ConditionalFlowDensityModel(nn.Module):
             "tw_flow_sample",
         )  # fmt: skip
         return y_coords, y_velocs, logp
+
+    def _sample_taped(self, atom_types, x_coords, x_velocs, mask, z_coords, z_velocs):
+        """S = 1 sampling with a grad_fn (flow.py:242-336 under autograd): parameters, prior log-scales and -- through them --
+        the samples and their log-density are differentiable; the conditioning state is not."""
+        dev = x_coords.device
+        B, V = x_coords.shape[:2]
+        if z_coords is None:  # same RNG contract as the inference path; the scaling stays on the autograd tape
+            z_coords = torch.empty(1, B, V, 3, dtype=torch.float32, device=dev).normal_() * torch.exp(self.coords_prior_log_scale)
+            z_velocs = torch.empty(1, B, V, 3, dtype=torch.float32, device=dev).normal_() * torch.exp(self.velocs_prior_log_scale)
+        elif z_coords.shape != (1, B, V, 3) or z_velocs.shape != (1, B, V, 3):
+            raise ValueError("latents must be [1, B, V, 3]")
+        self._param_table(dev)
+        self._set_pass_lengthscales(reverse=True)
+        extra = ()
+        if self._learnable:  # the log_lengthscales the sampling pass reads: first attention layer of the LAST coupling layer
+            extra = (self.flow.chain[len(self.flow.chain) - 1].scale_transformer.encoder_layers[0].self_attn.attention.log_lengthscales,)
+        zc, zv = z_coords[0], z_velocs[0]
+        y_coords, y_velocs, delta = _SampleFn.apply(self, atom_types, x_coords, x_velocs, mask.view(torch.uint8), zc, zv,
+                                                    *self._ordered_params(), *extra)
+        keep = (~mask)[:, :, None].to(torch.float32)
+
+        def prior(z, log_scale):  # Normal(0, exp(log_scale)).log_prob summed over the unmasked atoms (flow.py:322-334)
+            return ((-0.5 * (z * torch.exp(-log_scale)) ** 2 - log_scale - 0.5 * math.log(2.0 * math.pi)) * keep).sum((-1, -2))
+
+        logp = prior(zc, self.coords_prior_log_scale) + prior(zv, self.velocs_prior_log_scale) + delta
+        return y_coords[None], y_velocs[None], logp[None]
 
     # ---------------------------------------------------------------- test / debug hooks
     def attention_scores(self, x_coords_centred: Tensor, masked_elements: Tensor) -> Tensor:

@@ -1,0 +1,93 @@
+"""Energy-based training losses on the GPU path: losses.py:24-149 (energies) and :558-664
+(`EnergyLoss`).  The loss differentiates THROUGH the sampler: `conditional_sample_with_logp` runs the taped sampling pass
+(tw_flow_sample_train / tw_flow_sample_backward) and the potential energy returns -force as its gradient
+(tw_peptide_energy), so no OpenMM call and no eager PyTorch network evaluation sits in the training step.
+
+`AcceptanceLoss` (losses.py:274-555) additionally differentiates the reverse-move density w.r.t. its CONDITIONING state
+(the proposal); that gradient (through the attention scores and the conditioner inputs) is not built."""
+from __future__ import annotations
+
+from typing import Callable, Dict, Optional, Sequence, Tuple, Union
+
+import torch
+from torch import Tensor
+
+
+def compute_kinetic_energy(velocs: Tensor, masses: Optional[Tensor], kbT: Optional[float], random_velocs: bool = False) -> Tensor:
+    """losses.py:24-45 (differentiable torch expression; the MH drivers use the tw_kinetic_energy kernel instead)."""
+    if random_velocs:
+        return 0.5 * ((velocs**2.0).sum(-1)).sum(-1)
+    return 0.5 * (masses * (velocs**2.0).sum(-1)).sum(-1) / kbT
+
+
+class EnergyProvider:
+    """The part of `OpenMMProvider` (utils/openmm/openmm_provider.py:134-140) the losses use: an energy module and the
+    masses per protein name, one temperature."""
+
+    def __init__(self, energies: Dict[str, Callable[[Tensor], Tensor]], masses: Optional[Dict[str, Tensor]] = None):
+        self._energies, self._masses = dict(energies), dict(masses or {})
+        kbTs = {float(e.kbT) for e in self._energies.values()}
+        assert len(kbTs) == 1, "all systems of a provider share one temperature"
+        self.kbT = kbTs.pop()
+
+    def get_potential_energy_module(self, name: str):
+        return self._energies[name]
+
+    def get_masses(self, name: str) -> Tensor:
+        return self._masses[name]
+
+
+def compute_potential_energy(coords: Tensor, pdb_names: Sequence[str], masked_elements: Tensor, provider: EnergyProvider,
+                             segments: Optional[Sequence[int]] = None) -> Tensor:
+    """losses.py:48-99: U / kT per sample [B]; padding atoms are dropped before the energy call; contiguous segments of one
+    protein are evaluated as one batch."""
+    def single(coord, protein, mask):
+        pot = provider.get_potential_energy_module(protein)
+        return pot(coord[~mask, :].view(coord.size(0), -1, 3)).squeeze(-1) / provider.kbT
+
+    if segments is not None:
+        parts = [single(coords[segments[i]:segments[i + 1]], pdb_names[segments[i]], masked_elements[segments[i]:segments[i + 1]])
+                 for i in range(len(segments) - 1)]
+    else:
+        parts = [single(c[None], n, m[None]) for n, c, m in zip(pdb_names, coords, masked_elements)]
+    return torch.hstack(parts)
+
+
+def compute_energy(coords, velocs, pdb_names, masked_elements, provider: EnergyProvider, random_velocs: bool = False,
+                   masses: Optional[Tensor] = None, segments: Optional[Sequence[int]] = None) -> Tuple[Tensor, Tuple[Tensor, Tensor]]:
+    """losses.py:101-149: (kinetic + potential) / kT and its two parts, [B] each."""
+    if masses is None and not random_velocs:
+        ms = [provider.get_masses(n).to(coords.device) for n in pdb_names]
+        width = masked_elements.size(-1)
+        masses = torch.stack([torch.nn.functional.pad(m, (0, width - m.size(0)), "constant", 0) for m in ms])
+    kinetic = compute_kinetic_energy(velocs, masses, provider.kbT, random_velocs=random_velocs)
+    potential = compute_potential_energy(coords, pdb_names, masked_elements, provider, segments=segments)
+    return kinetic + potential, (potential, kinetic)
+
+
+class EnergyLoss:
+    """losses.py:558-583: configuration of the energy loss."""
+
+    def __init__(self, openmm_provider: EnergyProvider, random_velocs: bool = True, num_samples: int = 1):
+        self.openmm_provider, self.random_velocs, self.num_samples = openmm_provider, random_velocs, num_samples
+
+
+def energy_loss(loss: EnergyLoss, model, batch, device: Optional[Union[str, torch.device]] = None, logger=None) -> Tensor:
+    """`get_loss(EnergyLoss, ...)`, losses.py:586-664: mean over the batch of (E(y)/kT + log p(y|x)) / n_atoms for
+    y ~ p(.|x), averaged over `num_samples` draws.  `batch` carries atom_types / atom_coords / atom_velocs / adj_list /
+    edge_batch_idx / masked_elements / names / segments like `DenseMolDynBatch`."""
+    to = (lambda t: t.to(device, non_blocking=True)) if device is not None else (lambda t: t)
+    x_coords, atom_types, masked_elements = to(batch.atom_coords), to(batch.atom_types), to(batch.masked_elements)
+    adj_list, edge_batch_idx = to(batch.adj_list), to(batch.edge_batch_idx)
+    x_velocs = torch.randn_like(x_coords).contiguous() if loss.random_velocs else to(batch.atom_velocs)
+    num_atoms = (~masked_elements).sum(dim=-1)
+    total = torch.tensor(0.0, device=x_coords.device)
+    for _ in range(loss.num_samples):
+        y_coords, y_velocs, logp_xy = model.conditional_sample_with_logp(
+            atom_types=atom_types, x_coords=x_coords, x_velocs=x_velocs, adj_list=adj_list, edge_batch_idx=edge_batch_idx,
+            masked_elements=masked_elements, num_samples=1, logger=logger)
+        y_coords, y_velocs = y_coords.squeeze(0), y_velocs.squeeze(0)
+        energy, _ = compute_energy(y_coords, y_velocs, batch.names, masked_elements, loss.openmm_provider,
+                                   random_velocs=loss.random_velocs, segments=getattr(batch, "segments", None))
+        total = total + ((energy + logp_xy.reshape(energy.shape)) / num_atoms).mean()
+    return total / loss.num_samples
