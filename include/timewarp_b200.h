@@ -174,6 +174,18 @@ int tw_flow_log_likelihood_backward(const tw_flow_config* cfg, const void* const
                                     int64_t V, const float* grad_log_prob, const void* packed_weights, void* tape,
                                     size_t tape_bytes, void* workspace, size_t workspace_bytes, void* stream);
 
+/* tw_flow_log_likelihood_backward that also differentiates w.r.t. the INPUTS (AcceptanceLoss, losses.py:274-555: the
+ * reverse-move density is conditioned on the proposal).  Optional outputs [B,V,3] (NULL = not wanted; the first two come as
+ * a pair): out_grad_xc = d/d(CENTRED conditioning coordinates) through the conditioner inputs and the attention scores (the
+ * caller applies the centring  x - mean_unmasked(x)  chain rule and, with TW_FLOW_DISPLACEMENT_TARGET, subtracts
+ * out_grad_z0_coords); out_grad_x_velocs; out_grad_z0_coords / out_grad_z0_velocs = d/d(flow input), i.e. d/dy_coords
+ * (displacement or absolute) and d/dy_velocs. */
+int tw_flow_log_likelihood_backward_inputs(const tw_flow_config* cfg, const void* const* params, void* const* grads,
+                                           const int64_t* atom_types, const float* x_velocs, const uint8_t* mask, int64_t B, int64_t V,
+                                           const float* grad_log_prob, const void* packed_weights, void* tape, size_t tape_bytes,
+                                           void* workspace, size_t workspace_bytes, float* out_grad_xc, float* out_grad_x_velocs,
+                                           float* out_grad_z0_coords, float* out_grad_z0_velocs, void* stream);
+
 /* Sampling direction under autograd (conditional_sample_with_logp inside the energy-based losses, losses.py:396-664; the
  * reference differentiates flow.py:242-336 with torch autograd).  tw_flow_sample_train = tw_flow_sample for S = 1 with a tape
  * (same tape / workspace sizes as tw_flow_train_bytes): z_coords / z_velocs [B,V,3] are the scaled latent draws;

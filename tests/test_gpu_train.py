@@ -388,3 +388,106 @@ def test_energy_loss_trains_through_the_sampler():
     with torch.no_grad():
         after = losses.energy_loss(spec, m, Batch, device="cuda")
     assert float(after) < float(loss.detach()), (float(loss.detach()), float(after))
+
+
+def test_density_backward_input_gradients_match_oracle_autograd():
+    """log_likelihood differentiated w.r.t. its INPUTS (conditioning coordinates / velocities through the conditioner inputs,
+    the attention scores and the centring; target through the flow input), against the oracle's fp64 autograd on a ragged batch."""
+    torch.manual_seed(17)
+    B, V = 4, 26
+    lengths = [26, 19, 26, 8]
+    mask = torch.zeros(B, V, dtype=torch.bool)
+    for b, n in enumerate(lengths):
+        mask[b, n:] = True
+    keep = (~mask)[:, :, None]
+    x = 0.3 * torch.randn(B, V, 3) * keep
+    y = (x + 0.02 * torch.randn(B, V, 3)) * keep
+    xv, yv = torch.randn(B, V, 3) * keep, torch.randn(B, V, 3) * keep
+    at = torch.randint(0, 5, (B, V)) * (~mask)
+    w = torch.randn(B)
+    m, sd = build_model(FULL_O, "bf16x3", 6)
+    m.train()
+    leaves = [t.clone().cuda().requires_grad_(True) for t in (x, xv, y, yv)]
+    ll = m.log_likelihood(atom_types=at.cuda(), x_coords=leaves[0], x_velocs=leaves[1], y_coords=leaves[2], y_velocs=leaves[3],
+                          adj_list=EMPTY_ADJ.cuda(), edge_batch_idx=EMPTY_EBI.cuda(), masked_elements=mask.cuda())
+    (ll * w.cuda()).sum().backward()
+    ref_leaves = [t.double().clone().requires_grad_(True) for t in (x, xv, y, yv)]
+    rll = fo.log_likelihood(fo.to_dtype(sd, torch.float64), FULL_O, at, ref_leaves[0], ref_leaves[1], ref_leaves[2], ref_leaves[3], mask,
+                            distance_mode="direct")
+    ref = torch.autograd.grad((rll * w.double()).sum(), ref_leaves)
+    torch.testing.assert_close(ll.detach().cpu().double(), rll.detach(), rtol=1e-5, atol=1e-3)
+    for name, got, want in zip(("x_coords", "x_velocs", "y_coords", "y_velocs"), leaves, ref):
+        rows = keep.expand_as(want)
+        err = float((got.grad.cpu().double() - want)[rows].norm() / want[rows].norm())
+        assert err < GRAD_RTOL, (name, err)
+        assert float(got.grad.cpu()[~rows].abs().max()) < 1e-4 * float(want.abs().max()), name  # padding atoms: no gradient
+
+
+def test_acceptance_loss_matches_hand_composition():
+    """AcceptanceLoss (losses.py:358-555): value against the hand-composed (E(y) - E(x))/kT + log p(y|x) - log p(x|y) with the
+    fp64 energy oracle and inference-path densities on the same draws; gradients finite on every parameter; an Adam step on it
+    raises the (log) acceptance.  clamp / beta / high-energy filter variants on the same draws."""
+    from oracle import energy_oracle as eo
+    from timewarp_b200 import losses
+    from timewarp_b200.energy import PeptidePotentialEnergy
+    from timewarp_b200.forcefield import amber_like_system
+    from timewarp_b200.peptides import alanine_dipeptide
+    import bench
+
+    pep = alanine_dipeptide()
+    sysd = amber_like_system(pep)
+    energy = PeptidePotentialEnergy(sysd)
+    provider = losses.EnergyProvider({"ad": energy}, {"ad": torch.tensor(pep.masses, dtype=torch.float32)})
+    B, V = 6, pep.num_atoms
+    g = torch.Generator().manual_seed(4)
+
+    class Batch:
+        atom_coords = torch.tensor(pep.coords_nm, dtype=torch.float32)[None] + 0.005 * torch.randn(B, V, 3, generator=g)
+        atom_velocs = torch.zeros(B, V, 3)
+        atom_types = torch.tensor(pep.atom_types)[None].repeat(B, 1)
+        masked_elements = torch.zeros(B, V, dtype=torch.bool)
+        adj_list, edge_batch_idx = EMPTY_ADJ, EMPTY_EBI
+        names, segments = ["ad"] * B, [0, B]
+
+    m, _ = build_model(FULL_O, "bf16x3", 0)
+    m.load_state_dict({k: v.cuda() for k, v in bench.bench_state_dict(m, "proposal").items()})
+    m.train()
+    spec = losses.AcceptanceLoss(provider, random_velocs=True, num_samples=1)
+    torch.manual_seed(33)
+    loss = losses.acceptance_loss(spec, m, Batch, device="cuda")
+    m.zero_grad(set_to_none=True)
+    loss.backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in m.parameters())
+    # hand composition on the same draws (inference kernels + fp64 energy oracle)
+    torch.manual_seed(33)
+    xc = Batch.atom_coords.cuda()
+    xv = torch.randn_like(xc)
+    kw = dict(atom_types=Batch.atom_types.cuda(), adj_list=EMPTY_ADJ.cuda(), edge_batch_idx=EMPTY_EBI.cuda(), masked_elements=Batch.masked_elements.cuda())
+    with torch.no_grad():
+        yc, yv, lp = m.conditional_sample_with_logp(x_coords=xc, x_velocs=xv, num_samples=1, **kw)
+        p_yx = m.log_likelihood(x_coords=yc[0], x_velocs=yv[0], y_coords=xc, y_velocs=xv, **kw)
+    s32 = sysd.as_float32()
+    de = (eo.potential_energy(s32, yc[0].cpu().numpy().astype(np.float64)) - eo.potential_energy(s32, xc.cpu().numpy().astype(np.float64))) / energy.kbT
+    dk = (0.5 * (yv[0].double() ** 2).sum((-1, -2)) - 0.5 * (xv.double() ** 2).sum((-1, -2))).cpu().numpy()
+    nla = de + dk + (lp[0] - p_yx).double().cpu().numpy()
+    want = float((nla / V).mean())
+    assert abs(float(loss.detach()) - want) < 5e-4 * max(1.0, abs(want)), (float(loss.detach()), want)
+    # variants on the same draws
+    for kwargs, expect in ((dict(clamp=True), float((np.minimum(nla, 0.0) / V).mean())),
+                           (dict(beta=0.5), float(((nla + 0.5 * lp[0].double().cpu().numpy()) / V).mean()))):
+        torch.manual_seed(33)
+        with torch.no_grad():
+            v = float(losses.acceptance_loss(losses.AcceptanceLoss(provider, random_velocs=True, **kwargs), m, Batch, device="cuda"))
+        assert abs(v - expect) < 5e-4 * max(1.0, abs(expect)), (kwargs, v, expect)
+    torch.manual_seed(33)
+    with torch.no_grad():  # every proposal flagged: the reference's constant 10000 (losses.py:535-537)
+        spec_bad = losses.AcceptanceLoss(provider, high_energy_threshold=1e9, chirality_checker=lambda b, y, mk: torch.ones(len(y), dtype=torch.bool, device=y.device))
+        assert float(losses.acceptance_loss(spec_bad, m, Batch, device="cuda")) == 10000.0
+    with pytest.raises(ValueError):
+        losses.AcceptanceLoss(provider, high_energy_threshold=300.0)
+    # one Adam step on the loss lowers it on the same draws
+    torch.optim.Adam(m.parameters(), lr=1e-5).step()
+    torch.manual_seed(33)
+    with torch.no_grad():
+        after = float(losses.acceptance_loss(spec, m, Batch, device="cuda"))
+    assert after < float(loss.detach()), (float(loss.detach()), after)

@@ -88,6 +88,8 @@ _SIGNATURES = {
     "tw_flow_train_bytes": (C.c_int, [C.POINTER(FlowConfig), _I64, _I64, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     "tw_flow_log_likelihood_train": (C.c_int, [C.POINTER(FlowConfig), _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I32, _P, _P, _P, C.c_size_t, _P]),
     "tw_flow_log_likelihood_backward": (C.c_int, [C.POINTER(FlowConfig), _P, _P, _P, _P, _P, _I64, _I64, _P, _P, _P, C.c_size_t, _P, C.c_size_t, _P]),
+    "tw_flow_log_likelihood_backward_inputs": (C.c_int, [C.POINTER(FlowConfig), _P, _P, _P, _P, _P, _I64, _I64, _P, _P, _P, C.c_size_t, _P,
+                                                         C.c_size_t, _P, _P, _P, _P, _P]),
     "tw_flow_sample_train": (C.c_int, [C.POINTER(FlowConfig), _P, _P, _P, _P, _P, _I64, _I64, _I32, _P, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
     "tw_flow_sample_backward": (C.c_int, [C.POINTER(FlowConfig), _P, _P, _P, _P, _P, _I64, _I64, _P, _P, _P, _P, _P, C.c_size_t, _P, C.c_size_t,
                                           _P, _P, _P]),

@@ -520,7 +520,8 @@ __global__ void __launch_bounds__(256) k_features_img(const float* __restrict__ 
 // Gradient of the conditioner input [M,64] (both networks) -> flow state (columns E+6..E+8) and atom embedding
 __global__ void __launch_bounds__(256) k_du_scatter(const float* __restrict__ du0, const float* __restrict__ du1,
                                                     const int64_t* __restrict__ atom_types, int64_t M, int E, int n_types,
-                                                    float* __restrict__ dz_other, float* __restrict__ dembed) {
+                                                    float* __restrict__ dz_other, float* __restrict__ dembed,
+                                                    float* __restrict__ dxc, float* __restrict__ dxv) {
   extern __shared__ float acc[];  // [n_types * E]
   for (int i = threadIdx.x; i < n_types * E; i += blockDim.x) acc[i] = 0.f;
   __syncthreads();
@@ -536,6 +537,10 @@ __global__ void __launch_bounds__(256) k_du_scatter(const float* __restrict__ du
       atomicAdd(&acc[t * E + e], g);
     } else if (e >= E + 6 && e < E + 9) {
       dz_other[m * 3 + (e - E - 6)] += g;
+    } else if (dxc && e < E + 3) {  // conditioning coordinates / velocities as conditioner inputs (AcceptanceLoss)
+      dxc[m * 3 + (e - E)] += g;
+    } else if (dxv && e >= E + 3 && e < E + 6) {
+      dxv[m * 3 + (e - E - 3)] += g;
     }
   }
   __syncthreads();
@@ -720,6 +725,54 @@ __global__ void __launch_bounds__(256) k_ls_grad(const float* __restrict__ xc, c
   }
 }
 
+// Gradient of the row-normalised Gaussian scores w.r.t. the (centred) conditioning coordinates: with gK_ij = dL/dK_ij =
+// (S_ij - sum_j' S_ij' A_ij') / (s_i + eps) and K_ij = exp(-|x_i - x_j|^2 / l^2):  dL/dx_i += c_ij (x_i - x_j), dL/dx_j -= c_ij
+// (x_i - x_j), c_ij = gK_ij K_ij (-2 / l^2).  One block per state; accumulators in shared memory.
+__global__ void __launch_bounds__(256) k_score_coord_grad(const float* __restrict__ xc, const uint8_t* __restrict__ mask,
+                                                          const float* __restrict__ ls, const float* __restrict__ S, int V, int H,
+                                                          float* __restrict__ dxc) {
+  extern __shared__ float acc[];  // [V*3]
+  const int64_t b = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float* xb = xc + b * V * 3;
+  const uint8_t* mb = mask + b * V;
+  for (int i = threadIdx.x; i < V * 3; i += blockDim.x) acc[i] = 0.f;
+  __syncthreads();
+  for (int h = 0; h < H; h++) {
+    const float l = ls[h], inv_l2 = 1.f / (l * l);
+    const float* Sh = S + ((size_t)b * H + h) * V * V;
+    for (int i = warp; i < V; i += 8) {
+      const float xi = xb[i * 3], yi = xb[i * 3 + 1], zi = xb[i * 3 + 2];
+      float s = 0.f, dot = 0.f;
+      for (int j = lane; j < V; j += 32) {
+        if (mb[j]) continue;
+        const float dx = xi - xb[j * 3], dy = yi - xb[j * 3 + 1], dz = zi - xb[j * 3 + 2];
+        const float k = expf(-(dx * dx + dy * dy + dz * dz) * inv_l2);
+        s += k, dot = fmaf(Sh[(size_t)i * V + j], k, dot);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o), dot += __shfl_xor_sync(0xffffffffu, dot, o);
+      const float inv_den = 1.f / (s + 1e-5f);
+      dot *= inv_den;  // sum_j S_ij A_ij
+      float gx = 0.f, gy = 0.f, gz = 0.f;
+      for (int j = lane; j < V; j += 32) {
+        if (mb[j]) continue;
+        const float dx = xi - xb[j * 3], dy = yi - xb[j * 3 + 1], dz = zi - xb[j * 3 + 2];
+        const float k = expf(-(dx * dx + dy * dy + dz * dz) * inv_l2);
+        const float cij = (Sh[(size_t)i * V + j] - dot) * inv_den * k * (-2.f * inv_l2);
+        gx = fmaf(cij, dx, gx), gy = fmaf(cij, dy, gy), gz = fmaf(cij, dz, gz);
+        atomicAdd(&acc[j * 3], -cij * dx), atomicAdd(&acc[j * 3 + 1], -cij * dy), atomicAdd(&acc[j * 3 + 2], -cij * dz);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1)
+        gx += __shfl_xor_sync(0xffffffffu, gx, o), gy += __shfl_xor_sync(0xffffffffu, gy, o), gz += __shfl_xor_sync(0xffffffffu, gz, o);
+      if (lane == 0) atomicAdd(&acc[i * 3], gx), atomicAdd(&acc[i * 3 + 1], gy), atomicAdd(&acc[i * 3 + 2], gz);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < V * 3; i += blockDim.x) dxc[b * V * 3 + i] += acc[i];
+}
+
 // ============================================================================================
 // tape layout
 struct NetTape {
@@ -805,6 +858,8 @@ struct BwdBuffers {
   float* du[2];          // [M,64]
   float* dwc[2];         // [128, H*128]
   float* sgrad;          // [B,H,V,V] gradient w.r.t. the attention scores, summed over layers and networks (learnable lengthscales)
+  float* dxc;            // [M,3] gradient w.r.t. the centred conditioning coordinates (conditioner inputs + scores)
+  float* dxv;            // [M,3] gradient w.r.t. the conditioning velocities
 };
 
 static size_t carve_bwd(const tw_flow_config* c, int64_t B, int V, void* base, size_t cap, BwdBuffers* out) {
@@ -836,6 +891,8 @@ static size_t carve_bwd(const tw_flow_config* c, int64_t B, int V, void* base, s
   }
   b.img_u = take_img(1);
   b.sgrad = ar.take<float>((size_t)B * H * V * V);
+  b.dxc = ar.take<float>(M * 3);
+  b.dxv = ar.take<float>(M * 3);
   if (out) *out = b;
   return align_up(ar.off, 1024);
 }
@@ -870,6 +927,7 @@ struct BwdCtx {
   int V;
   int tiles;  // token tiles
   float* dls;  // [H] gradient w.r.t. the lengthscales of the pass (NULL: not requested)
+  bool want_inputs;  // gradients w.r.t. the conditioning state / the target requested
   cudaStream_t st;
 };
 
@@ -1005,7 +1063,7 @@ static int conditioner_bwd(BwdCtx& x, int k, float* dz_other, const float* z_oth
       TW_LAUNCH_CHECK();
     }
     // attention: r1 = x + sum_h W_c,h (A_h x)
-    if (x.dls) {  // S_h += (dr W_c,h) x^T; the [M, F] scratch of the FFN block is free here
+    if (x.dls || x.want_inputs) {  // S_h += (dr W_c,h) x^T; the [M, F] scratch of the FFN block is free here
       GemmArgs q = gemm_base(x, GEMM_NN);  // Q [M, H*128] = dr W_c
       for (int s = 0; s < 2; s++) q.A[s] = plain_img(b.img_d[s], 2), q.B[s] = plain_img(eb[s] + L.enc_wc, H * 2), q.C[s] = b.wide0[s];
       q.ldc = H * 128, q.rows = (int)x.M, q.cols = H * 128, q.tiles_m = x.tiles, q.tiles_n = H, q.KB = 2;
@@ -1079,7 +1137,8 @@ static int conditioner_bwd(BwdCtx& x, int k, float* dz_other, const float* z_oth
     e.bn = 64, e.ldc = 64, e.rows = (int)x.M, e.cols = 64, e.tiles_m = x.tiles, e.tiles_n = 1, e.KB = hid / 64;
     TW_TRY(launch_gemm(c, e, x.st));
     k_du_scatter<<<x.tiles, 256, c->num_atom_types * E * sizeof(float), x.st>>>(b.du[0], b.du[1], x.atom_types, x.M, E, c->num_atom_types,
-                                                                             dz_other, x.gv.embed());
+                                                                             dz_other, x.gv.embed(), x.want_inputs ? b.dxc : nullptr,
+                                                                             x.want_inputs ? b.dxv : nullptr);
     TW_LAUNCH_CHECK();
   }
   return TW_OK;
@@ -1283,7 +1342,11 @@ static int begin_backward(BwdCtx& x, const tw_flow_config* cfg, const void* cons
   x.st = (cudaStream_t)stream;
   // lengthscale gradient (learnable_kernel): requested by a non-NULL entry for the lengthscales of chain[0].scale.layer[0]
   x.dls = x.gv.enc(0, 0, 0, 1);
-  if (x.dls) {
+  if (x.want_inputs) {
+    TW_CUDA(cudaMemsetAsync(x.b.dxc, 0, (size_t)B * V * 3 * sizeof(float), x.st));
+    TW_CUDA(cudaMemsetAsync(x.b.dxv, 0, (size_t)B * V * 3 * sizeof(float), x.st));
+  }
+  if (x.dls || x.want_inputs) {
     TW_CHECK_ARG(cfg->num_heads * 128 <= (cfg->dim_feedforward > 256 ? cfg->dim_feedforward : 256),
                  "lengthscale gradient: H * 128 exceeds the [M, dim_feedforward] scratch");
     static bool attr_done = false;
@@ -1297,6 +1360,11 @@ static int begin_backward(BwdCtx& x, const tw_flow_config* cfg, const void* cons
 }
 
 static int finish_backward(BwdCtx& x) {
+  if (x.want_inputs) {
+    k_score_coord_grad<<<(unsigned)x.B, 256, (size_t)x.V * 3 * sizeof(float), x.st>>>(x.tp.xc, x.mask, x.pv.enc(0, 0, 0, 1), x.b.sgrad, x.V,
+                                                                                   x.c->num_heads, x.b.dxc);
+    TW_LAUNCH_CHECK();
+  }
   if (x.dls) {
     k_ls_grad<<<(unsigned)x.B, 256, 0, x.st>>>(x.tp.xc, x.mask, x.pv.enc(0, 0, 0, 1), x.b.sgrad, x.V, x.c->num_heads, x.dls);
     TW_LAUNCH_CHECK();
@@ -1308,10 +1376,22 @@ int tw_flow_log_likelihood_backward(const tw_flow_config* cfg, const void* const
                                     const int64_t* atom_types, const float* x_velocs, const uint8_t* mask, int64_t B, int64_t V,
                                     const float* grad_log_prob, const void* packed_weights, void* tape, size_t tape_bytes,
                                     void* workspace, size_t workspace_bytes, void* stream) {
+  return tw_flow_log_likelihood_backward_inputs(cfg, params, grads, atom_types, x_velocs, mask, B, V, grad_log_prob, packed_weights, tape,
+                                                tape_bytes, workspace, workspace_bytes, nullptr, nullptr, nullptr, nullptr, stream);
+}
+
+int tw_flow_log_likelihood_backward_inputs(const tw_flow_config* cfg, const void* const* params, void* const* grads,
+                                           const int64_t* atom_types, const float* x_velocs, const uint8_t* mask, int64_t B, int64_t V,
+                                           const float* grad_log_prob, const void* packed_weights, void* tape, size_t tape_bytes,
+                                           void* workspace, size_t workspace_bytes, float* out_grad_xc, float* out_grad_x_velocs,
+                                           float* out_grad_z0_coords, float* out_grad_z0_velocs, void* stream) {
   TW_TRY(check_train(cfg, params, B, V));
   if (B == 0) return TW_OK;
   TW_CHECK_ARG(grad_log_prob, "NULL pointer");
+  const bool want_inputs = out_grad_xc || out_grad_x_velocs;
+  TW_CHECK_ARG(!want_inputs || (out_grad_xc && out_grad_x_velocs), "conditioning gradients come as a pair (coords, velocs)");
   BwdCtx x{};
+  x.want_inputs = want_inputs;
   TW_TRY(begin_backward(x, cfg, params, grads, atom_types, x_velocs, mask, B, V, packed_weights, tape, tape_bytes, workspace, workspace_bytes, stream));
   const int L = cfg->num_coupling_layers;
   k_prior_bwd<<<(unsigned)B, 128, 0, x.st>>>(x.tp.z[L][0], x.tp.z[L][1], mask, x.pv.log_scale_c(), x.pv.log_scale_v(), grad_log_prob, (int)V,
@@ -1324,7 +1404,15 @@ int tw_flow_log_likelihood_backward(const tw_flow_config* cfg, const void* const
     TW_LAUNCH_CHECK();
     TW_TRY(conditioner_bwd(x, k, x.b.dz[oth], x.tp.z[k][oth]));
   }
-  return finish_backward(x);
+  TW_TRY(finish_backward(x));
+  const size_t bytes = (size_t)B * V * 3 * sizeof(float);
+  if (want_inputs) {
+    TW_CUDA(cudaMemcpyAsync(out_grad_xc, x.b.dxc, bytes, cudaMemcpyDeviceToDevice, x.st));
+    TW_CUDA(cudaMemcpyAsync(out_grad_x_velocs, x.b.dxv, bytes, cudaMemcpyDeviceToDevice, x.st));
+  }
+  if (out_grad_z0_coords) TW_CUDA(cudaMemcpyAsync(out_grad_z0_coords, x.b.dz[0], bytes, cudaMemcpyDeviceToDevice, x.st));
+  if (out_grad_z0_velocs) TW_CUDA(cudaMemcpyAsync(out_grad_z0_velocs, x.b.dz[1], bytes, cudaMemcpyDeviceToDevice, x.st));
+  return TW_OK;
 }
 
 // Backward of tw_flow_sample_train: given d/dy_coords, d/dy_velocs [B,V,3] and d/d(delta) [B], accumulates the parameter

@@ -105,20 +105,41 @@ class _LogLikelihoodFn(torch.autograd.Function):
         table = model._param_table(dev)
         ws = torch.empty(ws_b + 1024, dtype=torch.uint8, device=dev)
         g_in = grad_out.to(torch.float32).contiguous()
+        # gradients w.r.t. the inputs (x_coords, x_velocs, y_coords, y_velocs = inputs 2..5): AcceptanceLoss conditions the
+        # reverse-move density on the proposal (losses.py:452-462)
+        want_x = ctx.needs_input_grad[2] or ctx.needs_input_grad[3]
+        want_y = ctx.needs_input_grad[4] or ctx.needs_input_grad[5] or (want_x and model.use_displacement_as_target)
+        new3 = lambda: torch.empty(B, V, 3, dtype=torch.float32, device=dev)  # noqa: E731
+        dxc, dxv = (new3(), new3()) if want_x else (None, None)
+        dz0c, dz0v = (new3(), new3()) if want_y else (None, None)
         _lib.check(
-            lib.tw_flow_log_likelihood_backward(
+            lib.tw_flow_log_likelihood_backward_inputs(
                 C.byref(model._cfg), table, gtable, _lib.ptr(atom_types), _lib.ptr(x_velocs), _lib.ptr(mask_u8), B, V,
-                _lib.ptr(g_in), model._packed[1], _aligned(ctx.tape), tape_b, _aligned(ws), ws_b, model._stream(dev),
+                _lib.ptr(g_in), model._packed[1], _aligned(ctx.tape), tape_b, _aligned(ws), ws_b, _lib.ptr(dxc), _lib.ptr(dxv),
+                _lib.ptr(dz0c), _lib.ptr(dz0v), model._stream(dev),
             ),
-            "tw_flow_log_likelihood_backward",
+            "tw_flow_log_likelihood_backward_inputs",
         )  # fmt: skip
         ctx.tape = None
+        g_x = g_xv = g_y = g_yv = None
+        if want_x:
+            keep = (mask_u8 == 0)[:, :, None].to(torch.float32)
+            # x_c = x - mean over the unmasked atoms (molecule_utils.py:15-29): every atom's centred coordinate depends on them
+            g_x = dxc - keep * (dxc.sum(1, keepdim=True) / keep.sum(1, keepdim=True).clamp_min(1.0))
+            if model.use_displacement_as_target:  # the flow input is y - x (flow.py:148-149)
+                g_x = g_x - dz0c
+            g_xv = None if model.ignore_conditional_velocity else dxv
+        if ctx.needs_input_grad[4]:
+            g_y = dz0c
+        if ctx.needs_input_grad[5]:
+            g_yv = dz0v
+        head = (None, None, g_x if ctx.needs_input_grad[2] else None, g_xv if ctx.needs_input_grad[3] else None, g_y, g_yv, None)
         if ctx.n_extra:
             g_log_ls = None
             if ls_grad:  # d/d(log l) = l * d/dl, in place inside the flat buffer (data-parallel training all-reduces it)
                 g_log_ls = views[ls_slot].mul_(tensors[ls_slot])
-            return (None,) * 7 + tuple(grads) + (g_log_ls,)
-        return (None,) * 7 + tuple(grads)
+            return head + tuple(grads) + (g_log_ls,)
+        return head + tuple(grads)
 
 
 class _SampleFn(torch.autograd.Function):

@@ -3,8 +3,8 @@
 (tw_flow_sample_train / tw_flow_sample_backward) and the potential energy returns -force as its gradient
 (tw_peptide_energy), so no OpenMM call and no eager PyTorch network evaluation sits in the training step.
 
-`AcceptanceLoss` (losses.py:274-555) additionally differentiates the reverse-move density w.r.t. its CONDITIONING state
-(the proposal); that gradient (through the attention scores and the conditioner inputs) is not built."""
+`AcceptanceLoss` (losses.py:358-555) additionally differentiates the reverse-move density w.r.t. its CONDITIONING state (the
+proposal): tw_flow_log_likelihood_backward_inputs returns that gradient (conditioner inputs + attention scores + centring)."""
 from __future__ import annotations
 
 from typing import Callable, Dict, Optional, Sequence, Tuple, Union
@@ -90,4 +90,62 @@ def energy_loss(loss: EnergyLoss, model, batch, device: Optional[Union[str, torc
         energy, _ = compute_energy(y_coords, y_velocs, batch.names, masked_elements, loss.openmm_provider,
                                    random_velocs=loss.random_velocs, segments=getattr(batch, "segments", None))
         total = total + ((energy + logp_xy.reshape(energy.shape)) / num_atoms).mean()
+    return total / loss.num_samples
+
+
+class AcceptanceLoss:
+    """losses.py:358-393: configuration of the acceptance loss.  `chirality_checker(batch, y_coords, masked_elements) -> bool[B]`
+    replaces the reference's `CiralityChecker(openmm_provider.pdb_dirs)` (it reads PDB files; here any callable, e.g. built on
+    timewarp_b200.chirality.check_symmetry_change); required when `high_energy_threshold != -1`."""
+
+    def __init__(self, openmm_provider: EnergyProvider, random_velocs: bool = True, beta: float = 0.0, clamp: bool = False,
+                 num_samples: int = 1, high_energy_threshold: float = -1, chirality_checker: Optional[Callable] = None):
+        self.openmm_provider, self.random_velocs, self.beta, self.clamp = openmm_provider, random_velocs, beta, clamp
+        self.num_samples, self.high_energy_threshold, self.chirality_checker = num_samples, high_energy_threshold, chirality_checker
+        if high_energy_threshold != -1 and chirality_checker is None:
+            raise ValueError("high_energy_threshold needs a chirality_checker (losses.py:391-393)")
+
+
+def acceptance_loss(loss: AcceptanceLoss, model, batch, device: Optional[Union[str, torch.device]] = None, logger=None) -> Tensor:
+    """`get_loss(AcceptanceLoss, ...)`, losses.py:396-555: the negative log MH acceptance of a proposal y ~ p(.|x),
+        (E(y) - E(x)) / kT + log p(y|x) - log p(x|y)      [+ beta * log p(y|x)],
+    per atom, averaged over the batch and `num_samples` draws; optionally clamped at 0 (= min(1, acceptance)) and with
+    high-energy / chirality-flipping proposals dropped."""
+    to = (lambda t: t.to(device, non_blocking=True)) if device is not None else (lambda t: t)
+    x_coords, atom_types, masked_elements = to(batch.atom_coords), to(batch.atom_types), to(batch.masked_elements)
+    adj_list, edge_batch_idx = to(batch.adj_list), to(batch.edge_batch_idx)
+    random_velocs = loss.random_velocs
+    x_velocs = torch.randn_like(x_coords).contiguous() if random_velocs else to(batch.atom_velocs)
+    num_atoms_all = (~masked_elements).sum(dim=-1)
+    segments = getattr(batch, "segments", None)
+    masses = None
+    if not random_velocs:  # :464-471
+        ms = [loss.openmm_provider.get_masses(n).to(x_coords.device) for n in batch.names]
+        masses = torch.stack([torch.nn.functional.pad(m, (0, atom_types.size(-1) - m.size(0)), "constant", 0) for m in ms])
+    total = torch.tensor(0.0, device=x_coords.device)
+    for _ in range(loss.num_samples):
+        num_atoms = num_atoms_all
+        y_coords, y_velocs, logp_xy = model.conditional_sample_with_logp(
+            atom_types=atom_types, x_coords=x_coords, x_velocs=x_velocs, adj_list=adj_list, edge_batch_idx=edge_batch_idx,
+            masked_elements=masked_elements, num_samples=1, logger=logger)
+        y_coords, y_velocs, logp_xy = y_coords.squeeze(0), y_velocs.squeeze(0), logp_xy.squeeze(0)
+        logp_yx = model.log_likelihood(
+            atom_types=atom_types, x_coords=y_coords, x_velocs=y_velocs if random_velocs else -y_velocs, y_coords=x_coords,
+            y_velocs=x_velocs if random_velocs else -x_velocs, adj_list=adj_list, edge_batch_idx=edge_batch_idx,
+            masked_elements=masked_elements, logger=logger)  # :452-462
+        energy_x, _ = compute_energy(x_coords, x_velocs, batch.names, masked_elements, loss.openmm_provider, random_velocs=random_velocs,
+                                     masses=masses, segments=segments)
+        energy_y, _ = compute_energy(y_coords, y_velocs, batch.names, masked_elements, loss.openmm_provider, random_velocs=random_velocs,
+                                     masses=masses, segments=segments)
+        energy_delta = energy_y - energy_x
+        neg_log_acceptance = energy_delta + logp_xy - logp_yx  # :497
+        per_sample = (torch.clamp(neg_log_acceptance, max=0) if loss.clamp else neg_log_acceptance) + loss.beta * logp_xy  # :513-518
+        if loss.high_energy_threshold != -1:  # :522-537
+            changes = loss.chirality_checker(batch, y_coords, masked_elements)
+            energy_delta = energy_delta + 100000.0 * changes.to(energy_delta.dtype)
+            good = energy_delta < loss.high_energy_threshold
+            per_sample, num_atoms = per_sample[good.reshape(per_sample.shape)], num_atoms[good]
+            if len(num_atoms) == 0:
+                per_sample, num_atoms = torch.tensor(10000.0, device=x_coords.device), torch.tensor(1.0, device=x_coords.device)
+        total = total + (per_sample / num_atoms).mean()
     return total / loss.num_samples
