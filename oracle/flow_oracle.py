@@ -100,7 +100,7 @@ def kernel_attention_scores(
     if distance_mode == "cdist":
         # literal reference call (kernel_attention.py:98-102)
         d = torch.cdist(positions, positions, compute_mode="use_mm_for_euclid_dist_if_necessary")
-    elif distance_mode == "direct":
+    elif distance_mode in ("direct", "direct_sq"):
         diff = positions[:, :, None, :] - positions[:, None, :, :]
         d = torch.sqrt((diff * diff).sum(-1))
     else:
@@ -108,6 +108,10 @@ def kernel_attention_scores(
     scaled = d.unsqueeze(-3) / lengthscales[None, :, None, None]  # :105-110
     if cheb_coeffs is not None:
         w = chebyshev_basis(scaled, cheb_coeffs, force_asymptotic_zero)
+    elif distance_mode == "direct_sq":
+        # same value without the square root: torch's sqrt has an infinite derivative at the zero self-distances, which turns
+        # the gradient w.r.t. the positions into NaN; used by the tests that differentiate w.r.t. the conditioning state
+        w = torch.exp(-((diff * diff).sum(-1).unsqueeze(-3) / lengthscales[None, :, None, None] ** 2))
     else:
         w = torch.exp(-(scaled**2))  # gaussian_basis_function :9-10
     w = w.masked_fill(masked_elements[:, None, None, :], 0.0)  # :114
