@@ -81,3 +81,49 @@ def test_simulation_has_no_cpu_fallback():
         md.openmm_step(sim, x)
     v = sim.velocities_to_temperature(x)  # host-side draw: N(0, kT/m) per component
     assert v.shape == x.shape and np.isfinite(v.numpy()).all()
+
+
+def test_loss_wrapper_and_dispatch():
+    """LossWrapper / get_loss / wrap_or_replace_loss / unwrap_loss_wrapper (losses.py:215-303) and the NLL glue (losses.py:321-356)
+    with a stand-in model that records what it is called with."""
+    calls = []
+
+    class Model(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.w = torch.nn.Parameter(torch.zeros(2))
+
+        def forward(self, **kw):
+            calls.append(kw)
+            return kw["y_velocs"].sum() * 0 + self.w.sum()
+
+    class Batch:
+        atom_coords, atom_coord_targets = torch.zeros(2, 3, 3), torch.ones(2, 3, 3)
+        atom_velocs, atom_veloc_targets = torch.full((2, 3, 3), 2.0), torch.full((2, 3, 3), 3.0)
+        atom_types, masked_elements = torch.zeros(2, 3, dtype=torch.long), torch.zeros(2, 3, dtype=torch.bool)
+        adj_list, edge_batch_idx = torch.zeros(0, 2, dtype=torch.long), torch.zeros(0, dtype=torch.long)
+
+    m = Model()
+    w = losses.LossWrapper(m, losses.NegativeLogLikelihoodLoss(random_velocs=False))
+    w(Batch, device="cpu")
+    assert torch.equal(calls[-1]["x_velocs"], Batch.atom_velocs) and torch.equal(calls[-1]["y_velocs"], Batch.atom_veloc_targets)
+    assert torch.equal(calls[-1]["y_coords"], Batch.atom_coord_targets)
+    torch.manual_seed(0)
+    losses.LossWrapper(m, losses.NegativeLogLikelihoodLoss())(Batch)
+    torch.manual_seed(0)
+    a, b = torch.randn(2, 3, 3), torch.randn(2, 3, 3)  # conditioning velocities are drawn first (losses.py:333-334)
+    assert torch.equal(calls[-1]["x_velocs"], a) and torch.equal(calls[-1]["y_velocs"], b)
+    # (un)wrapping
+    w2 = losses.wrap_or_replace_loss(losses.LossWrapper(w, None), losses.NegativeLogLikelihoodLoss())
+    assert w2.module is m and losses.unwrap_loss_wrapper(losses.LossWrapper(w2)) is m
+    with pytest.raises(AssertionError):
+        losses.LossWrapper(m)(Batch)
+    with pytest.raises(TypeError):
+        losses.get_loss(object(), m, Batch)
+    # state dicts of a wrapper ("module." prefix, DeepSpeed checkpoints) and of the bare module both load
+    sd = {"w": torch.tensor([1.0, 2.0])}
+    w.load_state_dict(sd)
+    assert torch.equal(m.w.data, sd["w"])
+    w.load_state_dict({"module.w": torch.tensor([3.0, 4.0])})
+    assert torch.equal(m.w.data, torch.tensor([3.0, 4.0]))
+    assert set(w.state_dict()) == {"module.w"}

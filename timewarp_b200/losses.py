@@ -149,3 +149,72 @@ def acceptance_loss(loss: AcceptanceLoss, model, batch, device: Optional[Union[s
                 per_sample, num_atoms = torch.tensor(10000.0, device=x_coords.device), torch.tensor(1.0, device=x_coords.device)
         total = total + (per_sample / num_atoms).mean()
     return total / loss.num_samples
+
+
+class NegativeLogLikelihoodLoss:
+    """losses.py:306-319."""
+
+    def __init__(self, random_velocs: bool = True):
+        self.random_velocs = random_velocs
+
+
+def nll_loss(loss: NegativeLogLikelihoodLoss, model, batch, device: Optional[Union[str, torch.device]] = None, logger=None) -> Tensor:
+    """`get_loss(NegativeLogLikelihoodLoss, ...)`, losses.py:321-356: with `random_velocs` BOTH velocity tensors are fresh
+    standard-normal draws (conditioning first, then target -- the order matters for seeded runs), then `model(...)`."""
+    to = (lambda t: t.to(device, non_blocking=True)) if device is not None else (lambda t: t)
+    x_coords, y_coords = to(batch.atom_coords), to(batch.atom_coord_targets)
+    if loss.random_velocs:
+        x_velocs = torch.randn_like(x_coords).contiguous()
+        y_velocs = torch.randn_like(y_coords).contiguous()
+    else:
+        x_velocs, y_velocs = to(batch.atom_velocs), to(batch.atom_veloc_targets)
+    return model(atom_types=to(batch.atom_types), x_coords=x_coords, x_velocs=x_velocs, y_coords=y_coords, y_velocs=y_velocs,
+                 adj_list=to(batch.adj_list), edge_batch_idx=to(batch.edge_batch_idx), masked_elements=to(batch.masked_elements), logger=logger)
+
+
+def get_loss(loss, model, batch, device: Optional[Union[str, torch.device]] = None, logger=None) -> Tensor:
+    """losses.py:215-238: dispatch on the loss type (the reference uses `multimethod`)."""
+    for cls, fn in ((NegativeLogLikelihoodLoss, nll_loss), (AcceptanceLoss, acceptance_loss), (EnergyLoss, energy_loss)):
+        if isinstance(loss, cls):
+            return fn(loss, model, batch, device=device, logger=logger)
+    raise TypeError(f"no loss implementation for {type(loss).__name__}")
+
+
+class LossWrapper(torch.nn.Module):
+    """losses.py:241-272: `wrapper(batch, device=..., logger=...)` computes `loss` for `module`; a state dict saved from a
+    wrapper ("module.…" keys, what DeepSpeed checkpoints hold) or from the bare module both load."""
+
+    def __init__(self, module: torch.nn.Module, loss=None):
+        super().__init__()
+        self.module = module
+        self.loss = loss
+
+    def load_state_dict(self, state_dict, strict: bool = True):
+        if not any(k.split(".", 1)[0] == "module" for k in state_dict):
+            print("`state_dict` seems to be meant for `module`; loading this instead")
+            return self.module.load_state_dict(state_dict, strict=strict)
+        inner = {k.split(".", 1)[1]: v for k, v in state_dict.items() if k.split(".", 1)[0] == "module"}
+        out = self.module.load_state_dict(inner, strict=strict)
+        loss_sd = {k.split(".", 1)[1]: v for k, v in state_dict.items() if k.split(".", 1)[0] == "loss"}
+        if loss_sd:
+            if isinstance(self.loss, torch.nn.Module):
+                self.loss.load_state_dict(loss_sd, strict=strict)
+            elif strict:
+                print(f"LossWrapper: loss is not a `torch.nn.Module` but `state_dict` contains the following loss parameters {list(loss_sd)}")
+        return out
+
+    def forward(self, *args, **kwargs):
+        assert self.loss is not None, "`loss` is not given"
+        return get_loss(self.loss, self.module, *args, **kwargs)
+
+
+def wrap_or_replace_loss(model: torch.nn.Module, loss) -> LossWrapper:
+    """losses.py:274-289: wrap `model`, or replace the loss of an (arbitrarily nested) wrapper."""
+    return LossWrapper(module=unwrap_loss_wrapper(model), loss=loss)
+
+
+def unwrap_loss_wrapper(model: torch.nn.Module) -> torch.nn.Module:
+    """losses.py:292-303."""
+    while isinstance(model, LossWrapper):
+        model = model.module
+    return model
