@@ -509,6 +509,10 @@ class ConditionalFlowDensityModel(nn.Module):
         trainable = want_logp and S == 1 and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
         if trainable and (self.training or self._train_supported(B, V)):
             return self._sample_taped(atom_types, x_coords, x_velocs, mask, z_coords, z_velocs)
+        if self.training and want_logp and S > 1 and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            # no silent loss of the graph: the differentiable sampler covers num_samples == 1 (how the losses call it)
+            raise NotImplementedError("conditional_sample_with_logp under autograd supports num_samples == 1 only; "
+                                      "wrap inference calls in torch.no_grad()")
         if z_coords is None:
             # RNG contract (flow.py:274-275): two normal_() draws [S,B,V,3] from the device's default
             # generator, coords first, each scaled by exp(log_scale).
