@@ -200,9 +200,15 @@ class DataParallelTrainer:
         if flat is None:
             return False
         base = flat.untyped_storage().data_ptr()
+        seen = False
         for p in self.model.parameters():
-            if p.requires_grad and (p.grad is None or p.grad.untyped_storage().data_ptr() != base):
+            if not p.requires_grad or p.grad is None:  # (unused parameters, e.g. the log_lengthscales a pass never reads,
+                continue                               #  have no gradient on ANY rank: nothing to reduce)
+            if p.grad.untyped_storage().data_ptr() != base:
                 return False
+            seen = True
+        if not seen:
+            return False
         rank, world = world_info()
         if world > 1:
             dist.all_reduce(flat, op=dist.ReduceOp.SUM)
