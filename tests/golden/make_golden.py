@@ -400,7 +400,18 @@ def learnable_grad_case():
               extra_keys=["flow.chain.0.scale_transformer.encoder_layers.0.self_attn.attention.log_lengthscales"])
 
 
+def chebyshev_grad_case():
+    """chebyshev_kernel training: every attention layer's cheb_coeffs receives its own gradient."""
+    ad = alanine_dipeptide()
+    grad_case("grads_full_ad22_chebyshev", FULL_CHEB, ad, B=3, seed=32, lengths=[22, 17, 12],
+              extra_keys=["flow.chain.0.scale_transformer.encoder_layers.0.self_attn.attention.cheb_coeffs",
+                          "flow.chain.5.shift_transformer.encoder_layers.2.self_attn.attention.cheb_coeffs"])
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "chebyshev_grad":
+        chebyshev_grad_case()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "learnable_grad":
         learnable_grad_case()
         sys.exit(0)
@@ -436,6 +447,7 @@ if __name__ == "__main__":
     learnable_cases()
     learnable_grad_case()
     chebyshev_cases()
+    chebyshev_grad_case()
     local_cases()
     md_case()
     checkpoint_case()

@@ -252,7 +252,7 @@ def test_chebyshev_kernel_module_surface():
         a = fresh.log_likelihood(y_coords=g["y_coords"].cuda(), y_velocs=g["y_velocs"].cuda(), **kw)
         b = gauss.log_likelihood(y_coords=g["y_coords"].cuda(), y_velocs=g["y_velocs"].cuda(), **kw)
     assert_rel(a, b, rel=1e-4, what="initial Chebyshev coefficients == Gaussian kernel")
-    m.train()
+    m.train()  # (tiny layer sizes / fp32: no backward kernels -- chebyshev training at full size is in test_gpu_train.py)
     with pytest.raises(Exception):
         m(y_coords=g["y_coords"].cuda(), y_velocs=g["y_velocs"].cuda(), **kw)
 

@@ -9,7 +9,7 @@ import pytest
 import torch
 
 from oracle import flow_oracle as fo
-from tests.common import EMPTY_ADJ, EMPTY_EBI, FULL_L, FULL_O, GOLDEN, build_model
+from tests.common import EMPTY_ADJ, EMPTY_EBI, FULL_C, FULL_L, FULL_O, GOLDEN, build_model
 from timewarp_b200 import _lib
 
 pytestmark = pytest.mark.gpu
@@ -97,11 +97,11 @@ def _load(name):
     return {k: (torch.from_numpy(d[k]) if d[k].dtype.kind != "U" else d[k]) for k in d.files}
 
 
-@pytest.mark.parametrize("name", ["grads_full_ad22", "grads_full_ad22_ragged", "grads_full_ad22_learnable"])
+@pytest.mark.parametrize("name", ["grads_full_ad22", "grads_full_ad22_ragged", "grads_full_ad22_learnable", "grads_full_ad22_chebyshev"])
 def test_backward_matches_reference_gradients(name):
     g = _load(name)
     learnable = name.endswith("learnable")
-    m, _ = build_model(FULL_L if learnable else FULL_O, "bf16x3", int(g["weight_seed"]))
+    m, _ = build_model(FULL_L if learnable else (FULL_C if name.endswith("chebyshev") else FULL_O), "bf16x3", int(g["weight_seed"]))
     loss, grads = _loss_and_grads(m, g)
     assert abs(float(loss) - float(g["loss"])) < 1e-4 * abs(float(g["loss"]))
     names = [str(n) for n in g["grad_names"]]
@@ -195,6 +195,44 @@ def test_learnable_lengthscale_gradient_matches_oracle_autograd():
     loss2, grads2 = _loss_and_grads(m, g)
     assert float(loss2) == float(loss) and not any(k.endswith("log_lengthscales") for k in grads2)
     assert _rel(grads2[k2], grads[k2]) < 1e-5  # (weight gradients accumulate with fp32 atomics: not bit-reproducible)
+
+
+def test_chebyshev_coefficient_gradients_match_oracle_autograd():
+    """chebyshev_kernel training with the expansion forced to vanish at infinity (coefficient-mean subtraction in the chain
+    rule) on a ragged batch: every cheb_coeffs tensor and a few others against the oracle's fp64 autograd."""
+    import dataclasses
+    torch.manual_seed(19)
+    B, V = 5, 28
+    lengths = [28, 20, 13, 28, 7]
+    mask = torch.zeros(B, V, dtype=torch.bool)
+    for b, n in enumerate(lengths):
+        mask[b, n:] = True
+    keep = (~mask)[:, :, None]
+    x = 0.25 * torch.randn(B, V, 3) * keep
+    y = (x + 0.02 * torch.randn(B, V, 3)) * keep
+    xv, yv = torch.randn(B, V, 3) * keep, torch.randn(B, V, 3) * keep
+    at = torch.randint(0, 5, (B, V)) * (~mask)
+    cfg = dataclasses.replace(FULL_C, cheb_order=9, force_asymptotic_zero=True)
+    g = dict(atom_types=at, x_coords=x, x_velocs=xv, y_coords=y, y_velocs=yv, masked_elements=mask)
+    m, sd = build_model(cfg, "bf16x3", 8)
+    loss, grads = _loss_and_grads(m, g)
+    loss_ref, grads_ref = fo.nll_loss_and_grads(fo.to_dtype(sd, torch.float64), cfg, at, x.double(), xv.double(), y.double(), yv.double(),
+                                                mask, distance_mode="direct")
+    assert abs(float(loss) - float(loss_ref)) < 1e-4 * abs(float(loss_ref))
+    cheb = [k for k in grads_ref if k.endswith("cheb_coeffs")]
+    assert len(cheb) == 48
+    total = float(torch.sqrt(sum(grads_ref[k].double().norm() ** 2 for k in cheb)))
+    for k in cheb + ["flow.chain.3.shift_transformer.encoder_layers.1.self_attn.values_proj.weight", "flow.atom_embedder.weight"]:
+        ref = grads_ref[k].double()
+        err = float((grads[k].double() - ref).norm())
+        assert err <= GRAD_RTOL * max(float(ref.norm()), 1e-2 * total), (k, err, float(ref.norm()))
+    # frozen coefficients: the extra kernels are skipped, the other gradients do not move
+    for n, p in m.named_parameters():
+        if n.endswith("cheb_coeffs"):
+            p.requires_grad_(False)
+    _, grads2 = _loss_and_grads(m, g)
+    assert not any(k.endswith("cheb_coeffs") for k in grads2)
+    assert _rel(grads2["flow.atom_embedder.weight"], grads["flow.atom_embedder.weight"]) < 1e-5
 
 
 def test_inference_result_unchanged_and_no_grad_path():

@@ -17,11 +17,15 @@ def load_grad_case(golden_dir, name):
     return g
 
 
-@pytest.mark.parametrize("name", ["grads_full_ad22", "grads_full_ad22_ragged", "grads_full_ad22_learnable"])
+@pytest.mark.parametrize("name", ["grads_full_ad22", "grads_full_ad22_ragged", "grads_full_ad22_learnable", "grads_full_ad22_chebyshev"])
 def test_oracle_autograd_matches_reference(golden_dir, name):
     torch.set_num_threads(max(torch.get_num_threads(), 4))
     g = load_grad_case(golden_dir, name)
-    FULL = fo.OracleConfig(attention_type="learnable_kernel") if name.endswith("learnable") else fo.OracleConfig()
+    FULL = fo.OracleConfig()
+    if name.endswith("learnable"):
+        FULL = fo.OracleConfig(attention_type="learnable_kernel")
+    if name.endswith("chebyshev"):
+        FULL = fo.OracleConfig(attention_type="chebyshev_kernel", cheb_order=12, force_asymptotic_zero=False)
     sd = fo.synth_state_dict(FULL, int(g["weight_seed"]))
     loss, grads = fo.nll_loss_and_grads(sd, FULL, g["atom_types"], g["x_coords"], g["x_velocs"], g["y_coords"], g["y_velocs"],
                                         g["masked_elements"])

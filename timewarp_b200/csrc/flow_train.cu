@@ -655,14 +655,14 @@ struct ScoreGradArgs {
   const float* x[2];  // [M, 128] layer input
   float* S;           // [B, H, V, V]
 };
-__global__ void __launch_bounds__(128) k_score_grad(ScoreGradArgs a, int V, int H) {
+__global__ void __launch_bounds__(128) k_score_grad(ScoreGradArgs a, int V, int H, int net0, int net1) {
   extern __shared__ float sg[];
   float* sX = sg;                       // [V][129]
   float* sQ = sX + (size_t)V * 129;     // [4 warps][128]
   const int64_t b = blockIdx.x;
   const int h = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* S = a.S + ((size_t)b * H + h) * V * V;
-  for (int net = 0; net < 2; net++) {
+  for (int net = net0; net < net1; net++) {  // [0, 2): both networks share the scores; chebyshev_kernel: one at a time
     const float* X = a.x[net] + b * V * 128;
     for (int e = threadIdx.x; e < V * 128; e += blockDim.x) sX[(e >> 7) * 129 + (e & 127)] = X[e];
     __syncthreads();
@@ -722,6 +722,77 @@ __global__ void __launch_bounds__(256) k_ls_grad(const float* __restrict__ xc, c
       atomicAdd(&dls[h], t);
     }
     __syncthreads();
+  }
+}
+
+// chebyshev_kernel (kernel_attention.py:13-66,255-339): w_ij = sum_c (coef_c - mean) R_c((d_ij / l)^2) [j not padding],
+// A_ij = w_ij / (sum_j |w_ij| + eps).  With S = dL/dA of ONE attention layer of ONE network:
+//   dL/dw_ij = (S_ij - sign(w_ij) D_i) / s_i,  D_i = sum_j S_ij A_ij;   dL/dcoef_c = sum_ij dL/dw_ij R_c  (- the mean over c when
+// the expansion is forced to vanish at infinity).  One block per state, one warp per row, per-lane partial sums per coefficient.
+__global__ void __launch_bounds__(256) k_cheb_grad(const float* __restrict__ xc, const uint8_t* __restrict__ mask, const float* __restrict__ ls,
+                                                   const float* __restrict__ coef_all, int order, int force_zero,
+                                                   const float* __restrict__ S, int V, int H, float* __restrict__ dcoef) {
+  __shared__ float acc[TW_MAX_HEADS * TW_MAX_CHEB_ORDER];
+  const int64_t b = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float* xb = xc + b * V * 3;
+  const uint8_t* mb = mask + b * V;
+  for (int i = threadIdx.x; i < H * order; i += blockDim.x) acc[i] = 0.f;
+  __syncthreads();
+  for (int h = 0; h < H; h++) {
+    const float l = ls[h];
+    const float* coef = coef_all + (size_t)h * order;
+    const float cmean = cheb_mean(coef, order, force_zero);
+    const float* Sh = S + ((size_t)b * H + h) * V * V;
+    float part[TW_MAX_CHEB_ORDER];
+#pragma unroll
+    for (int c = 0; c < TW_MAX_CHEB_ORDER; c++) part[c] = 0.f;
+    for (int i = warp; i < V; i += 8) {
+      const float xi = xb[i * 3], yi = xb[i * 3 + 1], zi = xb[i * 3 + 2];
+      float s = 0.f, dot = 0.f;
+      for (int j = lane; j < V; j += 32) {
+        if (mb[j]) continue;
+        const float dx = xi - xb[j * 3], dy = yi - xb[j * 3 + 1], dz = zi - xb[j * 3 + 2];
+        const float w = attention_basis(sqrtf(dx * dx + dy * dy + dz * dz) / l, coef, order, cmean);
+        s += fabsf(w), dot = fmaf(Sh[(size_t)i * V + j], w, dot);
+      }
+      s = warp_sum(s) + 1e-5f, dot = warp_sum(dot) / s;  // dot = D_i
+      for (int j = lane; j < V; j += 32) {
+        if (mb[j]) continue;
+        const float dx = xi - xb[j * 3], dy = yi - xb[j * 3 + 1], dz = zi - xb[j * 3 + 2];
+        const float a = sqrtf(dx * dx + dy * dy + dz * dz) / l;
+        const float w = attention_basis(a, coef, order, cmean);
+        const float gw = (Sh[(size_t)i * V + j] - (w > 0.f ? dot : (w < 0.f ? -dot : 0.f))) / s;
+        const float y = a * a, rf = (y - 1.0f) / (y + 1.0f);
+        float rprev = 1.0f, rcur = rf;
+        part[0] += gw;
+        if (order >= 2) part[1] = fmaf(gw, rcur, part[1]);
+#pragma unroll
+        for (int c = 2; c < TW_MAX_CHEB_ORDER; c++) {
+          if (c < order) {
+            const float rnext = 2.0f * rf * rcur - rprev;
+            part[c] = fmaf(gw, rnext, part[c]);
+            rprev = rcur, rcur = rnext;
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < TW_MAX_CHEB_ORDER; c++) {
+      if (c < order) {
+        const float t = warp_sum(part[c]);
+        if (lane == 0) atomicAdd(&acc[h * order + c], t);
+      }
+    }
+  }
+  __syncthreads();
+  for (int h = threadIdx.x; h < H; h += blockDim.x) {
+    float m = 0.f;
+    if (force_zero) {
+      for (int c = 0; c < order; c++) m += acc[h * order + c];
+      m /= (float)order;
+    }
+    for (int c = 0; c < order; c++) atomicAdd(&dcoef[h * order + c], acc[h * order + c] - m);
   }
 }
 
@@ -827,8 +898,8 @@ static size_t carve_tape(const tw_flow_config* c, int64_t B, int V, void* base, 
 }
 
 static int check_train(const tw_flow_config* c, const void* const* params, int64_t B, int64_t V) {
-  if (c && c->attention_type != TW_ATTENTION_KERNEL)
-    return fail(TW_ERR_UNSUPPORTED, "the training path is built for the `kernel` attention only");
+  if (c && c->attention_type != TW_ATTENTION_KERNEL && c->attention_type != TW_ATTENTION_CHEBYSHEV)
+    return fail(TW_ERR_UNSUPPORTED, "the training path is built for the `kernel` / `learnable_kernel` / `chebyshev_kernel` attention");
   TW_CHECK_ARG(c != nullptr && params != nullptr, "NULL cfg / params");
   if (c->precision == TW_PRECISION_FP32 || !tc_supported(c))
     return fail(TW_ERR_UNSUPPORTED, "the training path needs a tensor-core precision (bf16x3 / bf16) and the flagship layer sizes");
@@ -1071,7 +1142,7 @@ static int conditioner_bwd(BwdCtx& x, int k, float* dz_other, const float* z_oth
       ScoreGradArgs sa{};
       for (int s = 0; s < 2; s++) sa.q[s] = b.wide0[s], sa.x[s] = x.tp.net[k][s].h[t];
       sa.S = b.sgrad;
-      k_score_grad<<<dim3((unsigned)x.B, H), 128, ((size_t)x.V * 129 + 4 * 128) * sizeof(float), x.st>>>(sa, x.V, H);
+      k_score_grad<<<dim3((unsigned)x.B, H), 128, ((size_t)x.V * 129 + 4 * 128) * sizeof(float), x.st>>>(sa, x.V, H, 0, 2);
       TW_LAUNCH_CHECK();
     }
     {
@@ -1087,7 +1158,35 @@ static int conditioner_bwd(BwdCtx& x, int k, float* dz_other, const float* z_oth
       k_wc_chain<<<dim3(H, 128, 2), 128, 0, x.st>>>(ch, 128, H);
       TW_LAUNCH_CHECK();
       // G_h = A_h^T dr  (transposed score images), then dx = dr + sum_h G_h W_c,h
-      TW_TRY(tc_mix(c, b.dr, b.img_g, x.tp.scores_img_t, x.B, x.B, x.V, x.st));
+      if (x.pv.chebyshev()) {
+        // per network: rebuild this layer's scores (fp32 + transposed images), G_h, and the coefficient gradient
+        GemmArgs q = gemm_base(x, GEMM_NN);  // Q [M, H*128] = dr W_c (both networks)
+        for (int s = 0; s < 2; s++) q.A[s] = plain_img(b.img_d[s], 2), q.B[s] = plain_img(eb[s] + L.enc_wc, H * 2), q.C[s] = b.wide0[s];
+        q.ldc = H * 128, q.rows = (int)x.M, q.cols = H * 128, q.tiles_m = x.tiles, q.tiles_n = H, q.KB = 2;
+        TW_TRY(launch_gemm(c, q, x.st));
+        for (int net = 0; net < 2; net++) {
+          const float* coef = x.pv.cheb(k, net, t);
+          TW_TRY(launch_scores(x.tp.xc, x.mask, x.pv.enc(0, 0, 0, 1), x.B, x.V, H, x.tp.scores, x.st, coef, c->cheb_order, c->force_asymptotic_zero));
+          TW_TRY(tc_scores_images(c, x.tp.scores, x.B, x.V, x.tp.scores_img_t, 1, x.st));
+          float* const dr1[2] = {b.dr[net], b.dr[net]};
+          uint8_t* const g1[2] = {b.img_g[net], b.img_g[net]};
+          TW_TRY(tc_mix(c, dr1, g1, x.tp.scores_img_t, x.B, x.B, x.V, x.st, 1));
+          float* dcoef = x.gv.at(x.pv.regular() + (k * 2 + net) * c->num_transformer_layers + t);
+          if (dcoef) {
+            TW_CUDA(cudaMemsetAsync(b.sgrad, 0, (size_t)x.B * H * x.V * x.V * sizeof(float), x.st));
+            ScoreGradArgs sa{};
+            for (int s = 0; s < 2; s++) sa.q[s] = b.wide0[s], sa.x[s] = x.tp.net[k][s].h[t];
+            sa.S = b.sgrad;
+            k_score_grad<<<dim3((unsigned)x.B, H), 128, ((size_t)x.V * 129 + 4 * 128) * sizeof(float), x.st>>>(sa, x.V, H, net, net + 1);
+            TW_LAUNCH_CHECK();
+            k_cheb_grad<<<(unsigned)x.B, 256, 0, x.st>>>(x.tp.xc, x.mask, x.pv.enc(0, 0, 0, 1), coef, c->cheb_order, c->force_asymptotic_zero,
+                                                        b.sgrad, x.V, H, dcoef);
+            TW_LAUNCH_CHECK();
+          }
+        }
+      } else {
+        TW_TRY(tc_mix(c, b.dr, b.img_g, x.tp.scores_img_t, x.B, x.B, x.V, x.st));
+      }
       GemmArgs d = gemm_base(x, GEMM_NN_HEADED);
       for (int s = 0; s < 2; s++) {
         d.A[s] = plain_img(b.img_g[s], H * 2);
@@ -1203,8 +1302,8 @@ int tw_flow_train_bytes(const tw_flow_config* cfg, int64_t B, int64_t V, size_t*
 
 // conditioner pair of coupling layer k on `z_other`, every layer boundary written to the tape; (s, t) end up in net[k][.].st
 static int taped_conditioner(const tw_flow_config* cfg, const ParamView& pv, const void* packed_weights, Tape& tp, int k,
-                             const float* z_other, const int64_t* atom_types, const float* x_velocs, int64_t B, int64_t V,
-                             cudaStream_t st) {
+                             const float* z_other, const int64_t* atom_types, const float* x_velocs, const uint8_t* mask, int64_t B,
+                             int64_t V, cudaStream_t st) {
   const int T = cfg->num_transformer_layers;
   const int64_t M = B * V;
   TcScratch tc{};
@@ -1223,7 +1322,16 @@ static int taped_conditioner(const tw_flow_config* cfg, const ParamView& pv, con
       const size_t tile_bytes = tc_mixed_img_bytes(cfg, 128);
       for (int s = 0; s < 2; s++) TW_CUDA(cudaMemsetAsync(tc.mixed_img[s] + (size_t)(M / 128) * tile_bytes, 0, tile_bytes, st));
     }
-    TW_TRY(tc_attention_layer(cfg, pv, k, t, tc, hin, y1, B, B, (int)V, st, r1));
+    if (pv.chebyshev()) {
+      // every attention layer of every network has its own basis function, hence its own scores (kernel_attention.py:333-335):
+      // the forward images are rebuilt in place per (layer, network); the backward rebuilds the transposed ones the same way
+      for (int net = 0; net < 2; net++) {
+        TW_TRY(tc_begin_pass_direct(cfg, tc, tp.xc, mask, pv.enc(0, 0, 0, 1), B, (int)V, st, pv.cheb(k, net, t), false));
+        TW_TRY(tc_attention_layer(cfg, pv, k, t, tc, hin, y1, B, B, (int)V, st, r1, net));
+      }
+    } else {
+      TW_TRY(tc_attention_layer(cfg, pv, k, t, tc, hin, y1, B, B, (int)V, st, r1));
+    }
     TW_TRY(tc_ffn_layer(cfg, pv, k, t, tc, y1, hout, M, st, r2));
   }
   float* hl[2] = {tp.net[k][0].h[T], tp.net[k][1].h[T]};
@@ -1235,9 +1343,11 @@ static int taped_conditioner(const tw_flow_config* cfg, const ParamView& pv, con
 static int begin_taped_pass(const tw_flow_config* cfg, const ParamView& pv, Tape& tp, const float* x_coords, const uint8_t* mask,
                             int64_t B, int64_t V, cudaStream_t st) {
   TW_TRY(launch_prep(x_coords, mask, B, (int)V, tp.xc, tp.com, st));
-  TW_TRY(launch_scores(tp.xc, mask, pv.enc(0, 0, 0, 1), B, (int)V, cfg->num_heads, tp.scores, st));
-  TW_TRY(tc_scores_images(cfg, tp.scores, B, (int)V, tp.scores_img, 0, st));
-  TW_TRY(tc_scores_images(cfg, tp.scores, B, (int)V, tp.scores_img_t, 1, st));
+  if (!pv.chebyshev()) {  // (chebyshev_kernel: the scores belong to an attention layer, not to the pass -- taped_conditioner)
+    TW_TRY(launch_scores(tp.xc, mask, pv.enc(0, 0, 0, 1), B, (int)V, cfg->num_heads, tp.scores, st));
+    TW_TRY(tc_scores_images(cfg, tp.scores, B, (int)V, tp.scores_img, 0, st));
+    TW_TRY(tc_scores_images(cfg, tp.scores, B, (int)V, tp.scores_img_t, 1, st));
+  }
   TW_CUDA(cudaMemsetAsync(tp.delta, 0, B * sizeof(float), st));
   return TW_OK;
 }
@@ -1266,7 +1376,7 @@ int tw_flow_log_likelihood_train(const tw_flow_config* cfg, const void* const* p
   TW_CUDA(cudaMemcpyAsync(tp.z[0][1], y_velocs, cnt * sizeof(float), cudaMemcpyDeviceToDevice, st));
   for (int k = 0; k < L; k++) {
     const bool pos = (k % 2) == cfg->position_layer_index_mod_2;
-    TW_TRY(taped_conditioner(cfg, pv, packed_weights, tp, k, pos ? tp.z[k][1] : tp.z[k][0], atom_types, x_velocs, B, V, st));
+    TW_TRY(taped_conditioner(cfg, pv, packed_weights, tp, k, pos ? tp.z[k][1] : tp.z[k][0], atom_types, x_velocs, mask, B, V, st));
     // next state: copy both halves, then transform the target half in place
     TW_CUDA(cudaMemcpyAsync(tp.z[k + 1][0], tp.z[k][0], cnt * sizeof(float), cudaMemcpyDeviceToDevice, st));
     TW_CUDA(cudaMemcpyAsync(tp.z[k + 1][1], tp.z[k][1], cnt * sizeof(float), cudaMemcpyDeviceToDevice, st));
@@ -1302,7 +1412,7 @@ int tw_flow_sample_train(const tw_flow_config* cfg, const void* const* params, c
   TW_CUDA(cudaMemcpyAsync(tp.z[L][1], z_velocs, cnt * sizeof(float), cudaMemcpyDeviceToDevice, st));
   for (int k = L - 1; k >= 0; k--) {
     const bool pos = (k % 2) == cfg->position_layer_index_mod_2;
-    TW_TRY(taped_conditioner(cfg, pv, packed_weights, tp, k, pos ? tp.z[k + 1][1] : tp.z[k + 1][0], atom_types, x_velocs, B, V, st));
+    TW_TRY(taped_conditioner(cfg, pv, packed_weights, tp, k, pos ? tp.z[k + 1][1] : tp.z[k + 1][0], atom_types, x_velocs, mask, B, V, st));
     TW_CUDA(cudaMemcpyAsync(tp.z[k][0], tp.z[k + 1][0], cnt * sizeof(float), cudaMemcpyDeviceToDevice, st));
     TW_CUDA(cudaMemcpyAsync(tp.z[k][1], tp.z[k + 1][1], cnt * sizeof(float), cudaMemcpyDeviceToDevice, st));
     TW_TRY(launch_coupling(tp.net[k][0].st, tp.net[k][1].st, pos ? tp.z[k][0] : tp.z[k][1], mask, tp.delta, B, B, (int)V, 1, nullptr, nullptr, st));
@@ -1329,7 +1439,8 @@ static int begin_backward(BwdCtx& x, const tw_flow_config* cfg, const void* cons
   for (int i = 0; i < x.pv.total(); i++) {
     const bool is_ls = i >= 3 && ((i - 3) % x.pv.per_net()) >= x.pv.per_mlp() && ((i - 3) % x.pv.per_net()) < x.pv.per_mlp() + 11 * cfg->num_transformer_layers &&
                        (((i - 3) % x.pv.per_net()) - x.pv.per_mlp()) % 11 == 1;
-    TW_CHECK_ARG(is_ls || i == 1 || i == 2 || grads[i] != nullptr, "gradient table entry %d is NULL", i);
+    const bool is_cheb = i >= x.pv.regular();  // trailing cheb_coeffs section: NULL = frozen
+    TW_CHECK_ARG(is_ls || is_cheb || i == 1 || i == 2 || grads[i] != nullptr, "gradient table entry %d is NULL", i);
   }
   x.L = TcLayout::make(cfg);
   x.packed = (const uint8_t*)packed_weights;
@@ -1342,6 +1453,14 @@ static int begin_backward(BwdCtx& x, const tw_flow_config* cfg, const void* cons
   x.st = (cudaStream_t)stream;
   // lengthscale gradient (learnable_kernel): requested by a non-NULL entry for the lengthscales of chain[0].scale.layer[0]
   x.dls = x.gv.enc(0, 0, 0, 1);
+  if (x.pv.chebyshev()) {
+    TW_CHECK_ARG(!x.dls && !x.want_inputs, "chebyshev_kernel: gradients w.r.t. lengthscales / conditioning state are not built");
+    static bool attr_cheb = false;
+    if (!attr_cheb) {
+      TW_CUDA(cudaFuncSetAttribute(k_score_grad, cudaFuncAttributeMaxDynamicSharedMemorySize, (128 * 129 + 4 * 128) * (int)sizeof(float)));
+      attr_cheb = true;
+    }
+  }
   if (x.want_inputs) {
     TW_CUDA(cudaMemsetAsync(x.b.dxc, 0, (size_t)B * V * 3 * sizeof(float), x.st));
     TW_CUDA(cudaMemsetAsync(x.b.dxv, 0, (size_t)B * V * 3 * sizeof(float), x.st));
