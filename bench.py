@@ -443,6 +443,11 @@ def run_ours(args):
     launches = launches_per_step * args.steps
     ffn_ms, ffn_scopes = C.c_double(0), C.c_longlong(0)
     _lib.check(lib.tw_prof_collect(C.byref(ffn_ms), C.byref(ffn_scopes)), "tw_prof_collect")
+    # ... and the same for the attention layer (the "kernel-attention tile" of the north star), one more eager step
+    lib.tw_prof_enable(2)
+    chains._step_impl()
+    attn_ms, attn_scopes = C.c_double(0), C.c_longlong(0)
+    _lib.check(lib.tw_prof_collect(C.byref(attn_ms), C.byref(attn_scopes)), "tw_prof_collect")
     lib.tw_prof_enable(0)
 
     # ---- end-to-end region: host (pinned) state in, host state + decisions out, every step --
@@ -497,6 +502,20 @@ def run_ours(args):
         ffn_flops = 2 * M * ffn_flops_per_token()  # one timed scope = FFN of BOTH conditioner networks over all tokens
         achieved = ffn_flops / (ffn_ms_avg / 1e3) / 1e12 if ffn_ms_avg > 0 else 0.0
         issued_factor = 3 if args.precision == "bf16x3" else 1
+        # attention layer (both networks per timed scope).  Algorithmic = the reference's arithmetic per token: value projection
+        # 196 608 + mixing 1 536 V + out projection 196 608.  Issued = what the fused kernel really feeds
+        # the tensor pipe: per (sample, head) MMA1 128 x 128 x VP and MMA2 128 x 128 x 128, every row of the 128-row tile.
+        n_attn = max(int(attn_scopes.value), 1)
+        attn_ms_avg = attn_ms.value / n_attn
+        attn_alg = 2 * M * (393216 + 1536 * V)
+        VP = (V + 15) // 16 * 16
+        attn_issued = 2 * args.chains * int(model._cfg.num_heads) * 2 * 128 * 128 * (VP + 128) * issued_factor
+        attn_roofline = {"bound": "tensor", "kernel": "fused attention layer (mixing + W_o W_v projection + residual + LayerNorm), both conditioner nets",
+                         "achieved": attn_alg / (attn_ms_avg / 1e3) / 1e12 if attn_ms_avg > 0 else 0.0, "peak": peaks["tf_sustained"],
+                         "unit": "TFLOP/s", "issued_tflops": attn_issued / (attn_ms_avg / 1e3) / 1e12 if attn_ms_avg > 0 else 0.0,
+                         "avg_launch_ms": attn_ms_avg, "launches_timed": n_attn}
+        attn_roofline["frac"] = attn_roofline["achieved"] / peaks["tf_sustained"]
+        attn_roofline["issued_frac"] = attn_roofline["issued_tflops"] / peaks["tf_sustained"]
         traffic = None
         tp = os.path.join(ROOT, "profiles", "ffn_traffic.json")
         if os.path.exists(tp):
@@ -521,9 +540,10 @@ def run_ours(args):
             "clocks": sampler.summary(),
             "roofline": {"bound": "tensor", "kernel": "fused FFN (linear1+ReLU+linear2+residual), both conditioner nets",
                          "achieved": achieved, "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["tf_sustained"],
-                         "peak_source": peaks["source"] + " (sustained bf16 cuBLAS)", "issued_mma_factor": issued_factor,
+                         "peak_source": peaks["source"] + " (sustained bf16 cuBLAS)", "issued_mma_factor": issued_factor, "issued_frac": issued_factor * achieved / peaks["tf_sustained"],
                          "avg_launch_ms": ffn_ms_avg, "launches_timed": n_ffn, "share_of_step": ffn_ms.value / ms_prof,
                          "timed_in": f"{n_prof} eagerly launched steps after the timed region (CUDA events around each launch)", "traffic": traffic},
+            "roofline_attention": attn_roofline,
             "whole_step_algorithmic_tflops": step_flops * args.steps / (ms_total / 1e3) / 1e12,
             "acceptance_rate_mean": float(acc_rate.mean().item()),
         }
