@@ -500,3 +500,34 @@ def test_energy_kernel_reference_golden_energies_with_openmm():
     energy = PeptidePotentialEnergy(system_description_from_openmm(system))
     e = energy(torch.from_numpy(g["pot_positions"]).cuda()).cpu().numpy()[:, 0]
     np.testing.assert_allclose(e, g["pot_openmm"], rtol=0, atol=1e-3)
+
+
+def test_mh_chains_with_integrator_steps():
+    """MHChains with `openmm_on_current` / `openmm_on_proposal`: every chain takes its integrator steps in one launch; the carried
+    potential energy follows the moved state; rejected chains still move (on_current) / do not move (on_proposal)."""
+    from timewarp_b200 import md
+
+    pep = alanine_dipeptide()
+    sysd = amber_like_system(pep)
+    energy = PeptidePotentialEnergy(sysd)
+    m, _ = build_model(TINY_O, "fp32", 0)  # random weights: (almost) every proposal is rejected
+    B = 16
+    x0 = torch.from_numpy(_confs(pep, B, 8, noise=0.002)).cuda()
+    at = torch.tensor(pep.atom_types)[None].repeat(B, 1).cuda()
+    mask = torch.zeros(B, pep.num_atoms, dtype=torch.bool).cuda()
+    masses = torch.tensor(pep.masses, dtype=torch.float32)
+    sim = md.Simulation(sysd, md.get_simulation_environment_integrator("T1-peptides"))
+    torch.manual_seed(2)
+    cur = sampling.MHChains(m, energy, at, mask, x0, masses=masses, sim=sim, num_openmm_steps=20, openmm_on_current=True)
+    acc = cur.step()
+    moved = (cur.x - x0).abs().amax((1, 2))
+    assert torch.all(moved > 1e-4) and torch.isfinite(cur.x).all()
+    rej = ~acc
+    assert rej.any()
+    torch.testing.assert_close(cur.e_pot_x[rej], (energy(cur.x) / energy.kbT).squeeze(-1)[rej], rtol=1e-6, atol=1e-4)
+    torch.manual_seed(2)
+    prop = sampling.MHChains(m, energy, at, mask, x0, masses=masses, sim=sim, num_openmm_steps=20, openmm_on_proposal=True)
+    acc2 = prop.step()
+    assert torch.equal(prop.x[~acc2], x0[~acc2])  # a rejected proposal leaves no trace of its integrator steps
+    with pytest.raises(AssertionError):
+        sampling.MHChains(m, energy, at, mask, x0, sim=sim, num_openmm_steps=5, openmm_on_current=True)  # masses are required

@@ -120,7 +120,8 @@ class MHChains:
 
     def __init__(self, model, energy, atom_types: Tensor, masked_elements: Tensor, x_coords: Tensor, x_velocs: Optional[Tensor] = None,
                  masses: Optional[Tensor] = None, random_velocs: bool = True, resample_velocs: bool = True,
-                 chirality_centers: Optional[Tensor] = None, reference_signs: Optional[Tensor] = None, accept: bool = True):
+                 chirality_centers: Optional[Tensor] = None, reference_signs: Optional[Tensor] = None, accept: bool = True,
+                 sim=None, num_openmm_steps: int = 0, openmm_on_current: bool = False, openmm_on_proposal: bool = False):
         assert x_coords.device.type == "cuda", "MHChains runs on CUDA only"
         self.model, self.energy = model, energy
         self.B, self.V = x_coords.shape[:2]
@@ -140,6 +141,14 @@ class MHChains:
         self._graph, self._graph_last = None, None
         self._empty_adj = torch.zeros(0, 2, dtype=torch.long, device=dev)
         self._empty_ebi = torch.zeros(0, dtype=torch.long, device=dev)
+        # integrator steps inside the chain (evaluation_utils.py:594-602,623-626): `sim` is a timewarp_b200.md.Simulation; every
+        # chain takes its `num_openmm_steps` steps in the same kernel launch
+        self.sim, self.num_openmm_steps = sim, int(num_openmm_steps)
+        self.openmm_on_current = bool(openmm_on_current and sim is not None and num_openmm_steps > 0)
+        self.openmm_on_proposal = bool(openmm_on_proposal and sim is not None and num_openmm_steps > 0)
+        if self.openmm_on_current or self.openmm_on_proposal:
+            assert masses is not None, "integrator steps need the masses (velocity scale sqrt(kT / m), evaluation_utils.py:556)"
+            self._velocs_std = torch.sqrt(self.kbT / masses.to(dev, torch.float32))[None, :, None]
 
     @torch.no_grad()  # the reference samples under no_grad (evaluation_utils.py:468)
     def step(self):
@@ -158,10 +167,20 @@ class MHChains:
         m = self.model
         if self.random_velocs and self.resample_velocs:
             self.xv.normal_()  # :590-592 (same draw as torch.randn_like, in place: the state keeps its address)
+        if self.openmm_on_current:  # :594-602
+            if self.random_velocs:
+                xn, _ = self.sim.step(self.x, self.xv * self._velocs_std, self.num_openmm_steps)
+            else:
+                xn, vn = self.sim.step(self.x, self.xv, self.num_openmm_steps)
+                self.xv.copy_(vn)
+            self.x.copy_(xn)
+            self.e_pot_x.copy_((self.energy(self.x) / self.kbT).squeeze(-1))  # the carried energy belongs to the moved state
         y, yv, p_xy = m.conditional_sample_with_logp(
             atom_types=self.atom_types, x_coords=self.x, x_velocs=self.xv, adj_list=self._empty_adj,
             edge_batch_idx=self._empty_ebi, masked_elements=self.mask, num_samples=1)  # :609-617
         y, yv, p_xy = y[0], yv[0], p_xy[0]
+        if self.openmm_on_proposal:  # :623-626
+            y, _ = self.sim.step(y, yv * self._velocs_std, self.num_openmm_steps)
         e_kin_x = compute_kinetic_energy(self.xv, self.masses, self.random_velocs, self.kbT)  # :629
         e_kin_y = compute_kinetic_energy(yv, self.masses, self.random_velocs, self.kbT)  # :632
         e_pot_y = (self.energy(y) / self.kbT).squeeze(-1)  # :635
