@@ -131,3 +131,54 @@ def test_single_process_is_a_no_op():
     twd.GradientBuckets([p]).all_reduce()
     assert torch.equal(p.grad, torch.full((3,), 2.0))
     assert abs(float(twd.clip_grad_norm([p], 1.0)) - 12 ** 0.5) < 1e-6 and abs(float(p.grad.norm()) - 1.0) < 1e-4
+
+
+class _FlatGradModel(torch.nn.Module):
+    """Stand-in for the CUDA model's contract: after backward every gradient is a view of ONE flat buffer published as
+    `_last_flat_grad`; `unused` never receives a gradient (like the log_lengthscales a pass does not read)."""
+
+    def __init__(self):
+        super().__init__()
+        torch.manual_seed(0)
+        self.a = torch.nn.Parameter(torch.randn(3, 2))
+        self.b = torch.nn.Parameter(torch.randn(2))
+        self.unused = torch.nn.Parameter(torch.zeros(4))
+        self._last_flat_grad = None
+
+    def forward(self, x, y):
+        return (((x @ self.a + self.b) - y) ** 2).mean()
+
+
+def _flat_allreduce(rank, world):
+    model = _FlatGradModel()
+    g = torch.Generator().manual_seed(1)
+    X, Y = torch.randn(8, 3, generator=g), torch.randn(8, 2, generator=g)
+    lo, hi = twd.shard_range(8, rank, world)
+
+    def loss_fn(m, batch):  # autograd computes the gradients, then they are re-homed into one flat buffer
+        loss = m(batch["x"], batch["y"])
+        ga, gb = torch.autograd.grad(loss, [m.a, m.b])
+        flat = torch.cat([ga.reshape(-1), gb.reshape(-1)])
+        m.a.grad, m.b.grad = flat[:6].view(3, 2), flat[6:].view(2)
+        m._last_flat_grad = flat
+        return loss.detach().requires_grad_(True) * 1.0  # (its own backward is a no-op for the parameters)
+
+    trainer = twd.DataParallelTrainer(model, torch.optim.SGD([model.a, model.b], lr=0.1), loss_fn=loss_fn)
+    calls = []
+    orig = trainer.buckets.all_reduce
+    trainer.buckets.all_reduce = lambda *a, **k: (calls.append(1), orig(*a, **k))
+    trainer.step({"x": X[lo:hi], "y": Y[lo:hi]})
+    return [model.a.grad.clone(), model.b.grad.clone()], len(calls), model.unused.grad is None
+
+
+def test_flat_gradient_buffer_is_reduced_in_place():
+    """One collective over the flat buffer (no bucket copies), also when some parameters have no gradient on any rank."""
+    out = _run(_flat_allreduce)
+    model = _FlatGradModel()
+    g = torch.Generator().manual_seed(1)
+    X, Y = torch.randn(8, 3, generator=g), torch.randn(8, 2, generator=g)
+    model(X, Y).backward()
+    for grads, bucket_calls, unused_none in out:
+        assert bucket_calls == 0 and unused_none
+        torch.testing.assert_close(grads[0], model.a.grad, rtol=1e-5, atol=1e-7)
+        torch.testing.assert_close(grads[1], model.b.grad, rtol=1e-5, atol=1e-7)
