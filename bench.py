@@ -524,7 +524,9 @@ def run_ours(args):
             except Exception:
                 traffic = None
         step_flops = args.chains * 2 * V * f_atom(V)
-        cpu_val, cpu_cores, _ = time_cpu_reference(args.cpu_sample, 2, 1, weights=args.weights) if not args.no_cpu_baseline else (None, None, None)
+        # the CPU baseline is a reported side figure: rank 0 at N = 1 only (the reference arm carries it at every N)
+        run_cpu = not args.no_cpu_baseline and world == 1
+        cpu_val, cpu_cores, _ = time_cpu_reference(args.cpu_sample, 2, 1, weights=args.weights) if run_cpu else (None, None, None)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
