@@ -208,6 +208,9 @@ class MHChains:
         """Capture one iteration into a CUDA graph (torch.cuda.graph: the torch RNG draws stay graph-safe, outputs live
         in the graph's private pool).  `warmup` eager iterations run first so that every lazy initialisation (weight
         packing, workspace, kernel attributes) happens outside the capture.  Returns self."""
+        if self.openmm_on_current or self.openmm_on_proposal:
+            # the integrator's Philox offset advances on the host between calls: a replayed graph would reuse one noise stream
+            raise NotImplementedError("capture_graph is not available with integrator steps inside the chain")
         for _ in range(max(int(warmup), 1)):
             self.step()
         torch.cuda.synchronize()
