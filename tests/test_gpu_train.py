@@ -545,3 +545,43 @@ def test_acceptance_loss_matches_hand_composition():
             return float(losses.acceptance_loss(spec, m, Batch, device="cuda"))
 
     _check_first_order_decrease(m, float(loss.detach()), evaluate)
+
+
+def test_learnable_lengthscales_with_both_passes_in_one_graph():
+    """learnable_kernel with a sampling pass AND a density pass in one autograd graph (the AcceptanceLoss shape): the sampling
+    pass reads the LAST coupling layer's log_lengthscales, the density pass the FIRST one's, both through one shared buffer --
+    each backward must see its own pass's values.  Gradients of both against the oracle's fp64 autograd."""
+    torch.manual_seed(23)
+    B, V = 4, 24
+    x, xv = 0.25 * torch.randn(B, V, 3), torch.randn(B, V, 3)
+    at = torch.randint(0, 5, (B, V))
+    mask = torch.zeros(B, V, dtype=torch.bool)
+    eps_c, eps_v = torch.randn(1, B, V, 3), torch.randn(1, B, V, 3)
+    G1, g3 = torch.randn(B, V, 3), torch.randn(B) / V
+    m, sd = build_model(FULL_L, "bf16x3", 9)
+    m.train()
+    m.zero_grad(set_to_none=True)
+    kw = dict(adj_list=EMPTY_ADJ.cuda(), edge_batch_idx=EMPTY_EBI.cuda())
+    zc = eps_c.cuda() * torch.exp(m.coords_prior_log_scale)
+    zv = eps_v.cuda() * torch.exp(m.velocs_prior_log_scale)
+    yc, yv, lp = m.sample_from_latents(at.cuda(), x.cuda(), xv.cuda(), mask.cuda(), zc, zv)
+    ll = m.log_likelihood(atom_types=at.cuda(), x_coords=yc[0], x_velocs=yv[0], y_coords=x.cuda(), y_velocs=xv.cuda(), masked_elements=mask.cuda(), **kw)
+    loss = (yc[0] * G1.cuda()).sum() + ((lp[0] - ll) * g3.cuda()).sum()
+    loss.backward()
+    first = "flow.chain.0.scale_transformer.encoder_layers.0.self_attn.attention.log_lengthscales"
+    last = "flow.chain.7.scale_transformer.encoder_layers.0.self_attn.attention.log_lengthscales"
+    got = {k: p.grad.detach().cpu().double() for k, p in m.named_parameters() if p.grad is not None}
+    assert sorted(k for k in got if k.endswith("log_lengthscales")) == sorted([first, last])
+    leaves = {k: v.double().clone().requires_grad_(not k.endswith(".lengthscales")) for k, v in sd.items()}
+    zc64 = eps_c.double() * torch.exp(leaves["coords_prior_log_scale"])
+    zv64 = eps_v.double() * torch.exp(leaves["velocs_prior_log_scale"])
+    ryc, ryv, rlp = fo.conditional_sample_with_logp(leaves, FULL_L, at, x.double(), xv.double(), mask, 1, zc64, zv64, distance_mode="direct_sq")
+    rll = fo.log_likelihood(leaves, FULL_L, at, ryc[0], ryv[0], x.double(), xv.double(), mask, distance_mode="direct_sq")
+    rloss = (ryc[0] * G1.double()).sum() + ((rlp[0] - rll) * g3.double()).sum()
+    assert abs(float(loss.detach()) - float(rloss.detach())) < 1e-4 * max(1.0, abs(float(rloss.detach())))
+    keys = [first, last, "flow.chain.3.shift_transformer.encoder_layers.1.self_attn.values_proj.weight", "coords_prior_log_scale"]
+    ref = dict(zip(keys, torch.autograd.grad(rloss, [leaves[k] for k in keys])))
+    assert float((ref[first] - ref[last]).abs().max()) > 1e-6  # the two lengthscale gradients differ: a mix-up would show
+    for k in keys:
+        err = float((got[k] - ref[k]).norm() / ref[k].norm().clamp_min(1e-12))
+        assert err < 2 * GRAD_RTOL, (k, err, got[k], ref[k])

@@ -88,6 +88,9 @@ class _LogLikelihoodFn(torch.autograd.Function):
         )  # fmt: skip
         ctx.model, ctx.tape, ctx.sizes = model, tape, (B, V, tape_b.value, ws_b.value)
         ctx.packed_key = model._packed[2]
+        # learnable_kernel: the table points at ONE buffer that every pass overwrites with its own lengthscales (density: first
+        # coupling layer, sampling: last); a loss with both passes in its graph must see each pass's values in its backward
+        ctx.ls_eff = model._ls_eff.clone() if model._learnable else None
         ctx.save_for_backward(atom_types, x_velocs, mask_u8)
         return out
 
@@ -101,6 +104,8 @@ class _LogLikelihoodFn(torch.autograd.Function):
         # (the re-pack epoch may differ: an inference call in between re-packs the same parameters into the same buffer)
         if model._packed is None or (model._packed[2][0], model._packed[2][2]) != (ctx.packed_key[0], ctx.packed_key[2]):
             raise _lib.TimewarpB200Error("parameters were modified between the forward and the backward pass")
+        if ctx.ls_eff is not None:
+            model._ls_eff.copy_(ctx.ls_eff)
         tensors, views, grads, gtable, ls_slot, ls_grad = _gradient_table(model, dev, ctx.n_extra == 1 and ctx.needs_input_grad[-1])
         table = model._param_table(dev)
         ws = torch.empty(ws_b + 1024, dtype=torch.uint8, device=dev)
@@ -174,6 +179,7 @@ class _SampleFn(torch.autograd.Function):
         )  # fmt: skip
         ctx.model, ctx.tape, ctx.sizes = model, tape, (B, V, tape_b.value, ws_b.value)
         ctx.packed_key = model._packed[2]
+        ctx.ls_eff = model._ls_eff.clone() if model._learnable else None  # (see _LogLikelihoodFn.forward)
         ctx.save_for_backward(atom_types, x_velocs, mask_u8)
         return y_coords, y_velocs, delta
 
@@ -186,6 +192,8 @@ class _SampleFn(torch.autograd.Function):
         B, V, tape_b, ws_b = ctx.sizes
         if model._packed is None or (model._packed[2][0], model._packed[2][2]) != (ctx.packed_key[0], ctx.packed_key[2]):
             raise _lib.TimewarpB200Error("parameters were modified between the forward and the backward pass")
+        if ctx.ls_eff is not None:
+            model._ls_eff.copy_(ctx.ls_eff)
         tensors, views, grads, gtable, ls_slot, ls_grad = _gradient_table(model, dev, ctx.n_extra == 1 and ctx.needs_input_grad[-1])
         table = model._param_table(dev)
         ws = torch.empty(ws_b + 1024, dtype=torch.uint8, device=dev)
