@@ -3,6 +3,7 @@ pairing (tests/golden/make_golden.py::dataloader_case)."""
 import os
 
 import numpy as np
+import pytest
 import torch
 
 from timewarp_b200 import dataloader as dl
@@ -68,3 +69,42 @@ def test_pdb_topology_reader(tmp_path):
     assert topo.atom_names == ad.atom_names and topo.residue_names == ad.residue_names
     np.testing.assert_allclose(topo.coords_nm, ad.coords_nm, atol=1e-4)
     assert np.array_equal(topo.bonds, ad.bonds) and np.array_equal(topo.atom_types, ad.atom_types)
+
+
+def test_raw_moldyn_dataset_directory(tmp_path, capsys):
+    """RawMolDynDataset (datasets/iterable_datasets.py:21-129) over a directory with one complete trajectory, one without its
+    npz and one corrupt one: names, graceful skipping, datapoints identical to the direct loader, collate-ready."""
+    import shutil
+    from timewarp_b200 import datasets as ds
+
+    ad = alanine_dipeptide()
+    lines = []
+    for i, (n, r, ri, xyz) in enumerate(zip(ad.atom_names, ad.residue_names, ad.residue_index, ad.coords_nm * 10.0)):
+        el = next(c for c in n if c.isalpha())
+        lines.append("ATOM  %5d %-4s %3s A%4d    %8.3f%8.3f%8.3f  1.00  0.00          %2s" % (i + 1, n if len(n) == 4 else " " + n, r, ri, *xyz, el))
+    pdb = "\n".join(lines + ["TER", "END"]) + "\n"
+    for name in ("good", "lonely", "broken"):
+        (tmp_path / f"{name}-traj-state0.pdb").write_text(pdb)
+    src = os.path.join(GOLDEN, "synthetic_ad-traj-arrays.npz")
+    shutil.copy(src, tmp_path / "good-traj-arrays.npz")
+    d = dict(np.load(src))
+    d["positions"] = d["positions"].copy()
+    d["positions"][1] += 1000.0  # a jump no integrator step makes
+    np.savez(tmp_path / "broken-traj-arrays.npz", **d)
+    (tmp_path / "notes.txt").write_text("ignored")
+    data = ds.RawMolDynDataset(data_dir=str(tmp_path), step_width=1)
+    assert ds.get_pdb_names(tmp_path) == ["broken", "good", "lonely"] and data.pdb_names == ("broken", "good", "lonely")
+    points = list(data.make_iterator(data.pdb_names))
+    out = capsys.readouterr().out
+    assert "W: lonely data not fully present." in out and "W: broken trajectory has" in out
+    want = dl.datapoints_from_trajectory(dl.load_pdb_trace_data("good", ad, src, step_width=1))
+    assert len(points) == len(want) > 0 and all(p.name == "good" for p in points)
+    for a, b in zip(points, want):
+        assert torch.equal(a.atom_coords, b.atom_coords) and torch.equal(a.atom_coord_targets, b.atom_coord_targets)
+        assert torch.equal(a.atom_types, b.atom_types) and torch.equal(a.adj_list, b.adj_list)
+    batch = dl.moldyn_dense_collate_fn(points[:3])
+    assert batch.atom_coords.shape == (3, 22, 3)
+    with pytest.raises(RuntimeError, match="unexpected exception"):
+        (tmp_path / "bad-traj-state0.pdb").write_text(pdb)
+        (tmp_path / "bad-traj-arrays.npz").write_text("not an npz")
+        list(ds.RawMolDynDataset(str(tmp_path), 1).make_iterator(["bad"]))

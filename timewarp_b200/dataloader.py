@@ -138,6 +138,10 @@ def read_pdb_topology(path: str, name: Optional[str] = None) -> Peptide:
     return Peptide(name or path, names, resn, resi, coords, _build_bonds(names, resn, resi))
 
 
+class CoordDeltaTooBig(ValueError):
+    """dataloader.py: a conditioning/target pair further apart than any physical step (corrupt trajectory)."""
+
+
 def load_pdb_trace_data(name: str, state0_file, traj_file: str, step_width: int = 1,
                         equal_data_spacing: bool = False) -> TrajectoryInformation:
     """dataloader.py:212-276: conditioning/target pairs (step, step + step_width) of one `*-traj-arrays.npz` trajectory.
@@ -164,7 +168,7 @@ def load_pdb_trace_data(name: str, state0_file, traj_file: str, step_width: int 
             continue
         delta = float(np.sqrt(np.sum((pos - nxt[0]) ** 2)))
         if delta > 100:
-            raise ValueError(f"{name} trajectory has {delta:g} distance between steps {step} and {step + step_width}")
+            raise CoordDeltaTooBig(f"{name} trajectory has {delta:g} distance between steps {step} and {step + step_width}")
         out.coord_features.append(pos), out.veloc_features.append(vel), out.force_features.append(frc)
         out.coord_targets.append(nxt[0]), out.veloc_targets.append(nxt[1]), out.force_targets.append(nxt[2])
     return out
