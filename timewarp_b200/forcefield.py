@@ -14,7 +14,7 @@ sets can be supplied by filling a SystemDescription directly.
 from __future__ import annotations
 
 import math
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from typing import Dict, List, Tuple
 
 import numpy as np

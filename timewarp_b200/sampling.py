@@ -13,10 +13,9 @@ available (no OpenMM) and raise if requested.
 """
 from __future__ import annotations
 
-import math
 import pickle
 from dataclasses import astuple, dataclass
-from typing import Optional, Tuple
+from typing import Optional
 
 import numpy as np
 import torch
