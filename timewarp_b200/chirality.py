@@ -36,6 +36,8 @@ def _run(coords: Tensor, centers: Tensor, ref_signs, want_signs: bool):
     signs = torch.empty(B, C_, dtype=torch.float32, device=x.device) if want_signs else None
     changed = torch.empty(B, dtype=torch.uint8, device=x.device) if ref_signs is not None else None
     ref = ref_signs.to(device=x.device, dtype=torch.float32).reshape(-1).contiguous() if ref_signs is not None else None
+    # one reference sign per centre (the reference's [1, C] row, utils/chirality.py:65-80); per-chain rows are not supported
+    assert ref is None or ref.numel() == C_, f"reference_signs must hold one sign per centre ({C_}), got shape {tuple(ref_signs.shape)}"
     _lib.check(
         _lib.load().tw_chirality(_lib.ptr(x), _lib.ptr(c) if C_ else None, _lib.ptr(ref) if (ref is not None and C_) else None,
                                  B, V, C_, _lib.ptr(changed), _lib.ptr(signs), torch.cuda.current_stream(x.device).cuda_stream),

@@ -5,6 +5,8 @@
 #include <stdio.h>
 #include <stdarg.h>
 
+#include <atomic>
+
 #include "../../include/timewarp_b200.h"
 
 namespace tw {
@@ -49,6 +51,26 @@ struct ProfScope {
     int _s = (call);          \
     if (_s != TW_OK) return _s; \
   } while (0)
+
+// Function attributes (the opt-in to > 48 KB of dynamic shared memory) are per device: one flag per device ordinal, so
+// that a process driving several GPUs sets them on each.  The attribute calls are idempotent, so two host threads
+// racing through the first call are harmless; the flag is published only after the attributes are set.
+struct DeviceOnce {
+  std::atomic<uint64_t> bits[4] = {};
+  static int dev() {
+    int d = 0;
+    cudaGetDevice(&d);
+    return d & 255;
+  }
+  bool done() const {
+    const int d = dev();
+    return (bits[d >> 6].load(std::memory_order_acquire) >> (d & 63)) & 1u;
+  }
+  void mark() {
+    const int d = dev();
+    bits[d >> 6].fetch_or(1ull << (d & 63), std::memory_order_release);
+  }
+};
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 

@@ -403,11 +403,11 @@ extern "C" int tw_peptide_energy(const tw_energy_system* sys, const float* coord
   TW_CHECK_ARG(!sys->use_gb || (sys->gb_radius && sys->gb_scale), "GB arrays missing");
   TW_CHECK_ARG(!out_forces || sys->n_atoms <= 2048, "forces: n_atoms out of range (1..2048)");
   size_t smem = (size_t)sys->n_atoms * (out_forces ? 9 : 4) * sizeof(double);
-  static bool attr_set = false;
-  if (smem > 48 * 1024 && !attr_set) {
+  static DeviceOnce attr_set;
+  if (smem > 48 * 1024 && !attr_set.done()) {
     TW_CUDA(cudaFuncSetAttribute(k_energy<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * 4 * (int)sizeof(double)));
     TW_CUDA(cudaFuncSetAttribute(k_energy<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2048 * 9 * (int)sizeof(double)));
-    attr_set = true;
+    attr_set.mark();
   }
   {
     ProfScope prof(PROF_ENERGY, (cudaStream_t)stream);
@@ -443,11 +443,11 @@ extern "C" int tw_langevin_steps(const tw_energy_system* sys, float* coords, flo
   TW_CHECK_ARG(B >= 0 && B <= 2147483647LL, "bad batch size");
   TW_CHECK_ARG(sys->n_atoms <= 1536, "integrator: n_atoms out of range (1..1536)");
   const size_t smem = (size_t)sys->n_atoms * 13 * sizeof(double);
-  static bool attr_set = false;
-  if (smem > 48 * 1024 && !attr_set) {
+  static DeviceOnce attr_set;
+  if (smem > 48 * 1024 && !attr_set.done()) {
     TW_CUDA(cudaFuncSetAttribute(k_langevin<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 1536 * 13 * (int)sizeof(double)));
     TW_CUDA(cudaFuncSetAttribute(k_langevin<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 1536 * 13 * (int)sizeof(double)));
-    attr_set = true;
+    attr_set.mark();
   }
   const double vscale = exp(-timestep * friction);
   const double fscale = friction == 0 ? timestep : (1.0 - vscale) / friction;

@@ -289,10 +289,10 @@ int launch_local_attn(const float* qkv0, const float* qkv1, float* o0, float* o1
   if (n == 0) return TW_OK;
   const size_t smem = ((size_t)2 * V * D + (size_t)V * 3 + (size_t)4 * V) * sizeof(float);
   TW_CHECK_ARG(smem <= 200 * 1024, "local attention: V * d_model too large for shared memory (V=%d)", V);
-  static bool attr_done = false;
-  if (!attr_done) {
+  static DeviceOnce attr_done;
+  if (!attr_done.done()) {
     TW_CUDA(cudaFuncSetAttribute(k_local_attn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_done = true;
+    attr_done.mark();
   }
   dim3 grid((unsigned)n, H, nets);
   k_local_attn<<<grid, 128, smem, st>>>(qkv0, qkv1, o0, o1, n_cond, V, H, D, xc, mask, max_radius, 1.0f / sqrtf((float)D));

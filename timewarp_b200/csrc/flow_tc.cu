@@ -1249,16 +1249,16 @@ void tc_set_trace(int cls, long long* buf) {
 static int launch_ffn_tc(const tw_flow_config* c, const FfnArgs& a_in, cudaStream_t st) {
   FfnArgs a = a_in;
   a.trace = g_ffn_trace;
-  static bool attr_done = false;
+  static DeviceOnce attr_done;
   static int use_pair = 1;
-  if (!attr_done) {
+  if (!attr_done.done()) {
     TW_CUDA(cudaFuncSetAttribute(k_ffn_tc<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, FfnSmem::TOTAL + 1024));
     TW_CUDA(cudaFuncSetAttribute(k_ffn_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FfnSmem::TOTAL + 1024));
     TW_CUDA(cudaFuncSetAttribute(k_ffn_pair<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, FfnPairSmem::TOTAL + 1024));
     TW_CUDA(cudaFuncSetAttribute(k_ffn_pair<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FfnPairSmem::TOTAL + 1024));
     const char* e = getenv("TW_FFN_PAIR");  // bring-up switch: 0 = single-CTA kernel
     use_pair = e ? atoi(e) : 1;
-    attr_done = true;
+    attr_done.mark();
   }
   TW_CHECK_ARG(a.F <= 4096, "dim_feedforward > 4096 not supported by the tensor-core FFN");
   const int sms = 148;
@@ -2880,10 +2880,10 @@ int tc_begin_pass_direct(const tw_flow_config* c, TcScratch& tc, const float* xc
   if (tc.ffn_tail && clear_tail) TW_CUDA(cudaMemsetAsync(tc.ffn_tail, 0, kFfnTailBytes, st));
   const int VP = pad16(V);
   const size_t smem = (((size_t)V * 12 + 15) & ~(size_t)15) + (((size_t)V + 15) & ~(size_t)15) + (size_t)VP * VP * 4;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static DeviceOnce attr_done;
+  if (!attr_done.done()) {
     TW_CUDA(cudaFuncSetAttribute(k_scores_direct_img, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 128 * 4 + 4096));
-    attr_done = true;
+    attr_done.mark();
   }
   if (n_cond < 1) return TW_OK;
   k_scores_direct_img<<<dim3((unsigned)n_cond, (unsigned)c->num_heads), 256, smem, st>>>(xc, mask, lengthscales, V, VP, c->num_heads, tc.scores_img, cheb,
@@ -2901,17 +2901,17 @@ size_t tc_mixed_img_bytes(const tw_flow_config* c, int64_t M) { return (size_t)(
 // mixed_h = A_h x for every head, written as A-operand images (both networks)
 int tc_mix(const tw_flow_config* c, const float* const x[2], uint8_t* const img[2], const uint8_t* scores_img, int64_t n,
            int64_t n_cond, int V, cudaStream_t st, int nets) {
-  static bool attr_done = false;
+  static DeviceOnce attr_done;
   const int VP = pad16(V), H = c->num_heads;
   const uint32_t stage_stride = (uint32_t)((2 * VP * VP * 2 + 1023) & ~1023);
   const int mix_stages = VP > 96 ? 2 : 3;
   const int mix_groups = VP > 96 ? 1 : 2;  // epilogue groups (a second staging buffer must fit next to the ring)
   const int mix_smem = mix_stages * stage_stride + mix_groups * VP * 512 + 256 + 1024;
-  if (!attr_done) {
+  if (!attr_done.done()) {
     TW_CUDA(cudaFuncSetAttribute(k_mix_tc<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 65536 + 2048));
     TW_CUDA(cudaFuncSetAttribute(k_mix_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 65536 + 2048));
     static_assert(2 * 65536 + 128 * 512 + 2048 <= 3 * 65536 + 2048, "mix smem budget");
-    attr_done = true;
+    attr_done.mark();
   }
   MixArgs a{};
   for (int s = 0; s < 2; s++) a.x[s] = x[s], a.img[s] = img[s];
@@ -2953,7 +2953,7 @@ int tc_mix(const tw_flow_config* c, const float* const x[2], uint8_t* const img[
 // out = LN1(x + attention(x)) for both networks of encoder layer t; `pre` (optional) receives the pre-LayerNorm sum
 int tc_attention_layer(const tw_flow_config* c, const ParamView& pv, int k, int t, const TcScratch& tc, float* const x_in[2],
                        float* const out_in[2], int64_t n, int64_t n_cond, int V, cudaStream_t st, float* const* pre, int only_net) {
-  static bool attr_done = false;
+  static DeviceOnce attr_done;
   const int H = c->num_heads;
   // only_net >= 0: run ONE network (its pointers in both slots, grid.y = 1) -- chebyshev_kernel attention has a different
   // score image per network and layer, written to tc.scores_img right before this call
@@ -2963,10 +2963,10 @@ int tc_attention_layer(const tw_flow_config* c, const ParamView& pv, int k, int 
   float* const out[2] = {out_in[net_of[0]], out_in[net_of[1]]};
   const int per_net = nets == 1 ? 148 : 74;
   const int proj_smem = kProjStages * kProjStageBytes + 1024 + 256 + 1024;
-  if (!attr_done) {
+  if (!attr_done.done()) {
     TW_CUDA(cudaFuncSetAttribute(k_proj_tc<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, proj_smem));
     TW_CUDA(cudaFuncSetAttribute(k_proj_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, proj_smem));
-    attr_done = true;
+    attr_done.mark();
   }
   TcLayout L = TcLayout::make(c);
   const int64_t M = n * V;
@@ -3069,11 +3069,11 @@ int tc_ffn_layer(const tw_flow_config* c, const ParamView& pv, int k, int t, con
 
 int tc_in_mlp(const tw_flow_config* c, const ParamView& pv, int k, const TcScratch& tc, const int64_t* atom_types, const float* xc,
               const float* xv, const float* z_other, float* const out[2], int64_t n, int64_t n_cond, int V, cudaStream_t st) {
-  static bool attr_done = false;
-  if (!attr_done) {
+  static DeviceOnce attr_done;
+  if (!attr_done.done()) {
     TW_CUDA(cudaFuncSetAttribute(k_in_mlp_tc<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, InMlpSmem::TOTAL + 1024));
     TW_CUDA(cudaFuncSetAttribute(k_in_mlp_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, InMlpSmem::TOTAL + 1024));
-    attr_done = true;
+    attr_done.mark();
   }
   TcLayout L = TcLayout::make(c);
   InMlpArgs a{};
@@ -3099,11 +3099,11 @@ int tc_in_mlp(const tw_flow_config* c, const ParamView& pv, int k, const TcScrat
 
 int tc_out_mlp(const tw_flow_config* c, const ParamView& pv, int k, const TcScratch& tc, float* const x[2], float* const out[2],
                int64_t M, cudaStream_t st) {
-  static bool attr_done = false;
-  if (!attr_done) {
+  static DeviceOnce attr_done;
+  if (!attr_done.done()) {
     TW_CUDA(cudaFuncSetAttribute(k_out_mlp_tc<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, OutMlpSmem::TOTAL + 1024));
     TW_CUDA(cudaFuncSetAttribute(k_out_mlp_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, OutMlpSmem::TOTAL + 1024));
-    attr_done = true;
+    attr_done.mark();
   }
   TcLayout L = TcLayout::make(c);
   OutMlpArgs a{};

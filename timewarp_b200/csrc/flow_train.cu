@@ -244,12 +244,12 @@ __global__ void __launch_bounds__(192, 1) k_gemm_img(GemmArgs a) {
 }
 
 static int launch_gemm(const tw_flow_config* c, GemmArgs& a, cudaStream_t st) {
-  static bool attr_done = false;
+  static DeviceOnce attr_done;
   const int smem = kGemmStages * kGemmStageBytes + 256 + 1024;
-  if (!attr_done) {
+  if (!attr_done.done()) {
     TW_CUDA(cudaFuncSetAttribute(k_gemm_img<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     TW_CUDA(cudaFuncSetAttribute(k_gemm_img<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_done = true;
+    attr_done.mark();
   }
   TW_CHECK_ARG(a.bn == 128 || a.bn == 64, "gemm: bn must be 64 or 128");
   TW_CHECK_ARG(a.mode != GEMM_NN_HEADED || (a.tiles_n == 1 && a.bn == 128), "gemm: headed mode has one column tile");
@@ -1455,10 +1455,10 @@ static int begin_backward(BwdCtx& x, const tw_flow_config* cfg, const void* cons
   x.dls = x.gv.enc(0, 0, 0, 1);
   if (x.pv.chebyshev()) {
     TW_CHECK_ARG(!x.dls && !x.want_inputs, "chebyshev_kernel: gradients w.r.t. lengthscales / conditioning state are not built");
-    static bool attr_cheb = false;
-    if (!attr_cheb) {
+    static DeviceOnce attr_cheb;
+    if (!attr_cheb.done()) {
       TW_CUDA(cudaFuncSetAttribute(k_score_grad, cudaFuncAttributeMaxDynamicSharedMemorySize, (128 * 129 + 4 * 128) * (int)sizeof(float)));
-      attr_cheb = true;
+      attr_cheb.mark();
     }
   }
   if (x.want_inputs) {
@@ -1468,10 +1468,10 @@ static int begin_backward(BwdCtx& x, const tw_flow_config* cfg, const void* cons
   if (x.dls || x.want_inputs) {
     TW_CHECK_ARG(cfg->num_heads * 128 <= (cfg->dim_feedforward > 256 ? cfg->dim_feedforward : 256),
                  "lengthscale gradient: H * 128 exceeds the [M, dim_feedforward] scratch");
-    static bool attr_done = false;
-    if (!attr_done) {
+    static DeviceOnce attr_done;
+    if (!attr_done.done()) {
       TW_CUDA(cudaFuncSetAttribute(k_score_grad, cudaFuncAttributeMaxDynamicSharedMemorySize, (128 * 129 + 4 * 128) * (int)sizeof(float)));
-      attr_done = true;
+      attr_done.mark();
     }
     TW_CUDA(cudaMemsetAsync(x.b.sgrad, 0, (size_t)B * cfg->num_heads * V * V * sizeof(float), x.st));
   }

@@ -172,6 +172,8 @@ def clip_grad_norm(params: Iterable[Tensor], max_norm: float) -> Tensor:
     """Global L2 clipping on the (already averaged) gradients -- DeepSpeed's `gradient_clipping`
     (train_deepspeed.py:116-117; 0.0 / None disables it)."""
     grads = [p.grad for p in params if p.grad is not None]
+    if not grads:  # nothing to clip (e.g. a step before any backward)
+        return torch.zeros(())
     total = torch.sqrt(sum((g.detach().float() ** 2).sum() for g in grads))
     if max_norm and max_norm > 0:
         scale = torch.clamp(max_norm / (total + 1e-6), max=1.0)

@@ -101,6 +101,9 @@ class _LogLikelihoodFn(torch.autograd.Function):
         atom_types, x_velocs, mask_u8 = ctx.saved_tensors
         dev = x_velocs.device
         B, V, tape_b, ws_b = ctx.sizes
+        if ctx.tape is None:
+            raise _lib.TimewarpB200Error("backward ran twice over the same graph: the activation tape is released after the first "
+                                         "backward (retain_graph=True is not supported)")
         # (the re-pack epoch may differ: an inference call in between re-packs the same parameters into the same buffer)
         if model._packed is None or (model._packed[2][0], model._packed[2][2]) != (ctx.packed_key[0], ctx.packed_key[2]):
             raise _lib.TimewarpB200Error("parameters were modified between the forward and the backward pass")
@@ -190,6 +193,9 @@ class _SampleFn(torch.autograd.Function):
         atom_types, x_velocs, mask_u8 = ctx.saved_tensors
         dev = x_velocs.device
         B, V, tape_b, ws_b = ctx.sizes
+        if ctx.tape is None:
+            raise _lib.TimewarpB200Error("backward ran twice over the same graph: the activation tape is released after the first "
+                                         "backward (retain_graph=True is not supported)")
         if model._packed is None or (model._packed[2][0], model._packed[2][2]) != (ctx.packed_key[0], ctx.packed_key[2]):
             raise _lib.TimewarpB200Error("parameters were modified between the forward and the backward pass")
         if ctx.ls_eff is not None:

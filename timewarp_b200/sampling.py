@@ -81,6 +81,8 @@ def compute_kinetic_energy(velocs: Tensor, masses: Optional[Tensor], random_velo
     else:
         assert kbT, "Requires kbT to compute energy"
         m, inv = masses.to(device=v.device, dtype=torch.float32).contiguous(), 1.0 / kbT
+        # the kernel reads one mass per atom; the reference also broadcasts [B, V] masses (evaluation_utils.py:434)
+        assert m.numel() == V, f"compute_kinetic_energy: masses must hold one entry per atom ({V}), got shape {tuple(masses.shape)}"
     _lib.check(_lib.load().tw_kinetic_energy(_lib.ptr(v), _lib.ptr(m), inv, B, V, _lib.ptr(out), _stream(v.device)), "tw_kinetic_energy")
     return out
 
@@ -95,15 +97,21 @@ def mh_accept(e_pot_x, e_pot_y, e_kin_x, e_kin_y, p_xy, p_yx, u, x_coords=None, 
     pa = torch.empty(n, dtype=torch.float32, device=dev)
     acc = torch.empty(n, dtype=torch.uint8, device=dev)
     first = torch.empty(1, dtype=torch.int32, device=dev) if want_first else None
-    f = lambda t: _lib.ptr(t.to(torch.float32).contiguous()) if t is not None else None  # noqa: E731
-    for t in (x_coords, x_velocs):
+    for t in (x_coords, x_velocs):  # updated in place: no converted copy possible
         assert t is None or (t.is_contiguous() and t.dtype == torch.float32)
+    # converted inputs are held in `keep` until the launch has been enqueued: a temporary freed right after data_ptr()
+    # could be handed to the next conversion by the caching allocator (e.g. fp64 energies of fp64 coordinates)
+    keep = [None if t is None else t.to(torch.float32).contiguous()
+            for t in (e_pot_x, e_pot_y, e_kin_x, e_kin_y, p_xy, p_yx, u, y_coords, y_velocs)]
+    for t in keep[:7]:
+        assert t is not None and t.numel() == n, "mh_accept: every energy / density / uniform needs one entry per proposal"
+    p = [_lib.ptr(t) for t in keep]
     _lib.check(
-        _lib.load().tw_mh_accept(f(e_pot_x), f(e_pot_y), f(e_kin_x), f(e_kin_y), f(p_xy), f(p_yx), f(u), n, V,
-                                 _lib.ptr(x_coords), _lib.ptr(x_velocs), f(y_coords), f(y_velocs), _lib.ptr(ex), _lib.ptr(pa),
-                                 _lib.ptr(acc), _lib.ptr(first), _stream(dev)),
+        _lib.load().tw_mh_accept(p[0], p[1], p[2], p[3], p[4], p[5], p[6], n, V, _lib.ptr(x_coords), _lib.ptr(x_velocs), p[7], p[8],
+                                 _lib.ptr(ex), _lib.ptr(pa), _lib.ptr(acc), _lib.ptr(first), _stream(dev)),
         "tw_mh_accept",
     )
+    del keep
     return ex, pa, acc, first
 
 
