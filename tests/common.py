@@ -64,3 +64,29 @@ def build_model(o: fo.OracleConfig, precision: str, weight_seed: int = 0, device
 
 EMPTY_ADJ = torch.zeros(0, 2, dtype=torch.long)
 EMPTY_EBI = torch.zeros(0, dtype=torch.long)
+
+
+def proposal_weights(sd, n_hidden: int = 1):
+    """The bench's "proposal" weight set (bench.py::bench_state_dict): the same synthetic tensors with the last layer of every
+    out_mlp scaled by 1e-5 and the prior scales (5e-4 nm, 1) -- a near-identity flow whose proposals are local moves, so both
+    branches of the MH rule are exercised."""
+    sd = dict(sd)
+    last = 2 * n_hidden
+    for k in list(sd):
+        if f".out_mlp._layers.{last}." in k:
+            sd[k] = sd[k] * 1e-5
+    sd["coords_prior_log_scale"] = torch.tensor(float(np.log(5e-4)))
+    sd["velocs_prior_log_scale"] = torch.tensor(0.0)
+    return sd
+
+
+class CudaReplayDraws:
+    """`draws` object for oracle/mh_oracle.py that takes every draw from the CUDA default generator (same calls, same
+    shapes, same order as the product code), so that after `torch.manual_seed(s)` the oracle replays the stream the product
+    consumed after the same seed."""
+
+    def randn(self, shape):
+        return torch.randn(tuple(shape), device="cuda").cpu()
+
+    def rand(self, n):
+        return torch.rand(n, device="cuda").cpu()
