@@ -92,6 +92,26 @@ def synthetic_chains(pep, n_chains, seed):
     return x, at, mask
 
 
+def workload_config(args, energy_name):
+    """`config` of the JSON line: describes the WORKLOAD only, so that both arms (ours / reference) print the same dict."""
+    V = 65
+    return {"workload": f"mh_2olx65_chains{args.chains}_per_gpu", "atoms": V, "chains_per_gpu": args.chains,
+            "model": f"kernel_transformer_nvp (35.97M params, synthetic weights: {args.weights})",
+            "energy": energy_name,
+            "l2": "working set per step (activations+workspace) >> 126 MB L2; no explicit flush",
+            "algorithmic_tflops_per_step": args.chains * 2 * V * f_atom(V) / 1e12}
+
+
+def bench_system(pep):
+    """The potential-energy system of the benchmark peptide: the ff99SB-ILDN + OBC2 table pinned to the reference's golden
+    energies when the product has it (forcefield.amber99sbildn_obc2), else the synthetic Amber-like parameters."""
+    from timewarp_b200 import forcefield as ff
+
+    if hasattr(ff, "amber99sbildn_obc2") and getattr(ff, "AMBER99SBILDN_PINNED", False):
+        return ff.amber99sbildn_obc2(pep), "ff99SB-ILDN + GB-OBC2 (pinned to the reference's golden 2olx energies)"
+    return ff.amber_like_system(pep), "synthetic Amber-like + GB-OBC2"
+
+
 def bench_state_dict(src, mode):
     """Synthetic weights of the full architecture.  `src` is the product model (GPU arm: timewarp_b200.synthetic) or an
     oracle config (CPU-baseline / reference arm: oracle.flow_oracle) -- the two generators give identical tensors
@@ -121,19 +141,28 @@ def bench_state_dict(src, mode):
 
 
 # --------------------------------------------------------------------------------------------
-def cpu_reference_iteration(sd, o, sysd, kbT, x, at, mask, gen):
-    """One MH iteration on the CPU through the oracle port of the reference path (flow in torch fp32
-    on all host threads + fp64 numpy energy): evaluation_utils.py:589-668."""
+def cpu_reference_iteration(flow, sd, o, sysd, kbT, x, at, mask, gen):
+    """One MH iteration on the CPU, evaluation_utils.py:589-668 with one proposal per chain.  `flow` is the UNMODIFIED
+    reference model (oracle/_ref, byte-compiled from /root/reference by oracle/build_ref.py) driven through its public
+    `conditional_sample_with_logp` / `log_likelihood` (the default torch generator supplies its latents), or None: the
+    oracle port of the same arithmetic (oracle/flow_oracle.py).  Energies: the fp64 numpy port (OpenMM is not installable
+    offline)."""
     from oracle import energy_oracle as eo
     from oracle import flow_oracle as fo
 
     n = x.shape[0]
     xv = torch.randn(x.shape, generator=gen)
-    zc = torch.randn((1,) + tuple(x.shape), generator=gen) * torch.exp(sd["coords_prior_log_scale"])
-    zv = torch.randn((1,) + tuple(x.shape), generator=gen) * torch.exp(sd["velocs_prior_log_scale"])
     with torch.no_grad():
-        yc, yv, p_xy = fo.conditional_sample_with_logp(sd, o, at, x, xv, mask, 1, zc, zv)
-        p_yx = fo.log_likelihood(sd, o, at, yc[0], yv[0], x, xv, mask)
+        if flow is not None:
+            kw = dict(atom_types=at, adj_list=torch.zeros(0, 2, dtype=torch.long), edge_batch_idx=torch.zeros(0, dtype=torch.long),
+                      masked_elements=mask)
+            yc, yv, p_xy = flow.conditional_sample_with_logp(x_coords=x, x_velocs=xv, num_samples=1, **kw)
+            p_yx = flow.log_likelihood(x_coords=yc[0], x_velocs=yv[0], y_coords=x, y_velocs=xv, **kw)
+        else:
+            zc = torch.randn((1,) + tuple(x.shape), generator=gen) * torch.exp(sd["coords_prior_log_scale"])
+            zv = torch.randn((1,) + tuple(x.shape), generator=gen) * torch.exp(sd["velocs_prior_log_scale"])
+            yc, yv, p_xy = fo.conditional_sample_with_logp(sd, o, at, x, xv, mask, 1, zc, zv)
+            p_yx = fo.log_likelihood(sd, o, at, yc[0], yv[0], x, xv, mask)
     e_x = torch.from_numpy(eo.potential_energy(sysd, x.numpy().astype(np.float64))).float() / kbT
     e_y = torch.from_numpy(eo.potential_energy(sysd, yc[0].numpy().astype(np.float64))).float() / kbT
     e_kin = 0.5 * (yv[0] ** 2).sum((-1, -2)) - 0.5 * (xv**2).sum((-1, -2))
@@ -143,26 +172,44 @@ def cpu_reference_iteration(sd, o, sysd, kbT, x, at, mask, gen):
 
 
 def time_cpu_reference(sample_chains, iters, warmup, seed=0, weights="proposal"):
+    """Times the CPU path on all host threads.  Returns a dict: value (proposals/s), cores, ms per iteration, kind, sample."""
     from oracle import flow_oracle as fo
-    from timewarp_b200.forcefield import MOLAR_GAS_CONSTANT_R, amber_like_system
+    from oracle import ref_flow
+    from timewarp_b200.forcefield import MOLAR_GAS_CONSTANT_R
     from timewarp_b200.peptides import tetrapeptide_2olx
 
     torch.set_num_threads(os.cpu_count() or 1)
     pep = tetrapeptide_2olx()
     o = fo.OracleConfig()
     sd = bench_state_dict(o, weights)
-    sysd = amber_like_system(pep).as_float32()
+    flow, kind = None, "port"
+    if ref_flow.available():
+        try:
+            flow = ref_flow.full_model(sd)
+            kind = "reference(flow)+port(energy)"
+        except Exception as e:  # pragma: no cover
+            sys.stderr.write(f"bench: oracle/_ref not usable ({e}); timing the oracle port\n")
+    sysd, energy_name = bench_system(pep)
+    sysd = sysd.as_float32()
     kbT = 310.0 * MOLAR_GAS_CONSTANT_R
     x, at, mask = synthetic_chains(pep, sample_chains, seed)
     gen = torch.Generator().manual_seed(seed)
+    torch.manual_seed(seed)
+    acc_n = 0
     for _ in range(warmup):
-        x, _ = cpu_reference_iteration(sd, o, sysd, kbT, x, at, mask, gen)
+        x, _ = cpu_reference_iteration(flow, sd, o, sysd, kbT, x, at, mask, gen)
     times = []
     for _ in range(iters):
         t0 = time.perf_counter()
-        x, _ = cpu_reference_iteration(sd, o, sysd, kbT, x, at, mask, gen)
+        x, acc = cpu_reference_iteration(flow, sd, o, sysd, kbT, x, at, mask, gen)
         times.append(time.perf_counter() - t0)
-    return sample_chains * iters / sum(times), torch.get_num_threads(), 1e3 * sum(times) / iters
+        acc_n += int(acc.sum())
+    flow_name = ("unmodified reference modules (oracle/_ref, byte-compiled from /root/reference): ConditionalFlowDensityModel."
+                 "conditional_sample_with_logp + .log_likelihood, torch-CPU fp32") if flow is not None else "oracle/flow_oracle.py (torch-CPU fp32)"
+    return {"value": sample_chains * iters / sum(times), "cores": torch.get_num_threads(), "ms": 1e3 * sum(times) / iters, "kind": kind,
+            "acceptance_rate": acc_n / max(sample_chains * iters, 1), "energy": energy_name,
+            "sample": f"{sample_chains} chains x {iters} MH iterations (+{warmup} warm-up) of the same 2olx-65 workload: flow 2 passes through "
+                      f"{flow_name} + 2 energies each through oracle/energy_oracle.py (numpy fp64, {energy_name})"}
 
 
 def run_reference(args):
@@ -170,17 +217,20 @@ def run_reference(args):
     if rank != 0:
         return
     S = args.cpu_sample
-    w = min(args.warmup, 1)
-    value, cores, ms = time_cpu_reference(S, args.steps, w, weights=args.weights)
+    r = time_cpu_reference(S, args.steps, args.warmup, weights=args.weights)
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": w,
-        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"mh_2olx65_chains{args.chains}_per_gpu", "atoms": 65, "chains_per_gpu": args.chains,
-                   "note": "reference is pure Python (PyTorch + OpenMM); OpenMM is not installable offline, so this arm runs the oracle port "
-                           "of the same path (oracle/flow_oracle.py torch-CPU fp32 + oracle/energy_oracle.py numpy fp64) on a bounded sample"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{S} chains x {args.steps} MH iterations of the same 2olx-65 workload (flow 2 passes + 2 energies each)"},
-        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": r["ms"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": workload_config(args, r["energy"]),
+        "kernel_config": {"chains_timed_per_step": S,
+                          "note": "the reference's CPU path for this workload: proposals/s of one CPU process is insensitive to the number "
+                                  "of chains per call (SURVEY.md section 6: 20-22 /s at 64...256 chains on 8 cores), so each step is a "
+                                  f"bounded sample of {S} chains; OpenMM is not installable offline, so the energies come from the fp64 "
+                                  "numpy port"},
+        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
+        "acceptance_rate_mean": r["acceptance_rate"],
+        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
 
@@ -296,28 +346,22 @@ def time_reference_s_mode(model, energy, pep, dev, S, num_samples=96):
             "note": "sample_with_model, 1 chain x S proposals per iteration (shared conditioning), host bookkeeping and per-iteration sync included"}
 
 
-def run_nll(args):
-    """`--workload nll`: data-parallel NLL training (BASELINE.json configs[3]: dipeptide set, batch 2048 over 8 GPUs =
-    256 per GPU, one gradient all-reduce per step).  Synthetic 2AA-like ragged batches: atom counts uniform in [17, 51],
-    padded to the batch maximum with `masked_elements`.  Prints ONE JSON line (atoms/s = un-padded atoms of all ranks)."""
+def measure_nll_dp(dev, rank, world, prec, B, steps, warmup):
+    """Data-parallel NLL training (BASELINE.json configs[3]: dipeptide set, batch 2048 over 8 GPUs = 256 per GPU, ONE
+    gradient all-reduce per step -- train_deepspeed.py:99-120,186-188).  Synthetic 2AA-like ragged batches: atom counts
+    uniform in [17, 51], padded to the batch maximum with `masked_elements`.  Every rank calls this; returns the result
+    dict (atoms/s = un-padded atoms of all ranks / max-over-ranks device time; `allreduce_ms` = device time of the flat
+    gradient all-reduce inside the step, CUDA events)."""
     import timewarp_b200 as tw
     from timewarp_b200 import distributed as twd
     from timewarp_b200.synthetic import synth_state_dict
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    twd.init_from_env("nccl", dev)
-    prec = args.precision
     model = tw.custom_transformer_nvp_constructor(tw.kernel_transformer_nvp_config(prec))
     model.load_state_dict(synth_state_dict(model, 0))
     model = model.to(dev).train()
     twd.broadcast_parameters(model.parameters())
     opt = torch.optim.Adam(model.parameters(), lr=1e-4, fused=True)
     trainer = twd.DataParallelTrainer(model, opt)
-    B = args.batch
     g = torch.Generator().manual_seed(100 + rank)
     lengths = torch.randint(17, 52, (B,), generator=g)
     V = int(lengths.max())
@@ -330,18 +374,20 @@ def run_nll(args):
                  y_velocs=(torch.randn(B, V, 3, generator=g) * keep).to(dev), adj_list=torch.zeros(0, 2, dtype=torch.long, device=dev),
                  edge_batch_idx=torch.zeros(0, dtype=torch.long, device=dev), masked_elements=mask.to(dev))
     atoms = torch.tensor([float(lengths.sum())], device=dev, dtype=torch.float64)
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         trainer.step(batch)
+    trainer.time_collective = True
+    trainer.collective_ms()
     if world > 1:
         torch.distributed.barrier()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         loss = trainer.step(batch)
     e1.record()
     torch.cuda.synchronize()
-    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    t = torch.tensor([e0.elapsed_time(e1), trainer.collective_ms() * steps], device=dev, dtype=torch.float64)
     # replicas must stay bit-identical: compare a parameter checksum across ranks
     chk = torch.stack([p.detach().double().sum() for p in model.parameters()]).sum().reshape(1)
     if world > 1:
@@ -353,16 +399,35 @@ def run_nll(args):
         in_sync = bool((lo == hi).item())
     else:
         in_sync = True
+    ms, ar_ms = float(t[0].item()) / steps, float(t[1].item()) / steps
+    nbytes = int(trainer.collective_bytes)
+    res = {"metric": "nll_train_atoms_per_sec", "value": float(atoms.item()) / (ms / 1e3), "unit": "atoms/s", "n_gpus": world,
+           "steps": steps, "warmup": warmup, "step_ms": ms, "ms_per_step": ms, "allreduce_ms": ar_ms, "bytes": nbytes,
+           "allreduce_busbw_gbs": (nbytes * 2 * (world - 1) / world / (ar_ms / 1e3) / 1e9) if (world > 1 and ar_ms > 0) else None,
+           "allreduce_share_of_step": ar_ms / ms if ms > 0 else None, "higher_is_better": True, "scaling": "weak", "dtype": prec,
+           "config": {"workload": f"nll_train_2aa_like_batch{B}_per_gpu", "batch_per_gpu": B, "global_batch": B * world, "padded_atoms": V,
+                      "atoms_per_step_all_ranks": float(atoms.item()), "optimizer": "Adam(fused)", "precision": prec,
+                      "collective": "one NCCL all-reduce over the flat fp32 gradient buffer per step, in place"},
+           "final_loss": float(loss.detach()), "replicas_in_sync": in_sync}
+    del trainer, opt, model
+    torch.cuda.empty_cache()
+    return res
+
+
+def run_nll(args):
+    """`--workload nll`: the data-parallel NLL training workload alone.  Prints ONE JSON line."""
+    from timewarp_b200 import distributed as twd
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    twd.init_from_env("nccl", dev)
+    res = measure_nll_dp(dev, rank, world, args.precision, args.batch, args.steps, args.warmup)
     if rank == 0:
-        ms = float(t.item()) / args.steps
-        print(json.dumps({
-            "metric": "nll_train_atoms_per_sec", "value": float(atoms.item()) / (ms / 1e3), "unit": "atoms/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": prec, "data": "synthetic",
-            "config": {"workload": f"nll_train_2aa_like_batch{B}_per_gpu", "batch_per_gpu": B, "padded_atoms": V,
-                       "atoms_per_step_all_ranks": float(atoms.item()), "optimizer": "Adam(fused)",
-                       "collective": "one NCCL all-reduce over the flat gradient buffer per step"},
-            "final_loss": float(loss.detach()), "replicas_in_sync": in_sync}), flush=True)
+        res.update({"vs_baseline": None, "data": "synthetic"})
+        print(json.dumps(res), flush=True)
     if world > 1:
         torch.distributed.destroy_process_group()
 
@@ -373,7 +438,6 @@ def run_ours(args):
     import timewarp_b200 as tw
     from timewarp_b200 import _lib
     from timewarp_b200.energy import PeptidePotentialEnergy
-    from timewarp_b200.forcefield import amber_like_system
     from timewarp_b200.peptides import tetrapeptide_2olx
     from timewarp_b200.sampling import MHChains
 
@@ -401,7 +465,8 @@ def run_ours(args):
     model = tw.custom_transformer_nvp_constructor(tw.kernel_transformer_nvp_config(args.precision))
     model.load_state_dict(bench_state_dict(model, args.weights))
     model = model.to(dev).eval()
-    energy = PeptidePotentialEnergy(amber_like_system(pep))
+    sysd, energy_name = bench_system(pep)
+    energy = PeptidePotentialEnergy(sysd)
     x0, at, mask = synthetic_chains(pep, args.chains, seed=1000 + rank)
     torch.manual_seed(args.seed + rank)  # per-rank generator
     chains = MHChains(model, energy, at.to(dev), mask.to(dev), x0.to(dev))
@@ -491,6 +556,15 @@ def run_ours(args):
         acc_rate = torch.cat(gathered)
     ms_total, ms_e2e = t.tolist()
     total_chains = args.chains * world
+    # ---- secondary: the workload that really communicates (BASELINE.json configs[3]), on every rank, after the MH numbers
+    nll_dp = None
+    if not args.no_nll:
+        nll_dp = {}
+        for prec in ("bf16", "bf16x3"):  # configs[3] says bf16; bf16x3 is the parity-grade default of this repo
+            try:
+                nll_dp[prec] = measure_nll_dp(dev, rank, world, prec, args.batch, 5, 3)
+            except Exception as e:  # the MH line must not depend on the training path
+                nll_dp[prec] = {"metric": "nll_train_atoms_per_sec", "error": str(e)[:200]}
     value = total_chains * args.steps / (ms_total / 1e3)
     e2e_value = total_chains * args.steps / (ms_e2e / 1e3)
 
@@ -526,17 +600,14 @@ def run_ours(args):
         step_flops = args.chains * 2 * V * f_atom(V)
         # the CPU baseline is a reported side figure: rank 0 at N = 1 only (the reference arm carries it at every N)
         run_cpu = not args.no_cpu_baseline and world == 1
-        cpu_val, cpu_cores, _ = time_cpu_reference(args.cpu_sample, 2, 1, weights=args.weights) if run_cpu else (None, None, None)
+        cpu = time_cpu_reference(args.cpu_sample, 8, 2, weights=args.weights) if run_cpu else None
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": {"fp32": "f32", "bf16x3": "bf16x3(f32-accumulate)", "bf16": "bf16"}[args.precision], "data": "synthetic",
-            "config": {"workload": f"mh_2olx65_chains{args.chains}_per_gpu", "atoms": V, "chains_per_gpu": args.chains,
-                       "model": f"kernel_transformer_nvp (35.97M params, synthetic weights: {args.weights})", "precision": args.precision,
-                       "energy": "synthetic Amber-like + GB-OBC2, on-GPU fp64",
-                       "l2": "working set per step (activations+workspace) >> 126 MB L2; no explicit flush",
-                       "launch": "one CUDA graph replay per MH step" if args.graph else "eager (host launches hidden behind the kernels)",
-                       "algorithmic_tflops_per_step": step_flops / 1e12},
+            "config": workload_config(args, energy_name),
+            "kernel_config": {"precision": args.precision, "energy_kernel": "on-GPU fp64",
+                              "launch": "one CUDA graph replay per MH step" if args.graph else "eager (host launches hidden behind the kernels)"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
@@ -554,14 +625,16 @@ def run_ours(args):
                 line["reference_s_mode"] = time_reference_s_mode(model, energy, pep, dev, args.chains)
             except Exception as e:
                 line["reference_s_mode"] = {"error": str(e)[:200]}
-        if not args.no_nll:
-            try:
-                line["secondary"] = time_nll_training(dev, args.precision)
-            except Exception as e:  # the MH line must not depend on the training path
-                line["secondary"] = {"metric": "nll_train_atoms_per_sec", "error": str(e)[:200]}
-        if cpu_val is not None:
-            line["cpu_baseline"] = {"value": cpu_val, "unit": UNIT, "cores": cpu_cores, "kind": "port",
-                                    "sample": f"{args.cpu_sample} chains x 2 MH iterations of the same workload through oracle/ (torch-CPU fp32 flow + numpy fp64 energy)"}
+        if nll_dp is not None:
+            line["secondary"] = dict(nll_dp["bf16"])
+            line["secondary"]["bf16x3"] = nll_dp["bf16x3"]
+        if world == 1 and not args.no_nll:
+            try:  # BASELINE.json configs[1]: AD-22 batch 256 on one GPU, step replayed as one CUDA graph
+                line["secondary_ad22"] = time_nll_training(dev, args.precision)
+            except Exception as e:
+                line["secondary_ad22"] = {"metric": "nll_train_atoms_per_sec", "error": str(e)[:200]}
+        if cpu is not None:
+            line["cpu_baseline"] = {"value": cpu["value"], "unit": UNIT, "cores": cpu["cores"], "kind": cpu["kind"], "sample": cpu["sample"]}
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
@@ -575,7 +648,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--chains", type=int, default=1024, help="chains per GPU (BASELINE configs[2]: 1024)")
     ap.add_argument("--precision", default=os.environ.get("TW_PRECISION", "bf16x3"), choices=["fp32", "bf16x3", "bf16"])
-    ap.add_argument("--cpu-sample", type=int, default=32, help="chains in the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-sample", type=int, default=64, help="chains in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--weights", default="proposal", choices=["proposal", "init"], help="synthetic weight set (see bench_state_dict)")

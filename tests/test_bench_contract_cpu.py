@@ -5,6 +5,8 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
 
 
 def test_reference_arm_json_line():
@@ -19,7 +21,12 @@ def test_reference_arm_json_line():
     assert d["value"] > 0 and d["ms_per_step"] > 0
     assert d["config"]["workload"] == "mh_2olx65_chains1024_per_gpu"
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb
+    # the flow half runs the byte-compiled unmodified reference when oracle/_ref was built (python -m oracle.build_ref), else the port
+    from oracle import ref_flow
+
+    assert cb["kind"] == ("reference(flow)+port(energy)" if ref_flow.available() else "port")
+    assert cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb
+    assert set(d["config"]) >= {"workload", "atoms", "chains_per_gpu", "model", "energy", "l2"}
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 

@@ -193,6 +193,21 @@ class DataParallelTrainer:
         self.clip = clip_grad_norm_value
         self.buckets = GradientBuckets(model.parameters(), bucket_bytes)
         self.loss_fn = loss_fn or (lambda m, batch: m(**batch))
+        # optional device timing of the gradient collective (bench.py): CUDA event pairs recorded on the current stream around
+        # the all-reduce (the NCCL stream is joined to it on both sides), one pair per step; see `collective_ms`
+        self.time_collective = False
+        self._collective_events: List[Tuple[torch.cuda.Event, torch.cuda.Event]] = []
+        self.collective_bytes = 0
+
+    def collective_ms(self, reset: bool = True) -> float:
+        """Mean device time of the gradient all-reduce (+ the 1/world scale) over the steps since the last reset."""
+        if not self._collective_events:
+            return 0.0
+        torch.cuda.synchronize()
+        ms = sum(a.elapsed_time(b) for a, b in self._collective_events) / len(self._collective_events)
+        if reset:
+            self._collective_events = []
+        return ms
 
     @torch.no_grad()
     def _all_reduce_flat(self) -> bool:
@@ -212,9 +227,17 @@ class DataParallelTrainer:
         if not seen:
             return False
         rank, world = world_info()
+        self.collective_bytes = flat.numel() * flat.element_size()
         if world > 1:
+            timed = self.time_collective and flat.is_cuda
+            if timed:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
             dist.all_reduce(flat, op=dist.ReduceOp.SUM)
             flat.mul_(1.0 / world)
+            if timed:
+                e1.record()
+                self._collective_events.append((e0, e1))
         return True
 
     def step(self, local_batch: dict) -> Tensor:
