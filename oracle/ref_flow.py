@@ -1,4 +1,4 @@
-"""TEST INFRASTRUCTURE -- loader for the byte-compiled, UNMODIFIED reference flow model in oracle/_ref/ (built by
+"""TEST INFRASTRUCTURE -- loader for the byte-compiled, UNMODIFIED reference flow model in oracle/_ref/reference_flow.zip (built by
 oracle/build_ref.py).  Import recipe = SURVEY.md Appendix C: stub modules for the plotting / trajectory packages the
 reference imports at module top but never uses on this path, stdlib `profile` imported before the reference's own
 profile.py could shadow it, and a `__hash__` for one dataclass that Python >= 3.11 rejects as a mutable default."""
@@ -10,11 +10,12 @@ import types
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF_DIR = os.path.join(HERE, "_ref")
+ARCHIVE = os.path.join(REF_DIR, "reference_flow.zip")
+STAMP = os.path.join(REF_DIR, "reference_flow.python_version")
 
 
 def available() -> bool:
-    stamp = os.path.join(REF_DIR, "timewarp", ".python_version")
-    return os.path.exists(stamp) and open(stamp).read().strip() == sys.version.split()[0]
+    return os.path.exists(ARCHIVE) and os.path.exists(STAMP) and open(STAMP).read().strip() == sys.version.split()[0]
 
 
 def load():
@@ -24,9 +25,8 @@ def load():
     import cProfile  # noqa: F401
     import profile  # noqa: F401
 
-    if REF_DIR not in sys.path:
-        sys.path.insert(0, REF_DIR)
-        sys.path.append(os.path.join(REF_DIR, "timewarp"))  # the reference imports `utilities.*` as a top-level package
+    if ARCHIVE not in sys.path:
+        sys.path.insert(0, ARCHIVE)  # zipimport: `timewarp.*` and the top-level `utilities` package the reference imports
     for n in ("pymol2", "mdtraj", "matplotlib", "matplotlib.pyplot"):
         sys.modules.setdefault(n, types.ModuleType(n))
     import timewarp.modules.model_wrappers.flow as F
