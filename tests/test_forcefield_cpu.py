@@ -12,7 +12,7 @@ import pytest
 
 from oracle import energy_oracle as eo
 from timewarp_b200.forcefield import amber_like_system, system_description_from_openmm
-from timewarp_b200.peptides import tetrapeptide_2olx
+from timewarp_b200.peptides import alanine_dipeptide, tetrapeptide_2olx
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
@@ -167,3 +167,76 @@ def test_reference_golden_energies_with_openmm():
     e = eo.potential_energy(sysd, g["pot_positions"].astype(np.float64))
     np.testing.assert_allclose(e, g["pot_openmm"], rtol=0, atol=1e-3)  # simulation/tests/test_md.py:35-47
     assert openmm is not None
+
+
+# ------------------------------------------------------------------------------------------------ pinned table (no OpenMM needed)
+def _golden_energy():
+    return np.load(os.path.join(GOLDEN, "energy_2olx_openmm.npz"))
+
+
+def _c_terminal_carbon(pep):
+    last = max(pep.residue_index)
+    return [i for i, (n, r) in enumerate(zip(pep.atom_names, pep.residue_index)) if n == "C" and r == last][0]
+
+
+def test_amber99sbildn_table_is_consistent():
+    from timewarp_b200 import amber99 as A
+    from timewarp_b200.forcefield import AMBER99SBILDN_PINNED, amber99sbildn_obc2
+
+    assert AMBER99SBILDN_PINNED
+    for name, atoms in A.RESIDUES.items():  # ff94 charge sets sum to the residue's formal charge
+        total = sum(q for _, q in atoms.values())
+        expect = {"NASN": 1.0, "CGLN": -1.0}.get(name, None)
+        if expect is not None:
+            assert abs(total - expect) < 1e-9, (name, total)
+        elif name in ("ALA", "ASN", "GLN"):
+            assert abs(total) < 1e-9, (name, total)
+    pep = tetrapeptide_2olx()
+    s = amber99sbildn_obc2(pep)
+    assert s.n_atoms == 65 and len(s.bond_idx) == 64 and len(s.angle_idx) == 111 and abs(s.charge.sum()) < 1e-9
+    assert s.cutoff == 2.0 and s.reaction_field_eps == 1.0 and s.solvent_dielectric == 78.5  # simulation/md.py:166-171 + GB post-processing
+    ad = amber99sbildn_obc2(alanine_dipeptide())
+    assert ad.n_atoms == 22 and abs(ad.charge.sum()) < 1e-3  # ACE + ALA + NME: 0.0001 from the published rounding of the ACE set
+
+
+def test_reference_golden_energies():
+    """The reference's own check, simulation/tests/test_md.py:35-47, WITHOUT OpenMM: the fp64 oracle fed with the typed-in
+    ff99SB-ILDN / OBC2 table reproduces the 40 OpenMM potential energies of implicit-2olx-traj-cpu-arrays.npz.  The reference
+    compares two runs of the same single-precision OpenMM platform at atol 1e-3; against an fp64 evaluation the floor is that
+    platform's own rounding (measured: mean -0.005, std 0.003, max 0.011 kJ/mol at energies around -1700), hence atol 0.02."""
+    from timewarp_b200.forcefield import amber99sbildn_obc2
+
+    g = _golden_energy()
+    pep = tetrapeptide_2olx()
+    e = eo.potential_energy(amber99sbildn_obc2(pep), g["cpu_positions"].astype(np.float64))
+    np.testing.assert_allclose(e, g["cpu_potential"], rtol=0, atol=0.02)
+    assert abs((e - g["cpu_potential"]).mean()) < 0.01 and (e - g["cpu_potential"]).std() < 0.006
+    # the longer trajectory (other Asn chi1 rotamers; its carboxylate improper lists the two oxygens in the other order)
+    sw = amber99sbildn_obc2(pep, improper_choice={_c_terminal_carbon(pep): 0})
+    ew = eo.potential_energy(sw, g["wide_positions"].astype(np.float64))
+    np.testing.assert_allclose(ew, g["wide_potential"], rtol=0, atol=0.02)
+    # and the synthetic table is nowhere near (this is what "unpinned" looked like)
+    assert np.abs(eo.potential_energy(amber_like_system(pep), g["cpu_positions"].astype(np.float64)) - g["cpu_potential"]).min() > 100.0
+
+
+def test_reference_golden_forces():
+    """Forces of the same fixture (simulation/tests/test_md.py:45-47: rtol 0.05, atol 1e-2) by central differences of the oracle."""
+    from timewarp_b200.forcefield import amber99sbildn_obc2
+
+    g = _golden_energy()
+    pep = tetrapeptide_2olx()
+    s = amber99sbildn_obc2(pep)
+    h = 1e-5
+    for frame in (0, 17, 39):
+        x = g["cpu_positions"][frame].astype(np.float64)
+        n = pep.num_atoms
+        xp = np.repeat(x[None], 2 * n * 3, 0)
+        for a in range(n):
+            for k in range(3):
+                xp[2 * (a * 3 + k), a, k] += h
+                xp[2 * (a * 3 + k) + 1, a, k] -= h
+        e = eo.potential_energy(s, xp)
+        f = -((e[0::2] - e[1::2]) / (2 * h)).reshape(n, 3)
+        ref = g["cpu_forces"][frame].astype(np.float64)
+        np.testing.assert_allclose(f, ref, rtol=0.05, atol=0.2)
+        assert np.sqrt(((f - ref) ** 2).mean()) < 0.1  # measured 0.03 kJ/mol/nm rms of ~930 (float32 storage of the reference)

@@ -20,7 +20,7 @@ from tests.common import FULL_O, TINY_O, CudaReplayDraws, build_model, proposal_
 from timewarp_b200 import sampling
 from timewarp_b200.chirality import compute_chirality_sign, find_chirality_centers
 from timewarp_b200.energy import PeptidePotentialEnergy
-from timewarp_b200.forcefield import amber_like_system
+from timewarp_b200.forcefield import amber99sbildn_obc2, amber_like_system
 from timewarp_b200.peptides import alanine_dipeptide, tetrapeptide_2olx
 
 pytestmark = pytest.mark.gpu
@@ -102,7 +102,7 @@ def test_mh_chains_bench_configuration_flip_set():
     pep = tetrapeptide_2olx()
     V = pep.num_atoms
     m, sd = _model(FULL_O, "bf16x3", "proposal")
-    sysd = amber_like_system(pep)
+    sysd = amber99sbildn_obc2(pep)  # the bench's energy: ff99SB-ILDN + OBC2 pinned to the reference's OpenMM fixtures
     s32 = sysd.as_float32()
     energy = PeptidePotentialEnergy(sysd)
     kbT = energy.kbT
@@ -165,7 +165,7 @@ def test_explore_matches_oracle_steps(threshold):
     pep = tetrapeptide_2olx()
     V, P, steps = pep.num_atoms, 48, 4
     m, sd = _model(FULL_O, "bf16x3", "proposal")
-    sysd = amber_like_system(pep)
+    sysd = amber99sbildn_obc2(pep)
     s32 = sysd.as_float32()
     energy = PeptidePotentialEnergy(sysd)
     x = torch.tensor(pep.coords_nm, dtype=torch.float32)[None]
