@@ -1244,6 +1244,7 @@ void tc_set_trace(int cls, long long* buf) {
   if (cls == 1) g_ffn_trace = buf;
   if (cls == 2) g_mix_trace = buf;
   if (cls == 3) g_attn_trace = buf;
+  if (cls == 4) tc_set_fm_trace(buf);
 }
 
 static int launch_ffn_tc(const tw_flow_config* c, const FfnArgs& a_in, cudaStream_t st) {
@@ -2976,10 +2977,25 @@ int tc_attention_layer(const tw_flow_config* c, const ParamView& pv, int k, int 
     if (use_fused < 0) {
       const char* e = getenv("TW_ATTN_FUSED");  // bring-up switch: 0 = mixing + projection kernels
       use_fused = e ? atoi(e) : 1;
+    }
+    static DeviceOnce fused_attr;
+    if (!fused_attr.done()) {
       TW_CUDA(cudaFuncSetAttribute(k_attn_fused<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
       TW_CUDA(cudaFuncSetAttribute(k_attn_fused<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+      fused_attr.mark();
     }
     const int VP = pad16(V);
+    // inference: the feature-major kernel (values projected first, mixed per sample afterwards); the taped training forward
+    // keeps the two-kernel form because the backward reads the per-head mixed images
+    if (use_fused && !pre && tc_attn_fm_supported(V, n)) {
+      const uint8_t* wcs[2];
+      const float *gs[2], *bs[2];
+      for (int s = 0; s < 2; s++) {
+        wcs[s] = tc.packed + L.net_offset(k, net_of[s]) + L.enc0 + (size_t)t * L.enc_stride + L.enc_wc;
+        gs[s] = pv.enc(k, net_of[s], t, 7), bs[s] = pv.enc(k, net_of[s], t, 8);
+      }
+      return tc_attn_fm(c, x, out, wcs, gs, bs, tc.scores_img, n, n_cond, V, nets, st);
+    }
     const int fused_smem = (int)AttnSmem(V, VP).total() + 1024;
     // the training tape needs the per-head mixed images, so the taped forward keeps the two-kernel form
     if (use_fused && !pre && VP <= kMixTokMaxVP && fused_smem <= 232448 && n >= 1) {

@@ -53,6 +53,12 @@ void tc_set_trace(int cls, long long* buf);  // 1 fused FFN, 2 mixing kernel  //
 int tc_attention_layer(const tw_flow_config* c, const ParamView& pv, int k, int t, const TcScratch& tc, float* const x[2],
                        float* const out[2], int64_t n, int64_t n_cond, int V, cudaStream_t st, float* const* pre = nullptr,
                        int only_net = -1);
+// feature-major fused attention layer (attn_fm.cu): project every head first, mix per sample afterwards; any atom count <= 128
+bool tc_attn_fm_supported(int V, int64_t n);
+int tc_attn_fm(const tw_flow_config* c, const float* const x[2], float* const out[2], const uint8_t* const wc[2],
+               const float* const gamma[2], const float* const beta[2], const uint8_t* scores_img, int64_t n, int64_t n_cond, int V,
+               int nets, cudaStream_t st);
+void tc_set_fm_trace(long long* buf);
 // the mixing step alone (also used by the backward pass with the transposed score images)
 int tc_mix(const tw_flow_config* c, const float* const x[2], uint8_t* const img[2], const uint8_t* scores_img, int64_t n,
            int64_t n_cond, int V, cudaStream_t st, int nets = 2);

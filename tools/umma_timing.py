@@ -5,7 +5,7 @@ from timewarp_b200 import _lib
 lib = _lib.load()
 out = torch.zeros(2, dtype=torch.int64, device="cuda")
 print("n_mma   N ts noswz | issue_cycles total_cycles per_mma")
-for N in (256, 128, 80, 64):
+for N in (256, 240, 160, 128, 96, 80, 64, 32):
     for ts in (0, 1):
         for nosw in (0, 1):
             for rep in range(2):
