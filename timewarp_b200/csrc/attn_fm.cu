@@ -17,8 +17,8 @@
 // rows real at 65 atoms, 39 M128xN128 MMAs per (sample, head).  Here a (sample, head) costs 24 MMAs of N = G*VP / G (projection)
 // + 3 VP/16 MMAs of N = VP (mixing): 39 MMAs of N = 80 at 65 atoms -- 0.625 of the tensor work, and atom counts up to 128.
 //
-// Warp roles (448 threads): 0 producers (lane 0 W_c units, lane 1 score images; bulk async copies), 1 MMA issuer,
-// 2-5 x-tile builders + LayerNorm, 6-13 two epilogue groups (column halves).  TMEM: PT0 | PT1 | DT0 | DT1, 128 columns each.
+// Warp roles (480 threads): 0 W_c producer, 14 score-image producer (bulk async copies; two lanes of ONE warp starve each other
+// while one of them spins on a full ring), 1 MMA issuer, 2-5 x-tile builders + LayerNorm, 6-13 two epilogue groups (column halves).  TMEM: PT0 | PT1 | DT0 | DT1, 128 columns each.
 // MMA issue order over a global head counter g: P(g), M(g-1) -- the tensor pipe executes in issue order, so PT[g & 1] is not
 // overwritten before M(g - 2) has read it, and the conversion of PT(g) overlaps M(g-1) + P(g+1).
 #include <stdlib.h>
@@ -29,7 +29,7 @@
 namespace tw {
 using namespace umma;
 
-constexpr int kFmThreads = 448;
+constexpr int kFmThreads = 480;
 constexpr int kFmWcStage = 16384;  // the hi or the lo image of one [128 out x 64 in] K block of W_c,h
 constexpr uint32_t FM_PT = 0, FM_DT = 256;
 
@@ -45,6 +45,7 @@ struct FmArgs {
   int wc_stages, sc_stages;
   float eps;
   long long* trace;
+  int exp;  // timing experiments (TW_FM_EXP, bring-up only; results are wrong when set)
 };
 
 struct FmSmem {
@@ -61,8 +62,8 @@ struct FmSmem {
   __host__ __device__ uint32_t sc() const { return wc() + wc_stages * kFmWcStage; }
   __host__ __device__ uint32_t stg() const { return sc() + sc_stages * sc_unit; }
   __host__ __device__ uint32_t vec() const { return stg() + stg_bytes; }
-  __host__ __device__ uint32_t bars() const { return vec() + 2 * 128 * 4; }
-  __host__ __device__ uint32_t total() const { return bars() + 512; }
+  __host__ __device__ uint32_t bars() const { return vec(); }
+  __host__ __device__ uint32_t total() const { return bars() + 384; }
 };
 
 // mbarrier wait with a watchdog: a protocol error traps (the launch fails) instead of hanging the GPU
@@ -92,7 +93,8 @@ __device__ __forceinline__ void fm_epi_bar() { asm volatile("bar.sync 3, 256;" :
 template <int kSplit>
 __global__ void __launch_bounds__(kFmThreads, 1) k_attn_fm(FmArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw;  // no static shared memory in this kernel: the dynamic window is 1024-byte aligned (checked below)
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
   const int net = blockIdx.y;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int V = a.V, VP = a.VP, H = a.H, G = a.G;
@@ -119,7 +121,6 @@ __global__ void __launch_bounds__(kFmThreads, 1) k_attn_fm(FmArgs a) {
   uint64_t* stg_full = dt_free + 2;         // 256 arrivals: staging rows written
   uint64_t* stg_free = stg_full + 1;        // 128 arrivals: LayerNorm read the staging rows
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stg_free + 1);
-  float* vecs = reinterpret_cast<float*>(smem + L.vec());
 
   if (tid == 0) {
     for (int i = 0; i < 8; i++) mbar_init(&wc_full[i], 1), mbar_init(&wc_empty[i], 1);
@@ -132,7 +133,6 @@ __global__ void __launch_bounds__(kFmThreads, 1) k_attn_fm(FmArgs a) {
     mbar_fence_init();
   }
   if (warp == 1) tmem_alloc<512>(tmem_slot);
-  for (int i = tid; i < 128; i += blockDim.x) vecs[i] = a.gamma[net][i], vecs[128 + i] = a.beta[net][i];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(kFmThreads, 1) k_attn_fm(FmArgs a) {
   }
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ producers: W_c units (lane 0), score images (lane 1)
+    // ------------------------------------------------------------------ producer: W_c units
     if (lane == 0) {
       uint32_t ws = 0, wp = 0;
       const int64_t total_heads = my_groups * H;
@@ -161,7 +161,11 @@ __global__ void __launch_bounds__(kFmThreads, 1) k_attn_fm(FmArgs a) {
           if (++ws == L.wc_stages) ws = 0, wp ^= 1;
         }
       }
-    } else if (lane == 1) {
+    }
+    __syncwarp();
+  } else if (warp == 14) {
+    // ------------------------------------------------------------------ producer: score images, one unit per (sample, head)
+    if (lane == 0) {
       uint32_t ss = 0, sp = 0;
       for (int64_t it = 0; it < my_groups; it++) {
         const int64_t grp = group_of(it);
@@ -193,8 +197,9 @@ __global__ void __launch_bounds__(kFmThreads, 1) k_attn_fm(FmArgs a) {
       const uint32_t xt = smem_u32(smem + L.xb((int)(it & 1)));
       for (int kb = 0; kb < 2; kb++) {
         const uint32_t x_hi = xt + kb * blk, x_lo = xt + 2 * blk + kb * blk;
-        fm_wait(&wc_full[ws], wp);  // hi image of this K block
+        if (!(a.exp & 1)) fm_wait(&wc_full[ws], wp);  // hi image of this K block
         tc_fence_after();
+        if (kb == 0) { FM_TRACE(0, 3, g); }
         if (elect_one()) {
           const uint32_t w = smem_u32(smem + L.wc() + ws * kFmWcStage);
 #pragma unroll
@@ -212,7 +217,7 @@ __global__ void __launch_bounds__(kFmThreads, 1) k_attn_fm(FmArgs a) {
         __syncwarp();
         if (++ws == L.wc_stages) ws = 0, wp ^= 1;
         if (kSplit == 3) {
-          fm_wait(&wc_full[ws], wp);  // lo image
+          if (!(a.exp & 1)) fm_wait(&wc_full[ws], wp);  // lo image
           tc_fence_after();
           if (elect_one()) {
             const uint32_t w = smem_u32(smem + L.wc() + ws * kFmWcStage);
@@ -236,12 +241,14 @@ __global__ void __launch_bounds__(kFmThreads, 1) k_attn_fm(FmArgs a) {
         fm_wait(&dt_free[db], (ph_dtfree >> db) & 1u);
         ph_dtfree ^= 1u << db;
       }
-      fm_wait(&h_full[b], (ph_h >> b) & 1u);
+      if (!(a.exp & 2)) fm_wait(&h_full[b], (ph_h >> b) & 1u);
       ph_h ^= 1u << b;
       tc_fence_after();
+      FM_TRACE(0, 4, g);
       for (int s = 0; s < ns; s++) {
-        fm_wait(&sc_full[ss], sp);
+        if (!(a.exp & 2)) fm_wait(&sc_full[ss], sp);
         tc_fence_after();
+        if (s == 0) { FM_TRACE(0, 5, g); }
         if (elect_one()) {
           const uint32_t s_hi = smem_u32(smem + L.sc() + ss * L.sc_unit), s_lo = s_hi + mat_bytes;
           const uint32_t d = tmem + FM_DT + (uint32_t)db * 128 + (uint32_t)(s * VP);
@@ -281,7 +288,7 @@ __global__ void __launch_bounds__(kFmThreads, 1) k_attn_fm(FmArgs a) {
     const int hw = lane >> 4;         // half-warp: row parity
     const int c = lane & 15;          // 16-byte chunk of a row's bf16 image = 8 features
     uint32_t ph_free = 0, ph_stg = 0;
-    const float4 gm = *reinterpret_cast<const float4*>(vecs + 4 * lane), bt = *reinterpret_cast<const float4*>(vecs + 128 + 4 * lane);
+    const float4 gm = __ldg(reinterpret_cast<const float4*>(a.gamma[net]) + lane), bt = __ldg(reinterpret_cast<const float4*>(a.beta[net]) + lane);
 
     auto build_tiles = [&](int64_t it) {  // group it -> xb[it & 1]: bf16 hi/lo K-major SW128 rows of the group's tokens
       const int b = (int)(it & 1);
@@ -294,7 +301,7 @@ __global__ void __launch_bounds__(kFmThreads, 1) k_attn_fm(FmArgs a) {
       uint8_t* tile = smem + L.xb(b);
       const uint32_t blk = (uint32_t)N * 128u;
       const int kb = c >> 3, cc = c & 7;
-      for (int r0 = 0; r0 < N; r0 += 32) {  // 8 rows per pass of the 4 warps, 4 passes in flight
+      for (int r0 = 0; r0 < ((a.exp & 8) ? 0 : N); r0 += 32) {  // 8 rows per pass of the 4 warps, 4 passes in flight
         float4 v[4][2];
 #pragma unroll
         for (int p = 0; p < 4; p++) {
@@ -332,7 +339,7 @@ __global__ void __launch_bounds__(kFmThreads, 1) k_attn_fm(FmArgs a) {
       const float* xg = a.x[net] + grp * G * V * 128;
       float* og = a.out[net] + grp * G * V * 128;
       const uint8_t* stg = smem + L.stg();
-      for (int r0 = lw; r0 < rows; r0 += 16) {  // 4 rows per warp in flight
+      for (int r0 = lw; r0 < ((a.exp & 8) ? 0 : rows); r0 += 16) {  // 4 rows per warp in flight
         float4 xv[4], sv[4];
 #pragma unroll
         for (int p = 0; p < 4; p++) {
@@ -396,14 +403,15 @@ __global__ void __launch_bounds__(kFmThreads, 1) k_attn_fm(FmArgs a) {
         if (q == 2 && e == 0) { FM_TRACE(1, 0, g); }
         const uint32_t base = tmem + lane_base + FM_PT + (uint32_t)b * 128;
         uint32_t r[8][8];
+        const int nchunk_c = (a.exp & 4) ? 0 : nchunk;
 #pragma unroll
         for (int i = 0; i < 8; i++)
-          if (i < nchunk) tmem_ld8(base + (uint32_t)(e * half + 8 * i), r[i]);
+          if (i < nchunk_c) tmem_ld8(base + (uint32_t)(e * half + 8 * i), r[i]);
         tmem_ld_wait();
         fm_epi_bar();  // both halves have read their fp32 columns: the in-place writes below may cross into the other half
 #pragma unroll
         for (int i = 0; i < 8; i++)
-          if (i < nchunk) {
+          if (i < nchunk_c) {
             uint32_t hi[4], lo[4];
 #pragma unroll
             for (int j = 0; j < 4; j++) split2(__uint_as_float(r[i][2 * j]), __uint_as_float(r[i][2 * j + 1]), hi[j], lo[j]);
@@ -490,7 +498,7 @@ static bool fm_plan(int V, int VP, int64_t n, int* G, int* wcs, int* scs, int* s
   if ((int64_t)g > n) g = (int)(n < 1 ? 1 : n);
   for (int w = 4; w >= 3; w--)
     for (int s = (g > 1 ? 4 : 2); s >= 2; s--) {
-      const int total = (int)FmSmem(V, VP, g, w, s).total() + 1024;
+      const int total = (int)FmSmem(V, VP, g, w, s).total();
       if (total <= 232448) {
         *G = g, *wcs = w, *scs = s, *smem_bytes = total;
         return true;
@@ -526,6 +534,10 @@ int tc_attn_fm(const tw_flow_config* c, const float* const x[2], float* const ou
   a.scores_img = scores_img;
   a.n = n, a.n_cond = n_cond, a.V = V, a.VP = VP, a.H = c->num_heads, a.eps = c->layer_norm_eps;
   a.trace = g_fm_trace;
+  {
+    const char* e = getenv("TW_FM_EXP");
+    a.exp = e ? atoi(e) : 0;
+  }
   const int per_net = nets == 1 ? 148 : 74;
   const int64_t groups = (n + a.G - 1) / a.G;
   dim3 grid((unsigned)(groups < per_net ? groups : per_net), nets);

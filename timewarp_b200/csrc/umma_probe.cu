@@ -126,7 +126,8 @@ __global__ void __launch_bounds__(128, 1) k_umma_probe(ProbeArgs p) {
 
 // Timing micro-benchmark: an elected lane issues `n_mma` back-to-back M128 x N x K16 MMAs (SS or TS, B operand
 // swizzled or not) into one accumulator, ONE commit at the end.  out[0] = cycles to issue, out[1] = cycles until done.
-__global__ void __launch_bounds__(128, 1) k_umma_timing(int n_mma, int N, int ts, int b_noswizzle, long long* out) {
+__global__ void __launch_bounds__(128, 1) k_umma_timing(int n_mma, int N, int ts, int b_noswizzle, long long* out, int fill, int a_units,
+                                                        int a_off, int b_off) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   __shared__ uint64_t bar;
@@ -137,7 +138,11 @@ __global__ void __launch_bounds__(128, 1) k_umma_timing(int n_mma, int N, int ts
     mbar_init(&bar, 1);
     mbar_fence_init();
   }
-  for (int i = tid; i < 96 * 1024 / 16; i += 128) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = tid; i < 192 * 1024 / 16; i += 128) {  // fill: 0 zeros, 1 pseudo-random bf16 values of magnitude ~1
+    uint32_t h = (uint32_t)i * 2654435761u;
+    auto v = [&](uint32_t x) { x ^= x >> 13; x *= 0x5bd1e995u; x ^= x >> 15; return ((x & 0x80008000u) | 0x3f003f00u | (x & 0x007f007fu)); };
+    reinterpret_cast<uint4*>(smem)[i] = fill ? make_uint4(v(h), v(h + 1), v(h + 2), v(h + 3)) : make_uint4(0, 0, 0, 0);
+  }
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
@@ -145,14 +150,28 @@ __global__ void __launch_bounds__(128, 1) k_umma_timing(int n_mma, int N, int ts
   const uint32_t tmem = tmem_slot;
   if (warp == 1) {
     const uint32_t idesc = make_idesc_bf16(128, N, 0, 0);
-    const uint32_t a0 = smem_u32(smem), b0 = smem_u32(smem + 32 * 1024);
+    const uint32_t a0 = smem_u32(smem + a_off), b0 = smem_u32(smem + b_off);  // byte offsets of the A units (16 KB each) and the B tile
     long long t0 = clock64(), t1 = 0;
     if (elect_one()) {
-      for (int i = 0; i < n_mma; i++) {
-        uint64_t bd = b_noswizzle ? make_smem_desc(b0 + (i & 3) * 256, 128, 1024, LAYOUT_NONE)  // K = 64 wide tile: 32 KB for N = 256
-                                  : desc_kmajor_sw128(b0 + (i & 3) * 32);
-        if (ts) mma_ts(tmem, tmem + 256 + (i & 7) * 8, bd, idesc, 1);
-        else mma_ss(tmem, desc_kmajor_sw128(a0 + (i & 3) * 32), bd, idesc, 1);
+      // descriptors precomputed, issue loop unrolled by 8: the loop measures the tensor pipe, not the issuing thread
+      uint64_t ad[8], bd[8];
+      uint32_t at[8];
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        ad[j] = desc_kmajor_sw128(a0 + ((j >> 2) % a_units) * 16384 + (j & 3) * 32);
+        bd[j] = b_noswizzle ? make_smem_desc(b0 + (j & 3) * 256, 128, 1024, LAYOUT_NONE) : desc_kmajor_sw128(b0 + (j & 3) * 32);
+        at[j] = tmem + 256 + j * 8;
+      }
+      if (ts) {
+        for (int i = 0; i < n_mma; i += 8) {
+#pragma unroll
+          for (int j = 0; j < 8; j++) mma_ts(tmem, at[j], bd[j], idesc, 1);
+        }
+      } else {
+        for (int i = 0; i < n_mma; i += 8) {
+#pragma unroll
+          for (int j = 0; j < 8; j++) mma_ss(tmem, ad[j], bd[j], idesc, 1);
+        }
       }
       mma_commit(&bar);
       t1 = clock64();
@@ -187,11 +206,32 @@ extern "C" int tw_debug_umma_probe(const float* A, const float* B, float* out, i
   return TW_OK;
 }
 
+extern "C" int tw_debug_umma_timing2(int n_mma, int N, int ts, int b_noswizzle, long long* out, int fill, int a_units, void* stream) {
+  TW_CHECK_ARG(out && n_mma > 0 && N >= 16 && N <= 256 && N % 16 == 0, "bad args");
+  TW_CHECK_ARG(a_units >= 1 && a_units <= 8, "bad a_units");
+  const int smem = 193 * 1024 + 1024;
+  TW_CUDA(cudaFuncSetAttribute(k_umma_timing, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  k_umma_timing<<<1, 128, smem, (cudaStream_t)stream>>>(n_mma, N, ts, b_noswizzle, out, fill, a_units, 0, 128 * 1024);
+  TW_LAUNCH_CHECK();
+  return TW_OK;
+}
+
+extern "C" int tw_debug_umma_timing3(int n_mma, int N, int ts, long long* out, int fill, int a_units, int a_off, int b_off, void* stream) {
+  TW_CHECK_ARG(out && n_mma > 0 && N >= 16 && N <= 256 && N % 16 == 0 && a_units >= 1 && a_units <= 8, "bad args");
+  TW_CHECK_ARG(a_off >= 0 && b_off >= 0 && a_off % 1024 == 0 && b_off % 1024 == 0 && a_off + a_units * 16384 <= 192 * 1024 &&
+                   b_off + 32768 <= 192 * 1024, "bad offsets");
+  const int smem = 193 * 1024 + 1024;
+  TW_CUDA(cudaFuncSetAttribute(k_umma_timing, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  k_umma_timing<<<1, 128, smem, (cudaStream_t)stream>>>(n_mma, N, ts, 0, out, fill, a_units, a_off, b_off);
+  TW_LAUNCH_CHECK();
+  return TW_OK;
+}
+
 extern "C" int tw_debug_umma_timing(int n_mma, int N, int ts, int b_noswizzle, long long* out, void* stream) {
   TW_CHECK_ARG(out && n_mma > 0 && N >= 16 && N <= 256 && N % 16 == 0, "bad args");
-  const int smem = 97 * 1024 + 1024;
+  const int smem = 193 * 1024 + 1024;
   TW_CUDA(cudaFuncSetAttribute(k_umma_timing, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  k_umma_timing<<<1, 128, smem, (cudaStream_t)stream>>>(n_mma, N, ts, b_noswizzle, out);
+  k_umma_timing<<<1, 128, smem, (cudaStream_t)stream>>>(n_mma, N, ts, b_noswizzle, out, 0, 1, 0, 32 * 1024);  // the round-1 placement
   TW_LAUNCH_CHECK();
   return TW_OK;
 }

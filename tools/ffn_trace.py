@@ -10,7 +10,7 @@ from timewarp_b200.peptides import tetrapeptide_2olx
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 lo, hi = (int(sys.argv[2]), int(sys.argv[3])) if len(sys.argv) > 3 else (20, 28)
-cls = int(sys.argv[4]) if len(sys.argv) > 4 else 1  # 1 fused FFN, 2 mixing kernel, 3 fused attention
+cls = int(sys.argv[4]) if len(sys.argv) > 4 else 1  # 1 fused FFN, 2 mixing kernel, 3 token-major fused attention, 4 feature-major fused attention
 pep = tetrapeptide_2olx()
 m = tw.custom_transformer_nvp_constructor(tw.kernel_transformer_nvp_config("bf16x3"))
 m.load_state_dict(fo.synth_state_dict(fo.OracleConfig(), 0))
@@ -42,6 +42,9 @@ if cls == 3:
     names = {0: {0: 'mma: head top', 1: 'mma: scores landed', 2: 'mma: MMA1 issued', 3: 'mma2: Wc kb0 landed', 4: 'mma2: h_full kb0', 5: 'mma2: Wc kb1 landed', 6: 'mma2: h_full kb1', 7: 'mma: sample top (item=sample)', 8: 'mma: xb_full (item=sample)'},
              1: {0: 'epi: wait dm', 1: 'epi: dm_full', 2: 'epi: h arrived', 3: 'epi: LN done', 4: 'epi: init_do done'},
              2: {0: 'conv: wait xs (item=sample)', 1: 'conv: xs_full', 2: 'conv: xb_free', 3: 'conv: done'}}
+elif cls == 4:
+    names = {0: {0: 'mma: head top', 1: 'mma: P(g) issued', 2: 'mma: M(g-1) issued', 3: 'mma: first W unit landed', 4: 'mma: h_full (item = g-1)', 5: 'mma: scores landed (item = g-1)'},
+             1: {0: 'epi: pt_full', 1: 'epi: converted', 2: 'epi: drained previous group'}, 2: {}}
 elif cls == 2:
     names = {0: {0: 'mma: sample top', 1: 'mma: hs_full', 2: 'mma: head top', 3: 'mma: scores landed', 4: 'mma: head issued'},
              1: {2: 'epi0: wait d_full', 3: 'epi0: d_full', 5: 'epi0: staging free', 4: 'epi0: staged', 7: 'epi0: sync2', 6: 'epi0: stores issued'},

@@ -20,7 +20,9 @@ xv, yv = torch.randn(B, 65, 3, generator=g).cuda(), torch.randn(B, 65, 3, genera
 at = torch.tensor(pep.atom_types)[None].repeat(B, 1).cuda()
 mask = torch.zeros(B, 65, dtype=torch.bool).cuda()
 e = torch.zeros(0, 2, dtype=torch.long).cuda()
+inference = os.environ.get("TW_PROFILE_TAPED", "0") != "1"  # default: the inference path (fused kernels); 1 = taped training forward
 for _ in range(passes):
+  with torch.set_grad_enabled(not inference):
     ll = m.log_likelihood(atom_types=at, x_coords=x, x_velocs=xv, y_coords=y, y_velocs=yv, adj_list=e, edge_batch_idx=e[:, 0], masked_elements=mask)
-    torch.cuda.synchronize()
+  torch.cuda.synchronize()
 print(ll[:4].tolist())
