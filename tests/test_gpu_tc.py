@@ -73,7 +73,11 @@ def test_bf16_plain_is_close():
     assert_rel(ll, g["log_likelihood"], rel=2e-2, what="plain bf16 (training precision)")
 
 
-@pytest.mark.parametrize("B,V,lengths", [(37, 65, None), (9, 65, [65, 64, 33, 65, 1, 17, 65, 48, 65]), (3, 80, [80, 79, 66]), (130, 22, None), (150, 65, None)])
+@pytest.mark.parametrize("B,V,lengths", [(37, 65, None), (9, 65, [65, 64, 33, 65, 1, 17, 65, 48, 65]), (3, 80, [80, 79, 66]), (130, 22, None), (150, 65, None),
+                                         # the feature-major attention kernel at every group size: G = 10 (16 atoms), 3 (48), 1 (100, 128);
+                                         # batch sizes that leave a partial last group
+                                         (11, 16, [16, 15, 1, 16, 9, 16, 16, 3, 16, 16, 2]), (7, 48, None), (5, 100, [100, 99, 81, 100, 97]),
+                                         (3, 128, [128, 127, 113]), (1, 65, None)])
 def test_bf16x3_inference_path_odd_sizes_vs_oracle(B, V, lengths):
     """The inference kernels (CTA-pair FFN with a partial last 256-token tile, fused attention with ragged / masked
     samples, samples straddling tile boundaries; 150 x 65 tokens = 39 pair tiles over 37 pairs: two leftover tiles split

@@ -189,6 +189,70 @@ __global__ void __launch_bounds__(128, 1) k_umma_timing(int n_mma, int N, int ts
   if (warp == 0) tmem_dealloc<512>(tmem);
 }
 
+
+// Cost of the bookkeeping around MMA blocks: `n_blocks` blocks of `per_block` TS MMAs (N columns), with optionally, per block,
+// flags bit 0: tcgen05.commit to a (never waited) mbarrier, bit 1: tcgen05.fence::after_thread_sync, bit 2: elect.sync +
+// __syncwarp around the block (otherwise ONE elected thread runs the whole loop), bit 3: a try_wait on a completed mbarrier,
+// bit 4: two commits per block.  out[1] = total cycles.
+__global__ void __launch_bounds__(128, 1) k_umma_overhead(int n_blocks, int per_block, int N, int flags, long long* out) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t bar, bar2, bar3;
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (warp == 0) tmem_alloc<512>(&tmem_slot);
+  if (tid == 0) {
+    mbar_init(&bar, 1), mbar_init(&bar2, 1), mbar_init(&bar3, 1);
+    mbar_fence_init();
+  }
+  for (int i = tid; i < 64 * 1024 / 16; i += 128) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (tid == 0) mbar_arrive(&bar3);  // completes phase 0 of bar3: try_wait(bar3, 0) succeeds immediately from now on
+  __syncthreads();
+  const uint32_t tmem = tmem_slot;
+  if (warp == 1) {
+    const uint32_t idesc = make_idesc_bf16(128, N, 0, 0);
+    const uint32_t b0 = smem_u32(smem);
+    uint64_t bd[4];
+    for (int j = 0; j < 4; j++) bd[j] = desc_kmajor_sw128(b0 + j * 32);
+    const long long t0 = clock64();
+    auto block = [&]() {
+      for (int j = 0; j < per_block; j++) mma_ts(tmem, tmem + 256 + (j & 7) * 8, bd[j & 3], idesc, 1);
+      if (flags & 1) mma_commit(&bar2);
+      if (flags & 16) mma_commit(&bar2);
+    };
+    if (flags & 4) {
+      for (int i = 0; i < n_blocks; i++) {
+        if (flags & 8) mbar_wait(&bar3, 0);
+        if (flags & 2) tc_fence_after();
+        if (elect_one()) block();
+        __syncwarp();
+      }
+      if (elect_one()) mma_commit(&bar);
+      __syncwarp();
+    } else {
+      if (elect_one()) {
+        for (int i = 0; i < n_blocks; i++) {
+          if (flags & 8) mbar_wait(&bar3, 0);
+          if (flags & 2) tc_fence_after();
+          block();
+        }
+        mma_commit(&bar);
+      }
+      __syncwarp();
+    }
+    mbar_wait(&bar, 0);
+    const long long t2 = clock64();
+    if ((tid & 31) == 0) out[0] = n_blocks, out[1] = t2 - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<512>(tmem);
+}
+
 }  // namespace tw
 
 using namespace tw;
@@ -232,6 +296,15 @@ extern "C" int tw_debug_umma_timing(int n_mma, int N, int ts, int b_noswizzle, l
   const int smem = 193 * 1024 + 1024;
   TW_CUDA(cudaFuncSetAttribute(k_umma_timing, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   k_umma_timing<<<1, 128, smem, (cudaStream_t)stream>>>(n_mma, N, ts, b_noswizzle, out, 0, 1, 0, 32 * 1024);  // the round-1 placement
+  TW_LAUNCH_CHECK();
+  return TW_OK;
+}
+
+extern "C" int tw_debug_umma_overhead(int n_blocks, int per_block, int N, int flags, long long* out, void* stream) {
+  TW_CHECK_ARG(out && n_blocks > 0 && per_block >= 0 && N >= 16 && N <= 256 && N % 16 == 0, "bad args");
+  const int smem = 65 * 1024 + 1024;
+  TW_CUDA(cudaFuncSetAttribute(k_umma_overhead, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  k_umma_overhead<<<1, 128, smem, (cudaStream_t)stream>>>(n_blocks, per_block, N, flags, out);
   TW_LAUNCH_CHECK();
   return TW_OK;
 }

@@ -26,25 +26,29 @@ kw = dict(atom_types=at, x_coords=x, x_velocs=xv, y_coords=y, y_velocs=yv, adj_l
 with torch.no_grad():
     m.log_likelihood(**kw)
     torch.cuda.synchronize()
-    buf = torch.zeros(3 * 1024 * 2 + 8, dtype=torch.int64, device="cuda")
+    NR = 4 if cls == 4 else 3
+    buf = torch.zeros(NR * 1024 * 2 + 8, dtype=torch.int64, device="cuda")
     lib = _lib.load()
     lib.tw_debug_set_trace(cls, buf.data_ptr())
     m.log_likelihood(**kw)
     torch.cuda.synchronize()
     lib.tw_debug_set_trace(cls, None)
 raw = buf.cpu().numpy()
-t = raw[:3 * 2048].reshape(3, 1024, 2)
-c0, g0, c1, g1 = (int(v) for v in raw[3 * 2048:3 * 2048 + 4])
+NR = 4 if cls == 4 else 3
+t = raw[:NR * 2048].reshape(NR, 1024, 2)
+c0, g0, c1, g1 = (int(v) for v in raw[NR * 2048:NR * 2048 + 4])
 if g1 > g0:
     print(f"MMA warp: {c1 - c0} cycles in {g1 - g0} ns -> SM clock {1e3 * (c1 - c0) / (g1 - g0):.0f} MHz")
-t0 = min(int(t[r, 0, 1]) for r in range(3) if t[r, 0, 1] > 0)
+t0 = min(int(t[r, 0, 1]) for r in range(NR) if t[r, 0, 1] > 0)
 if cls == 3:
     names = {0: {0: 'mma: head top', 1: 'mma: scores landed', 2: 'mma: MMA1 issued', 3: 'mma2: Wc kb0 landed', 4: 'mma2: h_full kb0', 5: 'mma2: Wc kb1 landed', 6: 'mma2: h_full kb1', 7: 'mma: sample top (item=sample)', 8: 'mma: xb_full (item=sample)'},
              1: {0: 'epi: wait dm', 1: 'epi: dm_full', 2: 'epi: h arrived', 3: 'epi: LN done', 4: 'epi: init_do done'},
              2: {0: 'conv: wait xs (item=sample)', 1: 'conv: xs_full', 2: 'conv: xb_free', 3: 'conv: done'}}
 elif cls == 4:
-    names = {0: {0: 'mma: head top', 1: 'mma: P(g) issued', 2: 'mma: M(g-1) issued', 3: 'mma: first W unit landed', 4: 'mma: h_full (item = g-1)', 5: 'mma: scores landed (item = g-1)'},
-             1: {0: 'epi: pt_full', 1: 'epi: converted', 2: 'epi: drained previous group'}, 2: {}}
+    names = {0: {0: 'P: head top', 1: 'P: issued'},
+             1: {0: 'epi: pt_full', 1: 'epi: converted', 2: 'epi: drained previous group (item = group)'},
+             2: {0: 'M: head top', 1: 'M: h_full', 2: 'M: scores landed', 3: 'M: issued'},
+             3: {0: 'build: top (item = group)', 1: 'build: tiles free', 2: 'build: tiles written', 3: 'LN: rows landed (item = group)', 4: 'LN: done'}}
 elif cls == 2:
     names = {0: {0: 'mma: sample top', 1: 'mma: hs_full', 2: 'mma: head top', 3: 'mma: scores landed', 4: 'mma: head issued'},
              1: {2: 'epi0: wait d_full', 3: 'epi0: d_full', 5: 'epi0: staging free', 4: 'epi0: staged', 7: 'epi0: sync2', 6: 'epi0: stores issued'},
@@ -54,13 +58,13 @@ else:
            1: {0: "epi0: wait d1", 1: "epi0: d1_full", 2: "epi0: ld done", 3: "epi0: st done", 4: "epi0: arrived", 5: "epi0: LN got y_full (item=tile128)", 6: "epi0: LN stats done", 7: "epi0: LN y_free"},
            2: {0: "epi1: wait d1", 1: "epi1: d1_full", 2: "epi1: ld done", 3: "epi1: st done", 4: "epi1: arrived", 5: "epi1: got y_free", 6: "epi1: init_y done"}}
 rows = []
-for r in range(3):
+for r in range(NR):
     for i in range(1024):
         code, clk = int(t[r, i, 0]), int(t[r, i, 1])
         if clk == 0:
             break
         ev, item = code & 0xFF, code >> 8
-        if lo <= item < hi or (cls == 3 and ((r == 2) or (r == 0 and ev >= 7)) and lo <= item * 6 < hi):
+        if lo <= item < hi or (cls == 4 and r == 3 and lo <= item * 6 + 5 < hi + 6) or (cls == 3 and ((r == 2) or (r == 0 and ev >= 7)) and lo <= item * 6 < hi):
             rows.append((clk - t0, item, names[r][ev]))
 rows.sort()
 prev = rows[0][0] if rows else 0
