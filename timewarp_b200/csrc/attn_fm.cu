@@ -170,12 +170,15 @@ __global__ void __launch_bounds__(kFmThreads, 1) k_attn_fm(FmArgs a) {
       int x_r0 = 0, x_half = 0;
       bool x_done = my_groups == 0;
       long long t_idle = 0;
+      // the score images (157 MB per launch at 1024 x 65 atoms) are read once per launch: evict them first, so that the layer
+      // input / output rows (read three times) and the weights stay L2-resident
+      const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
       while (w_left > 0 || !s_done || !x_done) {
         bool progress = false;
-        if (w_left > 0 && mbar_try_wait(&wc_empty[ws], wp ^ 1)) {
+        if (w_left > 0 && mbar_test_wait(&wc_empty[ws], wp ^ 1)) {
           const int kb = w_u / kParts, part = w_u % kParts;
           mbar_arrive_expect_tx(&wc_full[ws], (uint32_t)kFmWcStage);
-          bulk_g2s(smem + L.wc() + ws * kFmWcStage, a.wc[net] + (size_t)(w_h * 2 + kb) * 32768 + part * 16384, kFmWcStage, &wc_full[ws]);
+          bulk_g2s_hint(smem + L.wc() + ws * kFmWcStage, a.wc[net] + (size_t)(w_h * 2 + kb) * 32768 + part * 16384, kFmWcStage, &wc_full[ws], pol_keep);
           if (++ws == L.wc_stages) ws = 0, wp ^= 1;
           if (++w_u == 2 * kParts) {
             w_u = 0;
@@ -184,12 +187,12 @@ __global__ void __launch_bounds__(kFmThreads, 1) k_attn_fm(FmArgs a) {
           w_left--;
           progress = true;
         }
-        if (!s_done && mbar_try_wait(&sc_empty[ss], sp ^ 1)) {
+        if (!s_done && mbar_test_wait(&sc_empty[ss], sp ^ 1)) {
           const int64_t grp = group_of(s_it);
           const int64_t n = grp * G + s_s;
           const uint8_t* src = a.scores_img + ((size_t)(a.n_cond == a.n ? n : n % a.n_cond) * H + s_h) * (2 * (size_t)mat_bytes);
           mbar_arrive_expect_tx(&sc_full[ss], kParts * mat_bytes);
-          bulk_g2s(smem + L.sc() + ss * L.sc_unit, src, kParts * mat_bytes, &sc_full[ss]);
+          bulk_g2s_hint(smem + L.sc() + ss * L.sc_unit, src, kParts * mat_bytes, &sc_full[ss], pol_stream);
           if (++ss == L.sc_stages) ss = 0, sp ^= 1;
           if (++s_s == samples_in(grp)) {
             s_s = 0;
@@ -202,19 +205,19 @@ __global__ void __launch_bounds__(kFmThreads, 1) k_attn_fm(FmArgs a) {
         }
         if (!x_done) {
           if (x_phase == 1) {
-            if (mbar_try_wait(rows_out, ph_rows)) {
+            if (mbar_test_wait(rows_out, ph_rows)) {
               ph_rows ^= 1;
               asm volatile("fence.proxy.async;" ::: "memory");  // rows written with generic stores, read by the bulk copies
               x_phase = 2, x_r0 = 0, x_half = 0;
               progress = true;
             }
-          } else if (mbar_try_wait(&xs_empty[xs], xp ^ 1)) {
+          } else if (mbar_test_wait(&xs_empty[xs], xp ^ 1)) {
             const int64_t grp = group_of(x_phase == 0 ? x_it : x_it - 1);
             const int rows = samples_in(grp) * V;
             const uint32_t bytes = (uint32_t)(rows - x_r0 < kFmXsRows ? rows - x_r0 : kFmXsRows) * 512u;
             const float* base = (x_phase == 2 && x_half == 1) ? a.out[net] : a.x[net];
             mbar_arrive_expect_tx(&xs_full[xs], bytes);
-            bulk_g2s(smem + L.xs() + xs * kFmXsChunk, base + (grp * G * V + x_r0) * 128, bytes, &xs_full[xs]);
+            bulk_g2s_hint(smem + L.xs() + xs * kFmXsChunk, base + (grp * G * V + x_r0) * 128, bytes, &xs_full[xs], pol_keep);
             if (++xs == kFmXsStages) xs = 0, xp ^= 1;
             if (x_phase == 0) {
               x_r0 += kFmXsRows;
