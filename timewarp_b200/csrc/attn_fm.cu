@@ -47,7 +47,6 @@ struct FmArgs {
   int wc_stages, sc_stages;
   float eps;
   long long* trace;
-  int exp;  // timing experiments (TW_FM_EXP, bring-up only; results are wrong when set)
 };
 
 struct FmSmem {
@@ -71,11 +70,7 @@ __device__ __forceinline__ void fm_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {
-      printf("k_attn_fm: barrier timeout (block %d,%d thread %d bar %u parity %u)\n", blockIdx.x, blockIdx.y, threadIdx.x,
-             smem_u32(bar), parity);
-      __trap();
-    }
+    if (clock64() - t0 > 4000000000LL) __trap();  // (no printf: a call in the wait loop makes the compiler save live registers around it)
   }
 }
 
@@ -375,7 +370,6 @@ __global__ void __launch_bounds__(kFmThreads, 1) k_attn_fm(FmArgs a) {
     // ------------------------------------------------------------------ x-tile builders + LayerNorm (128 threads)
     const int lt = tid - 64;          // 0..127
     const int lw = lt >> 5;           // 0..3
-    const int hw = lane >> 4;         // half-warp: row parity
     const int c = lane & 15;          // 16-byte chunk of a row's bf16 image = 8 features
     uint32_t ph_free = 0;
     const float4 gm = __ldg(reinterpret_cast<const float4*>(a.gamma[net]) + lane), bt = __ldg(reinterpret_cast<const float4*>(a.beta[net]) + lane);
@@ -439,7 +433,7 @@ __global__ void __launch_bounds__(kFmThreads, 1) k_attn_fm(FmArgs a) {
 #pragma unroll
         for (int j = 0; j < 4; j++) {
           const int rl = lw * 4 + j;
-          if (r0 + rl < rows && !(a.exp & 8)) {  // (warp-uniform)
+          if (r0 + rl < rows) {  // (warp-uniform)
             const float4 xv = *reinterpret_cast<const float4*>(xa + rl * 512 + lane * 16);
             const float4 sv = *reinterpret_cast<const float4*>(pa + rl * 512 + lane * 16);
             const float y0 = xv.x + sv.x, y1 = xv.y + sv.y, y2 = xv.z + sv.z, y3 = xv.w + sv.w;
@@ -483,29 +477,35 @@ __global__ void __launch_bounds__(kFmThreads, 1) k_attn_fm(FmArgs a) {
     const int nchunk = half >> 3;           // chunks of 8 columns (<= 10)
     uint32_t ph_pt = 0, ph_dt = 0;
 
-    auto drain = [&](int64_t pit) {  // accumulator of group pit -> pre-LayerNorm rows in `out` (4-byte stores, 128 B per warp)
+    uint32_t r[10][8];
+    // start of this thread's column range as (sample, atom): one division per launch
+    const int col0 = e * half;
+    const int s00 = col0 / VP, at00 = col0 - s00 * VP;
+
+    auto drain = [&](int64_t pit) {  // accumulator of group pit -> registers (DT handed back at once) -> pre-LayerNorm rows in `out`
       fm_wait(dt_full, ph_dt);
       ph_dt ^= 1;
       tc_fence_after();
+      const uint32_t dbase = tmem + lane_base + TM_DT + (uint32_t)col0;
+#pragma unroll
+      for (int i = 0; i < 10; i++)
+        if (i < nchunk) tmem_ld8(dbase + (uint32_t)(8 * i), r[i]);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(dt_free);
       const int64_t grp = group_of(pit);
       const int ns = samples_in(grp);
       float* og = a.out[net] + grp * G * V * 128 + f;
-      const uint32_t dbase = tmem + lane_base + TM_DT;
-#pragma unroll 1
-      for (int i = 0; i < nchunk; i += 2) {
-        uint32_t v0[8], v1[8];
-        tmem_ld8(dbase + (uint32_t)(e * half + 8 * i), v0);
-        if (i + 1 < nchunk) tmem_ld8(dbase + (uint32_t)(e * half + 8 * i + 8), v1);
-        tmem_ld_wait();
+      int s = s00, at = at00;  // 4-byte stores, 128 contiguous bytes per warp; no division in the loop
 #pragma unroll
-        for (int j = 0; j < 16; j++) {
-          const int t = e * half + 8 * i + j;
-          const int s = t / VP, at = t - s * VP;
-          if ((j < 8 || i + 1 < nchunk) && s < ns && at < V) og[(size_t)(s * V + at) * 128] = __uint_as_float(j < 8 ? v0[j] : v1[j - 8]);
+      for (int i = 0; i < 10; i++)
+        if (i < nchunk) {
+#pragma unroll
+          for (int j = 0; j < 8; j++) {
+            if (s < ns && at < V) og[(size_t)(s * V + at) * 128] = __uint_as_float(r[i][j]);
+            if (++at == VP) at = 0, s++;
+          }
         }
-      }
-      tc_fence_before();
-      mbar_arrive(dt_free);
       __threadfence();  // the bulk copies of the LayerNorm stage read these rows through L2
       mbar_arrive(rows_out);
       if (q == 2 && e == 0) { FM_TRACE(1, 2, pit); }
@@ -514,27 +514,24 @@ __global__ void __launch_bounds__(kFmThreads, 1) k_attn_fm(FmArgs a) {
     int64_t g = 0;
     for (int64_t it = 0; it < my_groups; it++) {
       for (int h = 0; h < H; h++, g++) {
-        if (h == 0 && it > 0) drain(it - 1);  // M(last head) of the previous group is issued before P(g): drained first
         const int b = (int)(g & 1);
         fm_wait(&pt_full[b], (ph_pt >> b) & 1u);
         ph_pt ^= 1u << b;
         tc_fence_after();
         if (q == 2 && e == 0) { FM_TRACE(1, 0, g); }
         const uint32_t base = tmem + lane_base + TM_PT + (uint32_t)b * (uint32_t)N;
-        uint32_t r[10][8];
-        const int nchunk_c = (a.exp & 4) ? 0 : nchunk;
 #pragma unroll
         for (int i = 0; i < 10; i++)
-          if (i < nchunk_c) tmem_ld8(base + (uint32_t)(e * half + 8 * i), r[i]);
+          if (i < nchunk) tmem_ld8(base + (uint32_t)(col0 + 8 * i), r[i]);
         tmem_ld_wait();
         fm_epi_bar();  // both halves have read their fp32 columns: the in-place writes below may cross into the other half
 #pragma unroll
         for (int i = 0; i < 10; i++)
-          if (i < nchunk_c) {
+          if (i < nchunk) {
             uint32_t hi[4], lo[4];
 #pragma unroll
             for (int j = 0; j < 4; j++) split2(__uint_as_float(r[i][2 * j]), __uint_as_float(r[i][2 * j + 1]), hi[j], lo[j]);
-            const uint32_t col = (uint32_t)((e * half + 8 * i) >> 1);  // packed column of tokens (8i, 8i+1)
+            const uint32_t col = (uint32_t)((col0 + 8 * i) >> 1);  // packed column of tokens (8i, 8i+1)
             tmem_st4(base + col, hi[0], hi[1], hi[2], hi[3]);
             if (kSplit == 3) tmem_st4(base + (uint32_t)half + col, lo[0], lo[1], lo[2], lo[3]);
           }
@@ -542,6 +539,9 @@ __global__ void __launch_bounds__(kFmThreads, 1) k_attn_fm(FmArgs a) {
         tc_fence_before();
         mbar_arrive(&h_full[b]);
         if (q == 2 && e == 0) { FM_TRACE(1, 1, g); }
+        // The previous group's accumulator: its last mixing head was issued before this group's first projection retired, so
+        // the first conversion of the new group goes first (the mixing issuer needs it next) and the drain follows.
+        if (h == 0 && it > 0) drain(it - 1);
       }
     }
     if (my_groups > 0) drain(my_groups - 1);
@@ -601,10 +601,6 @@ int tc_attn_fm(const tw_flow_config* c, const float* const x[2], float* const ou
   a.scores_img = scores_img;
   a.n = n, a.n_cond = n_cond, a.V = V, a.VP = VP, a.H = c->num_heads, a.eps = c->layer_norm_eps;
   a.trace = g_fm_trace;
-  {
-    const char* e = getenv("TW_FM_EXP");
-    a.exp = e ? atoi(e) : 0;
-  }
   const int per_net = nets == 1 ? 148 : 74;
   const int64_t groups = (n + a.G - 1) / a.G;
   dim3 grid((unsigned)(groups < per_net ? groups : per_net), nets);

@@ -48,7 +48,7 @@ elif cls == 4:
     names = {0: {0: 'P: head top', 1: 'P: issued'},
              1: {0: 'epi: pt_full', 1: 'epi: converted', 2: 'epi: drained previous group (item = group)'},
              2: {0: 'M: head top', 1: 'M: h_full', 2: 'M: scores landed', 3: 'M: issued'},
-             3: {0: 'build: top (item = group)', 1: 'build: tiles free', 2: 'build: tiles written', 3: 'LN: rows landed (item = group)', 4: 'LN: done'}}
+             3: {0: 'build: top (item = group)', 1: 'build: tiles free', 2: 'build: tiles written', 3: 'LN: finished (item = group)', 4: 'prefetch issued', 5: 'LN: rows_out seen', 6: 'LN: batch loads issued', 7: 'LN: pre-LN row 0 arrived', 8: 'LN: x row 0 arrived'}}
 elif cls == 2:
     names = {0: {0: 'mma: sample top', 1: 'mma: hs_full', 2: 'mma: head top', 3: 'mma: scores landed', 4: 'mma: head issued'},
              1: {2: 'epi0: wait d_full', 3: 'epi0: d_full', 5: 'epi0: staging free', 4: 'epi0: staged', 7: 'epi0: sync2', 6: 'epi0: stores issued'},
