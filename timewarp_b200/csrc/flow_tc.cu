@@ -312,7 +312,7 @@ struct FfnSmem {
 template <int kSplit>
 __global__ void __launch_bounds__(kFfnThreads, 1) k_ffn_tc(FfnArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // (pointer arithmetic keeps the shared address space: LDS / STS)
   const int net = blockIdx.y;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n_chunks = a.F / kFfnChunk;
@@ -719,7 +719,7 @@ static_assert(FfnPairSmem::TOTAL + 1024 <= 232448, "pair FFN shared memory excee
 template <int kSplit>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1) k_ffn_pair(FfnArgs a) {  // 11 warps: 3 on one SMSP -> 168 registers
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // (pointer arithmetic keeps the shared address space: LDS / STS)
   const int net = blockIdx.y;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t rank = cluster_ctarank();
@@ -1237,6 +1237,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1) k_f
 }
 
 static long long* g_ffn_trace = nullptr;
+static long long* g_inmlp_trace = nullptr;
 static long long* g_mix_trace = nullptr;
 static long long* g_attn_trace = nullptr;
 void tc_set_ffn_trace(long long* buf) { g_ffn_trace = buf; }
@@ -1245,6 +1246,7 @@ void tc_set_trace(int cls, long long* buf) {
   if (cls == 2) g_mix_trace = buf;
   if (cls == 3) g_attn_trace = buf;
   if (cls == 4) tc_set_fm_trace(buf);
+  if (cls == 5) g_inmlp_trace = buf;
 }
 
 static int launch_ffn_tc(const tw_flow_config* c, const FfnArgs& a_in, cudaStream_t st) {
@@ -1408,7 +1410,7 @@ __device__ __forceinline__ void group_bar_sync(int g) { asm volatile("bar.sync %
 template <int kSplit>
 __global__ void __launch_bounds__(320, 1) k_mix_tc(MixArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // (pointer arithmetic keeps the shared address space: LDS / STS)
   const int net = blockIdx.y;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int V = a.V, VP = a.VP, H = a.H, n_stages = a.n_stages;
@@ -1652,7 +1654,7 @@ struct MixTokSmem {
 template <int kSplit>
 __global__ void __launch_bounds__(kMixTokThreads, 1) k_mix_tok(MixArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // (pointer arithmetic keeps the shared address space: LDS / STS)
   const int net = blockIdx.y;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int V = a.V, VP = a.VP, H = a.H;
@@ -1899,7 +1901,7 @@ struct ProjArgs {
 template <int kSplit>
 __global__ void __launch_bounds__(192, 1) k_proj_tc(ProjArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // (pointer arithmetic keeps the shared address space: LDS / STS)
   const int net = blockIdx.y;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t n_tiles = (a.M + 127) / 128;
@@ -2064,7 +2066,7 @@ struct AttnSmem {
 template <int kSplit>
 __global__ void __launch_bounds__(kAttnThreads, 1) k_attn_fused(AttnArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // (pointer arithmetic keeps the shared address space: LDS / STS)
   const int net = blockIdx.y;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int V = a.V, VP = a.VP, H = a.H;
@@ -2441,7 +2443,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) k_attn_fused(AttnArgs a) {
 __device__ __forceinline__ float silu_f(float v) { return __fdividef(v, 1.f + __expf(-v)); }
 __device__ __forceinline__ void epi_bar_sync256() { asm volatile("bar.sync 2, 256;" ::: "memory"); }
 
-constexpr int kMlpThreads = 320;  // warp 0 loader, warp 1 MMA, warps 2-9 epilogue (two groups of four)
+constexpr int kInMlpThreads = 832;  // in_mlp: warp 0 weight loader, 1 MMA issuer, 2-17 SiLU epilogue, 18-25 feature gather + output rows
 
 struct InMlpArgs {
   const uint8_t* w1[2];   // [256 x 64] hi 32K | lo 32K
@@ -2456,6 +2458,7 @@ struct InMlpArgs {
   const float* z_other;   // [M,3]
   int64_t M, n_cond;
   int V, E, n_types;
+  long long* trace;  // debug: event trace of CTA (0,0) (tw_debug_set_trace class 5)
 };
 
 struct InMlpSmem {
@@ -2463,30 +2466,43 @@ struct InMlpSmem {
   static constexpr int TOTAL = BARS + 128;
 };
 
+// Chunk pipeline (the fused-FFN scheme with two hidden chunks of 128): items g = (tile, chunk c).
+//   G1(g):   DH[c] = A_tile W1[c]^T                 12 SS MMAs of N = 128 (A: gathered features, smem; K = 64)
+//   SiLU(g): DH[c] fp32 -> silu(. + b1) -> bf16 hi | lo IN PLACE                       [16 epilogue warps: 32 columns per thread]
+//   G2(g):   Y[tile & 1] += H(g) W2[:, c]^T          24 TS MMAs of N = 128 (A: TMEM)
+//   out:     Y[tile & 1] + b2 -> global rows; gather of the next tile's features       [8 gather / output warps]
+// Issue order G1(g), G2(g-1): the tensor pipe executes in issue order, so DH[c] is not overwritten by G1(tile+1, c) before
+// G2(tile, c) has read it, and SiLU(g) overlaps G1(g+1) + G2(g-1).  TMEM: DH0 | DH1 | Y0 | Y1 (128 columns each).
+// (The first version ran gather -> GEMM1 -> SiLU -> GEMM2 -> store tile by tile on the same 8 warps: 88 us per launch for 26 us
+// of tensor work.  A warp retires about one dependent instruction per 4-5 cycles, so the cure is roles that overlap and enough
+// warps per role: with 8 SiLU + 4 output warps the row-per-thread output stores alone took 6.5 k cycles per tile -- 32 cache
+// lines per store instruction -- hence 256-bit stores and half a row per thread.)
 template <int kSplit>
-__global__ void __launch_bounds__(kMlpThreads, 1) k_in_mlp_tc(InMlpArgs a) {
+__global__ void __launch_bounds__(kInMlpThreads, 1) k_in_mlp_tc(InMlpArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // (pointer arithmetic keeps the shared address space: LDS / STS)
   const int net = blockIdx.y;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t n_tiles = (a.M + 127) / 128;
+  const int64_t my_tiles = ((int64_t)blockIdx.x < n_tiles) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + InMlpSmem::BARS);
-  uint64_t* w_full = bars;       // weights resident
-  uint64_t* a_full = bars + 1;   // feature operand written (256)
-  uint64_t* d1_full = bars + 2;  // GEMM1 done
-  uint64_t* h_full = bars + 3;   // hidden in TMEM (256)
-  uint64_t* d2_full = bars + 4;  // GEMM2 done
-  uint64_t* d_free = bars + 5;   // D2 drained (256)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+  uint64_t* w_full = bars;        // weights resident
+  uint64_t* a_full = bars + 1;    // 256 arrivals: feature operand of a tile written
+  uint64_t* a_free = bars + 2;    // commit: G1(tile, 1) retired
+  uint64_t* d1_full = bars + 3;   // [2] commit: G1(tile, c) retired
+  uint64_t* h_full = bars + 5;    // [2] 512 arrivals: H(tile, c) in TMEM
+  uint64_t* y_full = bars + 7;    // [2] commit: G2(tile, 1) retired
+  uint64_t* y_free = bars + 9;    // [2] 256 arrivals: Y[tile & 1] read out
+  uint64_t* w2_full = bars + 11;  // second-layer weights resident
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
   float* b1s = reinterpret_cast<float*>(smem + InMlpSmem::B1);
   float* b2s = reinterpret_cast<float*>(smem + InMlpSmem::B2);
   if (tid == 0) {
     mbar_init(w_full, 1);
+    mbar_init(w2_full, 1);
     mbar_init(a_full, 256);
-    mbar_init(d1_full, 1);
-    mbar_init(h_full, 256);
-    mbar_init(d2_full, 1);
-    mbar_init(d_free, 256);
+    mbar_init(a_free, 1);
+    for (int i = 0; i < 2; i++) mbar_init(&d1_full[i], 1), mbar_init(&h_full[i], 512), mbar_init(&y_full[i], 1), mbar_init(&y_free[i], 256);
     mbar_fence_init();
   }
   if (warp == 1) tmem_alloc<512>(tmem_slot);
@@ -2496,82 +2512,139 @@ __global__ void __launch_bounds__(kMlpThreads, 1) k_in_mlp_tc(InMlpArgs a) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  constexpr uint32_t T_D = 0, T_HHI = 256, T_HLO = 384;
+  constexpr uint32_t T_DH = 0, T_Y = 256;
+  const bool tr_on = a.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0;
+  int tr_n = 0;
+#define IM_TRACE(role, ev, item)                                                      \
+  if (tr_on && tr_n < 1024) {                                                         \
+    a.trace[((role) * 1024 + tr_n) * 2] = (long long)(ev) | ((long long)(item) << 8); \
+    a.trace[((role) * 1024 + tr_n) * 2 + 1] = clock64();                              \
+    tr_n++;                                                                           \
+  }
 
   if (warp == 0) {
     if (elect_one()) {
+      // W1 first, on its own barrier: the first GEMM starts after a third of the bytes (every CTA of a launch pulls the same
+      // 192 KB through L2 at the same moment: ~9 us until the last byte)
       const uint32_t w1b = kSplit == 3 ? 65536 : 32768;
-      mbar_arrive_expect_tx(w_full, w1b + (kSplit == 3 ? 131072 : 4 * 16384));
+      mbar_arrive_expect_tx(w_full, w1b);
       bulk_g2s(smem + InMlpSmem::W1, a.w1[net], w1b, w_full);
-      for (int i = 0; i < 4; i++) bulk_g2s(smem + InMlpSmem::W2 + i * 32768, a.w2[net] + i * 32768, kSplit == 3 ? 32768 : 16384, w_full);
+      mbar_arrive_expect_tx(w2_full, kSplit == 3 ? 131072 : 4 * 16384);
+      for (int i = 0; i < 4; i++) bulk_g2s(smem + InMlpSmem::W2 + i * 32768, a.w2[net] + i * 32768, kSplit == 3 ? 32768 : 16384, w2_full);
     }
     __syncwarp();
   } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
     mbar_wait(w_full, 0);
-    const uint32_t idesc1 = make_idesc_bf16(128, 256, 0, 0), idesc2 = make_idesc_bf16(128, 128, 0, 0);
+    const uint32_t idesc = make_idesc_bf16(128, 128, 0, 0);
     const uint32_t ahi = smem_u32(smem + InMlpSmem::A_HI), alo = smem_u32(smem + InMlpSmem::A_LO);
     const uint32_t w1hi = smem_u32(smem + InMlpSmem::W1), w1lo = w1hi + 32768, w2 = smem_u32(smem + InMlpSmem::W2);
-    uint32_t ph = 0;
-    int64_t it = 0;
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, it++) {
-      mbar_wait(a_full, ph);
-      if (it > 0) mbar_wait(d_free, ph ^ 1);  // previous tile's D2 (aliases D1) has been read
+    auto issue_g2 = [&](int64_t gp) {
+      const int64_t tp = gp >> 1;
+      const int cp = (int)(gp & 1), yb = (int)(tp & 1);
+      IM_TRACE(0, 2, gp);
+      if (gp == 0) mbar_wait(w2_full, 0);
+      mbar_wait(&h_full[cp], (uint32_t)(tp & 1));
+      IM_TRACE(0, 3, gp);
+      if (cp == 0 && tp >= 2) mbar_wait(&y_free[yb], (uint32_t)(((tp - 2) >> 1) & 1));
       tc_fence_after();
       if (elect_one()) {
+        const uint32_t d = tmem + T_Y + yb * 128, hh = tmem + T_DH + cp * 128, hl = hh + 64;
+        const uint32_t wb = w2 + (uint32_t)cp * 65536;  // K blocks 2 cp, 2 cp + 1
 #pragma unroll
-        for (int k = 0; k < 4; k++) mma_ss(tmem + T_D, desc_kmajor_sw128(ahi + k * 32), desc_kmajor_sw128(w1hi + k * 32), idesc1, k > 0);
+        for (int k = 0; k < 8; k++) mma_ts(d, hh + k * 8, desc_kmajor_sw128(wb + (k >> 2) * 32768 + (k & 3) * 32), idesc, (cp | k) != 0);
         if (kSplit == 3) {
 #pragma unroll
-          for (int k = 0; k < 4; k++) mma_ss(tmem + T_D, desc_kmajor_sw128(alo + k * 32), desc_kmajor_sw128(w1hi + k * 32), idesc1, 1);
+          for (int k = 0; k < 8; k++) mma_ts(d, hl + k * 8, desc_kmajor_sw128(wb + (k >> 2) * 32768 + (k & 3) * 32), idesc, 1);
 #pragma unroll
-          for (int k = 0; k < 4; k++) mma_ss(tmem + T_D, desc_kmajor_sw128(ahi + k * 32), desc_kmajor_sw128(w1lo + k * 32), idesc1, 1);
+          for (int k = 0; k < 8; k++) mma_ts(d, hh + k * 8, desc_kmajor_sw128(wb + (k >> 2) * 32768 + 16384 + (k & 3) * 32), idesc, 1);
         }
-        mma_commit(d1_full);
+        if (cp == 1) mma_commit(&y_full[yb]);
       }
       __syncwarp();
-      mbar_wait(h_full, ph);
+      IM_TRACE(0, 4, gp);
+    };
+    for (int64_t g = 0; g < 2 * my_tiles; g++) {
+      const int64_t it = g >> 1;
+      const int c = (int)(g & 1);
+      IM_TRACE(0, 0, g);
+      if (c == 0) mbar_wait(a_full, (uint32_t)(it & 1));
       tc_fence_after();
+      IM_TRACE(0, 1, g);
       if (elect_one()) {
+        const uint32_t d = tmem + T_DH + c * 128;
+        const uint32_t wh = w1hi + (uint32_t)c * 16384, wl = w1lo + (uint32_t)c * 16384;  // hidden units 128 c .. 128 c + 127
 #pragma unroll
-        for (int k = 0; k < 16; k++)
-          mma_ts(tmem + T_D, tmem + T_HHI + k * 8, desc_kmajor_sw128(w2 + (k >> 2) * 32768 + (k & 3) * 32), idesc2, k > 0);
+        for (int k = 0; k < 4; k++) mma_ss(d, desc_kmajor_sw128(ahi + k * 32), desc_kmajor_sw128(wh + k * 32), idesc, k > 0);
         if (kSplit == 3) {
 #pragma unroll
-          for (int k = 0; k < 16; k++)
-            mma_ts(tmem + T_D, tmem + T_HLO + k * 8, desc_kmajor_sw128(w2 + (k >> 2) * 32768 + (k & 3) * 32), idesc2, 1);
+          for (int k = 0; k < 4; k++) mma_ss(d, desc_kmajor_sw128(alo + k * 32), desc_kmajor_sw128(wh + k * 32), idesc, 1);
 #pragma unroll
-          for (int k = 0; k < 16; k++)
-            mma_ts(tmem + T_D, tmem + T_HHI + k * 8, desc_kmajor_sw128(w2 + (k >> 2) * 32768 + 16384 + (k & 3) * 32), idesc2, 1);
+          for (int k = 0; k < 4; k++) mma_ss(d, desc_kmajor_sw128(ahi + k * 32), desc_kmajor_sw128(wl + k * 32), idesc, 1);
         }
-        mma_commit(d2_full);
+        mma_commit(&d1_full[c]);
+        if (c == 1) mma_commit(a_free);
       }
       __syncwarp();
-      ph ^= 1;
+      if (g >= 1) issue_g2(g - 1);
+    }
+    if (my_tiles > 0) issue_g2(2 * my_tiles - 1);
+  } else if (warp < 18) {
+    // ------------------------------------------------------------------ SiLU epilogue: D1 + b1 -> SiLU -> hi | lo in place
+    const int q = warp & 3;
+    const int hq = (warp - 2) >> 2;  // column quarter of the chunk (32 hidden units)
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    for (int64_t g = 0; g < 2 * my_tiles; g++) {
+      const int c = (int)(g & 1);
+      if (warp == 2) { IM_TRACE(1, 0, g); }
+      mbar_wait(&d1_full[c], (uint32_t)((g >> 1) & 1));
+      tc_fence_after();
+      if (warp == 2) { IM_TRACE(1, 1, g); }
+      const uint32_t base = tmem + lane_base + T_DH + c * 128;
+      uint32_t r[32];
+      tmem_ld32(base + hq * 32, r);
+      tmem_ld_wait();
+      asm volatile("bar.sync 2, 512;" ::: "memory");  // every quarter holds its fp32 columns: the in-place writes below cross quarters
+      const float4* bb = reinterpret_cast<const float4*>(b1s + c * 128 + hq * 32);
+      uint32_t hi[16], lo[16];
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        const float4 b4 = bb[j];
+        split2(silu_f(__uint_as_float(r[4 * j]) + b4.x), silu_f(__uint_as_float(r[4 * j + 1]) + b4.y), hi[2 * j], lo[2 * j]);
+        split2(silu_f(__uint_as_float(r[4 * j + 2]) + b4.z), silu_f(__uint_as_float(r[4 * j + 3]) + b4.w), hi[2 * j + 1], lo[2 * j + 1]);
+      }
+      tmem_st16(base + hq * 16, hi);
+      if (kSplit == 3) tmem_st16(base + 64 + hq * 16, lo);
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&h_full[c]);
+      if (warp == 2) { IM_TRACE(1, 2, g); }
     }
   } else {
+    // ------------------------------------------------------------------ feature gather (next tile) + output rows (this tile)
     const int q = warp & 3;
-    const int hf = (warp - 2) >> 2;  // epilogue group: half of the features / hidden units / outputs
+    const int hf = (warp - 18) >> 2;  // half of the features / of the output row
     const int row = q * 32 + lane;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     const int E = a.E;
-    uint32_t ph = 0;
-    auto gather = [&](int64_t tile) {  // features 32*hf .. 32*hf+31 of token `row`
+    const bool own_cond = a.n_cond * a.V == a.M;
+    auto gather = [&](int64_t tile) {  // features 32 hf .. 32 hf + 31 of token `row` (E + 9 real ones): bf16 hi / lo K-major SW128 rows
       const int64_t m = tile * 128 + row;
       float f[32];
 #pragma unroll
       for (int j = 0; j < 32; j++) f[j] = 0.f;
       if (m < a.M) {
         const int64_t smp = m / a.V;
-        const int v = (int)(m % a.V);
-        const int64_t mc = (smp % a.n_cond) * a.V + v;
-        int64_t t = a.atom_types[mc];
-        t = t < 0 ? 0 : (t >= a.n_types ? a.n_types - 1 : t);
-        const float* er = a.embed + t * E;
+        const int v = (int)(m - smp * a.V);
+        const int64_t mc = (own_cond ? smp : smp % a.n_cond) * a.V + v;
         if (E == 32) {
           if (hf == 0) {
+            int64_t t = a.atom_types[mc];
+            t = t < 0 ? 0 : (t >= a.n_types ? a.n_types - 1 : t);
+            const float4* er = reinterpret_cast<const float4*>(a.embed + t * E);
 #pragma unroll
             for (int j = 0; j < 8; j++) {
-              float4 e4 = __ldg(reinterpret_cast<const float4*>(er) + j);
+              const float4 e4 = __ldg(er + j);
               f[4 * j] = e4.x, f[4 * j + 1] = e4.y, f[4 * j + 2] = e4.z, f[4 * j + 3] = e4.w;
             }
           } else {
@@ -2583,6 +2656,9 @@ __global__ void __launch_bounds__(kMlpThreads, 1) k_in_mlp_tc(InMlpArgs a) {
             }
           }
         } else {
+          int64_t t = a.atom_types[mc];
+          t = t < 0 ? 0 : (t >= a.n_types ? a.n_types - 1 : t);
+          const float* er = a.embed + t * E;
 #pragma unroll
           for (int j = 0; j < 32; j++) {
             const int e = hf * 32 + j;
@@ -2598,69 +2674,55 @@ __global__ void __launch_bounds__(kMlpThreads, 1) k_in_mlp_tc(InMlpArgs a) {
         uint32_t h[4], l[4];
 #pragma unroll
         for (int j = 0; j < 4; j++) split2(f[c * 8 + 2 * j], f[c * 8 + 2 * j + 1], h[j], l[j]);
-        uint32_t off = row * 128u + (((uint32_t)(hf * 4 + c) ^ (row & 7u)) << 4);
+        const uint32_t off = row * 128u + (((uint32_t)(hf * 4 + c) ^ (row & 7u)) << 4);
         *reinterpret_cast<uint4*>(smem + InMlpSmem::A_HI + off) = make_uint4(h[0], h[1], h[2], h[3]);
-        *reinterpret_cast<uint4*>(smem + InMlpSmem::A_LO + off) = make_uint4(l[0], l[1], l[2], l[3]);
+        if (kSplit == 3) *reinterpret_cast<uint4*>(smem + InMlpSmem::A_LO + off) = make_uint4(l[0], l[1], l[2], l[3]);
       }
       fence_proxy_async_smem();
       mbar_arrive(a_full);
     };
-    if ((int64_t)blockIdx.x < n_tiles) gather(blockIdx.x);
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      // ---- hidden units hf*128 .. +127: D1 + b1 -> SiLU -> hi/lo -> TMEM
-      mbar_wait(d1_full, ph);
-      tc_fence_after();
-#pragma unroll 1
-      for (int g = 0; g < 4; g++) {
-        uint32_t r[32];
-        tmem_ld32(tmem + lane_base + T_D + hf * 128 + g * 32, r);
-        tmem_ld_wait();
-        uint32_t hi[16], lo[16];
-#pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-          float v0 = silu_f(__uint_as_float(r[j]) + b1s[hf * 128 + g * 32 + j]);
-          float v1 = silu_f(__uint_as_float(r[j + 1]) + b1s[hf * 128 + g * 32 + j + 1]);
-          split2(v0, v1, hi[j >> 1], lo[j >> 1]);
-        }
-        tmem_st16(tmem + lane_base + T_HHI + hf * 64 + g * 16, hi);
-        if (kSplit == 3) tmem_st16(tmem + lane_base + T_HLO + hf * 64 + g * 16, lo);
+    if (my_tiles > 0) gather(blockIdx.x);
+    for (int64_t it = 0; it < my_tiles; it++) {
+      const int64_t tile = blockIdx.x + it * gridDim.x;
+      if (warp == 18) { IM_TRACE(2, 0, it); }
+      if (it + 1 < my_tiles) {
+        mbar_wait(a_free, (uint32_t)(it & 1));  // G1 of this tile has read the operand
+        if (warp == 18) { IM_TRACE(2, 1, it); }
+        gather(tile + gridDim.x);
+        if (warp == 18) { IM_TRACE(2, 2, it); }
       }
-      tmem_st_wait();
-      tc_fence_before();
-      mbar_arrive(h_full);
-      // the feature operand of the next tile can be written now (GEMM1 of this tile has completed)
-      if (tile + gridDim.x < n_tiles) gather(tile + gridDim.x);
-      // ---- outputs hf*64 .. +63: D2 + b2 -> global
-      mbar_wait(d2_full, ph);
+      const int yb = (int)(it & 1);
+      mbar_wait(&y_full[yb], (uint32_t)((it >> 1) & 1));
       tc_fence_after();
+      if (warp == 18) { IM_TRACE(2, 3, it); }
       const int64_t m = tile * 128 + row;
       float* orow = a.out[net] + m * 128 + hf * 64;
-#pragma unroll 1
-      for (int g = 0; g < 2; g++) {
-        uint32_t r[32];
-        tmem_ld32(tmem + lane_base + T_D + hf * 64 + g * 32, r);
-        tmem_ld_wait();
-        if (m < a.M) {
+      uint32_t r0[32], r1[32];
+      tmem_ld32(tmem + lane_base + T_Y + yb * 128 + hf * 64, r0);
+      tmem_ld32(tmem + lane_base + T_Y + yb * 128 + hf * 64 + 32, r1);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(&y_free[yb]);  // the accumulator half is in registers
+      if (m < a.M) {
+        const float4* bb = reinterpret_cast<const float4*>(b2s + hf * 64);
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float* bb = b2s + hf * 64 + g * 32 + j;
-            float4 o;
-            o.x = __uint_as_float(r[j]) + bb[0];
-            o.y = __uint_as_float(r[j + 1]) + bb[1];
-            o.z = __uint_as_float(r[j + 2]) + bb[2];
-            o.w = __uint_as_float(r[j + 3]) + bb[3];
-            *reinterpret_cast<float4*>(orow + g * 32 + j) = o;
-          }
+        for (int j = 0; j < 8; j++) {  // 256-bit stores: a row-per-thread store instruction touches 32 cache lines whatever its width
+          const float4 ba = bb[2 * j], bc = bb[2 * j + 1];
+          const uint32_t* rr = j < 4 ? &r0[8 * j] : &r1[8 * (j - 4)];
+          asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(orow + 8 * j), "f"(__uint_as_float(rr[0]) + ba.x),
+                       "f"(__uint_as_float(rr[1]) + ba.y), "f"(__uint_as_float(rr[2]) + ba.z), "f"(__uint_as_float(rr[3]) + ba.w),
+                       "f"(__uint_as_float(rr[4]) + bc.x), "f"(__uint_as_float(rr[5]) + bc.y), "f"(__uint_as_float(rr[6]) + bc.z),
+                       "f"(__uint_as_float(rr[7]) + bc.w)
+                       : "memory");
         }
       }
-      tc_fence_before();
-      mbar_arrive(d_free);
-      ph ^= 1;
+      if (warp == 18) { IM_TRACE(2, 4, it); }
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc<512>(tmem);
+#undef IM_TRACE
 }
 
 // ============================================================================================
@@ -2676,27 +2738,31 @@ struct OutMlpArgs {
   int64_t M;
 };
 struct OutMlpSmem {
-  static constexpr int X_HI = 0, X_LO = 32768, W3 = 65536, B3 = W3 + 131072, W4 = B3 + 1024, RED = W4 + 3 * 1024 + 16;
+  static constexpr int X_HI = 0, X_LO = 32768, W3 = 65536, CST = W3 + 131072, RED = CST + 256 * 16 + 16;
   static constexpr int BARS = RED + 2 * 128 * 4 * 4;
   static constexpr int TOTAL = BARS + 128;
 };
+constexpr int kOutMlpThreads = 576;  // warp 0 weight loader, 1 MMA issuer, 2-9 epilogue (two groups of four), 10-17 x-tile loaders
 
+// Roles overlap: while the epilogue warps run SiLU + the 256 -> 3 layer on the accumulator of tile t (two accumulators), the
+// loader warps convert the rows of tile t + 1 (first half prefetched into registers before the operand buffer is free) and the
+// tensor pipe runs its GEMM.  (First version: the same 8 warps loaded, waited and reduced tile by tile: 57 us per launch.)
 template <int kSplit>
-__global__ void __launch_bounds__(kMlpThreads, 1) k_out_mlp_tc(OutMlpArgs a) {
+__global__ void __launch_bounds__(kOutMlpThreads, 1) k_out_mlp_tc(OutMlpArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // (pointer arithmetic keeps the shared address space: LDS / STS)
   const int net = blockIdx.y;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t n_tiles = (a.M + 127) / 128;
+  const int64_t my_tiles = ((int64_t)blockIdx.x < n_tiles) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OutMlpSmem::BARS);
   uint64_t* w_full = bars;
-  uint64_t* x_full = bars + 1;   // 256
-  uint64_t* d_full = bars + 2;   // [2]
-  uint64_t* d_free = bars + 4;   // [2] 256
+  uint64_t* x_full = bars + 1;   // 256 arrivals: operand images of a tile written
+  uint64_t* d_full = bars + 2;   // [2] commit: GEMM of a tile retired (accumulator ready, operand buffer free)
+  uint64_t* d_free = bars + 4;   // [2] 256 arrivals: accumulator read
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
-  float* b3s = reinterpret_cast<float*>(smem + OutMlpSmem::B3);
-  float* w4s = reinterpret_cast<float*>(smem + OutMlpSmem::W4);  // [3][256] then b4[3]
-  float* red = reinterpret_cast<float*>(smem + OutMlpSmem::RED);  // [2][128][4] partial sums of group 1
+  float4* cst = reinterpret_cast<float4*>(smem + OutMlpSmem::CST);  // per hidden unit: b3, w4[0], w4[1], w4[2]; then b4
+  float* red = reinterpret_cast<float*>(smem + OutMlpSmem::RED);    // [2][128][4] partial sums of group 1
   if (tid == 0) {
     mbar_init(w_full, 1);
     mbar_init(x_full, 256);
@@ -2704,9 +2770,8 @@ __global__ void __launch_bounds__(kMlpThreads, 1) k_out_mlp_tc(OutMlpArgs a) {
     mbar_fence_init();
   }
   if (warp == 1) tmem_alloc<512>(tmem_slot);
-  for (int i = tid; i < 256; i += blockDim.x) b3s[i] = a.b3[net][i];
-  for (int i = tid; i < 768; i += blockDim.x) w4s[i] = a.w4[net][i];
-  if (tid < 3) w4s[768 + tid] = a.b4[net][tid];
+  for (int i = tid; i < 256; i += blockDim.x) cst[i] = make_float4(a.b3[net][i], a.w4[net][i], a.w4[net][256 + i], a.w4[net][512 + i]);
+  if (tid == 0) cst[256] = make_float4(a.b4[net][0], a.b4[net][1], a.b4[net][2], 0.f);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -2724,12 +2789,10 @@ __global__ void __launch_bounds__(kMlpThreads, 1) k_out_mlp_tc(OutMlpArgs a) {
     mbar_wait(w_full, 0);
     const uint32_t idesc = make_idesc_bf16(128, 256, 0, 0);
     const uint32_t xhi = smem_u32(smem + OutMlpSmem::X_HI), xlo = smem_u32(smem + OutMlpSmem::X_LO), w3 = smem_u32(smem + OutMlpSmem::W3);
-    uint32_t ph_x = 0, ph_free[2] = {0, 0};
-    int64_t it = 0;
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, it++) {
-      const int tb = it & 1;
-      mbar_wait(x_full, ph_x);
-      ph_x ^= 1;
+    uint32_t ph_free[2] = {0, 0};
+    for (int64_t it = 0; it < my_tiles; it++) {
+      const int tb = (int)(it & 1);
+      mbar_wait(x_full, (uint32_t)(it & 1));
       if (it >= 2) {
         mbar_wait(&d_free[tb], ph_free[tb]);
         ph_free[tb] ^= 1;
@@ -2758,59 +2821,33 @@ __global__ void __launch_bounds__(kMlpThreads, 1) k_out_mlp_tc(OutMlpArgs a) {
       }
       __syncwarp();
     }
-  } else {
+  } else if (warp < 10) {
+    // ------------------------------------------------------------------ epilogue: SiLU(D + b3) . w4 + b4 (hidden half hf of row `row`)
     const int q = warp & 3;
     const int hf = (warp - 2) >> 2;
     const int row = q * 32 + lane;
-    const int ew = warp - 2;  // 0..7: 16 rows of the tile each
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     uint32_t ph_full[2] = {0, 0};
-    const float* x = a.x[net];
-    auto load_x = [&](int64_t tile) {
-      const int64_t row0 = tile * 128;
-#pragma unroll 1
-      for (int it = 0; it < 16; it += 8) {
-        float4 v[8];
-#pragma unroll
-        for (int u = 0; u < 8; u++) {
-          int r = ew * 16 + it + u;
-          v[u] = (row0 + r < a.M) ? __ldg(reinterpret_cast<const float4*>(x + (row0 + r) * 128) + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-#pragma unroll
-        for (int u = 0; u < 8; u++) {
-          int r = ew * 16 + it + u;
-          uint32_t h0, l0, h1, l1;
-          split2(v[u].x, v[u].y, h0, l0);
-          split2(v[u].z, v[u].w, h1, l1);
-          uint32_t off = sw128_offset(r, lane * 4, 128);
-          *reinterpret_cast<uint2*>(smem + OutMlpSmem::X_HI + off) = make_uint2(h0, h1);
-          *reinterpret_cast<uint2*>(smem + OutMlpSmem::X_LO + off) = make_uint2(l0, l1);
-        }
-      }
-      fence_proxy_async_smem();
-      mbar_arrive(x_full);
-    };
-    int64_t it = 0;
-    if ((int64_t)blockIdx.x < n_tiles) load_x(blockIdx.x);
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, it++) {
-      const int tb = it & 1;
-      mbar_wait(&d_full[tb], ph_full[tb]);  // GEMM of this tile complete -> the X images are free again
+    for (int64_t it = 0; it < my_tiles; it++) {
+      const int64_t tile = blockIdx.x + it * gridDim.x;
+      const int tb = (int)(it & 1);
+      mbar_wait(&d_full[tb], ph_full[tb]);
       ph_full[tb] ^= 1;
       tc_fence_after();
-      if (tile + gridDim.x < n_tiles) load_x(tile + gridDim.x);
       float s0 = 0.f, s1 = 0.f, s2 = 0.f;
 #pragma unroll 1
       for (int g = 0; g < 4; g++) {
         uint32_t r[32];
         tmem_ld32(tmem + lane_base + tb * 256 + hf * 128 + g * 32, r);
         tmem_ld_wait();
+        const float4* cc = cst + hf * 128 + g * 32;
 #pragma unroll
         for (int j = 0; j < 32; j++) {
-          int col = hf * 128 + g * 32 + j;
-          float v = silu_f(__uint_as_float(r[j]) + b3s[col]);
-          s0 = fmaf(v, w4s[col], s0);
-          s1 = fmaf(v, w4s[256 + col], s1);
-          s2 = fmaf(v, w4s[512 + col], s2);
+          const float4 c4 = cc[j];
+          const float v = silu_f(__uint_as_float(r[j]) + c4.x);
+          s0 = fmaf(v, c4.y, s0);
+          s1 = fmaf(v, c4.z, s1);
+          s2 = fmaf(v, c4.w, s2);
         }
       }
       tc_fence_before();
@@ -2821,12 +2858,52 @@ __global__ void __launch_bounds__(kMlpThreads, 1) k_out_mlp_tc(OutMlpArgs a) {
       if (hf == 0) {
         const int64_t m = tile * 128 + row;
         if (m < a.M) {
+          const float4 b4 = cst[256];
           float* o = a.out[net] + m * 3;
-          o[0] = (s0 + rr[0]) + w4s[768];
-          o[1] = (s1 + rr[1]) + w4s[769];
-          o[2] = (s2 + rr[2]) + w4s[770];
+          o[0] = (s0 + rr[0]) + b4.x;
+          o[1] = (s1 + rr[1]) + b4.y;
+          o[2] = (s2 + rr[2]) + b4.z;
         }
       }
+    }
+  } else {
+    // ------------------------------------------------------------------ x-tile loaders: 16 rows per warp, a float4 column per lane
+    const int lw = warp - 10;  // 0..7
+    const float* x = a.x[net];
+    uint32_t ph_full[2] = {0, 0};
+    float4 v[8];
+    auto load8 = [&](int64_t tile, int half) {
+      const int64_t row0 = tile * 128 + lw * 16 + half * 8;
+#pragma unroll
+      for (int u = 0; u < 8; u++)
+        v[u] = (row0 + u < a.M) ? __ldg(reinterpret_cast<const float4*>(x + (row0 + u) * 128) + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    auto store8 = [&](int half) {
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        const int r = lw * 16 + half * 8 + u;
+        uint32_t h0, l0, h1, l1;
+        split2(v[u].x, v[u].y, h0, l0);
+        split2(v[u].z, v[u].w, h1, l1);
+        const uint32_t off = sw128_offset(r, lane * 4, 128);
+        *reinterpret_cast<uint2*>(smem + OutMlpSmem::X_HI + off) = make_uint2(h0, h1);
+        if (kSplit == 3) *reinterpret_cast<uint2*>(smem + OutMlpSmem::X_LO + off) = make_uint2(l0, l1);
+      }
+    };
+    if (my_tiles > 0) load8(blockIdx.x, 0);
+    for (int64_t it = 0; it < my_tiles; it++) {
+      const int64_t tile = blockIdx.x + it * gridDim.x;
+      if (it >= 1) {  // the GEMM of the previous tile has read the operand images
+        const int pb = (int)((it - 1) & 1);
+        mbar_wait(&d_full[pb], ph_full[pb]);
+        ph_full[pb] ^= 1;
+      }
+      store8(0);
+      load8(tile, 1);
+      store8(1);
+      fence_proxy_async_smem();
+      mbar_arrive(x_full);
+      if (it + 1 < my_tiles) load8(tile + gridDim.x, 0);  // first half of the next tile: in registers while this tile's GEMM runs
     }
   }
   tc_fence_before();
@@ -3102,13 +3179,14 @@ int tc_in_mlp(const tw_flow_config* c, const ParamView& pv, int k, const TcScrat
   }
   a.embed = pv.embed(), a.atom_types = atom_types, a.xc = xc, a.xv = xv, a.z_other = z_other;
   a.M = n * V, a.n_cond = n_cond, a.V = V, a.E = c->atom_embedding_dim, a.n_types = c->num_atom_types;
+  a.trace = g_inmlp_trace;
   int64_t n_tiles = (a.M + 127) / 128;
   dim3 grid((unsigned)(n_tiles < 74 ? n_tiles : 74), 2);
   ProfScope prof(PROF_MLP, st);
   if (c->precision == TW_PRECISION_BF16X3)
-    k_in_mlp_tc<3><<<grid, kMlpThreads, InMlpSmem::TOTAL + 1024, st>>>(a);
+    k_in_mlp_tc<3><<<grid, kInMlpThreads, InMlpSmem::TOTAL + 1024, st>>>(a);
   else
-    k_in_mlp_tc<1><<<grid, kMlpThreads, InMlpSmem::TOTAL + 1024, st>>>(a);
+    k_in_mlp_tc<1><<<grid, kInMlpThreads, InMlpSmem::TOTAL + 1024, st>>>(a);
   TW_LAUNCH_CHECK();
   return TW_OK;
 }
@@ -3136,9 +3214,9 @@ int tc_out_mlp(const tw_flow_config* c, const ParamView& pv, int k, const TcScra
   dim3 grid((unsigned)(n_tiles < 74 ? n_tiles : 74), 2);
   ProfScope prof(PROF_MLP, st);
   if (c->precision == TW_PRECISION_BF16X3)
-    k_out_mlp_tc<3><<<grid, kMlpThreads, OutMlpSmem::TOTAL + 1024, st>>>(a);
+    k_out_mlp_tc<3><<<grid, kOutMlpThreads, OutMlpSmem::TOTAL + 1024, st>>>(a);
   else
-    k_out_mlp_tc<1><<<grid, kMlpThreads, OutMlpSmem::TOTAL + 1024, st>>>(a);
+    k_out_mlp_tc<1><<<grid, kOutMlpThreads, OutMlpSmem::TOTAL + 1024, st>>>(a);
   TW_LAUNCH_CHECK();
   return TW_OK;
 }

@@ -66,7 +66,7 @@ constexpr int kGemmStageBytes = 65536;  // A hi 16K | A lo 16K | B hi 16K | B lo
 template <int kSplit>
 __global__ void __launch_bounds__(192, 1) k_gemm_img(GemmArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // (pointer arithmetic keeps the shared address space: LDS / STS)
   const int net = blockIdx.y;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   uint8_t* ring = smem;

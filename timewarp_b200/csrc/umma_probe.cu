@@ -29,7 +29,7 @@ __device__ __forceinline__ uint32_t off_mnmajor_sw128(uint32_t mn, uint32_t k, u
 
 __global__ void __launch_bounds__(128, 1) k_umma_probe(ProbeArgs p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // (pointer arithmetic keeps the shared address space: LDS / STS)
   uint8_t* sA = smem;                      // up to 128*256*2 = 64 KB
   uint8_t* sB = smem + 64 * 1024;          // up to 256*256*2 = 128 KB
   __shared__ uint64_t bar;
@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(128, 1) k_umma_probe(ProbeArgs p) {
 __global__ void __launch_bounds__(128, 1) k_umma_timing(int n_mma, int N, int ts, int b_noswizzle, long long* out, int fill, int a_units,
                                                         int a_off, int b_off) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // (pointer arithmetic keeps the shared address space: LDS / STS)
   __shared__ uint64_t bar;
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, warp = tid >> 5;
@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(128, 1) k_umma_timing(int n_mma, int N, int ts
 // bit 4: two commits per block.  out[1] = total cycles.
 __global__ void __launch_bounds__(128, 1) k_umma_overhead(int n_blocks, int per_block, int N, int flags, long long* out) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // (pointer arithmetic keeps the shared address space: LDS / STS)
   __shared__ uint64_t bar, bar2, bar3;
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, warp = tid >> 5;

@@ -44,6 +44,10 @@ if cls == 3:
     names = {0: {0: 'mma: head top', 1: 'mma: scores landed', 2: 'mma: MMA1 issued', 3: 'mma2: Wc kb0 landed', 4: 'mma2: h_full kb0', 5: 'mma2: Wc kb1 landed', 6: 'mma2: h_full kb1', 7: 'mma: sample top (item=sample)', 8: 'mma: xb_full (item=sample)'},
              1: {0: 'epi: wait dm', 1: 'epi: dm_full', 2: 'epi: h arrived', 3: 'epi: LN done', 4: 'epi: init_do done'},
              2: {0: 'conv: wait xs (item=sample)', 1: 'conv: xs_full', 2: 'conv: xb_free', 3: 'conv: done'}}
+elif cls == 5:
+    names = {0: {0: 'mma: item top', 1: 'mma: a_full / ready', 2: 'mma: G2 top', 3: 'mma: h_full', 4: 'mma: G2 issued'},
+             1: {0: 'silu: wait d1', 1: 'silu: d1_full', 2: 'silu: done'},
+             2: {0: 'io: tile top (item=tile)', 1: 'io: a_free', 2: 'io: gathered next', 3: 'io: y_full', 4: 'io: rows out'}}
 elif cls == 4:
     names = {0: {0: 'P: head top', 1: 'P: issued'},
              1: {0: 'epi: pt_full', 1: 'epi: converted', 2: 'epi: drained previous group (item = group)'},
@@ -64,7 +68,7 @@ for r in range(NR):
         if clk == 0:
             break
         ev, item = code & 0xFF, code >> 8
-        if lo <= item < hi or (cls == 4 and r == 3 and lo <= item * 6 + 5 < hi + 6) or (cls == 3 and ((r == 2) or (r == 0 and ev >= 7)) and lo <= item * 6 < hi):
+        if (cls == 5 and (lo <= (item if r < 2 else 2 * item) < hi)) or (cls != 5 and lo <= item < hi) or (cls == 4 and r == 3 and lo <= item * 6 + 5 < hi + 6) or (cls == 3 and ((r == 2) or (r == 0 and ev >= 7)) and lo <= item * 6 < hi):
             rows.append((clk - t0, item, names[r][ev]))
 rows.sort()
 prev = rows[0][0] if rows else 0
