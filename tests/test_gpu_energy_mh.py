@@ -267,7 +267,26 @@ def test_sample_on_batches_against_oracle(random_velocs):
         ex = torch.from_numpy(e_pot).float() + ke(yv) - ke(xv) + p_xy[0] - p_yx
         p_ref = torch.clamp(torch.exp(-ex), max=1.0).numpy()
         np.testing.assert_allclose(acc[i], p_ref, rtol=5e-2, atol=1e-6)
-    with pytest.raises(NotImplementedError):
+    # data_augmentation=True (evaluation_utils.py:227-229): one random rigid motion per batch, drawn like the reference draws it
+    # (scipy rotation from numpy's generator, one CPU torch.randn(1, 3)); equal to running on hand-transformed batches
+    from timewarp_b200.dataloader import DenseMolDynBatch
+    from timewarp_b200.equivariance import transform_batch
+
+    dense = [DenseMolDynBatch(names=["ad"], atom_types=b.atom_types, adj_list=b.adj_list, edge_batch_idx=b.edge_batch_idx,
+                              atom_coords=b.atom_coords, atom_velocs=b.atom_velocs, atom_forces=torch.zeros_like(b.atom_coords),
+                              atom_coord_targets=b.atom_coord_targets, atom_veloc_targets=b.atom_veloc_targets,
+                              atom_force_targets=torch.zeros_like(b.atom_coords), masked_elements=b.masked_elements) for b in batches]
+    np.random.seed(3)
+    torch.manual_seed(21)
+    aug = sampling.sample_on_batches(dense, m, torch.device("cuda"), energy, True, masses, random_velocs=random_velocs)
+    np.random.seed(3)
+    torch.manual_seed(21)
+    moved = [transform_batch(b) for b in dense]  # (CPU generator only: the CUDA stream of the model is untouched)
+    ref = sampling.sample_on_batches(moved, m, torch.device("cuda"), energy, False, masses, random_velocs=random_velocs)
+    for a, b in zip(aug, ref):
+        np.testing.assert_array_equal(a, b)
+    assert not np.allclose(aug[4], out[4])  # the conditioning states really moved
+    with pytest.raises(AssertionError):  # like the reference: only dense batches can be augmented
         sampling.sample_on_batches(batches, m, torch.device("cuda"), energy, True, masses)
 
 
@@ -558,3 +577,28 @@ def test_energy_kernel_reference_golden_energies_and_forces():
         np.testing.assert_allclose(f, ref_f, rtol=0.05, atol=0.2)
         assert np.sqrt(((f - ref_f) ** 2).mean()) < 0.1
         np.testing.assert_allclose(e, eo.potential_energy(sysd.as_float32(), g[f"{tag}_positions"].astype(np.float64)), rtol=0, atol=1e-3)
+
+
+def test_openmm_provider_energy_modules(tmp_path):
+    """OpenMMProvider (utils/openmm/openmm_provider.py:110-143): the module it builds from `<protein>-traj-state0.pdb` gives the
+    energies of the pinned 2olx system, is cached, and feeds losses.compute_potential_energy."""
+    from timewarp_b200.energy import OpenMMProvider
+    from timewarp_b200.forcefield import amber99sbildn_obc2
+    from timewarp_b200.losses import compute_potential_energy
+    from timewarp_b200.peptides import tetrapeptide_2olx
+
+    pep = tetrapeptide_2olx()
+    with open(tmp_path / "2olx-traj-state0.pdb", "w") as f:
+        for i, (n, rn, ri, xyz) in enumerate(zip(pep.atom_names, pep.residue_names, pep.residue_index, pep.coords_nm * 10.0)):
+            name = (" " + n) if len(n) < 4 else n
+            f.write("ATOM  %5d %-4s %3s A%4d    %8.3f%8.3f%8.3f  1.00  0.00\n" % (i + 1, name, rn, ri, xyz[0], xyz[1], xyz[2]))
+        f.write("ENDMDL\n")
+    prov = OpenMMProvider(str(tmp_path), parameters="T1-peptides", device="cuda", cache_size=2)
+    mod = prov.get_potential_energy_module("2olx")
+    assert prov.get_potential_energy_module("2olx") is mod
+    x = torch.from_numpy(_confs(pep, 4, 9)).cuda()
+    ref = PeptidePotentialEnergy(amber99sbildn_obc2(pep), temperature=310.0).cuda()(x)
+    torch.testing.assert_close(mod(x), ref, atol=2e-3, rtol=0)  # (PDB coordinates are rounded to 1e-3 A: only the topology is used)
+    mask = torch.zeros(4, pep.num_atoms, dtype=torch.bool, device="cuda")
+    u = compute_potential_energy(x, ["2olx"] * 4, mask, prov)
+    torch.testing.assert_close(u, ref.squeeze(-1) / prov.kbT, atol=1e-3, rtol=0)

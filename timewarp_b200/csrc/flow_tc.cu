@@ -759,6 +759,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1) k_f
     tr_n++;                                                                         \
   }
 
+  if (tr_on && warp == 1) {  // kernel entry / exit stamps of CTA (0,0): slots 4..7 after the event rows
+    long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    a.trace[3 * 2048 + 4] = clock64(), a.trace[3 * 2048 + 5] = gt;
+  }
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FfnPairSmem::BARS);
   uint64_t* full = bars;                         // [8] own half of a weight tile part has landed
   uint64_t* peer_full = full + kPairStages;      // [8] (rank 0) rank 1's half has landed
@@ -1232,6 +1237,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1) k_f
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();  // the peer may still read this CTA's shared memory / arrive on its barriers until here
+  if (tr_on && warp == 1) {
+    long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    a.trace[3 * 2048 + 6] = clock64(), a.trace[3 * 2048 + 7] = gt;
+  }
   if (warp == 1) tmem_dealloc_pair<512>(tmem);
 #undef FFN_TRACE
 }

@@ -149,3 +149,77 @@ class OpenmmPotentialEnergyTorch(PeptidePotentialEnergy):
             t = integrator.getTemperature()
             t = float(getattr(t, "_value", t))
         super().__init__(system, temperature=t)
+
+
+class OpenMMProvider:
+    """Energy modules of several proteins behind one object -- utils/openmm/openmm_provider.py:20-175, same constructor
+    arguments, methods and FIFO cache behaviour (`cache_size` modules; the oldest entry is dropped first; `cache_size <= 0`
+    disables caching).  `get_system(protein)` finds `<protein>-traj-state0.pdb` under `pdb_dirs` like the reference and builds
+    the ff99SB-ILDN + OBC2 `SystemDescription` from the residue table of `timewarp_b200/amber99.py` (the reference calls OpenMM's
+    `ForceField.createSystem`; residues outside the table raise).  `losses.compute_energy` and the energy-based losses take
+    this object wherever they take the reference's."""
+
+    def __init__(self, pdb_dirs, parameters: str = "T1B-peptides", device="cuda", cache_size: int = 8):
+        import os
+
+        if isinstance(pdb_dirs, (str, os.PathLike)):
+            pdb_dirs = [pdb_dirs]
+        self.pdb_dirs = list(pdb_dirs)
+        self.parameters = parameters
+        self.device = device if isinstance(device, torch.device) else torch.device(device)
+        self.cache_size = cache_size
+        self._potential_energy_cache = {}
+        self._masses = {}
+
+    def clear_cache(self):
+        self._potential_energy_cache.clear()
+
+    def clear_cache_to_size(self, size=None):
+        size = self.cache_size if size is None else size
+        if size <= 0:
+            self.clear_cache()
+            return self
+        while len(self._potential_energy_cache) > size:
+            oldest = next(iter(self._potential_energy_cache))  # dicts keep insertion order: first in, first out
+            del self._potential_energy_cache[oldest]
+        return self
+
+    def get_integrator(self):
+        from .md import get_simulation_environment_integrator
+
+        return get_simulation_environment_integrator(self.parameters)
+
+    @property
+    def kbT(self) -> float:
+        return 8.31446261815324e-3 * float(self.get_integrator().getTemperature())  # kJ/mol
+
+    def _peptide(self, protein: str):
+        import os
+
+        from .dataloader import read_pdb_topology
+
+        for pdb_dir in self.pdb_dirs:
+            for dirpath, _, _ in os.walk(str(pdb_dir)):
+                candidate = os.path.join(dirpath, f"{protein}-traj-state0.pdb")
+                if os.path.isfile(candidate):
+                    return read_pdb_topology(candidate, name=protein)
+        raise ValueError(f"could not find PDB file for {protein} in any of the provided paths {self.pdb_dirs}")
+
+    def get_system(self, protein: str):
+        from .forcefield import amber99sbildn_obc2
+
+        return amber99sbildn_obc2(self._peptide(protein))
+
+    def get_potential_energy_module(self, protein: str):
+        if protein in self._potential_energy_cache:
+            return self._potential_energy_cache[protein]
+        self.clear_cache_to_size(self.cache_size - 1)  # room for one more
+        module = OpenmmPotentialEnergyTorch(self.get_system(protein), self.get_integrator(), platform_name="CUDA").to(self.device)
+        if self.cache_size > 0:
+            self._potential_energy_cache[protein] = module
+        return module
+
+    def get_masses(self, protein: str) -> Tensor:
+        if protein not in self._masses:
+            self._masses[protein] = torch.tensor([float(m) for m in self._peptide(protein).masses], device=self.device)  # (float32 like the reference)
+        return self._masses[protein]

@@ -361,12 +361,16 @@ def sample_on_batches(batches, model, device, openmm_potential_energy_torch, dat
     same draws from the device generator in the same order, same 11-tuple of numpy arrays.  `batch` needs the
     DenseMolDynBatch attributes used at :229-252 (atom_types, atom_coords, atom_velocs, atom_coord_targets,
     atom_veloc_targets, adj_list, edge_batch_idx, masked_elements)."""
-    if data_augmentation:
-        raise NotImplementedError("data_augmentation needs the reference's transform_batch (random rotations, equivariance/: out of scope)")
     energy = openmm_potential_energy_torch
     masses = masses.to(device) if masses is not None else None
     cols = {k: [] for k in ("y_c", "y_v", "t_c", "t_v", "c_c", "c_v", "acc", "p_xy", "p_yx", "p_xy_tr", "p_yx_tr", "e_pot", "e_kin")}
     for batch in batches:
+        if data_augmentation:  # :227-229: one random translation + rotation per batch
+            from .dataloader import DenseMolDynBatch
+            from .equivariance import transform_batch
+
+            assert isinstance(batch, DenseMolDynBatch)
+            batch = transform_batch(batch)
         x_coords = batch.atom_coords.to(device).to(torch.float32).contiguous()  # :229
         y_coord_targets = batch.atom_coord_targets.to(device).to(torch.float32).contiguous()
         if random_velocs:  # :232-234

@@ -30,8 +30,12 @@ with torch.no_grad():
     buf = torch.zeros(NR * 1024 * 2 + 8, dtype=torch.int64, device="cuda")
     lib = _lib.load()
     lib.tw_debug_set_trace(cls, buf.data_ptr())
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
     m.log_likelihood(**kw)
+    e1.record()
     torch.cuda.synchronize()
+    print(f"traced pass: {e0.elapsed_time(e1):.3f} ms")
     lib.tw_debug_set_trace(cls, None)
 raw = buf.cpu().numpy()
 NR = 4 if cls == 4 else 3
@@ -39,6 +43,10 @@ t = raw[:NR * 2048].reshape(NR, 1024, 2)
 c0, g0, c1, g1 = (int(v) for v in raw[NR * 2048:NR * 2048 + 4])
 if g1 > g0:
     print(f"MMA warp: {c1 - c0} cycles in {g1 - g0} ns -> SM clock {1e3 * (c1 - c0) / (g1 - g0):.0f} MHz")
+if cls == 1:
+    ce, ge, cx, gx = (int(v) for v in raw[NR * 2048 + 4:NR * 2048 + 8])
+    if gx > ge:
+        print(f"CTA (0,0): entry -> exit {cx - ce} cycles = {gx - ge} ns; entry -> first MMA-loop stamp {c0 - ce} cycles; last MMA-loop stamp -> exit {cx - c1} cycles")
 t0 = min(int(t[r, 0, 1]) for r in range(NR) if t[r, 0, 1] > 0)
 if cls == 3:
     names = {0: {0: 'mma: head top', 1: 'mma: scores landed', 2: 'mma: MMA1 issued', 3: 'mma2: Wc kb0 landed', 4: 'mma2: h_full kb0', 5: 'mma2: Wc kb1 landed', 6: 'mma2: h_full kb1', 7: 'mma: sample top (item=sample)', 8: 'mma: xb_full (item=sample)'},
