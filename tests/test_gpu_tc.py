@@ -77,7 +77,9 @@ def test_bf16_plain_is_close():
                                          # the feature-major attention kernel at every group size: G = 10 (16 atoms), 3 (48), 1 (100, 128);
                                          # batch sizes that leave a partial last group
                                          (11, 16, [16, 15, 1, 16, 9, 16, 16, 3, 16, 16, 2]), (7, 48, None), (5, 100, [100, 99, 81, 100, 97]),
-                                         (3, 128, [128, 127, 113]), (1, 65, None)])
+                                         (3, 128, [128, 127, 113]), (1, 65, None),
+                                         # more than 128 atoms (1hgv has 691): attention on the CUDA-core kernels, MLPs and FFN on tcgen05
+                                         (2, 150, [150, 131]), (1, 691, None)])
 def test_bf16x3_inference_path_odd_sizes_vs_oracle(B, V, lengths):
     """The inference kernels (CTA-pair FFN with a partial last 256-token tile, fused attention with ragged / masked
     samples, samples straddling tile boundaries; 150 x 65 tokens = 39 pair tiles over 37 pairs: two leftover tiles split

@@ -94,7 +94,9 @@ static int conditioner(PassCtx& p, int k) {
   const int D = c->d_model, H = c->num_heads, F = c->dim_feedforward, E = c->atom_embedding_dim, nh = c->num_mlp_hidden;
   const bool pos = (k % 2) == c->position_layer_index_mod_2;
   uint32_t tcs = (c->precision == TW_PRECISION_FP32) ? 0u : tc_stage_mask();
-  if (p.pv.local()) tcs &= ~(uint32_t)(TC_MIX | TC_ATTN_PROJ);  // dot-product attention runs on the CUDA-core kernels
+  // dot-product attention, and samples of more than 128 atoms (the tensor-core attention kernels hold one sample's scores on
+  // chip), run their attention on the CUDA-core kernels; the MLPs and the FFN stay on tcgen05
+  if (p.pv.local() || p.V > 128) tcs &= ~(uint32_t)(TC_MIX | TC_ATTN_PROJ);
   TcScratch tcx = b.tc;
   tcx.packed = p.packed;
   const float* cur[2] = {b.feat, b.feat};
@@ -205,8 +207,8 @@ static int begin_pass(PassCtx& p, const float* x_coords) {
   if (p.c->precision != TW_PRECISION_FP32 && tc_supported(p.c) && tc_scores_direct_supported(p.V))
     return tc_begin_pass_direct(p.c, p.fb.tc, p.fb.xc, p.mask, ls, p.n_cond, p.V, p.st);  // no fp32 score tensor
   TW_TRY(launch_scores(p.fb.xc, p.mask, ls, p.n_cond, p.V, p.c->num_heads, p.fb.scores, p.st));
-  if (p.c->precision != TW_PRECISION_FP32)
-    TW_TRY(tc_begin_pass(p.c, p.pv, p.fb.tc, p.fb.scores, p.mask, p.n, p.n_cond, p.V, p.st));
+  if (p.c->precision != TW_PRECISION_FP32)  // (V > 128: fp32 scores only, no operand images)
+    TW_TRY(tc_begin_pass(p.c, p.pv, p.fb.tc, p.V > 128 ? nullptr : p.fb.scores, p.mask, p.n, p.n_cond, p.V, p.st));
   return TW_OK;
 }
 

@@ -2935,7 +2935,7 @@ void tc_carve(const tw_flow_config* c, int64_t n, int64_t n_cond, int64_t V, Are
     out->mixed_img[i] = ar.take<uint8_t>(tiles * tile_bytes);
   }
   ar.off = align_up(ar.off, 1024);
-  out->scores_img = ar.take<uint8_t>((size_t)n_cond * c->num_heads * 2 * VP * VP * 2);
+  out->scores_img = ar.take<uint8_t>(V > 128 ? 0 : (size_t)n_cond * c->num_heads * 2 * VP * VP * 2);  // (V > 128: CUDA-core attention)
   ar.off = align_up(ar.off, 1024);
   out->ffn_tail = reinterpret_cast<float*>(ar.take<uint8_t>(kFfnTailBytes));
 }
