@@ -207,8 +207,9 @@ def grad_case(name, cfg, peptide, B, seed, lengths=None, wseed=0, extra_keys=())
         norms.append(0.0 if p.grad is None else float(p.grad.double().norm()))
     out["grad_names"] = np.array(names)
     out["grad_norms"] = np.array(norms)
-    for k in list(GRAD_FULL_KEYS) + list(extra_keys):
-        g = dict(model.named_parameters())[k].grad
+    named = dict(model.named_parameters())
+    for k in [k for k in GRAD_FULL_KEYS if k in named] + list(extra_keys):  # (`local` modules have other attention parameter names)
+        g = named[k].grad
         out["grad::" + k] = (g[:8] if g.numel() > 20000 else g).numpy()  # large matrices: first 8 rows
     np.savez_compressed(os.path.join(HERE, f"{name}.npz"), **out)
     print(name, "loss", float(loss), "total grad norm", float(np.sqrt((np.array(norms) ** 2).sum())))
@@ -400,6 +401,14 @@ def learnable_grad_case():
               extra_keys=["flow.chain.0.scale_transformer.encoder_layers.0.self_attn.attention.log_lengthscales"])
 
 
+def local_grad_case():
+    """`local` attention training (local_self_attention.py:46-119 under autograd): qkv_proj / output_proj gradients."""
+    ad = alanine_dipeptide()
+    grad_case("grads_full_ad22_local", FULL_LOCAL, ad, B=3, seed=33, lengths=[22, 17, 12],
+              extra_keys=["flow.chain.3.shift_transformer.encoder_layers.1.self_attn.qkv_proj.weight",
+                          "flow.chain.3.shift_transformer.encoder_layers.1.self_attn.output_proj.weight"])
+
+
 def chebyshev_grad_case():
     """chebyshev_kernel training: every attention layer's cheb_coeffs receives its own gradient."""
     ad = alanine_dipeptide()
@@ -411,6 +420,9 @@ def chebyshev_grad_case():
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "chebyshev_grad":
         chebyshev_grad_case()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "local_grad":
+        local_grad_case()
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "learnable_grad":
         learnable_grad_case()
@@ -449,6 +461,7 @@ if __name__ == "__main__":
     chebyshev_cases()
     chebyshev_grad_case()
     local_cases()
+    local_grad_case()
     md_case()
     checkpoint_case()
     dataloader_case()

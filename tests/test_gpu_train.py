@@ -9,7 +9,7 @@ import pytest
 import torch
 
 from oracle import flow_oracle as fo
-from tests.common import EMPTY_ADJ, EMPTY_EBI, FULL_C, FULL_L, FULL_O, GOLDEN, build_model
+from tests.common import EMPTY_ADJ, EMPTY_EBI, FULL_C, FULL_L, FULL_LOC, FULL_O, GOLDEN, build_model
 from timewarp_b200 import _lib
 
 pytestmark = pytest.mark.gpu
@@ -97,11 +97,13 @@ def _load(name):
     return {k: (torch.from_numpy(d[k]) if d[k].dtype.kind != "U" else d[k]) for k in d.files}
 
 
-@pytest.mark.parametrize("name", ["grads_full_ad22", "grads_full_ad22_ragged", "grads_full_ad22_learnable", "grads_full_ad22_chebyshev"])
+@pytest.mark.parametrize("name", ["grads_full_ad22", "grads_full_ad22_ragged", "grads_full_ad22_learnable", "grads_full_ad22_chebyshev",
+                                  "grads_full_ad22_local"])
 def test_backward_matches_reference_gradients(name):
     g = _load(name)
     learnable = name.endswith("learnable")
-    m, _ = build_model(FULL_L if learnable else (FULL_C if name.endswith("chebyshev") else FULL_O), "bf16x3", int(g["weight_seed"]))
+    m, _ = build_model(FULL_L if learnable else (FULL_C if name.endswith("chebyshev") else (FULL_LOC if name.endswith("local") else FULL_O)),
+                       "bf16x3", int(g["weight_seed"]))
     loss, grads = _loss_and_grads(m, g)
     assert abs(float(loss) - float(g["loss"])) < 1e-4 * abs(float(g["loss"]))
     names = [str(n) for n in g["grad_names"]]
@@ -157,6 +159,41 @@ def test_backward_matches_oracle_autograd_every_tensor():
         assert err <= _tol(k) * scale, (k, err, float(ref.norm()))
     assert float(np.median(errs)) < GRAD_MEDIAN_RTOL
     print("worst per-tensor gradient rel err", worst, "median", float(np.median(errs)))
+
+
+def test_local_attention_gradients_match_oracle_autograd():
+    """`local` attention trains (local_self_attention.py:46-119; the reference's tests/test_batching.py:132-177 runs train-capable
+    models of all three attention types): every parameter gradient -- qkv_proj / output_proj included -- against the oracle's
+    fp64 autograd on a ragged batch with sparse neighbourhoods (max_radius 0.45 nm, positions spread over ~1 nm)."""
+    torch.manual_seed(17)
+    B, V = 4, 26
+    lengths = [26, 19, 26, 7]
+    mask = torch.zeros(B, V, dtype=torch.bool)
+    for b, n in enumerate(lengths):
+        mask[b, n:] = True
+    keep = (~mask)[:, :, None]
+    x = 0.3 * torch.randn(B, V, 3) * keep
+    y = (x + 0.02 * torch.randn(B, V, 3)) * keep
+    xv, yv = torch.randn(B, V, 3) * keep, torch.randn(B, V, 3) * keep
+    at = torch.randint(0, 5, (B, V)) * (~mask)
+    g = dict(atom_types=at, x_coords=x, x_velocs=xv, y_coords=y, y_velocs=yv, masked_elements=mask)
+    m, sd = build_model(FULL_LOC, "bf16x3", 4)
+    loss, grads = _loss_and_grads(m, g)
+    loss_ref, grads_ref = fo.nll_loss_and_grads(fo.to_dtype(sd, torch.float64), FULL_LOC, at, x.double(), xv.double(), y.double(),
+                                                yv.double(), mask, distance_mode="direct")
+    assert abs(float(loss) - float(loss_ref)) < 1e-4 * abs(float(loss_ref))
+    assert any(k.endswith("qkv_proj.weight") for k in grads_ref) and set(grads_ref) == set(grads)
+    total = float(torch.sqrt(sum(v.double().norm() ** 2 for v in grads_ref.values())))
+    worst, errs = ("", 0.0), []
+    for k, ref in grads_ref.items():
+        err = float((grads[k].double() - ref.double()).norm())
+        scale = max(float(ref.double().norm()), 1e-4 * total)
+        errs.append(err / scale)
+        if err / scale > worst[1]:
+            worst = (k, err / scale)
+        assert err <= _tol(k) * scale, (k, err, float(ref.norm()))
+    assert float(np.median(errs)) < GRAD_MEDIAN_RTOL
+    print("local attention: worst per-tensor gradient rel err", worst, "median", float(np.median(errs)))
 
 
 def test_learnable_lengthscale_gradient_matches_oracle_autograd():

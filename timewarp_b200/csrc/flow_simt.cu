@@ -300,6 +300,120 @@ int launch_local_attn(const float* qkv0, const float* qkv1, float* o0, float* o1
   return TW_OK;
 }
 
+// Backward of the masked-softmax attention above (training path of `local` attention, local_self_attention.py:46-119 under
+// autograd): given d out, the gradient w.r.t. q | k | v of every head.  The radius mask is a hard function of the positions, so no
+// gradient flows to them.  One CTA per (sample, head, network); pass A: one warp per query row i -- P_i. and dS_i. = P_i. (dP_i. -
+// sum_j P_ij dP_ij) into shared memory, dq_i = dS_i. K / sqrt(D); pass B: one warp per key row j -- dk_j = dS_.j^T Q / sqrt(D),
+// dv_j = P_.j^T d out.  K / V / Q rows are read from global memory (L1 / L2: one head of one sample is V * 3 D floats).
+__global__ void __launch_bounds__(128) k_local_attn_bwd(const float* __restrict__ qkv0, const float* __restrict__ qkv1,
+                                                        const float* __restrict__ do0, const float* __restrict__ do1,
+                                                        float* __restrict__ dqkv0, float* __restrict__ dqkv1, int64_t n_cond, int V, int H,
+                                                        int D, const float* __restrict__ xc, const uint8_t* __restrict__ mask,
+                                                        float max_radius, float inv_sqrt_d) {
+  extern __shared__ float sm[];
+  float* sP = sm;                     // [V][V] attention weights
+  float* sS = sP + (size_t)V * V;     // [V][V] gradient w.r.t. the scores
+  float* sX = sS + (size_t)V * V;     // [V][3]
+  const int64_t n = blockIdx.x;
+  const int h = blockIdx.y, net = blockIdx.z;
+  const int64_t nc = n % n_cond;
+  const int ld = H * 3 * D;
+  const float* qkv = (net ? qkv1 : qkv0) + n * (int64_t)V * ld + (size_t)h * 3 * D;
+  const float* dout = (net ? do1 : do0) + n * (int64_t)V * (H * D) + (size_t)h * D;
+  float* dqkv = (net ? dqkv1 : dqkv0) + n * (int64_t)V * ld + (size_t)h * 3 * D;
+  const uint8_t* mb = mask + nc * V;
+  for (int e = threadIdx.x; e < V * 3; e += blockDim.x) sX[e] = xc[nc * V * 3 + e];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = warp; i < V; i += 4) {
+    const float* q = qkv + (int64_t)i * ld;
+    const float* g = dout + (int64_t)i * (H * D);
+    float* p = sP + (size_t)i * V;
+    float* ds = sS + (size_t)i * V;
+    const float xi = sX[i * 3], yi = sX[i * 3 + 1], zi = sX[i * 3 + 2];
+    float mx = -INFINITY;
+    for (int j = 0; j < V; j++) {
+      const float* kj = qkv + (int64_t)j * ld + D;
+      float part = 0.f;
+      for (int d = lane; d < D; d += 32) part = fmaf(q[d], kj[d], part);
+      part = warp_sum(part) * inv_sqrt_d;
+      const float dx = xi - sX[j * 3], dy = yi - sX[j * 3 + 1], dz = zi - sX[j * 3 + 2];
+      const bool outside = mb[i] || mb[j] || sqrtf(dx * dx + dy * dy + dz * dz) > max_radius;
+      const float sc = outside ? -INFINITY : part;
+      if (lane == 0) p[j] = sc;
+      mx = fmaxf(mx, sc);
+    }
+    __syncwarp();
+    float den = 0.f;
+    for (int j = lane; j < V; j += 32) {
+      const float e = (p[j] == -INFINITY) ? 0.f : expf(p[j] - mx);
+      p[j] = e;
+      den += e;
+    }
+    den = warp_sum(den);
+    const float inv = den > 0.f ? 1.f / den : 0.f;
+    __syncwarp();
+    float rs = 0.f;  // sum_j P_ij dP_ij (every lane ends up with the same value)
+    for (int j = 0; j < V; j++) {
+      const float pij = p[j] * inv;
+      float dp = 0.f;
+      if (pij != 0.f) {  // (warp-uniform)
+        const float* vj = qkv + (int64_t)j * ld + 2 * D;
+        for (int d = lane; d < D; d += 32) dp = fmaf(g[d], vj[d], dp);
+        dp = warp_sum(dp);
+      }
+      if (lane == 0) ds[j] = dp;
+      rs = fmaf(pij, dp, rs);
+    }
+    __syncwarp();
+    for (int j = lane; j < V; j += 32) {
+      const float pij = p[j] * inv;
+      p[j] = pij;
+      ds[j] = pij * (ds[j] - rs);
+    }
+    __syncwarp();
+    for (int d = lane; d < D; d += 32) {
+      float acc = 0.f;
+      for (int j = 0; j < V; j++) {
+        const float w = ds[j];
+        if (w != 0.f) acc = fmaf(w, qkv[(int64_t)j * ld + D + d], acc);
+      }
+      dqkv[(int64_t)i * ld + d] = acc * inv_sqrt_d;
+    }
+  }
+  __syncthreads();
+  for (int j = warp; j < V; j += 4) {
+    for (int d = lane; d < D; d += 32) {
+      float dk = 0.f, dv = 0.f;
+      for (int i = 0; i < V; i++) {
+        const float w = sS[(size_t)i * V + j], pw = sP[(size_t)i * V + j];
+        if (w != 0.f) dk = fmaf(w, qkv[(int64_t)i * ld + d], dk);
+        if (pw != 0.f) dv = fmaf(pw, dout[(int64_t)i * (H * D) + d], dv);
+      }
+      dqkv[(int64_t)j * ld + D + d] = dk * inv_sqrt_d;
+      dqkv[(int64_t)j * ld + 2 * D + d] = dv;
+    }
+  }
+}
+
+int launch_local_attn_bwd(const float* qkv0, const float* qkv1, const float* do0, const float* do1, float* dqkv0, float* dqkv1, int nets,
+                          int64_t n, int64_t n_cond, int V, int H, int D, const float* xc, const uint8_t* mask, float max_radius,
+                          cudaStream_t st) {
+  if (n == 0) return TW_OK;
+  const size_t smem = ((size_t)2 * V * V + (size_t)V * 3) * sizeof(float);
+  TW_CHECK_ARG(smem <= 200 * 1024, "local attention backward: V=%d too large for shared memory", V);
+  static DeviceOnce attr_done;
+  if (!attr_done.done()) {
+    TW_CUDA(cudaFuncSetAttribute(k_local_attn_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_done.mark();
+  }
+  dim3 grid((unsigned)n, H, nets);
+  k_local_attn_bwd<<<grid, 128, smem, st>>>(qkv0, qkv1, do0, do1, dqkv0, dqkv1, n_cond, V, H, D, xc, mask, max_radius,
+                                            1.0f / sqrtf((float)D));
+  TW_LAUNCH_CHECK();
+  return TW_OK;
+}
+
 // ------------------------------------------------------------------------------------------
 // get_centre_of_mass + centring (utils/molecule_utils.py:15-29, flow.py:156-157): one block / state
 __global__ void __launch_bounds__(128) k_prep(const float* __restrict__ x, const uint8_t* __restrict__ mask, int V,

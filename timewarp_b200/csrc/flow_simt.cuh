@@ -54,6 +54,9 @@ int launch_attn_mix(const float* scores, const float* v0, const float* v1, float
                     int64_t n_cond, int V, int H, int Dv, cudaStream_t st);
 // LocalSelfAttention (local_self_attention.py:46-119) on qkv [n*V, H*3*D] (per head: q | k | v): masked softmax over the
 // atoms within max_radius of the conditioning positions xc [n_cond, V, 3]; out [n*V, H*D]
+int launch_local_attn_bwd(const float* qkv0, const float* qkv1, const float* do0, const float* do1, float* dqkv0, float* dqkv1, int nets,
+                          int64_t n, int64_t n_cond, int V, int H, int D, const float* xc, const uint8_t* mask, float max_radius,
+                          cudaStream_t st);  // d(out) -> d(q | k | v)
 int launch_local_attn(const float* qkv0, const float* qkv1, float* o0, float* o1, int nets, int64_t n, int64_t n_cond, int V, int H,
                       int D, const float* xc, const uint8_t* mask, float max_radius, cudaStream_t st);
 int launch_prep(const float* x, const uint8_t* mask, int64_t n_cond, int V, float* xc, float* com, cudaStream_t st);

@@ -863,6 +863,13 @@ struct Tape {
   float* z[17][2];      // flow state (coords, velocs) before coupling layer k; [L] = final latent
   float* delta;
   NetTape net[16][2];
+  // `local` attention (dot-product attention within max_radius): scratch of the taped forward, shared by every layer
+  float* qkv[2];        // [M, 3 H D]
+  float* att[2];        // [M, H D]
+  uint8_t* img_x[2];    // image of the layer input [M,128]
+  uint8_t* img_att[2];  // image of the attention output [M, H D]
+  uint8_t* img_wq[2];   // image of qkv_proj.weight [3 H D, 128]
+  uint8_t* img_wo[2];   // image of output_proj.weight [128, H D]
 };
 
 static size_t carve_tape(const tw_flow_config* c, int64_t B, int V, void* base, size_t cap, Tape* out) {
@@ -870,13 +877,26 @@ static size_t carve_tape(const tw_flow_config* c, int64_t B, int V, void* base, 
   const int64_t M = B * V;
   const int L = c->num_coupling_layers, T = c->num_transformer_layers, H = c->num_heads;
   Tape t{};
+  const bool local = c->attention_type == TW_ATTENTION_LOCAL;
   t.xc = ar.take<float>(M * 3);
   t.com = ar.take<float>(B * 3);
-  t.scores = ar.take<float>((size_t)B * H * V * V);
+  t.scores = ar.take<float>(local ? 0 : (size_t)B * H * V * V);
   ar.off = align_up(ar.off, 1024);
-  t.scores_img = ar.take<uint8_t>(tc_scores_img_bytes(c, B, V));
+  t.scores_img = ar.take<uint8_t>(local ? 0 : tc_scores_img_bytes(c, B, V));
   ar.off = align_up(ar.off, 1024);
-  t.scores_img_t = ar.take<uint8_t>(tc_scores_img_bytes(c, B, V));
+  t.scores_img_t = ar.take<uint8_t>(local ? 0 : tc_scores_img_bytes(c, B, V));
+  if (local) {
+    const int HD = H * c->d_model;
+    for (int s = 0; s < 2; s++) {
+      t.qkv[s] = ar.take<float>(M * 3 * HD);
+      t.att[s] = ar.take<float>(M * HD);
+      ar.off = align_up(ar.off, 1024);
+      t.img_x[s] = ar.take<uint8_t>(plain_img_bytes(M, 2));
+      t.img_att[s] = ar.take<uint8_t>(plain_img_bytes(M, HD / 64));
+      t.img_wq[s] = ar.take<uint8_t>(plain_img_bytes(3 * HD, 2));
+      t.img_wo[s] = ar.take<uint8_t>(plain_img_bytes(128, HD / 64));
+    }
+  }
   t.delta = ar.take<float>(B);
   for (int k = 0; k <= L; k++)
     for (int i = 0; i < 2; i++) t.z[k][i] = ar.take<float>(M * 3);
@@ -890,7 +910,7 @@ static size_t carve_tape(const tw_flow_config* c, int64_t B, int V, void* base, 
         n.r1[i] = ar.take<float>(M * 128);
         n.r2[i] = ar.take<float>(M * 128);
         ar.off = align_up(ar.off, 1024);
-        n.mixed[i] = ar.take<uint8_t>(tc_mixed_img_bytes(c, M));
+        n.mixed[i] = ar.take<uint8_t>(local ? 0 : tc_mixed_img_bytes(c, M));
       }
     }
   if (out) *out = t;
@@ -898,8 +918,9 @@ static size_t carve_tape(const tw_flow_config* c, int64_t B, int V, void* base, 
 }
 
 static int check_train(const tw_flow_config* c, const void* const* params, int64_t B, int64_t V) {
-  if (c && c->attention_type != TW_ATTENTION_KERNEL && c->attention_type != TW_ATTENTION_CHEBYSHEV)
-    return fail(TW_ERR_UNSUPPORTED, "the training path is built for the `kernel` / `learnable_kernel` / `chebyshev_kernel` attention");
+  if (c && c->attention_type != TW_ATTENTION_KERNEL && c->attention_type != TW_ATTENTION_CHEBYSHEV && c->attention_type != TW_ATTENTION_LOCAL)
+    return fail(TW_ERR_UNSUPPORTED, "the training path is built for the `kernel` / `learnable_kernel` / `chebyshev_kernel` / `local` attention");
+  if (c && c->attention_type == TW_ATTENTION_LOCAL && c->max_radius <= 0.f) return fail(TW_ERR_INVALID, "local attention needs max_radius > 0");
   TW_CHECK_ARG(c != nullptr && params != nullptr, "NULL cfg / params");
   if (c->precision == TW_PRECISION_FP32 || !tc_supported(c))
     return fail(TW_ERR_UNSUPPORTED, "the training path needs a tensor-core precision (bf16x3 / bf16) and the flagship layer sizes");
@@ -931,6 +952,14 @@ struct BwdBuffers {
   float* sgrad;          // [B,H,V,V] gradient w.r.t. the attention scores, summed over layers and networks (learnable lengthscales)
   float* dxc;            // [M,3] gradient w.r.t. the centred conditioning coordinates (conditioner inputs + scores)
   float* dxv;            // [M,3] gradient w.r.t. the conditioning velocities
+  // `local` attention: recomputed q | k | v and attention output, their gradients, and the weight images packed per layer
+  float* lqkv[2];        // [M, 3 H D]
+  float* ldqkv[2];       // [M, 3 H D]
+  float* latt[2];        // [M, H D]
+  float* ldatt[2];       // [M, H D]
+  uint8_t* img_dq[2];    // image of ldqkv
+  uint8_t* img_wq[2];    // image of qkv_proj.weight [3 H D, 128]
+  uint8_t* img_wo[2];    // image of output_proj.weight [128, H D]
 };
 
 static size_t carve_bwd(const tw_flow_config* c, int64_t B, int V, void* base, size_t cap, BwdBuffers* out) {
@@ -961,6 +990,19 @@ static size_t carve_bwd(const tw_flow_config* c, int64_t B, int V, void* base, s
     b.img_g[i] = take_img(H * 2);
   }
   b.img_u = take_img(1);
+  if (c->attention_type == TW_ATTENTION_LOCAL) {
+    const int HD = H * 128;
+    for (int i = 0; i < 2; i++) {
+      b.lqkv[i] = ar.take<float>(M * 3 * HD);
+      b.ldqkv[i] = ar.take<float>(M * 3 * HD);
+      b.latt[i] = ar.take<float>(M * HD);
+      b.ldatt[i] = ar.take<float>(M * HD);
+      b.img_dq[i] = take_img(3 * HD / 64);
+      ar.off = align_up(ar.off, 1024);
+      b.img_wq[i] = ar.take<uint8_t>(plain_img_bytes(3 * HD, 2));
+      b.img_wo[i] = ar.take<uint8_t>(plain_img_bytes(128, HD / 64));
+    }
+  }
   b.sgrad = ar.take<float>((size_t)B * H * V * V);
   b.dxc = ar.take<float>(M * 3);
   b.dxv = ar.take<float>(M * 3);
@@ -1009,6 +1051,37 @@ static int pack_act(BwdCtx& x, float* const X[2], uint8_t* const img[2], int C, 
   k_pack_act<<<dim3(C / 64, x.tiles, 2), 256, 0, x.st>>>(a);
   TW_LAUNCH_CHECK();
   return TW_OK;
+}
+
+// operand images of two row-major [rows, C] matrices (one per network)
+static int pack_mat(cudaStream_t st, const float* const X[2], uint8_t* const img[2], int64_t rows, int C) {
+  PackArgs a{};
+  for (int s = 0; s < 2; s++) a.X[s] = X[s], a.img[s] = img[s], a.colsum[s] = nullptr;
+  a.M = rows, a.C = C, a.ld = C, a.n_ct = C / 64;
+  k_pack_act<<<dim3(C / 64, (unsigned)((rows + 127) / 128), 2), 256, 0, st>>>(a);
+  TW_LAUNCH_CHECK();
+  return TW_OK;
+}
+
+// `local` attention, forward half shared by the taped pass and the backward's recomputation (local_self_attention.py:46-119):
+// qkv = x Wqkv^T on the generic tcgen05 GEMM, masked-softmax attention per (sample, head) on CUDA cores -> att [M, H D].
+// Leaves the images of x and of Wqkv in img_x / img_wq.
+static int local_attention_qkv_att(const tw_flow_config* c, const ParamView& pv, int k, int t, float* const x[2], uint8_t* const img_x[2],
+                                   uint8_t* const img_wq[2], float* const qkv[2], float* const att[2], const float* xc,
+                                   const uint8_t* mask, int64_t B, int V, cudaStream_t st) {
+  const int H = c->num_heads, HD = H * 128;
+  const int64_t M = B * V;
+  const int tiles = (int)((M + 127) / 128);
+  const float* xin[2] = {x[0], x[1]};
+  TW_TRY(pack_mat(st, xin, img_x, M, 128));
+  const float* wq[2] = {pv.enc(k, 0, t, 0), pv.enc(k, 1, t, 0)};
+  TW_TRY(pack_mat(st, wq, img_wq, 3 * HD, 128));
+  GemmArgs g{};
+  g.mode = GEMM_NT, g.bn = 128, g.splits = 1;
+  for (int s = 0; s < 2; s++) g.A[s] = plain_img(img_x[s], 2), g.B[s] = plain_img(img_wq[s], 2), g.C[s] = qkv[s];
+  g.ldc = 3 * HD, g.rows = (int)M, g.cols = 3 * HD, g.tiles_m = tiles, g.tiles_n = 3 * HD / 128, g.KB = 2;
+  TW_TRY(launch_gemm(c, g, st));
+  return launch_local_attn(qkv[0], qkv[1], att[0], att[1], 2, B, B, V, H, 128, xc, mask, c->max_radius, st);
 }
 
 static GemmArgs gemm_base(BwdCtx& x, int mode) {
@@ -1132,6 +1205,38 @@ static int conditioner_bwd(BwdCtx& x, int k, float* dz_other, const float* z_oth
       a.M = x.M, a.eps = c->layer_norm_eps;
       k_ln_bwd<<<dim3(x.tiles, 2), 256, 0, x.st>>>(a);
       TW_LAUNCH_CHECK();
+    }
+    if (x.pv.local()) {
+      // local attention: r1 = x + att(x Wqkv^T) Wo^T (local_self_attention.py:46-119).  qkv and att are recomputed from the layer
+      // input; projections and their weight / input gradients on the generic tcgen05 GEMM, the attention core on CUDA cores.
+      const int HD = H * 128;
+      float* hin[2] = {x.tp.net[k][0].h[t], x.tp.net[k][1].h[t]};
+      TW_TRY(local_attention_qkv_att(c, x.pv, k, t, hin, b.img_x, b.img_wq, b.lqkv, b.latt, x.tp.xc, x.mask, x.B, x.V, x.st));
+      const float* att_c[2] = {b.latt[0], b.latt[1]};
+      TW_TRY(pack_mat(x.st, att_c, b.img_g, x.M, HD));
+      GemmArgs w = gemm_base(x, GEMM_TN);  // dWo [128, H D] += dr^T att
+      for (int s = 0; s < 2; s++) w.A[s] = plain_img(b.img_d[s], 2), w.B[s] = plain_img(b.img_g[s], HD / 64), w.C[s] = x.gv.enc(k, s, t, 2);
+      w.ldc = HD, w.rows = 128, w.cols = HD, w.tiles_m = 1, w.tiles_n = HD / 128, w.KB = x.tiles * 2, w.splits = wgrad_splits(x, HD / 128);
+      TW_TRY(launch_gemm(c, w, x.st));
+      const float* wo[2] = {x.pv.enc(k, 0, t, 2), x.pv.enc(k, 1, t, 2)};
+      TW_TRY(pack_mat(x.st, wo, b.img_wo, 128, HD));
+      GemmArgs d = gemm_base(x, GEMM_NN);  // datt [M, H D] = dr Wo
+      for (int s = 0; s < 2; s++) d.A[s] = plain_img(b.img_d[s], 2), d.B[s] = plain_img(b.img_wo[s], HD / 64), d.C[s] = b.ldatt[s];
+      d.ldc = HD, d.rows = (int)x.M, d.cols = HD, d.tiles_m = x.tiles, d.tiles_n = HD / 128, d.KB = 2;
+      TW_TRY(launch_gemm(c, d, x.st));
+      TW_TRY(launch_local_attn_bwd(b.lqkv[0], b.lqkv[1], b.ldatt[0], b.ldatt[1], b.ldqkv[0], b.ldqkv[1], 2, x.B, x.B, x.V, H, 128, x.tp.xc,
+                                   x.mask, c->max_radius, x.st));
+      const float* dq_c[2] = {b.ldqkv[0], b.ldqkv[1]};
+      TW_TRY(pack_mat(x.st, dq_c, b.img_dq, x.M, 3 * HD));
+      GemmArgs wq = gemm_base(x, GEMM_TN);  // dWqkv [3 H D, 128] += dqkv^T x
+      for (int s = 0; s < 2; s++) wq.A[s] = plain_img(b.img_dq[s], 3 * HD / 64), wq.B[s] = plain_img(b.img_x[s], 2), wq.C[s] = x.gv.enc(k, s, t, 0);
+      wq.ldc = 128, wq.rows = 3 * HD, wq.cols = 128, wq.tiles_m = 3 * HD / 128, wq.tiles_n = 1, wq.KB = x.tiles * 2, wq.splits = wgrad_splits(x, 3 * HD / 128);
+      TW_TRY(launch_gemm(c, wq, x.st));
+      GemmArgs e = gemm_base(x, GEMM_NN);  // dx = dr + dqkv Wqkv
+      for (int s = 0; s < 2; s++) e.A[s] = plain_img(b.img_dq[s], 3 * HD / 64), e.B[s] = plain_img(b.img_wq[s], 2), e.C[s] = b.dyA[s], e.resid[s] = b.dr[s];
+      e.ldc = 128, e.ldr = 128, e.rows = (int)x.M, e.cols = 128, e.tiles_m = x.tiles, e.tiles_n = 1, e.KB = 3 * HD / 64;
+      TW_TRY(launch_gemm(c, e, x.st));
+      continue;
     }
     // attention: r1 = x + sum_h W_c,h (A_h x)
     if (x.dls || x.want_inputs) {  // S_h += (dr W_c,h) x^T; the [M, F] scratch of the FFN block is free here
@@ -1318,11 +1423,29 @@ static int taped_conditioner(const tw_flow_config* cfg, const ParamView& pv, con
     float* r2[2] = {tp.net[k][0].r2[t], tp.net[k][1].r2[t]};
     float* hout[2] = {tp.net[k][0].h[t + 1], tp.net[k][1].h[t + 1]};
     tc.mixed_img[0] = tp.net[k][0].mixed[t], tc.mixed_img[1] = tp.net[k][1].mixed[t];
-    if (M % 128) {  // rows past the last token of the tail tile are read by the weight-gradient GEMM: keep them zero
+    if (M % 128 && !pv.local()) {  // rows past the last token of the tail tile are read by the weight-gradient GEMM: keep them zero
       const size_t tile_bytes = tc_mixed_img_bytes(cfg, 128);
       for (int s = 0; s < 2; s++) TW_CUDA(cudaMemsetAsync(tc.mixed_img[s] + (size_t)(M / 128) * tile_bytes, 0, tile_bytes, st));
     }
-    if (pv.chebyshev()) {
+    if (pv.local()) {
+      // qkv projection (tcgen05 GEMM) -> masked softmax attention within max_radius (CUDA cores) -> output projection + residual
+      // (tcgen05 GEMM) -> LayerNorm 1.  Nothing of the attention is taped: the backward recomputes qkv and att from the layer input.
+      const int HD = cfg->num_heads * 128;
+      TW_TRY(local_attention_qkv_att(cfg, pv, k, t, hin, tp.img_x, tp.img_wq, tp.qkv, tp.att, tp.xc, mask, B, (int)V, st));
+      const float* att_c[2] = {tp.att[0], tp.att[1]};
+      TW_TRY(pack_mat(st, att_c, tp.img_att, M, HD));
+      const float* wo[2] = {pv.enc(k, 0, t, 2), pv.enc(k, 1, t, 2)};
+      TW_TRY(pack_mat(st, wo, tp.img_wo, 128, HD));
+      GemmArgs g{};
+      g.mode = GEMM_NT, g.bn = 128, g.splits = 1;
+      for (int s = 0; s < 2; s++)
+        g.A[s] = plain_img(tp.img_att[s], HD / 64), g.B[s] = plain_img(tp.img_wo[s], HD / 64), g.C[s] = r1[s], g.resid[s] = hin[s];
+      g.ldc = 128, g.ldr = 128, g.rows = (int)M, g.cols = 128, g.tiles_m = (int)((M + 127) / 128), g.tiles_n = 1, g.KB = HD / 64;
+      TW_TRY(launch_gemm(cfg, g, st));
+      for (int s = 0; s < 2; s++) TW_CUDA(cudaMemcpyAsync(y1[s], r1[s], (size_t)M * 128 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      TW_TRY(launch_layernorm(y1[0], y1[1], pv.enc(k, 0, t, 7), pv.enc(k, 1, t, 7), pv.enc(k, 0, t, 8), pv.enc(k, 1, t, 8), 2, M, 128,
+                              cfg->layer_norm_eps, st));
+    } else if (pv.chebyshev()) {
       // every attention layer of every network has its own basis function, hence its own scores (kernel_attention.py:333-335):
       // the forward images are rebuilt in place per (layer, network); the backward rebuilds the transposed ones the same way
       for (int net = 0; net < 2; net++) {
@@ -1343,7 +1466,8 @@ static int taped_conditioner(const tw_flow_config* cfg, const ParamView& pv, con
 static int begin_taped_pass(const tw_flow_config* cfg, const ParamView& pv, Tape& tp, const float* x_coords, const uint8_t* mask,
                             int64_t B, int64_t V, cudaStream_t st) {
   TW_TRY(launch_prep(x_coords, mask, B, (int)V, tp.xc, tp.com, st));
-  if (!pv.chebyshev()) {  // (chebyshev_kernel: the scores belong to an attention layer, not to the pass -- taped_conditioner)
+  if (!pv.chebyshev() && !pv.local()) {  // (chebyshev_kernel: the scores belong to an attention layer, not to the pass -- taped_conditioner;
+                                           //  local: no position-only scores at all)
     TW_TRY(launch_scores(tp.xc, mask, pv.enc(0, 0, 0, 1), B, (int)V, cfg->num_heads, tp.scores, st));
     TW_TRY(tc_scores_images(cfg, tp.scores, B, (int)V, tp.scores_img, 0, st));
     TW_TRY(tc_scores_images(cfg, tp.scores, B, (int)V, tp.scores_img_t, 1, st));
@@ -1452,7 +1576,7 @@ static int begin_backward(BwdCtx& x, const tw_flow_config* cfg, const void* cons
   x.B = B, x.V = (int)V, x.M = B * V, x.tiles = (int)((x.M + 127) / 128);
   x.st = (cudaStream_t)stream;
   // lengthscale gradient (learnable_kernel): requested by a non-NULL entry for the lengthscales of chain[0].scale.layer[0]
-  x.dls = x.gv.enc(0, 0, 0, 1);
+  x.dls = x.pv.local() ? nullptr : x.gv.enc(0, 0, 0, 1);  // (local: that slot is unused; the radius mask has no gradient)
   if (x.pv.chebyshev()) {
     TW_CHECK_ARG(!x.dls && !x.want_inputs, "chebyshev_kernel: gradients w.r.t. lengthscales / conditioning state are not built");
     static DeviceOnce attr_cheb;
@@ -1465,7 +1589,7 @@ static int begin_backward(BwdCtx& x, const tw_flow_config* cfg, const void* cons
     TW_CUDA(cudaMemsetAsync(x.b.dxc, 0, (size_t)B * V * 3 * sizeof(float), x.st));
     TW_CUDA(cudaMemsetAsync(x.b.dxv, 0, (size_t)B * V * 3 * sizeof(float), x.st));
   }
-  if (x.dls || x.want_inputs) {
+  if ((x.dls || x.want_inputs) && !x.pv.local()) {
     TW_CHECK_ARG(cfg->num_heads * 128 <= (cfg->dim_feedforward > 256 ? cfg->dim_feedforward : 256),
                  "lengthscale gradient: H * 128 exceeds the [M, dim_feedforward] scratch");
     static DeviceOnce attr_done;
@@ -1479,7 +1603,7 @@ static int begin_backward(BwdCtx& x, const tw_flow_config* cfg, const void* cons
 }
 
 static int finish_backward(BwdCtx& x) {
-  if (x.want_inputs) {
+  if (x.want_inputs && !x.pv.local()) {
     k_score_coord_grad<<<(unsigned)x.B, 256, (size_t)x.V * 3 * sizeof(float), x.st>>>(x.tp.xc, x.mask, x.pv.enc(0, 0, 0, 1), x.b.sgrad, x.V,
                                                                                    x.c->num_heads, x.b.dxc);
     TW_LAUNCH_CHECK();
