@@ -589,7 +589,7 @@ def run_ours(args):
         G = max(1, 160 // VP)
         groups = (args.chains + G - 1) // G
         attn_issued = 2 * issued_factor * H * (groups * 8 * (2 * 128 * G * VP * 16) + args.chains * (VP // 16) * (2 * 128 * VP * 16))
-        attn_roofline = {"bound": "tensor (measured: L2 -> SM operand traffic, DESIGN.md section 5)",
+        attn_roofline = {"bound": "tensor (ncu: tensor pipe 41% of elapsed, L2 22%: a dependency chain between the projection, the in-TMEM conversion and the mixing MMAs, DESIGN.md section 5)",
                          "kernel": "fused attention layer, feature-major (W_o W_v projection of every head, per-sample mixing, residual + LayerNorm), both conditioner nets",
                          "achieved": attn_alg / (attn_ms_avg / 1e3) / 1e12 if attn_ms_avg > 0 else 0.0, "peak": peaks["tf_sustained"],
                          "unit": "TFLOP/s", "issued_tflops": attn_issued / (attn_ms_avg / 1e3) / 1e12 if attn_ms_avg > 0 else 0.0,

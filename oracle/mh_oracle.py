@@ -152,7 +152,7 @@ def mh_step(sd, o, sysd32, kbT, atom_types, x_coords, mask, draws, masses=None, 
 def sample_with_model(sd, o, sysd32, kbT, atom_types, atom_coords, atom_velocs, masked_elements, masses, num_samples, draws,
                       accept=False, random_velocs=False, resample_velocs=False, num_proposal_steps=1, adaptive_parallelism=False,
                       acceptance_rate_smoothing_factor=0.01, reference_signs=None, chirality_centers=None, distance_mode="direct",
-                      trace=None):
+                      trace=None, rotate=False):
     """utils/evaluation_utils.py:468-745 for one chain (batch size 1, :517).  Returns the reference's 4-tuple
     `(sampled_coords, sampled_velocs, accepted, stats)` with `stats` a dict of the ChainStats arrays (:721-731).  If `trace`
     is a list, one dict per iteration (S, u, p_acc, first_acc_idx) is appended for the lock-step comparison."""
@@ -175,6 +175,11 @@ def sample_with_model(sd, o, sysd32, kbT, atom_types, atom_coords, atom_velocs, 
         S = num_proposal_steps
         if random_velocs and resample_velocs:
             x_velocs = draws.randn(x_velocs.shape)  # :590-592
+        if rotate:  # :604-607: Q = random_rotation_matrix() (scipy Rotation.random(), numpy's global generator), applied per atom
+            from scipy.spatial.transform import Rotation as _R  # (the reference's `(Q @ x.T).T` on [1, V, 3] only type-checks for V == 3)
+
+            Q = torch.tensor(_R.random().as_matrix(), dtype=x_coords.dtype)
+            x_coords, x_velocs = x_coords @ Q.T, x_velocs @ Q.T
         zc = draws.randn((S, 1, V, 3)) * torch.exp(sd["coords_prior_log_scale"])  # flow.py:274-277
         zv = draws.randn((S, 1, V, 3)) * torch.exp(sd["velocs_prior_log_scale"])
         rec = proposal_terms(sd, o, sysd32, kbT, atom_types, x_coords, x_velocs, masked_elements, S, zc, zv, masses, random_velocs,

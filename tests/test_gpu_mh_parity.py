@@ -46,9 +46,9 @@ def _model(o, precision, weights):
     return m, sd
 
 
-@pytest.mark.parametrize("S,adaptive", [(1, False), (10, False), (10, True)])
+@pytest.mark.parametrize("S,adaptive,rotate", [(1, False, False), (10, False, False), (10, True, False), (10, False, True)])
 @pytest.mark.parametrize("chirality", [False, True])
-def test_sample_with_model_matches_oracle_chain(S, adaptive, chirality):
+def test_sample_with_model_matches_oracle_chain(S, adaptive, chirality, rotate):
     pep = alanine_dipeptide()
     m, sd = _model(TINY_O, "fp32", "proposal")
     sysd = amber_like_system(pep)
@@ -60,13 +60,15 @@ def test_sample_with_model_matches_oracle_chain(S, adaptive, chirality):
         centers = find_chirality_centers(batch.adj_list, batch.atom_types)
         ref_signs = compute_chirality_sign(batch.atom_coords.cuda(), centers.cuda())
     kw = dict(accept=True, random_velocs=True, resample_velocs=True, num_proposal_steps=S, adaptive_parallelism=adaptive,
-              acceptance_rate_smoothing_factor=0.3 if adaptive else 0.01)
+              acceptance_rate_smoothing_factor=0.3 if adaptive else 0.01, rotate=rotate)
     n = 30
     for seed in (5, 6, 7, 8):  # a seed whose first decisions all lie outside the error band (fp32 path: |u - p_acc| > 1e-4)
         torch.manual_seed(seed)
+        np.random.seed(seed)  # (rotate=True draws its rotations from numpy's global generator, evaluation_utils.py:604-605)
         coords, velocs, accepted, stats = sampling.sample_with_model(batch, m, torch.device("cuda"), energy, masses, n,
                                                                      reference_signs=ref_signs, chirality_centers=centers, **kw)
         torch.manual_seed(seed)
+        np.random.seed(seed)
         trace = []
         o_coords, o_velocs, o_acc, o_st = mo.sample_with_model(
             sd, TINY_O, sysd.as_float32(), energy.kbT, batch.atom_types, batch.atom_coords, batch.atom_velocs, batch.masked_elements, masses,

@@ -287,8 +287,14 @@ def sample_with_model(batch, model, device, openmm_potential_energy_torch, masse
                 x_coords, _ = openmm_step(sim, x_coords, x_velocs * velocs_std, num_steps=num_openmm_steps)
             else:
                 x_coords, x_velocs = openmm_step(sim, x_coords, x_velocs, num_steps=num_openmm_steps)
-        if rotate:  # :604-607
-            raise NotImplementedError("rotate=True: the reference applies `(Q @ x_coords.T).T` to [1, V, 3] tensors (evaluation_utils.py:604-607), which only type-checks for V == 3; not reproduced")
+        if rotate:  # :604-607: one Haar-random rotation of the current state per iteration (drawn like the reference draws it:
+            # scipy's Rotation.random(), numpy's global generator).  The reference writes `(Q @ x_coords.T).T` on the [1, V, 3]
+            # tensors, which only type-checks for V == 3; this is the per-atom rotation that line intends.
+            from .equivariance import random_rotation_matrix
+
+            Q = random_rotation_matrix(device=device, dtype=x_coords.dtype)
+            x_coords = (x_coords @ Q.T).contiguous()
+            x_velocs = (x_velocs @ Q.T).contiguous()
         y_coords, y_velocs, p_xy = model.conditional_sample_with_logp(
             atom_types=atom_types, x_coords=x_coords, x_velocs=x_velocs, adj_list=adj_list, edge_batch_idx=edge_batch_idx,
             masked_elements=masked_elements, num_samples=S)  # :609-617
