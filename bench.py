@@ -658,8 +658,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--weights", default="proposal", choices=["proposal", "init"], help="synthetic weight set (see bench_state_dict)")
-    ap.add_argument("--graph", action="store_true", help="replay one CUDA graph per MH step instead of launching every kernel from the host "
-                    "(measured slower on the power-capped B200: 29.2 vs 27.0 ms/step -- the host launches are already hidden)")
+    ap.add_argument("--graph", action=argparse.BooleanOptionalAction, default=True,
+                    help="replay one CUDA graph per MH step instead of launching every kernel from the host: same GPU time (25.60 vs 25.75 "
+                    "ms per step, tools/graph_vs_eager.py), but enqueueing a step eagerly costs the host 20.8 ms -- with one process per GPU "
+                    "on a shared host the replay keeps the step device-bound (--no-graph: eager launches)")
     ap.add_argument("--workload", default="mh", choices=["mh", "nll"], help="mh: the headline MH benchmark; nll: data-parallel NLL training")
     ap.add_argument("--batch", type=int, default=256, help="--workload nll: samples per GPU")
     ap.add_argument("--no-nll", action="store_true", help="skip the secondary NLL-training throughput measurement")
