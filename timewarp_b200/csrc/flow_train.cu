@@ -349,6 +349,8 @@ __global__ void __launch_bounds__(256) k_act_bwd(ActBwdArgs a) {
   uint8_t* dp_hi = a.img_dpre[net] + toff;
   const int lane = threadIdx.x & 31, kp = lane * 2, gc = tc * 64 + kp;
   float s0 = 0.f, s1 = 0.f;
+  // (requesting every row of the tile before the first store was measured slower: 88 vs 76 us -- the kernel is bound by its
+  // 4-byte image stores, not by load latency)
   for (int r = threadIdx.x >> 5; r < 128; r += 8) {
     const int64_t gr = (int64_t)tr * 128 + r;
     float a0 = 0.f, a1 = 0.f, d0 = 0.f, d1 = 0.f;
@@ -446,12 +448,25 @@ __global__ void __launch_bounds__(256) k_ln_bwd(LnBwdArgs a) {
   const float4 gm = *reinterpret_cast<const float4*>(a.gamma[net] + 4 * lane);
   float4 ag = make_float4(0.f, 0.f, 0.f, 0.f), ab = ag, as = ag;
   uint8_t* tile_hi = a.img_dr[net] + ((size_t)tr * 2 + (lane >> 4)) * 32768;
-  for (int r = w; r < 128; r += 8) {
+  for (int rb = w; rb < 128; rb += 64) {  // eight rows of the warp requested at once (a load-shuffle-store loop runs one round trip per row)
+   float4 xs[8], dys[8];
+#pragma unroll
+   for (int u = 0; u < 8; u++) {
+     const int64_t gr = (int64_t)tr * 128 + rb + 8 * u;
+     xs[u] = dys[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+     if (gr < a.M) {
+       xs[u] = __ldg(reinterpret_cast<const float4*>(a.pre[net] + gr * 128 + 4 * lane));
+       dys[u] = __ldg(reinterpret_cast<const float4*>(a.dy[net] + gr * 128 + 4 * lane));
+     }
+   }
+#pragma unroll
+   for (int u = 0; u < 8; u++) {
+    const int r = rb + 8 * u;
     const int64_t gr = (int64_t)tr * 128 + r;
     float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
     if (gr < a.M) {
-      const float4 x = *reinterpret_cast<const float4*>(a.pre[net] + gr * 128 + 4 * lane);
-      const float4 dy = *reinterpret_cast<const float4*>(a.dy[net] + gr * 128 + 4 * lane);
+      const float4 x = xs[u];
+      const float4 dy = dys[u];
       const float mean = warp_sum((x.x + x.y) + (x.z + x.w)) * (1.f / 128.f);
       const float4 xc = make_float4(x.x - mean, x.y - mean, x.z - mean, x.w - mean);
       const float var = warp_sum(xc.x * xc.x + xc.y * xc.y + xc.z * xc.z + xc.w * xc.w) * (1.f / 128.f);
@@ -473,6 +488,7 @@ __global__ void __launch_bounds__(256) k_ln_bwd(LnBwdArgs a) {
     const uint32_t off = sw128_offset(r, (4 * lane) & 63, 128);
     *reinterpret_cast<uint2*>(tile_hi + off) = make_uint2(h0, h1);
     *reinterpret_cast<uint2*>(tile_hi + 16384 + off) = make_uint2(l0, l1);
+   }
   }
   *reinterpret_cast<float4*>(&red[0][w][4 * lane]) = ag;
   *reinterpret_cast<float4*>(&red[1][w][4 * lane]) = ab;
@@ -628,19 +644,40 @@ __global__ void __launch_bounds__(128) k_wc_chain(WcChainArgs a, int D, int H) {
   __shared__ float srow[128];  // dWc[r, hD + :]  (D == 128, checked by the caller)
   srow[c] = dwc[(size_t)r * HD + h * D + c];
   __syncthreads();
-  // dW_o[i = r, hD + k] += sum_j dWc[r, hD + j] W_v[hD + k, j]: one warp per k, lanes over j (coalesced rows of W_v)
-  for (int k = warp * 32; k < warp * 32 + 32; k++) {
-    const float* wrow = wv + (size_t)(h * D + k) * D;
-    float p = 0.f;
+  // dW_o[i = r, hD + k] += sum_j dWc[r, hD + j] W_v[hD + k, j]: one warp per k, lanes over j (coalesced rows of W_v).
+  // Eight rows in flight per warp: the loads, not the 4 FMAs, are the cost (the first version ran one row at a time: 68 us).
+  for (int k0 = warp * 32; k0 < warp * 32 + 32; k0 += 8) {
+    float p[8];
 #pragma unroll
-    for (int j = lane; j < 128; j += 32) p = fmaf(srow[j], wrow[j], p);
+    for (int u = 0; u < 8; u++) {
+      const float4 w4 = __ldg(reinterpret_cast<const float4*>(wv + (size_t)(h * D + k0 + u) * D) + lane);
+      p[u] = fmaf(srow[4 * lane], w4.x, fmaf(srow[4 * lane + 1], w4.y, fmaf(srow[4 * lane + 2], w4.z, srow[4 * lane + 3] * w4.w)));
+    }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
-    if (lane == 0) a.dwo[net][(size_t)r * HD + h * D + k] += p;
+    for (int u = 0; u < 8; u++) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) p[u] += __shfl_xor_sync(0xffffffffu, p[u], o);
+    }
+    if (lane < 8) {
+      float v = p[0];
+#pragma unroll
+      for (int u = 1; u < 8; u++) v = lane == u ? p[u] : v;
+      a.dwo[net][(size_t)r * HD + h * D + k0 + lane] += v;
+    }
   }
-  // dW_v[hD + k = r, j = c] += sum_i W_o[i, hD + r] dWc[i, hD + c]   (coalesced over c, W_o element broadcast)
+  // dW_v[hD + k = r, j = c] += sum_i W_o[i, hD + r] dWc[i, hD + c]   (coalesced over c, W_o element broadcast), 16 loads in flight
   float acc2 = 0.f;
-  for (int i = 0; i < D; i++) acc2 = fmaf(wo[(size_t)i * HD + h * D + r], dwc[(size_t)i * HD + h * D + c], acc2);
+#pragma unroll 1
+  for (int i0 = 0; i0 < 128; i0 += 16) {
+    float wa[16], da[16];
+#pragma unroll
+    for (int u = 0; u < 16; u++) {
+      wa[u] = __ldg(wo + (size_t)(i0 + u) * HD + h * D + r);
+      da[u] = __ldg(dwc + (size_t)(i0 + u) * HD + h * D + c);
+    }
+#pragma unroll
+    for (int u = 0; u < 16; u++) acc2 = fmaf(wa[u], da[u], acc2);
+  }
   a.dwv[net][(size_t)(h * D + r) * D + c] += acc2;
 }
 
