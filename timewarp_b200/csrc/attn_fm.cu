@@ -340,7 +340,7 @@ __global__ void __launch_bounds__(kFmThreads, 1) k_attn_fm(FmArgs a) {
           if (s == 0) { FM_TRACE(2, 2, g); }
           if (elect_one()) {
             const uint32_t s_addr = sring + ss * L.sc_unit;
-            const uint64_t s_hi = sd0 + (uint64_t)(s_addr >> 4), s_lo = s_hi + (uint64_t)(mat_bytes >> 4);
+            const uint64_t s_hi = sd0 + (uint64_t)((s_addr >> 4) & 0x3FFFu), s_lo = s_hi + (uint64_t)(mat_bytes >> 4);  // (14-bit address field: the shared window of cluster rank 1 has higher bits set)
             const uint32_t d = tmem + TM_DT + (uint32_t)(s * VP);
             const uint32_t p_hi = tmem + TM_PT + (uint32_t)b * (uint32_t)N + (uint32_t)(s * (VP >> 1)), p_lo = p_hi + (uint32_t)(N >> 1);
 #pragma unroll
@@ -555,6 +555,7 @@ __global__ void __launch_bounds__(kFmThreads, 1) k_attn_fm(FmArgs a) {
 // -------------------------------------------------------------------------------------------- host side
 static long long* g_fm_trace = nullptr;
 void tc_set_fm_trace(long long* buf) { g_fm_trace = buf; }
+long long* tc_get_fm_trace() { return g_fm_trace; }
 
 // Group size and ring depths for an atom count; false if the kernel's buffers do not fit (the caller falls back).
 static bool fm_plan(int V, int VP, int64_t n, int* G, int* wcs, int* scs, int* smem_bytes) {

@@ -3081,6 +3081,7 @@ int tc_attention_layer(const tw_flow_config* c, const ParamView& pv, int k, int 
         wcs[s] = tc.packed + L.net_offset(k, net_of[s]) + L.enc0 + (size_t)t * L.enc_stride + L.enc_wc;
         gs[s] = pv.enc(k, net_of[s], t, 7), bs[s] = pv.enc(k, net_of[s], t, 8);
       }
+      if (tc_attn_fm3_supported(V, n)) return tc_attn_fm3(c, x, out, wcs, gs, bs, tc.scores_img, n, n_cond, V, nets, st);  // <= 80 tokens per group
       return tc_attn_fm(c, x, out, wcs, gs, bs, tc.scores_img, n, n_cond, V, nets, st);
     }
     const int fused_smem = (int)AttnSmem(V, VP).total() + 1024;

@@ -55,6 +55,11 @@ int tc_attention_layer(const tw_flow_config* c, const ParamView& pv, int k, int 
                        int only_net = -1);
 // feature-major fused attention layer (attn_fm.cu): project every head first, mix per sample afterwards; any atom count <= 128
 bool tc_attn_fm_supported(int V, int64_t n);
+// ... with groups of at most 80 tokens and a deeper pipeline (attn_fm3.cu: four projection buffers, two accumulators, two tile sets)
+bool tc_attn_fm3_supported(int V, int64_t n);
+int tc_attn_fm3(const tw_flow_config* c, const float* const x[2], float* const out[2], const uint8_t* const wc[2],
+                const float* const gamma[2], const float* const beta[2], const uint8_t* scores_img, int64_t n, int64_t n_cond, int V,
+                int nets, cudaStream_t st);
 int tc_attn_fm(const tw_flow_config* c, const float* const x[2], float* const out[2], const uint8_t* const wc[2],
                const float* const gamma[2], const float* const beta[2], const uint8_t* scores_img, int64_t n, int64_t n_cond, int V,
                int nets, cudaStream_t st);
