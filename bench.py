@@ -584,13 +584,14 @@ def run_ours(args):
         attn_alg = 2 * M * (393216 + 1536 * V)
         VP = (V + 15) // 16 * 16
         H = int(model._cfg.num_heads)
-        # issued by the feature-major kernel (csrc/attn_fm.cu): per (group of G samples, head) the projection as 8 K-steps of
-        # M128 x N x K16 with N = G VP tokens, per (sample, head) the mixing as VP/16 K-steps of M128 x VP x K16; x3 for the split
-        G = max(1, 160 // VP)
+        # issued by the feature-major kernels (csrc/attn_fm3.cu for VP <= 80, csrc/attn_fm.cu above): per (group of G samples, head)
+        # the projection as 8 K-steps of M128 x N x K16 with N = G VP tokens, per (sample, head) the mixing as VP/16 K-steps of
+        # M128 x VP x K16; x3 for the split
+        G = max(1, (80 if VP <= 80 else 160) // VP)
         groups = (args.chains + G - 1) // G
         attn_issued = 2 * issued_factor * H * (groups * 8 * (2 * 128 * G * VP * 16) + args.chains * (VP // 16) * (2 * 128 * VP * 16))
-        attn_roofline = {"bound": "tensor (ncu: tensor pipe 41% of elapsed, L2 22%: a dependency chain between the projection, the in-TMEM conversion and the mixing MMAs, DESIGN.md section 5)",
-                         "kernel": "fused attention layer, feature-major (W_o W_v projection of every head, per-sample mixing, residual + LayerNorm), both conditioner nets",
+        attn_roofline = {"bound": "tensor (in-kernel trace: 2.7 k cycles per (sample, head) for 1.88 k cycles of tensor work; the rest is issue and hand-over latency around N = 80 MMAs, DESIGN.md section 5)",
+                         "kernel": "fused attention layer, feature-major deep pipeline k_attn_fm3 (W_o W_v projection of every head, per-sample mixing, residual + LayerNorm; W_c multicast over CTA pairs), both conditioner nets",
                          "achieved": attn_alg / (attn_ms_avg / 1e3) / 1e12 if attn_ms_avg > 0 else 0.0, "peak": peaks["tf_sustained"],
                          "unit": "TFLOP/s", "issued_tflops": attn_issued / (attn_ms_avg / 1e3) / 1e12 if attn_ms_avg > 0 else 0.0,
                          "avg_launch_ms": attn_ms_avg, "launches_timed": n_attn}
