@@ -26,7 +26,7 @@ namespace tw {
 using namespace umma;
 
 constexpr int kF3Threads = 640;
-constexpr int kF3WcStage = 16384;  // the hi or the lo image of one [128 out x 64 in] K block of W_c,h
+constexpr int kF3WcStage = 32768;  // the hi and the lo image (16 KB each) of one [128 out x 64 in] K block of W_c,h
 constexpr int kF3MaxN = 80;        // tokens of a group: 6 N <= 512 TMEM columns
 constexpr int kF3Pt = 4, kF3Dt = 2, kF3Xb = 2;
 
@@ -162,7 +162,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kF3Threads, 1) k_att
     // ------------------------------------------------------------------ producer: ONE thread feeds the W_c and score-image rings
     if (lane == 0) {
       uint32_t ws = 0, wp = 0;
-      int64_t w_left = w_iters * H * 2 * kParts;  // per head: K block 0 hi, lo, K block 1 hi, lo
+      int64_t w_left = w_iters * H * 2;  // per head: K block 0, K block 1 (hi | lo images)
       int w_h = 0, w_u = 0;
       uint32_t ss = 0, sp = 0;
       int64_t s_it = 0;
@@ -173,15 +173,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kF3Threads, 1) k_att
       while (w_left > 0 || !s_done) {
         bool progress = false;
         if (w_left > 0 && mbar_test_wait(&wc_empty[ws], wp ^ 1)) {
-          const int kb = w_u / kParts, part = w_u % kParts;
-          mbar_arrive_expect_tx(&wc_full[ws], (uint32_t)kF3WcStage);  // (own half + the peer's half)
-          if (a.dbg & 1)
-            bulk_g2s_hint(smem + L.wc() + ws * kF3WcStage, a.wc[net] + (size_t)(w_h * 2 + kb) * 32768 + part * 16384, kF3WcStage, &wc_full[ws], pol_keep);
-          else
-            f3_bulk_g2s_pair(smem + L.wc() + ws * kF3WcStage + rank * (kF3WcStage / 2),
-                             a.wc[net] + (size_t)(w_h * 2 + kb) * 32768 + part * 16384 + rank * (kF3WcStage / 2), kF3WcStage / 2, &wc_full[ws], pol_keep);
+          // each CTA of the pair copies half of the unit into both shared memories: with the 3-way split rank 0 the hi image and
+          // rank 1 the lo image (16 KB each), otherwise rows [64 rank, 64 rank + 64) of the hi image
+          const uint32_t unit = kSplit == 3 ? 32768u : 16384u, half_b = unit / 2;
+          const uint8_t* src = a.wc[net] + (size_t)(w_h * 2 + w_u) * 32768;
+          mbar_arrive_expect_tx(&wc_full[ws], unit);  // (own half + the peer's half)
+          f3_bulk_g2s_pair(smem + L.wc() + ws * kF3WcStage + rank * half_b, src + rank * half_b, half_b, &wc_full[ws], pol_keep);
           if (++ws == L.wc_stages) ws = 0, wp ^= 1;
-          if (++w_u == 2 * kParts) {
+          if (++w_u == 2) {
             w_u = 0;
             if (++w_h == H) w_h = 0;
           }
@@ -232,47 +231,33 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kF3Threads, 1) k_att
         F3_TRACE(0, 0, g);
         const uint32_t d = tmem + (uint32_t)b * (uint32_t)N;
 #pragma unroll
-        for (int kb = 0; kb < 2; kb++) {
+        for (int kb = 0; kb < 2; kb++) {  // one ring unit per K block: W hi | W lo
           const uint64_t xh = kb ? xd_hi1 : xd_hi0, xl = kb ? xd_lo1 : xd_lo0;
-          f3_wait(&wc_full[ws], wp);  // hi image of this K block
+          f3_wait(&wc_full[ws], wp);
           tc_fence_after();
           if (elect_one()) {
-            const uint64_t wd = desc_kmajor_sw128(wring + ws * kF3WcStage);
+            const uint64_t wd = desc_kmajor_sw128(wring + ws * kF3WcStage), wl = desc_kmajor_sw128(wring + ws * kF3WcStage + 16384);
 #pragma unroll
             for (int k = 0; k < 4; k++) mma_ss(d, wd + 2 * k, xh + 2 * k, idescP, (kb | k) != 0);
             if (kSplit == 3) {
 #pragma unroll
               for (int k = 0; k < 4; k++) mma_ss(d, wd + 2 * k, xl + 2 * k, idescP, 1);
+#pragma unroll
+              for (int k = 0; k < 4; k++) mma_ss(d, wl + 2 * k, xh + 2 * k, idescP, 1);
             }
             f3_commit_pair(&wc_empty[ws]);
-            if (kSplit != 3 && kb == 1) {
+            if (kb == 1) {
               mma_commit(&pt_full[b]);
               if (h == H - 1) mma_commit(&xb_free[xbuf]);
             }
           }
           __syncwarp();
           if (++ws == L.wc_stages) ws = 0, wp ^= 1;
-          if (kSplit == 3) {
-            f3_wait(&wc_full[ws], wp);  // lo image
-            tc_fence_after();
-            if (elect_one()) {
-              const uint64_t wd = desc_kmajor_sw128(wring + ws * kF3WcStage);
-#pragma unroll
-              for (int k = 0; k < 4; k++) mma_ss(d, wd + 2 * k, xh + 2 * k, idescP, 1);
-              f3_commit_pair(&wc_empty[ws]);
-              if (kb == 1) {
-                mma_commit(&pt_full[b]);
-                if (h == H - 1) mma_commit(&xb_free[xbuf]);
-              }
-            }
-            __syncwarp();
-            if (++ws == L.wc_stages) ws = 0, wp ^= 1;
-          }
         }
         F3_TRACE(0, 1, g);
       }
     }
-    for (int64_t u = (w_iters - my_groups) * H * 2 * kParts; u > 0; u--) {  // the peer's extra group: release its W_c units unused
+    for (int64_t u = (w_iters - my_groups) * H * 2; u > 0; u--) {  // the peer's extra group: release its W_c units unused
       f3_wait(&wc_full[ws], wp);
       if (elect_one()) mbar_arrive_cluster(&wc_empty[ws], 0), mbar_arrive_cluster(&wc_empty[ws], 1);
       __syncwarp();
@@ -530,7 +515,7 @@ static bool f3_plan(int VP, int64_t n, int* G, int* wcs, int* scs, int* smem_byt
   if (VP > kF3MaxN || VP < 16) return false;
   int g = kF3MaxN / VP;
   if ((int64_t)g > n) g = (int)(n < 1 ? 1 : n);
-  for (int w = 6; w >= 3; w--)  // (a head's W_c is 4 units: the ring should hold more than one head)
+  for (int w = 3; w >= 2; w--)  // (a head's W_c is 2 units of 32 KB: the ring holds 1.5 heads)
     for (int s = 4; s >= (g > 2 ? g : 2); s--) {
       const int total = (int)F3Smem(VP, g, w, s).total();
       if (total <= 232448) {
