@@ -66,6 +66,37 @@ def test_bf16x3_many_tiles_and_tail():
     assert_rel(m.log_likelihood(**kw), m32.log_likelihood(**kw), rel=2e-5, what="after in-place weight update")
 
 
+@pytest.mark.parametrize("V", [17, 31, 33, 47, 49, 63, 64, 66, 79, 81, 97, 127])
+@torch.no_grad()
+def test_attention_kernels_sweep_vs_fp32_path(V):
+    """Every group size / buffer plan of the two feature-major attention kernels (k_attn_fm3 for V <= 80: G = 80 // VP samples per
+    group; k_attn_fm above), with sample counts that leave a partial last group, an odd number of groups (a CTA without work in a
+    pair), more groups than CTAs, ragged masks -- and proposals from ONE conditioning state (shared score images) -- against the
+    fp32 CUDA-core path of the same model."""
+    torch.manual_seed(V)
+    m, _ = build_model(FULL_O, "bf16x3", 5)
+    m32, _ = build_model(FULL_O, "fp32", 5)
+    for B in (1, 2, 7, 151 if V <= 33 else 11):
+        lengths = torch.randint(max(1, V // 2), V + 1, (B,))
+        lengths[0] = V
+        mask = (torch.arange(V)[None, :] >= lengths[:, None]).cuda()
+        keep = (~mask)[:, :, None]
+        at = torch.randint(0, 5, (B, V), device="cuda") * (~mask)
+        x, xv, y, yv = (torch.randn(B, V, 3, device="cuda") * s * keep for s in (0.3, 1.0, 0.3, 1.0))
+        kw = dict(atom_types=at, x_coords=x, x_velocs=xv, adj_list=EMPTY_ADJ.cuda(), edge_batch_idx=EMPTY_EBI.cuda(), masked_elements=mask)
+        assert_rel(m.log_likelihood(y_coords=y, y_velocs=yv, **kw), m32.log_likelihood(y_coords=y, y_velocs=yv, **kw), rel=2e-5,
+                   what=f"V={V} B={B}: bf16x3 vs fp32 path")
+    # S proposals from one state: the conditioning (and its score images) is shared by all S samples
+    S = 5
+    zc, zv = torch.randn(S, 1, V, 3, device="cuda") * 0.01, torch.randn(S, 1, V, 3, device="cuda")
+    kw1 = dict(atom_types=at[:1], x_coords=x[:1], x_velocs=xv[:1], masked_elements=mask[:1], z_coords=zc, z_velocs=zv)
+    a = m.sample_from_latents(**kw1)
+    b = m32.sample_from_latents(**kw1)
+    assert_rel(a[2], b[2], rel=2e-5, what=f"V={V}: S proposals, log p")
+    keep1 = (~mask[:1])[None, :, :, None].expand_as(a[0])
+    assert_rel(a[0][keep1], b[0][keep1], rel=1e-4, what=f"V={V}: S proposals, y_coords")  # (max-norm relative, like the golden tests)
+
+
 def test_bf16_plain_is_close():
     g = load_golden("full_ad22")
     m, _ = build_model(FULL_O, "bf16", 0)
