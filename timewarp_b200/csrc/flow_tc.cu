@@ -764,6 +764,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1) k_f
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
     a.trace[3 * 2048 + 4] = clock64(), a.trace[3 * 2048 + 5] = gt;
   }
+  if (a.trace != nullptr && tid == 0) {  // ... and of EVERY CTA (global timer): slots 8 + 2 * cta, + 1
+    long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    a.trace[3 * 2048 + 8 + 2 * (blockIdx.y * gridDim.x + blockIdx.x)] = gt;
+  }
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FfnPairSmem::BARS);
   uint64_t* full = bars;                         // [8] own half of a weight tile part has landed
   uint64_t* peer_full = full + kPairStages;      // [8] (rank 0) rank 1's half has landed
@@ -1241,6 +1246,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1) k_f
     long long gt;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
     a.trace[3 * 2048 + 6] = clock64(), a.trace[3 * 2048 + 7] = gt;
+  }
+  if (a.trace != nullptr && tid == 0) {
+    long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    a.trace[3 * 2048 + 8 + 2 * (blockIdx.y * gridDim.x + blockIdx.x) + 1] = gt;
   }
   if (warp == 1) tmem_dealloc_pair<512>(tmem);
 #undef FFN_TRACE

@@ -27,7 +27,7 @@ with torch.no_grad():
     m.log_likelihood(**kw)
     torch.cuda.synchronize()
     NR = 4 if cls == 4 else 3
-    buf = torch.zeros(NR * 1024 * 2 + 8, dtype=torch.int64, device="cuda")
+    buf = torch.zeros(NR * 1024 * 2 + 8 + 2 * 160, dtype=torch.int64, device="cuda")
     lib = _lib.load()
     lib.tw_debug_set_trace(cls, buf.data_ptr())
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -47,6 +47,13 @@ if cls == 1:
     ce, ge, cx, gx = (int(v) for v in raw[NR * 2048 + 4:NR * 2048 + 8])
     if gx > ge:
         print(f"CTA (0,0): entry -> exit {cx - ce} cycles = {gx - ge} ns; entry -> first MMA-loop stamp {c0 - ce} cycles; last MMA-loop stamp -> exit {cx - c1} cycles")
+    per = raw[NR * 2048 + 8:NR * 2048 + 8 + 2 * 148].reshape(148, 2)
+    if per[:, 0].min() > 0:
+        e, x = per[:, 0], per[:, 1]
+        t0 = e.min()
+        print(f"all 148 CTAs (global timer, ns after the first entry): entries {int(e.min() - t0)}..{int(e.max() - t0)}, exits {int(x.min() - t0)}..{int(x.max() - t0)}; "
+              f"lifetimes {int((x - e).min())}..{int((x - e).max())} (median {int(np.median(x - e))}); kernel span {int(x.max() - t0)}; "
+              f"exits by cluster rank-0 CTA index: first 20 pairs {[int(v - t0) for v in x[0:40:2]]}")
 t0 = min(int(t[r, 0, 1]) for r in range(NR) if t[r, 0, 1] > 0)
 if cls == 3:
     names = {0: {0: 'mma: head top', 1: 'mma: scores landed', 2: 'mma: MMA1 issued', 3: 'mma2: Wc kb0 landed', 4: 'mma2: h_full kb0', 5: 'mma2: Wc kb1 landed', 6: 'mma2: h_full kb1', 7: 'mma: sample top (item=sample)', 8: 'mma: xb_full (item=sample)'},
