@@ -893,8 +893,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1) k_f
       }
     }
     if (my_tiles > 0) {
-      mbar_wait(ln_staged, ph_staged);  // LayerNorm of the last tile parked (split tile: only by the last pair to arrive)
-      if (!has_partial || *reinterpret_cast<volatile int*>(tail_flag)) store_out(my_tiles - 1);
+      mbar_wait(ln_staged, ph_staged);  // LayerNorm of the last tile parked (split tile: stored by the epilogue warps themselves)
+      if (!has_partial) store_out(my_tiles - 1);
     }
     if (lane == 0) bulk_wait_group0();
     __syncwarp();
@@ -1201,40 +1201,66 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1) k_f
       uint32_t ya[32], yb[32];
       drain_y(ya, yb);
       const int64_t row0t = tile_row0(my_tiles - 1);
-      bool normalise = true;
-      if (has_partial) {
-        // split tile: add this part's accumulator to the scratch tile; the last of the S pairs to arrive owns the result
-        float4* srow = reinterpret_cast<float4*>(a.tail[net] + ((size_t)(part_l * 2 + rank) * 128 + row) * 128 + hf * 64);
+      if (!has_partial) {
+        mbar_wait(xs_full, ph_xsfull);  // the staging buffer is free (the previous tile's rows have been stored)
+        layer_norm_half(row0t, ya, yb);
+      } else {
+        // split tile: every part writes its accumulator to its own slot of the scratch tile (plain coalesced-per-row stores; the
+        // first version added into one tile with float4 atomics: 8-15 us under 16-way contention); when all S parts are in, EVERY
+        // participating pair sums, normalises and stores 1/S of the rows -- one warp per row, straight to global memory (the first
+        // version left the whole tile to the last pair to arrive: another 11 us with 147 SMs idle).
+        float* tile_base = a.tail[net] + (size_t)part_l * 16 * 2 * 128 * 128;
+        float4* slot = reinterpret_cast<float4*>(tile_base + (((size_t)part_p * 2 + rank) * 128 + row) * 128 + hf * 64);
 #pragma unroll
         for (int j = 0; j < 8; j++) {
-          atomicAdd(srow + j, make_float4(__uint_as_float(ya[4 * j]), __uint_as_float(ya[4 * j + 1]), __uint_as_float(ya[4 * j + 2]), __uint_as_float(ya[4 * j + 3])));
-          atomicAdd(srow + 8 + j, make_float4(__uint_as_float(yb[4 * j]), __uint_as_float(yb[4 * j + 1]), __uint_as_float(yb[4 * j + 2]), __uint_as_float(yb[4 * j + 3])));
+          __stcg(slot + j, make_float4(__uint_as_float(ya[4 * j]), __uint_as_float(ya[4 * j + 1]), __uint_as_float(ya[4 * j + 2]), __uint_as_float(ya[4 * j + 3])));
+          __stcg(slot + 8 + j, make_float4(__uint_as_float(yb[4 * j]), __uint_as_float(yb[4 * j + 1]), __uint_as_float(yb[4 * j + 2]), __uint_as_float(yb[4 * j + 3])));
         }
         __threadfence();
         asm volatile("bar.sync 1, 256;" ::: "memory");
+        int* cnt = a.tail_cnt[net] + part_l * 4 + rank;
         if (warp == 2 && lane == 0) {
-          int* cnt = a.tail_cnt[net] + part_l * 2 + rank;
-          const int old = atomicAdd(cnt, 1);
-          if (old == S - 1) atomicExch(cnt, 0);  // self-cleaning: ready for the next layer
-          *tail_flag = (old == S - 1);
-        }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        normalise = *reinterpret_cast<volatile int*>(tail_flag) != 0;
-        if (normalise) {
-          __threadfence();
-#pragma unroll
-          for (int j = 0; j < 8; j++) {
-            const float4 v0 = __ldcg(srow + j), v1 = __ldcg(srow + 8 + j);
-            ya[4 * j] = __float_as_uint(v0.x), ya[4 * j + 1] = __float_as_uint(v0.y), ya[4 * j + 2] = __float_as_uint(v0.z), ya[4 * j + 3] = __float_as_uint(v0.w);
-            yb[4 * j] = __float_as_uint(v1.x), yb[4 * j + 1] = __float_as_uint(v1.y), yb[4 * j + 2] = __float_as_uint(v1.z), yb[4 * j + 3] = __float_as_uint(v1.w);
-            __stcg(srow + j, make_float4(0.f, 0.f, 0.f, 0.f));
-            __stcg(srow + 8 + j, make_float4(0.f, 0.f, 0.f, 0.f));
+          atomicAdd(cnt, 1);
+          // every participant is resident (persistent grid, one CTA per SM): spinning on the others cannot deadlock
+          const long long t0 = clock64();
+          while (*reinterpret_cast<volatile int*>(cnt) < S) {
+            if (clock64() - t0 > 4000000000LL) __trap();
           }
         }
-      }
-      if (normalise) {
-        mbar_wait(xs_full, ph_xsfull);  // the staging buffer is free (the previous tile's rows have been stored)
-        layer_norm_half(row0t, ya, yb);
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        __threadfence();  // (acquire: the other parts' sums)
+        const int rows_per = 128 / S;
+        const float4 gm = *reinterpret_cast<const float4*>(vecs + 128 + 4 * lane), bt = *reinterpret_cast<const float4*>(vecs + 256 + 4 * lane);
+        for (int rr = warp - 2; rr < rows_per; rr += 8) {  // one warp per row, a float4 of columns per lane
+          const int r = part_p * rows_per + rr;
+          if (row0t + r >= a.M) continue;  // (warp-uniform)
+          float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int pp = 0; pp < S; pp++) {
+            const float4 v = __ldcg(reinterpret_cast<const float4*>(tile_base + (((size_t)pp * 2 + rank) * 128 + r) * 128) + lane);
+            y.x += v.x, y.y += v.y, y.z += v.z, y.w += v.w;
+          }
+          float sum = (y.x + y.y) + (y.z + y.w);
+          float sq = fmaf(y.x, y.x, fmaf(y.y, y.y, fmaf(y.z, y.z, y.w * y.w)));
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            sq += __shfl_xor_sync(0xffffffffu, sq, o);
+          }
+          const float mean = sum * (1.f / 128.f);
+          const float var = fmaxf(sq * (1.f / 128.f) - mean * mean, 0.f);
+          const float rstd = 1.0f / sqrtf(var + a.eps);
+          if (a.pre[net]) *(reinterpret_cast<float4*>(a.pre[net] + (row0t + r) * 128) + lane) = y;  // training tape: the pre-LayerNorm sum
+          float4 o4;
+          o4.x = (y.x - mean) * rstd * gm.x + bt.x;
+          o4.y = (y.y - mean) * rstd * gm.y + bt.y;
+          o4.z = (y.z - mean) * rstd * gm.z + bt.z;
+          o4.w = (y.w - mean) * rstd * gm.w + bt.w;
+          *(reinterpret_cast<float4*>(a.out[net] + (row0t + r) * 128) + lane) = o4;
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (warp == 2 && lane == 0) {  // the last pair to have read its rows resets both counters
+          if (atomicAdd(cnt + 2, 1) == S - 1) atomicExch(cnt, 0), atomicExch(cnt + 2, 0);
+        }
       }
       mbar_arrive(ln_staged);
     }
@@ -2963,7 +2989,7 @@ int tc_scores_images(const tw_flow_config* c, const float* scores, int64_t n_con
 
 int tc_begin_pass(const tw_flow_config* c, const ParamView&, TcScratch& tc, const float* scores, const uint8_t*, int64_t,
                   int64_t n_cond, int V, cudaStream_t st) {
-  if (tc.ffn_tail) TW_CUDA(cudaMemsetAsync(tc.ffn_tail, 0, kFfnTailBytes, st));
+  if (tc.ffn_tail) TW_CUDA(cudaMemsetAsync(tc.ffn_tail + kFfnTailFloats, 0, kFfnTailBytes - kFfnTailFloats * 4, st));  // (the counters; the partial sums are overwritten)
   if (!(tc_stage_mask() & TC_MIX) || scores == nullptr) return TW_OK;
   return tc_scores_images(c, scores, n_cond, V, tc.scores_img, 0, st);
 }
@@ -2975,7 +3001,7 @@ bool tc_scores_direct_supported(int V) {  // the CUDA-core attention fallback (b
 // Inference: score images straight from the centred conditioning coordinates (no fp32 score tensor).
 int tc_begin_pass_direct(const tw_flow_config* c, TcScratch& tc, const float* xc, const uint8_t* mask, const float* lengthscales,
                          int64_t n_cond, int V, cudaStream_t st, const float* cheb, bool clear_tail) {
-  if (tc.ffn_tail && clear_tail) TW_CUDA(cudaMemsetAsync(tc.ffn_tail, 0, kFfnTailBytes, st));
+  if (tc.ffn_tail && clear_tail) TW_CUDA(cudaMemsetAsync(tc.ffn_tail + kFfnTailFloats, 0, kFfnTailBytes - kFfnTailFloats * 4, st));
   const int VP = pad16(V);
   const size_t smem = (((size_t)V * 12 + 15) & ~(size_t)15) + (((size_t)V + 15) & ~(size_t)15) + (size_t)VP * VP * 4;
   static DeviceOnce attr_done;
@@ -3167,7 +3193,7 @@ int tc_ffn_layer(const tw_flow_config* c, const ParamView& pv, int k, int t, con
     int* cnt = reinterpret_cast<int*>(tc.ffn_tail + kFfnTailFloats);
     for (int s = 0; s < 2; s++) {
       a.tail[s] = tc.ffn_tail + (size_t)s * (kFfnTailFloats / 2);
-      a.tail_cnt[s] = cnt + s * kFfnTailTiles * 2;
+      a.tail_cnt[s] = cnt + s * kFfnTailTiles * 4;
     }
   }
   {

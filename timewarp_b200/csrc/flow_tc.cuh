@@ -26,12 +26,13 @@ struct TcScratch {
   uint8_t* mixed_img[2];  // A-operand images of the per-head neighbourhood averages: [tile][H*2][hi|lo][16 KB]
   uint8_t* scores_img;    // B-operand images of the attention weights: [n_cond][H][hi|lo][VP*VP*2]
   const uint8_t* packed;  // packed weights (caller-owned, persistent)
-  float* ffn_tail;        // split-tile scratch of the pair FFN: [2 nets][kFfnTailTiles][2 ranks][128 x 128] fp32 partial sums,
-                          // followed by [2 nets][kFfnTailTiles][2] arrival counters; zeroed once per pass, self-cleaning
+  float* ffn_tail;        // split-tile scratch of the pair FFN: [2 nets][kFfnTailTiles][16 parts][2 ranks][128 x 128] fp32 partial sums,
+                          // followed by [2 nets][kFfnTailTiles][2 ranks | 2 ranks] arrival and done counters; zeroed once per pass,
+                          // self-cleaning
 };
-constexpr int kFfnTailTiles = 18;
-constexpr size_t kFfnTailFloats = (size_t)2 * kFfnTailTiles * 2 * 128 * 128;
-constexpr size_t kFfnTailBytes = kFfnTailFloats * 4 + 2 * kFfnTailTiles * 2 * 4;
+constexpr int kFfnTailTiles = 4;
+constexpr size_t kFfnTailFloats = (size_t)2 * kFfnTailTiles * 16 * 2 * 128 * 128;
+constexpr size_t kFfnTailBytes = kFfnTailFloats * 4 + 2 * kFfnTailTiles * 4 * 4;
 
 enum TcStage : uint32_t { TC_FFN = 1, TC_ATTN_PROJ = 2, TC_MIX = 4, TC_IN_MLP = 8, TC_OUT_MLP = 16, TC_ALL = 31 };
 constexpr uint32_t TC_IMPLEMENTED = TC_ALL;  // stages with a tensor-core kernel; the rest run on CUDA cores
