@@ -270,6 +270,221 @@ static int launch_gemm(const tw_flow_config* c, GemmArgs& a, cudaStream_t st) {
 }
 
 // ============================================================================================
+// FFN backward, first half, in ONE launch per encoder layer (custom_attention_encoder.py:102-113 differentiated):
+//   pre  = y1 W1^T + b1   (NT, re-computed)            dhid = dr W2   (NN)
+//   act  = relu(pre)  -> operand image (for dW2 += dr^T act)
+//   dpre = dhid where pre > 0, else 0  -> operand image (for dW1 += dpre^T y1 and dy1 = dr + dpre W1),  db1 += column sums of dpre
+// Both products of an output tile [128 tokens x 128 hidden] accumulate side by side in TMEM (2 x 256 columns, double
+// buffered), so neither [M, F] fp32 matrix is ever written: the epilogue reads the pair and stores the two images with
+// 16-byte swizzled-chunk stores.  Same roles as k_gemm_img: warp 0 streams tiles, warp 1 issues, warps 2-5 drain.
+struct FfnBwdPreArgs {
+  ImgRef Ay[2], Ad[2];  // y1 and dr images (plain, 2 column tiles)
+  ImgRef W1[2], W2[2];
+  const float* b1[2];
+  uint8_t* img_act[2];   // plain images, n_ct column tiles
+  uint8_t* img_dpre[2];
+  float* db1[2];
+  int rows, tiles_m, tiles_n, n_ct;
+};
+
+// column sums of a [32 rows (lanes) x 32 columns (registers)] block: lane j returns the sum of column j (31 shuffles)
+__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    const bool up = (lane & s) != 0;
+#pragma unroll
+    for (int i = 0; i < s; i++) {
+      const float send = up ? v[i] : v[i + s];
+      const float keep = up ? v[i + s] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
+  return v[0];
+}
+
+template <int kSplit>
+__global__ void __launch_bounds__(192, 1) k_ffn_bwd_pre(FfnBwdPreArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int net = blockIdx.y;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  uint8_t* ring = smem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kGemmStages * kGemmStageBytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kGemmStages;
+  uint64_t* acc_full = empty + kGemmStages;  // [2]
+  uint64_t* acc_free = acc_full + 2;         // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_free + 2);
+  if (tid == 0) {
+    for (int i = 0; i < kGemmStages; i++) mbar_init(&full[i], 1), mbar_init(&empty[i], 1);
+    for (int i = 0; i < 2; i++) mbar_init(&acc_full[i], 1), mbar_init(&acc_free[i], 128);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const int n_work = a.tiles_m * a.tiles_n;
+  const uint32_t parts = kSplit == 3 ? 2u : 1u;
+
+  if (warp == 0) {
+    uint32_t stage = 0, phase = 0;
+    const ImgRef Ay = a.Ay[net], Ad = a.Ad[net], W1 = a.W1[net], W2 = a.W2[net];
+    for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+      const int tn = w % a.tiles_n, tm = w / a.tiles_n;
+      for (int u = 0; u < 4; u++) {  // u = 2 * product + K block
+        const int kb = u & 1;
+        mbar_wait(&empty[stage], phase ^ 1);
+        if (elect_one()) {
+          uint8_t* dst = ring + stage * kGemmStageBytes;
+          mbar_arrive_expect_tx(&full[stage], parts * 32768u);
+          const ImgRef& A = u < 2 ? Ay : Ad;
+          const uint8_t* src = img_tile(A, tm, kb);
+          bulk_g2s(dst, src, 16384, &full[stage]);
+          if (kSplit == 3) bulk_g2s(dst + 16384, src + A.lo, 16384, &full[stage]);
+          if (u < 2) {
+            const uint8_t* wsrc = img_tile(W1, tn, kb);
+            bulk_g2s(dst + 32768, wsrc, 16384, &full[stage]);
+            if (kSplit == 3) bulk_g2s(dst + 49152, wsrc + W1.lo, 16384, &full[stage]);
+          } else {
+            for (int c = 0; c < 2; c++) {
+              const uint8_t* wsrc = img_tile(W2, 0, 2 * tn + c) + kb * 8192;
+              bulk_g2s(dst + 32768 + c * 8192, wsrc, 8192, &full[stage]);
+              if (kSplit == 3) bulk_g2s(dst + 49152 + c * 8192, wsrc + W2.lo, 8192, &full[stage]);
+            }
+          }
+        }
+        __syncwarp();
+        if (++stage == kGemmStages) stage = 0, phase ^= 1;
+      }
+    }
+  } else if (warp == 1) {
+    uint32_t stage = 0, phase = 0, ph_free[2] = {0, 0};
+    const uint32_t idesc_nt = make_idesc_bf16(128, 128, 0, 0), idesc_nn = make_idesc_bf16(128, 128, 0, 1);
+    int it = 0;
+    for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+      const int tb = it & 1;
+      if (it >= 2) {
+        mbar_wait(&acc_free[tb], ph_free[tb]);
+        ph_free[tb] ^= 1;
+      }
+      it++;
+      tc_fence_after();
+      for (int u = 0; u < 4; u++) {
+        const uint32_t d = tmem + tb * 256 + (u >> 1) * 128;
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t base = smem_u32(ring + stage * kGemmStageBytes);
+          const uint32_t ahi = base, alo = base + 16384, bhi = base + 32768, blo = base + 49152;
+#pragma unroll
+          for (int term = 0; term < (kSplit == 3 ? 3 : 1); term++) {
+            const uint32_t ab = (term == 1) ? alo : ahi, bb = (term == 2) ? blo : bhi;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+              const uint64_t ad = desc_kmajor_sw128(ab + k * 32);
+              const uint64_t bd = u >= 2 ? make_smem_desc(bb + k * 2048, 8192, 1024, LAYOUT_SW128) : desc_kmajor_sw128(bb + k * 32);
+              mma_ss(d, ad, bd, u >= 2 ? idesc_nn : idesc_nt, ((u & 1) || term > 0 || k > 0) ? 1 : 0);
+            }
+          }
+          mma_commit(&empty[stage]);
+          if (u == 3) mma_commit(&acc_full[tb]);
+        }
+        __syncwarp();
+        if (++stage == kGemmStages) stage = 0, phase ^= 1;
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    uint32_t ph_full[2] = {0, 0};
+    const float* b1 = a.b1[net];
+    float* db1 = a.db1[net];
+    int it = 0;
+    for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+      const int tn = w % a.tiles_n, tm = w / a.tiles_n;
+      const int tb = it & 1;
+      it++;
+      mbar_wait(&acc_full[tb], ph_full[tb]);
+      ph_full[tb] ^= 1;
+      tc_fence_after();
+      const bool valid = (int64_t)tm * 128 + row < a.rows;
+#pragma unroll 1
+      for (int g = 0; g < 4; g++) {
+        const int col0 = tn * 128 + g * 32;
+        const size_t toff = ((size_t)tm * a.n_ct + (size_t)(col0 >> 6)) * 32768;
+        uint8_t* act_hi = a.img_act[net] + toff;
+        uint8_t* dp_hi = a.img_dpre[net] + toff;
+        const uint32_t chunk0 = (uint32_t)(col0 & 63) >> 3;
+        const float bl = __ldg(b1 + col0 + lane);
+        uint32_t r[32];
+        tmem_ld32(tmem + lane_base + tb * 256 + g * 32, r);
+        tmem_ld_wait();
+        uint32_t keep = 0;
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          float v[8];
+#pragma unroll
+          for (int j = 0; j < 8; j++) {
+            const float p = __uint_as_float(r[u * 8 + j]) + __shfl_sync(0xffffffffu, bl, u * 8 + j);
+            const bool on = valid && p > 0.f;
+            keep |= on ? (1u << (u * 8 + j)) : 0u;
+            v[j] = on ? p : 0.f;
+          }
+          uint4 h, l;
+          split2(v[0], v[1], h.x, l.x), split2(v[2], v[3], h.y, l.y), split2(v[4], v[5], h.z, l.z), split2(v[6], v[7], h.w, l.w);
+          const uint32_t off = (uint32_t)row * 128u + (((chunk0 + u) ^ ((uint32_t)row & 7u)) << 4);
+          *reinterpret_cast<uint4*>(act_hi + off) = h;
+          if (kSplit == 3) *reinterpret_cast<uint4*>(act_hi + 16384 + off) = l;
+        }
+        tmem_ld32(tmem + lane_base + tb * 256 + 128 + g * 32, r);
+        tmem_ld_wait();
+        float dv[32];
+#pragma unroll
+        for (int j = 0; j < 32; j++) dv[j] = ((keep >> j) & 1u) ? __uint_as_float(r[j]) : 0.f;
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          uint4 h, l;
+          split2(dv[u * 8], dv[u * 8 + 1], h.x, l.x), split2(dv[u * 8 + 2], dv[u * 8 + 3], h.y, l.y);
+          split2(dv[u * 8 + 4], dv[u * 8 + 5], h.z, l.z), split2(dv[u * 8 + 6], dv[u * 8 + 7], h.w, l.w);
+          const uint32_t off = (uint32_t)row * 128u + (((chunk0 + u) ^ ((uint32_t)row & 7u)) << 4);
+          *reinterpret_cast<uint4*>(dp_hi + off) = h;
+          if (kSplit == 3) *reinterpret_cast<uint4*>(dp_hi + 16384 + off) = l;
+        }
+        const float cs = warp_colsum32(dv, lane);
+        atomicAdd(db1 + col0 + lane, cs);
+      }
+      tc_fence_before();
+      mbar_arrive(&acc_free[tb]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(tmem);
+}
+
+static int launch_ffn_bwd_pre(const tw_flow_config* c, FfnBwdPreArgs& a, cudaStream_t st) {
+  static DeviceOnce attr_done;
+  const int smem = kGemmStages * kGemmStageBytes + 256 + 1024;
+  if (!attr_done.done()) {
+    TW_CUDA(cudaFuncSetAttribute(k_ffn_bwd_pre<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    TW_CUDA(cudaFuncSetAttribute(k_ffn_bwd_pre<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_done.mark();
+  }
+  const int n_work = a.tiles_m * a.tiles_n;
+  if (n_work == 0) return TW_OK;
+  dim3 grid((unsigned)(n_work < 74 ? n_work : 74), 2);
+  if (c->precision == TW_PRECISION_BF16X3)
+    k_ffn_bwd_pre<3><<<grid, 192, smem, st>>>(a);
+  else
+    k_ffn_bwd_pre<1><<<grid, 192, smem, st>>>(a);
+  TW_LAUNCH_CHECK();
+  return TW_OK;
+}
+
+// ============================================================================================
 // tile-wise element kernels.  One CTA = one [128 rows x 64 cols] image tile, 256 threads; thread e covers
 // row (e >> 5) + 8*i, columns 2*(e & 31), +1  -> 4-byte stores that fill 128-byte swizzled rows.
 __device__ __forceinline__ float silu_fwd(float v) { return v / (1.f + __expf(-v)); }
@@ -1205,20 +1420,13 @@ static int conditioner_bwd(BwdCtx& x, int k, float* dz_other, const float* z_oth
     float* y1[2] = {x.tp.net[k][0].y1[t], x.tp.net[k][1].y1[t]};
     TW_TRY(pack_act(x, y1, b.img_x, 128, nullptr));
     {
-      GemmArgs g = gemm_base(x, GEMM_NT);  // pre = y1 W1^T + b1
-      for (int s = 0; s < 2; s++) g.A[s] = plain_img(b.img_x[s], 2), g.B[s] = w1[s], g.C[s] = b.wide0[s], g.bias[s] = x.pv.enc(k, s, t, 4);
-      g.ldc = F, g.rows = (int)x.M, g.cols = F, g.tiles_m = x.tiles, g.tiles_n = F / 128, g.KB = 2;
-      TW_TRY(launch_gemm(c, g, x.st));
-      GemmArgs d = gemm_base(x, GEMM_NN);  // dhid = dr W2
-      for (int s = 0; s < 2; s++) d.A[s] = plain_img(b.img_d[s], 2), d.B[s] = w2[s], d.C[s] = b.wide1[s];
-      d.ldc = F, d.rows = (int)x.M, d.cols = F, d.tiles_m = x.tiles, d.tiles_n = F / 128, d.KB = 2;
-      TW_TRY(launch_gemm(c, d, x.st));
-      ActBwdArgs r{};
-      for (int s = 0; s < 2; s++)
-        r.pre[s] = b.wide0[s], r.dact[s] = b.wide1[s], r.img_act[s] = b.img_w0[s], r.img_dpre[s] = b.img_w1[s], r.dbias[s] = x.gv.enc(k, s, t, 4);
-      r.M = x.M, r.C = F, r.n_ct = F / 64;
-      k_act_bwd<ACT_RELU><<<dim3(F / 64, x.tiles, 2), 256, 0, x.st>>>(r);
-      TW_LAUNCH_CHECK();
+      FfnBwdPreArgs f{};  // act = relu(y1 W1^T + b1), dpre = (dr W2) where pre > 0, db1: one launch, no [M, F] fp32 matrix
+      for (int s = 0; s < 2; s++) {
+        f.Ay[s] = plain_img(b.img_x[s], 2), f.Ad[s] = plain_img(b.img_d[s], 2), f.W1[s] = w1[s], f.W2[s] = w2[s];
+        f.b1[s] = x.pv.enc(k, s, t, 4), f.img_act[s] = b.img_w0[s], f.img_dpre[s] = b.img_w1[s], f.db1[s] = x.gv.enc(k, s, t, 4);
+      }
+      f.rows = (int)x.M, f.tiles_m = x.tiles, f.tiles_n = F / 128, f.n_ct = F / 64;
+      TW_TRY(launch_ffn_bwd_pre(c, f, x.st));
       GemmArgs wa = gemm_base(x, GEMM_TN);  // dW2 [128,F] += dr^T hid
       for (int s = 0; s < 2; s++) wa.A[s] = plain_img(b.img_d[s], 2), wa.B[s] = plain_img(b.img_w0[s], F / 64), wa.C[s] = x.gv.enc(k, s, t, 5);
       wa.ldc = F, wa.rows = 128, wa.cols = F, wa.tiles_m = 1, wa.tiles_n = F / 128, wa.KB = x.tiles * 2, wa.splits = wgrad_splits(x, F / 128);
