@@ -248,7 +248,9 @@ def time_nll_training(dev, precision, batch=256, steps=5, warmup=3, use_graph=Tr
     model = tw.custom_transformer_nvp_constructor(tw.kernel_transformer_nvp_config(precision))
     model.load_state_dict(synth_state_dict(model, 0))
     model = model.to(dev).train()
-    opt = torch.optim.Adam(model.parameters(), lr=1e-4, capturable=True, fused=True)
+    from timewarp_b200.optim import FlatAdam
+
+    opt = FlatAdam(model, lr=1e-4)  # torch.optim.Adam's update rule as one launch over the flat gradient buffer
     g = torch.Generator().manual_seed(0)
     x = torch.tensor(pep.coords_nm, dtype=torch.float32)[None] + 0.01 * torch.randn(batch, V, 3, generator=g)
     y = x + 0.02 * torch.randn(batch, V, 3, generator=g)
@@ -268,7 +270,7 @@ def time_nll_training(dev, precision, batch=256, steps=5, warmup=3, use_graph=Tr
         step()
     torch.cuda.synchronize()
     # The step is launch-bound at this size (5632 tokens, ~1500 kernel launches): replay it as ONE CUDA graph
-    # (forward with tape + hand-written backward + capturable Adam).  Falls back to eager launches if capture fails.
+    # (forward with tape + hand-written backward + Adam).  Falls back to eager launches if capture fails.
     launch = "eager"
     graph_step = None
     if use_graph:
@@ -302,7 +304,7 @@ def time_nll_training(dev, precision, batch=256, steps=5, warmup=3, use_graph=Tr
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
     return {"metric": "nll_train_atoms_per_sec", "value": batch * V / (ms / 1e3), "unit": "atoms/s", "ms_per_step": ms,
-            "config": {"workload": f"nll_train_ad22_batch{batch}", "atoms": V, "batch": batch, "optimizer": "Adam", "precision": precision,
+            "config": {"workload": f"nll_train_ad22_batch{batch}", "atoms": V, "batch": batch, "optimizer": "Adam (optim.FlatAdam, one launch)", "precision": precision,
                        "launch": launch},
             "final_loss": float(loss.detach())}
 
@@ -360,7 +362,9 @@ def measure_nll_dp(dev, rank, world, prec, B, steps, warmup):
     model.load_state_dict(synth_state_dict(model, 0))
     model = model.to(dev).train()
     twd.broadcast_parameters(model.parameters())
-    opt = torch.optim.Adam(model.parameters(), lr=1e-4, fused=True)
+    from timewarp_b200.optim import FlatAdam
+
+    opt = FlatAdam(model, lr=1e-4)
     trainer = twd.DataParallelTrainer(model, opt)
     g = torch.Generator().manual_seed(100 + rank)
     lengths = torch.randint(17, 52, (B,), generator=g)
@@ -406,7 +410,7 @@ def measure_nll_dp(dev, rank, world, prec, B, steps, warmup):
            "allreduce_busbw_gbs": (nbytes * 2 * (world - 1) / world / (ar_ms / 1e3) / 1e9) if (world > 1 and ar_ms > 0) else None,
            "allreduce_share_of_step": ar_ms / ms if ms > 0 else None, "higher_is_better": True, "scaling": "weak", "dtype": prec,
            "config": {"workload": f"nll_train_2aa_like_batch{B}_per_gpu", "batch_per_gpu": B, "global_batch": B * world, "padded_atoms": V,
-                      "atoms_per_step_all_ranks": float(atoms.item()), "optimizer": "Adam(fused)", "precision": prec,
+                      "atoms_per_step_all_ranks": float(atoms.item()), "optimizer": "Adam (optim.FlatAdam, one launch)", "precision": prec,
                       "collective": "one NCCL all-reduce over the flat fp32 gradient buffer per step, in place"},
            "final_loss": float(loss.detach()), "replicas_in_sync": in_sync}
     del trainer, opt, model

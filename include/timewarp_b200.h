@@ -283,6 +283,13 @@ int tw_mh_accept(const float* e_pot_x, const float* e_pot_y, const float* e_kin_
 int tw_threshold_accept(float* x_coords, float* e_old, const float* y_coords, const float* e_new, float threshold,
                         int64_t n, int64_t V, uint8_t* out_accepted, void* stream);
 
+/* One Adam step over flat buffers (the reference's optimizer, utilities/training_utils.py:356-368:
+ * torch.optim.Adam(lr, weight_decay) -- L2 decay added to the gradient, bias-corrected moments):
+ * params / grads / exp_avg / exp_avg_sq [n] fp32, 16-byte aligned, n a multiple of 4; hyper (DEVICE memory, so a
+ * captured CUDA graph follows a learning-rate schedule) = {lr, beta1, beta2, eps, weight_decay, step (1-based)}. */
+int tw_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, const float* hyper,
+                 void* stream);
+
 /* Debug: single-CTA tcgen05 probe, out[128,N] = bf16(A[128,K]) * bf16(B[N,K])^T with selectable operand
  * placement (a_mode 0 smem K-major SW128 / 1 K-major no swizzle / 2 MN-major SW128 / 3 TMEM; b_mode 0..2),
  * accumulator at TMEM column d_col.  status[0] = 1 if the MMA never completed.  Used by the GPU tests to

@@ -325,6 +325,77 @@ def test_fused_optimizer_updates_reach_the_packed_weights():
     assert abs(traj["foreach_eval"] - traj["fused_eval"]) < 2e-3 * max(1.0, abs(traj["foreach_eval"])), traj
 
 
+def test_flat_adam_kernel_matches_torch_adam():
+    """tw_adam_step against torch.optim.Adam (utilities/training_utils.py:356-368: lr + L2 weight decay) on identical
+    gradients, six steps: parameters and both moments."""
+    from timewarp_b200 import _lib as L
+    n = 4 * 50_001
+    g = torch.Generator(device="cuda").manual_seed(3)
+    p0 = torch.randn(n, device="cuda", generator=g)
+    ref_p = torch.nn.Parameter(p0.clone())
+    ref = torch.optim.Adam([ref_p], lr=3e-4, betas=(0.9, 0.99), eps=1e-8, weight_decay=1e-2)
+    p, m, v = p0.clone(), torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+    hyper = torch.tensor([3e-4, 0.9, 0.99, 1e-8, 1e-2, 0.0, 0.0, 0.0], device="cuda")
+    for it in range(6):
+        grad = torch.randn(n, device="cuda", generator=g) * (10.0 ** torch.randint(-6, 2, (n,), device="cuda", generator=g).float())
+        ref_p.grad = grad.clone()
+        ref.step()
+        hyper[5] += 1
+        L.check(L.load().tw_adam_step(L.ptr(p), L.ptr(grad), L.ptr(m), L.ptr(v), n, L.ptr(hyper), torch.cuda.current_stream().cuda_stream), "adam")
+        st = ref.state[ref_p]
+        torch.testing.assert_close(m, st["exp_avg"], rtol=1e-5, atol=1e-12)
+        torch.testing.assert_close(v, st["exp_avg_sq"], rtol=1e-5, atol=1e-20)
+        torch.testing.assert_close(p, ref_p.detach(), rtol=1e-6, atol=2e-8)  # a few ulps of p; one step moves p by 3e-4
+
+
+def test_flat_adam_trains_like_torch_adam():
+    """optim.FlatAdam (parameters re-homed into one flat buffer, one launch per step) against torch.optim.Adam on the full
+    model: same loss trajectory, state-dict keys and shapes untouched, the inference path sees the trained weights, and a
+    foreign gradient is refused."""
+    from timewarp_b200.optim import FlatAdam
+    g = _load("grads_full_ad22")
+    kw = dict(atom_types=g["atom_types"].cuda(), x_coords=g["x_coords"].cuda(), x_velocs=g["x_velocs"].cuda(), y_coords=g["y_coords"].cuda(),
+              y_velocs=g["y_velocs"].cuda(), adj_list=EMPTY_ADJ.cuda(), edge_batch_idx=EMPTY_EBI.cuda(), masked_elements=g["masked_elements"].cuda())
+    traj, finals = {}, {}
+    for name in ("torch", "flat"):
+        m, _ = build_model(FULL_O, "bf16x3", 0)
+        m.train()
+        keys = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+        opt = torch.optim.Adam(m.parameters(), lr=1e-4, weight_decay=1e-3) if name == "torch" else FlatAdam(m, lr=1e-4, weight_decay=1e-3)
+        losses = []
+        for _ in range(4):
+            opt.zero_grad(set_to_none=True)
+            loss = m(**kw)
+            loss.backward()
+            opt.step()
+            losses.append(float(loss.detach()))
+        traj[name] = losses
+        assert {k: tuple(v.shape) for k, v in m.state_dict().items()} == keys
+        finals[name] = {k: v.detach().clone() for k, v in m.state_dict().items()}
+        with torch.no_grad():
+            m.eval()
+            traj[name + "_eval"] = float(m(**kw))
+        if name == "flat":
+            assert all(p.data_ptr() >= opt._flat_p.data_ptr() for p in m.parameters() if p.requires_grad)
+            m.train()
+            p0 = next(p for p in m.parameters() if p.requires_grad)
+            opt.zero_grad(set_to_none=True)
+            m(**kw).backward()
+            p0.grad = p0.grad.clone()  # a gradient outside the flat buffer
+            with pytest.raises(RuntimeError, match="flat gradient buffer"):
+                opt.step()
+    assert abs(traj["torch"][0] - traj["flat"][0]) < 1e-6
+    assert abs(traj["torch"][1] - traj["torch"][0]) > 1e-3
+    for a, b in zip(traj["torch"], traj["flat"]):
+        assert abs(a - b) < 2e-3 * max(1.0, abs(a)), traj
+    assert abs(traj["torch_eval"] - traj["flat_eval"]) < 2e-3 * max(1.0, abs(traj["torch_eval"])), traj
+    # the big weights moved the same way (elements with a well-determined gradient sign: |delta| = lr-sized steps)
+    k = "flow.chain.0.scale_transformer.encoder_layers.0.linear1.weight"
+    k = k if k in finals["torch"] else next(x for x in finals["torch"] if x.endswith("linear1.weight"))
+    d = (finals["torch"][k] - finals["flat"][k]).abs()
+    assert float((d > 5e-5).float().mean()) < 0.05, float((d > 5e-5).float().mean())
+
+
 def test_training_trajectory_matches_oracle():
     """three Adam steps of NLL training (forward + hand-written backward + optimizer, weights
     re-packed every step) against the same three steps of the CPU oracle (fp64 autograd + torch Adam): the loss trajectory."""

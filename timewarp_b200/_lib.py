@@ -84,6 +84,7 @@ _SIGNATURES = {
     "tw_debug_umma_timing": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
     "tw_debug_set_ffn_trace": (C.c_int, [_P]),
     "tw_debug_set_trace": (C.c_int, [C.c_int, _P]),
+    "tw_adam_step": (C.c_int, [_P, _P, _P, _P, _I64, _P, _P]),
     "tw_threshold_accept": (C.c_int, [_P, _P, _P, _P, C.c_float, _I64, _I64, _P, _P]),
     "tw_flow_train_bytes": (C.c_int, [C.POINTER(FlowConfig), _I64, _I64, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     "tw_flow_log_likelihood_train": (C.c_int, [C.POINTER(FlowConfig), _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I32, _P, _P, _P, C.c_size_t, _P]),

@@ -9,7 +9,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libtimewarp_b200.so")
-SOURCES = ["flow_simt.cu", "flow_tc.cu", "attn_fm.cu", "attn_fm3.cu", "flow_train.cu", "flow_api.cu", "energy.cu", "mh.cu", "umma_probe.cu"]
+SOURCES = ["flow_simt.cu", "flow_tc.cu", "attn_fm.cu", "attn_fm3.cu", "flow_train.cu", "flow_api.cu", "energy.cu", "mh.cu", "optim.cu", "umma_probe.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

@@ -849,51 +849,61 @@ struct WcChainArgs {
   float* dwo[2];
   float* dwv[2];
 };
-__global__ void __launch_bounds__(128) k_wc_chain(WcChainArgs a, int D, int H) {
-  const int net = blockIdx.z, h = blockIdx.x, r = blockIdx.y, c = threadIdx.x;
-  const int warp = c >> 5, lane = c & 31;
-  const int HD = H * D;
-  const float* dwc = a.dwc[net];
-  const float* wo = a.wo[net];
-  const float* wv = a.wv[net];
-  __shared__ float srow[128];  // dWc[r, hD + :]  (D == 128, checked by the caller)
-  srow[c] = dwc[(size_t)r * HD + h * D + c];
+// One CTA per (head, block of 16 rows, network), 256 threads: the head's W_v block (padded rows) and dWc block live in shared
+// memory (138 KB), so each 64 KB matrix is read 8 times per head instead of 128 times (the row-per-CTA version moved 200 MB
+// through L2 per launch: 49 us for 50 MFLOP).  Thread t owns column (t & 127) of 8 output rows in both products.
+constexpr int kWcChainSmem = (128 * 129 + 128 * 128 + 128 * 16) * (int)sizeof(float);
+__global__ void __launch_bounds__(256) k_wc_chain(WcChainArgs a, int H) {
+  extern __shared__ __align__(16) float wsm[];
+  float* sV = wsm;                  // [128 k][129]   W_v[hD + k, j]
+  float* sD = sV + 128 * 129;       // [128 i][128]   dWc[i, hD + j]
+  float* sO = sD + 128 * 128;       // [128 i][16]    W_o[i, hD + 16 rb + kk]
+  const int net = blockIdx.z, h = blockIdx.x, rb = blockIdx.y, t = threadIdx.x;
+  const int HD = H * 128;
+  const float* dwc = a.dwc[net] + h * 128;
+  const float* wo = a.wo[net] + h * 128;
+  const float* wv = a.wv[net] + (size_t)h * 128 * 128;
+  for (int e = t; e < 128 * 32; e += 256) {  // float4 pieces: row = e >> 5, columns 4 * (e & 31)
+    const int r = e >> 5, c4 = (e & 31) * 4;
+    const float4 v = __ldg(reinterpret_cast<const float4*>(wv + (size_t)r * 128 + c4));
+    sV[r * 129 + c4] = v.x, sV[r * 129 + c4 + 1] = v.y, sV[r * 129 + c4 + 2] = v.z, sV[r * 129 + c4 + 3] = v.w;
+    *reinterpret_cast<float4*>(sD + r * 128 + c4) = __ldg(reinterpret_cast<const float4*>(dwc + (size_t)r * HD + c4));
+  }
+  for (int e = t; e < 128 * 4; e += 256) {
+    const int r = e >> 2, c4 = (e & 3) * 4;
+    *reinterpret_cast<float4*>(sO + r * 16 + c4) = __ldg(reinterpret_cast<const float4*>(wo + (size_t)r * HD + rb * 16 + c4));
+  }
   __syncthreads();
-  // dW_o[i = r, hD + k] += sum_j dWc[r, hD + j] W_v[hD + k, j]: one warp per k, lanes over j (coalesced rows of W_v).
-  // Eight rows in flight per warp: the loads, not the 4 FMAs, are the cost (the first version ran one row at a time: 68 us).
-  for (int k0 = warp * 32; k0 < warp * 32 + 32; k0 += 8) {
-    float p[8];
+  const int col = t & 127, g8 = (t >> 7) * 8;
+  // dW_o[i, hD + k] += sum_j dWc[i, hD + j] W_v[hD + k, j],   i = 16 rb + g8 + u, k = col
+  {
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const float* drow = sD + (rb * 16 + g8) * 128;
+#pragma unroll 4
+    for (int j = 0; j < 128; j += 4) {
+      const float v0 = sV[col * 129 + j], v1 = sV[col * 129 + j + 1], v2 = sV[col * 129 + j + 2], v3 = sV[col * 129 + j + 3];
 #pragma unroll
-    for (int u = 0; u < 8; u++) {
-      const float4 w4 = __ldg(reinterpret_cast<const float4*>(wv + (size_t)(h * D + k0 + u) * D) + lane);
-      p[u] = fmaf(srow[4 * lane], w4.x, fmaf(srow[4 * lane + 1], w4.y, fmaf(srow[4 * lane + 2], w4.z, srow[4 * lane + 3] * w4.w)));
+      for (int u = 0; u < 8; u++) {
+        const float4 d = *reinterpret_cast<const float4*>(drow + u * 128 + j);  // broadcast
+        acc[u] = fmaf(d.x, v0, fmaf(d.y, v1, fmaf(d.z, v2, fmaf(d.w, v3, acc[u]))));
+      }
     }
 #pragma unroll
-    for (int u = 0; u < 8; u++) {
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) p[u] += __shfl_xor_sync(0xffffffffu, p[u], o);
-    }
-    if (lane < 8) {
-      float v = p[0];
-#pragma unroll
-      for (int u = 1; u < 8; u++) v = lane == u ? p[u] : v;
-      a.dwo[net][(size_t)r * HD + h * D + k0 + lane] += v;
-    }
+    for (int u = 0; u < 8; u++) a.dwo[net][(size_t)(rb * 16 + g8 + u) * HD + h * 128 + col] += acc[u];
   }
-  // dW_v[hD + k = r, j = c] += sum_i W_o[i, hD + r] dWc[i, hD + c]   (coalesced over c, W_o element broadcast), 16 loads in flight
-  float acc2 = 0.f;
-#pragma unroll 1
-  for (int i0 = 0; i0 < 128; i0 += 16) {
-    float wa[16], da[16];
-#pragma unroll
-    for (int u = 0; u < 16; u++) {
-      wa[u] = __ldg(wo + (size_t)(i0 + u) * HD + h * D + r);
-      da[u] = __ldg(dwc + (size_t)(i0 + u) * HD + h * D + c);
+  // dW_v[hD + k, j] += sum_i W_o[i, hD + k] dWc[i, hD + j],   k = 16 rb + g8 + u, j = col
+  {
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+    for (int i = 0; i < 128; i++) {
+      const float d = sD[i * 128 + col];
+      const float4 o0 = *reinterpret_cast<const float4*>(sO + i * 16 + g8), o1 = *reinterpret_cast<const float4*>(sO + i * 16 + g8 + 4);
+      acc[0] = fmaf(o0.x, d, acc[0]), acc[1] = fmaf(o0.y, d, acc[1]), acc[2] = fmaf(o0.z, d, acc[2]), acc[3] = fmaf(o0.w, d, acc[3]);
+      acc[4] = fmaf(o1.x, d, acc[4]), acc[5] = fmaf(o1.y, d, acc[5]), acc[6] = fmaf(o1.z, d, acc[6]), acc[7] = fmaf(o1.w, d, acc[7]);
     }
 #pragma unroll
-    for (int u = 0; u < 16; u++) acc2 = fmaf(wa[u], da[u], acc2);
+    for (int u = 0; u < 8; u++) a.dwv[net][(size_t)(h * 128 + rb * 16 + g8 + u) * 128 + col] += acc[u];
   }
-  a.dwv[net][(size_t)(h * D + r) * D + c] += acc2;
 }
 
 // ============================================================================================
@@ -1505,7 +1515,12 @@ static int conditioner_bwd(BwdCtx& x, int k, float* dz_other, const float* z_oth
       WcChainArgs ch{};
       for (int s = 0; s < 2; s++)
         ch.dwc[s] = b.dwc[s], ch.wo[s] = x.pv.enc(k, s, t, 2), ch.wv[s] = x.pv.enc(k, s, t, 0), ch.dwo[s] = x.gv.enc(k, s, t, 2), ch.dwv[s] = x.gv.enc(k, s, t, 0);
-      k_wc_chain<<<dim3(H, 128, 2), 128, 0, x.st>>>(ch, 128, H);
+      static DeviceOnce chain_attr;
+      if (!chain_attr.done()) {
+        TW_CUDA(cudaFuncSetAttribute(k_wc_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, kWcChainSmem));
+        chain_attr.mark();
+      }
+      k_wc_chain<<<dim3(H, 8, 2), 256, kWcChainSmem, x.st>>>(ch, H);
       TW_LAUNCH_CHECK();
       // G_h = A_h^T dr  (transposed score images), then dx = dr + sum_h G_h W_c,h
       if (x.pv.chebyshev()) {
