@@ -1364,62 +1364,66 @@ __global__ void __launch_bounds__(256) k_scores_img(const float* __restrict__ sc
 // Scores straight to operand images (inference): the fp32 score tensor [n_cond, H, V, V] (104 MB at 1024 x 65 atoms) is
 // only an intermediate of the tensor-core path, so one CTA per conditioning state computes
 //   w_hij = exp(-(|x_i - x_j| / l_h)^2), key-masked, L1-row-normalised (+1e-5)      kernel_attention.py:98-119
-// with exactly the arithmetic of k_scores (same operation order, same warp reduction) and writes the bf16 hi/lo
-// image of k_scores_img through a shared-memory staging buffer (16-byte coalesced stores).
-__global__ void __launch_bounds__(256) k_scores_direct_img(const float* __restrict__ xc, const uint8_t* __restrict__ mask,
-                                                           const float* __restrict__ ls, int V, int VP, int H,
-                                                           uint8_t* __restrict__ img, const float* __restrict__ cheb, int order,
-                                                           int force_zero) {
+// for every head and writes the bf16 hi/lo images of k_scores_img.  The distances of the state go to shared memory
+// once; then one thread per (head, image row): row sum in a first sweep, and in a second sweep eight columns at a time
+// -- exactly one 16-byte chunk of the swizzle-free [8 x 8] core-matrix layout -- so eight neighbouring lanes (rows) fill one
+// 128-byte line with plain 16-byte stores and the padding rows / columns are written as zeros on the way.  (The first
+// version ran one warp per row and (state, head) CTA through a shared staging image: 4 column slots per lane for 65 columns,
+// IEEE divisions per element, 2-byte scatter stores -- issue-bound at 179 us per launch for 157 MB of output.)
+__global__ void __launch_bounds__(1024) k_scores_direct_img(const float* __restrict__ xc, const uint8_t* __restrict__ mask,
+                                                            const float* __restrict__ ls, int V, int VP, int H,
+                                                            uint8_t* __restrict__ img, const float* __restrict__ cheb, int order,
+                                                            int force_zero) {
   extern __shared__ __align__(16) uint8_t sm_raw[];
   float* xs = reinterpret_cast<float*>(sm_raw);                  // [V][3]
   uint8_t* ms = sm_raw + (((size_t)V * 12 + 15) & ~(size_t)15);  // [V]
-  uint8_t* stg = ms + (((size_t)V + 15) & ~(size_t)15);          // [hi: VP*VP*2][lo: VP*VP*2]
+  float* dist = reinterpret_cast<float*>(ms + (((size_t)V + 15) & ~(size_t)15));  // [V][VS], odd row stride
+  const int VS = V | 1;
   const int64_t b = blockIdx.x;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x;
   for (int i = tid; i < V * 3; i += blockDim.x) xs[i] = xc[b * V * 3 + i];
   for (int i = tid; i < V; i += blockDim.x) ms[i] = mask[b * V + i];
-  const uint32_t mat = (uint32_t)VP * VP * 2;
   __syncthreads();
-  for (int h = blockIdx.y; h < H; h += gridDim.y) {  // grid.y = H: one (state, head) image per CTA, several CTAs per SM
-    const float l = ls[h];
+  for (int e = tid; e < V * V; e += blockDim.x) {
+    const int i = e / V, j = e - i * V;
+    const float dx = xs[i * 3] - xs[j * 3], dy = xs[i * 3 + 1] - xs[j * 3 + 1], dz = xs[i * 3 + 2] - xs[j * 3 + 2];
+    dist[i * VS + j] = sqrtf(dx * dx + dy * dy + dz * dz);
+  }
+  __syncthreads();
+  const uint32_t mat = (uint32_t)VP * VP * 2;
+  const int nb = VP >> 3;
+  for (int t = tid; t < H * VP; t += blockDim.x) {
+    const int h = t / VP, i = t - h * VP;
+    uint8_t* dst = img + ((size_t)b * H + h) * 2 * mat + (size_t)(i >> 3) * ((size_t)nb * 128) + (size_t)(i & 7) * 16;
+    if (i >= V) {
+      for (int jb = 0; jb < nb; jb++) {
+        *reinterpret_cast<uint4*>(dst + jb * 128) = make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4*>(dst + mat + jb * 128) = make_uint4(0, 0, 0, 0);
+      }
+      continue;
+    }
+    const float inv_l = 1.0f / ls[h];
     const float* coef = cheb ? cheb + (size_t)h * order : nullptr;
     const float cmean = cheb_mean(coef, order, force_zero);
-    for (uint32_t o = tid * 16; o < 2 * mat; o += blockDim.x * 16) *reinterpret_cast<uint4*>(stg + o) = make_uint4(0, 0, 0, 0);
-    __syncthreads();
-    for (int i = warp; i < V; i += 8) {
-      const float xi = xs[i * 3], yi = xs[i * 3 + 1], zi = xs[i * 3 + 2];
-      float w[4];  // V <= 128: at most four columns per lane
-      float sum = 0.f;
-#pragma unroll
-      for (int u = 0; u < 4; u++) {
-        const int j = lane + 32 * u;
-        w[u] = 0.f;
-        if (j < V) {
-          float dx = xi - xs[j * 3], dy = yi - xs[j * 3 + 1], dz = zi - xs[j * 3 + 2];
-          float d = sqrtf(dx * dx + dy * dy + dz * dz);
-          float a = d / l;
-          w[u] = ms[j] ? 0.f : attention_basis(a, coef, order, cmean);
-          sum += fabsf(w[u]);
-        }
-      }
-      sum = warp_sum(sum) + 1e-5f;
-#pragma unroll
-      for (int u = 0; u < 4; u++) {
-        const int j = lane + 32 * u;
-        if (j < V) {
-          const float v = w[u] / sum;
-          __nv_bfloat16 hb = __float2bfloat16(v);
-          __nv_bfloat16 lb = __float2bfloat16(v - __bfloat162float(hb));
-          const uint32_t off = (i >> 3) * ((VP >> 3) * 128u) + (j >> 3) * 128u + (i & 7) * 16u + (j & 7) * 2u;
-          *reinterpret_cast<__nv_bfloat16*>(stg + off) = hb;
-          *reinterpret_cast<__nv_bfloat16*>(stg + mat + off) = lb;
-        }
-      }
+    const float* drow = dist + i * VS;
+    float sum = 0.f;
+    for (int j = 0; j < V; j++) {
+      const float w = ms[j] ? 0.f : attention_basis(drow[j] * inv_l, coef, order, cmean);
+      sum += fabsf(w);
     }
-    __syncthreads();
-    uint8_t* dst = img + ((size_t)b * H + h) * 2 * mat;
-    for (uint32_t o = tid * 16; o < 2 * mat; o += blockDim.x * 16) *reinterpret_cast<uint4*>(dst + o) = *reinterpret_cast<const uint4*>(stg + o);
-    __syncthreads();
+    const float inv = 1.0f / (sum + 1e-5f);
+    for (int jb = 0; jb < nb; jb++) {
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        const int j = jb * 8 + u;
+        v[u] = (j < V && !ms[j]) ? attention_basis(drow[j] * inv_l, coef, order, cmean) * inv : 0.f;
+      }
+      uint4 hi, lo;
+      split2(v[0], v[1], hi.x, lo.x), split2(v[2], v[3], hi.y, lo.y), split2(v[4], v[5], hi.z, lo.z), split2(v[6], v[7], hi.w, lo.w);
+      *reinterpret_cast<uint4*>(dst + jb * 128) = hi;
+      *reinterpret_cast<uint4*>(dst + mat + jb * 128) = lo;
+    }
   }
 }
 
@@ -3003,15 +3007,17 @@ int tc_begin_pass_direct(const tw_flow_config* c, TcScratch& tc, const float* xc
                          int64_t n_cond, int V, cudaStream_t st, const float* cheb, bool clear_tail) {
   if (tc.ffn_tail && clear_tail) TW_CUDA(cudaMemsetAsync(tc.ffn_tail + kFfnTailFloats, 0, kFfnTailBytes - kFfnTailFloats * 4, st));
   const int VP = pad16(V);
-  const size_t smem = (((size_t)V * 12 + 15) & ~(size_t)15) + (((size_t)V + 15) & ~(size_t)15) + (size_t)VP * VP * 4;
+  const size_t smem = (((size_t)V * 12 + 15) & ~(size_t)15) + (((size_t)V + 15) & ~(size_t)15) + (size_t)V * (V | 1) * 4;
   static DeviceOnce attr_done;
   if (!attr_done.done()) {
-    TW_CUDA(cudaFuncSetAttribute(k_scores_direct_img, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 128 * 4 + 4096));
+    TW_CUDA(cudaFuncSetAttribute(k_scores_direct_img, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 129 * 4 + 4096));
     attr_done.mark();
   }
   if (n_cond < 1) return TW_OK;
-  k_scores_direct_img<<<dim3((unsigned)n_cond, (unsigned)c->num_heads), 256, smem, st>>>(xc, mask, lengthscales, V, VP, c->num_heads, tc.scores_img, cheb,
-                                                           c->cheb_order, c->force_asymptotic_zero);
+  int threads = (c->num_heads * VP + 31) & ~31;
+  if (threads > 1024) threads = 1024;
+  k_scores_direct_img<<<(unsigned)n_cond, threads, smem, st>>>(xc, mask, lengthscales, V, VP, c->num_heads, tc.scores_img, cheb,
+                                                             c->cheb_order, c->force_asymptotic_zero);
   TW_LAUNCH_CHECK();
   return TW_OK;
 }

@@ -287,6 +287,17 @@ struct FfnBwdPreArgs {
   int rows, tiles_m, tiles_n, n_ct;
 };
 
+// 256-bit global store of two 16-byte chunks (sm_100: st.global.v8)
+__device__ __forceinline__ void st_global_v8(void* p, const uint4& a, const uint4& b) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y),
+               "r"(b.z), "r"(b.w)
+               : "memory");
+}
+
+__device__ __forceinline__ uint4 sel4(bool c, const uint4& a, const uint4& b) {
+  return make_uint4(c ? a.x : b.x, c ? a.y : b.y, c ? a.z : b.z, c ? a.w : b.w);
+}
+
 // column sums of a [32 rows (lanes) x 32 columns (registers)] block: lane j returns the sum of column j (31 shuffles)
 __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
 #pragma unroll
@@ -302,22 +313,34 @@ __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
   return v[0];
 }
 
+// Token-tile stationary: the y1 and dr tiles of a token tile (128 KB with the lo parts) stay in shared memory while the CTA
+// walks over the hidden chunks, only the weight tiles stream through the ring -- 144 KB instead of 256 KB of L2 reads per
+// output tile.  Every CTA takes a contiguous range of (token tile, hidden chunk) items, so it re-loads the resident tiles at
+// most twice.
+constexpr int kFbpStages = 3;
+constexpr int kFbpStageBytes = 32768;   // W hi 16K | W lo 16K
+constexpr int kFbpResident = 131072;    // y1 kb0, kb1, dr kb0, kb1: each hi 16K | lo 16K
+constexpr int kFbpThreads = 320;        // producer, MMA issuer, 8 epilogue warps (two per TMEM lane quarter: column groups 0-1 / 2-3)
 template <int kSplit>
-__global__ void __launch_bounds__(192, 1) k_ffn_bwd_pre(FfnBwdPreArgs a) {
+__global__ void __launch_bounds__(kFbpThreads, 1) k_ffn_bwd_pre(FfnBwdPreArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int net = blockIdx.y;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  uint8_t* ring = smem;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kGemmStages * kGemmStageBytes);
+  uint8_t* resident = smem;
+  uint8_t* ring = smem + kFbpResident;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + kFbpStages * kFbpStageBytes);
   uint64_t* full = bars;
-  uint64_t* empty = bars + kGemmStages;
-  uint64_t* acc_full = empty + kGemmStages;  // [2]
-  uint64_t* acc_free = acc_full + 2;         // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_free + 2);
+  uint64_t* empty = bars + kFbpStages;
+  uint64_t* acc_full = empty + kFbpStages;  // [2]
+  uint64_t* acc_free = acc_full + 2;        // [2]
+  uint64_t* res_full = acc_free + 2;        // the resident tiles have landed
+  uint64_t* res_free = res_full + 1;        // every MMA that reads them has retired
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_free + 1);
   if (tid == 0) {
-    for (int i = 0; i < kGemmStages; i++) mbar_init(&full[i], 1), mbar_init(&empty[i], 1);
-    for (int i = 0; i < 2; i++) mbar_init(&acc_full[i], 1), mbar_init(&acc_free[i], 128);
+    for (int i = 0; i < kFbpStages; i++) mbar_init(&full[i], 1), mbar_init(&empty[i], 1);
+    for (int i = 0; i < 2; i++) mbar_init(&acc_full[i], 1), mbar_init(&acc_free[i], 256);
+    mbar_init(res_full, 1), mbar_init(res_free, 1);
     mbar_fence_init();
   }
   if (warp == 1) tmem_alloc<512>(tmem_slot);
@@ -326,44 +349,67 @@ __global__ void __launch_bounds__(192, 1) k_ffn_bwd_pre(FfnBwdPreArgs a) {
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const int n_work = a.tiles_m * a.tiles_n;
+  const int w0 = (int)((int64_t)blockIdx.x * n_work / gridDim.x), w1 = (int)((int64_t)(blockIdx.x + 1) * n_work / gridDim.x);
   const uint32_t parts = kSplit == 3 ? 2u : 1u;
 
   if (warp == 0) {
-    uint32_t stage = 0, phase = 0;
+    uint32_t stage = 0, phase = 0, ph_res = 0;
+    int cur_tm = -1;
     const ImgRef Ay = a.Ay[net], Ad = a.Ad[net], W1 = a.W1[net], W2 = a.W2[net];
-    for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+    for (int w = w0; w < w1; w++) {
       const int tn = w % a.tiles_n, tm = w / a.tiles_n;
+      if (tm != cur_tm) {
+        if (cur_tm >= 0) {
+          mbar_wait(res_free, ph_res);
+          ph_res ^= 1;
+        }
+        cur_tm = tm;
+        if (elect_one()) {
+          mbar_arrive_expect_tx(res_full, parts * 4u * 16384u);
+          for (int u = 0; u < 4; u++) {
+            const ImgRef& A = u < 2 ? Ay : Ad;
+            const uint8_t* src = img_tile(A, tm, u & 1);
+            bulk_g2s(resident + u * 32768, src, 16384, res_full);
+            if (kSplit == 3) bulk_g2s(resident + u * 32768 + 16384, src + A.lo, 16384, res_full);
+          }
+        }
+        __syncwarp();
+      }
       for (int u = 0; u < 4; u++) {  // u = 2 * product + K block
         const int kb = u & 1;
         mbar_wait(&empty[stage], phase ^ 1);
         if (elect_one()) {
-          uint8_t* dst = ring + stage * kGemmStageBytes;
-          mbar_arrive_expect_tx(&full[stage], parts * 32768u);
-          const ImgRef& A = u < 2 ? Ay : Ad;
-          const uint8_t* src = img_tile(A, tm, kb);
-          bulk_g2s(dst, src, 16384, &full[stage]);
-          if (kSplit == 3) bulk_g2s(dst + 16384, src + A.lo, 16384, &full[stage]);
+          uint8_t* dst = ring + stage * kFbpStageBytes;
+          mbar_arrive_expect_tx(&full[stage], parts * 16384u);
           if (u < 2) {
             const uint8_t* wsrc = img_tile(W1, tn, kb);
-            bulk_g2s(dst + 32768, wsrc, 16384, &full[stage]);
-            if (kSplit == 3) bulk_g2s(dst + 49152, wsrc + W1.lo, 16384, &full[stage]);
+            bulk_g2s(dst, wsrc, 16384, &full[stage]);
+            if (kSplit == 3) bulk_g2s(dst + 16384, wsrc + W1.lo, 16384, &full[stage]);
           } else {
             for (int c = 0; c < 2; c++) {
               const uint8_t* wsrc = img_tile(W2, 0, 2 * tn + c) + kb * 8192;
-              bulk_g2s(dst + 32768 + c * 8192, wsrc, 8192, &full[stage]);
-              if (kSplit == 3) bulk_g2s(dst + 49152 + c * 8192, wsrc + W2.lo, 8192, &full[stage]);
+              bulk_g2s(dst + c * 8192, wsrc, 8192, &full[stage]);
+              if (kSplit == 3) bulk_g2s(dst + 16384 + c * 8192, wsrc + W2.lo, 8192, &full[stage]);
             }
           }
         }
         __syncwarp();
-        if (++stage == kGemmStages) stage = 0, phase ^= 1;
+        if (++stage == kFbpStages) stage = 0, phase ^= 1;
       }
     }
   } else if (warp == 1) {
-    uint32_t stage = 0, phase = 0, ph_free[2] = {0, 0};
+    uint32_t stage = 0, phase = 0, ph_free[2] = {0, 0}, ph_res = 0;
     const uint32_t idesc_nt = make_idesc_bf16(128, 128, 0, 0), idesc_nn = make_idesc_bf16(128, 128, 0, 1);
-    int it = 0;
-    for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+    const uint32_t res_base = smem_u32(resident);
+    int it = 0, cur_tm = -1;
+    for (int w = w0; w < w1; w++) {
+      const int tm = w / a.tiles_n;
+      if (tm != cur_tm) {
+        mbar_wait(res_full, ph_res);
+        ph_res ^= 1;
+        cur_tm = tm;
+      }
+      const bool last_of_tm = (w + 1 == w1) || ((w + 1) / a.tiles_n != tm);
       const int tb = it & 1;
       if (it >= 2) {
         mbar_wait(&acc_free[tb], ph_free[tb]);
@@ -376,8 +422,8 @@ __global__ void __launch_bounds__(192, 1) k_ffn_bwd_pre(FfnBwdPreArgs a) {
         mbar_wait(&full[stage], phase);
         tc_fence_after();
         if (elect_one()) {
-          const uint32_t base = smem_u32(ring + stage * kGemmStageBytes);
-          const uint32_t ahi = base, alo = base + 16384, bhi = base + 32768, blo = base + 49152;
+          const uint32_t ahi = res_base + u * 32768, alo = ahi + 16384;
+          const uint32_t bhi = smem_u32(ring + stage * kFbpStageBytes), blo = bhi + 16384;
 #pragma unroll
           for (int term = 0; term < (kSplit == 3 ? 3 : 1); term++) {
             const uint32_t ab = (term == 1) ? alo : ahi, bb = (term == 2) ? blo : bhi;
@@ -389,21 +435,25 @@ __global__ void __launch_bounds__(192, 1) k_ffn_bwd_pre(FfnBwdPreArgs a) {
             }
           }
           mma_commit(&empty[stage]);
-          if (u == 3) mma_commit(&acc_full[tb]);
+          if (u == 3) {
+            mma_commit(&acc_full[tb]);
+            if (last_of_tm) mma_commit(res_free);
+          }
         }
         __syncwarp();
-        if (++stage == kGemmStages) stage = 0, phase ^= 1;
+        if (++stage == kFbpStages) stage = 0, phase ^= 1;
       }
     }
   } else {
-    const int q = warp & 3;
+    const int q = warp & 3, half = (warp - 2) >> 2;
     const int row = q * 32 + lane;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    const uint32_t sw = (uint32_t)row & 7u;
     uint32_t ph_full[2] = {0, 0};
     const float* b1 = a.b1[net];
     float* db1 = a.db1[net];
     int it = 0;
-    for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+    for (int w = w0; w < w1; w++) {
       const int tn = w % a.tiles_n, tm = w / a.tiles_n;
       const int tb = it & 1;
       it++;
@@ -412,9 +462,9 @@ __global__ void __launch_bounds__(192, 1) k_ffn_bwd_pre(FfnBwdPreArgs a) {
       tc_fence_after();
       const bool valid = (int64_t)tm * 128 + row < a.rows;
 #pragma unroll 1
-      for (int g = 0; g < 4; g++) {
+      for (int g = 2 * half; g < 2 * half + 2; g++) {
         const int col0 = tn * 128 + g * 32;
-        const size_t toff = ((size_t)tm * a.n_ct + (size_t)(col0 >> 6)) * 32768;
+        const size_t toff = ((size_t)tm * a.n_ct + (size_t)(col0 >> 6)) * 32768 + (size_t)row * 128;
         uint8_t* act_hi = a.img_act[net] + toff;
         uint8_t* dp_hi = a.img_dpre[net] + toff;
         const uint32_t chunk0 = (uint32_t)(col0 & 63) >> 3;
@@ -423,21 +473,27 @@ __global__ void __launch_bounds__(192, 1) k_ffn_bwd_pre(FfnBwdPreArgs a) {
         tmem_ld32(tmem + lane_base + tb * 256 + g * 32, r);
         tmem_ld_wait();
         uint32_t keep = 0;
+        // two 16-byte chunks (8 columns each) of a swizzled 128-byte row form an aligned 32-byte pair: one 256-bit store
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
-          float v[8];
+        for (int u = 0; u < 2; u++) {
+          uint4 h[2], l[2];
 #pragma unroll
-          for (int j = 0; j < 8; j++) {
-            const float p = __uint_as_float(r[u * 8 + j]) + __shfl_sync(0xffffffffu, bl, u * 8 + j);
-            const bool on = valid && p > 0.f;
-            keep |= on ? (1u << (u * 8 + j)) : 0u;
-            v[j] = on ? p : 0.f;
+          for (int c = 0; c < 2; c++) {
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+              const int e = u * 16 + c * 8 + j;
+              const float p = __uint_as_float(r[e]) + __shfl_sync(0xffffffffu, bl, e);
+              const bool on = valid && p > 0.f;
+              keep |= on ? (1u << e) : 0u;
+              v[j] = on ? p : 0.f;
+            }
+            split2(v[0], v[1], h[c].x, l[c].x), split2(v[2], v[3], h[c].y, l[c].y), split2(v[4], v[5], h[c].z, l[c].z), split2(v[6], v[7], h[c].w, l[c].w);
           }
-          uint4 h, l;
-          split2(v[0], v[1], h.x, l.x), split2(v[2], v[3], h.y, l.y), split2(v[4], v[5], h.z, l.z), split2(v[6], v[7], h.w, l.w);
-          const uint32_t off = (uint32_t)row * 128u + (((chunk0 + u) ^ ((uint32_t)row & 7u)) << 4);
-          *reinterpret_cast<uint4*>(act_hi + off) = h;
-          if (kSplit == 3) *reinterpret_cast<uint4*>(act_hi + 16384 + off) = l;
+          const uint32_t off = (((chunk0 + 2 * u) ^ sw) & ~1u) << 4;
+          const bool odd = (sw & 1u) != 0;  // odd rows: the even chunk sits in the upper half of the pair
+          st_global_v8(act_hi + off, sel4(odd, h[1], h[0]), sel4(odd, h[0], h[1]));
+          if (kSplit == 3) st_global_v8(act_hi + 16384 + off, sel4(odd, l[1], l[0]), sel4(odd, l[0], l[1]));
         }
         tmem_ld32(tmem + lane_base + tb * 256 + 128 + g * 32, r);
         tmem_ld_wait();
@@ -445,13 +501,18 @@ __global__ void __launch_bounds__(192, 1) k_ffn_bwd_pre(FfnBwdPreArgs a) {
 #pragma unroll
         for (int j = 0; j < 32; j++) dv[j] = ((keep >> j) & 1u) ? __uint_as_float(r[j]) : 0.f;
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
-          uint4 h, l;
-          split2(dv[u * 8], dv[u * 8 + 1], h.x, l.x), split2(dv[u * 8 + 2], dv[u * 8 + 3], h.y, l.y);
-          split2(dv[u * 8 + 4], dv[u * 8 + 5], h.z, l.z), split2(dv[u * 8 + 6], dv[u * 8 + 7], h.w, l.w);
-          const uint32_t off = (uint32_t)row * 128u + (((chunk0 + u) ^ ((uint32_t)row & 7u)) << 4);
-          *reinterpret_cast<uint4*>(dp_hi + off) = h;
-          if (kSplit == 3) *reinterpret_cast<uint4*>(dp_hi + 16384 + off) = l;
+        for (int u = 0; u < 2; u++) {
+          uint4 h[2], l[2];
+#pragma unroll
+          for (int c = 0; c < 2; c++) {
+            const int e = u * 16 + c * 8;
+            split2(dv[e], dv[e + 1], h[c].x, l[c].x), split2(dv[e + 2], dv[e + 3], h[c].y, l[c].y);
+            split2(dv[e + 4], dv[e + 5], h[c].z, l[c].z), split2(dv[e + 6], dv[e + 7], h[c].w, l[c].w);
+          }
+          const uint32_t off = (((chunk0 + 2 * u) ^ sw) & ~1u) << 4;
+          const bool odd = (sw & 1u) != 0;
+          st_global_v8(dp_hi + off, sel4(odd, h[1], h[0]), sel4(odd, h[0], h[1]));
+          if (kSplit == 3) st_global_v8(dp_hi + 16384 + off, sel4(odd, l[1], l[0]), sel4(odd, l[0], l[1]));
         }
         const float cs = warp_colsum32(dv, lane);
         atomicAdd(db1 + col0 + lane, cs);
@@ -467,7 +528,7 @@ __global__ void __launch_bounds__(192, 1) k_ffn_bwd_pre(FfnBwdPreArgs a) {
 
 static int launch_ffn_bwd_pre(const tw_flow_config* c, FfnBwdPreArgs& a, cudaStream_t st) {
   static DeviceOnce attr_done;
-  const int smem = kGemmStages * kGemmStageBytes + 256 + 1024;
+  const int smem = kFbpResident + kFbpStages * kFbpStageBytes + 256 + 1024;
   if (!attr_done.done()) {
     TW_CUDA(cudaFuncSetAttribute(k_ffn_bwd_pre<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     TW_CUDA(cudaFuncSetAttribute(k_ffn_bwd_pre<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -477,9 +538,9 @@ static int launch_ffn_bwd_pre(const tw_flow_config* c, FfnBwdPreArgs& a, cudaStr
   if (n_work == 0) return TW_OK;
   dim3 grid((unsigned)(n_work < 74 ? n_work : 74), 2);
   if (c->precision == TW_PRECISION_BF16X3)
-    k_ffn_bwd_pre<3><<<grid, 192, smem, st>>>(a);
+    k_ffn_bwd_pre<3><<<grid, kFbpThreads, smem, st>>>(a);
   else
-    k_ffn_bwd_pre<1><<<grid, 192, smem, st>>>(a);
+    k_ffn_bwd_pre<1><<<grid, kFbpThreads, smem, st>>>(a);
   TW_LAUNCH_CHECK();
   return TW_OK;
 }
