@@ -585,23 +585,46 @@ struct PackArgs {
   int C, ld, n_ct;
 };
 __global__ void __launch_bounds__(256) k_pack_act(PackArgs a) {
+  // one 16-byte chunk (8 columns) per thread and pass: eight neighbouring threads read 256 contiguous bytes and fill one
+  // 128-byte swizzled row of each part (C is a multiple of 64, rows are 16-byte aligned)
   __shared__ float red[8 * 64];
   const int net = blockIdx.z, tc = blockIdx.x, tr = blockIdx.y;
   const float* X = a.X[net];
   uint8_t* hi = a.img[net] + ((size_t)tr * a.n_ct + tc) * 32768;
-  const int lane = threadIdx.x & 31, kp = lane * 2, gc = tc * 64 + kp;
-  float s0 = 0.f, s1 = 0.f;
-  for (int r = threadIdx.x >> 5; r < 128; r += 8) {
+  const int ch = threadIdx.x & 7, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int r = threadIdx.x >> 3; r < 128; r += 32) {
     const int64_t gr = (int64_t)tr * 128 + r;
-    float v0 = 0.f, v1 = 0.f;
-    if (gr < a.M && gc < a.C) {
-      const float2 v = *reinterpret_cast<const float2*>(X + gr * a.ld + gc);
-      v0 = v.x, v1 = v.y;
+    float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+    if (gr < a.M) {
+      const float4* src = reinterpret_cast<const float4*>(X + gr * a.ld + tc * 64 + ch * 8);
+      v0 = src[0], v1 = src[1];
     }
-    s0 += v0, s1 += v1;
-    img_store2(hi, 16384, r, kp, v0, v1);
+    s[0] += v0.x, s[1] += v0.y, s[2] += v0.z, s[3] += v0.w, s[4] += v1.x, s[5] += v1.y, s[6] += v1.z, s[7] += v1.w;
+    uint4 h, l;
+    split2(v0.x, v0.y, h.x, l.x), split2(v0.z, v0.w, h.y, l.y), split2(v1.x, v1.y, h.z, l.z), split2(v1.z, v1.w, h.w, l.w);
+    const uint32_t off = sw128_offset(r, ch * 8, 128);
+    *reinterpret_cast<uint4*>(hi + off) = h;
+    *reinterpret_cast<uint4*>(hi + 16384 + off) = l;
   }
-  if (a.colsum[net]) tile_colsum_add(s0, s1, red, a.colsum[net], tc * 64, a.C);
+  if (a.colsum[net]) {
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      s[j] += __shfl_xor_sync(0xffffffffu, s[j], 8);
+      s[j] += __shfl_xor_sync(0xffffffffu, s[j], 16);
+    }
+    if (lane < 8) {
+#pragma unroll
+      for (int j = 0; j < 8; j++) red[w * 64 + lane * 8 + j] = s[j];
+    }
+    __syncthreads();
+    if (threadIdx.x < 64) {
+      float t = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; i++) t += red[i * 64 + threadIdx.x];
+      if (tc * 64 + (int)threadIdx.x < a.C) atomicAdd(a.colsum[net] + tc * 64 + threadIdx.x, t);
+    }
+  }
 }
 
 // Backward through an activation: given the pre-activation `pre` (bias included) and the gradient w.r.t.
@@ -719,15 +742,17 @@ struct LnBwdArgs {
 };
 __global__ void __launch_bounds__(256) k_ln_bwd(LnBwdArgs a) {
   __shared__ float red[3][8][128];
-  const int net = blockIdx.y, tr = blockIdx.x;
+  // one CTA per 32 rows of a tile (four rows per warp, all requested at once): 44 token tiles alone leave most SMs idle
+  const int net = blockIdx.y, tr = blockIdx.x >> 2, rbase = (blockIdx.x & 3) * 32;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const float4 gm = *reinterpret_cast<const float4*>(a.gamma[net] + 4 * lane);
   float4 ag = make_float4(0.f, 0.f, 0.f, 0.f), ab = ag, as = ag;
   uint8_t* tile_hi = a.img_dr[net] + ((size_t)tr * 2 + (lane >> 4)) * 32768;
-  for (int rb = w; rb < 128; rb += 64) {  // eight rows of the warp requested at once (a load-shuffle-store loop runs one round trip per row)
-   float4 xs[8], dys[8];
+  {
+   const int rb = rbase + w;
+   float4 xs[4], dys[4];
 #pragma unroll
-   for (int u = 0; u < 8; u++) {
+   for (int u = 0; u < 4; u++) {
      const int64_t gr = (int64_t)tr * 128 + rb + 8 * u;
      xs[u] = dys[u] = make_float4(0.f, 0.f, 0.f, 0.f);
      if (gr < a.M) {
@@ -736,7 +761,7 @@ __global__ void __launch_bounds__(256) k_ln_bwd(LnBwdArgs a) {
      }
    }
 #pragma unroll
-   for (int u = 0; u < 8; u++) {
+   for (int u = 0; u < 4; u++) {
     const int r = rb + 8 * u;
     const int64_t gr = (int64_t)tr * 128 + r;
     float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -787,10 +812,11 @@ __global__ void __launch_bounds__(256) k_features_img(const float* __restrict__ 
                                                       const float* __restrict__ xc, const float* __restrict__ xv,
                                                       const float* __restrict__ z_other, int64_t M, int V, int E, int n_types,
                                                       uint8_t* __restrict__ img) {
-  const int tr = blockIdx.x;
+  // one CTA per 32 rows of a tile: a launch over the 44 token tiles of a training batch is pure load latency
+  const int tr = blockIdx.x >> 2, rbase = (blockIdx.x & 3) * 32;
   uint8_t* hi = img + (size_t)tr * 32768;
   const int lane = threadIdx.x & 31, kp = lane * 2;
-  for (int r = threadIdx.x >> 5; r < 128; r += 8) {
+  for (int r = rbase + (threadIdx.x >> 5); r < rbase + 32; r += 8) {
     const int64_t m = (int64_t)tr * 128 + r;
     float v[2] = {0.f, 0.f};
     if (m < M) {
@@ -817,8 +843,8 @@ __global__ void __launch_bounds__(256) k_du_scatter(const float* __restrict__ du
   extern __shared__ float acc[];  // [n_types * E]
   for (int i = threadIdx.x; i < n_types * E; i += blockDim.x) acc[i] = 0.f;
   __syncthreads();
-  const int64_t m0 = (int64_t)blockIdx.x * 128;
-  for (int idx = threadIdx.x; idx < 128 * 64; idx += blockDim.x) {
+  const int64_t m0 = (int64_t)blockIdx.x * 32;  // 32 rows per CTA (see k_features_img)
+  for (int idx = threadIdx.x; idx < 32 * 64; idx += blockDim.x) {
     const int64_t m = m0 + (idx >> 6);
     const int e = idx & 63;
     if (m >= M) continue;
@@ -1479,7 +1505,7 @@ static int conditioner_bwd(BwdCtx& x, int k, float* dz_other, const float* z_oth
         a.dgamma[s] = x.gv.enc(k, s, t, 9), a.dbeta[s] = x.gv.enc(k, s, t, 10), a.dbias[s] = x.gv.enc(k, s, t, 6);
       }
       a.M = x.M, a.eps = c->layer_norm_eps;
-      k_ln_bwd<<<dim3(x.tiles, 2), 256, 0, x.st>>>(a);
+      k_ln_bwd<<<dim3(x.tiles * 4, 2), 256, 0, x.st>>>(a);
       TW_LAUNCH_CHECK();
     }
     // FFN weight images of this layer: W1 [F,128] row tile c at c*128K (+kb*16K), lo +32K; W2 [128,F] col tile b
@@ -1519,7 +1545,7 @@ static int conditioner_bwd(BwdCtx& x, int k, float* dz_other, const float* z_oth
         a.dgamma[s] = x.gv.enc(k, s, t, 7), a.dbeta[s] = x.gv.enc(k, s, t, 8), a.dbias[s] = nullptr;
       }
       a.M = x.M, a.eps = c->layer_norm_eps;
-      k_ln_bwd<<<dim3(x.tiles, 2), 256, 0, x.st>>>(a);
+      k_ln_bwd<<<dim3(x.tiles * 4, 2), 256, 0, x.st>>>(a);
       TW_LAUNCH_CHECK();
     }
     if (x.pv.local()) {
@@ -1626,7 +1652,7 @@ static int conditioner_bwd(BwdCtx& x, int k, float* dz_other, const float* z_oth
 
   // ------------------------------------------------------------------ in_mlp (dyA = gradient w.r.t. h0)
   {
-    k_features_img<<<x.tiles, 256, 0, x.st>>>(x.pv.embed(), x.atom_types, x.tp.xc, x.x_velocs, z_other_in, x.M, x.V, E, c->num_atom_types, b.img_u);
+    k_features_img<<<x.tiles * 4, 256, 0, x.st>>>(x.pv.embed(), x.atom_types, x.tp.xc, x.x_velocs, z_other_in, x.M, x.V, E, c->num_atom_types, b.img_u);
     TW_LAUNCH_CHECK();
     ImgRef w1[2], w2[2];
     for (int s = 0; s < 2; s++) {
@@ -1661,7 +1687,7 @@ static int conditioner_bwd(BwdCtx& x, int k, float* dz_other, const float* z_oth
     for (int s = 0; s < 2; s++) e.A[s] = plain_img(b.img_w1[s], hid / 64), e.B[s] = w1[s], e.C[s] = b.du[s];
     e.bn = 64, e.ldc = 64, e.rows = (int)x.M, e.cols = 64, e.tiles_m = x.tiles, e.tiles_n = 1, e.KB = hid / 64;
     TW_TRY(launch_gemm(c, e, x.st));
-    k_du_scatter<<<x.tiles, 256, c->num_atom_types * E * sizeof(float), x.st>>>(b.du[0], b.du[1], x.atom_types, x.M, E, c->num_atom_types,
+    k_du_scatter<<<x.tiles * 4, 256, c->num_atom_types * E * sizeof(float), x.st>>>(b.du[0], b.du[1], x.atom_types, x.M, E, c->num_atom_types,
                                                                              dz_other, x.gv.embed(), x.want_inputs ? b.dxc : nullptr,
                                                                              x.want_inputs ? b.dxv : nullptr);
     TW_LAUNCH_CHECK();
