@@ -641,34 +641,62 @@ struct ActBwdArgs {
 };
 template <int kAct>
 __global__ void __launch_bounds__(256) k_act_bwd(ActBwdArgs a) {
+  // one 16-byte chunk (8 columns) per thread and pass, like k_pack_act
   __shared__ float red[8 * 64];
   const int net = blockIdx.z, tc = blockIdx.x, tr = blockIdx.y;
   const size_t toff = ((size_t)tr * a.n_ct + tc) * 32768;
   uint8_t* act_hi = a.img_act[net] + toff;
   uint8_t* dp_hi = a.img_dpre[net] + toff;
-  const int lane = threadIdx.x & 31, kp = lane * 2, gc = tc * 64 + kp;
-  float s0 = 0.f, s1 = 0.f;
-  // (requesting every row of the tile before the first store was measured slower: 88 vs 76 us -- the kernel is bound by its
-  // 4-byte image stores, not by load latency)
-  for (int r = threadIdx.x >> 5; r < 128; r += 8) {
+  const int ch = threadIdx.x & 7, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int r = threadIdx.x >> 3; r < 128; r += 32) {
     const int64_t gr = (int64_t)tr * 128 + r;
-    float a0 = 0.f, a1 = 0.f, d0 = 0.f, d1 = 0.f;
+    float p[8], g[8], av[8], dv[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) p[j] = g[j] = 0.f;
     if (gr < a.M) {
-      const float2 p = *reinterpret_cast<const float2*>(a.pre[net] + gr * a.C + gc);
-      const float2 g = *reinterpret_cast<const float2*>(a.dact[net] + gr * a.C + gc);
-      if (kAct == ACT_RELU) {
-        a0 = fmaxf(p.x, 0.f), a1 = fmaxf(p.y, 0.f);
-        d0 = p.x > 0.f ? g.x : 0.f, d1 = p.y > 0.f ? g.y : 0.f;
-      } else {
-        a0 = silu_fwd(p.x), a1 = silu_fwd(p.y);
-        d0 = g.x * silu_grad(p.x), d1 = g.y * silu_grad(p.y);
-      }
+      const float4* ps = reinterpret_cast<const float4*>(a.pre[net] + gr * a.C + tc * 64 + ch * 8);
+      const float4* gs = reinterpret_cast<const float4*>(a.dact[net] + gr * a.C + tc * 64 + ch * 8);
+      const float4 p0 = ps[0], p1 = ps[1], g0 = gs[0], g1 = gs[1];
+      p[0] = p0.x, p[1] = p0.y, p[2] = p0.z, p[3] = p0.w, p[4] = p1.x, p[5] = p1.y, p[6] = p1.z, p[7] = p1.w;
+      g[0] = g0.x, g[1] = g0.y, g[2] = g0.z, g[3] = g0.w, g[4] = g1.x, g[5] = g1.y, g[6] = g1.z, g[7] = g1.w;
     }
-    s0 += d0, s1 += d1;
-    img_store2(act_hi, 16384, r, kp, a0, a1);
-    img_store2(dp_hi, 16384, r, kp, d0, d1);
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      if (gr >= a.M) {
+        av[j] = dv[j] = 0.f;
+      } else if (kAct == ACT_RELU) {
+        av[j] = fmaxf(p[j], 0.f), dv[j] = p[j] > 0.f ? g[j] : 0.f;
+      } else {
+        av[j] = silu_fwd(p[j]), dv[j] = g[j] * silu_grad(p[j]);
+      }
+      s[j] += dv[j];
+    }
+    uint4 h, l;
+    const uint32_t off = sw128_offset(r, ch * 8, 128);
+    split2(av[0], av[1], h.x, l.x), split2(av[2], av[3], h.y, l.y), split2(av[4], av[5], h.z, l.z), split2(av[6], av[7], h.w, l.w);
+    *reinterpret_cast<uint4*>(act_hi + off) = h;
+    *reinterpret_cast<uint4*>(act_hi + 16384 + off) = l;
+    split2(dv[0], dv[1], h.x, l.x), split2(dv[2], dv[3], h.y, l.y), split2(dv[4], dv[5], h.z, l.z), split2(dv[6], dv[7], h.w, l.w);
+    *reinterpret_cast<uint4*>(dp_hi + off) = h;
+    *reinterpret_cast<uint4*>(dp_hi + 16384 + off) = l;
   }
-  tile_colsum_add(s0, s1, red, a.dbias[net], tc * 64, a.C);
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    s[j] += __shfl_xor_sync(0xffffffffu, s[j], 8);
+    s[j] += __shfl_xor_sync(0xffffffffu, s[j], 16);
+  }
+  if (lane < 8) {
+#pragma unroll
+    for (int j = 0; j < 8; j++) red[w * 64 + lane * 8 + j] = s[j];
+  }
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; i++) t += red[i * 64 + threadIdx.x];
+    if (tc * 64 + (int)threadIdx.x < a.C) atomicAdd(a.dbias[net] + tc * 64 + threadIdx.x, t);
+  }
 }
 
 // Last layer of the out_mlp (hidden -> 3, mlp.py:18-23) backward, fused with the SiLU backward of the hidden
