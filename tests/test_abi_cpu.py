@@ -189,6 +189,28 @@ def test_no_cpu_fallback():
         e(torch.zeros(1, 21, 3))
 
 
+def test_flat_adam_host_side():
+    """optim.FlatAdam without the CUDA backward: the reference-shaped constructor (utilities/training_utils.py:356-368), a loud
+    error instead of a silent torch fallback, and its state dict."""
+    from types import SimpleNamespace
+    from timewarp_b200.optim import FlatAdam, get_optimizer
+    m = tw.custom_transformer_nvp_constructor(model_config(TINY_O, "bf16x3"))
+    opt = get_optimizer(m, SimpleNamespace(optimizer="Adam", learning_rate=3e-4, weight_decay=1e-2, warmup_steps=0))
+    assert isinstance(opt, FlatAdam) and isinstance(opt, torch.optim.Optimizer)
+    g = opt.param_groups[0]
+    assert (g["lr"], g["weight_decay"], g["betas"], g["eps"]) == (3e-4, 1e-2, (0.9, 0.999), 1e-8)
+    assert len(g["params"]) == sum(1 for p in m.parameters() if p.requires_grad)
+    with pytest.raises(_lib.TimewarpB200Error, match="no flat gradient buffer"):
+        opt.step()
+    sd = opt.state_dict()
+    assert sd["flat"] and sd["exp_avg"] is None and sd["hyper"]["lr"] == 3e-4
+    opt.load_state_dict({**sd, "hyper": {**sd["hyper"], "lr": 1e-5}})
+    assert opt.param_groups[0]["lr"] == 1e-5
+    with pytest.raises(ValueError):
+        opt.load_state_dict(torch.optim.Adam(m.parameters()).state_dict())
+    opt.zero_grad(set_to_none=True)
+
+
 def test_chirality_centers_host():
     from timewarp_b200.chirality import find_chirality_centers
     g = np.load(os.path.join(GOLDEN, "chirality_2olx.npz"))
