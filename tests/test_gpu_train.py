@@ -161,6 +161,41 @@ def test_backward_matches_oracle_autograd_every_tensor():
     print("worst per-tensor gradient rel err", worst, "median", float(np.median(errs)))
 
 
+def test_large_batch_gradient_is_the_mean_of_chunk_gradients():
+    """Size-independent property at a size the oracle would take minutes for: the mean-NLL gradient of 96 ragged samples
+    (2112 tokens = 17 token tiles: every CTA of the fused FFN-backward kernel walks over several token tiles, the weight-gradient
+    GEMMs split their contraction) equals the mean of the gradients of its 8 chunks of 12 samples (3 token tiles each)."""
+    torch.manual_seed(11)
+    B, V, n_chunks = 96, 22, 8
+    lengths = torch.randint(9, V + 1, (B,))
+    lengths[::12] = V
+    mask = torch.arange(V)[None, :] >= lengths[:, None]
+    keep = (~mask)[:, :, None]
+    x = 0.3 * torch.randn(B, V, 3) * keep
+    y = (x + 0.02 * torch.randn(B, V, 3)) * keep
+    xv, yv = torch.randn(B, V, 3) * keep, torch.randn(B, V, 3) * keep
+    at = torch.randint(0, 5, (B, V)) * (~mask)
+    g = dict(atom_types=at, x_coords=x, x_velocs=xv, y_coords=y, y_velocs=yv, masked_elements=mask)
+    m, _ = build_model(FULL_O, "bf16x3", 2)
+    loss, grads = _loss_and_grads(m, g)
+    acc, loss_acc = None, 0.0
+    per = B // n_chunks
+    for c in range(n_chunks):
+        gc = {k: v[c * per:(c + 1) * per] for k, v in g.items()}
+        lc, gr = _loss_and_grads(m, gc)
+        loss_acc += float(lc) / n_chunks
+        acc = {k: v.double() / n_chunks for k, v in gr.items()} if acc is None else {k: acc[k] + gr[k].double() / n_chunks for k in acc}
+    assert abs(float(loss) - loss_acc) < 1e-5 * abs(loss_acc)
+    total = float(torch.sqrt(sum(v.norm() ** 2 for v in acc.values())))
+    errs = []
+    for k, ref in acc.items():
+        err = float((grads[k].double() - ref).norm())
+        scale = max(float(ref.norm()), 1e-4 * total)
+        errs.append(err / scale)
+        assert err <= 2e-4 * scale, (k, err / scale)
+    assert float(np.median(errs)) < 2e-5, float(np.median(errs))
+
+
 def test_local_attention_gradients_match_oracle_autograd():
     """`local` attention trains (local_self_attention.py:46-119; the reference's tests/test_batching.py:132-177 runs train-capable
     models of all three attention types): every parameter gradient -- qkv_proj / output_proj included -- against the oracle's
