@@ -1712,8 +1712,10 @@ struct MixTokSmem {
   __host__ __device__ uint32_t total() const { return bars() + 256; }
 };
 
-template <int kSplit>
-__global__ void __launch_bounds__(kMixTokThreads, 1) k_mix_tok(MixArgs a) {
+// kMinBlocks = 2: small samples (shared memory below half an SM's) run two CTAs per SM -- the kernel allocates 256 TMEM columns --
+// so that a training batch of a few hundred samples needs half as many rounds (register budget 80 per thread).
+template <int kSplit, int kMinBlocks = 1>
+__global__ void __launch_bounds__(kMixTokThreads, kMinBlocks) k_mix_tok(MixArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // (pointer arithmetic keeps the shared address space: LDS / STS)
   const int net = blockIdx.y;
@@ -3070,12 +3072,23 @@ int tc_mix(const tw_flow_config* c, const float* const x[2], uint8_t* const img[
     const int max_smem = 232448;
     TW_CUDA(cudaFuncSetAttribute(k_mix_tok<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     TW_CUDA(cudaFuncSetAttribute(k_mix_tok<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    TW_CUDA(cudaFuncSetAttribute((k_mix_tok<3, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+    TW_CUDA(cudaFuncSetAttribute((k_mix_tok<1, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
   }
   if (use_tok && VP <= kMixTokMaxVP) {
     int tok_stages = kMixTokStages;
     if ((int)MixTokSmem(V, VP, tok_stages).total() + 1024 > 232448) tok_stages = 2;
     const int smem_tok = (int)MixTokSmem(V, VP, tok_stages).total() + 1024;
     a.n_stages = tok_stages;
+    if (smem_tok <= 112 * 1024 && n > per_net) {  // two CTAs per SM
+      const int gx2 = (int)(n < 2 * per_net ? n : 2 * per_net);
+      if (c->precision == TW_PRECISION_BF16X3)
+        k_mix_tok<3, 2><<<dim3(gx2, nets), kMixTokThreads, smem_tok, st>>>(a);
+      else
+        k_mix_tok<1, 2><<<dim3(gx2, nets), kMixTokThreads, smem_tok, st>>>(a);
+      TW_LAUNCH_CHECK();
+      return TW_OK;
+    }
     if (c->precision == TW_PRECISION_BF16X3)
       k_mix_tok<3><<<grid, kMixTokThreads, smem_tok, st>>>(a);
     else
