@@ -200,7 +200,11 @@ def test_flat_adam_host_side():
     g = opt.param_groups[0]
     assert (g["lr"], g["weight_decay"], g["betas"], g["eps"]) == (3e-4, 1e-2, (0.9, 0.999), 1e-8)
     assert len(g["params"]) == sum(1 for p in m.parameters() if p.requires_grad)
-    with pytest.raises(_lib.TimewarpB200Error, match="no flat gradient buffer"):
+    with pytest.raises(_lib.TimewarpB200Error, match="no gradient to apply"):
+        opt.step()
+    for q in m.parameters():
+        q.grad = torch.zeros_like(q)
+    with pytest.raises(_lib.TimewarpB200Error, match="no CPU fallback"):
         opt.step()
     sd = opt.state_dict()
     assert sd["flat"] and sd["exp_avg"] is None and sd["hyper"]["lr"] == 3e-4

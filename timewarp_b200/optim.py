@@ -5,7 +5,7 @@ On this model that is 659 parameter tensors, most of them 128 x 128: torch's fus
 1.1 ms per step for 1 GB of traffic.  The hand-written backward already returns every gradient as a slice of one flat buffer
 (flow.py `_gradient_table`); `FlatAdam` re-homes the parameters into a buffer with the same slice offsets (the tensors keep
 their identity, shapes and state-dict keys -- only their storage moves) and keeps both moment buffers flat, so a step is a
-single 28-bytes-per-element stream over the buffers.  Same update rule as `torch.optim.Adam` (bias-corrected moments, L2
+single 28-bytes-per-element stream over the buffers (gradients that are not views of that buffer are gathered first).  Same update rule as `torch.optim.Adam` (bias-corrected moments, L2
 weight decay added to the gradient, no amsgrad), checked against it step by step in tests/test_gpu_train.py.
 
 The hyper-parameters live in a small device tensor: a captured CUDA graph of the training step follows a learning-rate
@@ -22,10 +22,14 @@ from . import _lib
 
 
 class FlatAdam(torch.optim.Optimizer):
-    """Adam over the flat gradient buffer of a `ConditionalFlowDensityModel` (CUDA, tensor-core precisions).
+    """Adam over flat parameter / gradient / moment buffers (CUDA): one launch per step.
 
-    Every trainable parameter of `model` must receive its gradient from the model's own backward (as a view of
-    `model._last_flat_grad`); a parameter with a foreign gradient raises -- use `torch.optim.Adam` for such modules."""
+    Fast path: every `p.grad` is the view of `model._last_flat_grad` that the model's own backward handed out (autograd's
+    AccumulateGrad keeps such a gradient as it is when nothing else references it) -- the kernel reads that buffer directly.
+    Otherwise (autograd cloned the gradients -- it does under compute-sanitizer, for instance --, a second autograd node, a
+    foreign module, gradients the data-parallel trainer reduced in buckets) the gradients are first gathered into a flat
+    buffer of the optimizer's own with one `torch._foreach_copy_`.  A parameter without a gradient keeps zero moments and
+    does not move, like in torch.optim.Adam."""
 
     def __init__(self, model, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0):
         params = [p for p in model.parameters() if p.requires_grad]
@@ -39,36 +43,70 @@ class FlatAdam(torch.optim.Optimizer):
         self._hyper: Optional[Tensor] = None  # device: lr, beta1, beta2, eps, weight_decay, step
         self._hyper_host = None
         self._offsets = None
+        self._gbuf: Optional[Tensor] = None   # gather path: the optimizer's own flat gradient buffer ...
+        self._gviews = None                   # ... and its per-parameter views
+        self.fast_path_steps = 0              # steps that read the model's flat gradient buffer directly
+        self.gather_steps = 0
 
     # ------------------------------------------------------------------ layout
-    def _param_offsets(self, flat_g: Tensor, params=None):
+    def _view_offsets(self, flat_g: Optional[Tensor]):
+        """Offsets of every p.grad inside flat_g, or None if any gradient is missing / lives elsewhere."""
+        if flat_g is None or not flat_g.is_cuda or flat_g.dtype != torch.float32:
+            return None
         base, end = flat_g.data_ptr(), flat_g.data_ptr() + flat_g.numel() * 4
         offs = []
-        for p in (self.param_groups[0]["params"] if params is None else params):
+        for p in self.param_groups[0]["params"]:
             g = p.grad
-            if g is None:
-                raise _lib.TimewarpB200Error("FlatAdam: a trainable parameter has no gradient (run the model's backward first)")
+            if g is None or g.dtype != torch.float32 or not g.is_contiguous():
+                return None
             a = g.data_ptr()
-            if not (g.dtype == torch.float32 and g.is_contiguous() and base <= a and a + g.numel() * 4 <= end):
-                raise _lib.TimewarpB200Error("FlatAdam: a gradient does not live in the model's flat gradient buffer "
-                                             "(foreign module or a second autograd node: use torch.optim.Adam)")
+            if not (base <= a and a + g.numel() * 4 <= end):
+                return None
             offs.append((a - base) // 4)
         return offs
 
-    def _adopt(self, flat_g: Tensor) -> None:
-        """First step: move every parameter into a flat buffer laid out like the gradient buffer."""
-        offs = self._param_offsets(flat_g)
-        flat_p = torch.zeros_like(flat_g)
-        for p, o in zip(self.param_groups[0]["params"], offs):
+    def _adopt(self, flat_g: Optional[Tensor]) -> None:
+        """First step: move every parameter into a flat buffer -- laid out like the model's gradient buffer when the gradients
+        are views of it (so that later steps can read it in place), else packed in parameter order (16-byte aligned slices)."""
+        params = self.param_groups[0]["params"]
+        dev = params[0].device
+        if not params[0].is_cuda:
+            raise _lib.TimewarpB200Error("FlatAdam: no CPU fallback -- the parameters must live on a CUDA device")
+        offs = self._view_offsets(flat_g)
+        if offs is not None:
+            n = flat_g.numel()
+        else:
+            offs, n = [], 0
+            for p in params:
+                offs.append(n)
+                n += (p.numel() + 3) // 4 * 4
+        flat_p = torch.zeros(n, dtype=torch.float32, device=dev)
+        for p, o in zip(params, offs):
+            if p.dtype != torch.float32:
+                raise TypeError("FlatAdam: parameters must be float32")
             view = flat_p[o:o + p.numel()].view(p.shape)
             view.copy_(p.data)
             p.data = view
         self._flat_p, self._offsets = flat_p, offs
-        self._m, self._v = torch.zeros_like(flat_g), torch.zeros_like(flat_g)
-        self._hyper = torch.zeros(8, dtype=torch.float32, device=flat_g.device)
+        self._m, self._v = torch.zeros_like(flat_p), torch.zeros_like(flat_p)
+        self._hyper = torch.zeros(8, dtype=torch.float32, device=dev)
         # the model caches raw parameter pointers and the packed bf16 weight images: both refer to the old storage
-        self.model._table = None
-        self.model._packed = None
+        if hasattr(self.model, "_table"):
+            self.model._table = None
+        if hasattr(self.model, "_packed"):
+            self.model._packed = None
+
+    def _gather(self) -> Tensor:
+        params = self.param_groups[0]["params"]
+        if self._gbuf is None:
+            self._gbuf = torch.zeros_like(self._flat_p)
+            self._gviews = [self._gbuf[o:o + p.numel()].view(p.shape) for p, o in zip(params, self._offsets)]
+        have = [(v, p.grad) for v, p in zip(self._gviews, params) if p.grad is not None]
+        if len(have) != len(params):
+            self._gbuf.zero_()
+        if have:
+            torch._foreach_copy_([v for v, _ in have], [g for _, g in have])
+        return self._gbuf
 
     def sync_hyper(self) -> None:
         """Upload lr / betas / eps / weight_decay if they changed on the host (not allowed while a graph is being captured)."""
@@ -87,23 +125,28 @@ class FlatAdam(torch.optim.Optimizer):
         if closure is not None:
             with torch.enable_grad():
                 loss = closure()
+        params = self.param_groups[0]["params"]
+        if all(p.grad is None for p in params):
+            raise _lib.TimewarpB200Error("FlatAdam: no gradient to apply (the backward has not run)")
         flat_g = getattr(self.model, "_last_flat_grad", None)
-        if flat_g is None or not flat_g.is_cuda:
-            raise _lib.TimewarpB200Error("FlatAdam: no flat gradient buffer (the model's CUDA training backward has not run)")
         if self._flat_p is None:
             self._adopt(flat_g)
-        else:  # cheap per-step checks (first and last parameter): same gradient layout, parameters still inside the flat buffer
-            ends = [self.param_groups[0]["params"][0], self.param_groups[0]["params"][-1]]
-            if flat_g.numel() != self._flat_p.numel() or self._param_offsets(flat_g, ends) != [self._offsets[0], self._offsets[-1]]:
-                raise _lib.TimewarpB200Error("FlatAdam: the gradient layout changed between steps")
-            for p, o in zip(ends, (self._offsets[0], self._offsets[-1])):  # `.to()` / `.data = ...` would silently detach a parameter
-                if p.data_ptr() != self._flat_p.data_ptr() + 4 * o:
-                    raise _lib.TimewarpB200Error("FlatAdam: a parameter left the flat buffer (model.to() after the first step?)")
+        else:
+            first, last = params[0], params[-1]  # `.to()` / `.data = ...` would silently detach a parameter from the flat buffer
+            if (first.data_ptr() != self._flat_p.data_ptr() + 4 * self._offsets[0]
+                    or last.data_ptr() != self._flat_p.data_ptr() + 4 * self._offsets[-1]):
+                raise _lib.TimewarpB200Error("FlatAdam: a parameter left the flat buffer (model.to() after the first step?)")
+        if flat_g is not None and flat_g.numel() == self._flat_p.numel() and self._view_offsets(flat_g) == self._offsets:
+            g_buf = flat_g
+            self.fast_path_steps += 1
+        else:
+            g_buf = self._gather()
+            self.gather_steps += 1
         self.sync_hyper()
         self._hyper[5:6].add_(1.0)
-        stream = torch.cuda.current_stream(flat_g.device).cuda_stream
-        _lib.check(_lib.load().tw_adam_step(_lib.ptr(self._flat_p), _lib.ptr(flat_g), _lib.ptr(self._m), _lib.ptr(self._v),
-                                            flat_g.numel(), _lib.ptr(self._hyper), stream), "tw_adam_step")
+        stream = torch.cuda.current_stream(g_buf.device).cuda_stream
+        _lib.check(_lib.load().tw_adam_step(_lib.ptr(self._flat_p), _lib.ptr(g_buf), _lib.ptr(self._m), _lib.ptr(self._v),
+                                            g_buf.numel(), _lib.ptr(self._hyper), stream), "tw_adam_step")
         return loss
 
     # ------------------------------------------------------------------ checkpointing (utilities/model_utils.py:12-32)
