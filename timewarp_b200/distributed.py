@@ -216,12 +216,13 @@ class DataParallelTrainer:
         flat = getattr(self.model, "_last_flat_grad", None)
         if flat is None:
             return False
-        base = flat.untyped_storage().data_ptr()
+        lo, hi = flat.data_ptr(), flat.data_ptr() + flat.numel() * flat.element_size()
         seen = False
         for p in self.model.parameters():
             if not p.requires_grad or p.grad is None:  # (unused parameters, e.g. the log_lengthscales a pass never reads,
                 continue                               #  have no gradient on ANY rank: nothing to reduce)
-            if p.grad.untyped_storage().data_ptr() != base:
+            a = p.grad.data_ptr()  # (address range instead of storage identity: no Python storage object per parameter and step)
+            if a < lo or a + p.grad.numel() * p.grad.element_size() > hi:
                 return False
             seen = True
         if not seen:
