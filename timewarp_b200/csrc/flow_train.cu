@@ -964,39 +964,46 @@ struct WcChainArgs {
   float* dwo[2];
   float* dwv[2];
 };
-// One CTA per (head, block of 16 rows, network), 256 threads: the head's W_v block (padded rows) and dWc block live in shared
-// memory (138 KB), so each 64 KB matrix is read 8 times per head instead of 128 times (the row-per-CTA version moved 200 MB
-// through L2 per launch: 49 us for 50 MFLOP).  Thread t owns column (t & 127) of 8 output rows in both products.
-constexpr int kWcChainSmem = (128 * 129 + 128 * 128 + 128 * 16) * (int)sizeof(float);
+// One CTA per (head, block of 16 rows, network, product), 256 threads.  Product 0 (dW_o) keeps the head's W_v block (padded rows)
+// and its 16 rows of dWc in shared memory, product 1 (dW_v) the head's dWc block and 16 columns of W_o: 74 KB per CTA, three CTAs
+// per SM, 192 CTAs in one wave (the row-per-CTA first version moved 200 MB through L2 per launch: 49 us for 50 MFLOP; both
+// products in one CTA of 138 KB: 22 us).  Thread t owns column (t & 127) of 8 output rows.
+constexpr int kWcChainSmem = (128 * 129 + 128 * 16) * (int)sizeof(float);
 __global__ void __launch_bounds__(256) k_wc_chain(WcChainArgs a, int H) {
   extern __shared__ __align__(16) float wsm[];
-  float* sV = wsm;                  // [128 k][129]   W_v[hD + k, j]
-  float* sD = sV + 128 * 129;       // [128 i][128]   dWc[i, hD + j]
-  float* sO = sD + 128 * 128;       // [128 i][16]    W_o[i, hD + 16 rb + kk]
-  const int net = blockIdx.z, h = blockIdx.x, rb = blockIdx.y, t = threadIdx.x;
+  float* sBig = wsm;                 // product 0: [128 k][129] W_v[hD + k, j];  product 1: [128 i][128] dWc[i, hD + j]
+  float* sSmall = wsm + 128 * 129;   // product 0: [16 i][128] dWc[16 rb + i, hD + j];  product 1: [128 i][16] W_o[i, hD + 16 rb + kk]
+  const int net = blockIdx.z >> 1, prod = blockIdx.z & 1, h = blockIdx.x, rb = blockIdx.y, t = threadIdx.x;
   const int HD = H * 128;
   const float* dwc = a.dwc[net] + h * 128;
   const float* wo = a.wo[net] + h * 128;
   const float* wv = a.wv[net] + (size_t)h * 128 * 128;
-  for (int e = t; e < 128 * 32; e += 256) {  // float4 pieces: row = e >> 5, columns 4 * (e & 31)
-    const int r = e >> 5, c4 = (e & 31) * 4;
-    const float4 v = __ldg(reinterpret_cast<const float4*>(wv + (size_t)r * 128 + c4));
-    sV[r * 129 + c4] = v.x, sV[r * 129 + c4 + 1] = v.y, sV[r * 129 + c4 + 2] = v.z, sV[r * 129 + c4 + 3] = v.w;
-    *reinterpret_cast<float4*>(sD + r * 128 + c4) = __ldg(reinterpret_cast<const float4*>(dwc + (size_t)r * HD + c4));
-  }
-  for (int e = t; e < 128 * 4; e += 256) {
-    const int r = e >> 2, c4 = (e & 3) * 4;
-    *reinterpret_cast<float4*>(sO + r * 16 + c4) = __ldg(reinterpret_cast<const float4*>(wo + (size_t)r * HD + rb * 16 + c4));
-  }
-  __syncthreads();
   const int col = t & 127, g8 = (t >> 7) * 8;
-  // dW_o[i, hD + k] += sum_j dWc[i, hD + j] W_v[hD + k, j],   i = 16 rb + g8 + u, k = col
-  {
+  if (prod == 0) {
+    {  // float4 pieces: row = e >> 5, columns 4 * (e & 31); all 16 loads of a thread in flight before the first store
+      float4 v[16];
+#pragma unroll
+      for (int i = 0; i < 16; i++) {
+        const int e = t + 256 * i;
+        v[i] = __ldg(reinterpret_cast<const float4*>(wv + (size_t)(e >> 5) * 128 + (e & 31) * 4));
+      }
+#pragma unroll
+      for (int i = 0; i < 16; i++) {
+        const int e = t + 256 * i, r = e >> 5, c4 = (e & 31) * 4;
+        sBig[r * 129 + c4] = v[i].x, sBig[r * 129 + c4 + 1] = v[i].y, sBig[r * 129 + c4 + 2] = v[i].z, sBig[r * 129 + c4 + 3] = v[i].w;
+      }
+    }
+    for (int e = t; e < 16 * 32; e += 256) {
+      const int r = e >> 5, c4 = (e & 31) * 4;
+      *reinterpret_cast<float4*>(sSmall + r * 128 + c4) = __ldg(reinterpret_cast<const float4*>(dwc + (size_t)(rb * 16 + r) * HD + c4));
+    }
+    __syncthreads();
+    // dW_o[i, hD + k] += sum_j dWc[i, hD + j] W_v[hD + k, j],   i = 16 rb + g8 + u, k = col
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    const float* drow = sD + (rb * 16 + g8) * 128;
+    const float* drow = sSmall + g8 * 128;
 #pragma unroll 4
     for (int j = 0; j < 128; j += 4) {
-      const float v0 = sV[col * 129 + j], v1 = sV[col * 129 + j + 1], v2 = sV[col * 129 + j + 2], v3 = sV[col * 129 + j + 3];
+      const float v0 = sBig[col * 129 + j], v1 = sBig[col * 129 + j + 1], v2 = sBig[col * 129 + j + 2], v3 = sBig[col * 129 + j + 3];
 #pragma unroll
       for (int u = 0; u < 8; u++) {
         const float4 d = *reinterpret_cast<const float4*>(drow + u * 128 + j);  // broadcast
@@ -1005,14 +1012,31 @@ __global__ void __launch_bounds__(256) k_wc_chain(WcChainArgs a, int H) {
     }
 #pragma unroll
     for (int u = 0; u < 8; u++) a.dwo[net][(size_t)(rb * 16 + g8 + u) * HD + h * 128 + col] += acc[u];
-  }
-  // dW_v[hD + k, j] += sum_i W_o[i, hD + k] dWc[i, hD + j],   k = 16 rb + g8 + u, j = col
-  {
+  } else {
+    {
+      float4 v[16];
+#pragma unroll
+      for (int i = 0; i < 16; i++) {
+        const int e = t + 256 * i;
+        v[i] = __ldg(reinterpret_cast<const float4*>(dwc + (size_t)(e >> 5) * HD + (e & 31) * 4));
+      }
+#pragma unroll
+      for (int i = 0; i < 16; i++) {
+        const int e = t + 256 * i;
+        *reinterpret_cast<float4*>(sBig + (e >> 5) * 128 + (e & 31) * 4) = v[i];
+      }
+    }
+    for (int e = t; e < 128 * 4; e += 256) {
+      const int r = e >> 2, c4 = (e & 3) * 4;
+      *reinterpret_cast<float4*>(sSmall + r * 16 + c4) = __ldg(reinterpret_cast<const float4*>(wo + (size_t)r * HD + rb * 16 + c4));
+    }
+    __syncthreads();
+    // dW_v[hD + k, j] += sum_i W_o[i, hD + k] dWc[i, hD + j],   k = 16 rb + g8 + u, j = col
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll 4
     for (int i = 0; i < 128; i++) {
-      const float d = sD[i * 128 + col];
-      const float4 o0 = *reinterpret_cast<const float4*>(sO + i * 16 + g8), o1 = *reinterpret_cast<const float4*>(sO + i * 16 + g8 + 4);
+      const float d = sBig[i * 128 + col];
+      const float4 o0 = *reinterpret_cast<const float4*>(sSmall + i * 16 + g8), o1 = *reinterpret_cast<const float4*>(sSmall + i * 16 + g8 + 4);
       acc[0] = fmaf(o0.x, d, acc[0]), acc[1] = fmaf(o0.y, d, acc[1]), acc[2] = fmaf(o0.z, d, acc[2]), acc[3] = fmaf(o0.w, d, acc[3]);
       acc[4] = fmaf(o1.x, d, acc[4]), acc[5] = fmaf(o1.y, d, acc[5]), acc[6] = fmaf(o1.z, d, acc[6]), acc[7] = fmaf(o1.w, d, acc[7]);
     }
@@ -1635,7 +1659,7 @@ static int conditioner_bwd(BwdCtx& x, int k, float* dz_other, const float* z_oth
         TW_CUDA(cudaFuncSetAttribute(k_wc_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, kWcChainSmem));
         chain_attr.mark();
       }
-      k_wc_chain<<<dim3(H, 8, 2), 256, kWcChainSmem, x.st>>>(ch, H);
+      k_wc_chain<<<dim3(H, 8, 4), 256, kWcChainSmem, x.st>>>(ch, H);
       TW_LAUNCH_CHECK();
       // G_h = A_h^T dr  (transposed score images), then dx = dr + sum_h G_h W_c,h
       if (x.pv.chebyshev()) {
