@@ -332,7 +332,7 @@ __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
 constexpr int kFbpStages = 3;
 constexpr int kFbpStageBytes = 32768;   // W hi 16K | W lo 16K
 constexpr int kFbpResident = 131072;    // y1 kb0, kb1, dr kb0, kb1: each hi 16K | lo 16K
-constexpr int kFbpThreads = 320;        // producer, MMA issuer, 8 epilogue warps (two per TMEM lane quarter: column groups 0-1 / 2-3)
+constexpr int kFbpThreads = 576;        // producer, MMA issuer, 16 epilogue warps (four per TMEM lane quarter: one 32-column group each)
 template <int kSplit>
 __global__ void __launch_bounds__(kFbpThreads, 1) k_ffn_bwd_pre(FfnBwdPreArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -351,7 +351,7 @@ __global__ void __launch_bounds__(kFbpThreads, 1) k_ffn_bwd_pre(FfnBwdPreArgs a)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_free + 1);
   if (tid == 0) {
     for (int i = 0; i < kFbpStages; i++) mbar_init(&full[i], 1), mbar_init(&empty[i], 1);
-    for (int i = 0; i < 2; i++) mbar_init(&acc_full[i], 1), mbar_init(&acc_free[i], 256);
+    for (int i = 0; i < 2; i++) mbar_init(&acc_full[i], 1), mbar_init(&acc_free[i], 512);
     mbar_init(res_full, 1), mbar_init(res_free, 1);
     mbar_fence_init();
   }
@@ -457,7 +457,7 @@ __global__ void __launch_bounds__(kFbpThreads, 1) k_ffn_bwd_pre(FfnBwdPreArgs a)
       }
     }
   } else {
-    const int q = warp & 3, half = (warp - 2) >> 2;
+    const int q = warp & 3, g = (warp - 2) >> 2;
     const int row = q * 32 + lane;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     const uint32_t sw = (uint32_t)row & 7u;
@@ -473,8 +473,7 @@ __global__ void __launch_bounds__(kFbpThreads, 1) k_ffn_bwd_pre(FfnBwdPreArgs a)
       ph_full[tb] ^= 1;
       tc_fence_after();
       const bool valid = (int64_t)tm * 128 + row < a.rows;
-#pragma unroll 1
-      for (int g = 2 * half; g < 2 * half + 2; g++) {
+      {
         const int col0 = tn * 128 + g * 32;
         const size_t toff = ((size_t)tm * a.n_ct + (size_t)(col0 >> 6)) * 32768 + (size_t)row * 128;
         uint8_t* act_hi = a.img_act[net] + toff;
