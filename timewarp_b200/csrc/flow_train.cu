@@ -738,11 +738,19 @@ __global__ void __launch_bounds__(256) k_out_last_bwd(OutLastArgs a) {
 #pragma unroll
   for (int i = 0; i < 3; i++) w[i][0] = a.w4[net][i * a.hid + gc], w[i][1] = a.w4[net][i * a.hid + gc + 1];
   float s0 = 0.f, s1 = 0.f, gw[3][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
-  for (int r = threadIdx.x >> 5; r < 128; r += 8) {
+  float2 pv[16];  // the thread's 16 pre-activation pairs, requested at once
+#pragma unroll
+  for (int i = 0; i < 16; i++) {
+    const int64_t gr = (int64_t)tr * 128 + (threadIdx.x >> 5) + 8 * i;
+    pv[i] = gr < a.M ? __ldg(reinterpret_cast<const float2*>(a.pre[net] + gr * a.hid + gc)) : make_float2(0.f, 0.f);
+  }
+#pragma unroll
+  for (int i = 0; i < 16; i++) {
+    const int r = (threadIdx.x >> 5) + 8 * i;
     const int64_t gr = (int64_t)tr * 128 + r;
     float d0 = 0.f, d1 = 0.f;
     if (gr < a.M) {
-      const float2 p = *reinterpret_cast<const float2*>(a.pre[net] + gr * a.hid + gc);
+      const float2 p = pv[i];
       const float g0 = sd[r * 3], g1 = sd[r * 3 + 1], g2 = sd[r * 3 + 2];
       const float act0 = silu_fwd(p.x), act1 = silu_fwd(p.y);
       gw[0][0] = fmaf(g0, act0, gw[0][0]), gw[0][1] = fmaf(g0, act1, gw[0][1]);
