@@ -55,9 +55,42 @@ class ClockSampler(threading.Thread):
     def __init__(self, gpu_index):
         super().__init__(daemon=True)
         self.gpu, self.rows, self.stop_flag = gpu_index, [], threading.Event()
+        # NVML in-process (the library behind nvidia-smi): a query costs microseconds.  Spawning nvidia-smi five times a second
+        # stalls work submission for milliseconds each time, which a region with one host round trip per step (e2e) pays in full.
+        self.source, self._nvml, self._h = "nvidia-smi", None, None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self._nvml, self._h, self.source = pynvml, pynvml.nvmlDeviceGetHandleByIndex(gpu_index), "nvml"
+        except Exception:
+            self._nvml = None
+
+    def _sample_nvml(self):
+        n, h = self._nvml, self._h
+        sm = n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM)
+        mx = n.nvmlDeviceGetMaxClockInfo(h, n.NVML_CLOCK_SM)
+        try:
+            bits = n.nvmlDeviceGetCurrentClocksEventReasons(h)
+        except Exception:
+            bits = n.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+        try:
+            power = n.nvmlDeviceGetPowerUsage(h) / 1000.0
+        except Exception:
+            power = float("nan")
+        flag = lambda m: "Active" if bits & m else "Not Active"  # noqa: E731
+        # nvml.h: SwPowerCap 0x4, HwSlowdown 0x8, SwThermalSlowdown 0x20, HwThermalSlowdown 0x40
+        return [str(self.gpu), str(sm), str(mx), f"{power:.1f}", hex(bits), flag(0x8), flag(0x40), flag(0x20), flag(0x4)]
 
     def run(self):
         while not self.stop_flag.is_set():
+            if self._nvml is not None:
+                try:
+                    self.rows.append(self._sample_nvml())
+                    self.stop_flag.wait(0.2)
+                    continue
+                except Exception:
+                    self._nvml, self.source = None, "nvidia-smi"
             try:
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.gpu)],
                                      capture_output=True, text=True, timeout=5).stdout.strip()
@@ -80,7 +113,8 @@ class ClockSampler(threading.Thread):
                     reasons.add(n)
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm),
+                "source": self.source}
 
 
 def synthetic_chains(pep, n_chains, seed):
