@@ -36,3 +36,39 @@ def test_reference_arm_other_ranks_exit_quietly():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"],
                          capture_output=True, text=True, timeout=300, cwd=ROOT, env=env)
     assert out.returncode == 0 and not [l for l in out.stdout.splitlines() if l.startswith("{")]
+
+
+def test_clock_sampler_rows_and_sources():
+    """The clocks line of the bench contract: NVML in-process when a driver is present, nvidia-smi otherwise; both feed the same
+    summary (median SM clock under load, max clock, active slowdown reasons)."""
+    import bench
+
+    smp = bench.ClockSampler(0)
+    assert smp.source in ("nvml", "nvidia-smi")
+
+    class FakeNvml:
+        NVML_CLOCK_SM = 1
+
+        @staticmethod
+        def nvmlDeviceGetClockInfo(h, kind):
+            return 1650
+
+        @staticmethod
+        def nvmlDeviceGetMaxClockInfo(h, kind):
+            return 1965
+
+        @staticmethod
+        def nvmlDeviceGetCurrentClocksEventReasons(h):
+            return 0x4 | 0x40  # sw_power_cap + hw_thermal_slowdown
+
+        @staticmethod
+        def nvmlDeviceGetPowerUsage(h):
+            return 950_000
+
+    smp._nvml, smp._h, smp.source = FakeNvml, object(), "nvml"
+    smp.rows = [smp._sample_nvml(), smp._sample_nvml()]
+    out = smp.summary()
+    assert out["sm_mhz"] == 1650.0 and out["sm_max_mhz"] == 1965.0 and out["samples"] == 2 and out["source"] == "nvml"
+    assert out["reasons"] == ["hw_thermal_slowdown", "sw_power_cap"]
+    smp.rows = [["0", "1700", "1965", "900.0", "0x0", "Not Active", "Not Active", "Not Active", "Not Active"]]  # an nvidia-smi row
+    assert smp.summary()["reasons"] == []
