@@ -213,6 +213,13 @@ def test_flat_adam_host_side():
     with pytest.raises(ValueError):
         opt.load_state_dict(torch.optim.Adam(m.parameters()).state_dict())
     opt.zero_grad(set_to_none=True)
+    # checkpoints move between the two flat layouts parameter by parameter
+    src = torch.arange(12.0)
+    dst = torch.zeros(16)
+    FlatAdam._remap(src, [0, 4, 8], dst, [8, 0, 12], [3, 4, 2])
+    assert dst.tolist() == [4.0, 5.0, 6.0, 7.0, 0, 0, 0, 0, 0.0, 1.0, 2.0, 0, 8.0, 9.0, 0, 0]
+    with pytest.raises(ValueError, match="different parameters"):
+        opt.load_state_dict({**sd, "exp_avg": torch.zeros(4), "exp_avg_sq": torch.zeros(4), "offsets": [0], "numels": [4], "step": 1.0})
 
 
 def test_chirality_centers_host():

@@ -436,6 +436,49 @@ def test_flat_adam_trains_like_torch_adam():
         assert float((d > 5e-5).float().mean()) < 0.05, float((d > 5e-5).float().mean())
 
 
+def test_flat_adam_resumes_from_a_checkpoint():
+    """utilities/model_utils.py:12-32 / tests/test_training_utils.py:23-67: a run resumed from (model, optimizer) state dicts -- the
+    optimizer state loaded BEFORE its first step, into whatever flat layout the new process ends up with -- continues like the
+    uninterrupted one."""
+    from timewarp_b200.optim import FlatAdam
+    g = _load("grads_full_ad22")
+    kw = dict(atom_types=g["atom_types"].cuda(), x_coords=g["x_coords"].cuda(), x_velocs=g["x_velocs"].cuda(), y_coords=g["y_coords"].cuda(),
+              y_velocs=g["y_velocs"].cuda(), adj_list=EMPTY_ADJ.cuda(), edge_batch_idx=EMPTY_EBI.cuda(), masked_elements=g["masked_elements"].cuda())
+
+    def steps(m, opt, n, clone_grads=False):
+        out = []
+        for _ in range(n):
+            opt.zero_grad(set_to_none=True)
+            loss = m(**kw)
+            loss.backward()
+            if clone_grads:  # forces the optimizer's own flat layout (gather path)
+                for p in m.parameters():
+                    if p.grad is not None:
+                        p.grad = p.grad.clone()
+            opt.step()
+            out.append(float(loss.detach()))
+        return out
+
+    m, _ = build_model(FULL_O, "bf16x3", 0)
+    m.train()
+    opt = FlatAdam(m, lr=1e-4)
+    first = steps(m, opt, 2)
+    model_sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    opt_sd = {k: (v.detach().clone() if torch.is_tensor(v) else v) for k, v in opt.state_dict().items()}
+    straight = steps(m, opt, 2)
+    for clone_grads in (False, True):
+        m2, _ = build_model(FULL_O, "bf16x3", 1)  # different weights until the checkpoint is loaded
+        m2.load_state_dict(model_sd)
+        m2.train()
+        opt2 = FlatAdam(m2, lr=1e-4)
+        opt2.load_state_dict(opt_sd)
+        resumed = steps(m2, opt2, 2, clone_grads)
+        assert float(opt2._hyper[5]) == 4.0
+        for a, b in zip(straight, resumed):
+            assert abs(a - b) < 2e-3 * max(1.0, abs(a)), (first, straight, resumed)
+    assert abs(straight[0] - first[1]) > 1e-4  # the run was still moving
+
+
 def test_training_trajectory_matches_oracle():
     """three Adam steps of NLL training (forward + hand-written backward + optimizer, weights
     re-packed every step) against the same three steps of the CPU oracle (fp64 autograd + torch Adam): the loss trajectory."""

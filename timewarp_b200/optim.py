@@ -45,6 +45,7 @@ class FlatAdam(torch.optim.Optimizer):
         self._offsets = None
         self._gbuf: Optional[Tensor] = None   # gather path: the optimizer's own flat gradient buffer ...
         self._gviews = None                   # ... and its per-parameter views
+        self._pending = None                  # a state dict loaded before the first step
         self.fast_path_steps = 0              # steps that read the model's flat gradient buffer directly
         self.gather_steps = 0
 
@@ -90,6 +91,9 @@ class FlatAdam(torch.optim.Optimizer):
         self._flat_p, self._offsets = flat_p, offs
         self._m, self._v = torch.zeros_like(flat_p), torch.zeros_like(flat_p)
         self._hyper = torch.zeros(8, dtype=torch.float32, device=dev)
+        if self._pending is not None:
+            self._apply_state(self._pending)
+            self._pending = None
         # the model caches raw parameter pointers and the packed bf16 weight images: both refer to the old storage
         if hasattr(self.model, "_table"):
             self.model._table = None
@@ -150,10 +154,17 @@ class FlatAdam(torch.optim.Optimizer):
         return loss
 
     # ------------------------------------------------------------------ checkpointing (utilities/model_utils.py:12-32)
+    @staticmethod
+    def _remap(src: Tensor, src_offsets, dst: Tensor, dst_offsets, numels) -> None:
+        """Copy per-parameter slices between two flat layouts (a checkpoint may come from a run with the other layout)."""
+        for so, do, n in zip(src_offsets, dst_offsets, numels):
+            dst[do:do + n].copy_(src[so:so + n])
+
     def state_dict(self):
         g = self.param_groups[0]
         return {"flat": True, "step": None if self._hyper is None else float(self._hyper[5]),
-                "exp_avg": self._m, "exp_avg_sq": self._v,
+                "exp_avg": self._m, "exp_avg_sq": self._v, "offsets": None if self._offsets is None else list(self._offsets),
+                "numels": [p.numel() for p in g["params"]],
                 "hyper": dict(lr=g["lr"], betas=g["betas"], eps=g["eps"], weight_decay=g["weight_decay"])}
 
     def load_state_dict(self, sd) -> None:
@@ -162,10 +173,19 @@ class FlatAdam(torch.optim.Optimizer):
         self.param_groups[0].update(sd["hyper"])
         if sd["exp_avg"] is None:
             return
+        if sd["numels"] != [p.numel() for p in self.param_groups[0]["params"]]:
+            raise ValueError("FlatAdam.load_state_dict: the checkpoint belongs to a model with different parameters")
         if self._flat_p is None:
-            raise _lib.TimewarpB200Error("FlatAdam.load_state_dict: run one training step first (the flat layout is fixed by the first backward)")
-        self._m.copy_(sd["exp_avg"]), self._v.copy_(sd["exp_avg_sq"])
-        self._hyper[5] = sd["step"]
+            self._pending = sd  # the flat layout is fixed by the first backward: the moments are restored inside the first step()
+            return
+        self._apply_state(sd)
+
+    def _apply_state(self, sd) -> None:
+        numels = sd["numels"]
+        self._m.zero_(), self._v.zero_()
+        self._remap(sd["exp_avg"].to(self._m.device), sd["offsets"], self._m, self._offsets, numels)
+        self._remap(sd["exp_avg_sq"].to(self._v.device), sd["offsets"], self._v, self._offsets, numels)
+        self._hyper[5] = float(sd["step"])
 
 
 def get_optimizer(model, config) -> torch.optim.Optimizer:
